@@ -1,0 +1,186 @@
+/*
+ * bellman.h — C ABI of libbellman.so: the backward Bellman value-iteration sweep on B200.
+ *
+ * This is the drop-in boundary for ONE path of abdolrezat/Optimal-Control-Dynamic-Programming:
+ * the per-stage operator
+ *
+ *     [F.Values, idx] = min( J_current + F(x_next...), [], ctrl_dim )
+ *
+ * and the stage loop around it, i.e. (reference file:line)
+ *     test/Dynamic_Solver.m:86-102 + 202-211        (run / J_state_M)
+ *     position-control/Solver_position.m:132-141    (simplified_run)
+ *     attitude-control/Solver_attitude.m:236-247    (simplified_run)
+ *     pos-att/Solver_pos_att.m:270-286              (calculate_one_channel_U_Opt)
+ * plus the batched forward rollout of test/Dynamic_Solver.m:108-145,191-194 (get_optimal_path).
+ *
+ * The reference has no FFI layer (it is 100 % MATLAB); these entry points are what a MEX gateway
+ * (optimal-control-dynamic-programming_b200/matlab/bellman_mex.cpp) or a ctypes binding
+ * (optimal-control-dynamic-programming_b200/_lib.py) binds.  See INTEGRATION.md.
+ *
+ * Conventions
+ *   - plain C types only; every host pointer is owned by the caller and is copied during the call,
+ *     never retained.  All device memory, streams and NCCL communicators live behind the handle.
+ *   - arrays are COLUMN-MAJOR (dimension 0 fastest), exactly as MATLAB stores them; no transposes.
+ *   - control indices are 0-based int32 (the MATLAB facade adds 1).
+ *   - every function returns 0 on success or a negative bellman_status; text via
+ *     bellman_last_error().  No exceptions or aborts cross the ABI.  There is NO CPU fallback:
+ *     without a usable CUDA device bellman_create() fails with BELLMAN_ERR_CUDA.
+ *   - a handle is not thread-safe; calls are synchronous on return unless stated otherwise.
+ *
+ * ---------------------------------------------------------------------------------------------
+ * The stage operator (normative arithmetic; oracle/bellman_oracle.c restates it on the CPU)
+ * ---------------------------------------------------------------------------------------------
+ * All arithmetic is IEEE-754 binary64, round-to-nearest-even, one rounding per written operation,
+ * no contraction except where fma() is written.  For every grid state i = (i_0 .. i_{D-1}):
+ *
+ *   base_d = Ta_d[i_{src_a[d]}]                         if Tb_d is absent
+ *          = Ta_d[i_{src_a[d]}] + Tb_d[i_{src_b[d]}]    otherwise
+ *   gs     = q_{o0}[i_{o0}] + q_{o1}[i_{o1}] + ...      (left-associated, o = q_order)
+ *   for c = 0 .. C-1 (in this order):
+ *       xq_d = base_d + Tc_d[c]     (or base_d when Tc_d is absent)
+ *       (cell_d, t_d) = locate_d(xq_d)
+ *       v    = multilinear interpolation of J_{k+1} at cells/weights, dimension 0 reduced first,
+ *              each 1-D step  lerp(a,b,t) = fma(t, b - a, a);  queries outside the grid use the
+ *              edge cell with t<0 or t>1 (linear extrapolation, griddedInterpolant's default)
+ *       tot  = (gs + r[c]) + v
+ *       if tot < best (strictly): best = tot, arg = c        -> first index wins ties (MATLAB min)
+ *   J_k[i] = best ; idx_k[i] = arg
+ *
+ *   locate_d(x):  t = (x - s[cell]) * rinv[cell],  rinv[i] = 1/(s[i+1]-s[i]) (IEEE division, host)
+ *     BELLMAN_LOCATE_UNIFORM : cell = clamp( (int)floor( fma(x, inv_h, off) ), 0, n-2 )
+ *                              inv_h = (n-1)/(s[n-1]-s[0]),  off = -s[0]*inv_h   (host, rounded once each)
+ *     BELLMAN_LOCATE_SEARCH  : cell = clamp( #{ i : s[i] <= x } - 1, 0, n-2 )    (exact bin rule)
+ *   The library picks UNIFORM for a dimension when the grid vector is uniform to 1e-9 of a cell,
+ *   else SEARCH; bellman_query_locate() reports the choice so the oracle uses the same one.
+ *   (Near a grid node the two rules may pick adjacent cells; interpolation is continuous there,
+ *   the results differ by O(1 ulp).)
+ */
+#ifndef BELLMAN_H
+#define BELLMAN_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BELLMAN_ABI_VERSION 1
+#define BELLMAN_MAX_DIM 4
+
+typedef enum bellman_status {
+    BELLMAN_OK = 0,
+    BELLMAN_ERR_BAD_ARG = -1,
+    BELLMAN_ERR_CUDA = -2,
+    BELLMAN_ERR_NCCL = -3,
+    BELLMAN_ERR_OOM = -4,
+    BELLMAN_ERR_NOT_RUN = -5,   /* requested stage has not been computed / not stored */
+    BELLMAN_ERR_STATE = -6      /* call sequence error (e.g. run past stage 1)          */
+} bellman_status;
+
+enum { BELLMAN_LOCATE_UNIFORM = 0, BELLMAN_LOCATE_SEARCH = 1 };
+enum { BELLMAN_KERNEL_AUTO = 0, BELLMAN_KERNEL_DIRECT = 1, BELLMAN_KERNEL_WINDOW = 2,
+       BELLMAN_KERNEL_SPLITC = 3 };
+
+typedef struct bellman_handle bellman_handle;
+
+/*
+ * Problem descriptor: P independent problems ("axes" / "channels") that share grid SHAPE and
+ * control count but have their own tables.  Every table pointer addresses P consecutive rows.
+ *
+ * Replaces the S x C arrays the reference precomputes and streams every stage:
+ *   X_next_M1/M2, J_current_state      test/Dynamic_Solver.m:81-82,184-200
+ *   x*_next, v*_next, J_current_*      position-control/Solver_position.m:113-128
+ *   w*_next, t*_next, J_current_*      attitude-control/Solver_attitude.m:220-233
+ *   x_next..w_next (repmat), J_current pos-att/Solver_pos_att.m:257-263,299-328,784-802
+ * All of them are sums of 1-D tables; the facade evaluates the 1-D tables with the reference's
+ * own operation order and the kernel forms the sums on the fly.
+ */
+typedef struct bellman_desc {
+    int32_t struct_size;               /* = sizeof(bellman_desc)                               */
+    int32_t D;                         /* state dimensions, 2..BELLMAN_MAX_DIM                 */
+    int32_t n[BELLMAN_MAX_DIM];        /* grid points per dimension (>= 2)                     */
+    int32_t C;                         /* number of discrete controls                          */
+    int32_t P;                         /* independent problems sharing the shape (>= 1)        */
+    int32_t N;                         /* horizon: stages are numbered N (terminal) .. 1       */
+    const double *grid[BELLMAN_MAX_DIM];  /* [P][n[d]] strictly increasing grid vectors        */
+    int32_t src_a[BELLMAN_MAX_DIM];    /* state dim that indexes Ta[d]                         */
+    int32_t src_b[BELLMAN_MAX_DIM];    /* state dim that indexes Tb[d], -1 if Tb[d] absent     */
+    const double *Ta[BELLMAN_MAX_DIM]; /* [P][n[src_a[d]]]                                     */
+    const double *Tb[BELLMAN_MAX_DIM]; /* [P][n[src_b[d]]] or NULL                             */
+    const double *Tc[BELLMAN_MAX_DIM]; /* [P][C] or NULL (dimension does not depend on control)*/
+    int32_t q_order[BELLMAN_MAX_DIM];  /* order in which the state-cost terms are summed       */
+    const double *q[BELLMAN_MAX_DIM];  /* [P][n[d]] state-cost term of dimension d             */
+    const double *r;                   /* [P][C] control-cost term                             */
+    int32_t store_J_all;               /* keep J_k of every stage on the device                */
+    int32_t store_idx_all;             /* keep idx_k of every stage on the device              */
+    int32_t device;                    /* CUDA ordinal, -1 = current device                    */
+    /* slab partition of ONE dimension across ranks (one process per GPU); part_dim = -1: none */
+    int32_t part_dim;
+    int32_t rank;
+    int32_t nranks;
+} bellman_desc;
+
+typedef struct bellman_run_opts {
+    int32_t struct_size;     /* = sizeof(bellman_run_opts)                                      */
+    int32_t kernel;          /* BELLMAN_KERNEL_*                                                */
+    int32_t check_period;    /* >0: when (stage %% period)==0 form sum(J), sum(idx+1) and stop  */
+    double  check_tol;       /*     once |sum(J) - previous sum(J)| < tol (Solver_pos_att.m:273-285) */
+    int32_t use_graph;       /* 1: replay stages through a CUDA graph (small grids)             */
+    int32_t sync_each_stage; /* 1: host-sync after every stage (per-stage timing prints)        */
+} bellman_run_opts;
+
+/* slab plan of one rank, computed on the host from the tables alone (no GPU needed) */
+typedef struct bellman_slab {
+    int32_t own_lo, own_hi;  /* owned index range [lo,hi) along part_dim                        */
+    int32_t ext_lo, ext_hi;  /* range of J_{k+1} this rank reads (owned + halo), from an exact  */
+                             /* reach analysis of the next-state tables                         */
+} bellman_slab;
+
+int  bellman_version(void);
+const char *bellman_last_error(const bellman_handle *h);   /* h may be NULL: create() errors   */
+
+/* host-only helpers (usable without a GPU) */
+int  bellman_query_locate(const bellman_desc *d, int32_t mode_out[/*P*D*/]);
+int  bellman_plan_slabs(const bellman_desc *d, int32_t part_dim, int32_t nranks,
+                        bellman_slab slabs_out[/*nranks*/]);
+
+/* lifecycle */
+int  bellman_create(const bellman_desc *d, bellman_handle **out);
+void bellman_destroy(bellman_handle *h);
+
+/* multi-GPU bootstrap: rank 0 calls get_unique_id, the host distributes the 128 bytes
+   (torch.distributed / MPI / a file), every rank calls comm_init */
+int  bellman_get_unique_id(void *id128_out);
+int  bellman_comm_init(bellman_handle *h, const void *id128);
+
+/* sweep */
+int  bellman_set_J(bellman_handle *h, const double *J_host /*[P][S] global, NULL = zeros*/);
+int  bellman_stage(bellman_handle *h);                      /* one backward stage, default opts */
+int  bellman_run(bellman_handle *h, int32_t n_stages, const bellman_run_opts *opts);
+int  bellman_current_stage(const bellman_handle *h);        /* stage number of the current J    */
+int  bellman_get_J(bellman_handle *h, int32_t stage, double *J_host_out /*[P][S_own]*/);
+int  bellman_get_idx(bellman_handle *h, int32_t stage, int32_t *idx_host_out /*[P][S_own]*/);
+int  bellman_get_check_log(const bellman_handle *h, double *out /*[max][3]: stage,sumJ,sumIdx*/,
+                           int32_t max_entries);
+int  bellman_owned_range(const bellman_handle *h, bellman_slab *out);
+
+/* timing of the last bellman_run, measured with CUDA events on the library's own stream:
+   total ms, number of stage-kernel launches, and ms spent in halo exchange */
+int  bellman_last_run_stats(const bellman_handle *h, double *ms_total, int64_t *kernel_launches,
+                            double *ms_exchange);
+/* name of the stage kernel variant the last run used ("direct", "window", "splitc") */
+const char *bellman_last_kernel(const bellman_handle *h);
+
+/* batched forward rollout of test/Dynamic_Solver.m:108-145 (D = 2, P = 1, store_idx_all):
+ *   U(k) = interp2(u_values[idx_k], X(:,k));  X(:,k+1) = A*X(:,k) + B*U(k),  k = 1..N-1
+ * mode 0: time-varying policy u_star(:,:,k);  mode 1 ('ssu'): fixed stage ssu_stage.
+ * A is 2x2 column-major, B 2x1, u_values[C]; x0 is [2][batch] column-major;
+ * X_out [2][N][batch] (batch slowest), U_out [N][batch]. */
+int  bellman_rollout(bellman_handle *h, const double *A, const double *B, const double *u_values,
+                     const double *x0, int32_t batch, int32_t mode, int32_t ssu_stage,
+                     double *X_out, double *U_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BELLMAN_H */

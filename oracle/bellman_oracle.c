@@ -1,0 +1,273 @@
+/*
+ * bellman_oracle.c — CPU restatement of the reference's backward Bellman stage.  TEST INFRASTRUCTURE.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may
+ * build, load or call this file.  The product (libbellman.so and the package above it) never does.
+ *
+ * What it restates (reference file:line, all MATLAB):
+ *   stage operator  [F.Values,idx] = min(J_current + F(x_next..), [], ctrl_dim)
+ *       test/Dynamic_Solver.m:207-210      position-control/Solver_position.m:135-137
+ *       attitude-control/Solver_attitude.m:239-241      pos-att/Solver_pos_att.m:272
+ *   griddedInterpolant(...,'linear') evaluation incl. linear extrapolation from the edge cell
+ *       (MATLAB runtime, closed source, un-vendored; version pinned only by test/obj_1.mat's header:
+ *        PCWIN64, 24 Mar 2017 => R2016b/R2017a).  Published algorithm: N-linear interpolation on
+ *        the cell s[i] <= x < s[i+1], ExtrapolationMethod defaults to Method.
+ *   min(X,[],dim): first (lowest) index wins ties.
+ *   stage loop      Dynamic_Solver.m:86-102, Solver_position.m:132-141, Solver_attitude.m:236-247,
+ *                   Solver_pos_att.m:270-286 (incl. the every-50-stages sum check :273-285)
+ *   rollout         Dynamic_Solver.m:108-145,191-194
+ *
+ * The S x C arrays of the reference are sums of 1-D tables; the tables are evaluated by
+ * oracle/matlab_literal.py (array-at-a-time, literally as the .m files do) or by the product's
+ * facade, and passed here through the same descriptor the library takes (include/bellman.h),
+ * whose header comment is the normative operation-by-operation arithmetic.
+ *
+ * Parity pin: tests/test_oracle_golden.py checks this file against the reference's only golden
+ * vector, test/obj_1.mat (35x35 grid, 100 controls, 129 stages, fp64): u_star exact on all
+ * 158 025 entries, J within 1e-12 relative.  Position / attitude / pos-att have no stored
+ * outputs in the reference => parity unpinned against MATLAB for those tables (same operator).
+ *
+ * Build: make -C oracle   (gcc -O2 -fopenmp -ffp-contract=off; fma() calls are explicit)
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include "../include/bellman.h"
+
+#define MAXD BELLMAN_MAX_DIM
+
+/* --- locate-mode rule (same rule as the library; restated, not shared) -------------------- */
+static int grid_is_uniform(const double *s, int n)
+{
+    const double h = (s[n - 1] - s[0]) / (double)(n - 1);
+    for (int i = 0; i < n; ++i) {
+        const double dev = fabs(s[i] - (s[0] + (double)i * h));
+        if (!(dev <= 1e-9 * h)) return 0;
+    }
+    return 1;
+}
+
+int oracle_locate_modes(const bellman_desc *d, int32_t *modes /*[P][D]*/)
+{
+    for (int p = 0; p < d->P; ++p)
+        for (int k = 0; k < d->D; ++k)
+            modes[p * d->D + k] = grid_is_uniform(d->grid[k] + (size_t)p * d->n[k], d->n[k])
+                                      ? BELLMAN_LOCATE_UNIFORM : BELLMAN_LOCATE_SEARCH;
+    return 0;
+}
+
+typedef struct {
+    const double *s;
+    double *rinv;
+    int n, mode;
+    double inv_h, off;
+} dimtab;
+
+static inline int locate(const dimtab *g, double x, double *t)
+{
+    int cell;
+    if (g->mode == BELLMAN_LOCATE_UNIFORM) {
+        const double gg = fma(x, g->inv_h, g->off);
+        if (gg < 0.0) cell = 0;                       /* floor() then clamp, without int overflow */
+        else if (gg >= (double)(g->n - 1)) cell = g->n - 2;
+        else cell = (int)gg;
+    } else {
+        int lo = 0, hi = g->n;                        /* count of s[i] <= x */
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (g->s[mid] <= x) lo = mid + 1; else hi = mid;
+        }
+        cell = lo - 1;
+        if (cell < 0) cell = 0;
+        if (cell > g->n - 2) cell = g->n - 2;
+    }
+    *t = (x - g->s[cell]) * g->rinv[cell];
+    return cell;
+}
+
+static void dimtab_init(dimtab *g, const double *s, int n, int mode)
+{
+    g->s = s; g->n = n; g->mode = mode;
+    g->rinv = (double *)malloc(sizeof(double) * (size_t)(n - 1));
+    for (int i = 0; i < n - 1; ++i) g->rinv[i] = 1.0 / (s[i + 1] - s[i]);
+    g->inv_h = (double)(n - 1) / (s[n - 1] - s[0]);
+    g->off = -(s[0] * g->inv_h);
+}
+
+/*
+ * One backward stage over all P problems.  J_next / J_out are [P][S] column-major (dim 0 fastest),
+ * idx_out is [P][S] 0-based.  own_lo/own_hi restrict the states computed along part_dim (used by
+ * the multi-rank tests); pass part_dim = -1 for the whole grid.  Outputs are always indexed
+ * globally.
+ */
+int oracle_stage(const bellman_desc *d, const int32_t *modes, const double *J_next, double *J_out,
+                 int32_t *idx_out, int part_dim, int own_lo, int own_hi, int nthreads)
+{
+    const int D = d->D, C = d->C;
+    if (D < 1 || D > MAXD) return -1;
+    int64_t stride[MAXD], S = 1;
+    for (int k = 0; k < D; ++k) { stride[k] = S; S *= d->n[k]; }
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+    for (int p = 0; p < d->P; ++p) {
+        dimtab g[MAXD];
+        const double *Ta[MAXD], *Tb[MAXD], *Tc[MAXD], *q[MAXD];
+        for (int k = 0; k < D; ++k) {
+            dimtab_init(&g[k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * D + k]);
+            Ta[k] = d->Ta[k] + (size_t)p * d->n[d->src_a[k]];
+            Tb[k] = (d->Tb[k] && d->src_b[k] >= 0) ? d->Tb[k] + (size_t)p * d->n[d->src_b[k]] : NULL;
+            Tc[k] = d->Tc[k] ? d->Tc[k] + (size_t)p * C : NULL;
+            q[k] = d->q[k] + (size_t)p * d->n[k];
+        }
+        const double *r = d->r + (size_t)p * C;
+        const double *Jn = J_next + (size_t)p * S;
+        double *Jo = J_out + (size_t)p * S;
+        int32_t *Io = idx_out + (size_t)p * S;
+
+#pragma omp parallel for schedule(static)
+        for (int64_t s = 0; s < S; ++s) {
+            int i[MAXD];
+            int64_t rem = s;
+            for (int k = 0; k < D; ++k) { i[k] = (int)(rem % d->n[k]); rem /= d->n[k]; }
+            if (part_dim >= 0 && (i[part_dim] < own_lo || i[part_dim] >= own_hi)) continue;
+
+            double base[MAXD];
+            for (int k = 0; k < D; ++k) {
+                base[k] = Ta[k][i[d->src_a[k]]];
+                if (Tb[k]) base[k] = base[k] + Tb[k][i[d->src_b[k]]];
+            }
+            double gs = q[d->q_order[0]][i[d->q_order[0]]];
+            for (int m = 1; m < D; ++m) gs = gs + q[d->q_order[m]][i[d->q_order[m]]];
+
+            double best = INFINITY;
+            int arg = 0;
+            for (int c = 0; c < C; ++c) {
+                int cell[MAXD];
+                double t[MAXD];
+                int64_t o = 0;
+                for (int k = 0; k < D; ++k) {
+                    const double xq = Tc[k] ? base[k] + Tc[k][c] : base[k];
+                    cell[k] = locate(&g[k], xq, &t[k]);
+                    o += cell[k] * stride[k];
+                }
+                double v[1 << MAXD];
+                for (int m = 0; m < (1 << D); ++m) {
+                    int64_t oo = o;
+                    for (int k = 0; k < D; ++k) if (m & (1 << k)) oo += stride[k];
+                    v[m] = Jn[oo];
+                }
+                for (int k = 0; k < D; ++k)                       /* dimension 0 reduced first */
+                    for (int m = 0; m < (1 << (D - 1 - k)); ++m)
+                        v[m] = fma(t[k], v[2 * m + 1] - v[2 * m], v[2 * m]);
+                const double tot = (gs + r[c]) + v[0];
+                if (tot < best) { best = tot; arg = c; }
+            }
+            Jo[s] = best;
+            Io[s] = arg;
+        }
+        for (int k = 0; k < D; ++k) free(g[k].rinv);
+    }
+    return 0;
+}
+
+/*
+ * Full sweep from the terminal cost J_N (NULL = zeros) down n_stages stages.
+ * J_all / idx_all (may be NULL) receive every stage: layout [N][P][S], slot (stage-1); slot N-1 of
+ * J_all holds the terminal cost, slot N-1 of idx_all is left untouched.  J_last/idx_last (may be
+ * NULL) receive the final stage only.  check_period/check_tol restate Solver_pos_att.m:273-285
+ * (with idsum50_prev defined as 0 — the reference uses it undefined); the return
+ * value is the stage number of the last computed J.
+ */
+int oracle_sweep(const bellman_desc *d, const int32_t *modes, const double *J_N, int n_stages,
+                 double *J_all, int32_t *idx_all, double *J_last, int32_t *idx_last,
+                 int check_period, double check_tol, int nthreads)
+{
+    int64_t S = 1;
+    for (int k = 0; k < d->D; ++k) S *= d->n[k];
+    const size_t PS = (size_t)d->P * (size_t)S;
+    double *a = (double *)malloc(sizeof(double) * PS), *b = (double *)malloc(sizeof(double) * PS);
+    int32_t *ib = (int32_t *)malloc(sizeof(int32_t) * PS);
+    if (J_N) memcpy(a, J_N, sizeof(double) * PS); else memset(a, 0, sizeof(double) * PS);
+    int stage = d->N;
+    if (J_all) memcpy(J_all + (size_t)(stage - 1) * PS, a, sizeof(double) * PS);
+    double fsum_prev = 0.0;
+    for (int it = 0; it < n_stages && stage > 1; ++it) {
+        oracle_stage(d, modes, a, b, ib, -1, 0, 0, nthreads);
+        --stage;
+        double *tmp = a; a = b; b = tmp;
+        if (J_all) memcpy(J_all + (size_t)(stage - 1) * PS, a, sizeof(double) * PS);
+        if (idx_all) memcpy(idx_all + (size_t)(stage - 1) * PS, ib, sizeof(int32_t) * PS);
+        if (check_period > 0 && (stage % check_period) == 0) {
+            double fsum = 0.0;
+            for (size_t k = 0; k < PS; ++k) fsum += a[k];
+            const double e = fsum - fsum_prev;
+            fsum_prev = fsum;
+            if (fabs(e) < check_tol) break;
+        }
+    }
+    if (J_last) memcpy(J_last, a, sizeof(double) * PS);
+    if (idx_last) memcpy(idx_last, ib, sizeof(int32_t) * PS);
+    free(a); free(b); free(ib);
+    return stage;
+}
+
+/*
+ * Rollout of Dynamic_Solver.get_optimal_path (test/Dynamic_Solver.m:108-145,191-194), fp64:
+ *   U(k) = Fu(X(1,k),X(2,k)) with Fu = griddedInterpolant(X1_mesh,X2_mesh,u_star(:,:,k),'linear')
+ *   X(:,k+1) = A*[X1;X2] + B*U(k)
+ * idx_all is [N][S] (slot stage-1), u_values[C].  The 2x2 product is evaluated as
+ * (A(r,1)*x1 + A(r,2)*x2) + B(r)*u with separate roundings (MATLAB's own mtimes rounding for a
+ * 2x2 is not documented; the rollout is compared with a tolerance).
+ */
+int oracle_rollout(const bellman_desc *d, const int32_t *modes, const int32_t *idx_all,
+                   const double *A, const double *B, const double *u_values, const double *x0,
+                   int batch, int mode, int ssu_stage, double *X_out, double *U_out)
+{
+    if (d->D != 2 || d->P != 1) return -1;
+    const int N = d->N, n0 = d->n[0], n1 = d->n[1];
+    const int64_t S = (int64_t)n0 * n1;
+    dimtab g[2];
+    dimtab_init(&g[0], d->grid[0], n0, modes[0]);
+    dimtab_init(&g[1], d->grid[1], n1, modes[1]);
+    for (int b = 0; b < batch; ++b) {
+        double x1 = x0[2 * b], x2 = x0[2 * b + 1];
+        double *X = X_out + (size_t)b * 2 * N, *U = U_out + (size_t)b * N;
+        X[0] = x1; X[1] = x2;
+        for (int k = 1; k <= N - 1; ++k) {
+            const int st = (mode == 1) ? ssu_stage : k;
+            const int32_t *id = idx_all + (size_t)(st - 1) * S;
+            double t0, t1;
+            const int c0 = locate(&g[0], x1, &t0), c1 = locate(&g[1], x2, &t1);
+            const double v00 = u_values[id[c0 + (int64_t)c1 * n0]];
+            const double v10 = u_values[id[c0 + 1 + (int64_t)c1 * n0]];
+            const double v01 = u_values[id[c0 + (int64_t)(c1 + 1) * n0]];
+            const double v11 = u_values[id[c0 + 1 + (int64_t)(c1 + 1) * n0]];
+            const double a = fma(t0, v10 - v00, v00), bb = fma(t0, v11 - v01, v01);
+            const double u = fma(t1, bb - a, a);
+            U[k - 1] = u;
+            const double nx1 = (A[0] * x1 + A[2] * x2) + B[0] * u;
+            const double nx2 = (A[1] * x1 + A[3] * x2) + B[1] * u;
+            x1 = nx1; x2 = nx2;
+            X[2 * k] = x1; X[2 * k + 1] = x2;
+        }
+        U[N - 1] = 0.0;
+    }
+    free(g[0].rinv); free(g[1].rinv);
+    return 0;
+}
+
+int oracle_num_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}

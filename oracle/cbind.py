@@ -1,0 +1,152 @@
+"""ctypes binding of oracle/libbellman_oracle.so (the C restatement).  TEST INFRASTRUCTURE.
+
+Takes any object with the attributes of the product's ``tables.Desc`` (n, C, P, N, grid, src_a,
+src_b, Ta, Tb, Tc, q_order, q, r) — duck-typed so this package does not import the product.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+MAXD = 4
+_dp = C.POINTER(C.c_double)
+
+
+class CDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("D", C.c_int32), ("n", C.c_int32 * MAXD), ("C", C.c_int32),
+        ("P", C.c_int32), ("N", C.c_int32), ("grid", _dp * MAXD),
+        ("src_a", C.c_int32 * MAXD), ("src_b", C.c_int32 * MAXD),
+        ("Ta", _dp * MAXD), ("Tb", _dp * MAXD), ("Tc", _dp * MAXD),
+        ("q_order", C.c_int32 * MAXD), ("q", _dp * MAXD), ("r", _dp),
+        ("store_J_all", C.c_int32), ("store_idx_all", C.c_int32), ("device", C.c_int32),
+        ("part_dim", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+    ]
+
+
+def build(force=False):
+    so = os.path.join(HERE, "libbellman_oracle.so")
+    src = os.path.join(HERE, "bellman_oracle.c")
+    if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
+        subprocess.run(["make", "-C", HERE], check=True, capture_output=True)
+    return so
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        so = os.path.join(HERE, "libbellman_oracle.so")
+        if not os.path.exists(so):
+            build()
+        _lib = C.CDLL(so)
+    return _lib
+
+
+def _arr(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def to_cdesc(d):
+    """Returns (CDesc, keepalive list)."""
+    cd = CDesc()
+    keep = []
+    D = len(d.n)
+    cd.struct_size = C.sizeof(CDesc)
+    cd.D, cd.C, cd.P, cd.N = D, int(d.C), int(d.P), int(d.N)
+    for k in range(D):
+        cd.n[k] = int(d.n[k])
+        cd.src_a[k] = int(d.src_a[k])
+        cd.src_b[k] = int(d.src_b[k])
+        cd.q_order[k] = int(d.q_order[k])
+        for name in ("grid", "Ta", "Tb", "Tc", "q"):
+            a = getattr(d, name)[k]
+            if a is None:
+                getattr(cd, name)[k] = _dp()
+            else:
+                a = _arr(a)
+                keep.append(a)
+                getattr(cd, name)[k] = a.ctypes.data_as(_dp)
+    r = _arr(d.r)
+    keep.append(r)
+    cd.r = r.ctypes.data_as(_dp)
+    cd.device, cd.part_dim, cd.rank, cd.nranks = -1, -1, 0, 1
+    return cd, keep
+
+
+def locate_modes(d):
+    cd, keep = to_cdesc(d)
+    modes = np.zeros(d.P * len(d.n), dtype=np.int32)
+    lib().oracle_locate_modes(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)))
+    return modes
+
+
+def stage(d, J_next, modes=None, part_dim=-1, own_lo=0, own_hi=0, nthreads=0):
+    """One backward stage.  J_next: [P, S] (S column-major flattened).  Returns (J, idx0)."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    S = int(np.prod(d.n))
+    Jn = _arr(J_next).reshape(d.P, S)
+    Jo = np.zeros_like(Jn)
+    Io = np.zeros((d.P, S), dtype=np.int32)
+    rc = lib().oracle_stage(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)),
+                            Jn.ctypes.data_as(_dp), Jo.ctypes.data_as(_dp),
+                            Io.ctypes.data_as(C.POINTER(C.c_int32)),
+                            C.c_int(part_dim), C.c_int(own_lo), C.c_int(own_hi), C.c_int(nthreads))
+    assert rc == 0
+    return Jo, Io
+
+
+def sweep(d, n_stages=None, J_N=None, keep_all=False, check_period=0, check_tol=0.0, nthreads=0,
+          modes=None):
+    """Backward sweep from stage N.  Returns dict(J_last, idx_last, stage[, J_all, idx_all])."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    S = int(np.prod(d.n))
+    n_stages = d.N - 1 if n_stages is None else int(n_stages)
+    J_last = np.zeros((d.P, S))
+    idx_last = np.zeros((d.P, S), dtype=np.int32)
+    J_all = np.zeros((d.N, d.P, S)) if keep_all else None
+    idx_all = np.zeros((d.N, d.P, S), dtype=np.int32) if keep_all else None
+    JN = None if J_N is None else _arr(J_N).reshape(d.P, S)
+    fn = lib().oracle_sweep
+    fn.restype = C.c_int
+    stage_no = fn(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)),
+                  JN.ctypes.data_as(_dp) if JN is not None else _dp(), C.c_int(n_stages),
+                  J_all.ctypes.data_as(_dp) if keep_all else _dp(),
+                  idx_all.ctypes.data_as(C.POINTER(C.c_int32)) if keep_all else C.POINTER(C.c_int32)(),
+                  J_last.ctypes.data_as(_dp), idx_last.ctypes.data_as(C.POINTER(C.c_int32)),
+                  C.c_int(check_period), C.c_double(check_tol), C.c_int(nthreads))
+    out = {"J_last": J_last, "idx_last": idx_last, "stage": stage_no}
+    if keep_all:
+        out["J_all"], out["idx_all"] = J_all, idx_all
+    return out
+
+
+def rollout(d, idx_all, A, B, u_values, x0, mode=0, ssu_stage=1, modes=None):
+    """idx_all [N, S]; x0 [batch, 2].  Returns X [batch, N, 2], U [batch, N]."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    x0 = _arr(x0).reshape(-1, 2)
+    batch = x0.shape[0]
+    X = np.zeros((batch, d.N, 2))
+    U = np.zeros((batch, d.N))
+    ia = np.ascontiguousarray(idx_all, dtype=np.int32)
+    A = _arr(np.asarray(A).ravel(order="F"))
+    B = _arr(np.asarray(B).ravel())
+    uv = _arr(u_values)
+    rc = lib().oracle_rollout(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)),
+                              ia.ctypes.data_as(C.POINTER(C.c_int32)), A.ctypes.data_as(_dp),
+                              B.ctypes.data_as(_dp), uv.ctypes.data_as(_dp), x0.ctypes.data_as(_dp),
+                              C.c_int(batch), C.c_int(mode), C.c_int(ssu_stage),
+                              X.ctypes.data_as(_dp), U.ctypes.data_as(_dp))
+    assert rc == 0
+    return X, U
+
+
+def num_threads():
+    return int(lib().oracle_num_threads())
