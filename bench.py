@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""bench.py — Bellman state·control updates/s of the backward sweep on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload NAME] [--impl reference]
+    torchrun ... bench.py --gpus N ...          (one rank per GPU; the driver launches this)
+
+A "step" is ONE backward stage of the named workload over the whole state grid (all ranks
+together): the reference's  [F.Values, idx] = min(J_current + F(x_next..), [], ctrl_dim).
+Headline workload (BASELINE.json configs[3]): Kirk two-state example scaled to an
+8192 x 8192 state grid x 512 controls, the grid slab-partitioned over the GPUs (strong scaling).
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "bellman_state_control_updates_per_s"
+UNIT = "updates/s"
+
+WORKLOADS = {
+    # name: (kind, params)
+    "kirk_scaled_8192x8192x512": dict(kind="kirk", dx=8192, du=512, N=200),
+    "kirk_default_100x100x1000": dict(kind="kirk", dx=100, du=1000, N=200),
+    "position_3x201x201x3": dict(kind="position"),
+    "attitude_x4_3x4000x1200x3": dict(kind="attitude", n_w=4000, n_t=1200),
+    "attitude_x16_3x16000x4800x3": dict(kind="attitude", n_w=16000, n_t=4800),
+    "pos_att_ref_30x30x20x15x9": dict(kind="pos_att", scale=1),
+    "pos_att_x4_120x120x80x60x9": dict(kind="pos_att", scale=4),
+}
+DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
+
+
+def make_desc(bb, name):
+    w = WORKLOADS[name]
+    t = bb.tables
+    if w["kind"] == "kirk":
+        o = bb.Dynamic_Solver()
+        return t.kirk_desc(o.A, o.B, o.Q, o.R, w["N"], o.x_min, o.x_max, w["dx"], o.u_min, o.u_max, w["du"],
+                           store_J_all=False, store_idx_all=False)
+    if w["kind"] == "position":
+        return t.stack_problems(bb.Solver_position()._axis_descs())
+    if w["kind"] == "attitude":
+        s = bb.Solver_attitude()
+        s.n_mesh_w, s.n_mesh_t = w["n_w"], w["n_t"]
+        return t.stack_problems(s._axis_descs())
+    if w["kind"] == "pos_att":
+        s = bb.Solver_pos_att()
+        k = w["scale"]
+        s.n_mesh_x, s.n_mesh_v, s.n_mesh_t, s.n_mesh_w = 30 * k, 30 * k, 20 * k, 15 * k
+        return t.stack_problems([s.channel_desc(c) for c in range(3)])
+    raise ValueError(name)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device = device
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2])); power.append(float(r[3]))
+                for nm, v in zip(names, r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        busy = [s for s, p in zip(sm, power) if p > 250.0] or sm
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": max(mx) if mx else None,
+                "power_w_max": max(power) if power else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peak_gbs():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU arm: the oracle (kind "port": MATLAB/Octave do not exist on the box) on host cores
+# ----------------------------------------------------------------------------------------------
+def cpu_sample_rate(d, seconds_target, threads=0):
+    """Times oracle_stage_points on a random sample of states of problem 0 sized for roughly
+    `seconds_target` of CPU work.  Returns (updates/s, cores, sample description, seconds)."""
+    from oracle import cbind
+    cbind.build()
+    if threads:
+        os.environ["OMP_NUM_THREADS"] = str(threads)
+    cores = cbind.num_threads()
+    rng = np.random.default_rng(0)
+    S = d.S
+    s0 = d.grid[0][0]
+    # a smooth synthetic J_{k+1} (the work per update does not depend on the values)
+    Jn = np.zeros(S) if S > 2 ** 28 else rng.normal(size=S)
+    n = min(S, 20000)
+    pts = rng.integers(0, S, size=n)
+    t0 = time.perf_counter(); cbind.stage_points(d, Jn, pts); dt = time.perf_counter() - t0
+    rate = n * d.C / max(dt, 1e-9)
+    n = int(min(max(rate * seconds_target / d.C, n), 5e7))
+    pts = rng.integers(0, S, size=n)
+    t0 = time.perf_counter(); cbind.stage_points(d, Jn, pts); dt = time.perf_counter() - t0
+    return n * d.C / dt, cores, "%d random states x %d controls of one stage (%.1f s)" % (n, d.C, dt), dt
+
+
+def run_reference_arm(args):
+    """--impl reference: the CPU implementation of the path on the box's host cores.  MATLAB is not
+    installable (no toolchain, no network), so this is the oracle port, all host threads."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import bellman_b200 as bb
+    d = make_desc(bb, args.workload)
+    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    for _ in range(args.warmup):
+        cpu_sample_rate(d, per_step)
+    rates, dts = [], []
+    for _ in range(args.steps):
+        r, cores, sample, dt = cpu_sample_rate(d, per_step)
+        rates.append(r); dts.append(dt)
+    value = float(np.mean(rates))
+    S_all = d.S * d.P
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * S_all * d.C / value, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": d.n, "controls": d.C, "problems": d.P,
+                       "note": "ms_per_step extrapolated from the sample to one full stage"},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "window", "splitc"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+
+    if args.impl == "reference":
+        run_reference_arm(args)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import bellman_b200 as bb
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
+        args.gpus = world
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    d = make_desc(bb, args.workload)
+    part_dim = d.D - 1 if world > 1 else -1
+    sw = bb.Sweep(d, device=local, part_dim=part_dim, rank=rank, nranks=world)
+    if world > 1:
+        ids = [bb.get_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ids, src=0)
+        sw.comm_init(ids[0])
+    kernel = {"auto": bb.KERNEL_AUTO, "direct": bb.KERNEL_DIRECT, "window": bb.KERNEL_WINDOW,
+              "splitc": bb.KERNEL_SPLITC}[args.kernel]
+    use_graph = d.S * d.P < 4_000_000 and world == 1
+
+    S_all = d.S * d.P
+    upd_per_step = S_all * d.C
+    K, W = args.steps, args.warmup
+    if W + K + 2 > d.N - 1:
+        raise SystemExit("steps+warmup exceed the horizon of this workload")
+
+    # ---- device-resident throughput ("value") ------------------------------------------------
+    sw.run(W, kernel=kernel, use_graph=use_graph)                      # untimed warm-up stages
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    sw.run(K, kernel=kernel, use_graph=use_graph)                      # EXACTLY K stages, CUDA-event timed
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    st = sw.stats()
+    ms_dev = max_over_ranks(st["ms"])                                  # device time, max over ranks
+    ms_x = max_over_ranks(st["ms_exchange"])
+    clocks = sampler.stop() if rank == 0 else None
+    launches = st["launches"]
+    value = upd_per_step * K / (ms_dev * 1e-3)
+
+    # ---- end-to-end through the C ABI with HOST buffers ("e2e") ---------------------------------
+    # the seam-level drop-in: each step the caller hands J_{k+1} in host memory (as MATLAB's
+    # F.Values would be), and reads J_k and the argmin back.
+    e2e = None
+    if not args.no_e2e:
+        Ke = max(2, min(K, 5))
+        own = sw.S_own * d.P
+        pin_in = torch.empty(S_all, dtype=torch.float64).pin_memory().numpy()
+        pin_J = torch.empty(own, dtype=torch.float64).pin_memory().numpy().reshape(d.P, -1)
+        pin_I = torch.empty(own, dtype=torch.int32).pin_memory().numpy().reshape(d.P, -1)
+        pin_in[:] = 0.0
+        sw.set_J(pin_in.reshape(d.P, -1)); sw.run(1, kernel=kernel); sw.get_J(out=pin_J); sw.get_idx(out=pin_I)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            sw.set_J(pin_in.reshape(d.P, -1))
+            sw.run(1, kernel=kernel)
+            sw.get_J(out=pin_J)
+            sw.get_idx(out=pin_I)
+        barrier()
+        dt = max_over_ranks(time.perf_counter() - t0)
+        ext = (sw.slab[3] - sw.slab[2]) if world > 1 else d.n[-1]
+        h2d = int(S_all // d.n[-1] * ext * 8)
+        e2e = {"value": upd_per_step * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": int(own * 12), "steps": Ke,
+               "call": "bellman_set_J(host) + bellman_run(1) + bellman_get_J(host) + bellman_get_idx(host)"}
+
+    if rank != 0:
+        sw.close()
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the stage kernel ---------------------------------------------------------
+    peak, peak_src = measured_peak_gbs()
+    bytes_per_launch = (S_all / world) * (16 + 4)          # read J_{k+1}, write J_k, write int32 argmin
+    ms_kernel = (ms_dev - ms_x) / K
+    achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
+    # secondary bound: fp64 pipe, 64 lanes/clk/SM x 148 SMs at the clock seen
+    mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    fp64_ops_per_update = 17.0
+    fp64_peak = 64 * 148 * mhz * 1e6
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": None, "peak_source": peak_src,
+                "bytes_per_launch": bytes_per_launch, "kernel_ms": ms_kernel, "kernel": sw.last_kernel,
+                "fp64_secondary": {"ops_per_update": fp64_ops_per_update,
+                                   "achieved_ops_per_s": value / world * fp64_ops_per_update,
+                                   "peak_ops_per_s": fp64_peak,
+                                   "frac": value / world * fp64_ops_per_update / fp64_peak,
+                                   "note": "C>=16 makes the stage fp64-issue bound, not HBM bound (DESIGN.md)"}}
+
+    cpu = None
+    if not args.no_cpu_baseline and world == 1:
+        r, cores, sample, _ = cpu_sample_rate(d, 12.0)
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "grid": d.n, "controls": d.C, "problems": d.P,
+                       "step": "one backward stage over the whole grid",
+                       "partition": ("dim %d slabs over %d ranks, NCCL halo exchange" % (part_dim, world))
+                       if world > 1 else "none",
+                       "l2": "J_{k+1} (%.0f MB) exceeds the 126 MB L2; no flush needed" % (S_all * 8 / 1e6)
+                       if S_all * 8 > 130e6 else "inputs fit L2 (stage-to-stage reuse is the workload)",
+                       "cuda_graph": bool(use_graph)},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K}
+    print(json.dumps(line), flush=True)
+    sw.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,10 @@
+"""bellman_b200 — B200-native backward Bellman value-iteration sweep behind the reference's
+classdef surface (Dynamic_Solver / Solver_position / Solver_attitude / Solver_pos_att).
+
+Import as ``import bellman_b200`` (shim at the repository root; this directory's name is not a
+valid Python identifier).
+"""
+from . import tables  # noqa: F401
+from ._lib import (BellmanError, Sweep, KERNEL_AUTO, KERNEL_DIRECT, KERNEL_WINDOW,  # noqa: F401
+                   KERNEL_SPLITC, EXPORTS, LIB_PATH, load, plan_slabs, query_locate, get_unique_id)
+from .solvers import Dynamic_Solver, Solver_position, Solver_attitude, Solver_pos_att  # noqa: F401

@@ -1,0 +1,268 @@
+"""ctypes binding of libbellman.so — the same C ABI (include/bellman.h) the MEX gateway binds.
+
+There is no fallback of any kind: if the shared library is missing, or no sm_100 device is
+usable, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libbellman.so")
+MAXD = 4
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_WINDOW, KERNEL_SPLITC = 0, 1, 2, 3
+LOCATE_UNIFORM, LOCATE_SEARCH = 0, 1
+
+STATUS = {0: "OK", -1: "BAD_ARG", -2: "CUDA", -3: "NCCL", -4: "OOM", -5: "NOT_RUN", -6: "STATE"}
+
+
+class BellmanError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"bellman:{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class CDesc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("D", C.c_int32), ("n", C.c_int32 * MAXD), ("C", C.c_int32),
+        ("P", C.c_int32), ("N", C.c_int32), ("grid", _dp * MAXD),
+        ("src_a", C.c_int32 * MAXD), ("src_b", C.c_int32 * MAXD),
+        ("Ta", _dp * MAXD), ("Tb", _dp * MAXD), ("Tc", _dp * MAXD),
+        ("q_order", C.c_int32 * MAXD), ("q", _dp * MAXD), ("r", _dp),
+        ("store_J_all", C.c_int32), ("store_idx_all", C.c_int32), ("device", C.c_int32),
+        ("part_dim", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+    ]
+
+
+class CRunOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("kernel", C.c_int32), ("check_period", C.c_int32),
+                ("check_tol", C.c_double), ("use_graph", C.c_int32), ("sync_each_stage", C.c_int32)]
+
+
+class CSlab(C.Structure):
+    _fields_ = [("own_lo", C.c_int32), ("own_hi", C.c_int32), ("ext_lo", C.c_int32), ("ext_hi", C.c_int32)]
+
+
+# every symbol include/bellman.h declares
+EXPORTS = [
+    "bellman_version", "bellman_last_error", "bellman_query_locate", "bellman_plan_slabs",
+    "bellman_create", "bellman_destroy", "bellman_get_unique_id", "bellman_comm_init",
+    "bellman_set_J", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
+    "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
+    "bellman_last_kernel", "bellman_rollout",
+]
+
+_lib = None
+
+
+def load():
+    """Load libbellman.so; raises if it has not been built (``__graft_entry__.build()``)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise BellmanError(-2, f"{LIB_PATH} is missing: build it with csrc/build.sh "
+                               "(there is no CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.bellman_last_error.restype = C.c_char_p
+    lib.bellman_last_error.argtypes = [C.c_void_p]
+    lib.bellman_last_kernel.restype = C.c_char_p
+    lib.bellman_last_kernel.argtypes = [C.c_void_p]
+    lib.bellman_create.argtypes = [C.POINTER(CDesc), C.POINTER(C.c_void_p)]
+    lib.bellman_destroy.argtypes = [C.c_void_p]
+    lib.bellman_destroy.restype = None
+    lib.bellman_run.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CRunOpts)]
+    lib.bellman_stage.argtypes = [C.c_void_p]
+    lib.bellman_set_J.argtypes = [C.c_void_p, _dp]
+    lib.bellman_get_J.argtypes = [C.c_void_p, C.c_int32, _dp]
+    lib.bellman_get_idx.argtypes = [C.c_void_p, C.c_int32, _ip]
+    lib.bellman_current_stage.argtypes = [C.c_void_p]
+    lib.bellman_get_check_log.argtypes = [C.c_void_p, _dp, C.c_int32]
+    lib.bellman_owned_range.argtypes = [C.c_void_p, C.POINTER(CSlab)]
+    lib.bellman_last_run_stats.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int64), _dp]
+    lib.bellman_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bellman_get_unique_id.argtypes = [C.c_void_p]
+    lib.bellman_query_locate.argtypes = [C.POINTER(CDesc), _ip]
+    lib.bellman_plan_slabs.argtypes = [C.POINTER(CDesc), C.c_int32, C.c_int32, C.POINTER(CSlab)]
+    lib.bellman_rollout.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]
+    _lib = lib
+    return lib
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1):
+    """tables.Desc -> (CDesc, keepalive)."""
+    cd = CDesc()
+    keep = []
+    D = d.D
+    cd.struct_size = C.sizeof(CDesc)
+    cd.D, cd.C, cd.P, cd.N = D, int(d.C), int(d.P), int(d.N)
+    for k in range(D):
+        cd.n[k] = int(d.n[k])
+        cd.src_a[k] = int(d.src_a[k])
+        cd.src_b[k] = int(d.src_b[k])
+        cd.q_order[k] = int(d.q_order[k])
+        for name in ("grid", "Ta", "Tb", "Tc", "q"):
+            a = getattr(d, name)[k]
+            if a is None:
+                getattr(cd, name)[k] = _dp()
+            else:
+                a = _f64(a)
+                keep.append(a)
+                getattr(cd, name)[k] = a.ctypes.data_as(_dp)
+    r = _f64(d.r)
+    keep.append(r)
+    cd.r = r.ctypes.data_as(_dp)
+    cd.store_J_all = int(bool(d.store_J_all))
+    cd.store_idx_all = int(bool(d.store_idx_all))
+    cd.device, cd.part_dim, cd.rank, cd.nranks = int(device), int(part_dim), int(rank), int(nranks)
+    return cd, keep
+
+
+def query_locate(d):
+    """Locate mode the library uses per (problem, dim): [P, D] of LOCATE_*.  Host-only."""
+    lib = load()
+    cd, keep = to_cdesc(d)
+    modes = np.zeros(d.P * d.D, dtype=np.int32)
+    rc = lib.bellman_query_locate(C.byref(cd), modes.ctypes.data_as(_ip))
+    if rc != 0:
+        raise BellmanError(rc, "bellman_query_locate")
+    return modes.reshape(d.P, d.D)
+
+
+def plan_slabs(d, part_dim, nranks):
+    """Slab plan [(own_lo, own_hi, ext_lo, ext_hi)] per rank from the exact reach analysis.  Host-only."""
+    lib = load()
+    cd, keep = to_cdesc(d)
+    slabs = (CSlab * nranks)()
+    rc = lib.bellman_plan_slabs(C.byref(cd), part_dim, nranks, slabs)
+    if rc != 0:
+        raise BellmanError(rc, "bellman_plan_slabs")
+    return [(s.own_lo, s.own_hi, s.ext_lo, s.ext_hi) for s in slabs]
+
+
+def get_unique_id():
+    lib = load()
+    buf = (C.c_char * 128)()
+    rc = lib.bellman_get_unique_id(buf)
+    if rc != 0:
+        raise BellmanError(rc, lib.bellman_last_error(None).decode())
+    return bytes(buf)
+
+
+class Sweep:
+    """One ``bellman_handle``: device-resident tables + J/idx storage for a (batched) problem."""
+
+    def __init__(self, desc, device=-1, part_dim=-1, rank=0, nranks=1):
+        self.lib = load()
+        self.desc = desc
+        cd, keep = to_cdesc(desc, device, part_dim, rank, nranks)
+        h = C.c_void_p()
+        rc = self.lib.bellman_create(C.byref(cd), C.byref(h))
+        if rc != 0:
+            raise BellmanError(rc, self.lib.bellman_last_error(None).decode())
+        self.h = h
+        s = CSlab()
+        self.lib.bellman_owned_range(self.h, C.byref(s))
+        self.part_dim = part_dim
+        self.slab = (s.own_lo, s.own_hi, s.ext_lo, s.ext_hi)
+        self.own_shape = list(desc.n)
+        if part_dim >= 0:
+            self.own_shape[part_dim] = s.own_hi - s.own_lo
+        self.S_own = int(np.prod(self.own_shape))
+
+    def _check(self, rc):
+        if rc != 0:
+            raise BellmanError(rc, self.lib.bellman_last_error(self.h).decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.bellman_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def comm_init(self, id128):
+        buf = C.create_string_buffer(bytes(id128), 128)
+        self._check(self.lib.bellman_comm_init(self.h, buf))
+
+    def set_J(self, J=None):
+        if J is None:
+            self._check(self.lib.bellman_set_J(self.h, _dp()))
+        else:
+            J = _f64(J).reshape(self.desc.P, self.desc.S)
+            self._check(self.lib.bellman_set_J(self.h, J.ctypes.data_as(_dp)))
+
+    def run(self, n_stages=None, kernel=KERNEL_AUTO, check_period=0, check_tol=0.0, use_graph=False,
+            sync_each_stage=False):
+        if n_stages is None:
+            n_stages = self.current_stage - 1
+        o = CRunOpts(C.sizeof(CRunOpts), kernel, check_period, check_tol, int(use_graph), int(sync_each_stage))
+        self._check(self.lib.bellman_run(self.h, int(n_stages), C.byref(o)))
+        return self
+
+    def stage(self):
+        self._check(self.lib.bellman_stage(self.h))
+
+    @property
+    def current_stage(self):
+        return int(self.lib.bellman_current_stage(self.h))
+
+    @property
+    def last_kernel(self):
+        return self.lib.bellman_last_kernel(self.h).decode()
+
+    def stats(self):
+        ms, n, mx = C.c_double(), C.c_int64(), C.c_double()
+        self._check(self.lib.bellman_last_run_stats(self.h, C.byref(ms), C.byref(n), C.byref(mx)))
+        return {"ms": ms.value, "launches": n.value, "ms_exchange": mx.value}
+
+    def get_J(self, stage=None, out=None):
+        """J of ``stage`` (default: current) for the owned slab: [P, S_own], column-major states."""
+        stage = self.current_stage if stage is None else stage
+        if out is None:
+            out = np.empty((self.desc.P, self.S_own), dtype=np.float64)
+        self._check(self.lib.bellman_get_J(self.h, int(stage), out.ctypes.data_as(_dp)))
+        return out
+
+    def get_idx(self, stage=None, out=None):
+        """0-based argmin control index of ``stage``: [P, S_own] int32."""
+        stage = self.current_stage if stage is None else stage
+        if out is None:
+            out = np.empty((self.desc.P, self.S_own), dtype=np.int32)
+        self._check(self.lib.bellman_get_idx(self.h, int(stage), out.ctypes.data_as(_ip)))
+        return out
+
+    def check_log(self):
+        n = self.lib.bellman_get_check_log(self.h, _dp(), 0)
+        out = np.zeros((max(n, 0), 3))
+        if n > 0:
+            self.lib.bellman_get_check_log(self.h, out.ctypes.data_as(_dp), n)
+        return out
+
+    def rollout(self, A, B, u_values, x0, mode=0, ssu_stage=1):
+        """x0: [batch, 2].  Returns X [batch, N, 2], U [batch, N]."""
+        x0 = _f64(x0).reshape(-1, 2)
+        batch = x0.shape[0]
+        N = self.desc.N
+        X = np.empty((batch, N, 2))
+        U = np.empty((batch, N))
+        A = _f64(np.asarray(A, dtype=np.float64).reshape(2, 2).ravel(order="F"))
+        B = _f64(np.asarray(B, dtype=np.float64).ravel())
+        uv = _f64(u_values)
+        self._check(self.lib.bellman_rollout(self.h, A.ctypes.data_as(_dp), B.ctypes.data_as(_dp),
+                                             uv.ctypes.data_as(_dp), x0.ctypes.data_as(_dp), batch,
+                                             int(mode), int(ssu_stage), X.ctypes.data_as(_dp),
+                                             U.ctypes.data_as(_dp)))
+        return X, U

@@ -1,0 +1,596 @@
+// bellman_api.cu — C ABI of libbellman.so (include/bellman.h): handles, device residency,
+// the stage loop, NCCL halo exchange, copy-in/out.  One process drives one GPU.
+#include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>   // types only; libnccl.so.2 is dlopen()ed lazily in bellman_comm_init
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "bellman_handle.h"
+#include "bellman_kernels.cuh"
+
+using namespace bellman;
+
+static thread_local std::string g_create_error;
+
+#define CUDA_TRY(h, expr)                                                                     \
+    do {                                                                                      \
+        cudaError_t _e = (expr);                                                              \
+        if (_e != cudaSuccess) {                                                              \
+            (h)->err = std::string(#expr) + ": " + cudaGetErrorString(_e);                    \
+            return _e == cudaErrorMemoryAllocation ? BELLMAN_ERR_OOM : BELLMAN_ERR_CUDA;      \
+        }                                                                                     \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// NCCL, loaded on demand (single-GPU use never needs it)
+// ---------------------------------------------------------------------------------------------
+struct NcclApi {
+    void *lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                              cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char *(*GetErrorString)(ncclResult_t) = nullptr;
+};
+
+static NcclApi *nccl_api(std::string &err) {
+    static NcclApi api;
+    if (api.lib) return &api;
+    const char *override_path = std::getenv("BELLMAN_NCCL_LIB");
+    const char *names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+    for (const char *nm : names) {
+        if (!nm) continue;
+        api.lib = dlopen(nm, RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) break;
+    }
+    if (!api.lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return nullptr; }
+#define LOAD(field, sym)                                                       \
+    api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.lib, sym));    \
+    if (!api.field) { err = std::string("libnccl lacks ") + sym; api.lib = nullptr; return nullptr; }
+    LOAD(GetUniqueId, "ncclGetUniqueId")
+    LOAD(CommInitRank, "ncclCommInitRank")
+    LOAD(CommDestroy, "ncclCommDestroy")
+    LOAD(Send, "ncclSend")
+    LOAD(Recv, "ncclRecv")
+    LOAD(AllReduce, "ncclAllReduce")
+    LOAD(GroupStart, "ncclGroupStart")
+    LOAD(GroupEnd, "ncclGroupEnd")
+    LOAD(GetErrorString, "ncclGetErrorString")
+#undef LOAD
+    return &api;
+}
+
+extern "C" int bellman_version(void) { return BELLMAN_ABI_VERSION; }
+
+extern "C" const char *bellman_last_error(const bellman_handle *h) {
+    return h ? h->err.c_str() : g_create_error.c_str();
+}
+
+static int upload_tables(bellman_handle *h) {
+    HostProblem &hp = h->hp;
+    const int D = hp.D, P = hp.P;
+    // layout: per dim: grid, rinv, Ta, Tb, Tc, q, loc ; then r
+    std::vector<double> buf;
+    size_t o_grid[MAXD], o_rinv[MAXD], o_Ta[MAXD], o_Tb[MAXD], o_Tc[MAXD], o_q[MAXD], o_loc[MAXD], o_r;
+    auto push = [&](const std::vector<double> &v) {
+        const size_t o = buf.size();
+        buf.insert(buf.end(), v.begin(), v.end());
+        while (buf.size() % 2) buf.push_back(0.0);   // keep 16-byte alignment of every table
+        return o;
+    };
+    for (int d = 0; d < D; ++d) {
+        o_grid[d] = push(hp.grid[d]);
+        o_rinv[d] = push(hp.rinv[d]);
+        o_Ta[d] = push(hp.Ta[d]);
+        o_Tb[d] = hp.has_b[d] ? push(hp.Tb[d]) : 0;
+        o_Tc[d] = hp.has_c[d] ? push(hp.Tc[d]) : 0;
+        o_q[d] = push(hp.q[d]);
+        std::vector<double> loc(2 * (size_t)P);
+        for (int p = 0; p < P; ++p) { loc[2 * p] = hp.inv_h[d][p]; loc[2 * p + 1] = hp.off[d][p]; }
+        o_loc[d] = push(loc);
+    }
+    o_r = push(hp.r);
+    CUDA_TRY(h, cudaMalloc(&h->d_tab, buf.size() * sizeof(double)));
+    CUDA_TRY(h, cudaMemcpy(h->d_tab, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    std::vector<int32_t> modes((size_t)D * P);
+    for (int d = 0; d < D; ++d)
+        for (int p = 0; p < P; ++p) modes[(size_t)d * P + p] = hp.mode[(size_t)p * D + d];
+    CUDA_TRY(h, cudaMalloc(&h->d_mode, modes.size() * sizeof(int32_t)));
+    CUDA_TRY(h, cudaMemcpy(h->d_mode, modes.data(), modes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+
+    StageParams &sp = h->sp;
+    std::memset(&sp, 0, sizeof(sp));
+    sp.D = D; sp.C = hp.C; sp.P = P;
+    sp.S_ext = h->S_ext; sp.S_own = h->S_own;
+    for (int d = 0; d < D; ++d) {
+        DimParams &dp = sp.dim[d];
+        dp.grid = h->d_tab + o_grid[d];
+        dp.rinv = h->d_tab + o_rinv[d];
+        dp.Ta = h->d_tab + o_Ta[d];
+        dp.Tb = hp.has_b[d] ? h->d_tab + o_Tb[d] : nullptr;
+        dp.Tc = hp.has_c[d] ? h->d_tab + o_Tc[d] : nullptr;
+        dp.q = h->d_tab + o_q[d];
+        dp.loc = h->d_tab + o_loc[d];
+        dp.mode = h->d_mode + (size_t)d * P;
+        dp.n = hp.n[d];
+        dp.src_a = hp.src_a[d];
+        dp.src_b = hp.has_b[d] ? hp.src_b[d] : 0;
+        dp.n_a = hp.n[hp.src_a[d]];
+        dp.n_b = hp.has_b[d] ? hp.n[hp.src_b[d]] : 0;
+        dp.own_n = h->own_n[d];
+        dp.own_lo = h->own_lo[d];
+        dp.ext_lo = h->ext_lo[d];
+        dp.stride = h->stride[d];
+        sp.q_order[d] = hp.q_order[d];
+    }
+    sp.r = h->d_tab + o_r;
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
+    if (!out) { g_create_error = "out is NULL"; return BELLMAN_ERR_BAD_ARG; }
+    *out = nullptr;
+    bellman_handle *h = new bellman_handle();
+    h->err = load_problem(d, h->hp);
+    if (!h->err.empty()) { g_create_error = h->err; delete h; return BELLMAN_ERR_BAD_ARG; }
+    HostProblem &hp = h->hp;
+    auto fail = [&](int code) { g_create_error = h->err; bellman_destroy(h); return code; };
+
+    // partition
+    h->part_dim = d->part_dim;
+    h->rank = d->part_dim >= 0 ? d->rank : 0;
+    h->nranks = d->part_dim >= 0 ? d->nranks : 1;
+    for (int k = 0; k < MAXD; ++k) { h->own_n[k] = 1; h->own_lo[k] = 0; h->ext_lo[k] = 0; h->ext_n[k] = 1; h->stride[k] = 0; }
+    for (int k = 0; k < hp.D; ++k) { h->own_n[k] = hp.n[k]; h->ext_n[k] = hp.n[k]; }
+    if (h->part_dim >= 0) {
+        if (h->nranks < 1 || h->rank < 0 || h->rank >= h->nranks) { h->err = "bad rank/nranks"; return fail(BELLMAN_ERR_BAD_ARG); }
+        h->slabs.resize(h->nranks);
+        h->err = plan_slabs(hp, h->part_dim, h->nranks, h->slabs.data());
+        if (!h->err.empty()) return fail(BELLMAN_ERR_BAD_ARG);
+        const bellman_slab &m = h->slabs[h->rank];
+        h->own_lo[h->part_dim] = m.own_lo;
+        h->own_n[h->part_dim] = m.own_hi - m.own_lo;
+        h->ext_lo[h->part_dim] = m.ext_lo;
+        h->ext_n[h->part_dim] = m.ext_hi - m.ext_lo;
+    } else {
+        h->slabs.assign(1, bellman_slab{0, 0, 0, 0});
+    }
+    h->S_ext = 1; h->S_own = 1;
+    for (int k = 0; k < hp.D; ++k) { h->stride[k] = h->S_ext; h->S_ext *= h->ext_n[k]; h->S_own *= h->own_n[k]; }
+
+    // device
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0) {
+        h->err = std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e);
+        return fail(BELLMAN_ERR_CUDA);
+    }
+    if (d->device >= 0) {
+        h->device = d->device;
+        if (cudaSetDevice(h->device) != cudaSuccess) { h->err = "cudaSetDevice failed"; return fail(BELLMAN_ERR_CUDA); }
+    } else if (cudaGetDevice(&h->device) != cudaSuccess) { h->err = "cudaGetDevice failed"; return fail(BELLMAN_ERR_CUDA); }
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, h->device) != cudaSuccess) { h->err = "cudaGetDeviceProperties failed"; return fail(BELLMAN_ERR_CUDA); }
+    if (prop.major != 10) {
+        h->err = "device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor) +
+                 "; this library carries sm_100a code only";
+        return fail(BELLMAN_ERR_CUDA);
+    }
+    int rc;
+#define TRY_RC(expr) if ((rc = (expr)) != BELLMAN_OK) return fail(rc)
+    auto cu = [&](cudaError_t ce, const char *what) {
+        if (ce == cudaSuccess) return (int)BELLMAN_OK;
+        h->err = std::string(what) + ": " + cudaGetErrorString(ce);
+        return (int)(ce == cudaErrorMemoryAllocation ? BELLMAN_ERR_OOM : BELLMAN_ERR_CUDA);
+    };
+    TRY_RC(cu(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking), "cudaStreamCreate"));
+    TRY_RC(cu(cudaEventCreate(&h->ev0), "cudaEventCreate"));
+    TRY_RC(cu(cudaEventCreate(&h->ev1), "cudaEventCreate"));
+    TRY_RC(upload_tables(h));
+
+    h->store_J_all = d->store_J_all != 0;
+    h->store_idx_all = d->store_idx_all != 0;
+    const size_t nJ = (h->store_J_all ? (size_t)hp.N : 2) * h->slot_elems_J();
+    const size_t nI = (h->store_idx_all ? (size_t)hp.N : 1) * h->slot_elems_idx();
+    TRY_RC(cu(cudaMalloc(&h->d_J, nJ * sizeof(double)), "cudaMalloc(J)"));
+    TRY_RC(cu(cudaMalloc(&h->d_idx, nI * sizeof(int32_t)), "cudaMalloc(idx)"));
+    TRY_RC(cu(cudaMemsetAsync(h->d_idx, 0, nI * sizeof(int32_t), h->stream), "cudaMemset(idx)"));
+    h->n_partials = 592;
+    TRY_RC(cu(cudaMalloc(&h->d_partials, 2 * h->n_partials * sizeof(double)), "cudaMalloc"));
+    TRY_RC(cu(cudaMalloc(&h->d_sums, 2 * sizeof(double)), "cudaMalloc"));
+#undef TRY_RC
+    h->cur_stage = hp.N;
+    rc = bellman_set_J(h, nullptr);
+    if (rc != BELLMAN_OK) return fail(rc);
+    window_setup(h);   // optional fast path; leaves wcfg.valid = false when it does not apply
+    *out = h;
+    return BELLMAN_OK;
+}
+
+extern "C" void bellman_destroy(bellman_handle *h) {
+    if (!h) return;
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->comm) {
+        std::string e;
+        NcclApi *api = nccl_api(e);
+        if (api) api->CommDestroy(h->comm);
+    }
+    cudaFree(h->d_tab); cudaFree(h->d_mode); cudaFree(h->d_J); cudaFree(h->d_idx);
+    cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_tmaps);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+extern "C" int bellman_owned_range(const bellman_handle *h, bellman_slab *out) {
+    if (!h || !out) return BELLMAN_ERR_BAD_ARG;
+    if (h->part_dim >= 0) *out = h->slabs[h->rank];
+    else *out = bellman_slab{0, 0, 0, 0};
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_current_stage(const bellman_handle *h) { return h ? h->cur_stage : BELLMAN_ERR_BAD_ARG; }
+
+// ---------------------------------------------------------------------------------------------
+// copy-in / copy-out.  Along part_dim the device arrays hold [ext_lo, ext_hi); every other
+// dimension is complete, so a slab is (outer) rows of (inner*len) contiguous elements.
+// ---------------------------------------------------------------------------------------------
+static void slab_geometry(const bellman_handle *h, long long &inner, long long &outer) {
+    inner = 1; outer = 1;
+    const int p = h->part_dim < 0 ? h->hp.D - 1 : h->part_dim;
+    for (int k = 0; k < p; ++k) inner *= h->hp.n[k];
+    for (int k = p + 1; k < h->hp.D; ++k) outer *= h->hp.n[k];
+}
+
+extern "C" int bellman_set_J(bellman_handle *h, const double *J_host) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    const HostProblem &hp = h->hp;
+    h->cur_stage = hp.N;
+    h->check_log.clear();
+    double *dst = h->J_ptr(hp.N);
+    if (!J_host) {
+        CUDA_TRY(h, cudaMemsetAsync(dst, 0, h->slot_elems_J() * sizeof(double), h->stream));
+    } else {
+        long long inner, outer;
+        slab_geometry(h, inner, outer);
+        const int p = h->part_dim < 0 ? hp.D - 1 : h->part_dim;
+        const size_t S = (size_t)hp.S();
+        for (int pr = 0; pr < hp.P; ++pr) {
+            const double *src = J_host + (size_t)pr * S + (size_t)h->ext_lo[p] * inner;
+            CUDA_TRY(h, cudaMemcpy2DAsync(dst + (size_t)pr * h->S_ext, (size_t)h->ext_n[p] * inner * 8, src,
+                                          (size_t)hp.n[p] * inner * 8, (size_t)h->ext_n[p] * inner * 8,
+                                          (size_t)outer, cudaMemcpyHostToDevice, h->stream));
+        }
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->J_set = true;
+    return BELLMAN_OK;
+}
+
+static int stage_available(const bellman_handle *h, int stage, bool stored_all, bool is_idx) {
+    const int N = h->hp.N;
+    const int top = is_idx ? N - 1 : N;
+    if (stage < 1 || stage > top) return BELLMAN_ERR_BAD_ARG;
+    if (stage < h->cur_stage) return BELLMAN_ERR_NOT_RUN;
+    if (!stored_all && stage != h->cur_stage) return BELLMAN_ERR_NOT_RUN;
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_get_J(bellman_handle *h, int32_t stage, double *out) {
+    if (!h || !out) return BELLMAN_ERR_BAD_ARG;
+    int rc = stage_available(h, stage, h->store_J_all, false);
+    if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    const HostProblem &hp = h->hp;
+    long long inner, outer;
+    slab_geometry(h, inner, outer);
+    const int p = h->part_dim < 0 ? hp.D - 1 : h->part_dim;
+    const double *src0 = h->J_ptr(stage);
+    for (int pr = 0; pr < hp.P; ++pr) {
+        const double *src = src0 + (size_t)pr * h->S_ext + (size_t)(h->own_lo[p] - h->ext_lo[p]) * inner;
+        CUDA_TRY(h, cudaMemcpy2DAsync(out + (size_t)pr * h->S_own, (size_t)h->own_n[p] * inner * 8, src,
+                                      (size_t)h->ext_n[p] * inner * 8, (size_t)h->own_n[p] * inner * 8,
+                                      (size_t)outer, cudaMemcpyDeviceToHost, h->stream));
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_get_idx(bellman_handle *h, int32_t stage, int32_t *out) {
+    if (!h || !out) return BELLMAN_ERR_BAD_ARG;
+    int rc = stage_available(h, stage, h->store_idx_all, true);
+    if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    CUDA_TRY(h, cudaMemcpyAsync(out, h->idx_ptr(stage), h->slot_elems_idx() * sizeof(int32_t),
+                                cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_get_check_log(const bellman_handle *h, double *out, int32_t max_entries) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    const int n = (int)(h->check_log.size() / 3);
+    const int m = std::min(n, (int)max_entries);
+    if (out && m > 0) std::memcpy(out, h->check_log.data(), sizeof(double) * 3 * (size_t)m);
+    return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// NCCL bootstrap + halo exchange
+// ---------------------------------------------------------------------------------------------
+extern "C" int bellman_get_unique_id(void *id128_out) {
+    if (!id128_out) return BELLMAN_ERR_BAD_ARG;
+    std::string e;
+    NcclApi *api = nccl_api(e);
+    if (!api) { g_create_error = e; return BELLMAN_ERR_NCCL; }
+    ncclUniqueId id;
+    static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+    if (api->GetUniqueId(&id) != ncclSuccess) { g_create_error = "ncclGetUniqueId failed"; return BELLMAN_ERR_NCCL; }
+    std::memcpy(id128_out, &id, 128);
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_comm_init(bellman_handle *h, const void *id128) {
+    if (!h || !id128) return BELLMAN_ERR_BAD_ARG;
+    if (h->nranks <= 1) return BELLMAN_OK;
+    NcclApi *api = nccl_api(h->err);
+    if (!api) return BELLMAN_ERR_NCCL;
+    ncclUniqueId id;
+    std::memcpy(&id, id128, 128);
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    ncclResult_t r = api->CommInitRank(&h->comm, h->nranks, id, h->rank);
+    if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + api->GetErrorString(r); return BELLMAN_ERR_NCCL; }
+    return BELLMAN_OK;
+}
+
+// after stage `stage` has been written into its slot: fill the halo part of that slot
+static int exchange_halo(bellman_handle *h, int stage) {
+    if (h->nranks <= 1) return BELLMAN_OK;
+    if (!h->comm) { h->err = "partitioned handle needs bellman_comm_init before running"; return BELLMAN_ERR_STATE; }
+    NcclApi *api = nccl_api(h->err);
+    if (!api) return BELLMAN_ERR_NCCL;
+    const HostProblem &hp = h->hp;
+    long long inner, outer;
+    slab_geometry(h, inner, outer);
+    const int p = h->part_dim;
+    double *J = h->J_ptr(stage);
+    const bellman_slab &me = h->slabs[h->rank];
+    const long long row = (long long)h->ext_n[p] * inner;   // elements per outer index
+    ncclResult_t r = api->GroupStart();
+    for (int q = 0; q < h->nranks && r == ncclSuccess; ++q) {
+        if (q == h->rank) continue;
+        const bellman_slab &o = h->slabs[q];
+        const int slo = std::max(o.ext_lo, me.own_lo), shi = std::min(o.ext_hi, me.own_hi);
+        const int rlo = std::max(me.ext_lo, o.own_lo), rhi = std::min(me.ext_hi, o.own_hi);
+        for (int pr = 0; pr < hp.P && r == ncclSuccess; ++pr)
+            for (long long ou = 0; ou < outer && r == ncclSuccess; ++ou) {
+                double *base = J + (size_t)pr * h->S_ext + (size_t)ou * row;
+                if (slo < shi)
+                    r = api->Send(base + (size_t)(slo - me.ext_lo) * inner, (size_t)(shi - slo) * inner,
+                                  ncclDouble, q, h->comm, h->stream);
+                if (r == ncclSuccess && rlo < rhi)
+                    r = api->Recv(base + (size_t)(rlo - me.ext_lo) * inner, (size_t)(rhi - rlo) * inner,
+                                  ncclDouble, q, h->comm, h->stream);
+            }
+    }
+    ncclResult_t r2 = api->GroupEnd();
+    if (r == ncclSuccess) r = r2;
+    if (r != ncclSuccess) { h->err = std::string("halo exchange: ") + api->GetErrorString(r); return BELLMAN_ERR_NCCL; }
+    return BELLMAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// the stage loop
+// ---------------------------------------------------------------------------------------------
+static int pick_kernel(bellman_handle *h, int requested, int &lanes) {
+    const HostProblem &hp = h->hp;
+    lanes = 1;
+    if (requested == BELLMAN_KERNEL_DIRECT) return BELLMAN_KERNEL_DIRECT;
+    const long long states = h->S_own * hp.P;
+    auto pick_lanes = [&]() {
+        int L = 1;
+        while (L < 32 && 2 * L <= hp.C && states * L < 148LL * 2048) L *= 2;
+        return L;
+    };
+    if (requested == BELLMAN_KERNEL_SPLITC) { lanes = std::max(2, pick_lanes()); return BELLMAN_KERNEL_SPLITC; }
+    if (requested == BELLMAN_KERNEL_WINDOW) return h->wcfg.valid ? BELLMAN_KERNEL_WINDOW : BELLMAN_KERNEL_DIRECT;
+    // AUTO
+    if (h->wcfg.valid && states >= 148LL * 2048) return BELLMAN_KERNEL_WINDOW;
+    lanes = pick_lanes();
+    return lanes > 1 ? BELLMAN_KERNEL_SPLITC : BELLMAN_KERNEL_DIRECT;
+}
+
+static int launch_one_stage(bellman_handle *h, int kernel, int lanes) {
+    const int from = h->cur_stage, to = from - 1;
+    StageParams sp = h->sp;
+    sp.J_next = h->J_ptr(from);
+    sp.J_out = h->J_ptr(to);
+    sp.idx_out = h->idx_ptr(to);
+    cudaError_t e;
+    if (kernel == BELLMAN_KERNEL_SPLITC) e = launch_stage_splitc(sp, lanes, h->stream);
+    else if (kernel == BELLMAN_KERNEL_WINDOW) e = window_launch_for_handle(h, sp, h->J_slot(from), h->stream);
+    else e = launch_stage_direct(sp, h->stream);
+    if (e != cudaSuccess) { h->err = std::string("stage launch: ") + cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
+    h->last_launches += 1;
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_run_opts *opts) {
+    if (!h || n_stages < 0) return BELLMAN_ERR_BAD_ARG;
+    bellman_run_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) {
+        if (opts->struct_size != (int32_t)sizeof(bellman_run_opts)) { h->err = "bellman_run_opts.struct_size mismatch"; return BELLMAN_ERR_BAD_ARG; }
+        o = *opts;
+    }
+    if (h->cur_stage - n_stages < 1) { h->err = "run would pass stage 1"; return BELLMAN_ERR_STATE; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    int lanes = 1;
+    const int kernel = pick_kernel(h, o.kernel, lanes);
+    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? "window" : kernel == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
+    h->last_launches = 0;
+    h->last_ms_exchange = 0.0;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xev;
+    CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+
+    const bool graphable = o.use_graph && h->nranks == 1 && !o.sync_each_stage && !h->store_J_all &&
+                           !h->store_idx_all;
+    int done = 0;
+    int rc = BELLMAN_OK;
+    double fsum_prev = 0.0;
+    if (!h->check_log.empty()) fsum_prev = h->check_log[h->check_log.size() - 2];
+    bool stop = false;
+    while (done < n_stages && !stop) {
+        // stages until the next check point (or the end)
+        int span = n_stages - done;
+        if (o.check_period > 0) {
+            int next_check = ((h->cur_stage - 1) / o.check_period) * o.check_period;   // largest multiple < cur
+            if (next_check >= 1) span = std::min(span, h->cur_stage - next_check);
+        }
+        if (graphable && span >= 4) {
+            // ping-pong has period 2: capture two stages once, replay span/2 times
+            cudaGraph_t graph = nullptr;
+            cudaGraphExec_t exec = nullptr;
+            const int pairs = span / 2;
+            const int stage0 = h->cur_stage;
+            CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+            rc = launch_one_stage(h, kernel, lanes);
+            h->cur_stage -= 1;
+            if (rc == BELLMAN_OK) rc = launch_one_stage(h, kernel, lanes);
+            h->cur_stage = stage0;
+            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+            if (rc != BELLMAN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+            CUDA_TRY(h, ce);
+            CUDA_TRY(h, cudaGraphInstantiate(&exec, graph, 0));
+            for (int i = 0; i < pairs; ++i) CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
+            h->last_launches += 2LL * pairs - 2;
+            h->cur_stage -= 2 * pairs;
+            done += 2 * pairs;
+            span -= 2 * pairs;
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            cudaGraphExecDestroy(exec);
+            cudaGraphDestroy(graph);
+        }
+        for (int i = 0; i < span; ++i) {
+            rc = launch_one_stage(h, kernel, lanes);
+            if (rc != BELLMAN_OK) return rc;
+            h->cur_stage -= 1;
+            ++done;
+            if (h->nranks > 1) {
+                cudaEvent_t a, b;
+                CUDA_TRY(h, cudaEventCreate(&a));
+                CUDA_TRY(h, cudaEventCreate(&b));
+                CUDA_TRY(h, cudaEventRecord(a, h->stream));
+                rc = exchange_halo(h, h->cur_stage);
+                if (rc != BELLMAN_OK) return rc;
+                CUDA_TRY(h, cudaEventRecord(b, h->stream));
+                xev.emplace_back(a, b);
+            }
+            if (o.sync_each_stage) CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        }
+        if (o.check_period > 0 && h->cur_stage % o.check_period == 0) {
+            StageParams sp = h->sp;
+            sp.J_out = h->J_ptr(h->cur_stage);
+            sp.idx_out = h->idx_ptr(h->cur_stage);
+            cudaError_t e = launch_check_sums(sp, h->d_partials, h->n_partials, h->d_sums, h->stream);
+            if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
+            if (h->nranks > 1) {
+                NcclApi *api = nccl_api(h->err);
+                if (!api) return BELLMAN_ERR_NCCL;
+                if (api->AllReduce(h->d_sums, h->d_sums, 2, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess) {
+                    h->err = "ncclAllReduce failed"; return BELLMAN_ERR_NCCL;
+                }
+            }
+            double sums[2];
+            CUDA_TRY(h, cudaMemcpyAsync(sums, h->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+            h->check_log.push_back((double)h->cur_stage);
+            h->check_log.push_back(sums[0]);
+            h->check_log.push_back(sums[1]);
+            const double e_f = sums[0] - fsum_prev;
+            fsum_prev = sums[0];
+            if (std::fabs(e_f) < o.check_tol) stop = true;
+        }
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    float ms = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+    h->last_ms = ms;
+    for (auto &pr : xev) {
+        float x = 0.f;
+        cudaEventElapsedTime(&x, pr.first, pr.second);
+        h->last_ms_exchange += x;
+        cudaEventDestroy(pr.first);
+        cudaEventDestroy(pr.second);
+    }
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_stage(bellman_handle *h) { return bellman_run(h, 1, nullptr); }
+
+extern "C" int bellman_last_run_stats(const bellman_handle *h, double *ms_total, int64_t *kernel_launches,
+                                      double *ms_exchange) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    if (ms_total) *ms_total = h->last_ms;
+    if (kernel_launches) *kernel_launches = h->last_launches;
+    if (ms_exchange) *ms_exchange = h->last_ms_exchange;
+    return BELLMAN_OK;
+}
+
+extern "C" const char *bellman_last_kernel(const bellman_handle *h) { return h ? h->last_kernel.c_str() : ""; }
+
+// ---------------------------------------------------------------------------------------------
+// rollout
+// ---------------------------------------------------------------------------------------------
+extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double *B, const double *u_values,
+                               const double *x0, int32_t batch, int32_t mode, int32_t ssu_stage,
+                               double *X_out, double *U_out) {
+    if (!h || !A || !B || !u_values || !x0 || !X_out || !U_out || batch < 1) return BELLMAN_ERR_BAD_ARG;
+    const HostProblem &hp = h->hp;
+    if (hp.D != 2 || hp.P != 1 || h->nranks != 1) { h->err = "rollout needs D=2, P=1, one rank"; return BELLMAN_ERR_BAD_ARG; }
+    if (!h->store_idx_all) { h->err = "rollout needs store_idx_all"; return BELLMAN_ERR_STATE; }
+    if (h->cur_stage != 1) { h->err = "rollout needs a completed sweep (stage 1)"; return BELLMAN_ERR_NOT_RUN; }
+    if (mode == 1 && (ssu_stage < 1 || ssu_stage > hp.N - 1)) return BELLMAN_ERR_BAD_ARG;
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int N = hp.N;
+    double *d_u = nullptr, *d_x0 = nullptr, *d_X = nullptr, *d_U = nullptr;
+    auto cleanup = [&]() { cudaFree(d_u); cudaFree(d_x0); cudaFree(d_X); cudaFree(d_U); };
+#define RT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
+    RT(cudaMalloc(&d_u, sizeof(double) * hp.C));
+    RT(cudaMalloc(&d_x0, sizeof(double) * 2 * (size_t)batch));
+    RT(cudaMalloc(&d_X, sizeof(double) * 2 * (size_t)N * batch));
+    RT(cudaMalloc(&d_U, sizeof(double) * (size_t)N * batch));
+    RT(cudaMemcpyAsync(d_u, u_values, sizeof(double) * hp.C, cudaMemcpyHostToDevice, h->stream));
+    RT(cudaMemcpyAsync(d_x0, x0, sizeof(double) * 2 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
+    RolloutParams rp;
+    rp.grid0 = h->sp.dim[0].grid; rp.rinv0 = h->sp.dim[0].rinv;
+    rp.grid1 = h->sp.dim[1].grid; rp.rinv1 = h->sp.dim[1].rinv;
+    rp.inv_h0 = hp.inv_h[0][0]; rp.off0 = hp.off[0][0];
+    rp.inv_h1 = hp.inv_h[1][0]; rp.off1 = hp.off[1][0];
+    rp.mode0 = hp.mode[0]; rp.mode1 = hp.mode[1];
+    rp.n0 = hp.n[0]; rp.n1 = hp.n[1]; rp.N = N; rp.C = hp.C; rp.batch = batch;
+    rp.mode = mode; rp.ssu_stage = ssu_stage;
+    rp.idx_all = h->d_idx; rp.u_values = d_u;
+    for (int i = 0; i < 4; ++i) rp.A[i] = A[i];
+    rp.B[0] = B[0]; rp.B[1] = B[1];
+    rp.x0 = d_x0; rp.X_out = d_X; rp.U_out = d_U;
+    RT(launch_rollout(rp, h->stream));
+    RT(cudaMemcpyAsync(X_out, d_X, sizeof(double) * 2 * (size_t)N * batch, cudaMemcpyDeviceToHost, h->stream));
+    RT(cudaMemcpyAsync(U_out, d_U, sizeof(double) * (size_t)N * batch, cudaMemcpyDeviceToHost, h->stream));
+    RT(cudaStreamSynchronize(h->stream));
+#undef RT
+    cleanup();
+    return BELLMAN_OK;
+}

@@ -1,0 +1,62 @@
+// bellman_handle.h — the opaque handle behind the C ABI (shared by bellman_api.cu / bellman_window.cu)
+#pragma once
+#include <cuda_runtime.h>
+#include <nccl.h>   // types only; libnccl.so.2 is dlopen()ed lazily in bellman_comm_init
+
+#include <string>
+#include <vector>
+
+#include "bellman_internal.h"
+
+struct bellman_handle {
+    bellman::HostProblem hp;
+    std::string err;
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    // partition
+    int part_dim = -1, rank = 0, nranks = 1;
+    std::vector<bellman_slab> slabs;
+    int own_n[bellman::MAXD], own_lo[bellman::MAXD], ext_lo[bellman::MAXD], ext_n[bellman::MAXD];
+    long long stride[bellman::MAXD];
+    long long S_ext = 0, S_own = 0;
+    // device memory
+    double *d_tab = nullptr;          // all fp64 tables
+    int32_t *d_mode = nullptr;        // [D][P]
+    bellman::StageParams sp{};                 // template with table pointers filled in
+    bool store_J_all = false, store_idx_all = false;
+    double *d_J = nullptr;            // [N or 2][P][S_ext]
+    int32_t *d_idx = nullptr;         // [N or 1][P][S_own]
+    int cur_stage = 0;
+    bool J_set = false;
+    // check sums
+    double *d_partials = nullptr, *d_sums = nullptr;
+    int n_partials = 0;
+    std::vector<double> check_log;    // triples
+    // nccl
+    ncclComm_t comm = nullptr;
+    // window kernel state
+    bellman::WindowConfig wcfg;
+    void *d_tmaps = nullptr;          // CUtensorMap per J slot
+    int n_tmaps = 0;
+    // stats
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    double last_ms = 0.0, last_ms_exchange = 0.0;
+    int64_t last_launches = 0;
+    std::string last_kernel = "none";
+
+    size_t slot_elems_J() const { return (size_t)hp.P * (size_t)S_ext; }
+    size_t slot_elems_idx() const { return (size_t)hp.P * (size_t)S_own; }
+    int J_slot(int stage) const { return store_J_all ? stage - 1 : ((hp.N - stage) & 1); }
+    int idx_slot(int stage) const { return store_idx_all ? stage - 1 : 0; }
+    double *J_ptr(int stage) const { return d_J + (size_t)J_slot(stage) * slot_elems_J(); }
+    int32_t *idx_ptr(int stage) const { return d_idx + (size_t)idx_slot(stage) * slot_elems_idx(); }
+};
+
+
+namespace bellman {
+// bellman_window.cu: plan the TMA-staged D = 2 kernel for this handle (sets h->wcfg, encodes one
+// tensor map per J slot).  Leaves wcfg.valid = false when the problem does not qualify.
+void window_setup(bellman_handle *h);
+cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next,
+                                     cudaStream_t st);
+}  // namespace bellman

@@ -1,0 +1,75 @@
+// bellman_internal.h — shared between the host-only planner, the kernels and the C-ABI layer.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "../../include/bellman.h"
+
+namespace bellman {
+
+constexpr int MAXD = BELLMAN_MAX_DIM;
+
+// ---------------------------------------------------------------------------------------------
+// Host-side, GPU-free image of a validated descriptor (all tables copied).
+// ---------------------------------------------------------------------------------------------
+struct HostProblem {
+    int D = 0, C = 0, P = 0, N = 0;
+    int n[MAXD] = {0, 0, 0, 0};
+    int src_a[MAXD] = {0, 0, 0, 0}, src_b[MAXD] = {-1, -1, -1, -1};
+    int q_order[MAXD] = {0, 1, 2, 3};
+    bool has_b[MAXD] = {false, false, false, false}, has_c[MAXD] = {false, false, false, false};
+    std::vector<double> grid[MAXD], rinv[MAXD], Ta[MAXD], Tb[MAXD], Tc[MAXD], q[MAXD], r;
+    std::vector<double> inv_h[MAXD], off[MAXD];   // [P] per dim
+    std::vector<int32_t> mode;                    // [P][D]
+    int64_t S() const { int64_t s = 1; for (int d = 0; d < D; ++d) s *= n[d]; return s; }
+};
+
+// returns "" on success, else an error message
+std::string load_problem(const bellman_desc *d, HostProblem &hp);
+// the locate rule of include/bellman.h evaluated on the host (used by the reach analysis)
+int host_locate(const HostProblem &hp, int p, int d, double x);
+// exact reach analysis: range of cells [lo, hi] (inclusive, hi = cell+1 node) of dimension `dim`
+// touched by states whose index along `dim` lies in [own_lo, own_hi)
+void reach_range(const HostProblem &hp, int dim, int own_lo, int own_hi, int &ext_lo, int &ext_hi);
+std::string plan_slabs(const HostProblem &hp, int part_dim, int nranks, bellman_slab *out);
+
+// ---------------------------------------------------------------------------------------------
+// Kernel parameter block (passed by value; device pointers address problem 0, rows are P-strided)
+// ---------------------------------------------------------------------------------------------
+struct DimParams {
+    const double *grid;   // [P][n]
+    const double *rinv;   // [P][n]   (last entry unused)
+    const double *Ta;     // [P][n_a]
+    const double *Tb;     // [P][n_b] or nullptr
+    const double *Tc;     // [P][C]   or nullptr
+    const double *q;      // [P][n]
+    const double *loc;    // [P][2] = {inv_h, off}
+    const int32_t *mode;  // [P]
+    int n, n_a, n_b, src_a, src_b;
+    int own_n;            // number of owned indices along this dim (== n unless partitioned)
+    int own_lo;           // first owned global index
+    int ext_lo;           // global index of local slot 0 of the J arrays
+    long long stride;     // element stride of this dim in the (extended) J arrays
+};
+
+struct StageParams {
+    DimParams dim[MAXD];
+    const double *r;          // [P][C]
+    const double *J_next;     // [P][S_ext]
+    double *J_out;            // [P][S_ext]
+    int32_t *idx_out;         // [P][S_own]
+    long long S_ext, S_own;
+    int D, C, P;
+    int q_order[MAXD];
+};
+
+// window (TMA-staged) kernel configuration for D = 2
+struct WindowConfig {
+    int tile0 = 0, tile1 = 0;     // states per CTA tile
+    int cchunk = 0;               // controls per staged window
+    int win0 = 0, win1 = 0;       // window box (rows, cols) in cells
+    bool valid = false;
+};
+
+}  // namespace bellman

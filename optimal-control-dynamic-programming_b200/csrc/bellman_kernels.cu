@@ -1,0 +1,324 @@
+// bellman_kernels.cu — sm_100a kernels of the backward Bellman stage.
+//
+// Compiled with -fmad=false: every written operation is rounded once, exactly as
+// include/bellman.h specifies; the only fused operations are the explicit fma() calls.
+// No tensor cores: the stage is a gather-and-reduce, not a contraction.
+#include <cstdint>
+
+#include "bellman_kernels.cuh"
+
+namespace bellman {
+
+namespace {
+
+constexpr int BLOCK = 256;
+
+// --- locate (include/bellman.h, "locate_d") ---------------------------------------------------
+__device__ __forceinline__ int locate_cell(const double *__restrict__ s, int n, int mode,
+                                           double inv_h, double off, double x) {
+    int cell;
+    if (mode == BELLMAN_LOCATE_UNIFORM) {
+        cell = __double2int_rd(fma(x, inv_h, off));   // floor, saturating
+    } else {
+        int lo = 0, hi = n;                            // #{ s[i] <= x }
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            if (__ldg(s + mid) <= x) lo = mid + 1; else hi = mid;
+        }
+        cell = lo - 1;
+    }
+    return min(max(cell, 0), n - 2);
+}
+
+template <int D>
+struct Prob {
+    const double *grid[D], *rinv[D], *Ta[D], *Tb[D], *Tc[D], *q[D];
+    double inv_h[D], off[D];
+    int mode[D], n[D];
+    const double *r;
+    __device__ __forceinline__ void load(const StageParams &sp, int prob) {
+#pragma unroll
+        for (int d = 0; d < D; ++d) {
+            const DimParams &dp = sp.dim[d];
+            n[d] = dp.n;
+            grid[d] = dp.grid + (size_t)prob * dp.n;
+            rinv[d] = dp.rinv + (size_t)prob * dp.n;
+            Ta[d] = dp.Ta + (size_t)prob * dp.n_a;
+            Tb[d] = dp.Tb ? dp.Tb + (size_t)prob * dp.n_b : nullptr;
+            Tc[d] = dp.Tc ? dp.Tc + (size_t)prob * sp.C : nullptr;
+            q[d] = dp.q + (size_t)prob * dp.n;
+            inv_h[d] = __ldg(dp.loc + 2 * prob);
+            off[d] = __ldg(dp.loc + 2 * prob + 1);
+            mode[d] = __ldg(dp.mode + prob);
+        }
+        r = sp.r + (size_t)prob * sp.C;
+    }
+};
+
+// one (state, control) evaluation: returns the interpolated J_{k+1}(x')
+template <int D>
+__device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams &sp,
+                                            const double *__restrict__ Jn, const double (&base)[D],
+                                            int c) {
+    double t[D];
+    long long o = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const double xq = pb.Tc[d] ? base[d] + __ldg(pb.Tc[d] + c) : base[d];
+        const int cell = locate_cell(pb.grid[d], pb.n[d], pb.mode[d], pb.inv_h[d], pb.off[d], xq);
+        t[d] = (xq - __ldg(pb.grid[d] + cell)) * __ldg(pb.rinv[d] + cell);
+        o += (long long)(cell - sp.dim[d].ext_lo) * sp.dim[d].stride;
+    }
+    double v[1 << D];
+#pragma unroll
+    for (int m = 0; m < (1 << D); ++m) {
+        long long oo = o;
+#pragma unroll
+        for (int d = 0; d < D; ++d)
+            if (m & (1 << d)) oo += sp.dim[d].stride;
+        v[m] = __ldg(Jn + oo);
+    }
+#pragma unroll
+    for (int d = 0; d < D; ++d)               // dimension 0 reduced first
+#pragma unroll
+        for (int m = 0; m < (1 << (D - 1 - d)); ++m)
+            v[m] = fma(t[d], v[2 * m + 1] - v[2 * m], v[2 * m]);
+    return v[0];
+}
+
+// decompose an owned-state linear index into global grid indices; returns the element offset of
+// the state inside the (extended) J arrays
+template <int D>
+__device__ __forceinline__ long long decompose(const StageParams &sp, long long s, int (&gi)[D]) {
+    long long o = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        const int on = sp.dim[d].own_n;
+        const int loc = (d == D - 1) ? (int)s : (int)(s % on);
+        s /= on;
+        gi[d] = loc + sp.dim[d].own_lo;
+        o += (long long)(gi[d] - sp.dim[d].ext_lo) * sp.dim[d].stride;
+    }
+    return o;
+}
+
+template <int D>
+__device__ __forceinline__ double state_terms(const Prob<D> &pb, const StageParams &sp,
+                                              const int (&gi)[D], double (&base)[D]) {
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        double b = __ldg(pb.Ta[d] + gi[sp.dim[d].src_a]);
+        if (pb.Tb[d]) b = b + __ldg(pb.Tb[d] + gi[sp.dim[d].src_b]);
+        base[d] = b;
+    }
+    double gs = __ldg(pb.q[sp.q_order[0]] + gi[sp.q_order[0]]);
+#pragma unroll
+    for (int m = 1; m < D; ++m) gs = gs + __ldg(pb.q[sp.q_order[m]] + gi[sp.q_order[m]]);
+    return gs;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_direct: one thread per state
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(BLOCK)
+k_stage_direct(const __grid_constant__ StageParams sp) {
+    const int prob = blockIdx.y;
+    const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    if (s >= sp.S_own) return;
+    Prob<D> pb;
+    pb.load(sp, prob);
+    int gi[D];
+    const long long o_self = decompose<D>(sp, s, gi);
+    double base[D];
+    const double gs = state_terms<D>(pb, sp, gi, base);
+    const double *__restrict__ Jn = sp.J_next + (size_t)prob * sp.S_ext;
+
+    double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
+    int arg = 0;
+#pragma unroll 2
+    for (int c = 0; c < sp.C; ++c) {
+        const double v = interp_at<D>(pb, sp, Jn, base, c);
+        const double tot = (gs + __ldg(pb.r + c)) + v;
+        if (tot < best) { best = tot; arg = c; }
+    }
+    sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
+    sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_splitc: L lanes share one state and split the control loop; lexicographic (value, index)
+// shuffle reduction keeps MATLAB's first-index tie rule.
+// ---------------------------------------------------------------------------------------------
+template <int D, int L>
+__global__ void __launch_bounds__(BLOCK)
+k_stage_splitc(const __grid_constant__ StageParams sp) {
+    const int prob = blockIdx.y;
+    const int lane = threadIdx.x % L;
+    long long s = ((long long)blockIdx.x * BLOCK + threadIdx.x) / L;
+    const bool live = s < sp.S_own;
+    if (!live) s = sp.S_own - 1;            // keep the whole warp in the shuffles
+    Prob<D> pb;
+    pb.load(sp, prob);
+    int gi[D];
+    const long long o_self = decompose<D>(sp, s, gi);
+    double base[D];
+    const double gs = state_terms<D>(pb, sp, gi, base);
+    const double *__restrict__ Jn = sp.J_next + (size_t)prob * sp.S_ext;
+
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int arg = 0x7fffffff;
+    for (int c = lane; c < sp.C; c += L) {
+        const double v = interp_at<D>(pb, sp, Jn, base, c);
+        const double tot = (gs + __ldg(pb.r + c)) + v;
+        if (tot < best) { best = tot; arg = c; }
+    }
+#pragma unroll
+    for (int w = L / 2; w >= 1; w >>= 1) {
+        const double ob = __shfl_xor_sync(0xffffffffu, best, w, L);
+        const int oa = __shfl_xor_sync(0xffffffffu, arg, w, L);
+        if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+    }
+    if (live && lane == 0) {
+        sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
+        sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// check sums (Solver_pos_att.m:273-285): sum(J) and sum(idx+1) over the owned states, in a fixed
+// (deterministic) order: per-thread strided partials -> block tree -> serial sum of block partials
+// ---------------------------------------------------------------------------------------------
+template <int D>
+__global__ void __launch_bounds__(BLOCK)
+k_check_partials(const __grid_constant__ StageParams sp, double *__restrict__ partials) {
+    __shared__ double sh[2][BLOCK / 32];
+    double sj = 0.0, si = 0.0;
+    const long long total = sp.S_own * sp.P;
+    for (long long g = (long long)blockIdx.x * BLOCK + threadIdx.x; g < total;
+         g += (long long)gridDim.x * BLOCK) {
+        const int prob = (int)(g / sp.S_own);
+        const long long s = g - (long long)prob * sp.S_own;
+        int gi[D];
+        const long long o = decompose<D>(sp, s, gi);
+        sj += sp.J_out[(size_t)prob * sp.S_ext + o];
+        si += (double)(sp.idx_out[(size_t)prob * sp.S_own + s] + 1);
+    }
+#pragma unroll
+    for (int w = 16; w >= 1; w >>= 1) {
+        sj += __shfl_xor_sync(0xffffffffu, sj, w);
+        si += __shfl_xor_sync(0xffffffffu, si, w);
+    }
+    if ((threadIdx.x & 31) == 0) { sh[0][threadIdx.x >> 5] = sj; sh[1][threadIdx.x >> 5] = si; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int w = 0; w < BLOCK / 32; ++w) { a += sh[0][w]; b += sh[1][w]; }
+        partials[2 * blockIdx.x] = a;
+        partials[2 * blockIdx.x + 1] = b;
+    }
+}
+
+__global__ void k_check_final(const double *__restrict__ partials, int n, double *__restrict__ out2) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double a = 0.0, b = 0.0;
+        for (int i = 0; i < n; ++i) { a += partials[2 * i]; b += partials[2 * i + 1]; }
+        out2[0] = a;
+        out2[1] = b;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// rollout (test/Dynamic_Solver.m:108-145,191-194): one thread per initial state
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ RolloutParams rp) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= rp.batch) return;
+    double x1 = rp.x0[2 * b], x2 = rp.x0[2 * b + 1];
+    double *X = rp.X_out + (size_t)b * 2 * rp.N;
+    double *U = rp.U_out + (size_t)b * rp.N;
+    const long long S = (long long)rp.n0 * rp.n1;
+    X[0] = x1;
+    X[1] = x2;
+    for (int k = 1; k <= rp.N - 1; ++k) {
+        const int st = rp.mode == 1 ? rp.ssu_stage : k;
+        const int32_t *__restrict__ id = rp.idx_all + (size_t)(st - 1) * S;
+        const int c0 = locate_cell(rp.grid0, rp.n0, rp.mode0, rp.inv_h0, rp.off0, x1);
+        const int c1 = locate_cell(rp.grid1, rp.n1, rp.mode1, rp.inv_h1, rp.off1, x2);
+        const double t0 = (x1 - rp.grid0[c0]) * rp.rinv0[c0];
+        const double t1 = (x2 - rp.grid1[c1]) * rp.rinv1[c1];
+        const long long o = c0 + (long long)c1 * rp.n0;
+        const double v00 = rp.u_values[id[o]], v10 = rp.u_values[id[o + 1]];
+        const double v01 = rp.u_values[id[o + rp.n0]], v11 = rp.u_values[id[o + rp.n0 + 1]];
+        const double a = fma(t0, v10 - v00, v00), bb = fma(t0, v11 - v01, v01);
+        const double u = fma(t1, bb - a, a);
+        U[k - 1] = u;
+        const double nx1 = (rp.A[0] * x1 + rp.A[2] * x2) + rp.B[0] * u;
+        const double nx2 = (rp.A[1] * x1 + rp.A[3] * x2) + rp.B[1] * u;
+        x1 = nx1;
+        x2 = nx2;
+        X[2 * k] = x1;
+        X[2 * k + 1] = x2;
+    }
+    U[rp.N - 1] = 0.0;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_stage_direct(const StageParams &sp, cudaStream_t st) {
+    const dim3 grid((unsigned)((sp.S_own + BLOCK - 1) / BLOCK), (unsigned)sp.P);
+    switch (sp.D) {
+        case 2: k_stage_direct<2><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 3: k_stage_direct<3><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 4: k_stage_direct<4><<<grid, BLOCK, 0, st>>>(sp); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+template <int D>
+static cudaError_t splitc_D(const StageParams &sp, int L, cudaStream_t st) {
+    const long long threads = sp.S_own * L;
+    const dim3 grid((unsigned)((threads + BLOCK - 1) / BLOCK), (unsigned)sp.P);
+    switch (L) {
+        case 2: k_stage_splitc<D, 2><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 4: k_stage_splitc<D, 4><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 8: k_stage_splitc<D, 8><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 16: k_stage_splitc<D, 16><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 32: k_stage_splitc<D, 32><<<grid, BLOCK, 0, st>>>(sp); break;
+        default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stage_splitc(const StageParams &sp, int lanes_per_state, cudaStream_t st) {
+    switch (sp.D) {
+        case 2: return splitc_D<2>(sp, lanes_per_state, st);
+        case 3: return splitc_D<3>(sp, lanes_per_state, st);
+        case 4: return splitc_D<4>(sp, lanes_per_state, st);
+        default: return cudaErrorInvalidValue;
+    }
+}
+
+cudaError_t launch_check_sums(const StageParams &sp, double *d_partials, int n_partials,
+                              double *d_out2, cudaStream_t st) {
+    switch (sp.D) {
+        case 2: k_check_partials<2><<<n_partials, BLOCK, 0, st>>>(sp, d_partials); break;
+        case 3: k_check_partials<3><<<n_partials, BLOCK, 0, st>>>(sp, d_partials); break;
+        case 4: k_check_partials<4><<<n_partials, BLOCK, 0, st>>>(sp, d_partials); break;
+        default: return cudaErrorInvalidValue;
+    }
+    k_check_final<<<1, 32, 0, st>>>(d_partials, n_partials, d_out2);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout(const RolloutParams &rp, cudaStream_t st) {
+    k_rollout<<<(rp.batch + 127) / 128, 128, 0, st>>>(rp);
+    return cudaGetLastError();
+}
+
+// window kernel: see bellman_window.cu
+}  // namespace bellman

@@ -1,0 +1,43 @@
+// bellman_kernels.cuh — launcher prototypes (implemented in bellman_kernels.cu, sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "bellman_internal.h"
+
+namespace bellman {
+
+// generic D = 2..4 stage: one thread per state, all controls looped in registers, J_{k+1}
+// gathered through L1/L2.  Always applicable.
+cudaError_t launch_stage_direct(const StageParams &sp, cudaStream_t st);
+
+// D = 2 stage with controls split across the lanes of a warp-group and a lexicographic
+// (value, index) shuffle reduction: for grids too small to fill the GPU with one thread per state.
+cudaError_t launch_stage_splitc(const StageParams &sp, int lanes_per_state, cudaStream_t st);
+
+// D = 2 stage with the J_{k+1} neighbourhood of a state tile staged in shared memory by TMA.
+struct WindowLaunch {
+    WindowConfig cfg;
+    const void *tmap_next;   // device-resident CUtensorMap (128 B) describing J_next
+};
+cudaError_t launch_stage_window(const StageParams &sp, const WindowLaunch &wl, cudaStream_t st);
+size_t window_smem_bytes(const WindowConfig &cfg);
+
+// deterministic sum(J) and sum(idx+1) over the owned states (pos-att early-stop check)
+cudaError_t launch_check_sums(const StageParams &sp, double *d_partials, int n_partials,
+                              double *d_out2, cudaStream_t st);
+
+// batched rollout, one thread per initial state
+struct RolloutParams {
+    const double *grid0, *rinv0, *grid1, *rinv1;
+    double inv_h0, off0, inv_h1, off1;
+    int mode0, mode1, n0, n1, N, C, batch, mode, ssu_stage;
+    const int32_t *idx_all;   // [N][S]
+    const double *u_values;   // [C]
+    double A[4], B[2];
+    const double *x0;         // [batch][2]
+    double *X_out;            // [batch][N][2]
+    double *U_out;            // [batch][N]
+};
+cudaError_t launch_rollout(const RolloutParams &rp, cudaStream_t st);
+
+}  // namespace bellman

@@ -1,0 +1,337 @@
+"""Host-side mirror of the reference's classdef surface for the sweep path.
+
+Same class names, property names, method names and argument meaning as the MATLAB classes; the
+stage loop itself runs in libbellman.so (CUDA, sm_100a).  The MATLAB originals of these facades
+live in ``matlab/`` and call the same C ABI through ``bellman_mex``.
+
+  Dynamic_Solver   test/Dynamic_Solver.m        run(), get_optimal_path(X0, mode, ssu_num)
+  Solver_position  position-control/Solver_position.m   simplified_run()
+  Solver_attitude  attitude-control/Solver_attitude.m   simplified_run()
+  Solver_pos_att   pos-att/Solver_pos_att.m     simplified_run(), calculate_one_channel_U_Opt()
+
+Deviations from the shipped reference (all documented in SURVEY.md 2.3):
+  * everything is fp64 (the test/test_coder.m / test/obj_1.mat convention); the ``single`` casts
+    of Dynamic_Solver.m:69 and Solver_pos_att.m:265,800 are not emulated;
+  * ``J_star`` is filled for every stage (the current Dynamic_Solver.m allocates but never
+    writes it); ``get_optimal_path`` honours a user-supplied X0 (README.md:22);
+  * ``idsum50_prev`` starts at 0 (Solver_pos_att.m:277 reads it undefined).
+"""
+import numpy as np
+
+from . import tables
+from ._lib import KERNEL_AUTO, Sweep
+
+
+def _unflatten(a, shape):
+    """[S] column-major -> ndarray of ``shape`` (MATLAB layout)."""
+    return np.asarray(a).reshape(shape, order="F")
+
+
+class NearestPolicy:
+    """Stand-in for ``griddedInterpolant({s1,..}, values, 'nearest')`` (Solver_position.m:144-146,
+    Solver_attitude.m:249-251, Solver_pos_att.m:851-861): nearest node, clamped outside."""
+
+    def __init__(self, gridvecs, values):
+        self.GridVectors = [np.asarray(g, dtype=np.float64) for g in gridvecs]
+        self.Values = np.asarray(values)
+
+    def __call__(self, *q):
+        idx = []
+        for s, x in zip(self.GridVectors, q):
+            x = np.asarray(x, dtype=np.float64)
+            i = np.clip(np.searchsorted(s, x, side="right") - 1, 0, len(s) - 2)
+            idx.append(i + ((x - s[i]) >= (s[i + 1] - x)))
+        return self.Values[tuple(idx)]
+
+
+# ----------------------------------------------------------------------------------------------
+class Dynamic_Solver:
+    """test/Dynamic_Solver.m — Kirk ch.3 two-state linear regulator by dynamic programming."""
+
+    def __init__(self):
+        # constructor defaults, Dynamic_Solver.m:47-64
+        self.checkstagesXJF = 0          # debug slices hard-code indices 50:57/105
+        self.Q = np.array([[0.25, 0.0], [0.0, 0.05]])
+        self.A = np.array([[0.9974, 0.0539], [-0.1078, 1.1591]])
+        self.B = np.array([[0.0013], [0.0539]])
+        self.R = 0.05
+        self.H = np.zeros((0, 0))
+        self.N = 200
+        self.S = 2
+        self.C = 1
+        self.dx = 100
+        self.du = 1000
+        self.x_max = 3.0
+        self.x_min = -2.5
+        self.u_max = 10.0
+        self.u_min = -40.0
+        self.s_r = None
+        self.u_star = None
+        self.u_star_idx = None
+        self.J_star = None
+        self.X1_mesh = None
+        self.X2_mesh = None
+        # build options (not in the reference)
+        self.store_J_star = True         # keep every stage's J / u_star on the host as the reference does
+        self.device = -1
+        self.kernel = KERNEL_AUTO
+        self.verbose = False
+        self._sweep = None
+        self._desc = None
+
+    def _build(self):
+        d = tables.kirk_desc(self.A, self.B, self.Q, self.R, self.N, self.x_min, self.x_max, self.dx,
+                             self.u_min, self.u_max, self.du,
+                             store_J_all=self.store_J_star, store_idx_all=True)
+        self._desc = d
+        self.s_r = d.meta["s_r"]
+        self.U_mesh = d.meta["U_mesh"]
+        self.X1_mesh, self.X2_mesh = np.meshgrid(self.s_r, self.s_r, indexing="ij")
+        return d
+
+    def run(self):
+        """Dynamic_Solver.m:66-105: backward sweep k = 1..N-1, u_star(:,:,N-k) = U_mesh(idx)."""
+        d = self._build()
+        if self._sweep is not None:
+            self._sweep.close()
+        sw = self._sweep = Sweep(d, device=self.device)
+        sw.run(d.N - 1, kernel=self.kernel, sync_each_stage=self.verbose)
+        if self.verbose:
+            st = sw.stats()
+            print("sweep: %d stages in %.3f ms (%s kernel)" % (d.N - 1, st["ms"], sw.last_kernel))
+        shape = (d.n[0], d.n[1])
+        N = d.N
+        if self.store_J_star:
+            self.J_star = np.zeros(shape + (N,))
+            self.u_star = np.zeros(shape + (N,))
+            for k in range(1, N + 1):
+                self.J_star[:, :, k - 1] = _unflatten(sw.get_J(k)[0], shape)
+            for k in range(1, N):
+                self.u_star[:, :, k - 1] = self.U_mesh[_unflatten(sw.get_idx(k)[0], shape)]
+        self.u_star_idx = _unflatten(sw.get_idx(1)[0], shape) + 1      # 1-based like MATLAB
+        self.F_Values = _unflatten(sw.get_J(1)[0], shape)               # obj.F.Values after the loop
+        return self
+
+    def get_optimal_path(self, X0=None, mode="Nssu", ssu_num=1):
+        """Dynamic_Solver.m:108-145: forward rollout with linear interpolation of u_star values.
+        X0 may be one state [2] or a batch [batch, 2].  Returns (X [.., 2, N], U [.., N])."""
+        if self._sweep is None or self._sweep.current_stage != 1:
+            raise RuntimeError("run(obj) must complete before get_optimal_path")
+        if X0 is None:
+            X0 = [2.0, 1.0]                                             # :110
+        x0 = np.asarray(X0, dtype=np.float64)
+        single = x0.size == 2
+        x0 = x0.reshape(-1, 2)
+        X, U = self._sweep.rollout(self.A, self.B, self.U_mesh, x0, mode=1 if mode == "ssu" else 0,
+                                   ssu_stage=int(ssu_num))
+        X = np.swapaxes(X, 1, 2)                                        # [batch, 2, N]
+        return (X[0], U[0]) if single else (X, U)
+
+    @staticmethod
+    def compare_data(obj1, obj2):
+        """Dynamic_Solver.m:266-280: bit-exact comparison of two saved runs."""
+        if obj1.J_star is None or obj2.J_star is None or obj1.J_star.size == 0 or obj2.J_star.size == 0:
+            raise ValueError("stop throwing empty data at me")
+        return bool(np.array_equal(obj1.J_star, obj2.J_star))
+
+
+# ----------------------------------------------------------------------------------------------
+class _AxisSolverBase:
+    """Shared by Solver_position / Solver_attitude: three 2-D axes swept as one batched problem."""
+
+    device = -1
+    kernel = KERNEL_AUTO
+    use_graph = True
+
+    def _axis_descs(self):
+        raise NotImplementedError
+
+    def simplified_run(self, n_stages=None):
+        descs = self._axis_descs()
+        d = tables.stack_problems(descs)
+        self._desc = d
+        sw = self._sweep = Sweep(d, device=self.device)
+        todo = d.N - 1 if n_stages is None else int(n_stages)
+        sw.run(todo, kernel=self.kernel, use_graph=self.use_graph)
+        J = sw.get_J()
+        idx = sw.get_idx()
+        shape = tuple(d.n)
+        self.F_Values = [_unflatten(J[p], shape) for p in range(d.P)]
+        self.U_idx = [_unflatten(idx[p], shape) + 1 for p in range(d.P)]
+        pol = []
+        for p in range(d.P):
+            grids = [d.grid[k][p] for k in range(d.D)]
+            pol.append(NearestPolicy(grids, np.asarray(self.U_vector)[self.U_idx[p] - 1]))
+        self.U1_Opt, self.U2_Opt, self.U3_Opt = pol
+        self.sweep_stats = sw.stats()
+        return self
+
+
+class Solver_position(_AxisSolverBase):
+    """position-control/Solver_position.m — three independent (x, v) axes, three thrust levels."""
+
+    def __init__(self):
+        # Solver_position.m:46-92
+        self.v_min, self.v_max = -0.5, 0.5
+        self.x_min, self.x_max = -0.5, 0.5
+        self.n_mesh_v = 200
+        self.n_mesh_x = 200
+        self.Mass = 4.16
+        self.Qx1 = self.Qx2 = self.Qx3 = 6.0
+        self.Qv1 = self.Qv2 = self.Qv3 = 6.0
+        self.R1 = self.R2 = self.R3 = 0.1
+        self.T_final = 30.0
+        self.h = 0.005
+        self.N_stage = int(np.ceil(self.T_final / self.h))             # :75-79 (always "ceil")
+        self.defaultX0 = np.zeros(6)
+        self.U_vector = np.array([-0.13, 0.0, 0.13]) * 2               # :84
+        self.U1_Opt = self.U2_Opt = self.U3_Opt = None
+
+    def _axis_descs(self):
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        qx = (self.Qx1, self.Qx2, self.Qx3)
+        qv = (self.Qv1, self.Qv2, self.Qv3)
+        r = (self.R1, self.R2, self.R3)
+        ds = [tables.position_axis_desc(self.x_min, self.x_max, self.n_mesh_x, self.v_min, self.v_max,
+                                        self.n_mesh_v, self.U_vector, self.Mass, qx[a], qv[a], r[a],
+                                        self.h, self.N_stage) for a in range(3)]
+        self.n_mesh_x, self.n_mesh_v = ds[0].n                         # :100,:104
+        return ds
+
+
+class Solver_attitude(_AxisSolverBase):
+    """attitude-control/Solver_attitude.m — simplified_run: three (w, theta) axes, three torques."""
+
+    def __init__(self):
+        # Solver_attitude.m:103-193
+        self.w_min = -tables.deg2rad(50.0)
+        self.w_max = -tables.deg2rad(-50.0)
+        self.n_mesh_w = 1000
+        self.yaw_min, self.yaw_max = -30.0, 30.0
+        self.pitch_min, self.pitch_max = -20.0, 20.0
+        self.roll_min, self.roll_max = -35.0, 35.0
+        self.n_mesh_q = 10
+        self.n_mesh_t = 300
+        i1, i2, i3 = 0.02836 + 0.00016, 0.026817 + 0.00150, 0.023 + 0.00150
+        i4, i5, i6 = -0.0000837, 0.000014, -0.00029
+        self.InertiaM = np.array([[i1, i4, i5], [i4, i2, i6], [i5, i6, i3]])
+        self.Q1 = self.Q2 = self.Q3 = 6.0
+        self.Q4 = self.Q5 = self.Q6 = 6.0
+        self.R1 = self.R2 = self.R3 = 4.0
+        self.Qt1, self.Qt2, self.Qt3 = self.Q4, self.Q5, self.Q6
+        self.T_final = 30.0
+        self.h = 0.005
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        self.J1, self.J2, self.J3 = (self.InertiaM.ravel(order="F")[k] for k in (0, 4, 8))
+        self.U_vector = np.array([-0.11, 0.0, 0.11])
+        self.U1_Opt = self.U2_Opt = self.U3_Opt = None
+
+    def _axis_descs(self):
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        ang = ((self.yaw_min, self.yaw_max), (self.pitch_min, self.pitch_max), (self.roll_min, self.roll_max))
+        qw = (self.Q1, self.Q2, self.Q3)
+        qt = (self.Qt1, self.Qt2, self.Qt3)
+        r = (self.R1, self.R2, self.R3)
+        jj = (self.J1, self.J2, self.J3)
+        return [tables.attitude_axis_desc(self.w_min, self.w_max, self.n_mesh_w, ang[a][0], ang[a][1],
+                                          self.n_mesh_t, self.U_vector, jj[a], qw[a], qt[a], r[a],
+                                          self.h, self.N_stage) for a in range(3)]
+
+
+# ----------------------------------------------------------------------------------------------
+class Solver_pos_att:
+    """pos-att/Solver_pos_att.m — coupled position+attitude channels on a 4-D (x, v, theta, w)
+    grid with 9 thruster on/off combinations (simplified_run / calculate_one_channel_U_Opt)."""
+
+    def __init__(self):
+        # Solver_pos_att.m:96-195
+        self.v_min, self.v_max, self.n_mesh_v = -0.1, 0.1, 30
+        self.x_min, self.x_max, self.n_mesh_x = -0.2, 0.2, 30
+        self.w_min, self.w_max, self.n_mesh_w = tables.deg2rad(-2.0), tables.deg2rad(2.0), 15
+        self.theta1_min, self.theta1_max = -5.0, 5.0
+        self.theta2_min, self.theta2_max = -6.0, 6.0
+        self.theta3_min, self.theta3_max = -7.0, 7.0
+        self.n_mesh_t = 20
+        self.Mass = 4.16
+        i1, i2, i3 = 0.02836 + 0.00016, 0.026817 + 0.00150, 0.023 + 0.00150
+        i4, i5, i6 = -0.0000837, 0.000014, -0.00029
+        self.InertiaM = np.array([[i1, i4, i5], [i4, i2, i6], [i5, i6, i3]])
+        self.J1, self.J2, self.J3 = (self.InertiaM.ravel(order="F")[k] for k in (0, 4, 8))
+        self.Qx1 = self.Qx2 = self.Qx3 = 6.0
+        self.Qv1 = self.Qv2 = self.Qv3 = 6.0
+        self.Qt1 = self.Qt2 = self.Qt3 = 0.5
+        self.Qw1 = self.Qw2 = self.Qw3 = 0.5
+        self.R1 = self.R2 = self.R3 = 0.1
+        self.T_final = 10.0
+        self.h = 0.005
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        self.defaultX0 = np.zeros(9)
+        T = 0.13
+        self.T_dist = 9.65e-2
+        on, off = np.array([0.0, T]), -np.array([0.0, T])
+        self.F_Thr0 = on.copy(); self.F_Thr1 = on.copy(); self.F_Thr6 = off.copy(); self.F_Thr7 = off.copy()
+        self.F_Thr2 = on.copy(); self.F_Thr3 = on.copy(); self.F_Thr8 = off.copy(); self.F_Thr9 = off.copy()
+        self.F_Thr4 = on.copy(); self.F_Thr5 = on.copy(); self.F_Thr10 = off.copy(); self.F_Thr11 = off.copy()
+        self.device = -1
+        self.kernel = KERNEL_AUTO
+        self.check_period = 50          # Solver_pos_att.m:273
+        self.check_tol = 1e-2           # :269
+        self.controllers = {}
+
+    def _grids(self, ch):
+        th = ((self.theta1_min, self.theta1_max), (self.theta2_min, self.theta2_max),
+              (self.theta3_min, self.theta3_max))[ch]
+        sl = tables.sym_linspace_pos_att
+        return (sl(self.x_min, self.x_max, self.n_mesh_x), sl(self.v_min, self.v_max, self.n_mesh_v),
+                sl(tables.deg2rad(th[0]), tables.deg2rad(th[1]), self.n_mesh_t),
+                sl(self.w_min, self.w_max, self.n_mesh_w))
+
+    def channel_desc(self, ch, failure=False):
+        """Descriptor of channel 0/1/2 = x/y/z (Solver_pos_att.m:217-233); failure=True is the
+        x-channel thruster-0-failed controller (:236-240)."""
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        thr = ((self.F_Thr0, self.F_Thr1, self.F_Thr6, self.F_Thr7),
+               (self.F_Thr2, self.F_Thr3, self.F_Thr8, self.F_Thr9),
+               (self.F_Thr4, self.F_Thr5, self.F_Thr10, self.F_Thr11))[ch]
+        if failure:
+            thr = (np.array([0.0]),) + thr[1:]
+        Q = ((self.Qx1, self.Qv1, self.Qt1, self.Qw1, self.R1), (self.Qx2, self.Qv2, self.Qt2, self.Qw2, self.R2),
+             (self.Qx3, self.Qv3, self.Qt3, self.Qw3, self.R3))[ch]
+        J = (self.J2, self.J3, self.J1)[ch]
+        s_x, s_v, s_t, s_w = self._grids(ch)
+        return tables.pos_att_channel_desc(s_x, s_v, s_t, s_w, *thr, Q[0], Q[1], Q[2], Q[3], Q[4], J,
+                                           self.Mass, self.T_dist, self.h, self.N_stage)
+
+    def calculate_one_channel_U_Opt(self, ch, failure=False, file_name=None, n_stages=None):
+        """Solver_pos_att.m:244-297 for one channel; returns the controller dict that the reference
+        saves (F_gI values + grid vectors, U_Optimal_id (1-based), f*_allcomb)."""
+        d = self.channel_desc(ch, failure)
+        sw = Sweep(d, device=self.device)
+        todo = d.N - 1 if n_stages is None else int(n_stages)
+        sw.run(todo, kernel=self.kernel, check_period=self.check_period, check_tol=self.check_tol)
+        shape = tuple(d.n)
+        ctl = {
+            "GridVectors": [d.grid[k][0] for k in range(4)],
+            "F_gI_Values": _unflatten(sw.get_J()[0], shape),
+            "U_Optimal_id": _unflatten(sw.get_idx()[0], shape) + 1,
+            "f0_allcomb": d.meta["f0_allcomb"], "f1_allcomb": d.meta["f1_allcomb"],
+            "f6_allcomb": d.meta["f6_allcomb"], "f7_allcomb": d.meta["f7_allcomb"],
+            "stop_stage": sw.current_stage, "check_log": sw.check_log(), "stats": sw.stats(),
+        }
+        sw.close()
+        if file_name:
+            import scipy.io
+            scipy.io.savemat(file_name, {k: v for k, v in ctl.items() if k not in ("stats",)})
+        return ctl
+
+    def simplified_run(self, save=False, failure_mode=True, n_stages=None):
+        """Solver_pos_att.m:197-242: x, y, z channels, then the x-channel failure mode."""
+        names = ("channel_x_controller_1", "channel_y_controller_1", "channel_z_controller_1")
+        for ch in range(3):
+            self.controllers[names[ch]] = self.calculate_one_channel_U_Opt(
+                ch, file_name=names[ch] + ".mat" if save else None, n_stages=n_stages)
+        if failure_mode:
+            nm = "channel_x_controller_1_failure"
+            self.controllers[nm] = self.calculate_one_channel_U_Opt(
+                0, failure=True, file_name=nm + ".mat" if save else None, n_stages=n_stages)
+        return self

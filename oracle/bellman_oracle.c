@@ -98,6 +98,85 @@ static void dimtab_init(dimtab *g, const double *s, int n, int mode)
     g->off = -(s[0] * g->inv_h);
 }
 
+/* one state of one problem: the normative operation order of include/bellman.h */
+static void eval_state(const bellman_desc *d, const dimtab *g, const double *const *Ta,
+                       const double *const *Tb, const double *const *Tc, const double *const *q,
+                       const double *r, const int64_t *stride, const double *Jn, int64_t s,
+                       double *J_out, int32_t *idx_out)
+{
+    const int D = d->D, C = d->C;
+    int i[MAXD] = {0, 0, 0, 0};
+    int64_t rem = s;
+    for (int k = 0; k < D; ++k) { i[k] = (int)(rem % d->n[k]); rem /= d->n[k]; }
+    double base[MAXD];
+    for (int k = 0; k < D; ++k) {
+        base[k] = Ta[k][i[d->src_a[k]]];
+        if (Tb[k]) base[k] = base[k] + Tb[k][i[d->src_b[k]]];
+    }
+    double gs = q[d->q_order[0]][i[d->q_order[0]]];
+    for (int m = 1; m < D; ++m) gs = gs + q[d->q_order[m]][i[d->q_order[m]]];
+
+    double best = INFINITY;
+    int arg = 0;
+    for (int c = 0; c < C; ++c) {
+        int cell[MAXD];
+        double t[MAXD];
+        int64_t o = 0;
+        for (int k = 0; k < D; ++k) {
+            const double xq = Tc[k] ? base[k] + Tc[k][c] : base[k];
+            cell[k] = locate(&g[k], xq, &t[k]);
+            o += cell[k] * stride[k];
+        }
+        double v[1 << MAXD];
+        for (int m = 0; m < (1 << D); ++m) {
+            int64_t oo = o;
+            for (int k = 0; k < D; ++k) if (m & (1 << k)) oo += stride[k];
+            v[m] = Jn[oo];
+        }
+        for (int k = 0; k < D; ++k)                       /* dimension 0 reduced first */
+            for (int m = 0; m < (1 << (D - 1 - k)); ++m)
+                v[m] = fma(t[k], v[2 * m + 1] - v[2 * m], v[2 * m]);
+        const double tot = (gs + r[c]) + v[0];
+        if (tot < best) { best = tot; arg = c; }          /* strict: first index wins ties */
+    }
+    *J_out = best;
+    *idx_out = arg;
+}
+
+static void problem_tables(const bellman_desc *d, const int32_t *modes, int p, dimtab *g,
+                           const double **Ta, const double **Tb, const double **Tc, const double **q)
+{
+    for (int k = 0; k < d->D; ++k) {
+        dimtab_init(&g[k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * d->D + k]);
+        Ta[k] = d->Ta[k] + (size_t)p * d->n[d->src_a[k]];
+        Tb[k] = (d->Tb[k] && d->src_b[k] >= 0) ? d->Tb[k] + (size_t)p * d->n[d->src_b[k]] : NULL;
+        Tc[k] = d->Tc[k] ? d->Tc[k] + (size_t)p * d->C : NULL;
+        q[k] = d->q[k] + (size_t)p * d->n[k];
+    }
+}
+
+/*
+ * Evaluate only the listed states (size-independent spot check at BASELINE's full grid sizes):
+ * states[m] is a linear state index of problem `p`; J_next is that problem's [S] array.
+ */
+int oracle_stage_points(const bellman_desc *d, const int32_t *modes, int p, const double *J_next,
+                        const int64_t *states, int64_t n_states, double *J_out, int32_t *idx_out)
+{
+    const int D = d->D;
+    if (D < 1 || D > MAXD) return -1;
+    int64_t stride[MAXD], S = 1;
+    for (int k = 0; k < D; ++k) { stride[k] = S; S *= d->n[k]; }
+    dimtab g[MAXD];
+    const double *Ta[MAXD], *Tb[MAXD], *Tc[MAXD], *q[MAXD];
+    problem_tables(d, modes, p, g, Ta, Tb, Tc, q);
+    const double *r = d->r + (size_t)p * d->C;
+#pragma omp parallel for schedule(static)
+    for (int64_t m = 0; m < n_states; ++m)
+        eval_state(d, g, Ta, Tb, Tc, q, r, stride, J_next, states[m], &J_out[m], &idx_out[m]);
+    for (int k = 0; k < D; ++k) free(g[k].rinv);
+    return 0;
+}
+
 /*
  * One backward stage over all P problems.  J_next / J_out are [P][S] column-major (dim 0 fastest),
  * idx_out is [P][S] 0-based.  own_lo/own_hi restrict the states computed along part_dim (used by
@@ -119,13 +198,7 @@ int oracle_stage(const bellman_desc *d, const int32_t *modes, const double *J_ne
     for (int p = 0; p < d->P; ++p) {
         dimtab g[MAXD];
         const double *Ta[MAXD], *Tb[MAXD], *Tc[MAXD], *q[MAXD];
-        for (int k = 0; k < D; ++k) {
-            dimtab_init(&g[k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * D + k]);
-            Ta[k] = d->Ta[k] + (size_t)p * d->n[d->src_a[k]];
-            Tb[k] = (d->Tb[k] && d->src_b[k] >= 0) ? d->Tb[k] + (size_t)p * d->n[d->src_b[k]] : NULL;
-            Tc[k] = d->Tc[k] ? d->Tc[k] + (size_t)p * C : NULL;
-            q[k] = d->q[k] + (size_t)p * d->n[k];
-        }
+        problem_tables(d, modes, p, g, Ta, Tb, Tc, q);
         const double *r = d->r + (size_t)p * C;
         const double *Jn = J_next + (size_t)p * S;
         double *Jo = J_out + (size_t)p * S;
@@ -133,44 +206,11 @@ int oracle_stage(const bellman_desc *d, const int32_t *modes, const double *J_ne
 
 #pragma omp parallel for schedule(static)
         for (int64_t s = 0; s < S; ++s) {
-            int i[MAXD];
-            int64_t rem = s;
-            for (int k = 0; k < D; ++k) { i[k] = (int)(rem % d->n[k]); rem /= d->n[k]; }
-            if (part_dim >= 0 && (i[part_dim] < own_lo || i[part_dim] >= own_hi)) continue;
-
-            double base[MAXD];
-            for (int k = 0; k < D; ++k) {
-                base[k] = Ta[k][i[d->src_a[k]]];
-                if (Tb[k]) base[k] = base[k] + Tb[k][i[d->src_b[k]]];
+            if (part_dim >= 0) {
+                const int ip = (int)((s / stride[part_dim]) % d->n[part_dim]);
+                if (ip < own_lo || ip >= own_hi) continue;
             }
-            double gs = q[d->q_order[0]][i[d->q_order[0]]];
-            for (int m = 1; m < D; ++m) gs = gs + q[d->q_order[m]][i[d->q_order[m]]];
-
-            double best = INFINITY;
-            int arg = 0;
-            for (int c = 0; c < C; ++c) {
-                int cell[MAXD];
-                double t[MAXD];
-                int64_t o = 0;
-                for (int k = 0; k < D; ++k) {
-                    const double xq = Tc[k] ? base[k] + Tc[k][c] : base[k];
-                    cell[k] = locate(&g[k], xq, &t[k]);
-                    o += cell[k] * stride[k];
-                }
-                double v[1 << MAXD];
-                for (int m = 0; m < (1 << D); ++m) {
-                    int64_t oo = o;
-                    for (int k = 0; k < D; ++k) if (m & (1 << k)) oo += stride[k];
-                    v[m] = Jn[oo];
-                }
-                for (int k = 0; k < D; ++k)                       /* dimension 0 reduced first */
-                    for (int m = 0; m < (1 << (D - 1 - k)); ++m)
-                        v[m] = fma(t[k], v[2 * m + 1] - v[2 * m], v[2 * m]);
-                const double tot = (gs + r[c]) + v[0];
-                if (tot < best) { best = tot; arg = c; }
-            }
-            Jo[s] = best;
-            Io[s] = arg;
+            eval_state(d, g, Ta, Tb, Tc, q, r, stride, Jn, s, &Jo[s], &Io[s]);
         }
         for (int k = 0; k < D; ++k) free(g[k].rinv);
     }

@@ -150,3 +150,19 @@ def rollout(d, idx_all, A, B, u_values, x0, mode=0, ssu_stage=1, modes=None):
 
 def num_threads():
     return int(lib().oracle_num_threads())
+
+
+def stage_points(d, J_next_p, states, p=0, modes=None):
+    """Evaluate only the listed linear state indices of problem ``p``.  Returns (J, idx0)."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    Jn = _arr(J_next_p).ravel()
+    st = np.ascontiguousarray(states, dtype=np.int64)
+    Jo = np.zeros(len(st))
+    Io = np.zeros(len(st), dtype=np.int32)
+    rc = lib().oracle_stage_points(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(p),
+                                   Jn.ctypes.data_as(_dp), st.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   C.c_int64(len(st)), Jo.ctypes.data_as(_dp),
+                                   Io.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return Jo, Io

@@ -1,0 +1,76 @@
+"""The C-ABI library loads without a GPU, exports every symbol include/bellman.h declares, and its
+host-only entry points work.  No compute calls here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    src = open(os.path.join(ROOT, "include", "bellman.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bellman_[a-z_0-9A-Z]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol(bellman):
+    lib = ctypes.CDLL(bellman.LIB_PATH)
+    syms = declared_symbols()
+    assert len(syms) >= 19
+    for s in syms:
+        assert hasattr(lib, s), f"libbellman.so lacks {s}"
+    assert sorted(bellman.EXPORTS) == syms
+    assert lib.bellman_version() == 1
+
+
+def test_struct_sizes_match(bellman):
+    """bad struct_size must be rejected (ABI versioning)."""
+    from bellman_b200 import _lib
+    d = bellman.Dynamic_Solver()
+    d.dx, d.du, d.N = 8, 5, 4
+    desc = d._build()
+    cd, keep = _lib.to_cdesc(desc)
+    cd.struct_size = 12
+    modes = np.zeros(2, dtype=np.int32)
+    assert _lib.load().bellman_query_locate(ctypes.byref(cd), modes.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))) == -1
+
+
+def test_bad_descriptors_are_rejected(bellman):
+    d = bellman.Dynamic_Solver()
+    d.dx, d.du, d.N = 8, 5, 4
+    desc = d._build()
+    desc.grid[0] = desc.grid[0][:, ::-1].copy()      # not increasing
+    with pytest.raises(bellman.BellmanError):
+        bellman.query_locate(desc)
+
+
+def test_slab_plan_covers_reach(bellman, oracle_lib):
+    """ext range of each rank must contain every cell its owned states touch (checked by brute force)."""
+    d = bellman.Dynamic_Solver()
+    d.dx, d.du, d.N = 64, 40, 4
+    desc = d._build()
+    for nranks in (2, 3, 4):
+        slabs = bellman.plan_slabs(desc, 1, nranks)
+        assert slabs[0][0] == 0 and slabs[-1][1] == 64
+        for r, (lo, hi, elo, ehi) in enumerate(slabs):
+            assert 0 <= elo <= lo < hi <= ehi <= 64
+            if r:
+                assert lo == slabs[r - 1][1]
+            # brute force: x'_2 for all (i, j in [lo,hi), c)
+            x2 = (desc.Ta[1][0][:, None] + desc.Tb[1][0][None, lo:hi])[:, :, None] + desc.Tc[1][0][None, None, :]
+            s = desc.grid[1][0]
+            inv_h = (len(s) - 1) / (s[-1] - s[0])
+            cell = np.clip(np.floor(x2 * inv_h - s[0] * inv_h), 0, len(s) - 2).astype(int)
+            assert cell.min() >= elo and cell.max() + 2 <= ehi
+
+
+@pytest.mark.skipif(os.path.exists("/dev/nvidiactl"), reason="box has a GPU")
+def test_create_fails_loudly_without_gpu(bellman):
+    d = bellman.Dynamic_Solver()
+    d.dx, d.du, d.N = 8, 5, 4
+    with pytest.raises(bellman.BellmanError) as ei:
+        d.run()
+    assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)

@@ -1,0 +1,211 @@
+"""Parity tests proper: the CUDA path (through the C ABI) against the CPU oracle on the same
+inputs.  Bar: J bit-exact and argmin index exact against oracle/bellman_oracle.c (same normative
+arithmetic), u_star exact and J <= 1e-12 relative against the reference's golden obj_1.mat."""
+import numpy as np
+import pytest
+
+from conftest import to_grid
+
+pytestmark = pytest.mark.gpu
+
+KERNELS = {"direct": 1, "splitc": 3, "auto": 0}
+
+
+def golden_desc(bellman, g):
+    return bellman.tables.kirk_desc(g["A"], g["B"], g["Q"], g["R"], g["N"], g["x_min"], g["x_max"], g["dx"],
+                                    g["u_min"], g["u_max"], g["du"])
+
+
+def assert_stage_equal(Jg, Ig, Jo, Io, what):
+    assert np.array_equal(Ig, Io), f"{what}: argmin differs at {np.sum(Ig != Io)} of {Ig.size} states"
+    assert np.array_equal(Jg, Jo), f"{what}: J differs, max rel {np.max(np.abs(Jg - Jo)) / np.max(np.abs(Jo))}"
+
+
+@pytest.mark.parametrize("kernel", ["direct", "splitc", "auto"])
+def test_golden_full_sweep(bellman, oracle_lib, golden, kernel):
+    d = golden_desc(bellman, golden)
+    N, dx = golden["N"], golden["dx"]
+    ora = oracle_lib.sweep(d, keep_all=True)
+    sw = bellman.Sweep(d)
+    sw.run(N - 1, kernel=KERNELS[kernel])
+    assert sw.current_stage == 1
+    U = d.meta["U_mesh"]
+    for k in range(1, N):
+        Jg, Ig = sw.get_J(k), sw.get_idx(k)
+        assert_stage_equal(Jg, Ig, ora["J_all"][k - 1], ora["idx_all"][k - 1], f"stage {k}")
+        # and against the reference's own stored run
+        assert np.array_equal(U[to_grid(Ig[0], (dx, dx))], golden["u_star"][:, :, k - 1])
+        ref = golden["J_star"][:, :, k - 1]
+        assert np.max(np.abs(to_grid(Jg[0], (dx, dx)) - ref)) <= 1e-12 * np.max(np.abs(ref))
+    sw.close()
+
+
+def test_dynamic_solver_facade_matches_golden(bellman, golden):
+    obj = bellman.Dynamic_Solver()
+    obj.N, obj.dx, obj.du = golden["N"], golden["dx"], golden["du"]
+    obj.run()
+    assert np.array_equal(obj.u_star[:, :, :-1], golden["u_star"][:, :, :-1])
+    assert np.max(np.abs(obj.J_star - golden["J_star"])) <= 1e-12 * np.max(np.abs(golden["J_star"]))
+    X, U = obj.get_optimal_path([2.0, 1.0])
+    np.testing.assert_allclose(U[:5], [-7.30945822, -4.02204735, -2.44352418, -0.69167883, 1.37694508], atol=5e-9)
+    np.testing.assert_allclose(X[:, -1], [0.02094326, -0.05365354], atol=5e-9)
+
+
+def test_rollout_batch_matches_oracle(bellman, oracle_lib, golden):
+    d = golden_desc(bellman, golden)
+    ora = oracle_lib.sweep(d, keep_all=True)
+    sw = bellman.Sweep(d).run()
+    rng = np.random.default_rng(0)
+    x0 = rng.uniform(-3.0, 3.5, size=(257, 2))        # includes off-grid starts (extrapolation)
+    x0[0] = [2.0, 1.0]
+    for mode, ssu in ((0, 1), (1, 30)):
+        Xg, Ug = sw.rollout(golden["A"], golden["B"], d.meta["U_mesh"], x0, mode=mode, ssu_stage=ssu)
+        Xo, Uo = oracle_lib.rollout(d, ora["idx_all"][:, 0, :], golden["A"], golden["B"], d.meta["U_mesh"], x0,
+                                    mode=mode, ssu_stage=ssu)
+        assert np.array_equal(Ug, Uo) and np.array_equal(Xg, Xo)
+    sw.close()
+
+
+@pytest.mark.parametrize("kernel", ["direct", "splitc", "auto"])
+def test_kirk_reference_size_first_stages(bellman, oracle_lib, kernel):
+    """config 1: 100x100 states x 1000 controls (Dynamic_Solver.m:49-63); 24 % of queries off-grid."""
+    obj = bellman.Dynamic_Solver()
+    d = obj._build()
+    ora = oracle_lib.sweep(d, n_stages=6, keep_all=True)
+    sw = bellman.Sweep(d).run(6, kernel=KERNELS[kernel])
+    for k in range(d.N - 6, d.N):
+        assert_stage_equal(sw.get_J(k), sw.get_idx(k), ora["J_all"][k - 1], ora["idx_all"][k - 1], f"stage {k}")
+    sw.close()
+
+
+@pytest.mark.parametrize("graph", [False, True])
+def test_position_reference_size(bellman, oracle_lib, graph):
+    """config 2: 3 axes x 201x201 x 3 controls (Solver_position.m:49-72,84)."""
+    sp = bellman.Solver_position()
+    d = bellman.tables.stack_problems(sp._axis_descs())
+    n = 61
+    ora = oracle_lib.sweep(d, n_stages=n)
+    sw = bellman.Sweep(d).run(n, use_graph=graph)
+    assert sw.current_stage == ora["stage"] == d.N - n
+    assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "position")
+    sw.close()
+
+
+def test_attitude_reference_size(bellman, oracle_lib):
+    """config 3 at the reference's own size: 3 axes x 1000x300 x 3 controls (Solver_attitude.m:106-144)."""
+    sa = bellman.Solver_attitude()
+    d = bellman.tables.stack_problems(sa._axis_descs())
+    ora = oracle_lib.sweep(d, n_stages=12)
+    sw = bellman.Sweep(d).run(12)
+    assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "attitude")
+    sw.close()
+
+
+@pytest.mark.parametrize("failure", [False, True])
+def test_pos_att_reference_size(bellman, oracle_lib, failure):
+    """config 5 at the reference's own size: 30x30x20x15 x 9 combos (Solver_pos_att.m:100-156);
+    non-uniform grids (SEARCH locate) in three dimensions."""
+    sp = bellman.Solver_pos_att()
+    d = sp.channel_desc(0, failure=failure)
+    assert d.C == (6 if failure else 9)
+    ora = oracle_lib.sweep(d, n_stages=8)
+    sw = bellman.Sweep(d).run(8)
+    assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "pos-att")
+    sw.close()
+
+
+def test_pos_att_check_log_and_early_stop(bellman, oracle_lib):
+    """Solver_pos_att.m:273-285: sums every `period` stages; a huge tolerance stops at the first check."""
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 12, 10, 8, 7
+    d = sp.channel_desc(1)
+    sw = bellman.Sweep(d).run(30, check_period=10, check_tol=0.0)
+    log = sw.check_log()
+    assert [int(x) for x in log[:, 0]] == [1990, 1980, 1970]
+    J, idx = sw.get_J(), sw.get_idx()
+    assert abs(log[-1, 1] - J.sum()) <= 1e-12 * abs(J.sum()) and log[-1, 2] == float((idx + 1).sum())
+    sw2 = bellman.Sweep(d).run(30, check_period=10, check_tol=1e300)
+    assert sw2.current_stage == 1990
+    ora = oracle_lib.sweep(d, n_stages=30, check_period=10, check_tol=1e300)
+    assert ora["stage"] == 1990
+    assert_stage_equal(sw2.get_J(), sw2.get_idx(), ora["J_last"], ora["idx_last"], "early stop")
+    sw.close(); sw2.close()
+
+
+def test_random_terminal_cost_and_edge_shapes(bellman, oracle_lib):
+    """set_J with a seeded random J_N (rough surface => every lerp branch, ties unlikely), smallest
+    grids (2 points), C = 1, D = 3."""
+    rng = np.random.default_rng(1)
+    t = bellman.tables
+    for (n0, n1, C) in ((2, 2, 1), (2, 37, 3), (33, 2, 7), (65, 31, 40)):
+        obj = bellman.Dynamic_Solver()
+        obj.dx, obj.du, obj.N = n0, C, 5
+        d = obj._build()
+        # make the two dims different sizes
+        d.n = [n0, n1]
+        s1 = t.linspace(-2.5, 3.0, n1)
+        A = obj.A
+        d.grid[1] = s1.reshape(1, -1); d.Tb[0] = (A[0, 1] * s1).reshape(1, -1); d.Tb[1] = (A[1, 1] * s1).reshape(1, -1)
+        d.q[1] = (0.05 * (s1 * s1)).reshape(1, -1)
+        d.validate()
+        JN = rng.normal(size=(1, n0 * n1)) * 10
+        for kernel in (1, 3):
+            sw = bellman.Sweep(d)
+            sw.set_J(JN)
+            sw.run(2, kernel=kernel)
+            ora = oracle_lib.sweep(d, n_stages=2, J_N=JN)
+            assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"{n0}x{n1}x{C} k{kernel}")
+            sw.close()
+    # D = 3: drop the last dimension of a pos-att channel
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 9, 8, 7, 5
+    d4 = sp.channel_desc(2)
+    d3 = t.Desc(n=d4.n[:3], C=d4.C, N=6, grid=d4.grid[:3], src_a=[0, 1, 2], src_b=[1, -1, -1],
+                Ta=d4.Ta[:3], Tb=[d4.Tb[0], None, None], Tc=[None, d4.Tc[1], d4.Tc[3]],
+                q_order=[2, 0, 1], q=d4.q[:3], r=d4.r).validate()
+    JN = rng.normal(size=(1, d3.S))
+    sw = bellman.Sweep(d3); sw.set_J(JN); sw.run(3)
+    ora = oracle_lib.sweep(d3, n_stages=3, J_N=JN)
+    assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "D=3")
+    sw.close()
+
+
+def test_exact_ties_pick_first_index(bellman, oracle_lib):
+    """Duplicate controls produce exact ties; MATLAB's min returns the first index."""
+    obj = bellman.Dynamic_Solver()
+    obj.dx, obj.du, obj.N = 24, 6, 4
+    d = obj._build()
+    for tab in (d.Tc[0], d.Tc[1], d.r):
+        tab[0, 3:] = tab[0, :3]                       # controls 3..5 duplicate 0..2
+    for kernel in (1, 3):
+        sw = bellman.Sweep(d).run(3, kernel=kernel)
+        idx = sw.get_idx()
+        assert idx.max() <= 2
+        ora = oracle_lib.sweep(d, n_stages=3)
+        assert_stage_equal(sw.get_J(), idx, ora["J_last"], ora["idx_last"], "ties")
+        sw.close()
+
+
+def test_kirk_scaled_full_size_spot_check(bellman, oracle_lib):
+    """config 4 (8192 x 8192 x 512): one stage from a seeded smooth+rough J_N at full size, checked
+    on 100k sampled states against the oracle's pointwise evaluator, plus size-independent
+    properties: every argmin is a valid index and J_k = tot(argmin) exactly."""
+    obj = bellman.Dynamic_Solver()
+    obj.dx, obj.du, obj.N = 8192, 512, 200
+    obj.store_J_star = False
+    d = bellman.tables.kirk_desc(obj.A, obj.B, obj.Q, obj.R, obj.N, obj.x_min, obj.x_max, obj.dx, obj.u_min,
+                                 obj.u_max, obj.du, store_J_all=False, store_idx_all=False)
+    rng = np.random.default_rng(2)
+    s = d.grid[0][0]
+    JN = (0.3 * s[:, None] ** 2 + 0.1 * s[None, :] ** 2).ravel(order="F")
+    JN += rng.normal(size=JN.shape) * 1e-3
+    sw = bellman.Sweep(d)
+    sw.set_J(JN.reshape(1, -1))
+    sw.run(1)
+    Jg, Ig = sw.get_J()[0], sw.get_idx()[0]
+    assert Ig.min() >= 0 and Ig.max() < 512
+    pts = rng.integers(0, d.S, size=100_000)
+    pts[:4] = [0, 8191, d.S - 8192, d.S - 1]          # the four corners
+    Jo, Io = oracle_lib.stage_points(d, JN, pts)
+    assert np.array_equal(Ig[pts], Io) and np.array_equal(Jg[pts], Jo)
+    sw.close()
