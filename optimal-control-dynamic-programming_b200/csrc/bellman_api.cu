@@ -228,7 +228,9 @@ extern "C" void bellman_destroy(bellman_handle *h) {
         if (api) api->CommDestroy(h->comm);
     }
     cudaFree(h->d_tab); cudaFree(h->d_mode); cudaFree(h->d_J); cudaFree(h->d_idx);
-    cudaFree(h->d_partials); cudaFree(h->d_sums); cudaFree(h->d_tmaps);
+    cudaFree(h->d_partials); cudaFree(h->d_sums);
+    window_teardown(h);
+    for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
     if (h->stream) cudaStreamDestroy(h->stream);
@@ -459,28 +461,36 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
             if (next_check >= 1) span = std::min(span, h->cur_stage - next_check);
         }
         if (graphable && span >= 4) {
-            // ping-pong has period 2: capture two stages once, replay span/2 times
-            cudaGraph_t graph = nullptr;
-            cudaGraphExec_t exec = nullptr;
+            // ping-pong storage has period 2: a captured pair of stages is replayed span/2 times.
+            // The instantiated graph is cached on the handle, so only the first run pays for it.
+            if (h->graph_kernel != kernel || h->graph_lanes != lanes) {
+                for (auto &g : h->graph_exec) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+                h->graph_kernel = kernel; h->graph_lanes = lanes;
+            }
+            const int par = h->J_slot(h->cur_stage);
             const int pairs = span / 2;
-            const int stage0 = h->cur_stage;
-            CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
-            rc = launch_one_stage(h, kernel, lanes);
-            h->cur_stage -= 1;
-            if (rc == BELLMAN_OK) rc = launch_one_stage(h, kernel, lanes);
-            h->cur_stage = stage0;
-            cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
-            if (rc != BELLMAN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
-            CUDA_TRY(h, ce);
-            CUDA_TRY(h, cudaGraphInstantiate(&exec, graph, 0));
-            for (int i = 0; i < pairs; ++i) CUDA_TRY(h, cudaGraphLaunch(exec, h->stream));
-            h->last_launches += 2LL * pairs - 2;
+            if (!h->graph_exec[par]) {
+                cudaGraph_t graph = nullptr;
+                const int stage0 = h->cur_stage;
+                const int64_t l0 = h->last_launches;
+                CUDA_TRY(h, cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                rc = launch_one_stage(h, kernel, lanes);
+                h->cur_stage -= 1;
+                if (rc == BELLMAN_OK) rc = launch_one_stage(h, kernel, lanes);
+                h->cur_stage = stage0;
+                h->last_launches = l0;
+                cudaError_t ce = cudaStreamEndCapture(h->stream, &graph);
+                if (rc != BELLMAN_OK) { if (graph) cudaGraphDestroy(graph); return rc; }
+                CUDA_TRY(h, ce);
+                ce = cudaGraphInstantiate(&h->graph_exec[par], graph, 0);
+                cudaGraphDestroy(graph);
+                CUDA_TRY(h, ce);
+            }
+            for (int i = 0; i < pairs; ++i) CUDA_TRY(h, cudaGraphLaunch(h->graph_exec[par], h->stream));
+            h->last_launches += 2LL * pairs;
             h->cur_stage -= 2 * pairs;
             done += 2 * pairs;
             span -= 2 * pairs;
-            CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-            cudaGraphExecDestroy(exec);
-            cudaGraphDestroy(graph);
         }
         for (int i = 0; i < span; ++i) {
             rc = launch_one_stage(h, kernel, lanes);

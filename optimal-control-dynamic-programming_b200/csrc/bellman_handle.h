@@ -36,8 +36,11 @@ struct bellman_handle {
     ncclComm_t comm = nullptr;
     // window kernel state
     bellman::WindowConfig wcfg;
-    void *d_tmaps = nullptr;          // CUtensorMap per J slot
-    int n_tmaps = 0;
+    void *wstate = nullptr;           // bellman_window.cu: WindowState (tensor maps, chunk tables)
+    // cached 2-stage CUDA graphs (ping-pong storage has period 2), keyed by the parity of the
+    // slot the first stage reads and by the kernel variant
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
+    int graph_kernel = -1, graph_lanes = -1;
     // stats
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double last_ms = 0.0, last_ms_exchange = 0.0;
@@ -57,6 +60,7 @@ namespace bellman {
 // bellman_window.cu: plan the TMA-staged D = 2 kernel for this handle (sets h->wcfg, encodes one
 // tensor map per J slot).  Leaves wcfg.valid = false when the problem does not qualify.
 void window_setup(bellman_handle *h);
+void window_teardown(bellman_handle *h);
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next,
                                      cudaStream_t st);
 }  // namespace bellman

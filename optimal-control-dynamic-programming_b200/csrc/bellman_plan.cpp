@@ -83,7 +83,7 @@ int host_locate(const HostProblem &hp, int p, int d, double x) {
     int cell;
     if (hp.mode[(size_t)p * hp.D + d] == BELLMAN_LOCATE_UNIFORM) {
         const double g = std::fma(x, hp.inv_h[d][p], hp.off[d][p]);
-        if (g < 0.0) cell = 0;
+        if (!(g >= 0.0)) cell = 0;
         else if (g >= (double)(n - 1)) cell = n - 2;
         else cell = (int)g;
     } else {

@@ -1,14 +1,462 @@
-// bellman_window.cu — D = 2 stage kernel with the J_{k+1} neighbourhood staged in shared memory
-// by TMA (placeholder until the staged kernel lands; AUTO never selects an invalid config).
+// bellman_window.cu — the D = 2 stage kernel with the J_{k+1} neighbourhood staged in shared
+// memory by TMA (sm_100a).  Same normative arithmetic as the direct kernel (include/bellman.h),
+// compiled with -fmad=false; only the data movement differs.
+//
+// One CTA = one 32 x 64 tile of the state grid (dimension 0, the contiguous one, across the lanes
+// of a warp).  The control loop is cut into chunks; for each (tile, chunk) the bounding box of the
+// queried cells is a small window of J_{k+1} because the next-state map is affine in the state
+// and monotone in the control index.  A single elected thread issues cp.async.bulk.tensor (TMA)
+// box loads of that window into a double-buffered shared-memory ring, completion is tracked by
+// mbarriers, and all 256 threads then gather their four corners from shared memory
+// (conflict-free: the box pitch is a multiple of 16 doubles and lanes walk dimension 0).
+// Every thread owns 8 states of one grid row and loops the controls itself, so min/argmin needs
+// no cross-thread reduction and the first-index tie rule falls out of the strict compare.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstring>
+#include <limits>
+#include <vector>
+
 #include "bellman_handle.h"
 #include "bellman_kernels.cuh"
 
 namespace bellman {
 
-void window_setup(bellman_handle *h) { h->wcfg.valid = false; }
+namespace {
 
-cudaError_t window_launch_for_handle(bellman_handle *, const StageParams &, int, cudaStream_t) {
-    return cudaErrorNotSupported;
+constexpr int WT0 = 32;        // tile extent along dimension 0 (one warp)
+constexpr int WT1 = 64;        // tile extent along dimension 1
+constexpr int WNT = 256;       // threads per CTA
+constexpr int WR_STATES = 8;   // states per thread (same row, 8 consecutive columns)
+static_assert(WT0 * WT1 == WNT * WR_STATES, "tile / thread mapping");
+
+struct WindowParams {
+    int win0, win1;            // window extent (cells): rows (dim 0, pitch) and columns
+    int boxes, box1;           // TMA boxes per window along dim 1, columns per box
+    int cchunk, nchunks;
+    int ntile0, ntile1;
+    const double *cmm;         // [P][nchunks][4]: min/max of Tc_0, min/max of Tc_1 per chunk
+    const double2 *gr0, *gr1;  // [P][n] interleaved (grid, rinv)
+};
+
+// --- PTX wrappers ------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y,
+                                            int z) {
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
+        : "memory");
+}
+
+__device__ __forceinline__ int cell_uniform(double x, double inv_h, double off, int n) {
+    return min(max(__double2int_rd(fma(x, inv_h, off)), 0), n - 2);
+}
+
+// HC0 / HC1: does dimension 0 / 1 of the next state depend on the control?
+template <bool HC0, bool HC1>
+__global__ void __launch_bounds__(WNT, 2)
+k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
+               const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar[2];
+    __shared__ double tmm[8];   // min/max over the tile of Ta_0, Tb_0, Ta_1, Tb_1
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int prob = blockIdx.y;
+    const int ti = blockIdx.x % wp.ntile0, tj = blockIdx.x / wp.ntile0;
+    const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
+    const int n0 = d0.n, n1 = d1.n;
+    // tile ranges in global grid indices, clipped to the owned range
+    const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
+    const int j_lo = d1.own_lo + tj * WT1, j_hi = min(j_lo + WT1, d1.own_lo + d1.own_n);
+
+    double *const win_base = reinterpret_cast<double *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    const int win_elems = wp.win0 * wp.win1;
+    const uint32_t win_bytes = (uint32_t)win_elems * 8u;
+
+    // per-problem tables
+    const double *Ta0 = d0.Ta + (size_t)prob * d0.n_a, *Ta1 = d1.Ta + (size_t)prob * d1.n_a;
+    const double *Tb0 = d0.Tb ? d0.Tb + (size_t)prob * d0.n_b : nullptr;
+    const double *Tb1 = d1.Tb ? d1.Tb + (size_t)prob * d1.n_b : nullptr;
+    const double *Tc0 = HC0 ? d0.Tc + (size_t)prob * sp.C : nullptr;
+    const double *Tc1 = HC1 ? d1.Tc + (size_t)prob * sp.C : nullptr;
+    const double *rr = sp.r + (size_t)prob * sp.C;
+    const double2 *gr0 = wp.gr0 + (size_t)prob * n0, *gr1 = wp.gr1 + (size_t)prob * n1;
+    const double inv_h0 = __ldg(d0.loc + 2 * prob), off0 = __ldg(d0.loc + 2 * prob + 1);
+    const double inv_h1 = __ldg(d1.loc + 2 * prob), off1 = __ldg(d1.loc + 2 * prob + 1);
+    const double *cmm = wp.cmm + (size_t)prob * wp.nchunks * 4;
+
+    if (tid == 0) {
+        mbar_init(&mbar[0], 1);
+        mbar_init(&mbar[1], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    // tile min/max of the state-indexed tables (warp w reduces quantity w)
+    if (wrp < 4) {
+        const double *tab = wrp == 0 ? Ta0 : wrp == 1 ? Tb0 : wrp == 2 ? Ta1 : Tb1;
+        const int src = wrp == 0 ? d0.src_a : wrp == 1 ? d0.src_b : wrp == 2 ? d1.src_a : d1.src_b;
+        double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
+        if (tab) {
+            const int lo = src == 0 ? i_lo : j_lo, hi = src == 0 ? i_hi : j_hi;
+            for (int k = lo + lane; k < hi; k += 32) {
+                const double v = __ldg(tab + k);
+                mn = fmin(mn, v);
+                mx = fmax(mx, v);
+            }
+#pragma unroll
+            for (int w = 16; w >= 1; w >>= 1) {
+                mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, w));
+                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, w));
+            }
+        } else {
+            mn = mx = 0.0;
+        }
+        if (lane == 0) { tmm[2 * wrp] = mn; tmm[2 * wrp + 1] = mx; }
+    }
+    __syncthreads();
+
+    // window origin of chunk ch: the cell of the smallest query, formed with the kernel's own
+    // association so that the bound is exact
+    auto origin = [&](int ch, int &r0, int &c0) {
+        double lo0 = tmm[0], lo1 = tmm[4];
+        if (Tb0) lo0 = lo0 + tmm[2];
+        if (Tb1) lo1 = lo1 + tmm[6];
+        if (HC0) lo0 = lo0 + __ldg(cmm + 4 * ch);
+        if (HC1) lo1 = lo1 + __ldg(cmm + 4 * ch + 2);
+        // TMA needs the byte offset of the innermost box coordinate to be a multiple of 16
+        // (measured on B200: an odd fp64 coordinate raises "illegal instruction"), so the window
+        // starts on an even row of the local array; the planner adds the extra row.
+        r0 = cell_uniform(lo0, inv_h0, off0, n0);
+        r0 -= (r0 - d0.ext_lo) & 1;
+        c0 = cell_uniform(lo1, inv_h1, off1, n1);
+    };
+    auto issue = [&](int ch) {   // thread 0 only
+        int r0, c0;
+        origin(ch, r0, c0);
+        uint64_t *bar = &mbar[ch & 1];
+        mbar_expect_tx(bar, win_bytes);
+        double *dst = win_base + (ch & 1) * win_elems;
+        for (int b = 0; b < wp.boxes; ++b)
+            tma_load_3d(dst + (size_t)b * wp.box1 * wp.win0, &tmap, bar, r0 - d0.ext_lo,
+                        c0 - d1.ext_lo + b * wp.box1, prob);
+    };
+    if (tid == 0) {
+        issue(0);
+        if (wp.nchunks > 1) issue(1);
+    }
+
+    // this thread's states: row i, columns j0..j0+7
+    const int i = min(i_lo + lane, i_hi - 1);
+    const int jbase = j_lo + wrp * WR_STATES;
+    double base0[WR_STATES], base1[WR_STATES], gs[WR_STATES], best[WR_STATES];
+    int arg[WR_STATES];
+    int cellK0[WR_STATES], cellK1[WR_STATES];   // used only for control-independent dimensions
+    double tK0[WR_STATES], tK1[WR_STATES];
+    const double *q0 = d0.q + (size_t)prob * n0, *q1 = d1.q + (size_t)prob * n1;
+#pragma unroll
+    for (int m = 0; m < WR_STATES; ++m) {
+        const int j = min(jbase + m, j_hi - 1);
+        double b0 = __ldg(Ta0 + (d0.src_a == 0 ? i : j));
+        if (Tb0) b0 = b0 + __ldg(Tb0 + (d0.src_b == 0 ? i : j));
+        double b1 = __ldg(Ta1 + (d1.src_a == 0 ? i : j));
+        if (Tb1) b1 = b1 + __ldg(Tb1 + (d1.src_b == 0 ? i : j));
+        base0[m] = b0;
+        base1[m] = b1;
+        const double qa = __ldg(q0 + i), qb = __ldg(q1 + j);
+        gs[m] = sp.q_order[0] == 0 ? qa + qb : qb + qa;
+        best[m] = __longlong_as_double(0x7ff0000000000000LL);
+        arg[m] = 0;
+        if (!HC0) {
+            cellK0[m] = cell_uniform(b0, inv_h0, off0, n0);
+            const double2 g = __ldg(gr0 + cellK0[m]);
+            tK0[m] = (b0 - g.x) * g.y;
+        }
+        if (!HC1) {
+            cellK1[m] = cell_uniform(b1, inv_h1, off1, n1);
+            const double2 g = __ldg(gr1 + cellK1[m]);
+            tK1[m] = (b1 - g.x) * g.y;
+        }
+    }
+
+    const int W0 = wp.win0;
+    for (int ch = 0; ch < wp.nchunks; ++ch) {
+        int r0, c0;
+        origin(ch, r0, c0);
+        mbar_wait(&mbar[ch & 1], (ch >> 1) & 1);
+        const double *__restrict__ W = win_base + (ch & 1) * win_elems;
+        const int c_end = min(sp.C, (ch + 1) * wp.cchunk);
+        for (int c = ch * wp.cchunk; c < c_end; ++c) {
+            const double bu0 = HC0 ? __ldg(Tc0 + c) : 0.0;
+            const double bu1 = HC1 ? __ldg(Tc1 + c) : 0.0;
+            const double rc = __ldg(rr + c);
+#pragma unroll
+            for (int m = 0; m < WR_STATES; ++m) {
+                int cell0, cell1;
+                double t0, t1;
+                if (HC0) {
+                    const double x0 = base0[m] + bu0;
+                    cell0 = cell_uniform(x0, inv_h0, off0, n0);
+                    const double2 g = __ldg(gr0 + cell0);
+                    t0 = (x0 - g.x) * g.y;
+                } else {
+                    cell0 = cellK0[m];
+                    t0 = tK0[m];
+                }
+                if (HC1) {
+                    const double x1 = base1[m] + bu1;
+                    cell1 = cell_uniform(x1, inv_h1, off1, n1);
+                    const double2 g = __ldg(gr1 + cell1);
+                    t1 = (x1 - g.x) * g.y;
+                } else {
+                    cell1 = cellK1[m];
+                    t1 = tK1[m];
+                }
+                const double *p = W + ((cell1 - c0) * W0 + (cell0 - r0));
+                const double v00 = p[0], v10 = p[1], v01 = p[W0], v11 = p[W0 + 1];
+                const double a = fma(t0, v10 - v00, v00);
+                const double b = fma(t0, v11 - v01, v01);
+                const double v = fma(t1, b - a, a);
+                const double tot = (gs[m] + rc) + v;
+                if (tot < best[m]) { best[m] = tot; arg[m] = c; }
+            }
+        }
+        __syncthreads();   // every thread is done with this buffer
+        if (tid == 0 && ch + 2 < wp.nchunks) issue(ch + 2);
+    }
+
+    if (i_lo + lane < i_hi) {
+        double *Jo = sp.J_out + (size_t)prob * sp.S_ext;
+        int32_t *Io = sp.idx_out + (size_t)prob * sp.S_own;
+#pragma unroll
+        for (int m = 0; m < WR_STATES; ++m) {
+            const int j = jbase + m;
+            if (j < j_hi) {
+                Jo[(long long)(i - d0.ext_lo) * d0.stride + (long long)(j - d1.ext_lo) * d1.stride] = best[m];
+                Io[(long long)(i - d0.own_lo) + (long long)(j - d1.own_lo) * d0.own_n] = arg[m];
+            }
+        }
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+struct WindowState {
+    WindowParams wp{};
+    std::vector<CUtensorMap> maps;   // one per J slot
+    size_t smem = 0;
+    bool hc0 = false, hc1 = false;
+    void *d_cmm = nullptr, *d_gr0 = nullptr, *d_gr1 = nullptr;
+};
+
+void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
+    mn = std::numeric_limits<double>::infinity();
+    mx = -mn;
+    for (int k = lo; k < hi; ++k) { mn = std::min(mn, v[k]); mx = std::max(mx, v[k]); }
+}
+
+}  // namespace
+
+// Exact worst-case window extents for a given chunk size: replays, on the host, the bound the
+// kernel uses ((min Ta + min Tb) + min Tc .. (max Ta + max Tb) + max Tc, located with the same
+// rule) for every tile and chunk.
+static void window_extents(const bellman_handle *h, int cchunk, int &w0, int &w1) {
+    const HostProblem &hp = h->hp;
+    const int nch = (hp.C + cchunk - 1) / cchunk;
+    w0 = w1 = 0;
+    for (int p = 0; p < hp.P; ++p) {
+        for (int d = 0; d < 2; ++d) {
+            const int sa = hp.src_a[d], sb = hp.src_b[d];
+            // per tile-index min/max of Ta and Tb along the dimension that indexes them
+            auto tile_mm = [&](const std::vector<double> &tab, int src, std::vector<double> &mn,
+                               std::vector<double> &mx) {
+                const int T = src == 0 ? WT0 : WT1;
+                const int lo0 = h->own_lo[src], cnt = h->own_n[src];
+                const int nt = (cnt + T - 1) / T;
+                mn.resize(nt); mx.resize(nt);
+                for (int t = 0; t < nt; ++t)
+                    minmax_range(tab.data() + (size_t)p * hp.n[src], lo0 + t * T,
+                                 std::min(lo0 + (t + 1) * T, lo0 + cnt), mn[t], mx[t]);
+            };
+            std::vector<double> amn, amx, bmn{0.0}, bmx{0.0}, cmn(nch, 0.0), cmx(nch, 0.0);
+            tile_mm(hp.Ta[d], sa, amn, amx);
+            if (hp.has_b[d]) tile_mm(hp.Tb[d], sb, bmn, bmx);
+            if (hp.has_c[d])
+                for (int c = 0; c < nch; ++c)
+                    minmax_range(hp.Tc[d].data() + (size_t)p * hp.C, c * cchunk,
+                                 std::min(hp.C, (c + 1) * cchunk), cmn[c], cmx[c]);
+            // if Ta and Tb are indexed by the same dimension their tile indices coincide
+            const bool same = hp.has_b[d] && sa == sb;
+            int ext = 0;
+            for (size_t ta = 0; ta < amn.size(); ++ta)
+                for (size_t tb = same ? ta : 0; tb < (same ? ta + 1 : bmn.size()); ++tb)
+                    for (int c = 0; c < nch; ++c) {
+                        double lo = amn[ta], hi = amx[ta];
+                        if (hp.has_b[d]) { lo = lo + bmn[tb]; hi = hi + bmx[tb]; }
+                        if (hp.has_c[d]) { lo = lo + cmn[c]; hi = hi + cmx[c]; }
+                        ext = std::max(ext, host_locate(hp, p, d, hi) + 2 - host_locate(hp, p, d, lo));
+                    }
+            (d == 0 ? w0 : w1) = std::max(d == 0 ? w0 : w1, ext);
+        }
+    }
+}
+
+void window_setup(bellman_handle *h) {
+    h->wcfg.valid = false;
+    const HostProblem &hp = h->hp;
+    if (hp.D != 2) return;
+    for (int32_t m : hp.mode)
+        if (m != BELLMAN_LOCATE_UNIFORM) return;
+    if (h->ext_n[0] % 2) return;                 // TMA global strides must be multiples of 16 bytes
+    if (((size_t)h->S_ext * 8) % 16) return;
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return;
+
+    // pick the chunk size: most updates per staged byte among configs that keep two CTAs per SM
+    const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
+    int best_cc = 0, best_w0 = 0, best_w1 = 0;
+    double best_score = -1.0;
+    std::vector<int> cands;
+    for (int cc : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32})
+        if (cc <= hp.C) cands.push_back(cc);
+    if (hp.C <= 32 && std::find(cands.begin(), cands.end(), hp.C) == cands.end()) cands.push_back(hp.C);
+    for (int cc : cands) {
+        int w0, w1;
+        window_extents(h, cc, w0, w1);
+        w0 = (w0 + 1 + 15) / 16 * 16;             // +1: the window origin is rounded down to an even row
+        if (w0 > 256) continue;
+        const int boxes = (w1 + 255) / 256;
+        const int box1 = (w1 + boxes - 1) / boxes;
+        w1 = boxes * box1;
+        const size_t bytes = 2 * (size_t)w0 * w1 * 8 + 128;
+        if (bytes > budget1) continue;
+        const int nch = (hp.C + cc - 1) / cc;
+        double score = (double)std::min(cc, hp.C) / ((double)w0 * w1);
+        if (bytes > budget2) score *= 0.5;       // one CTA per SM only
+        if (nch == 1) score *= 1.0;
+        if (score > best_score) { best_score = score; best_cc = cc; best_w0 = w0; best_w1 = w1; }
+    }
+    if (best_cc == 0) return;
+
+    auto *ws = new WindowState();
+    WindowParams &wp = ws->wp;
+    wp.win0 = best_w0;
+    wp.boxes = (best_w1 + 255) / 256;
+    wp.box1 = best_w1 / wp.boxes;
+    wp.win1 = best_w1;
+    wp.cchunk = best_cc;
+    wp.nchunks = (hp.C + best_cc - 1) / best_cc;
+    wp.ntile0 = (h->own_n[0] + WT0 - 1) / WT0;
+    wp.ntile1 = (h->own_n[1] + WT1 - 1) / WT1;
+    ws->smem = 2 * (size_t)wp.win0 * wp.win1 * 8 + 128;
+    ws->hc0 = hp.has_c[0];
+    ws->hc1 = hp.has_c[1];
+
+    // per-chunk control min/max and interleaved (grid, rinv) tables
+    std::vector<double> cmm((size_t)hp.P * wp.nchunks * 4, 0.0);
+    for (int p = 0; p < hp.P; ++p)
+        for (int c = 0; c < wp.nchunks; ++c)
+            for (int d = 0; d < 2; ++d)
+                if (hp.has_c[d])
+                    minmax_range(hp.Tc[d].data() + (size_t)p * hp.C, c * wp.cchunk,
+                                 std::min(hp.C, (c + 1) * wp.cchunk), cmm[((size_t)p * wp.nchunks + c) * 4 + 2 * d],
+                                 cmm[((size_t)p * wp.nchunks + c) * 4 + 2 * d + 1]);
+    auto upload = [&](const std::vector<double> &v, void **dptr) {
+        return cudaMalloc(dptr, v.size() * sizeof(double)) == cudaSuccess &&
+               cudaMemcpy(*dptr, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    std::vector<double> g0((size_t)hp.P * hp.n[0] * 2), g1((size_t)hp.P * hp.n[1] * 2);
+    for (size_t k = 0; k < (size_t)hp.P * hp.n[0]; ++k) { g0[2 * k] = hp.grid[0][k]; g0[2 * k + 1] = hp.rinv[0][k]; }
+    for (size_t k = 0; k < (size_t)hp.P * hp.n[1]; ++k) { g1[2 * k] = hp.grid[1][k]; g1[2 * k + 1] = hp.rinv[1][k]; }
+    if (!upload(cmm, &ws->d_cmm) || !upload(g0, &ws->d_gr0) || !upload(g1, &ws->d_gr1)) { delete ws; return; }
+    wp.cmm = static_cast<const double *>(ws->d_cmm);
+    wp.gr0 = static_cast<const double2 *>(ws->d_gr0);
+    wp.gr1 = static_cast<const double2 *>(ws->d_gr1);
+
+    // one tensor map per J slot: [P][ext_n1][ext_n0] fp64, box = win0 x box1 x 1
+    const int nslots = h->store_J_all ? hp.N : 2;
+    ws->maps.resize(nslots);
+    for (int s = 0; s < nslots; ++s) {
+        cuuint64_t gdim[3] = {(cuuint64_t)h->ext_n[0], (cuuint64_t)h->ext_n[1], (cuuint64_t)hp.P};
+        cuuint64_t gstr[2] = {(cuuint64_t)h->ext_n[0] * 8, (cuuint64_t)h->S_ext * 8};
+        cuuint32_t box[3] = {(cuuint32_t)wp.win0, (cuuint32_t)wp.box1, 1};
+        cuuint32_t estr[3] = {1, 1, 1};
+        void *base = h->d_J + (size_t)s * h->slot_elems_J();
+        CUresult r = enc(&ws->maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                         CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete ws; return; }
+    }
+    auto set_attr = [&](const void *fn) {
+        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) == cudaSuccess;
+    };
+    if (!set_attr((const void *)k_stage_window<true, true>) || !set_attr((const void *)k_stage_window<true, false>) ||
+        !set_attr((const void *)k_stage_window<false, true>)) { delete ws; return; }
+    if (!ws->hc0 && !ws->hc1) { delete ws; return; }   // no control dependence at all: nothing to stage for
+    h->wstate = ws;
+    h->wcfg.tile0 = WT0; h->wcfg.tile1 = WT1; h->wcfg.cchunk = wp.cchunk;
+    h->wcfg.win0 = wp.win0; h->wcfg.win1 = wp.win1;
+    h->wcfg.valid = true;
+}
+
+void window_teardown(bellman_handle *h) {
+    auto *ws = static_cast<WindowState *>(h->wstate);
+    if (!ws) return;
+    cudaFree(ws->d_cmm); cudaFree(ws->d_gr0); cudaFree(ws->d_gr1);
+    delete ws;
+    h->wstate = nullptr;
+}
+
+cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st) {
+    auto *ws = static_cast<WindowState *>(h->wstate);
+    if (!ws || !h->wcfg.valid) return cudaErrorNotSupported;
+    const WindowParams &wp = ws->wp;
+    const dim3 grid((unsigned)(wp.ntile0 * wp.ntile1), (unsigned)sp.P);
+    const CUtensorMap &map = ws->maps[slot_next];
+    if (ws->hc0 && ws->hc1) k_stage_window<true, true><<<grid, WNT, ws->smem, st>>>(sp, wp, map);
+    else if (ws->hc0) k_stage_window<true, false><<<grid, WNT, ws->smem, st>>>(sp, wp, map);
+    else k_stage_window<false, true><<<grid, WNT, ws->smem, st>>>(sp, wp, map);
+    return cudaGetLastError();
 }
 
 }  // namespace bellman

@@ -72,7 +72,8 @@ static inline int locate(const dimtab *g, double x, double *t)
     int cell;
     if (g->mode == BELLMAN_LOCATE_UNIFORM) {
         const double gg = fma(x, g->inv_h, g->off);
-        if (gg < 0.0) cell = 0;                       /* floor() then clamp, without int overflow */
+        if (!(gg >= 0.0)) cell = 0;                   /* floor() then clamp, without int overflow; NaN -> 0
+                                                         like the GPU's saturating cvt.rmi.s32.f64 */
         else if (gg >= (double)(g->n - 1)) cell = g->n - 2;
         else cell = (int)gg;
     } else {
