@@ -46,14 +46,18 @@
  *       if tot < best (strictly): best = tot, arg = c        -> first index wins ties (MATLAB min)
  *   J_k[i] = best ; idx_k[i] = arg
  *
- *   locate_d(x):  t = (x - s[cell]) * rinv[cell],  rinv[i] = 1/(s[i+1]-s[i]) (IEEE division, host)
- *     BELLMAN_LOCATE_UNIFORM : cell = clamp( (int)floor( fma(x, inv_h, off) ), 0, n-2 )
- *                              inv_h = (n-1)/(s[n-1]-s[0]),  off = -s[0]*inv_h   (host, rounded once each)
+ *   locate_d(x) -> (cell, t):
+ *     BELLMAN_LOCATE_UNIFORM : g = fma(x, inv_h, off);  cell = clamp( (int)floor(g), 0, n-2 );
+ *                              t = g - (double)cell
+ *                              inv_h = (n-1)/(s[n-1]-s[0]),  off = -(s[0]*inv_h)   (host, rounded once each)
  *     BELLMAN_LOCATE_SEARCH  : cell = clamp( #{ i : s[i] <= x } - 1, 0, n-2 )    (exact bin rule)
- *   The library picks UNIFORM for a dimension when the grid vector is uniform to 1e-9 of a cell,
- *   else SEARCH; bellman_query_locate() reports the choice so the oracle uses the same one.
- *   (Near a grid node the two rules may pick adjacent cells; interpolation is continuous there,
- *   the results differ by O(1 ulp).)
+ *                              t = (x - s[cell]) * rinv[cell],  rinv[i] = 1/(s[i+1]-s[i]) (IEEE division, host)
+ *   The library picks UNIFORM for a dimension when every node lies within 1e-14 of the grid's
+ *   range from the uniform formula s[0] + i*h (MATLAB linspace grids do, with ~100x margin), else
+ *   SEARCH; bellman_query_locate() reports the choice so the oracle uses the same one.  In
+ *   UNIFORM mode the weight comes from the same fma that picks the cell, so cell and weight can
+ *   never disagree, and no table is read per query.  (Near a grid node the two rules may pick
+ *   adjacent cells; interpolation is continuous there, the results differ by O(1 ulp).)
  */
 #ifndef BELLMAN_H
 #define BELLMAN_H

@@ -14,20 +14,23 @@ namespace {
 constexpr int BLOCK = 256;
 
 // --- locate (include/bellman.h, "locate_d") ---------------------------------------------------
-__device__ __forceinline__ int locate_cell(const double *__restrict__ s, int n, int mode,
-                                           double inv_h, double off, double x) {
+__device__ __forceinline__ int locate(const double *__restrict__ s, const double *__restrict__ rinv, int n,
+                                      int mode, double inv_h, double off, double x, double &t) {
     int cell;
     if (mode == BELLMAN_LOCATE_UNIFORM) {
-        cell = __double2int_rd(fma(x, inv_h, off));   // floor, saturating
+        const double g = fma(x, inv_h, off);
+        cell = min(max(__double2int_rd(g), 0), n - 2);   // floor (saturating), then clamp
+        t = g - (double)cell;
     } else {
-        int lo = 0, hi = n;                            // #{ s[i] <= x }
+        int lo = 0, hi = n;                               // #{ s[i] <= x }
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
             if (__ldg(s + mid) <= x) lo = mid + 1; else hi = mid;
         }
-        cell = lo - 1;
+        cell = min(max(lo - 1, 0), n - 2);
+        t = (x - __ldg(s + cell)) * __ldg(rinv + cell);
     }
-    return min(max(cell, 0), n - 2);
+    return cell;
 }
 
 template <int D>
@@ -65,8 +68,7 @@ __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const double xq = pb.Tc[d] ? base[d] + __ldg(pb.Tc[d] + c) : base[d];
-        const int cell = locate_cell(pb.grid[d], pb.n[d], pb.mode[d], pb.inv_h[d], pb.off[d], xq);
-        t[d] = (xq - __ldg(pb.grid[d] + cell)) * __ldg(pb.rinv[d] + cell);
+        const int cell = locate(pb.grid[d], pb.rinv[d], pb.n[d], pb.mode[d], pb.inv_h[d], pb.off[d], xq, t[d]);
         o += (long long)(cell - sp.dim[d].ext_lo) * sp.dim[d].stride;
     }
     double v[1 << D];
@@ -243,10 +245,9 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
     for (int k = 1; k <= rp.N - 1; ++k) {
         const int st = rp.mode == 1 ? rp.ssu_stage : k;
         const int32_t *__restrict__ id = rp.idx_all + (size_t)(st - 1) * S;
-        const int c0 = locate_cell(rp.grid0, rp.n0, rp.mode0, rp.inv_h0, rp.off0, x1);
-        const int c1 = locate_cell(rp.grid1, rp.n1, rp.mode1, rp.inv_h1, rp.off1, x2);
-        const double t0 = (x1 - rp.grid0[c0]) * rp.rinv0[c0];
-        const double t1 = (x2 - rp.grid1[c1]) * rp.rinv1[c1];
+        double t0, t1;
+        const int c0 = locate(rp.grid0, rp.rinv0, rp.n0, rp.mode0, rp.inv_h0, rp.off0, x1, t0);
+        const int c1 = locate(rp.grid1, rp.rinv1, rp.n1, rp.mode1, rp.inv_h1, rp.off1, x2, t1);
         const long long o = c0 + (long long)c1 * rp.n0;
         const double v00 = rp.u_values[id[o]], v10 = rp.u_values[id[o + 1]];
         const double v01 = rp.u_values[id[o + rp.n0]], v11 = rp.u_values[id[o + rp.n0 + 1]];

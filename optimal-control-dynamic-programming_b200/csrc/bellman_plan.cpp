@@ -14,7 +14,7 @@ static bool grid_is_uniform(const double *s, int n) {
     const double h = (s[n - 1] - s[0]) / (double)(n - 1);
     for (int i = 0; i < n; ++i) {
         const double dev = std::fabs(s[i] - (s[0] + (double)i * h));
-        if (!(dev <= 1e-9 * h)) return false;
+        if (!(dev <= 1e-14 * (s[n - 1] - s[0]))) return false;
     }
     return true;
 }

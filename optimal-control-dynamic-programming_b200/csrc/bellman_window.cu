@@ -37,8 +37,9 @@ struct WindowParams {
     int boxes, box1;           // TMA boxes per window along dim 1, columns per box
     int cchunk, nchunks;
     int ntile0, ntile1;
+    int tj_fastest;            // 1: consecutive CTAs walk dimension 1 (the one the controls sweep)
+    int buf_doubles;           // doubles per ring slot (the window, 128 B aligned)
     const double *cmm;         // [P][nchunks][4]: min/max of Tc_0, min/max of Tc_1 per chunk
-    const double2 *gr0, *gr1;  // [P][n] interleaved (grid, rinv)
 };
 
 // --- PTX wrappers ------------------------------------------------------------------------------
@@ -74,8 +75,15 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
+// UNIFORM locate of include/bellman.h: g = fma(x, inv_h, off); cell = clamp(floor(g)); t = g - cell
 __device__ __forceinline__ int cell_uniform(double x, double inv_h, double off, int n) {
     return min(max(__double2int_rd(fma(x, inv_h, off)), 0), n - 2);
+}
+__device__ __forceinline__ int locate_uniform(double x, double inv_h, double off, int n, double &t) {
+    const double g = fma(x, inv_h, off);
+    const int cell = min(max(__double2int_rd(g), 0), n - 2);
+    t = g - (double)cell;
+    return cell;
 }
 
 // HC0 / HC1: does dimension 0 / 1 of the next state depend on the control?
@@ -83,20 +91,23 @@ template <bool HC0, bool HC1>
 __global__ void __launch_bounds__(WNT, 2)
 k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
                const __grid_constant__ CUtensorMap tmap) {
-    extern __shared__ unsigned char smem_raw[];
+    // ring of two window slots, win0 x win1 doubles each (dimension 0 contiguous)
+    extern __shared__ __align__(128) double ring[];
     __shared__ __align__(8) uint64_t mbar[2];
     __shared__ double tmm[8];   // min/max over the tile of Ta_0, Tb_0, Ta_1, Tb_1
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int prob = blockIdx.y;
-    const int ti = blockIdx.x % wp.ntile0, tj = blockIdx.x / wp.ntile0;
+    // CTAs that run together should sweep the same columns of J_{k+1} at staggered times: that
+    // keeps the union of their windows a thin band that lives in L2
+    const int ti = wp.tj_fastest ? blockIdx.x / wp.ntile1 : blockIdx.x % wp.ntile0;
+    const int tj = wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0;
     const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
     const int n0 = d0.n, n1 = d1.n;
     // tile ranges in global grid indices, clipped to the owned range
     const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
     const int j_lo = d1.own_lo + tj * WT1, j_hi = min(j_lo + WT1, d1.own_lo + d1.own_n);
 
-    double *const win_base = reinterpret_cast<double *>(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
     const int win_elems = wp.win0 * wp.win1;
     const uint32_t win_bytes = (uint32_t)win_elems * 8u;
 
@@ -107,7 +118,6 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     const double *Tc0 = HC0 ? d0.Tc + (size_t)prob * sp.C : nullptr;
     const double *Tc1 = HC1 ? d1.Tc + (size_t)prob * sp.C : nullptr;
     const double *rr = sp.r + (size_t)prob * sp.C;
-    const double2 *gr0 = wp.gr0 + (size_t)prob * n0, *gr1 = wp.gr1 + (size_t)prob * n1;
     const double inv_h0 = __ldg(d0.loc + 2 * prob), off0 = __ldg(d0.loc + 2 * prob + 1);
     const double inv_h1 = __ldg(d1.loc + 2 * prob), off1 = __ldg(d1.loc + 2 * prob + 1);
     const double *cmm = wp.cmm + (size_t)prob * wp.nchunks * 4;
@@ -161,7 +171,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         origin(ch, r0, c0);
         uint64_t *bar = &mbar[ch & 1];
         mbar_expect_tx(bar, win_bytes);
-        double *dst = win_base + (ch & 1) * win_elems;
+        double *dst = ring + (ch & 1) * wp.buf_doubles;
         for (int b = 0; b < wp.boxes; ++b)
             tma_load_3d(dst + (size_t)b * wp.box1 * wp.win0, &tmap, bar, r0 - d0.ext_lo,
                         c0 - d1.ext_lo + b * wp.box1, prob);
@@ -192,16 +202,8 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         gs[m] = sp.q_order[0] == 0 ? qa + qb : qb + qa;
         best[m] = __longlong_as_double(0x7ff0000000000000LL);
         arg[m] = 0;
-        if (!HC0) {
-            cellK0[m] = cell_uniform(b0, inv_h0, off0, n0);
-            const double2 g = __ldg(gr0 + cellK0[m]);
-            tK0[m] = (b0 - g.x) * g.y;
-        }
-        if (!HC1) {
-            cellK1[m] = cell_uniform(b1, inv_h1, off1, n1);
-            const double2 g = __ldg(gr1 + cellK1[m]);
-            tK1[m] = (b1 - g.x) * g.y;
-        }
+        if (!HC0) cellK0[m] = locate_uniform(b0, inv_h0, off0, n0, tK0[m]);
+        if (!HC1) cellK1[m] = locate_uniform(b1, inv_h1, off1, n1, tK1[m]);
     }
 
     const int W0 = wp.win0;
@@ -209,41 +211,43 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         int r0, c0;
         origin(ch, r0, c0);
         mbar_wait(&mbar[ch & 1], (ch >> 1) & 1);
-        const double *__restrict__ W = win_base + (ch & 1) * win_elems;
+        const double *__restrict__ W = ring + (ch & 1) * wp.buf_doubles;
         const int c_end = min(sp.C, (ch + 1) * wp.cchunk);
         for (int c = ch * wp.cchunk; c < c_end; ++c) {
             const double bu0 = HC0 ? __ldg(Tc0 + c) : 0.0;
             const double bu1 = HC1 ? __ldg(Tc1 + c) : 0.0;
             const double rc = __ldg(rr + c);
+            // two batches of four independent states: enough instruction-level parallelism to
+            // cover the fp64 / shared-memory latencies with 16 warps per SM, within 128 registers
 #pragma unroll
-            for (int m = 0; m < WR_STATES; ++m) {
-                int cell0, cell1;
-                double t0, t1;
-                if (HC0) {
-                    const double x0 = base0[m] + bu0;
-                    cell0 = cell_uniform(x0, inv_h0, off0, n0);
-                    const double2 g = __ldg(gr0 + cell0);
-                    t0 = (x0 - g.x) * g.y;
-                } else {
-                    cell0 = cellK0[m];
-                    t0 = tK0[m];
+            for (int mb = 0; mb < WR_STATES; mb += 4) {
+                int off[4];
+                double t0[4], t1[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int m = mb + u;
+                    int rel0, rel1;          // cell index relative to the window origin
+                    if (HC0) rel0 = locate_uniform(base0[m] + bu0, inv_h0, off0, n0, t0[u]) - r0;
+                    else { rel0 = cellK0[m] - r0; t0[u] = tK0[m]; }
+                    if (HC1) rel1 = locate_uniform(base1[m] + bu1, inv_h1, off1, n1, t1[u]) - c0;
+                    else { rel1 = cellK1[m] - c0; t1[u] = tK1[m]; }
+                    off[u] = rel1 * W0 + rel0;
                 }
-                if (HC1) {
-                    const double x1 = base1[m] + bu1;
-                    cell1 = cell_uniform(x1, inv_h1, off1, n1);
-                    const double2 g = __ldg(gr1 + cell1);
-                    t1 = (x1 - g.x) * g.y;
-                } else {
-                    cell1 = cellK1[m];
-                    t1 = tK1[m];
+                double v00[4], v10[4], v01[4], v11[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const double *p = W + off[u];
+                    v00[u] = p[0]; v10[u] = p[1]; v01[u] = p[W0]; v11[u] = p[W0 + 1];
                 }
-                const double *p = W + ((cell1 - c0) * W0 + (cell0 - r0));
-                const double v00 = p[0], v10 = p[1], v01 = p[W0], v11 = p[W0 + 1];
-                const double a = fma(t0, v10 - v00, v00);
-                const double b = fma(t0, v11 - v01, v01);
-                const double v = fma(t1, b - a, a);
-                const double tot = (gs[m] + rc) + v;
-                if (tot < best[m]) { best[m] = tot; arg[m] = c; }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int m = mb + u;
+                    const double a = fma(t0[u], v10[u] - v00[u], v00[u]);
+                    const double b = fma(t0[u], v11[u] - v01[u], v01[u]);
+                    const double v = fma(t1[u], b - a, a);
+                    const double tot = (gs[m] + rc) + v;
+                    if (tot < best[m]) { best[m] = tot; arg[m] = c; }
+                }
             }
         }
         __syncthreads();   // every thread is done with this buffer
@@ -286,7 +290,7 @@ struct WindowState {
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
     bool hc0 = false, hc1 = false;
-    void *d_cmm = nullptr, *d_gr0 = nullptr, *d_gr1 = nullptr;
+    void *d_cmm = nullptr;
 };
 
 void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
@@ -341,6 +345,9 @@ static void window_extents(const bellman_handle *h, int cchunk, int &w0, int &w1
     }
 }
 
+// bytes of one ring slot (w0 is a multiple of 16, so this is a multiple of 128)
+static size_t slot_bytes(int w0, int w1) { return (size_t)w0 * w1 * 8; }
+
 void window_setup(bellman_handle *h) {
     h->wcfg.valid = false;
     const HostProblem &hp = h->hp;
@@ -368,7 +375,7 @@ void window_setup(bellman_handle *h) {
         const int boxes = (w1 + 255) / 256;
         const int box1 = (w1 + boxes - 1) / boxes;
         w1 = boxes * box1;
-        const size_t bytes = 2 * (size_t)w0 * w1 * 8 + 128;
+        const size_t bytes = 2 * slot_bytes(w0, w1);
         if (bytes > budget1) continue;
         const int nch = (hp.C + cc - 1) / cc;
         double score = (double)std::min(cc, hp.C) / ((double)w0 * w1);
@@ -388,7 +395,18 @@ void window_setup(bellman_handle *h) {
     wp.nchunks = (hp.C + best_cc - 1) / best_cc;
     wp.ntile0 = (h->own_n[0] + WT0 - 1) / WT0;
     wp.ntile1 = (h->own_n[1] + WT1 - 1) / WT1;
-    ws->smem = 2 * (size_t)wp.win0 * wp.win1 * 8 + 128;
+    ws->smem = 2 * slot_bytes(wp.win0, wp.win1);
+    wp.buf_doubles = (int)(slot_bytes(wp.win0, wp.win1) / 8);
+    {   // fastest tile index = the dimension the control grid sweeps furthest (in cells)
+        double sweep[2] = {0.0, 0.0};
+        for (int d = 0; d < 2; ++d)
+            if (hp.has_c[d]) {
+                double mn, mx;
+                minmax_range(hp.Tc[d].data(), 0, hp.C, mn, mx);
+                sweep[d] = (mx - mn) * hp.inv_h[d][0];
+            }
+        wp.tj_fastest = sweep[1] >= sweep[0] ? 1 : 0;
+    }
     ws->hc0 = hp.has_c[0];
     ws->hc1 = hp.has_c[1];
 
@@ -405,13 +423,8 @@ void window_setup(bellman_handle *h) {
         return cudaMalloc(dptr, v.size() * sizeof(double)) == cudaSuccess &&
                cudaMemcpy(*dptr, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     };
-    std::vector<double> g0((size_t)hp.P * hp.n[0] * 2), g1((size_t)hp.P * hp.n[1] * 2);
-    for (size_t k = 0; k < (size_t)hp.P * hp.n[0]; ++k) { g0[2 * k] = hp.grid[0][k]; g0[2 * k + 1] = hp.rinv[0][k]; }
-    for (size_t k = 0; k < (size_t)hp.P * hp.n[1]; ++k) { g1[2 * k] = hp.grid[1][k]; g1[2 * k + 1] = hp.rinv[1][k]; }
-    if (!upload(cmm, &ws->d_cmm) || !upload(g0, &ws->d_gr0) || !upload(g1, &ws->d_gr1)) { delete ws; return; }
+    if (!upload(cmm, &ws->d_cmm)) { delete ws; return; }
     wp.cmm = static_cast<const double *>(ws->d_cmm);
-    wp.gr0 = static_cast<const double2 *>(ws->d_gr0);
-    wp.gr1 = static_cast<const double2 *>(ws->d_gr1);
 
     // one tensor map per J slot: [P][ext_n1][ext_n0] fp64, box = win0 x box1 x 1
     const int nslots = h->store_J_all ? hp.N : 2;
@@ -442,7 +455,7 @@ void window_setup(bellman_handle *h) {
 void window_teardown(bellman_handle *h) {
     auto *ws = static_cast<WindowState *>(h->wstate);
     if (!ws) return;
-    cudaFree(ws->d_cmm); cudaFree(ws->d_gr0); cudaFree(ws->d_gr1);
+    cudaFree(ws->d_cmm);
     delete ws;
     h->wstate = nullptr;
 }

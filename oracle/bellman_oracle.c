@@ -46,7 +46,7 @@ static int grid_is_uniform(const double *s, int n)
     const double h = (s[n - 1] - s[0]) / (double)(n - 1);
     for (int i = 0; i < n; ++i) {
         const double dev = fabs(s[i] - (s[0] + (double)i * h));
-        if (!(dev <= 1e-9 * h)) return 0;
+        if (!(dev <= 1e-14 * (s[n - 1] - s[0]))) return 0;
     }
     return 1;
 }
@@ -76,6 +76,7 @@ static inline int locate(const dimtab *g, double x, double *t)
                                                          like the GPU's saturating cvt.rmi.s32.f64 */
         else if (gg >= (double)(g->n - 1)) cell = g->n - 2;
         else cell = (int)gg;
+        *t = gg - (double)cell;
     } else {
         int lo = 0, hi = g->n;                        /* count of s[i] <= x */
         while (lo < hi) {
@@ -85,8 +86,8 @@ static inline int locate(const dimtab *g, double x, double *t)
         cell = lo - 1;
         if (cell < 0) cell = 0;
         if (cell > g->n - 2) cell = g->n - 2;
+        *t = (x - g->s[cell]) * g->rinv[cell];
     }
-    *t = (x - g->s[cell]) * g->rinv[cell];
     return cell;
 }
 
