@@ -17,6 +17,7 @@
 #include <algorithm>
 #include <cstring>
 #include <limits>
+#include <type_traits>
 #include <vector>
 
 #include "bellman_handle.h"
@@ -79,9 +80,11 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ int cell_uniform(double x, double inv_h, double off, int n) {
     return min(max(__double2int_rd(fma(x, inv_h, off)), 0), n - 2);
 }
+template <bool CLAMP = true>
 __device__ __forceinline__ int locate_uniform(double x, double inv_h, double off, int n, double &t) {
     const double g = fma(x, inv_h, off);
-    const int cell = min(max(__double2int_rd(g), 0), n - 2);
+    int cell = __double2int_rd(g);
+    if (CLAMP) cell = min(max(cell, 0), n - 2);   // skipped when the whole chunk is known to be interior
     t = g - (double)cell;
     return cell;
 }
@@ -202,16 +205,15 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         gs[m] = sp.q_order[0] == 0 ? qa + qb : qb + qa;
         best[m] = __longlong_as_double(0x7ff0000000000000LL);
         arg[m] = 0;
-        if (!HC0) cellK0[m] = locate_uniform(b0, inv_h0, off0, n0, tK0[m]);
-        if (!HC1) cellK1[m] = locate_uniform(b1, inv_h1, off1, n1, tK1[m]);
+        if (!HC0) cellK0[m] = locate_uniform<true>(b0, inv_h0, off0, n0, tK0[m]);
+        if (!HC1) cellK1[m] = locate_uniform<true>(b1, inv_h1, off1, n1, tK1[m]);
     }
 
     const int W0 = wp.win0;
-    for (int ch = 0; ch < wp.nchunks; ++ch) {
-        int r0, c0;
-        origin(ch, r0, c0);
-        mbar_wait(&mbar[ch & 1], (ch >> 1) & 1);
-        const double *__restrict__ W = ring + (ch & 1) * wp.buf_doubles;
+    // the control loop over one staged chunk; CLAMP = false when every query of the chunk falls in
+    // an interior cell (decided from the same exact bounds that place the window)
+    auto chunk_loop = [&](auto clamp_tag, int ch, const double *__restrict__ Wb) {
+        constexpr bool CLAMP = decltype(clamp_tag)::value;
         const int c_end = min(sp.C, (ch + 1) * wp.cchunk);
         for (int c = ch * wp.cchunk; c < c_end; ++c) {
             const double bu0 = HC0 ? __ldg(Tc0 + c) : 0.0;
@@ -226,17 +228,17 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                     const int m = mb + u;
-                    int rel0, rel1;          // cell index relative to the window origin
-                    if (HC0) rel0 = locate_uniform(base0[m] + bu0, inv_h0, off0, n0, t0[u]) - r0;
-                    else { rel0 = cellK0[m] - r0; t0[u] = tK0[m]; }
-                    if (HC1) rel1 = locate_uniform(base1[m] + bu1, inv_h1, off1, n1, t1[u]) - c0;
-                    else { rel1 = cellK1[m] - c0; t1[u] = tK1[m]; }
-                    off[u] = rel1 * W0 + rel0;
+                    int cell0, cell1;
+                    if (HC0) cell0 = locate_uniform<CLAMP>(base0[m] + bu0, inv_h0, off0, n0, t0[u]);
+                    else { cell0 = cellK0[m]; t0[u] = tK0[m]; }
+                    if (HC1) cell1 = locate_uniform<CLAMP>(base1[m] + bu1, inv_h1, off1, n1, t1[u]);
+                    else { cell1 = cellK1[m]; t1[u] = tK1[m]; }
+                    off[u] = cell1 * W0 + cell0;      // Wb already carries the window origin
                 }
                 double v00[4], v10[4], v01[4], v11[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const double *p = W + off[u];
+                    const double *p = Wb + off[u];
                     v00[u] = p[0]; v10[u] = p[1]; v01[u] = p[W0]; v11[u] = p[W0 + 1];
                 }
 #pragma unroll
@@ -250,6 +252,23 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
                 }
             }
         }
+    };
+
+    for (int ch = 0; ch < wp.nchunks; ++ch) {
+        // exact bounds of this chunk's queries, formed with the kernel's own association
+        double lo0 = tmm[0], hi0 = tmm[1], lo1 = tmm[4], hi1 = tmm[5];
+        if (Tb0) { lo0 = lo0 + tmm[2]; hi0 = hi0 + tmm[3]; }
+        if (Tb1) { lo1 = lo1 + tmm[6]; hi1 = hi1 + tmm[7]; }
+        if (HC0) { lo0 = lo0 + __ldg(cmm + 4 * ch); hi0 = hi0 + __ldg(cmm + 4 * ch + 1); }
+        if (HC1) { lo1 = lo1 + __ldg(cmm + 4 * ch + 2); hi1 = hi1 + __ldg(cmm + 4 * ch + 3); }
+        const bool interior = fma(lo0, inv_h0, off0) >= 0.0 && fma(hi0, inv_h0, off0) < (double)(n0 - 1) &&
+                              fma(lo1, inv_h1, off1) >= 0.0 && fma(hi1, inv_h1, off1) < (double)(n1 - 1);
+        int r0, c0;
+        origin(ch, r0, c0);
+        mbar_wait(&mbar[ch & 1], (ch >> 1) & 1);
+        const double *__restrict__ Wb = ring + (ch & 1) * wp.buf_doubles - (c0 * W0 + r0);
+        if (interior) chunk_loop(std::false_type{}, ch, Wb);
+        else chunk_loop(std::true_type{}, ch, Wb);
         __syncthreads();   // every thread is done with this buffer
         if (tid == 0 && ch + 2 < wp.nchunks) issue(ch + 2);
     }

@@ -1,0 +1,70 @@
+"""Run under torchrun (one rank per GPU): slab-partitioned sweep through libbellman.so + NCCL halo
+exchange, every rank's slab compared bit for bit with the single-process CPU oracle.
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P scripts/multi_gpu_check.py [kirk|attitude|pos_att]
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import bellman_b200 as bb  # noqa: E402
+from oracle import cbind  # noqa: E402
+
+
+def make(kind):
+    if kind == "kirk":
+        o = bb.Dynamic_Solver()
+        return bb.tables.kirk_desc(o.A, o.B, o.Q, o.R, 12, o.x_min, o.x_max, 256, o.u_min, o.u_max, 48,
+                                   store_J_all=False, store_idx_all=False)
+    if kind == "attitude":
+        s = bb.Solver_attitude()
+        s.n_mesh_w, s.n_mesh_t = 400, 120
+        return bb.tables.stack_problems(s._axis_descs())
+    s = bb.Solver_pos_att()
+    s.n_mesh_x, s.n_mesh_v, s.n_mesh_t, s.n_mesh_w = 12, 10, 8, 15
+    return s.channel_desc(0)
+
+
+def main():
+    kind = sys.argv[1] if len(sys.argv) > 1 else "kirk"
+    rank, world, local = (int(os.environ[k]) for k in ("RANK", "WORLD_SIZE", "LOCAL_RANK"))
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    d = make(kind)
+    part_dim = d.D - 1
+    sw = bb.Sweep(d, device=local, part_dim=part_dim, rank=rank, nranks=world)
+    ids = [bb.get_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    sw.comm_init(ids[0])
+    n_stages = 6
+    ok = True
+    for kernel in (bb.KERNEL_DIRECT, bb.KERNEL_AUTO):
+        sw.set_J(None)
+        sw.run(n_stages, kernel=kernel)
+        J, idx = sw.get_J(), sw.get_idx()
+        ref = cbind.sweep(d, n_stages=n_stages)
+        lo, hi = sw.slab[0], sw.slab[1]
+        inner = int(np.prod(d.n[:part_dim]))
+        Jr = ref["J_last"].reshape(d.P, -1, inner)[:, lo:hi, :].reshape(d.P, -1)
+        Ir = ref["idx_last"].reshape(d.P, -1, inner)[:, lo:hi, :].reshape(d.P, -1)
+        good = bool(np.array_equal(J, Jr) and np.array_equal(idx, Ir))
+        print(f"rank {rank}/{world} {kind} kernel={sw.last_kernel} slab={sw.slab} "
+              f"{'OK' if good else 'MISMATCH'} exchange_ms={sw.stats()['ms_exchange']:.3f}", flush=True)
+        ok = ok and good
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    sw.close()
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+if __name__ == "__main__":
+    main()
