@@ -1,0 +1,105 @@
+classdef Solver_attitude < handle
+    %SOLVER_ATTITUDE  Three (w, theta) axes with three torque levels, B200 back end.
+    %   Drop-in for simplified_run of the reference class (attitude-control/Solver_attitude.m
+    %   :196-259, :625-667).  The full 6-D run() of the reference never executed (SURVEY 2.3) and
+    %   is not provided; the forward simulations are outside this build's scope.
+
+    properties
+        w_min
+        w_max
+        n_mesh_w
+        yaw_min
+        yaw_max
+        pitch_min
+        pitch_max
+        roll_min
+        roll_max
+        n_mesh_q
+        n_mesh_t
+        InertiaM
+        J1
+        J2
+        J3
+        Q1
+        Q2
+        Q3
+        Q4
+        Q5
+        Q6
+        R1
+        R2
+        R3
+        Qt1
+        Qt2
+        Qt3
+        T_final
+        h
+        N_stage
+        defaultX0
+        U_vector
+        U1_Opt
+        U2_Opt
+        U3_Opt
+        F_Values
+        U_idx
+        device = -1
+    end
+
+    methods
+        function this = Solver_attitude()
+            this.w_min = -deg2rad(50);  this.w_max = -deg2rad(-50);  this.n_mesh_w = 1000;
+            this.yaw_min = -30;  this.yaw_max = 30;
+            this.pitch_min = -20;  this.pitch_max = 20;
+            this.roll_min = -35;  this.roll_max = 35;
+            this.n_mesh_q = 10;  this.n_mesh_t = 300;
+            i1 = 0.02836 + 0.00016; i2 = 0.026817 + 0.00150; i3 = 0.023 + 0.00150;
+            i4 = -0.0000837; i5 = 0.000014; i6 = -0.00029;
+            this.InertiaM = [i1 i4 i5; i4 i2 i6; i5 i6 i3];
+            this.Q1 = 6; this.Q2 = 6; this.Q3 = 6; this.Q4 = 6; this.Q5 = 6; this.Q6 = 6;
+            this.R1 = 4; this.R2 = 4; this.R3 = 4;
+            this.Qt1 = this.Q4; this.Qt2 = this.Q5; this.Qt3 = this.Q6;
+            this.T_final = 30;  this.h = 0.005;
+            this.N_stage = ceil(this.T_final/this.h);
+            this.J1 = this.InertiaM(1); this.J2 = this.InertiaM(5); this.J3 = this.InertiaM(9);
+            this.U_vector = [-0.11 0 0.11];
+        end
+
+        function simplified_run(obj, n_stages)
+            obj.N_stage = ceil(obj.T_final/obj.h);
+            if nargin < 2, n_stages = obj.N_stage - 1; end
+            s_w = linspace(obj.w_min, obj.w_max, obj.n_mesh_w).';
+            lim = [obj.yaw_min obj.yaw_max; obj.pitch_min obj.pitch_max; obj.roll_min obj.roll_max];
+            s_t = zeros(obj.n_mesh_t, 3);
+            for a = 1:3, s_t(:,a) = linspace(deg2rad(lim(a,1)), deg2rad(lim(a,2)), obj.n_mesh_t).'; end
+            U = obj.U_vector(:);  hh = obj.h;  Jax = [obj.J1 obj.J2 obj.J3];
+            k1 = s_w; k2 = s_w + k1*hh/2; k3 = s_w + k2*hh/2; k4 = s_w + k3*hh;
+            inct = hh*(k1 + 2*k2 + 2*k3 + k4)/6;             % theta' = T + inct(w)
+            incw = zeros(numel(U), 3);
+            for a = 1:3, kk = U/Jax(a); incw(:,a) = hh*(kk + 2*kk + 2*kk + kk)/6; end
+            Qw = [obj.Q1 obj.Q2 obj.Q3]; Qt = [obj.Qt1 obj.Qt2 obj.Qt3]; R = [obj.R1 obj.R2 obj.R3];
+            rep = @(v) repmat(v, 1, 3);
+            d.n = [obj.n_mesh_w, obj.n_mesh_t];  d.C = numel(U);  d.P = 3;  d.N = obj.N_stage;
+            d.grid = {rep(s_w), s_t};
+            d.src_a = [1 2];  d.src_b = [0 1];  d.q_order = [1 2];
+            d.Ta = {rep(s_w), s_t};
+            d.Tb = {[], rep(inct)};
+            d.Tc = {incw, []};
+            qt = zeros(size(s_t)); for a = 1:3, qt(:,a) = Qt(a)*s_t(:,a).^2; end
+            d.q  = {(s_w.^2)*Qw, qt};
+            d.r  = (U.^2)*R;
+            d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
+            hnd = bellman_mex('create', d);
+            tic
+            bellman_mex('run', hnd, n_stages, struct());
+            fprintf('%d stages - %f seconds\n', n_stages, toc)
+            sz = [obj.n_mesh_w, obj.n_mesh_t, 3];
+            obj.F_Values = reshape(bellman_mex('get_J', hnd), sz);
+            obj.U_idx = double(reshape(bellman_mex('get_idx', hnd), sz));
+            bellman_mex('destroy', hnd);
+            obj.U1_Opt = griddedInterpolant({s_w.', s_t(:,1).'}, obj.U_vector(obj.U_idx(:,:,1)), 'nearest');
+            obj.U2_Opt = griddedInterpolant({s_w.', s_t(:,2).'}, obj.U_vector(obj.U_idx(:,:,2)), 'nearest');
+            obj.U3_Opt = griddedInterpolant({s_w.', s_t(:,3).'}, obj.U_vector(obj.U_idx(:,:,3)), 'nearest');
+            fprintf('...Done!\n')
+        end
+    end
+end

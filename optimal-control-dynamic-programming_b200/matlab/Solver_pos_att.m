@@ -1,0 +1,184 @@
+classdef Solver_pos_att < handle
+    %SOLVER_POS_ATT  Coupled position+attitude channels on a 4-D (x, v, theta, w) grid, B200 back end.
+    %   Drop-in for the sweep path of the reference class (pos-att/Solver_pos_att.m):
+    %   simplified_run (:197-242), calculate_one_channel_U_Opt (:244-297), set_controller
+    %   (:849-884), vectors_allcomb (:886-904), sym_linspace (:906-918).  fp64 throughout (the
+    %   reference casts J to single); idsum50_prev starts at 0 (the reference reads it undefined).
+    %   The 13-state ode45 forward simulation is outside this build's scope.
+
+    properties
+        v_min
+        v_max
+        n_mesh_v
+        x_min
+        x_max
+        n_mesh_x
+        w_min
+        w_max
+        n_mesh_w
+        theta1_min
+        theta1_max
+        theta2_min
+        theta2_max
+        theta3_min
+        theta3_max
+        n_mesh_t
+        Mass
+        InertiaM
+        J1
+        J2
+        J3
+        Qx1
+        Qx2
+        Qx3
+        Qv1
+        Qv2
+        Qv3
+        Qt1
+        Qt2
+        Qt3
+        Qw1
+        Qw2
+        Qw3
+        R1
+        R2
+        R3
+        T_final
+        h
+        N_stage
+        defaultX0
+        T_dist
+        F_Thr0
+        F_Thr1
+        F_Thr2
+        F_Thr3
+        F_Thr4
+        F_Thr5
+        F_Thr6
+        F_Thr7
+        F_Thr8
+        F_Thr9
+        F_Thr10
+        F_Thr11
+        Opt_F_Thr0
+        Opt_F_Thr1
+        Opt_F_Thr2
+        Opt_F_Thr3
+        Opt_F_Thr4
+        Opt_F_Thr5
+        Opt_F_Thr6
+        Opt_F_Thr7
+        Opt_F_Thr8
+        Opt_F_Thr9
+        Opt_F_Thr10
+        Opt_F_Thr11
+        device = -1
+    end
+
+    methods
+        function this = Solver_pos_att()
+            this.v_min = -0.1;  this.v_max = 0.1;  this.n_mesh_v = 30;
+            this.x_min = -0.2;  this.x_max = 0.2;  this.n_mesh_x = 30;
+            this.w_min = deg2rad(-2);  this.w_max = deg2rad(2);  this.n_mesh_w = 15;
+            this.theta1_min = -5; this.theta1_max = 5;
+            this.theta2_min = -6; this.theta2_max = 6;
+            this.theta3_min = -7; this.theta3_max = 7;
+            this.n_mesh_t = 20;
+            this.Mass = 4.16;
+            i1 = 0.02836 + 0.00016; i2 = 0.026817 + 0.00150; i3 = 0.023 + 0.00150;
+            i4 = -0.0000837; i5 = 0.000014; i6 = -0.00029;
+            this.InertiaM = [i1 i4 i5; i4 i2 i6; i5 i6 i3];
+            this.J1 = this.InertiaM(1); this.J2 = this.InertiaM(5); this.J3 = this.InertiaM(9);
+            this.Qx1 = 6; this.Qx2 = 6; this.Qx3 = 6; this.Qv1 = 6; this.Qv2 = 6; this.Qv3 = 6;
+            this.Qt1 = .5; this.Qt2 = .5; this.Qt3 = .5; this.Qw1 = .5; this.Qw2 = .5; this.Qw3 = .5;
+            this.R1 = 0.1; this.R2 = 0.1; this.R3 = 0.1;
+            this.T_final = 10;  this.h = 0.005;
+            this.N_stage = ceil(this.T_final/this.h);
+            this.defaultX0 = zeros(9,1);
+            T = 0.13;  this.T_dist = 9.65E-2;
+            this.F_Thr0 = [0 T];  this.F_Thr1 = [0 T];  this.F_Thr6 = -[0 T];  this.F_Thr7 = -[0 T];
+            this.F_Thr2 = [0 T];  this.F_Thr3 = [0 T];  this.F_Thr8 = -[0 T];  this.F_Thr9 = -[0 T];
+            this.F_Thr4 = [0 T];  this.F_Thr5 = [0 T];  this.F_Thr10 = -[0 T]; this.F_Thr11 = -[0 T];
+        end
+
+        function simplified_run(obj)
+            sl = @(a,b,n) obj.sym_linspace(a, b, n);
+            s_x = sl(obj.x_min, obj.x_max, obj.n_mesh_x);  s_v = sl(obj.v_min, obj.v_max, obj.n_mesh_v);
+            s_w = sl(obj.w_min, obj.w_max, obj.n_mesh_w);
+            s_t1 = sl(deg2rad(obj.theta1_min), deg2rad(obj.theta1_max), obj.n_mesh_t);
+            s_t2 = sl(deg2rad(obj.theta2_min), deg2rad(obj.theta2_max), obj.n_mesh_t);
+            s_t3 = sl(deg2rad(obj.theta3_min), deg2rad(obj.theta3_max), obj.n_mesh_t);
+            obj.calculate_one_channel_U_Opt(s_x, s_v, s_t1, s_w, obj.F_Thr0, obj.F_Thr1, obj.F_Thr6, obj.F_Thr7, ...
+                obj.Qx1, obj.Qv1, obj.Qt1, obj.Qw1, obj.R1, obj.J2, 'channel_x_controller_1');
+            obj.calculate_one_channel_U_Opt(s_x, s_v, s_t2, s_w, obj.F_Thr2, obj.F_Thr3, obj.F_Thr8, obj.F_Thr9, ...
+                obj.Qx2, obj.Qv2, obj.Qt2, obj.Qw2, obj.R2, obj.J3, 'channel_y_controller_1');
+            obj.calculate_one_channel_U_Opt(s_x, s_v, s_t3, s_w, obj.F_Thr4, obj.F_Thr5, obj.F_Thr10, obj.F_Thr11, ...
+                obj.Qx3, obj.Qv3, obj.Qt3, obj.Qw3, obj.R3, obj.J1, 'channel_z_controller_1');
+            obj.calculate_one_channel_U_Opt(s_x, s_v, s_t1, s_w, 0, obj.F_Thr1, obj.F_Thr6, obj.F_Thr7, ...
+                obj.Qx1, obj.Qv1, obj.Qt1, obj.Qw1, obj.R1, obj.J2, 'channel_x_controller_1_failure');
+        end
+
+        function calculate_one_channel_U_Opt(obj, s_x, s_v, s_t, s_w, f0, f1, f6, f7, Qx, Qv, Qt, Qw, R, J, file_name)
+            [f0_allcomb, f1_allcomb, f6_allcomb, f7_allcomb] = obj.vectors_allcomb(f0, f1, f6, f7);
+            s_x = s_x(:); s_v = s_v(:); s_t = s_t(:); s_w = s_w(:);  hh = obj.h;  dd = obj.T_dist;
+            v_dot = (f0_allcomb + f1_allcomb + f6_allcomb + f7_allcomb)/obj.Mass;
+            w_dot = (f0_allcomb*dd + f1_allcomb*(-dd) + f6_allcomb*dd + f7_allcomb*(-dd))/J;
+            d.n = [numel(s_x), numel(s_v), numel(s_t), numel(s_w)];
+            d.C = numel(f0_allcomb);  d.P = 1;  d.N = obj.N_stage;
+            d.grid = {s_x, s_v, s_t, s_w};
+            d.src_a = [1 2 3 4];  d.src_b = [2 0 4 0];
+            d.Ta = {s_x, s_v, s_t, s_w};
+            d.Tb = {hh*s_v, [], hh*s_w, []};
+            d.Tc = {[], hh*v_dot, [], hh*w_dot};
+            d.q_order = [1 2 4 3];                       % Qx x^2 + Qv v^2 + Qw w^2 + Qt t^2
+            d.q  = {Qx*s_x.^2, Qv*s_v.^2, Qt*s_t.^2, Qw*s_w.^2};
+            d.r  = R*f0_allcomb.^2 + R*f1_allcomb.^2 + R*f6_allcomb.^2 + R*f7_allcomb.^2;
+            d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
+            hnd = bellman_mex('create', d);
+            tic
+            bellman_mex('run', hnd, obj.N_stage - 1, struct('check_period', 50, 'check_tol', 1e-2));
+            lg = bellman_mex('check_log', hnd);
+            prev = [0; 0];
+            for k = 1:size(lg, 2)
+                fprintf('stage %d - errorF %f - errorU %f\n', lg(1,k), lg(2,k) - prev(1), lg(3,k) - prev(2));
+                prev = lg(2:3,k);
+            end
+            if bellman_mex('current_stage', hnd) > 1
+                fprintf('sum of errors in the last 50 stages is under tolerance, breaking loop...\n')
+            end
+            fprintf('%f seconds\n', toc)
+            F_gI = griddedInterpolant({s_x.', s_v.', s_t.', s_w.'}, reshape(bellman_mex('get_J', hnd), d.n), 'linear');
+            U_Optimal_id = double(reshape(bellman_mex('get_idx', hnd), d.n));
+            bellman_mex('destroy', hnd);
+            save(file_name, 'F_gI', 'U_Optimal_id', 'f0_allcomb', 'f1_allcomb', 'f6_allcomb', 'f7_allcomb')
+            fprintf('\nstage calculations complete.\n')
+        end
+
+        function set_controller(obj, file, channel)
+            C = load(file);
+            mk = @(f) griddedInterpolant(C.F_gI.GridVectors, f(C.U_Optimal_id), 'nearest');
+            g0 = mk(C.f0_allcomb); g1 = mk(C.f1_allcomb); g6 = mk(C.f6_allcomb); g7 = mk(C.f7_allcomb);
+            switch channel
+                case 'x', obj.Opt_F_Thr0 = g0; obj.Opt_F_Thr1 = g1; obj.Opt_F_Thr6 = g6; obj.Opt_F_Thr7 = g7;
+                case 'y', obj.Opt_F_Thr2 = g0; obj.Opt_F_Thr3 = g1; obj.Opt_F_Thr8 = g6; obj.Opt_F_Thr9 = g7;
+                case 'z', obj.Opt_F_Thr4 = g0; obj.Opt_F_Thr5 = g1; obj.Opt_F_Thr10 = g6; obj.Opt_F_Thr11 = g7;
+                otherwise, error('wrong channel, must be one of x-y-z values')
+            end
+        end
+
+        function [a1, a2, a3, a4] = vectors_allcomb(~, f1, f2, f3, f4)
+            [g1, g2, g3, g4] = ndgrid(f1, f2, f3, f4);
+            g1 = g1(:); g2 = g2(:); g3 = g3(:); g4 = g4(:);
+            keep = ~((g1 > 0 & g3 < 0) | (g2 > 0 & g4 < 0));   % no opposing thrusters at once
+            a1 = g1(keep); a2 = g2(keep); a3 = g3(keep); a4 = g4(keep);
+        end
+
+        function v = sym_linspace(~, a, b, n)
+            if a > 0, error('minimum states are not negative, use normal linspace'); end
+            half = ceil(n/2);
+            if mod(n, 2) == 0, lo = linspace(a, 0, half + 1); else, lo = linspace(a, 0, half); end
+            hi = linspace(0, b, half);
+            v = [lo, hi(2:end)];
+        end
+    end
+end

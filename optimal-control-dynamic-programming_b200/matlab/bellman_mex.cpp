@@ -1,0 +1,230 @@
+// bellman_mex.cpp — thin MEX gateway over the C ABI of libbellman.so (include/bellman.h).
+//
+//   h      = bellman_mex('create', desc)              desc: struct, see Dynamic_Solver.m (build_desc)
+//            bellman_mex('set_J', h, J)               J: S x P double (terminal cost / resume), [] = zeros
+//            bellman_mex('run', h, n_stages, opts)    opts: struct with optional fields kernel,
+//                                                     check_period, check_tol, use_graph, sync_each_stage
+//   k      = bellman_mex('current_stage', h)
+//   J      = bellman_mex('get_J', h, stage)           S_own x P double, column-major like F.Values(:)
+//   idx    = bellman_mex('get_idx', h, stage)         S_own x P int32, 1-BASED (MATLAB's min index)
+//   log    = bellman_mex('check_log', h)              3 x n double: stage; sum(J); sum(idx)
+//   s      = bellman_mex('stats', h)                  struct: ms, launches, ms_exchange, kernel
+//   [X,U]  = bellman_mex('rollout', h, N, A, B, u_values, X0, mode, ssu_stage)   X0: 2 x batch,
+//                                                     X: 2 x (N*batch), U: N x batch
+//            bellman_mex('destroy', h)
+//   v      = bellman_mex('version')
+//
+// Arrays cross as column-major double / int32 with no transposition.  Library error codes become
+// mexErrMsgIdAndTxt('bellman:<code>', message).  The MEX file is locked while handles are alive
+// and frees them at exit.  There is no CPU fallback: without a B200 'create' raises bellman:CUDA.
+//
+// Build (on a machine with MATLAB):  mex -R2018a bellman_mex.cpp -I../../include -L.. -lbellman
+#include <cstdint>
+#include <cstring>
+#include <set>
+#include <string>
+#include <vector>
+
+#include "mex.h"
+
+#include "bellman.h"
+
+static std::set<bellman_handle *> g_live;
+
+static void at_exit() {
+    for (bellman_handle *h : g_live) bellman_destroy(h);
+    g_live.clear();
+}
+
+static const char *code_name(int rc) {
+    switch (rc) {
+        case BELLMAN_ERR_BAD_ARG: return "bellman:BAD_ARG";
+        case BELLMAN_ERR_CUDA: return "bellman:CUDA";
+        case BELLMAN_ERR_NCCL: return "bellman:NCCL";
+        case BELLMAN_ERR_OOM: return "bellman:OOM";
+        case BELLMAN_ERR_NOT_RUN: return "bellman:NOT_RUN";
+        case BELLMAN_ERR_STATE: return "bellman:STATE";
+        default: return "bellman:UNKNOWN";
+    }
+}
+
+static void check(int rc, bellman_handle *h) {
+    if (rc != BELLMAN_OK) mexErrMsgIdAndTxt(code_name(rc), "%s", bellman_last_error(h));
+}
+
+static bellman_handle *get_handle(const mxArray *a) {
+    if (!mxIsClass(a, "uint64") || mxGetNumberOfElements(a) != 1)
+        mexErrMsgIdAndTxt("bellman:BAD_ARG", "handle must be a uint64 scalar");
+    bellman_handle *h = reinterpret_cast<bellman_handle *>(*static_cast<uint64_t *>(mxGetData(a)));
+    if (!g_live.count(h)) mexErrMsgIdAndTxt("bellman:BAD_ARG", "stale or foreign handle");
+    return h;
+}
+
+static double field_scalar(const mxArray *s, const char *name, double dflt) {
+    const mxArray *f = mxGetField(s, 0, name);
+    return (f && !mxIsEmpty(f)) ? mxGetScalar(f) : dflt;
+}
+
+// cell field `name`, entry d -> pointer to doubles (or NULL when the entry is []), size checked
+static const double *cell_table(const mxArray *s, const char *name, int d, size_t want, bool optional) {
+    const mxArray *c = mxGetField(s, 0, name);
+    if (!c || !mxIsCell(c) || mxGetNumberOfElements(c) <= (size_t)d)
+        mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc.%s must be a cell with one entry per dimension", name);
+    const mxArray *e = mxGetCell(c, d);
+    if (!e || mxIsEmpty(e)) {
+        if (!optional) mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc.%s{%d} is empty", name, d + 1);
+        return nullptr;
+    }
+    if (!mxIsDouble(e) || mxGetNumberOfElements(e) != want)
+        mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc.%s{%d} must be double with %d elements", name, d + 1, (int)want);
+    return mxGetPr(e);
+}
+
+static void cmd_create(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    if (nrhs != 2 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: h = bellman_mex('create', desc)");
+    const mxArray *s = prhs[1];
+    bellman_desc d;
+    std::memset(&d, 0, sizeof(d));
+    d.struct_size = (int32_t)sizeof(d);
+    const mxArray *nn = mxGetField(s, 0, "n");
+    if (!nn || !mxIsDouble(nn)) mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc.n must be a double row vector");
+    d.D = (int32_t)mxGetNumberOfElements(nn);
+    if (d.D < 2 || d.D > BELLMAN_MAX_DIM) mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc.n must have 2..4 entries");
+    for (int k = 0; k < d.D; ++k) d.n[k] = (int32_t)mxGetPr(nn)[k];
+    d.C = (int32_t)field_scalar(s, "C", 0);
+    d.P = (int32_t)field_scalar(s, "P", 1);
+    d.N = (int32_t)field_scalar(s, "N", 0);
+    const mxArray *sa = mxGetField(s, 0, "src_a"), *sb = mxGetField(s, 0, "src_b"), *qo = mxGetField(s, 0, "q_order");
+    if (!sa || !sb || !qo) mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc needs src_a, src_b, q_order (1-based, 0 = absent)");
+    for (int k = 0; k < d.D; ++k) {
+        d.src_a[k] = (int32_t)mxGetPr(sa)[k] - 1;          // MATLAB dims are 1-based
+        d.src_b[k] = (int32_t)mxGetPr(sb)[k] - 1;          // 0 -> -1 = absent
+        d.q_order[k] = (int32_t)mxGetPr(qo)[k] - 1;
+    }
+    for (int k = 0; k < d.D; ++k) {
+        const size_t P = (size_t)d.P;
+        d.grid[k] = cell_table(s, "grid", k, P * d.n[k], false);
+        d.q[k] = cell_table(s, "q", k, P * d.n[k], false);
+        if (d.src_a[k] < 0 || d.src_a[k] >= d.D) mexErrMsgIdAndTxt("bellman:BAD_ARG", "src_a out of range");
+        d.Ta[k] = cell_table(s, "Ta", k, P * d.n[d.src_a[k]], false);
+        d.Tb[k] = d.src_b[k] >= 0 ? cell_table(s, "Tb", k, P * d.n[d.src_b[k]], false) : nullptr;
+        d.Tc[k] = cell_table(s, "Tc", k, P * d.C, true);
+    }
+    const mxArray *r = mxGetField(s, 0, "r");
+    if (!r || !mxIsDouble(r) || mxGetNumberOfElements(r) != (size_t)d.P * d.C)
+        mexErrMsgIdAndTxt("bellman:BAD_ARG", "desc.r must be C x P double");
+    d.r = mxGetPr(r);
+    d.store_J_all = (int32_t)field_scalar(s, "store_J_all", 0);
+    d.store_idx_all = (int32_t)field_scalar(s, "store_idx_all", 0);
+    d.device = (int32_t)field_scalar(s, "device", -1);
+    d.part_dim = (int32_t)field_scalar(s, "part_dim", 0) - 1;
+    d.rank = (int32_t)field_scalar(s, "rank", 0);
+    d.nranks = (int32_t)field_scalar(s, "nranks", 1);
+    bellman_handle *h = nullptr;
+    check(bellman_create(&d, &h), nullptr);
+    if (g_live.empty()) { mexLock(); mexAtExit(at_exit); }
+    g_live.insert(h);
+    plhs[0] = mxCreateNumericMatrix(1, 1, mxUINT64_CLASS, mxREAL);
+    *static_cast<uint64_t *>(mxGetData(plhs[0])) = reinterpret_cast<uint64_t>(h);
+    (void)nlhs;
+}
+
+struct Shape { size_t S_own, P; };
+static std::vector<std::pair<bellman_handle *, Shape>> g_shapes;
+
+static Shape shape_of(bellman_handle *h) {
+    for (auto &p : g_shapes) if (p.first == h) return p.second;
+    mexErrMsgIdAndTxt("bellman:BAD_ARG", "unknown handle");
+    return Shape{0, 0};
+}
+
+void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    if (nrhs < 1 || !mxIsChar(prhs[0])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "first argument must be a command string");
+    char *c = mxArrayToString(prhs[0]);
+    const std::string cmd(c);
+    mxFree(c);
+
+    if (cmd == "version") { plhs[0] = mxCreateDoubleScalar(bellman_version()); return; }
+    if (cmd == "create") {
+        cmd_create(nlhs, plhs, nrhs, prhs);
+        bellman_handle *h = reinterpret_cast<bellman_handle *>(*static_cast<uint64_t *>(mxGetData(plhs[0])));
+        // remember the owned shape for get_J / get_idx
+        const mxArray *s = prhs[1];
+        const mxArray *nn = mxGetField(s, 0, "n");
+        bellman_slab sl;
+        bellman_owned_range(h, &sl);
+        const int D = (int)mxGetNumberOfElements(nn);
+        const int pd = (int)field_scalar(s, "part_dim", 0) - 1;
+        size_t S = 1;
+        for (int k = 0; k < D; ++k) S *= (k == pd) ? (size_t)(sl.own_hi - sl.own_lo) : (size_t)mxGetPr(nn)[k];
+        g_shapes.push_back({h, Shape{S, (size_t)field_scalar(s, "P", 1)}});
+        return;
+    }
+    if (nrhs < 2) mexErrMsgIdAndTxt("bellman:BAD_ARG", "missing handle");
+    bellman_handle *h = get_handle(prhs[1]);
+    const Shape sh = shape_of(h);
+
+    if (cmd == "destroy") {
+        bellman_destroy(h);
+        g_live.erase(h);
+        for (size_t i = 0; i < g_shapes.size(); ++i) if (g_shapes[i].first == h) { g_shapes.erase(g_shapes.begin() + i); break; }
+        if (g_live.empty()) mexUnlock();
+    } else if (cmd == "set_J") {
+        const double *J = (nrhs > 2 && !mxIsEmpty(prhs[2])) ? mxGetPr(prhs[2]) : nullptr;
+        check(bellman_set_J(h, J), h);
+    } else if (cmd == "run") {
+        if (nrhs < 3) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: bellman_mex('run', h, n_stages, opts)");
+        bellman_run_opts o;
+        std::memset(&o, 0, sizeof(o));
+        o.struct_size = (int32_t)sizeof(o);
+        if (nrhs > 3 && mxIsStruct(prhs[3])) {
+            o.kernel = (int32_t)field_scalar(prhs[3], "kernel", 0);
+            o.check_period = (int32_t)field_scalar(prhs[3], "check_period", 0);
+            o.check_tol = field_scalar(prhs[3], "check_tol", 0.0);
+            o.use_graph = (int32_t)field_scalar(prhs[3], "use_graph", 0);
+            o.sync_each_stage = (int32_t)field_scalar(prhs[3], "sync_each_stage", 0);
+        }
+        check(bellman_run(h, (int32_t)mxGetScalar(prhs[2]), &o), h);
+    } else if (cmd == "stage") {
+        check(bellman_stage(h), h);
+    } else if (cmd == "current_stage") {
+        plhs[0] = mxCreateDoubleScalar(bellman_current_stage(h));
+    } else if (cmd == "get_J") {
+        const int32_t stage = nrhs > 2 ? (int32_t)mxGetScalar(prhs[2]) : bellman_current_stage(h);
+        plhs[0] = mxCreateDoubleMatrix(sh.S_own, sh.P, mxREAL);
+        check(bellman_get_J(h, stage, mxGetPr(plhs[0])), h);
+    } else if (cmd == "get_idx") {
+        const int32_t stage = nrhs > 2 ? (int32_t)mxGetScalar(prhs[2]) : bellman_current_stage(h);
+        plhs[0] = mxCreateNumericMatrix(sh.S_own, sh.P, mxINT32_CLASS, mxREAL);
+        int32_t *p = static_cast<int32_t *>(mxGetData(plhs[0]));
+        check(bellman_get_idx(h, stage, p), h);
+        for (size_t k = 0; k < sh.S_own * sh.P; ++k) p[k] += 1;   // MATLAB's min() index is 1-based
+    } else if (cmd == "check_log") {
+        const int n = bellman_get_check_log(h, nullptr, 0);
+        plhs[0] = mxCreateDoubleMatrix(3, n > 0 ? n : 0, mxREAL);
+        if (n > 0) bellman_get_check_log(h, mxGetPr(plhs[0]), n);
+    } else if (cmd == "stats") {
+        double ms = 0, mx = 0;
+        int64_t launches = 0;
+        check(bellman_last_run_stats(h, &ms, &launches, &mx), h);
+        const char *names[] = {"ms", "launches", "ms_exchange", "kernel"};
+        plhs[0] = mxCreateStructMatrix(1, 1, 4, names);
+        mxSetField(plhs[0], 0, "ms", mxCreateDoubleScalar(ms));
+        mxSetField(plhs[0], 0, "launches", mxCreateDoubleScalar((double)launches));
+        mxSetField(plhs[0], 0, "ms_exchange", mxCreateDoubleScalar(mx));
+        mxSetField(plhs[0], 0, "kernel", mxCreateString(bellman_last_kernel(h)));
+    } else if (cmd == "rollout") {
+        // [X,U] = bellman_mex('rollout', h, N, A, B, u_values, X0, mode, ssu_stage)
+        if (nrhs < 9) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,U] = bellman_mex('rollout', h, N, A, B, u_values, X0, mode, ssu_stage)");
+        const int N = (int)mxGetScalar(prhs[2]);
+        const size_t batch = mxGetNumberOfElements(prhs[6]) / 2;
+        plhs[0] = mxCreateDoubleMatrix(2, (size_t)N * batch, mxREAL);     // [2][N][batch]
+        mxArray *U = mxCreateDoubleMatrix((size_t)N, batch, mxREAL);
+        check(bellman_rollout(h, mxGetPr(prhs[3]), mxGetPr(prhs[4]), mxGetPr(prhs[5]), mxGetPr(prhs[6]),
+                              (int32_t)batch, (int32_t)mxGetScalar(prhs[7]), (int32_t)mxGetScalar(prhs[8]),
+                              mxGetPr(plhs[0]), mxGetPr(U)), h);
+        if (nlhs > 1) plhs[1] = U;
+    } else {
+        mexErrMsgIdAndTxt("bellman:BAD_ARG", "unknown command '%s'", cmd.c_str());
+    }
+}

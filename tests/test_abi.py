@@ -74,3 +74,16 @@ def test_create_fails_loudly_without_gpu(bellman):
     with pytest.raises(bellman.BellmanError) as ei:
         d.run()
     assert ei.value.code == -2 and "no CPU fallback" in str(ei.value)
+
+
+def test_mex_gateway_compiles():
+    """The MEX gateway is syntax-checked against a stub mex.h (no MATLAB in this image)."""
+    import subprocess
+    mdir = os.path.join(ROOT, "optimal-control-dynamic-programming_b200", "matlab")
+    r = subprocess.run(["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-Werror", "-I" + os.path.join(mdir, "stub"),
+                        "-I" + os.path.join(ROOT, "include"), os.path.join(mdir, "bellman_mex.cpp")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    for f in ("Dynamic_Solver.m", "Solver_position.m", "Solver_attitude.m", "Solver_pos_att.m"):
+        src = open(os.path.join(mdir, f)).read()
+        assert src.startswith("classdef " + f[:-2] + " < handle") and "bellman_mex('create'" in src
