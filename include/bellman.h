@@ -46,18 +46,25 @@
  *       if tot < best (strictly): best = tot, arg = c        -> first index wins ties (MATLAB min)
  *   J_k[i] = best ; idx_k[i] = arg
  *
- *   locate_d(x) -> (cell, t):
- *     BELLMAN_LOCATE_UNIFORM : g = fma(x, inv_h, off);  cell = clamp( (int)floor(g), 0, n-2 );
- *                              t = g - (double)cell
- *                              inv_h = (n-1)/(s[n-1]-s[0]),  off = -(s[0]*inv_h)   (host, rounded once each)
+ *   locate_d(x) -> (cell, t), by the locate mode of dimension d:
  *     BELLMAN_LOCATE_SEARCH  : cell = clamp( #{ i : s[i] <= x } - 1, 0, n-2 )    (exact bin rule)
- *                              t = (x - s[cell]) * rinv[cell],  rinv[i] = 1/(s[i+1]-s[i]) (IEEE division, host)
- *   The library picks UNIFORM for a dimension when every node lies within 1e-14 of the grid's
- *   range from the uniform formula s[0] + i*h (MATLAB linspace grids do, with ~100x margin), else
- *   SEARCH; bellman_query_locate() reports the choice so the oracle uses the same one.  In
- *   UNIFORM mode the weight comes from the same fma that picks the cell, so cell and weight can
- *   never disagree, and no table is read per query.  (Near a grid node the two rules may pick
- *   adjacent cells; interpolation is continuous there, the results differ by O(1 ulp).)
+ *                              t = (x - s[cell]) * rinv[cell],  rinv[i] = 1/(s[i+1]-s[i]) (IEEE division)
+ *     BELLMAN_LOCATE_UNIFORM : the dimension is evaluated in CELL UNITS.  With
+ *                                  inv_h = (n-1)/(s[n-1]-s[0]),  off = -(s[0]*inv_h)
+ *                              the library rescales the three next-state tables once, on the host
+ *                              (one rounding per entry):
+ *                                  Ta'[i] = fma(Ta[i], inv_h, off),  Tb'[i] = Tb[i]*inv_h,  Tc'[c] = Tc[c]*inv_h
+ *                              and the sums above are formed from the primed tables, so the query
+ *                              g = (Ta' + Tb') + Tc' is already the fractional cell coordinate:
+ *                                  cell = clamp( (int)floor(g), 0, n-2 ),   t = g - (double)cell
+ *                              Cell and weight come from one number, so they can never disagree, and
+ *                              no table is read per query.  The rounding error of g (~1e-12 cell at
+ *                              n = 8192) is the same size as that of forming x' in state units and
+ *                              locating it against rounded grid nodes, as the reference does.
+ *   The library picks UNIFORM when every node lies within 1e-14 of the grid's range from the
+ *   uniform formula s[0] + i*h (MATLAB linspace grids do, with ~100x margin), else SEARCH;
+ *   bellman_query_locate() reports the choice so the oracle uses the same one.
+ *   bellman_rollout() locates a free state x with g = fma(x, inv_h, off) (UNIFORM) or the bin rule.
  */
 #ifndef BELLMAN_H
 #define BELLMAN_H

@@ -14,13 +14,14 @@ namespace {
 constexpr int BLOCK = 256;
 
 // --- locate (include/bellman.h, "locate_d") ---------------------------------------------------
+// x is in kernel units: the fractional cell coordinate for UNIFORM dimensions (the host pre-scaled
+// the tables), the state value for SEARCH dimensions.
 __device__ __forceinline__ int locate(const double *__restrict__ s, const double *__restrict__ rinv, int n,
-                                      int mode, double inv_h, double off, double x, double &t) {
+                                      int mode, double x, double &t) {
     int cell;
     if (mode == BELLMAN_LOCATE_UNIFORM) {
-        const double g = fma(x, inv_h, off);
-        cell = min(max(__double2int_rd(g), 0), n - 2);   // floor (saturating), then clamp
-        t = g - (double)cell;
+        cell = min(max(__double2int_rd(x), 0), n - 2);   // floor (saturating), then clamp
+        t = x - (double)cell;
     } else {
         int lo = 0, hi = n;                               // #{ s[i] <= x }
         while (lo < hi) {
@@ -36,7 +37,6 @@ __device__ __forceinline__ int locate(const double *__restrict__ s, const double
 template <int D>
 struct Prob {
     const double *grid[D], *rinv[D], *Ta[D], *Tb[D], *Tc[D], *q[D];
-    double inv_h[D], off[D];
     int mode[D], n[D];
     const double *r;
     __device__ __forceinline__ void load(const StageParams &sp, int prob) {
@@ -50,8 +50,6 @@ struct Prob {
             Tb[d] = dp.Tb ? dp.Tb + (size_t)prob * dp.n_b : nullptr;
             Tc[d] = dp.Tc ? dp.Tc + (size_t)prob * sp.C : nullptr;
             q[d] = dp.q + (size_t)prob * dp.n;
-            inv_h[d] = __ldg(dp.loc + 2 * prob);
-            off[d] = __ldg(dp.loc + 2 * prob + 1);
             mode[d] = __ldg(dp.mode + prob);
         }
         r = sp.r + (size_t)prob * sp.C;
@@ -68,7 +66,7 @@ __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         const double xq = pb.Tc[d] ? base[d] + __ldg(pb.Tc[d] + c) : base[d];
-        const int cell = locate(pb.grid[d], pb.rinv[d], pb.n[d], pb.mode[d], pb.inv_h[d], pb.off[d], xq, t[d]);
+        const int cell = locate(pb.grid[d], pb.rinv[d], pb.n[d], pb.mode[d], xq, t[d]);
         o += (long long)(cell - sp.dim[d].ext_lo) * sp.dim[d].stride;
     }
     double v[1 << D];
@@ -246,8 +244,11 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
         const int st = rp.mode == 1 ? rp.ssu_stage : k;
         const int32_t *__restrict__ id = rp.idx_all + (size_t)(st - 1) * S;
         double t0, t1;
-        const int c0 = locate(rp.grid0, rp.rinv0, rp.n0, rp.mode0, rp.inv_h0, rp.off0, x1, t0);
-        const int c1 = locate(rp.grid1, rp.rinv1, rp.n1, rp.mode1, rp.inv_h1, rp.off1, x2, t1);
+        // a free state is brought to kernel units first (include/bellman.h, bellman_rollout)
+        const int c0 = locate(rp.grid0, rp.rinv0, rp.n0, rp.mode0,
+                              rp.mode0 == BELLMAN_LOCATE_UNIFORM ? fma(x1, rp.inv_h0, rp.off0) : x1, t0);
+        const int c1 = locate(rp.grid1, rp.rinv1, rp.n1, rp.mode1,
+                              rp.mode1 == BELLMAN_LOCATE_UNIFORM ? fma(x2, rp.inv_h1, rp.off1) : x2, t1);
         const long long o = c0 + (long long)c1 * rp.n0;
         const double v00 = rp.u_values[id[o]], v10 = rp.u_values[id[o + 1]];
         const double v01 = rp.u_values[id[o + rp.n0]], v11 = rp.u_values[id[o + rp.n0 + 1]];

@@ -71,21 +71,40 @@ std::string load_problem(const bellman_desc *d, HostProblem &hp) {
                 grid_is_uniform(s, n) ? BELLMAN_LOCATE_UNIFORM : BELLMAN_LOCATE_SEARCH;
         }
     }
+    // UNIFORM dimensions are evaluated in cell units (include/bellman.h): rescale the next-state
+    // tables of every (problem, dimension) that uses the uniform rule, one rounding per entry
+    for (int k = 0; k < hp.D; ++k)
+        for (int p = 0; p < hp.P; ++p) {
+            if (hp.mode[(size_t)p * hp.D + k] != BELLMAN_LOCATE_UNIFORM) continue;
+            const double ih = hp.inv_h[k][p], of = hp.off[k][p];
+            const int na = hp.n[hp.src_a[k]];
+            for (int i = 0; i < na; ++i) {
+                double &v = hp.Ta[k][(size_t)p * na + i];
+                v = std::fma(v, ih, of);
+            }
+            if (hp.has_b[k]) {
+                const int nb = hp.n[hp.src_b[k]];
+                for (int i = 0; i < nb; ++i) hp.Tb[k][(size_t)p * nb + i] *= ih;
+            }
+            if (hp.has_c[k])
+                for (int c = 0; c < hp.C; ++c) hp.Tc[k][(size_t)p * hp.C + c] *= ih;
+        }
     hp.r.assign(d->r, d->r + (size_t)hp.P * hp.C);
     for (double v : hp.r)
         if (!std::isfinite(v)) return "r table must be finite";
     return "";
 }
 
+// x is a query in the units the kernel sees: the fractional cell coordinate for UNIFORM
+// dimensions, the state value for SEARCH dimensions
 int host_locate(const HostProblem &hp, int p, int d, double x) {
     const int n = hp.n[d];
     const double *s = hp.grid[d].data() + (size_t)p * n;
     int cell;
     if (hp.mode[(size_t)p * hp.D + d] == BELLMAN_LOCATE_UNIFORM) {
-        const double g = std::fma(x, hp.inv_h[d][p], hp.off[d][p]);
-        if (!(g >= 0.0)) cell = 0;
-        else if (g >= (double)(n - 1)) cell = n - 2;
-        else cell = (int)g;
+        if (!(x >= 0.0)) cell = 0;
+        else if (x >= (double)(n - 1)) cell = n - 2;
+        else cell = (int)x;
     } else {
         cell = (int)(std::upper_bound(s, s + n, x) - s) - 1;
         cell = std::min(std::max(cell, 0), n - 2);

@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <type_traits>
@@ -76,22 +77,23 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
-// UNIFORM locate of include/bellman.h: g = fma(x, inv_h, off); cell = clamp(floor(g)); t = g - cell
-__device__ __forceinline__ int cell_uniform(double x, double inv_h, double off, int n) {
-    return min(max(__double2int_rd(fma(x, inv_h, off)), 0), n - 2);
+// UNIFORM locate of include/bellman.h: the tables are pre-scaled to cell units on the host, so the
+// query g IS the fractional cell coordinate: cell = clamp(floor(g)), t = g - cell.
+__device__ __forceinline__ int cell_uniform(double g, int n) {
+    return min(max(__double2int_rd(g), 0), n - 2);
 }
 template <bool CLAMP = true>
-__device__ __forceinline__ int locate_uniform(double x, double inv_h, double off, int n, double &t) {
-    const double g = fma(x, inv_h, off);
+__device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
     int cell = __double2int_rd(g);
     if (CLAMP) cell = min(max(cell, 0), n - 2);   // skipped when the whole chunk is known to be interior
     t = g - (double)cell;
     return cell;
 }
 
-// HC0 / HC1: does dimension 0 / 1 of the next state depend on the control?
-template <bool HC0, bool HC1>
-__global__ void __launch_bounds__(WNT, 2)
+// BATCH: states evaluated together (instruction-level parallelism); OCC: CTAs per SM the register
+// allocation is sized for
+template <bool HC0, bool HC1, int BATCH, int OCC>
+__global__ void __launch_bounds__(WNT, OCC)
 k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
                const __grid_constant__ CUtensorMap tmap) {
     // ring of two window slots, win0 x win1 doubles each (dimension 0 contiguous)
@@ -121,8 +123,6 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     const double *Tc0 = HC0 ? d0.Tc + (size_t)prob * sp.C : nullptr;
     const double *Tc1 = HC1 ? d1.Tc + (size_t)prob * sp.C : nullptr;
     const double *rr = sp.r + (size_t)prob * sp.C;
-    const double inv_h0 = __ldg(d0.loc + 2 * prob), off0 = __ldg(d0.loc + 2 * prob + 1);
-    const double inv_h1 = __ldg(d1.loc + 2 * prob), off1 = __ldg(d1.loc + 2 * prob + 1);
     const double *cmm = wp.cmm + (size_t)prob * wp.nchunks * 4;
 
     if (tid == 0) {
@@ -165,9 +165,9 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         // TMA needs the byte offset of the innermost box coordinate to be a multiple of 16
         // (measured on B200: an odd fp64 coordinate raises "illegal instruction"), so the window
         // starts on an even row of the local array; the planner adds the extra row.
-        r0 = cell_uniform(lo0, inv_h0, off0, n0);
+        r0 = cell_uniform(lo0, n0);
         r0 -= (r0 - d0.ext_lo) & 1;
-        c0 = cell_uniform(lo1, inv_h1, off1, n1);
+        c0 = cell_uniform(lo1, n1);
     };
     auto issue = [&](int ch) {   // thread 0 only
         int r0, c0;
@@ -205,8 +205,8 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         gs[m] = sp.q_order[0] == 0 ? qa + qb : qb + qa;
         best[m] = __longlong_as_double(0x7ff0000000000000LL);
         arg[m] = 0;
-        if (!HC0) cellK0[m] = locate_uniform<true>(b0, inv_h0, off0, n0, tK0[m]);
-        if (!HC1) cellK1[m] = locate_uniform<true>(b1, inv_h1, off1, n1, tK1[m]);
+        if (!HC0) cellK0[m] = locate_uniform<true>(b0, n0, tK0[m]);
+        if (!HC1) cellK1[m] = locate_uniform<true>(b1, n1, tK1[m]);
     }
 
     const int W0 = wp.win0;
@@ -222,27 +222,27 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
             // two batches of four independent states: enough instruction-level parallelism to
             // cover the fp64 / shared-memory latencies with 16 warps per SM, within 128 registers
 #pragma unroll
-            for (int mb = 0; mb < WR_STATES; mb += 4) {
-                int off[4];
-                double t0[4], t1[4];
+            for (int mb = 0; mb < WR_STATES; mb += BATCH) {
+                int off[BATCH];
+                double t0[BATCH], t1[BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < BATCH; ++u) {
                     const int m = mb + u;
                     int cell0, cell1;
-                    if (HC0) cell0 = locate_uniform<CLAMP>(base0[m] + bu0, inv_h0, off0, n0, t0[u]);
+                    if (HC0) cell0 = locate_uniform<CLAMP>(base0[m] + bu0, n0, t0[u]);
                     else { cell0 = cellK0[m]; t0[u] = tK0[m]; }
-                    if (HC1) cell1 = locate_uniform<CLAMP>(base1[m] + bu1, inv_h1, off1, n1, t1[u]);
+                    if (HC1) cell1 = locate_uniform<CLAMP>(base1[m] + bu1, n1, t1[u]);
                     else { cell1 = cellK1[m]; t1[u] = tK1[m]; }
                     off[u] = cell1 * W0 + cell0;      // Wb already carries the window origin
                 }
-                double v00[4], v10[4], v01[4], v11[4];
+                double v00[BATCH], v10[BATCH], v01[BATCH], v11[BATCH];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < BATCH; ++u) {
                     const double *p = Wb + off[u];
                     v00[u] = p[0]; v10[u] = p[1]; v01[u] = p[W0]; v11[u] = p[W0 + 1];
                 }
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
+                for (int u = 0; u < BATCH; ++u) {
                     const int m = mb + u;
                     const double a = fma(t0[u], v10[u] - v00[u], v00[u]);
                     const double b = fma(t0[u], v11[u] - v01[u], v01[u]);
@@ -261,8 +261,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         if (Tb1) { lo1 = lo1 + tmm[6]; hi1 = hi1 + tmm[7]; }
         if (HC0) { lo0 = lo0 + __ldg(cmm + 4 * ch); hi0 = hi0 + __ldg(cmm + 4 * ch + 1); }
         if (HC1) { lo1 = lo1 + __ldg(cmm + 4 * ch + 2); hi1 = hi1 + __ldg(cmm + 4 * ch + 3); }
-        const bool interior = fma(lo0, inv_h0, off0) >= 0.0 && fma(hi0, inv_h0, off0) < (double)(n0 - 1) &&
-                              fma(lo1, inv_h1, off1) >= 0.0 && fma(hi1, inv_h1, off1) < (double)(n1 - 1);
+        const bool interior = lo0 >= 0.0 && hi0 < (double)(n0 - 1) && lo1 >= 0.0 && hi1 < (double)(n1 - 1);
         int r0, c0;
         origin(ch, r0, c0);
         mbar_wait(&mbar[ch & 1], (ch >> 1) & 1);
@@ -309,6 +308,7 @@ struct WindowState {
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
     bool hc0 = false, hc1 = false;
+    int batch = 4, occ = 2;
     void *d_cmm = nullptr;
 };
 
@@ -319,6 +319,36 @@ void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
 }
 
 }  // namespace
+
+// picks the kernel instantiation; with set_attr_only it just raises the dynamic shared memory limit
+template <bool HC0, bool HC1, int BATCH, int OCC>
+static bool window_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
+                      cudaStream_t st, bool set_attr_only) {
+    auto fn = k_stage_window<HC0, HC1, BATCH, OCC>;
+    if (set_attr_only)
+        return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) ==
+               cudaSuccess;
+    fn<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+    return true;
+}
+template <bool HC0, bool HC1>
+static bool window_go_hc(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
+                         cudaStream_t st, bool sa) {
+    if (ws->occ == 1) {
+        if (ws->batch == 8) return window_go<HC0, HC1, 8, 1>(ws, sp, map, grid, st, sa);
+        if (ws->batch == 2) return window_go<HC0, HC1, 2, 1>(ws, sp, map, grid, st, sa);
+        return window_go<HC0, HC1, 4, 1>(ws, sp, map, grid, st, sa);
+    }
+    if (ws->batch == 8) return window_go<HC0, HC1, 8, 2>(ws, sp, map, grid, st, sa);
+    if (ws->batch == 2) return window_go<HC0, HC1, 2, 2>(ws, sp, map, grid, st, sa);
+    return window_go<HC0, HC1, 4, 2>(ws, sp, map, grid, st, sa);
+}
+static bool window_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map,
+                            const void *, dim3 grid, cudaStream_t st, bool sa) {
+    if (ws->hc0 && ws->hc1) return window_go_hc<true, true>(ws, sp, map, grid, st, sa);
+    if (ws->hc0) return window_go_hc<true, false>(ws, sp, map, grid, st, sa);
+    return window_go_hc<false, true>(ws, sp, map, grid, st, sa);
+}
 
 // Exact worst-case window extents for a given chunk size: replays, on the host, the bound the
 // kernel uses ((min Ta + min Tb) + min Tc .. (max Ta + max Tb) + max Tc, located with the same
@@ -422,7 +452,7 @@ void window_setup(bellman_handle *h) {
             if (hp.has_c[d]) {
                 double mn, mx;
                 minmax_range(hp.Tc[d].data(), 0, hp.C, mn, mx);
-                sweep[d] = (mx - mn) * hp.inv_h[d][0];
+                sweep[d] = mx - mn;   // already in cells
             }
         wp.tj_fastest = sweep[1] >= sweep[0] ? 1 : 0;
     }
@@ -459,11 +489,14 @@ void window_setup(bellman_handle *h) {
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete ws; return; }
     }
-    auto set_attr = [&](const void *fn) {
-        return cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) == cudaSuccess;
-    };
-    if (!set_attr((const void *)k_stage_window<true, true>) || !set_attr((const void *)k_stage_window<true, false>) ||
-        !set_attr((const void *)k_stage_window<false, true>)) { delete ws; return; }
+    {
+        const char *eb = std::getenv("BELLMAN_WIN_BATCH"), *eo = std::getenv("BELLMAN_WIN_OCC");
+        ws->batch = eb ? std::atoi(eb) : 4;
+        ws->occ = eo ? std::atoi(eo) : 2;
+        if (ws->batch != 2 && ws->batch != 4 && ws->batch != 8) ws->batch = 4;
+        if (ws->occ != 1 && ws->occ != 2) ws->occ = 2;
+    }
+    if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { delete ws; return; }
     if (!ws->hc0 && !ws->hc1) { delete ws; return; }   // no control dependence at all: nothing to stage for
     h->wstate = ws;
     h->wcfg.tile0 = WT0; h->wcfg.tile1 = WT1; h->wcfg.cchunk = wp.cchunk;
@@ -485,9 +518,7 @@ cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     const WindowParams &wp = ws->wp;
     const dim3 grid((unsigned)(wp.ntile0 * wp.ntile1), (unsigned)sp.P);
     const CUtensorMap &map = ws->maps[slot_next];
-    if (ws->hc0 && ws->hc1) k_stage_window<true, true><<<grid, WNT, ws->smem, st>>>(sp, wp, map);
-    else if (ws->hc0) k_stage_window<true, false><<<grid, WNT, ws->smem, st>>>(sp, wp, map);
-    else k_stage_window<false, true><<<grid, WNT, ws->smem, st>>>(sp, wp, map);
+    window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
     return cudaGetLastError();
 }
 

@@ -67,16 +67,16 @@ typedef struct {
     double inv_h, off;
 } dimtab;
 
+/* x is in kernel units: fractional cell coordinate (UNIFORM, tables pre-scaled) or state value (SEARCH) */
 static inline int locate(const dimtab *g, double x, double *t)
 {
     int cell;
     if (g->mode == BELLMAN_LOCATE_UNIFORM) {
-        const double gg = fma(x, g->inv_h, g->off);
-        if (!(gg >= 0.0)) cell = 0;                   /* floor() then clamp, without int overflow; NaN -> 0
+        if (!(x >= 0.0)) cell = 0;                    /* floor() then clamp, without int overflow; NaN -> 0
                                                          like the GPU's saturating cvt.rmi.s32.f64 */
-        else if (gg >= (double)(g->n - 1)) cell = g->n - 2;
-        else cell = (int)gg;
-        *t = gg - (double)cell;
+        else if (x >= (double)(g->n - 1)) cell = g->n - 2;
+        else cell = (int)x;
+        *t = x - (double)cell;
     } else {
         int lo = 0, hi = g->n;                        /* count of s[i] <= x */
         while (lo < hi) {
@@ -89,6 +89,12 @@ static inline int locate(const dimtab *g, double x, double *t)
         *t = (x - g->s[cell]) * g->rinv[cell];
     }
     return cell;
+}
+
+/* a free state value (rollout): brought to kernel units first */
+static inline int locate_state(const dimtab *g, double x, double *t)
+{
+    return locate(g, g->mode == BELLMAN_LOCATE_UNIFORM ? fma(x, g->inv_h, g->off) : x, t);
 }
 
 static void dimtab_init(dimtab *g, const double *s, int n, int mode)
@@ -145,16 +151,47 @@ static void eval_state(const bellman_desc *d, const dimtab *g, const double *con
     *idx_out = arg;
 }
 
+/* per-problem tables in kernel units: UNIFORM dimensions are pre-scaled to cell units
+ * (include/bellman.h): Ta' = fma(Ta, inv_h, off), Tb' = Tb*inv_h, Tc' = Tc*inv_h, one rounding each.
+ * The scaled copies are owned by `own` and released by problem_tables_free(). */
+typedef struct { double *buf[3 * MAXD]; int n; } owned_tabs;
+
 static void problem_tables(const bellman_desc *d, const int32_t *modes, int p, dimtab *g,
-                           const double **Ta, const double **Tb, const double **Tc, const double **q)
+                           const double **Ta, const double **Tb, const double **Tc, const double **q,
+                           owned_tabs *own)
 {
+    own->n = 0;
     for (int k = 0; k < d->D; ++k) {
         dimtab_init(&g[k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * d->D + k]);
         Ta[k] = d->Ta[k] + (size_t)p * d->n[d->src_a[k]];
         Tb[k] = (d->Tb[k] && d->src_b[k] >= 0) ? d->Tb[k] + (size_t)p * d->n[d->src_b[k]] : NULL;
         Tc[k] = d->Tc[k] ? d->Tc[k] + (size_t)p * d->C : NULL;
         q[k] = d->q[k] + (size_t)p * d->n[k];
+        if (g[k].mode == BELLMAN_LOCATE_UNIFORM) {
+            const double ih = g[k].inv_h, of = g[k].off;
+            const int na = d->n[d->src_a[k]];
+            double *a = (double *)malloc(sizeof(double) * (size_t)na);
+            for (int i = 0; i < na; ++i) a[i] = fma(Ta[k][i], ih, of);
+            Ta[k] = own->buf[own->n++] = a;
+            if (Tb[k]) {
+                const int nb = d->n[d->src_b[k]];
+                double *b = (double *)malloc(sizeof(double) * (size_t)nb);
+                for (int i = 0; i < nb; ++i) b[i] = Tb[k][i] * ih;
+                Tb[k] = own->buf[own->n++] = b;
+            }
+            if (Tc[k]) {
+                double *c = (double *)malloc(sizeof(double) * (size_t)d->C);
+                for (int i = 0; i < d->C; ++i) c[i] = Tc[k][i] * ih;
+                Tc[k] = own->buf[own->n++] = c;
+            }
+        }
     }
+}
+
+static void problem_tables_free(const bellman_desc *d, dimtab *g, owned_tabs *own)
+{
+    for (int k = 0; k < d->D; ++k) free(g[k].rinv);
+    for (int k = 0; k < own->n; ++k) free(own->buf[k]);
 }
 
 /*
@@ -170,12 +207,13 @@ int oracle_stage_points(const bellman_desc *d, const int32_t *modes, int p, cons
     for (int k = 0; k < D; ++k) { stride[k] = S; S *= d->n[k]; }
     dimtab g[MAXD];
     const double *Ta[MAXD], *Tb[MAXD], *Tc[MAXD], *q[MAXD];
-    problem_tables(d, modes, p, g, Ta, Tb, Tc, q);
+    owned_tabs own;
+    problem_tables(d, modes, p, g, Ta, Tb, Tc, q, &own);
     const double *r = d->r + (size_t)p * d->C;
 #pragma omp parallel for schedule(static)
     for (int64_t m = 0; m < n_states; ++m)
         eval_state(d, g, Ta, Tb, Tc, q, r, stride, J_next, states[m], &J_out[m], &idx_out[m]);
-    for (int k = 0; k < D; ++k) free(g[k].rinv);
+    problem_tables_free(d, g, &own);
     return 0;
 }
 
@@ -200,7 +238,8 @@ int oracle_stage(const bellman_desc *d, const int32_t *modes, const double *J_ne
     for (int p = 0; p < d->P; ++p) {
         dimtab g[MAXD];
         const double *Ta[MAXD], *Tb[MAXD], *Tc[MAXD], *q[MAXD];
-        problem_tables(d, modes, p, g, Ta, Tb, Tc, q);
+        owned_tabs own;
+        problem_tables(d, modes, p, g, Ta, Tb, Tc, q, &own);
         const double *r = d->r + (size_t)p * C;
         const double *Jn = J_next + (size_t)p * S;
         double *Jo = J_out + (size_t)p * S;
@@ -214,7 +253,7 @@ int oracle_stage(const bellman_desc *d, const int32_t *modes, const double *J_ne
             }
             eval_state(d, g, Ta, Tb, Tc, q, r, stride, Jn, s, &Jo[s], &Io[s]);
         }
-        for (int k = 0; k < D; ++k) free(g[k].rinv);
+        problem_tables_free(d, g, &own);
     }
     return 0;
 }
@@ -286,7 +325,7 @@ int oracle_rollout(const bellman_desc *d, const int32_t *modes, const int32_t *i
             const int st = (mode == 1) ? ssu_stage : k;
             const int32_t *id = idx_all + (size_t)(st - 1) * S;
             double t0, t1;
-            const int c0 = locate(&g[0], x1, &t0), c1 = locate(&g[1], x2, &t1);
+            const int c0 = locate_state(&g[0], x1, &t0), c1 = locate_state(&g[1], x2, &t1);
             const double v00 = u_values[id[c0 + (int64_t)c1 * n0]];
             const double v10 = u_values[id[c0 + 1 + (int64_t)c1 * n0]];
             const double v01 = u_values[id[c0 + (int64_t)(c1 + 1) * n0]];
