@@ -40,6 +40,9 @@ WORKLOADS = {
     "pos_att_x4_120x120x80x60x9": dict(kind="pos_att", scale=4),
 }
 DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch, from the committed
+# `ncu --set full` capture of the same command (profiles/r01_window_kirk_scaled_ncu_raw.csv)
+NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": 548.5e6 + 767.9e6}
 
 
 def make_desc(bb, name):
@@ -292,10 +295,10 @@ def main():
     achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
     # secondary bound: fp64 pipe, 64 lanes/clk/SM x 148 SMs at the clock seen
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp64_ops_per_update = 17.0
+    fp64_ops_per_update = 15.0     # window kernel, SASS-counted: 13 DADD/DFMA/DSETP + 2 DADD (exact int->double)
     fp64_peak = 64 * 148 * mhz * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "kernel_ms": ms_kernel, "kernel": sw.last_kernel,
                 "fp64_secondary": {"ops_per_update": fp64_ops_per_update,
                                    "achieved_ops_per_s": value / world * fp64_ops_per_update,

@@ -82,11 +82,18 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ int cell_uniform(double g, int n) {
     return min(max(__double2int_rd(g), 0), n - 2);
 }
+// (double)cell for 0 <= cell < 2^31 without a conversion instruction: the double with high word
+// 0x43300000 and low word cell is exactly 2^52 + cell.  Measured on B200 (scripts/ubench/pipes.cu):
+// F2I.F64 / I2F.F64 issue at 16 lanes/clk/SM (2 cycles per warp instruction), a DADD at 64 — and
+// the conversion pipe only partly overlaps with the shared-memory loads.
+__device__ __forceinline__ double cell_to_double(int cell) {
+    return __hiloint2double(0x43300000, cell) - 4503599627370496.0;
+}
 template <bool CLAMP = true>
 __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
     int cell = __double2int_rd(g);
     if (CLAMP) cell = min(max(cell, 0), n - 2);   // skipped when the whole chunk is known to be interior
-    t = g - (double)cell;
+    t = g - cell_to_double(cell);
     return cell;
 }
 
