@@ -163,6 +163,11 @@ void bellman_destroy(bellman_handle *h);
    (torch.distributed / MPI / a file), every rank calls comm_init */
 int  bellman_get_unique_id(void *id128_out);
 int  bellman_comm_init(bellman_handle *h, const void *id128);
+/* 1: halo states are stored straight into the neighbours' J buffers by the stage kernel (CUDA IPC
+ * peer memory over NVLink) and a stage ends with a 1-element all-reduce barrier;
+ * 0: grouped ncclSend/ncclRecv of the halo ranges after every stage (fallback, or BELLMAN_NO_P2P=1);
+ * valid after bellman_comm_init */
+int  bellman_halo_mode(const bellman_handle *h);
 
 /* sweep */
 int  bellman_set_J(bellman_handle *h, const double *J_host /*[P][S] global, NULL = zeros*/);

@@ -50,7 +50,7 @@ class CSlab(C.Structure):
 # every symbol include/bellman.h declares
 EXPORTS = [
     "bellman_version", "bellman_last_error", "bellman_query_locate", "bellman_plan_slabs",
-    "bellman_create", "bellman_destroy", "bellman_get_unique_id", "bellman_comm_init",
+    "bellman_create", "bellman_destroy", "bellman_get_unique_id", "bellman_comm_init", "bellman_halo_mode",
     "bellman_set_J", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout",
@@ -85,6 +85,7 @@ def load():
     lib.bellman_owned_range.argtypes = [C.c_void_p, C.POINTER(CSlab)]
     lib.bellman_last_run_stats.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_int64), _dp]
     lib.bellman_comm_init.argtypes = [C.c_void_p, C.c_void_p]
+    lib.bellman_halo_mode.argtypes = [C.c_void_p]
     lib.bellman_get_unique_id.argtypes = [C.c_void_p]
     lib.bellman_query_locate.argtypes = [C.POINTER(CDesc), _ip]
     lib.bellman_plan_slabs.argtypes = [C.POINTER(CDesc), C.c_int32, C.c_int32, C.POINTER(CSlab)]
@@ -196,6 +197,11 @@ class Sweep:
     def comm_init(self, id128):
         buf = C.create_string_buffer(bytes(id128), 128)
         self._check(self.lib.bellman_comm_init(self.h, buf))
+
+    @property
+    def halo_mode(self):
+        """'p2p' (stage kernel stores halos into peer memory) or 'nccl' (send/recv after each stage)."""
+        return "p2p" if self.lib.bellman_halo_mode(self.h) else "nccl"
 
     def set_J(self, J=None):
         if J is None:

@@ -40,6 +40,7 @@ struct NcclApi {
     ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                               cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -65,12 +66,15 @@ static NcclApi *nccl_api(std::string &err) {
     LOAD(Send, "ncclSend")
     LOAD(Recv, "ncclRecv")
     LOAD(AllReduce, "ncclAllReduce")
+    LOAD(AllGather, "ncclAllGather")
     LOAD(GroupStart, "ncclGroupStart")
     LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
     return &api;
 }
+
+static int stage_barrier(bellman_handle *h);
 
 extern "C" int bellman_version(void) { return BELLMAN_ABI_VERSION; }
 
@@ -222,6 +226,13 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
 extern "C" void bellman_destroy(bellman_handle *h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->fused_halo) {
+        // nobody may still be storing into my J when it is freed
+        stage_barrier(h);
+        cudaStreamSynchronize(h->stream);
+        for (double *pj : h->peer_J) if (pj) cudaIpcCloseMemHandle(pj);
+    }
+    cudaFree(h->d_barrier);
     if (h->comm) {
         std::string e;
         NcclApi *api = nccl_api(e);
@@ -343,6 +354,89 @@ extern "C" int bellman_get_unique_id(void *id128_out) {
     return BELLMAN_OK;
 }
 
+// Fused halo mode: map every neighbour's J allocation through CUDA IPC so the stage kernel can
+// store halo states straight into peer memory over NVLink.  The 64-byte IPC handles travel through
+// NCCL itself (all-gather), so the host language needs no extra plumbing.  Every rank takes the
+// same decision (an all-reduce of the per-rank outcome); on any failure the library keeps the
+// NCCL send/recv exchange.  BELLMAN_NO_P2P=1 forces the fallback.
+static void setup_fused_halo(bellman_handle *h, NcclApi *api) {
+    h->fused_halo = false;
+    const int n = h->nranks;
+    int ok = (n - 1 <= MAX_PEERS) && !std::getenv("BELLMAN_NO_P2P");
+    cudaIpcMemHandle_t mine;
+    std::memset(&mine, 0, sizeof(mine));
+    if (ok && cudaIpcGetMemHandle(&mine, h->d_J) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+    unsigned char *d_buf = nullptr;
+    const size_t hb = sizeof(cudaIpcMemHandle_t);
+    if (cudaMalloc(&d_buf, hb * (n + 1) + 16) != cudaSuccess) return;
+    if (cudaMalloc(&h->d_barrier, 2 * sizeof(double)) != cudaSuccess) { cudaFree(d_buf); return; }
+    cudaMemcpyAsync(d_buf + hb * n, &mine, hb, cudaMemcpyHostToDevice, h->stream);
+    std::vector<cudaIpcMemHandle_t> all(n);
+    bool comm_ok = api->AllGather(d_buf + hb * n, d_buf, hb, ncclChar, h->comm, h->stream) == ncclSuccess;
+    cudaMemcpyAsync(all.data(), d_buf, hb * n, cudaMemcpyDeviceToHost, h->stream);
+    cudaStreamSynchronize(h->stream);
+    h->peer_J.assign(n, nullptr);
+    if (ok && comm_ok) {
+        for (int q = 0; q < n && ok; ++q) {
+            if (q == h->rank) continue;
+            void *ptr = nullptr;
+            if (cudaIpcOpenMemHandle(&ptr, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { ok = 0; cudaGetLastError(); }
+            h->peer_J[q] = static_cast<double *>(ptr);
+        }
+    } else ok = 0;
+    // unanimous decision
+    double flag = ok ? 1.0 : 0.0;
+    cudaMemcpyAsync(h->d_barrier, &flag, sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    if (api->AllReduce(h->d_barrier, h->d_barrier, 1, ncclDouble, ncclMin, h->comm, h->stream) != ncclSuccess) flag = 0.0;
+    else {
+        cudaMemcpyAsync(&flag, h->d_barrier, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
+        cudaStreamSynchronize(h->stream);
+    }
+    cudaFree(d_buf);
+    if (flag < 0.5) {
+        for (double *&pj : h->peer_J) if (pj) { cudaIpcCloseMemHandle(pj); pj = nullptr; }
+        return;
+    }
+    h->fused_halo = true;
+}
+
+static void fill_peers(const bellman_handle *h, StageParams &sp, int out_stage) {
+    sp.n_peers = 0;
+    sp.part_dim = h->part_dim < 0 ? 0 : h->part_dim;
+    if (!h->fused_halo) return;
+    const HostProblem &hp = h->hp;
+    const bellman_slab &me = h->slabs[h->rank];
+    for (int q = 0; q < h->nranks; ++q) {
+        if (q == h->rank) continue;
+        const bellman_slab &o = h->slabs[q];
+        const int lo = std::max(o.ext_lo, me.own_lo), hi = std::min(o.ext_hi, me.own_hi);
+        if (lo >= hi) continue;
+        PeerHalo &ph = sp.peer[sp.n_peers++];
+        long long st = 1;
+        for (int d = 0; d < MAXD; ++d) {
+            ph.stride[d] = st;
+            if (d < hp.D) st *= (d == h->part_dim) ? (o.ext_hi - o.ext_lo) : hp.n[d];
+        }
+        ph.S_ext = st;
+        ph.J = h->peer_J[q] + (size_t)h->J_slot(out_stage) * (size_t)hp.P * (size_t)st;
+        ph.lo = lo; ph.hi = hi; ph.ext_lo = o.ext_lo; ph.pad_ = 0;
+    }
+}
+
+// fused mode: the neighbours' stores into my halo are complete once every rank's stage kernel
+// has finished; a 1-element all-reduce on the stream is the barrier
+static int stage_barrier(bellman_handle *h) {
+    NcclApi *api = nccl_api(h->err);
+    if (!api) return BELLMAN_ERR_NCCL;
+    if (api->AllReduce(h->d_barrier, h->d_barrier + 1, 1, ncclDouble, ncclSum, h->comm, h->stream) != ncclSuccess) {
+        h->err = "stage barrier (ncclAllReduce) failed";
+        return BELLMAN_ERR_NCCL;
+    }
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_halo_mode(const bellman_handle *h) { return h && h->fused_halo ? 1 : 0; }
+
 extern "C" int bellman_comm_init(bellman_handle *h, const void *id128) {
     if (!h || !id128) return BELLMAN_ERR_BAD_ARG;
     if (h->nranks <= 1) return BELLMAN_OK;
@@ -353,6 +447,7 @@ extern "C" int bellman_comm_init(bellman_handle *h, const void *id128) {
     CUDA_TRY(h, cudaSetDevice(h->device));
     ncclResult_t r = api->CommInitRank(&h->comm, h->nranks, id, h->rank);
     if (r != ncclSuccess) { h->err = std::string("ncclCommInitRank: ") + api->GetErrorString(r); return BELLMAN_ERR_NCCL; }
+    setup_fused_halo(h, api);
     return BELLMAN_OK;
 }
 
@@ -419,6 +514,7 @@ static int launch_one_stage(bellman_handle *h, int kernel, int lanes) {
     sp.J_next = h->J_ptr(from);
     sp.J_out = h->J_ptr(to);
     sp.idx_out = h->idx_ptr(to);
+    fill_peers(h, sp, to);
     cudaError_t e;
     if (kernel == BELLMAN_KERNEL_SPLITC) e = launch_stage_splitc(sp, lanes, h->stream);
     else if (kernel == BELLMAN_KERNEL_WINDOW) e = window_launch_for_handle(h, sp, h->J_slot(from), h->stream);
@@ -502,7 +598,7 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
                 CUDA_TRY(h, cudaEventCreate(&a));
                 CUDA_TRY(h, cudaEventCreate(&b));
                 CUDA_TRY(h, cudaEventRecord(a, h->stream));
-                rc = exchange_halo(h, h->cur_stage);
+                rc = h->fused_halo ? stage_barrier(h) : exchange_halo(h, h->cur_stage);
                 if (rc != BELLMAN_OK) return rc;
                 CUDA_TRY(h, cudaEventRecord(b, h->stream));
                 xev.emplace_back(a, b);

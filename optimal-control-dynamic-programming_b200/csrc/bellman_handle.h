@@ -34,6 +34,10 @@ struct bellman_handle {
     std::vector<double> check_log;    // triples
     // nccl
     ncclComm_t comm = nullptr;
+    // fused halo mode: neighbours' J allocations mapped through CUDA IPC (index = rank, own = nullptr)
+    bool fused_halo = false;
+    std::vector<double *> peer_J;
+    double *d_barrier = nullptr;
     // window kernel state
     bellman::WindowConfig wcfg;
     void *wstate = nullptr;           // bellman_window.cu: WindowState (tensor maps, chunk tables)

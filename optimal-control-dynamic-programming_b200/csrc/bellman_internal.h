@@ -53,6 +53,19 @@ struct DimParams {
     long long stride;     // element stride of this dim in the (extended) J arrays
 };
 
+// A neighbour rank that reads part of my owned slab: in fused (peer-memory) mode the stage kernel
+// stores those states straight into the neighbour's J buffer over NVLink, so no separate halo
+// exchange (pack / send / recv) exists — only a per-stage barrier.
+constexpr int MAX_PEERS = 7;
+struct PeerHalo {
+    double *J;              // neighbour's J_out slot (problem 0), peer-mapped (cudaIpc)
+    long long S_ext;        // neighbour's per-problem stride
+    long long stride[MAXD]; // neighbour's element strides
+    int lo, hi;             // global index range along part_dim the neighbour reads from me
+    int ext_lo;             // neighbour's first stored index along part_dim
+    int pad_;
+};
+
 struct StageParams {
     DimParams dim[MAXD];
     const double *r;          // [P][C]
@@ -62,7 +75,26 @@ struct StageParams {
     long long S_ext, S_own;
     int D, C, P;
     int q_order[MAXD];
+    int n_peers, part_dim;
+    PeerHalo peer[MAX_PEERS];
 };
+
+#ifdef __CUDACC__
+// store `v` (the new J of global state gi) into every neighbour whose halo covers it
+template <int D>
+__device__ __forceinline__ void peer_store(const StageParams &sp, int prob, const int (&gi)[D], double v) {
+    for (int e = 0; e < sp.n_peers; ++e) {
+        const PeerHalo &ph = sp.peer[e];
+        const int ip = gi[sp.part_dim];
+        if (ip >= ph.lo && ip < ph.hi) {
+            long long o = (long long)prob * ph.S_ext;
+#pragma unroll
+            for (int d = 0; d < D; ++d) o += (long long)(gi[d] - (d == sp.part_dim ? ph.ext_lo : 0)) * ph.stride[d];
+            ph.J[o] = v;
+        }
+    }
+}
+#endif
 
 // window (TMA-staged) kernel configuration for D = 2
 struct WindowConfig {

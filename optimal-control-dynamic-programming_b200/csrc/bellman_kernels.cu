@@ -144,6 +144,7 @@ k_stage_direct(const __grid_constant__ StageParams sp) {
     }
     sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
     sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
+    if (sp.n_peers) peer_store<D>(sp, prob, gi, best);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -182,6 +183,7 @@ k_stage_splitc(const __grid_constant__ StageParams sp) {
     if (live && lane == 0) {
         sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
         sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
+        if (sp.n_peers) peer_store<D>(sp, prob, gi, best);
     }
 }
 

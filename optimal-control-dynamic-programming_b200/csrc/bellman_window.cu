@@ -288,6 +288,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
             if (j < j_hi) {
                 Jo[(long long)(i - d0.ext_lo) * d0.stride + (long long)(j - d1.ext_lo) * d1.stride] = best[m];
                 Io[(long long)(i - d0.own_lo) + (long long)(j - d1.own_lo) * d0.own_n] = arg[m];
+                if (sp.n_peers) { const int gi[2] = {i, j}; peer_store<2>(sp, prob, gi, best[m]); }
             }
         }
     }

@@ -37,7 +37,18 @@ def main():
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     d = make(kind)
-    part_dim = d.D - 1
+    ok = True
+    for part_dim in ((d.D - 1, 0) if kind != "pos_att" else (d.D - 1, 2)):
+        ok = check(d, kind, part_dim, rank, world, local) and ok
+    t = torch.tensor([1 if ok else 0], device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    dist.destroy_process_group()
+    if rank == 0:
+        print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
+    sys.exit(0 if int(t.item()) == 1 else 1)
+
+
+def check(d, kind, part_dim, rank, world, local):
     sw = bb.Sweep(d, device=local, part_dim=part_dim, rank=rank, nranks=world)
     ids = [bb.get_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(ids, src=0)
@@ -51,19 +62,16 @@ def main():
         ref = cbind.sweep(d, n_stages=n_stages)
         lo, hi = sw.slab[0], sw.slab[1]
         inner = int(np.prod(d.n[:part_dim]))
-        Jr = ref["J_last"].reshape(d.P, -1, inner)[:, lo:hi, :].reshape(d.P, -1)
-        Ir = ref["idx_last"].reshape(d.P, -1, inner)[:, lo:hi, :].reshape(d.P, -1)
+        n_p = d.n[part_dim]
+        Jr = ref["J_last"].reshape(d.P, -1, n_p, inner)[:, :, lo:hi, :].reshape(d.P, -1)
+        Ir = ref["idx_last"].reshape(d.P, -1, n_p, inner)[:, :, lo:hi, :].reshape(d.P, -1)
         good = bool(np.array_equal(J, Jr) and np.array_equal(idx, Ir))
-        print(f"rank {rank}/{world} {kind} kernel={sw.last_kernel} slab={sw.slab} "
+        print(f"rank {rank}/{world} {kind} part_dim={part_dim} kernel={sw.last_kernel} slab={sw.slab} "
+              f"halo={os.environ.get('BELLMAN_NO_P2P') and 'nccl' or 'auto'} "
               f"{'OK' if good else 'MISMATCH'} exchange_ms={sw.stats()['ms_exchange']:.3f}", flush=True)
         ok = ok and good
-    t = torch.tensor([1 if ok else 0], device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MIN)
     sw.close()
-    dist.destroy_process_group()
-    if rank == 0:
-        print("MULTI_GPU_CHECK", "PASS" if int(t.item()) == 1 else "FAIL", flush=True)
-    sys.exit(0 if int(t.item()) == 1 else 1)
+    return ok
 
 
 if __name__ == "__main__":

@@ -15,8 +15,9 @@ def _ngpu():
     return torch.cuda.device_count()
 
 
+@pytest.mark.parametrize("halo", ["fused_p2p", "nccl_sendrecv"])
 @pytest.mark.parametrize("kind", ["kirk", "attitude", "pos_att"])
-def test_slab_partitioned_sweep_over_nccl(kind):
+def test_slab_partitioned_sweep_over_nccl(kind, halo):
     n = _ngpu()
     if n < 2:
         pytest.skip("needs at least 2 GPUs")
@@ -24,5 +25,8 @@ def test_slab_partitioned_sweep_over_nccl(kind):
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={n}",
            "--master-addr", "127.0.0.1", "--master-port", "29541",
            os.path.join(ROOT, "scripts", "multi_gpu_check.py"), kind]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if halo == "nccl_sendrecv":
+        env["BELLMAN_NO_P2P"] = "1"
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     assert "MULTI_GPU_CHECK PASS" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
