@@ -270,6 +270,9 @@ def main():
     barrier()
     wall_ms = (time.perf_counter() - t0) * 1e3
     st = sw.stats()
+    if os.environ.get("BELLMAN_BENCH_VERBOSE"):
+        print("rank %d slab %s: device ms %.3f, barrier/exchange ms %.3f, kernel %s" %
+              (rank, sw.slab, st["ms"], st["ms_exchange"], sw.last_kernel), file=sys.stderr, flush=True)
     ms_dev = max_over_ranks(st["ms"])                                  # device time, max over ranks
     ms_x = max_over_ranks(st["ms_exchange"])
     clocks = sampler.stop() if rank == 0 else None

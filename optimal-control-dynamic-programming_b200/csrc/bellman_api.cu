@@ -172,7 +172,12 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
         h->slabs.assign(1, bellman_slab{0, 0, 0, 0});
     }
     h->S_ext = 1; h->S_own = 1;
-    for (int k = 0; k < hp.D; ++k) { h->stride[k] = h->S_ext; h->S_ext *= h->ext_n[k]; h->S_own *= h->own_n[k]; }
+    h->ld0 = (h->part_dim == 0) ? ((h->ext_n[0] + 1) & ~1) : h->ext_n[0];
+    for (int k = 0; k < hp.D; ++k) {
+        h->stride[k] = h->S_ext;
+        h->S_ext *= (k == 0) ? h->ld0 : h->ext_n[k];
+        h->S_own *= h->own_n[k];
+    }
 
     // device
     int ndev = 0;
@@ -283,7 +288,7 @@ extern "C" int bellman_set_J(bellman_handle *h, const double *J_host) {
         const size_t S = (size_t)hp.S();
         for (int pr = 0; pr < hp.P; ++pr) {
             const double *src = J_host + (size_t)pr * S + (size_t)h->ext_lo[p] * inner;
-            CUDA_TRY(h, cudaMemcpy2DAsync(dst + (size_t)pr * h->S_ext, (size_t)h->ext_n[p] * inner * 8, src,
+            CUDA_TRY(h, cudaMemcpy2DAsync(dst + (size_t)pr * h->S_ext, (size_t)h->row_elems(p) * 8, src,
                                           (size_t)hp.n[p] * inner * 8, (size_t)h->ext_n[p] * inner * 8,
                                           (size_t)outer, cudaMemcpyHostToDevice, h->stream));
         }
@@ -314,7 +319,7 @@ extern "C" int bellman_get_J(bellman_handle *h, int32_t stage, double *out) {
     for (int pr = 0; pr < hp.P; ++pr) {
         const double *src = src0 + (size_t)pr * h->S_ext + (size_t)(h->own_lo[p] - h->ext_lo[p]) * inner;
         CUDA_TRY(h, cudaMemcpy2DAsync(out + (size_t)pr * h->S_own, (size_t)h->own_n[p] * inner * 8, src,
-                                      (size_t)h->ext_n[p] * inner * 8, (size_t)h->own_n[p] * inner * 8,
+                                      (size_t)h->row_elems(p) * 8, (size_t)h->own_n[p] * inner * 8,
                                       (size_t)outer, cudaMemcpyDeviceToHost, h->stream));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -415,7 +420,11 @@ static void fill_peers(const bellman_handle *h, StageParams &sp, int out_stage) 
         long long st = 1;
         for (int d = 0; d < MAXD; ++d) {
             ph.stride[d] = st;
-            if (d < hp.D) st *= (d == h->part_dim) ? (o.ext_hi - o.ext_lo) : hp.n[d];
+            if (d < hp.D) {
+                int ext = (d == h->part_dim) ? (o.ext_hi - o.ext_lo) : hp.n[d];
+                if (d == 0 && h->part_dim == 0) ext = (ext + 1) & ~1;   // the neighbour's padded leading dimension
+                st *= ext;
+            }
         }
         ph.S_ext = st;
         ph.J = h->peer_J[q] + (size_t)h->J_slot(out_stage) * (size_t)hp.P * (size_t)st;
@@ -463,7 +472,7 @@ static int exchange_halo(bellman_handle *h, int stage) {
     const int p = h->part_dim;
     double *J = h->J_ptr(stage);
     const bellman_slab &me = h->slabs[h->rank];
-    const long long row = (long long)h->ext_n[p] * inner;   // elements per outer index
+    const long long row = h->row_elems(p);   // stored elements per outer index
     ncclResult_t r = api->GroupStart();
     for (int q = 0; q < h->nranks && r == ncclSuccess; ++q) {
         if (q == h->rank) continue;

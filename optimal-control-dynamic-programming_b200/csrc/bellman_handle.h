@@ -18,6 +18,14 @@ struct bellman_handle {
     std::vector<bellman_slab> slabs;
     int own_n[bellman::MAXD], own_lo[bellman::MAXD], ext_lo[bellman::MAXD], ext_n[bellman::MAXD];
     long long stride[bellman::MAXD];
+    // leading dimension of the J arrays (elements): ext_n[0], rounded up to even when dimension 0
+    // is the partitioned one so that TMA's 16-byte stride rule holds for any slab width
+    int ld0 = 1;
+    long long row_elems(int p) const {   // stored elements per outer index of a slab along dim p
+        long long inner = 1;
+        for (int k = 0; k < p; ++k) inner *= hp.n[k];
+        return p == 0 ? (long long)ld0 : (long long)ext_n[p] * inner;
+    }
     long long S_ext = 0, S_own = 0;
     // device memory
     double *d_tab = nullptr;          // all fp64 tables

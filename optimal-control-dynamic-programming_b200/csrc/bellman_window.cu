@@ -411,7 +411,7 @@ void window_setup(bellman_handle *h) {
     if (hp.D != 2) return;
     for (int32_t m : hp.mode)
         if (m != BELLMAN_LOCATE_UNIFORM) return;
-    if (h->ext_n[0] % 2) return;                 // TMA global strides must be multiples of 16 bytes
+    if (h->ld0 % 2) return;                      // TMA global strides must be multiples of 16 bytes
     if (((size_t)h->S_ext * 8) % 16) return;
     PFN_encodeTiled enc = get_encode();
     if (!enc) return;
@@ -488,7 +488,7 @@ void window_setup(bellman_handle *h) {
     ws->maps.resize(nslots);
     for (int s = 0; s < nslots; ++s) {
         cuuint64_t gdim[3] = {(cuuint64_t)h->ext_n[0], (cuuint64_t)h->ext_n[1], (cuuint64_t)hp.P};
-        cuuint64_t gstr[2] = {(cuuint64_t)h->ext_n[0] * 8, (cuuint64_t)h->S_ext * 8};
+        cuuint64_t gstr[2] = {(cuuint64_t)h->ld0 * 8, (cuuint64_t)h->S_ext * 8};
         cuuint32_t box[3] = {(cuuint32_t)wp.win0, (cuuint32_t)wp.box1, 1};
         cuuint32_t estr[3] = {1, 1, 1};
         void *base = h->d_J + (size_t)s * h->slot_elems_J();
