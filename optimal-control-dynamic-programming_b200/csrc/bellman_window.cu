@@ -42,6 +42,12 @@ struct WindowParams {
     int tj_fastest;            // 1: consecutive CTAs walk dimension 1 (the one the controls sweep)
     int buf_doubles;           // doubles per ring slot (the window, 128 B aligned)
     const double *cmm;         // [P][nchunks][4]: min/max of Tc_0, min/max of Tc_1 per chunk
+    // per-tile-index min/max of the state-indexed tables, computed once on the host:
+    // tmm[p * tmm_stride + tmm_off[d][ab] + 2*t + {0: min, 1: max}], ab = 0 for Ta_d, 1 for Tb_d,
+    // t = tile index along the dimension that indexes that table
+    const double *tmm;
+    int tmm_off[2][2];
+    int tmm_stride;
 };
 
 // --- PTX wrappers ------------------------------------------------------------------------------
@@ -106,7 +112,6 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     // ring of two window slots, win0 x win1 doubles each (dimension 0 contiguous)
     extern __shared__ __align__(128) double ring[];
     __shared__ __align__(8) uint64_t mbar[2];
-    __shared__ double tmm[8];   // min/max over the tile of Ta_0, Tb_0, Ta_1, Tb_1
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int prob = blockIdx.y;
@@ -137,29 +142,26 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    // tile min/max of the state-indexed tables (warp w reduces quantity w)
-    if (wrp < 4) {
-        const double *tab = wrp == 0 ? Ta0 : wrp == 1 ? Tb0 : wrp == 2 ? Ta1 : Tb1;
-        const int src = wrp == 0 ? d0.src_a : wrp == 1 ? d0.src_b : wrp == 2 ? d1.src_a : d1.src_b;
-        double mn = __longlong_as_double(0x7ff0000000000000LL), mx = -mn;
-        if (tab) {
-            const int lo = src == 0 ? i_lo : j_lo, hi = src == 0 ? i_hi : j_hi;
-            for (int k = lo + lane; k < hi; k += 32) {
-                const double v = __ldg(tab + k);
-                mn = fmin(mn, v);
-                mx = fmax(mx, v);
-            }
-#pragma unroll
-            for (int w = 16; w >= 1; w >>= 1) {
-                mn = fmin(mn, __shfl_xor_sync(0xffffffffu, mn, w));
-                mx = fmax(mx, __shfl_xor_sync(0xffffffffu, mx, w));
-            }
-        } else {
-            mn = mx = 0.0;
+    __syncthreads();   // mbarrier init visible to every thread
+
+    // extrema of the state-indexed tables over this tile: precomputed on the host per tile index
+    // (no in-kernel reduction, no barrier that waits on global loads)
+    double tmm[8];
+    {
+        const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
+        const int ta0 = d0.src_a == 0 ? ti : tj, ta1 = d1.src_a == 0 ? ti : tj;
+        tmm[0] = __ldg(tm + wp.tmm_off[0][0] + 2 * ta0); tmm[1] = __ldg(tm + wp.tmm_off[0][0] + 2 * ta0 + 1);
+        tmm[4] = __ldg(tm + wp.tmm_off[1][0] + 2 * ta1); tmm[5] = __ldg(tm + wp.tmm_off[1][0] + 2 * ta1 + 1);
+        tmm[2] = tmm[3] = tmm[6] = tmm[7] = 0.0;
+        if (Tb0) {
+            const int tb = d0.src_b == 0 ? ti : tj;
+            tmm[2] = __ldg(tm + wp.tmm_off[0][1] + 2 * tb); tmm[3] = __ldg(tm + wp.tmm_off[0][1] + 2 * tb + 1);
         }
-        if (lane == 0) { tmm[2 * wrp] = mn; tmm[2 * wrp + 1] = mx; }
+        if (Tb1) {
+            const int tb = d1.src_b == 0 ? ti : tj;
+            tmm[6] = __ldg(tm + wp.tmm_off[1][1] + 2 * tb); tmm[7] = __ldg(tm + wp.tmm_off[1][1] + 2 * tb + 1);
+        }
     }
-    __syncthreads();
 
     // window origin of chunk ch: the cell of the smallest query, formed with the kernel's own
     // association so that the bound is exact
@@ -317,7 +319,7 @@ struct WindowState {
     size_t smem = 0;
     bool hc0 = false, hc1 = false;
     int batch = 4, occ = 2;
-    void *d_cmm = nullptr;
+    void *d_cmm = nullptr, *d_tmm = nullptr;
 };
 
 void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
@@ -483,6 +485,35 @@ void window_setup(bellman_handle *h) {
     if (!upload(cmm, &ws->d_cmm)) { delete ws; return; }
     wp.cmm = static_cast<const double *>(ws->d_cmm);
 
+    // per-tile-index extrema of the state-indexed tables (read by the kernel instead of reducing per tile)
+    {
+        int off = 0;
+        for (int d = 0; d < 2; ++d)
+            for (int ab = 0; ab < 2; ++ab) {
+                wp.tmm_off[d][ab] = off;
+                if (ab == 1 && !hp.has_b[d]) continue;
+                const int src = ab == 0 ? hp.src_a[d] : hp.src_b[d];
+                off += 2 * (src == 0 ? wp.ntile0 : wp.ntile1);
+            }
+        wp.tmm_stride = off;
+        std::vector<double> tmm((size_t)hp.P * off, 0.0);
+        for (int p = 0; p < hp.P; ++p)
+            for (int d = 0; d < 2; ++d)
+                for (int ab = 0; ab < 2; ++ab) {
+                    if (ab == 1 && !hp.has_b[d]) continue;
+                    const int src = ab == 0 ? hp.src_a[d] : hp.src_b[d];
+                    const std::vector<double> &tab = ab == 0 ? hp.Ta[d] : hp.Tb[d];
+                    const int T = src == 0 ? WT0 : WT1, nt = src == 0 ? wp.ntile0 : wp.ntile1;
+                    const int lo0 = h->own_lo[src], cnt = h->own_n[src];
+                    for (int t = 0; t < nt; ++t)
+                        minmax_range(tab.data() + (size_t)p * hp.n[src], lo0 + t * T, std::min(lo0 + (t + 1) * T, lo0 + cnt),
+                                     tmm[(size_t)p * off + wp.tmm_off[d][ab] + 2 * t],
+                                     tmm[(size_t)p * off + wp.tmm_off[d][ab] + 2 * t + 1]);
+                }
+        if (!upload(tmm, &ws->d_tmm)) { delete ws; return; }
+        wp.tmm = static_cast<const double *>(ws->d_tmm);
+    }
+
     // one tensor map per J slot: [P][ext_n1][ext_n0] fp64, box = win0 x box1 x 1
     const int nslots = h->store_J_all ? hp.N : 2;
     ws->maps.resize(nslots);
@@ -515,7 +546,7 @@ void window_setup(bellman_handle *h) {
 void window_teardown(bellman_handle *h) {
     auto *ws = static_cast<WindowState *>(h->wstate);
     if (!ws) return;
-    cudaFree(ws->d_cmm);
+    cudaFree(ws->d_cmm); cudaFree(ws->d_tmm);
     delete ws;
     h->wstate = nullptr;
 }
