@@ -48,6 +48,11 @@ struct WindowParams {
     const double *tmm;
     int tmm_off[2][2];
     int tmm_stride;
+    // canonical state tables (built on the host from Ta/Tb/q; IEEE addition is commutative, so
+    // base_d = row_d[i] + col_d[j] and gs = qrow[i] + qcol[j] reproduce the normative sums):
+    // rowpack[p][i] = {row_0, row_1, qrow, 0},  colpack[p][j] = {col_0, col_1, qcol, 0}
+    const double4 *rowpack, *colpack;
+    int col0_zero, col1_zero;  // the column part of dimension 0 / 1 is absent (all zeros)
 };
 
 // --- PTX wrappers ------------------------------------------------------------------------------
@@ -104,8 +109,14 @@ __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
 }
 
 // BATCH: states evaluated together (instruction-level parallelism); OCC: CTAs per SM the register
-// allocation is sized for
-template <bool HC0, bool HC1, int BATCH, int OCC>
+// allocation is sized for.
+// CHAIN (requires !HC1 and a dimension-0 query that does not depend on the dimension-1 index, e.g.
+// Solver_attitude: w' = w[i] + D[c], theta' = theta[j] + Wt[i]): the 8 states of a thread share
+// cell and weight along dimension 0, and their dimension-1 cells are consecutive, so per control
+// the thread interpolates 9 columns once along dimension 0 and every state blends two neighbouring
+// columns.  Same operations on the same operands as the generic path (bit-identical results),
+// 18 shared-memory loads and ~61 fp64 instructions per 8 updates instead of 32 and ~120.
+template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC>
 __global__ void __launch_bounds__(WNT, OCC)
 k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
                const __grid_constant__ CUtensorMap tmap) {
@@ -129,9 +140,6 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     const uint32_t win_bytes = (uint32_t)win_elems * 8u;
 
     // per-problem tables
-    const double *Ta0 = d0.Ta + (size_t)prob * d0.n_a, *Ta1 = d1.Ta + (size_t)prob * d1.n_a;
-    const double *Tb0 = d0.Tb ? d0.Tb + (size_t)prob * d0.n_b : nullptr;
-    const double *Tb1 = d1.Tb ? d1.Tb + (size_t)prob * d1.n_b : nullptr;
     const double *Tc0 = HC0 ? d0.Tc + (size_t)prob * sp.C : nullptr;
     const double *Tc1 = HC1 ? d1.Tc + (size_t)prob * sp.C : nullptr;
     const double *rr = sp.r + (size_t)prob * sp.C;
@@ -153,11 +161,11 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         tmm[0] = __ldg(tm + wp.tmm_off[0][0] + 2 * ta0); tmm[1] = __ldg(tm + wp.tmm_off[0][0] + 2 * ta0 + 1);
         tmm[4] = __ldg(tm + wp.tmm_off[1][0] + 2 * ta1); tmm[5] = __ldg(tm + wp.tmm_off[1][0] + 2 * ta1 + 1);
         tmm[2] = tmm[3] = tmm[6] = tmm[7] = 0.0;
-        if (Tb0) {
+        if (d0.Tb) {
             const int tb = d0.src_b == 0 ? ti : tj;
             tmm[2] = __ldg(tm + wp.tmm_off[0][1] + 2 * tb); tmm[3] = __ldg(tm + wp.tmm_off[0][1] + 2 * tb + 1);
         }
-        if (Tb1) {
+        if (d1.Tb) {
             const int tb = d1.src_b == 0 ? ti : tj;
             tmm[6] = __ldg(tm + wp.tmm_off[1][1] + 2 * tb); tmm[7] = __ldg(tm + wp.tmm_off[1][1] + 2 * tb + 1);
         }
@@ -167,8 +175,8 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     // association so that the bound is exact
     auto origin = [&](int ch, int &r0, int &c0) {
         double lo0 = tmm[0], lo1 = tmm[4];
-        if (Tb0) lo0 = lo0 + tmm[2];
-        if (Tb1) lo1 = lo1 + tmm[6];
+        if (d0.Tb) lo0 = lo0 + tmm[2];
+        if (d1.Tb) lo1 = lo1 + tmm[6];
         if (HC0) lo0 = lo0 + __ldg(cmm + 4 * ch);
         if (HC1) lo1 = lo1 + __ldg(cmm + 4 * ch + 2);
         // TMA needs the byte offset of the innermost box coordinate to be a multiple of 16
@@ -200,22 +208,32 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     int arg[WR_STATES];
     int cellK0[WR_STATES], cellK1[WR_STATES];   // used only for control-independent dimensions
     double tK0[WR_STATES], tK1[WR_STATES];
-    const double *q0 = d0.q + (size_t)prob * n0, *q1 = d1.q + (size_t)prob * n1;
+    // canonical packed tables: one 32-byte load per row, one per column
+    const double2 *rpk = reinterpret_cast<const double2 *>(wp.rowpack + (size_t)prob * n0 + i);
+    const double2 rp01 = __ldg(rpk), rp23 = __ldg(rpk + 1);
+    const double2 *cpk = reinterpret_cast<const double2 *>(wp.colpack + (size_t)prob * n1);
 #pragma unroll
     for (int m = 0; m < WR_STATES; ++m) {
         const int j = min(jbase + m, j_hi - 1);
-        double b0 = __ldg(Ta0 + (d0.src_a == 0 ? i : j));
-        if (Tb0) b0 = b0 + __ldg(Tb0 + (d0.src_b == 0 ? i : j));
-        double b1 = __ldg(Ta1 + (d1.src_a == 0 ? i : j));
-        if (Tb1) b1 = b1 + __ldg(Tb1 + (d1.src_b == 0 ? i : j));
+        const double2 cp01 = __ldg(cpk + 2 * j), cp23 = __ldg(cpk + 2 * j + 1);
+        const double b0 = wp.col0_zero ? rp01.x : rp01.x + cp01.x;
+        const double b1 = wp.col1_zero ? rp01.y : rp01.y + cp01.y;
         base0[m] = b0;
         base1[m] = b1;
-        const double qa = __ldg(q0 + i), qb = __ldg(q1 + j);
-        gs[m] = sp.q_order[0] == 0 ? qa + qb : qb + qa;
+        gs[m] = rp23.x + cp23.x;
         best[m] = __longlong_as_double(0x7ff0000000000000LL);
         arg[m] = 0;
         if (!HC0) cellK0[m] = locate_uniform<true>(b0, n0, tK0[m]);
         if (!HC1) cellK1[m] = locate_uniform<true>(b1, n1, tK1[m]);
+    }
+    // CHAIN fast path is taken by a warp only if, for every lane, the dimension-1 cells of the 8
+    // states are consecutive (always true in the interior of a uniform grid; ragged tiles and the
+    // clamped edge fall back to the generic path)
+    bool chain_ok = CHAIN;
+    if (CHAIN) {
+#pragma unroll
+        for (int m = 1; m < WR_STATES; ++m) chain_ok = chain_ok && (cellK1[m] == cellK1[0] + m);
+        chain_ok = __all_sync(0xffffffffu, chain_ok);
     }
 
     const int W0 = wp.win0;
@@ -228,6 +246,24 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
             const double bu0 = HC0 ? __ldg(Tc0 + c) : 0.0;
             const double bu1 = HC1 ? __ldg(Tc1 + c) : 0.0;
             const double rc = __ldg(rr + c);
+            if (CHAIN && chain_ok) {
+                double t0c;
+                const int cell0 = locate_uniform<CLAMP>(base0[0] + bu0, n0, t0c);
+                const double *p = Wb + (cellK1[0] * W0 + cell0);
+                double a[WR_STATES + 1];
+#pragma unroll
+                for (int k = 0; k <= WR_STATES; ++k) {
+                    const double lo = p[k * W0], hi = p[k * W0 + 1];
+                    a[k] = fma(t0c, hi - lo, lo);
+                }
+#pragma unroll
+                for (int m = 0; m < WR_STATES; ++m) {
+                    const double v = fma(tK1[m], a[m + 1] - a[m], a[m]);
+                    const double tot = (gs[m] + rc) + v;
+                    if (tot < best[m]) { best[m] = tot; arg[m] = c; }
+                }
+                continue;
+            }
             // two batches of four independent states: enough instruction-level parallelism to
             // cover the fp64 / shared-memory latencies with 16 warps per SM, within 128 registers
 #pragma unroll
@@ -266,8 +302,8 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     for (int ch = 0; ch < wp.nchunks; ++ch) {
         // exact bounds of this chunk's queries, formed with the kernel's own association
         double lo0 = tmm[0], hi0 = tmm[1], lo1 = tmm[4], hi1 = tmm[5];
-        if (Tb0) { lo0 = lo0 + tmm[2]; hi0 = hi0 + tmm[3]; }
-        if (Tb1) { lo1 = lo1 + tmm[6]; hi1 = hi1 + tmm[7]; }
+        if (d0.Tb) { lo0 = lo0 + tmm[2]; hi0 = hi0 + tmm[3]; }
+        if (d1.Tb) { lo1 = lo1 + tmm[6]; hi1 = hi1 + tmm[7]; }
         if (HC0) { lo0 = lo0 + __ldg(cmm + 4 * ch); hi0 = hi0 + __ldg(cmm + 4 * ch + 1); }
         if (HC1) { lo1 = lo1 + __ldg(cmm + 4 * ch + 2); hi1 = hi1 + __ldg(cmm + 4 * ch + 3); }
         const bool interior = lo0 >= 0.0 && hi0 < (double)(n0 - 1) && lo1 >= 0.0 && hi1 < (double)(n1 - 1);
@@ -282,16 +318,20 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     }
 
     if (i_lo + lane < i_hi) {
-        double *Jo = sp.J_out + (size_t)prob * sp.S_ext;
-        int32_t *Io = sp.idx_out + (size_t)prob * sp.S_own;
+        double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
+                     (long long)(jbase - d1.ext_lo) * d1.stride;
+        int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
+                      (long long)(jbase - d1.own_lo) * d0.own_n;
 #pragma unroll
         for (int m = 0; m < WR_STATES; ++m) {
-            const int j = jbase + m;
-            if (j < j_hi) {
-                Jo[(long long)(i - d0.ext_lo) * d0.stride + (long long)(j - d1.ext_lo) * d1.stride] = best[m];
-                Io[(long long)(i - d0.own_lo) + (long long)(j - d1.own_lo) * d0.own_n] = arg[m];
-                if (sp.n_peers) { const int gi[2] = {i, j}; peer_store<2>(sp, prob, gi, best[m]); }
+            if (jbase + m < j_hi) {
+                jo[(long long)m * d1.stride] = best[m];
+                io[(long long)m * d0.own_n] = arg[m];
             }
+        }
+        if (sp.n_peers) {
+            for (int m = 0; m < WR_STATES; ++m)
+                if (jbase + m < j_hi) { const int gi[2] = {i, jbase + m}; peer_store<2>(sp, prob, gi, best[m]); }
         }
     }
 }
@@ -317,9 +357,9 @@ struct WindowState {
     WindowParams wp{};
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
-    bool hc0 = false, hc1 = false;
+    bool hc0 = false, hc1 = false, chain = false;
     int batch = 4, occ = 2;
-    void *d_cmm = nullptr, *d_tmm = nullptr;
+    void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
 
 void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
@@ -331,33 +371,36 @@ void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
 }  // namespace
 
 // picks the kernel instantiation; with set_attr_only it just raises the dynamic shared memory limit
-template <bool HC0, bool HC1, int BATCH, int OCC>
+template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC>
 static bool window_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                       cudaStream_t st, bool set_attr_only) {
-    auto fn = k_stage_window<HC0, HC1, BATCH, OCC>;
+    auto fn = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC>;
     if (set_attr_only)
         return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) ==
                cudaSuccess;
     fn<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
     return true;
 }
-template <bool HC0, bool HC1>
+template <bool HC0, bool HC1, bool CHAIN>
 static bool window_go_hc(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                          cudaStream_t st, bool sa) {
+    if (CHAIN && ws->occ == 3) return window_go<HC0, HC1, CHAIN, 2, 3>(ws, sp, map, grid, st, sa);
+    if (CHAIN && ws->occ == 4) return window_go<HC0, HC1, CHAIN, 2, 4>(ws, sp, map, grid, st, sa);
     if (ws->occ == 1) {
-        if (ws->batch == 8) return window_go<HC0, HC1, 8, 1>(ws, sp, map, grid, st, sa);
-        if (ws->batch == 2) return window_go<HC0, HC1, 2, 1>(ws, sp, map, grid, st, sa);
-        return window_go<HC0, HC1, 4, 1>(ws, sp, map, grid, st, sa);
+        if (ws->batch == 8) return window_go<HC0, HC1, CHAIN, 8, 1>(ws, sp, map, grid, st, sa);
+        if (ws->batch == 2) return window_go<HC0, HC1, CHAIN, 2, 1>(ws, sp, map, grid, st, sa);
+        return window_go<HC0, HC1, CHAIN, 4, 1>(ws, sp, map, grid, st, sa);
     }
-    if (ws->batch == 8) return window_go<HC0, HC1, 8, 2>(ws, sp, map, grid, st, sa);
-    if (ws->batch == 2) return window_go<HC0, HC1, 2, 2>(ws, sp, map, grid, st, sa);
-    return window_go<HC0, HC1, 4, 2>(ws, sp, map, grid, st, sa);
+    if (ws->batch == 8) return window_go<HC0, HC1, CHAIN, 8, 2>(ws, sp, map, grid, st, sa);
+    if (ws->batch == 2) return window_go<HC0, HC1, CHAIN, 2, 2>(ws, sp, map, grid, st, sa);
+    return window_go<HC0, HC1, CHAIN, 4, 2>(ws, sp, map, grid, st, sa);
 }
 static bool window_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map,
                             const void *, dim3 grid, cudaStream_t st, bool sa) {
-    if (ws->hc0 && ws->hc1) return window_go_hc<true, true>(ws, sp, map, grid, st, sa);
-    if (ws->hc0) return window_go_hc<true, false>(ws, sp, map, grid, st, sa);
-    return window_go_hc<false, true>(ws, sp, map, grid, st, sa);
+    if (ws->hc0 && ws->hc1) return window_go_hc<true, true, false>(ws, sp, map, grid, st, sa);
+    if (ws->hc0 && ws->chain) return window_go_hc<true, false, true>(ws, sp, map, grid, st, sa);
+    if (ws->hc0) return window_go_hc<true, false, false>(ws, sp, map, grid, st, sa);
+    return window_go_hc<false, true, false>(ws, sp, map, grid, st, sa);
 }
 
 // Exact worst-case window extents for a given chunk size: replays, on the host, the bound the
@@ -468,6 +511,10 @@ void window_setup(bellman_handle *h) {
     }
     ws->hc0 = hp.has_c[0];
     ws->hc1 = hp.has_c[1];
+    // dimension-0 query independent of the dimension-1 index, dimension 1 independent of the control
+    ws->chain = ws->hc0 && !ws->hc1 && hp.src_a[0] == 0 && (!hp.has_b[0] || hp.src_b[0] == 0) &&
+                !std::getenv("BELLMAN_WIN_NOCHAIN");
+    if (hp.q_order[0] != 0 && hp.q_order[0] != 1) { delete ws; return; }
 
     // per-chunk control min/max and interleaved (grid, rinv) tables
     std::vector<double> cmm((size_t)hp.P * wp.nchunks * 4, 0.0);
@@ -484,6 +531,46 @@ void window_setup(bellman_handle *h) {
     };
     if (!upload(cmm, &ws->d_cmm)) { delete ws; return; }
     wp.cmm = static_cast<const double *>(ws->d_cmm);
+
+    // canonical packed state tables
+    {
+        std::vector<double> rowp((size_t)hp.P * hp.n[0] * 4, 0.0), colp((size_t)hp.P * hp.n[1] * 4, 0.0);
+        bool colz[2] = {true, true};
+        for (int p = 0; p < hp.P; ++p) {
+            for (int d = 0; d < 2; ++d) {
+                const double *ta = hp.Ta[d].data() + (size_t)p * hp.n[hp.src_a[d]];
+                const double *tb = hp.has_b[d] ? hp.Tb[d].data() + (size_t)p * hp.n[hp.src_b[d]] : nullptr;
+                const int sa = hp.src_a[d], sb = hp.has_b[d] ? hp.src_b[d] : -1;
+                for (int i = 0; i < hp.n[0]; ++i) {
+                    double v = 0.0;
+                    if (sa == 0 && sb == 0) v = ta[i] + tb[i];
+                    else if (sa == 0) v = ta[i];
+                    else if (sb == 0) v = tb[i];
+                    rowp[((size_t)p * hp.n[0] + i) * 4 + d] = v;
+                }
+                if (sa == 1 || sb == 1) colz[d] = false;
+                for (int j = 0; j < hp.n[1]; ++j) {
+                    double v = 0.0;
+                    if (sa == 1 && sb == 1) v = ta[j] + tb[j];
+                    else if (sa == 1) v = ta[j];
+                    else if (sb == 1) v = tb[j];
+                    colp[((size_t)p * hp.n[1] + j) * 4 + d] = v;
+                }
+            }
+            for (int i = 0; i < hp.n[0]; ++i) rowp[((size_t)p * hp.n[0] + i) * 4 + 2] = hp.q[0][(size_t)p * hp.n[0] + i];
+            for (int j = 0; j < hp.n[1]; ++j) colp[((size_t)p * hp.n[1] + j) * 4 + 2] = hp.q[1][(size_t)p * hp.n[1] + j];
+        }
+        // a dimension with neither table indexed by the row still needs the row part to be a true
+        // zero that is skipped, otherwise -0.0 + 0.0 would flip a sign; rows are always added, so
+        // require the row part to exist (true for every reference class)
+        for (int d = 0; d < 2; ++d)
+            if (hp.src_a[d] != 0 && !(hp.has_b[d] && hp.src_b[d] == 0)) { delete ws; return; }
+        if (!upload(rowp, &ws->d_rowp) || !upload(colp, &ws->d_colp)) { delete ws; return; }
+        wp.rowpack = static_cast<const double4 *>(ws->d_rowp);
+        wp.colpack = static_cast<const double4 *>(ws->d_colp);
+        wp.col0_zero = colz[0] ? 1 : 0;
+        wp.col1_zero = colz[1] ? 1 : 0;
+    }
 
     // per-tile-index extrema of the state-indexed tables (read by the kernel instead of reducing per tile)
     {
@@ -533,7 +620,7 @@ void window_setup(bellman_handle *h) {
         ws->batch = eb ? std::atoi(eb) : 4;
         ws->occ = eo ? std::atoi(eo) : 2;
         if (ws->batch != 2 && ws->batch != 4 && ws->batch != 8) ws->batch = 4;
-        if (ws->occ != 1 && ws->occ != 2) ws->occ = 2;
+        if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
     }
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { delete ws; return; }
     if (!ws->hc0 && !ws->hc1) { delete ws; return; }   // no control dependence at all: nothing to stage for
@@ -546,7 +633,7 @@ void window_setup(bellman_handle *h) {
 void window_teardown(bellman_handle *h) {
     auto *ws = static_cast<WindowState *>(h->wstate);
     if (!ws) return;
-    cudaFree(ws->d_cmm); cudaFree(ws->d_tmm);
+    cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp);
     delete ws;
     h->wstate = nullptr;
 }
