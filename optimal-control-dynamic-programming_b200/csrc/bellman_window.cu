@@ -29,10 +29,10 @@ namespace bellman {
 namespace {
 
 constexpr int WT0 = 32;        // tile extent along dimension 0 (one warp)
-constexpr int WT1 = 64;        // tile extent along dimension 1
 constexpr int WNT = 256;       // threads per CTA
-constexpr int WR_STATES = 8;   // states per thread (same row, 8 consecutive columns)
-static_assert(WT0 * WT1 == WNT * WR_STATES, "tile / thread mapping");
+// states per thread R (same row, R consecutive columns): 8 normally (tile 32 x 64), 4 for the
+// small-control CHAIN problems (tile 32 x 32, half the registers, twice the CTAs per SM)
+constexpr int tile1_of(int R) { return (WNT / 32) * R; }
 
 struct WindowParams {
     int win0, win1;            // window extent (cells): rows (dim 0, pitch) and columns
@@ -116,10 +116,11 @@ __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
 // the thread interpolates 9 columns once along dimension 0 and every state blends two neighbouring
 // columns.  Same operations on the same operands as the generic path (bit-identical results),
 // 18 shared-memory loads and ~61 fp64 instructions per 8 updates instead of 32 and ~120.
-template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC>
+template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int WR_STATES>
 __global__ void __launch_bounds__(WNT, OCC)
 k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
                const __grid_constant__ CUtensorMap tmap) {
+    constexpr int WT1 = (WNT / 32) * WR_STATES;
     // ring of two window slots, win0 x win1 doubles each (dimension 0 contiguous)
     extern __shared__ __align__(128) double ring[];
     __shared__ __align__(8) uint64_t mbar[2];
@@ -358,7 +359,7 @@ struct WindowState {
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
     bool hc0 = false, hc1 = false, chain = false;
-    int batch = 4, occ = 2;
+    int batch = 4, occ = 2, rstates = 8;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
 
@@ -371,10 +372,10 @@ void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
 }  // namespace
 
 // picks the kernel instantiation; with set_attr_only it just raises the dynamic shared memory limit
-template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC>
+template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int R = 8>
 static bool window_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                       cudaStream_t st, bool set_attr_only) {
-    auto fn = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC>;
+    auto fn = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R>;
     if (set_attr_only)
         return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) ==
                cudaSuccess;
@@ -384,8 +385,11 @@ static bool window_go(const WindowState *ws, const StageParams *sp, const CUtens
 template <bool HC0, bool HC1, bool CHAIN>
 static bool window_go_hc(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                          cudaStream_t st, bool sa) {
-    if (CHAIN && ws->occ == 3) return window_go<HC0, HC1, CHAIN, 2, 3>(ws, sp, map, grid, st, sa);
-    if (CHAIN && ws->occ == 4) return window_go<HC0, HC1, CHAIN, 2, 4>(ws, sp, map, grid, st, sa);
+    if (CHAIN && ws->rstates == 4) {
+        if (ws->occ == 3) return window_go<HC0, HC1, CHAIN, 2, 3, 4>(ws, sp, map, grid, st, sa);
+        if (ws->occ == 1) return window_go<HC0, HC1, CHAIN, 2, 4, 4>(ws, sp, map, grid, st, sa);
+        return window_go<HC0, HC1, CHAIN, 4, 4, 4>(ws, sp, map, grid, st, sa);
+    }
     if (ws->occ == 1) {
         if (ws->batch == 8) return window_go<HC0, HC1, CHAIN, 8, 1>(ws, sp, map, grid, st, sa);
         if (ws->batch == 2) return window_go<HC0, HC1, CHAIN, 2, 1>(ws, sp, map, grid, st, sa);
@@ -406,7 +410,7 @@ static bool window_dispatch(const WindowState *ws, const StageParams *sp, const 
 // Exact worst-case window extents for a given chunk size: replays, on the host, the bound the
 // kernel uses ((min Ta + min Tb) + min Tc .. (max Ta + max Tb) + max Tc, located with the same
 // rule) for every tile and chunk.
-static void window_extents(const bellman_handle *h, int cchunk, int &w0, int &w1) {
+static void window_extents(const bellman_handle *h, int cchunk, int wt1, int &w0, int &w1) {
     const HostProblem &hp = h->hp;
     const int nch = (hp.C + cchunk - 1) / cchunk;
     w0 = w1 = 0;
@@ -416,7 +420,7 @@ static void window_extents(const bellman_handle *h, int cchunk, int &w0, int &w1
             // per tile-index min/max of Ta and Tb along the dimension that indexes them
             auto tile_mm = [&](const std::vector<double> &tab, int src, std::vector<double> &mn,
                                std::vector<double> &mx) {
-                const int T = src == 0 ? WT0 : WT1;
+                const int T = src == 0 ? WT0 : wt1;
                 const int lo0 = h->own_lo[src], cnt = h->own_n[src];
                 const int nt = (cnt + T - 1) / T;
                 mn.resize(nt); mx.resize(nt);
@@ -461,6 +465,12 @@ void window_setup(bellman_handle *h) {
     PFN_encodeTiled enc = get_encode();
     if (!enc) return;
 
+    // small-control CHAIN problems run 4 states per thread (see k_stage_window)
+    const bool chain_cfg = hp.has_c[0] && !hp.has_c[1] && hp.src_a[0] == 0 && (!hp.has_b[0] || hp.src_b[0] == 0) &&
+                           !std::getenv("BELLMAN_WIN_NOCHAIN");
+    const int rstates = (chain_cfg && hp.C <= 8 && !std::getenv("BELLMAN_WIN_R8")) ? 4 : 8;
+    const int wt1 = tile1_of(rstates);
+
     // pick the chunk size: most updates per staged byte among configs that keep two CTAs per SM
     const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
     int best_cc = 0, best_w0 = 0, best_w1 = 0;
@@ -471,7 +481,7 @@ void window_setup(bellman_handle *h) {
     if (hp.C <= 32 && std::find(cands.begin(), cands.end(), hp.C) == cands.end()) cands.push_back(hp.C);
     for (int cc : cands) {
         int w0, w1;
-        window_extents(h, cc, w0, w1);
+        window_extents(h, cc, wt1, w0, w1);
         w0 = (w0 + 1 + 15) / 16 * 16;             // +1: the window origin is rounded down to an even row
         if (w0 > 256) continue;
         const int boxes = (w1 + 255) / 256;
@@ -496,7 +506,7 @@ void window_setup(bellman_handle *h) {
     wp.cchunk = best_cc;
     wp.nchunks = (hp.C + best_cc - 1) / best_cc;
     wp.ntile0 = (h->own_n[0] + WT0 - 1) / WT0;
-    wp.ntile1 = (h->own_n[1] + WT1 - 1) / WT1;
+    wp.ntile1 = (h->own_n[1] + wt1 - 1) / wt1;
     ws->smem = 2 * slot_bytes(wp.win0, wp.win1);
     wp.buf_doubles = (int)(slot_bytes(wp.win0, wp.win1) / 8);
     {   // fastest tile index = the dimension the control grid sweeps furthest (in cells)
@@ -512,8 +522,8 @@ void window_setup(bellman_handle *h) {
     ws->hc0 = hp.has_c[0];
     ws->hc1 = hp.has_c[1];
     // dimension-0 query independent of the dimension-1 index, dimension 1 independent of the control
-    ws->chain = ws->hc0 && !ws->hc1 && hp.src_a[0] == 0 && (!hp.has_b[0] || hp.src_b[0] == 0) &&
-                !std::getenv("BELLMAN_WIN_NOCHAIN");
+    ws->chain = chain_cfg;
+    ws->rstates = rstates;
     if (hp.q_order[0] != 0 && hp.q_order[0] != 1) { delete ws; return; }
 
     // per-chunk control min/max and interleaved (grid, rinv) tables
@@ -590,7 +600,7 @@ void window_setup(bellman_handle *h) {
                     if (ab == 1 && !hp.has_b[d]) continue;
                     const int src = ab == 0 ? hp.src_a[d] : hp.src_b[d];
                     const std::vector<double> &tab = ab == 0 ? hp.Ta[d] : hp.Tb[d];
-                    const int T = src == 0 ? WT0 : WT1, nt = src == 0 ? wp.ntile0 : wp.ntile1;
+                    const int T = src == 0 ? WT0 : wt1, nt = src == 0 ? wp.ntile0 : wp.ntile1;
                     const int lo0 = h->own_lo[src], cnt = h->own_n[src];
                     for (int t = 0; t < nt; ++t)
                         minmax_range(tab.data() + (size_t)p * hp.n[src], lo0 + t * T, std::min(lo0 + (t + 1) * T, lo0 + cnt),
@@ -625,7 +635,7 @@ void window_setup(bellman_handle *h) {
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { delete ws; return; }
     if (!ws->hc0 && !ws->hc1) { delete ws; return; }   // no control dependence at all: nothing to stage for
     h->wstate = ws;
-    h->wcfg.tile0 = WT0; h->wcfg.tile1 = WT1; h->wcfg.cchunk = wp.cchunk;
+    h->wcfg.tile0 = WT0; h->wcfg.tile1 = wt1; h->wcfg.cchunk = wp.cchunk;
     h->wcfg.win0 = wp.win0; h->wcfg.win1 = wp.win1;
     h->wcfg.valid = true;
 }
