@@ -102,15 +102,22 @@ static int upload_tables(bellman_handle *h) {
         o_Tc[d] = hp.has_c[d] ? push(hp.Tc[d]) : 0;
         o_q[d] = push(hp.q[d]);
         std::vector<double> loc(2 * (size_t)P);
-        for (int p = 0; p < P; ++p) { loc[2 * p] = hp.inv_h[d][p]; loc[2 * p + 1] = hp.off[d][p]; }
+        for (int p = 0; p < P; ++p) {
+            const bool uni = hp.mode[(size_t)p * D + d] == BELLMAN_LOCATE_UNIFORM;
+            loc[2 * p] = uni ? hp.inv_h[d][p] : hp.lut_invw[d][p];
+            loc[2 * p + 1] = uni ? hp.off[d][p] : hp.grid[d][(size_t)p * hp.n[d]];
+        }
         o_loc[d] = push(loc);
     }
     o_r = push(hp.r);
     CUDA_TRY(h, cudaMalloc(&h->d_tab, buf.size() * sizeof(double)));
     CUDA_TRY(h, cudaMemcpy(h->d_tab, buf.data(), buf.size() * sizeof(double), cudaMemcpyHostToDevice));
+    // int table: modes [D][P], then the bucket tables of every dimension
     std::vector<int32_t> modes((size_t)D * P);
     for (int d = 0; d < D; ++d)
         for (int p = 0; p < P; ++p) modes[(size_t)d * P + p] = hp.mode[(size_t)p * D + d];
+    size_t o_lut[MAXD];
+    for (int d = 0; d < D; ++d) { o_lut[d] = modes.size(); modes.insert(modes.end(), hp.lut[d].begin(), hp.lut[d].end()); }
     CUDA_TRY(h, cudaMalloc(&h->d_mode, modes.size() * sizeof(int32_t)));
     CUDA_TRY(h, cudaMemcpy(h->d_mode, modes.data(), modes.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
 
@@ -128,6 +135,8 @@ static int upload_tables(bellman_handle *h) {
         dp.q = h->d_tab + o_q[d];
         dp.loc = h->d_tab + o_loc[d];
         dp.mode = h->d_mode + (size_t)d * P;
+        dp.lut = h->d_mode + o_lut[d];
+        dp.lut_n = hp.lut_n[d];
         dp.n = hp.n[d];
         dp.src_a = hp.src_a[d];
         dp.src_b = hp.has_b[d] ? hp.src_b[d] : 0;
@@ -694,6 +703,9 @@ extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double 
     rp.grid1 = h->sp.dim[1].grid; rp.rinv1 = h->sp.dim[1].rinv;
     rp.inv_h0 = hp.inv_h[0][0]; rp.off0 = hp.off[0][0];
     rp.inv_h1 = hp.inv_h[1][0]; rp.off1 = hp.off[1][0];
+    rp.lut0 = h->sp.dim[0].lut; rp.lut1 = h->sp.dim[1].lut;
+    rp.lut_n0 = hp.lut_n[0]; rp.lut_n1 = hp.lut_n[1];
+    rp.lut_invw0 = hp.lut_invw[0][0]; rp.lut_invw1 = hp.lut_invw[1][0];
     rp.mode0 = hp.mode[0]; rp.mode1 = hp.mode[1];
     rp.n0 = hp.n[0]; rp.n1 = hp.n[1]; rp.N = N; rp.C = hp.C; rp.batch = batch;
     rp.mode = mode; rp.ssu_stage = ssu_stage;

@@ -21,6 +21,12 @@ struct HostProblem {
     bool has_b[MAXD] = {false, false, false, false}, has_c[MAXD] = {false, false, false, false};
     std::vector<double> grid[MAXD], rinv[MAXD], Ta[MAXD], Tb[MAXD], Tc[MAXD], q[MAXD], r;
     std::vector<double> inv_h[MAXD], off[MAXD];   // [P] per dim
+    // SEARCH dimensions: bucket table that starts the exact bin search a cell or two below the
+    // answer: lut[d][p*(lut_n[d]+1) + b] = cell of the lower edge of bucket b (4 buckets per cell),
+    // bucket(x) = floor((x - s[0]) * lut_invw[d][p])
+    std::vector<int32_t> lut[MAXD];
+    std::vector<double> lut_invw[MAXD];
+    int lut_n[MAXD] = {0, 0, 0, 0};
     std::vector<int32_t> mode;                    // [P][D]
     int64_t S() const { int64_t s = 1; for (int d = 0; d < D; ++d) s *= n[d]; return s; }
 };
@@ -44,8 +50,10 @@ struct DimParams {
     const double *Tb;     // [P][n_b] or nullptr
     const double *Tc;     // [P][C]   or nullptr
     const double *q;      // [P][n]
-    const double *loc;    // [P][2] = {inv_h, off}
+    const double *loc;    // [P][2] = {inv_h, off} (UNIFORM) or {lut_invw, s[0]} (SEARCH)
     const int32_t *mode;  // [P]
+    const int32_t *lut;   // [P][lut_n + 1] (SEARCH dimensions)
+    int lut_n;
     int n, n_a, n_b, src_a, src_b;
     int own_n;            // number of owned indices along this dim (== n unless partitioned)
     int own_lo;           // first owned global index

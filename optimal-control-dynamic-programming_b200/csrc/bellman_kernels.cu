@@ -17,18 +17,18 @@ constexpr int BLOCK = 256;
 // x is in kernel units: the fractional cell coordinate for UNIFORM dimensions (the host pre-scaled
 // the tables), the state value for SEARCH dimensions.
 __device__ __forceinline__ int locate(const double *__restrict__ s, const double *__restrict__ rinv, int n,
-                                      int mode, double x, double &t) {
+                                      int mode, const int32_t *__restrict__ lut, int lut_n, double lut_invw,
+                                      double x, double &t) {
     int cell;
     if (mode == BELLMAN_LOCATE_UNIFORM) {
         cell = min(max(__double2int_rd(x), 0), n - 2);   // floor (saturating), then clamp
         t = x - (double)cell;
     } else {
-        int lo = 0, hi = n;                               // #{ s[i] <= x }
-        while (lo < hi) {
-            const int mid = (lo + hi) >> 1;
-            if (__ldg(s + mid) <= x) lo = mid + 1; else hi = mid;
-        }
-        cell = min(max(lo - 1, 0), n - 2);
+        // exact bin rule  cell = clamp(#{ s[i] <= x } - 1, 0, n-2): the bucket table gives a cell at
+        // or below the answer (one bucket of slack absorbs rounding), a short scan finishes it
+        const int b = min(max(__double2int_rd((x - __ldg(s)) * lut_invw) - 1, 0), lut_n);
+        cell = __ldg(lut + b);
+        while (cell < n - 2 && __ldg(s + cell + 1) <= x) ++cell;
         t = (x - __ldg(s + cell)) * __ldg(rinv + cell);
     }
     return cell;
@@ -37,7 +37,9 @@ __device__ __forceinline__ int locate(const double *__restrict__ s, const double
 template <int D>
 struct Prob {
     const double *grid[D], *rinv[D], *Ta[D], *Tb[D], *Tc[D], *q[D];
-    int mode[D], n[D];
+    int mode[D], n[D], lut_n[D];
+    const int32_t *lut[D];
+    double lut_invw[D];
     const double *r;
     __device__ __forceinline__ void load(const StageParams &sp, int prob) {
 #pragma unroll
@@ -51,32 +53,63 @@ struct Prob {
             Tc[d] = dp.Tc ? dp.Tc + (size_t)prob * sp.C : nullptr;
             q[d] = dp.q + (size_t)prob * dp.n;
             mode[d] = __ldg(dp.mode + prob);
+            lut[d] = dp.lut + (size_t)prob * (dp.lut_n + 1);
+            lut_n[d] = dp.lut_n;
+            lut_invw[d] = __ldg(dp.loc + 2 * prob);
         }
         r = sp.r + (size_t)prob * sp.C;
     }
 };
 
+// control-independent dimensions are located once per state; FixedDims carries their cells/weights
+template <int D>
+struct FixedDims {
+    double t[D];
+    long long off;      // element offset contributed by the control-independent dimensions
+};
+
+template <int D>
+__device__ __forceinline__ void locate_fixed(const Prob<D> &pb, const StageParams &sp, const double (&base)[D],
+                                             FixedDims<D> &fx) {
+    fx.off = 0;
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        fx.t[d] = 0.0;
+        if (!pb.Tc[d]) {
+            const int cell = locate(pb.grid[d], pb.rinv[d], pb.n[d], pb.mode[d], pb.lut[d], pb.lut_n[d],
+                                    pb.lut_invw[d], base[d], fx.t[d]);
+            fx.off += (long long)(cell - sp.dim[d].ext_lo) * sp.dim[d].stride;
+        }
+    }
+}
+
 // one (state, control) evaluation: returns the interpolated J_{k+1}(x')
 template <int D>
 __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams &sp,
                                             const double *__restrict__ Jn, const double (&base)[D],
-                                            int c) {
+                                            const FixedDims<D> &fx, int c) {
     double t[D];
-    long long o = 0;
+    long long o = fx.off;
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        const double xq = pb.Tc[d] ? base[d] + __ldg(pb.Tc[d] + c) : base[d];
-        const int cell = locate(pb.grid[d], pb.rinv[d], pb.n[d], pb.mode[d], xq, t[d]);
-        o += (long long)(cell - sp.dim[d].ext_lo) * sp.dim[d].stride;
+        if (pb.Tc[d]) {
+            const double xq = base[d] + __ldg(pb.Tc[d] + c);
+            const int cell = locate(pb.grid[d], pb.rinv[d], pb.n[d], pb.mode[d], pb.lut[d], pb.lut_n[d],
+                                    pb.lut_invw[d], xq, t[d]);
+            o += (long long)(cell - sp.dim[d].ext_lo) * sp.dim[d].stride;
+        } else {
+            t[d] = fx.t[d];
+        }
     }
+    const double *__restrict__ p = Jn + o;
     double v[1 << D];
 #pragma unroll
     for (int m = 0; m < (1 << D); ++m) {
-        long long oo = o;
+        long long oo = 0;
 #pragma unroll
         for (int d = 0; d < D; ++d)
             if (m & (1 << d)) oo += sp.dim[d].stride;
-        v[m] = __ldg(Jn + oo);
+        v[m] = __ldg(p + oo);
     }
 #pragma unroll
     for (int d = 0; d < D; ++d)               // dimension 0 reduced first
@@ -134,11 +167,13 @@ k_stage_direct(const __grid_constant__ StageParams sp) {
     const double gs = state_terms<D>(pb, sp, gi, base);
     const double *__restrict__ Jn = sp.J_next + (size_t)prob * sp.S_ext;
 
+    FixedDims<D> fx;
+    locate_fixed<D>(pb, sp, base, fx);
     double best = __longlong_as_double(0x7ff0000000000000LL);   // +inf
     int arg = 0;
 #pragma unroll 2
     for (int c = 0; c < sp.C; ++c) {
-        const double v = interp_at<D>(pb, sp, Jn, base, c);
+        const double v = interp_at<D>(pb, sp, Jn, base, fx, c);
         const double tot = (gs + __ldg(pb.r + c)) + v;
         if (tot < best) { best = tot; arg = c; }
     }
@@ -167,10 +202,12 @@ k_stage_splitc(const __grid_constant__ StageParams sp) {
     const double gs = state_terms<D>(pb, sp, gi, base);
     const double *__restrict__ Jn = sp.J_next + (size_t)prob * sp.S_ext;
 
+    FixedDims<D> fx;
+    locate_fixed<D>(pb, sp, base, fx);
     double best = __longlong_as_double(0x7ff0000000000000LL);
     int arg = 0x7fffffff;
     for (int c = lane; c < sp.C; c += L) {
-        const double v = interp_at<D>(pb, sp, Jn, base, c);
+        const double v = interp_at<D>(pb, sp, Jn, base, fx, c);
         const double tot = (gs + __ldg(pb.r + c)) + v;
         if (tot < best) { best = tot; arg = c; }
     }
@@ -247,9 +284,9 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
         const int32_t *__restrict__ id = rp.idx_all + (size_t)(st - 1) * S;
         double t0, t1;
         // a free state is brought to kernel units first (include/bellman.h, bellman_rollout)
-        const int c0 = locate(rp.grid0, rp.rinv0, rp.n0, rp.mode0,
+        const int c0 = locate(rp.grid0, rp.rinv0, rp.n0, rp.mode0, rp.lut0, rp.lut_n0, rp.lut_invw0,
                               rp.mode0 == BELLMAN_LOCATE_UNIFORM ? fma(x1, rp.inv_h0, rp.off0) : x1, t0);
-        const int c1 = locate(rp.grid1, rp.rinv1, rp.n1, rp.mode1,
+        const int c1 = locate(rp.grid1, rp.rinv1, rp.n1, rp.mode1, rp.lut1, rp.lut_n1, rp.lut_invw1,
                               rp.mode1 == BELLMAN_LOCATE_UNIFORM ? fma(x2, rp.inv_h1, rp.off1) : x2, t1);
         const long long o = c0 + (long long)c1 * rp.n0;
         const double v00 = rp.u_values[id[o]], v10 = rp.u_values[id[o + 1]];

@@ -30,6 +30,9 @@ cudaError_t launch_check_sums(const StageParams &sp, double *d_partials, int n_p
 struct RolloutParams {
     const double *grid0, *rinv0, *grid1, *rinv1;
     double inv_h0, off0, inv_h1, off1;
+    const int32_t *lut0, *lut1;
+    int lut_n0, lut_n1;
+    double lut_invw0, lut_invw1;
     int mode0, mode1, n0, n1, N, C, batch, mode, ssu_stage;
     const int32_t *idx_all;   // [N][S]
     const double *u_values;   // [C]

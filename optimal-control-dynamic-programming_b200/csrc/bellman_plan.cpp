@@ -71,6 +71,24 @@ std::string load_problem(const bellman_desc *d, HostProblem &hp) {
                 grid_is_uniform(s, n) ? BELLMAN_LOCATE_UNIFORM : BELLMAN_LOCATE_SEARCH;
         }
     }
+    // SEARCH dimensions: bucket table (does not change the result of the bin search, only where it starts)
+    for (int k = 0; k < hp.D; ++k) {
+        const int n = hp.n[k];
+        hp.lut_n[k] = 4 * n;
+        hp.lut[k].assign((size_t)hp.P * (hp.lut_n[k] + 1), 0);
+        hp.lut_invw[k].assign(hp.P, 0.0);
+        for (int p = 0; p < hp.P; ++p) {
+            const double *s = hp.grid[k].data() + (size_t)p * n;
+            const double w = (s[n - 1] - s[0]) / (double)hp.lut_n[k];
+            hp.lut_invw[k][p] = 1.0 / w;
+            int cell = 0;
+            for (int b = 0; b <= hp.lut_n[k]; ++b) {
+                const double edge = s[0] + (double)b * w;
+                while (cell < n - 2 && s[cell + 1] <= edge) ++cell;
+                hp.lut[k][(size_t)p * (hp.lut_n[k] + 1) + b] = cell;
+            }
+        }
+    }
     // UNIFORM dimensions are evaluated in cell units (include/bellman.h): rescale the next-state
     // tables of every (problem, dimension) that uses the uniform rule, one rounding per entry
     for (int k = 0; k < hp.D; ++k)
