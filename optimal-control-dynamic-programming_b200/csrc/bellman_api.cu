@@ -551,6 +551,7 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
         o = *opts;
     }
     if (h->cur_stage - n_stages < 1) { h->err = "run would pass stage 1"; return BELLMAN_ERR_STATE; }
+    const HostProblem &hp = h->hp;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int lanes = 1;
     const int kernel = pick_kernel(h, o.kernel, lanes);
@@ -573,6 +574,31 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
         if (o.check_period > 0) {
             int next_check = ((h->cur_stage - 1) / o.check_period) * o.check_period;   // largest multiple < cur
             if (next_check >= 1) span = std::min(span, h->cur_stage - next_check);
+        }
+        // small single-GPU problems: the whole span in ONE cooperative launch (grid barrier per stage)
+        if (o.use_graph && h->nranks == 1 && !o.sync_each_stage && span >= 2 && o.kernel != BELLMAN_KERNEL_DIRECT &&
+            o.kernel != BELLMAN_KERNEL_WINDOW && !std::getenv("BELLMAN_NO_PERSISTENT")) {
+            int L = 1;
+            const long long states = h->S_own * hp.P;
+            // only when a stage is launch-latency sized (< ~2M updates); bigger stages want every
+            // resident thread busy and are better served by one launch per stage
+            const int cap = states * hp.C <= 2000000 ? persistent_capacity_threads(hp.D) : 0;
+            while (L < 32 && 2 * L <= hp.C && states * (2 * L) <= cap) L *= 2;
+            if (states * L <= cap) {
+                if (!h->d_barrier) CUDA_TRY(h, cudaMalloc(&h->d_barrier, 2 * sizeof(double)));
+                StageParams sp = h->sp;
+                sp.n_peers = 0; sp.part_dim = 0;
+                cudaError_t e = launch_sweep_persistent(sp, h->d_J, h->d_idx, (long long)h->slot_elems_J(),
+                                                        (long long)h->slot_elems_idx(), h->store_J_all ? 1 : 0,
+                                                        h->store_idx_all ? 1 : 0, hp.N, h->cur_stage, span, L,
+                                                        reinterpret_cast<unsigned int *>(h->d_barrier), h->stream);
+                if (e != cudaSuccess) { h->err = std::string("persistent sweep launch: ") + cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
+                h->last_kernel = "persistent";
+                h->last_launches += 1;
+                h->cur_stage -= span;
+                done += span;
+                span = 0;
+            }
         }
         if (graphable && span >= 4) {
             // ping-pong storage has period 2: a captured pair of stages is replayed span/2 times.

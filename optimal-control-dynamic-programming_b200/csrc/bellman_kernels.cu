@@ -84,7 +84,9 @@ __device__ __forceinline__ void locate_fixed(const Prob<D> &pb, const StageParam
 }
 
 // one (state, control) evaluation: returns the interpolated J_{k+1}(x')
-template <int D>
+// COHERENT: read J_{k+1} with ld.global.cg (L2 only).  Needed when J_{k+1} was written earlier in
+// the SAME kernel by other SMs (persistent multi-stage kernel); L1 is not coherent across SMs.
+template <int D, bool COHERENT = false>
 __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams &sp,
                                             const double *__restrict__ Jn, const double (&base)[D],
                                             const FixedDims<D> &fx, int c) {
@@ -109,7 +111,7 @@ __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams
 #pragma unroll
         for (int d = 0; d < D; ++d)
             if (m & (1 << d)) oo += sp.dim[d].stride;
-        v[m] = __ldg(p + oo);
+        v[m] = COHERENT ? __ldcg(p + oo) : __ldg(p + oo);
     }
 #pragma unroll
     for (int d = 0; d < D; ++d)               // dimension 0 reduced first
@@ -221,6 +223,86 @@ k_stage_splitc(const __grid_constant__ StageParams sp) {
         sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
         sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
         if (sp.n_peers) peer_store<D>(sp, prob, gi, best);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// K_persistent: the whole stage loop in ONE cooperative launch, for grids too small for a launch
+// per stage to make sense (Solver_position: 3 x 201 x 201 states x 3 controls x 5999 stages).
+// Every thread owns one (state, control-lane) pair for all stages; stages are separated by a
+// grid-wide barrier (monotone atomic counter; co-residency is guaranteed by the cooperative
+// launch).  J ping-pongs in global memory and stays in L2; gathers use ld.global.cg.
+// ---------------------------------------------------------------------------------------------
+struct PersistParams {
+    double *J_base;          // slot 0
+    int32_t *idx_base;
+    long long J_slot_elems, idx_slot_elems;
+    int store_J_all, store_idx_all, N;
+    int stage_from;          // stage number of the input J of the first stage
+    int n_stages;
+    int lanes;               // control lanes per state (power of two <= 32)
+    unsigned int *barrier;   // zero-initialised counter
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int target) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(counter, 1u);
+        unsigned int v;
+        do {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        } while (v < target);
+    }
+    __syncthreads();
+}
+
+template <int D>
+__global__ void __launch_bounds__(BLOCK, (D == 2 ? 4 : 2))
+k_sweep_persistent(const __grid_constant__ StageParams sp, const __grid_constant__ PersistParams pp) {
+    const int L = pp.lanes;
+    const long long gtid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    const long long total = sp.S_own * sp.P;              // states over all problems
+    long long g = gtid / L;
+    const int lane = (int)(gtid % L);
+    const bool live = g < total;
+    if (!live) g = total - 1;
+    const int prob = (int)(g / sp.S_own);
+    const long long s = g - (long long)prob * sp.S_own;
+    Prob<D> pb;
+    pb.load(sp, prob);
+    int gi[D];
+    const long long o_self = decompose<D>(sp, s, gi);
+    double base[D];
+    const double gs = state_terms<D>(pb, sp, gi, base);
+    FixedDims<D> fx;
+    locate_fixed<D>(pb, sp, base, fx);
+
+    for (int it = 0; it < pp.n_stages; ++it) {
+        const int from = pp.stage_from - it, to = from - 1;
+        const int js_from = pp.store_J_all ? from - 1 : ((pp.N - from) & 1);
+        const int js_to = pp.store_J_all ? to - 1 : ((pp.N - to) & 1);
+        const double *__restrict__ Jn = pp.J_base + (size_t)js_from * pp.J_slot_elems + (size_t)prob * sp.S_ext;
+        double *Jo = pp.J_base + (size_t)js_to * pp.J_slot_elems + (size_t)prob * sp.S_ext;
+        int32_t *Io = pp.idx_base + (size_t)(pp.store_idx_all ? to - 1 : 0) * pp.idx_slot_elems + (size_t)prob * sp.S_own;
+
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        int arg = 0x7fffffff;
+        for (int c = lane; c < sp.C; c += L) {
+            const double v = interp_at<D, true>(pb, sp, Jn, base, fx, c);
+            const double tot = (gs + __ldg(pb.r + c)) + v;
+            if (tot < best) { best = tot; arg = c; }
+        }
+        for (int w = L / 2; w >= 1; w >>= 1) {
+            const double ob = __shfl_xor_sync(0xffffffffu, best, w);
+            const int oa = __shfl_xor_sync(0xffffffffu, arg, w);
+            if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
+        }
+        if (live && lane == 0) {
+            Jo[o_self] = best;
+            Io[s] = arg;
+        }
+        if (it + 1 < pp.n_stages) grid_barrier(pp.barrier, (unsigned int)(it + 1) * gridDim.x);
     }
 }
 
@@ -354,6 +436,44 @@ cudaError_t launch_check_sums(const StageParams &sp, double *d_partials, int n_p
     }
     k_check_final<<<1, 32, 0, st>>>(d_partials, n_partials, d_out2);
     return cudaGetLastError();
+}
+
+int persistent_capacity_threads(int D) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaSuccess;
+    switch (D) {
+        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<2>, BLOCK, 0); break;
+        case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<3>, BLOCK, 0); break;
+        case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<4>, BLOCK, 0); break;
+        default: return 0;
+    }
+    if (e != cudaSuccess) { cudaGetLastError(); return 0; }
+    return sms * per_sm * BLOCK;
+}
+
+cudaError_t launch_sweep_persistent(const StageParams &sp, double *J_base, int32_t *idx_base,
+                                    long long J_slot_elems, long long idx_slot_elems, int store_J_all,
+                                    int store_idx_all, int N, int stage_from, int n_stages, int lanes,
+                                    unsigned int *d_barrier, cudaStream_t st) {
+    PersistParams pp;
+    pp.J_base = J_base; pp.idx_base = idx_base;
+    pp.J_slot_elems = J_slot_elems; pp.idx_slot_elems = idx_slot_elems;
+    pp.store_J_all = store_J_all; pp.store_idx_all = store_idx_all; pp.N = N;
+    pp.stage_from = stage_from; pp.n_stages = n_stages; pp.lanes = lanes; pp.barrier = d_barrier;
+    cudaError_t e = cudaMemsetAsync(d_barrier, 0, sizeof(unsigned int), st);
+    if (e != cudaSuccess) return e;
+    const long long threads = sp.S_own * sp.P * lanes;
+    const dim3 grid((unsigned)((threads + BLOCK - 1) / BLOCK));
+    StageParams spc = sp;
+    void *args[] = {(void *)&spc, (void *)&pp};
+    switch (sp.D) {
+        case 2: return cudaLaunchCooperativeKernel((const void *)k_sweep_persistent<2>, grid, dim3(BLOCK), args, 0, st);
+        case 3: return cudaLaunchCooperativeKernel((const void *)k_sweep_persistent<3>, grid, dim3(BLOCK), args, 0, st);
+        case 4: return cudaLaunchCooperativeKernel((const void *)k_sweep_persistent<4>, grid, dim3(BLOCK), args, 0, st);
+        default: return cudaErrorInvalidValue;
+    }
 }
 
 cudaError_t launch_rollout(const RolloutParams &rp, cudaStream_t st) {

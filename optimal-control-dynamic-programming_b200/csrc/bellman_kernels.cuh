@@ -14,6 +14,14 @@ cudaError_t launch_stage_direct(const StageParams &sp, cudaStream_t st);
 // (value, index) shuffle reduction: for grids too small to fill the GPU with one thread per state.
 cudaError_t launch_stage_splitc(const StageParams &sp, int lanes_per_state, cudaStream_t st);
 
+// whole stage loop in one cooperative launch (small grids): every thread keeps its state for all
+// stages, a grid-wide barrier separates stages.  persistent_capacity_threads() = resident threads.
+int persistent_capacity_threads(int D);
+cudaError_t launch_sweep_persistent(const StageParams &sp, double *J_base, int32_t *idx_base,
+                                    long long J_slot_elems, long long idx_slot_elems, int store_J_all,
+                                    int store_idx_all, int N, int stage_from, int n_stages, int lanes,
+                                    unsigned int *d_barrier, cudaStream_t st);
+
 // D = 2 stage with the J_{k+1} neighbourhood of a state tile staged in shared memory by TMA.
 struct WindowLaunch {
     WindowConfig cfg;

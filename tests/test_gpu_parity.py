@@ -114,8 +114,37 @@ def test_position_reference_size(bellman, oracle_lib, graph):
     n = 61
     ora = oracle_lib.sweep(d, n_stages=n)
     sw = bellman.Sweep(d).run(n, use_graph=graph)
+    if graph:
+        assert sw.last_kernel == "persistent"      # one cooperative launch, grid barrier per stage
     assert sw.current_stage == ora["stage"] == d.N - n
     assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "position")
+    sw.close()
+
+
+def test_persistent_kernel_variants(bellman, oracle_lib, golden, monkeypatch):
+    """Persistent multi-stage kernel: control lanes + store-all slots (golden Kirk), D = 4 pos-att,
+    and the CUDA-graph fallback when the persistent path is disabled."""
+    d = golden_desc(bellman, golden)
+    ora = oracle_lib.sweep(d, keep_all=True)
+    sw = bellman.Sweep(d).run(d.N - 1, use_graph=True)
+    assert sw.last_kernel == "persistent"
+    for k in (1, 7, d.N - 1):
+        assert_stage_equal(sw.get_J(k), sw.get_idx(k), ora["J_all"][k - 1], ora["idx_all"][k - 1], f"persistent stage {k}")
+    sw.close()
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 12, 10, 8, 7
+    d4 = sp.channel_desc(0)
+    o4 = oracle_lib.sweep(d4, n_stages=9)
+    sw = bellman.Sweep(d4).run(9, use_graph=True)
+    assert sw.last_kernel == "persistent"
+    assert_stage_equal(sw.get_J(), sw.get_idx(), o4["J_last"], o4["idx_last"], "persistent D=4")
+    sw.close()
+    monkeypatch.setenv("BELLMAN_NO_PERSISTENT", "1")
+    pos = bellman.tables.stack_problems(bellman.Solver_position()._axis_descs())
+    op = oracle_lib.sweep(pos, n_stages=11)
+    sw = bellman.Sweep(pos).run(11, use_graph=True)
+    assert sw.last_kernel != "persistent"
+    assert_stage_equal(sw.get_J(), sw.get_idx(), op["J_last"], op["idx_last"], "graph fallback")
     sw.close()
 
 
