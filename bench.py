@@ -187,6 +187,7 @@ def main():
     ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "window", "splitc"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (N = 1 default run)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -315,6 +316,8 @@ def main():
 
     # ---- roofline of the stage kernel ---------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
+    kernel_name = sw.last_kernel
+    halo_mode = sw.halo_mode if world > 1 else None
     bytes_per_launch = (S_all / world) * (16 + 4)          # read J_{k+1}, write J_k, write int32 argmin
     ms_kernel = (ms_dev - ms_x) / K
     achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
@@ -324,12 +327,34 @@ def main():
     fp64_peak = 64 * 148 * mhz * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "kernel_ms": ms_kernel, "kernel": sw.last_kernel,
+                "bytes_per_launch": bytes_per_launch, "kernel_ms": ms_kernel, "kernel": kernel_name,
                 "fp64_secondary": {"ops_per_update": fp64_ops_per_update,
                                    "achieved_ops_per_s": value / world * fp64_ops_per_update,
                                    "peak_ops_per_s": fp64_peak,
                                    "frac": value / world * fp64_ops_per_update / fp64_peak,
                                    "note": "C>=16 makes the stage fp64-issue bound, not HBM bound (DESIGN.md)"}}
+
+    # other configurations of BASELINE.json, device-resident, same timing rules (N = 1 only):
+    # the small-control ones are where the HBM roofline is the relevant bound
+    others = {}
+    if world == 1 and not args.no_others and args.workload == DEFAULT_WORKLOAD:
+        sw.close()
+        sw = None
+        for name, steps in (("attitude_x16_3x16000x4800x3", 20), ("attitude_x4_3x4000x1200x3", 40),
+                            ("position_3x201x201x3", 400), ("kirk_default_100x100x1000", 40),
+                            ("pos_att_x4_120x120x80x60x9", 5)):
+            d2 = make_desc(bb, name)
+            s2 = bb.Sweep(d2, device=local)
+            g2 = d2.S * d2.P < 4_000_000
+            s2.run(3, use_graph=g2)
+            s2.run(steps, use_graph=g2)
+            t2 = s2.stats()
+            ms2 = t2["ms"] / steps
+            by2 = d2.S * d2.P * 20
+            others[name] = {"ms_per_step": ms2, "value": d2.S * d2.P * d2.C / (ms2 * 1e-3), "kernel": s2.last_kernel,
+                            "hbm_frac": by2 / (ms2 * 1e-3) / 1e9 / peak, "gpu_launches": t2["launches"],
+                            "j_bytes": d2.S * d2.P * 8}
+            s2.close()
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -344,15 +369,17 @@ def main():
                        "partition": ("dim %d slabs over %d ranks; halo: %s" % (
                            part_dim, world,
                            "stored into peer memory by the stage kernel (NVLink P2P) + 1-element all-reduce barrier"
-                           if sw.halo_mode == "p2p" else "grouped ncclSend/ncclRecv after each stage"))
+                           if halo_mode == "p2p" else "grouped ncclSend/ncclRecv after each stage"))
                        if world > 1 else "none",
                        "l2": "J_{k+1} (%.0f MB) exceeds the 126 MB L2; no flush needed" % (S_all * 8 / 1e6)
                        if S_all * 8 > 130e6 else "inputs fit L2 (stage-to-stage reuse is the workload)",
                        "cuda_graph": bool(use_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
-            "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K}
+            "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K,
+            "other_workloads": others}
     print(json.dumps(line), flush=True)
-    sw.close()
+    if sw is not None:
+        sw.close()
     if world > 1:
         dist.destroy_process_group()
 
