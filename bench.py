@@ -130,8 +130,8 @@ def cpu_sample_rate(d, seconds_target, threads=0):
     `seconds_target` of CPU work.  Returns (updates/s, cores, sample description, seconds)."""
     from oracle import cbind
     cbind.build()
-    if threads:
-        os.environ["OMP_NUM_THREADS"] = str(threads)
+    # every host core, whatever OMP_NUM_THREADS says (torchrun exports OMP_NUM_THREADS=1)
+    cbind.set_threads(threads or len(os.sched_getaffinity(0)))
     cores = cbind.num_threads()
     rng = np.random.default_rng(0)
     S = d.S

@@ -344,6 +344,16 @@ int oracle_rollout(const bellman_desc *d, const int32_t *modes, const int32_t *i
     return 0;
 }
 
+/* torchrun exports OMP_NUM_THREADS=1; the CPU arm wants every host core */
+void oracle_set_threads(int n)
+{
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 int oracle_num_threads(void)
 {
 #ifdef _OPENMP

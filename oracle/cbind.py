@@ -152,6 +152,10 @@ def num_threads():
     return int(lib().oracle_num_threads())
 
 
+def set_threads(n):
+    lib().oracle_set_threads(C.c_int(int(n)))
+
+
 def stage_points(d, J_next_p, states, p=0, modes=None):
     """Evaluate only the listed linear state indices of problem ``p``.  Returns (J, idx0)."""
     cd, keep = to_cdesc(d)
