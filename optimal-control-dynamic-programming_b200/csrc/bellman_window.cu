@@ -100,11 +100,13 @@ __device__ __forceinline__ int cell_uniform(double g, int n) {
 __device__ __forceinline__ double cell_to_double(int cell) {
     return __hiloint2double(0x43300000, cell) - 4503599627370496.0;
 }
-template <bool CLAMP = true>
+// XUCVT: take (double)cell from the conversion pipe (I2F.F64) instead of the fp64 pipe.  The hot
+// loop uses one of each per update so that neither pipe carries both conversions.
+template <bool CLAMP = true, bool XUCVT = false>
 __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
     int cell = __double2int_rd(g);
     if (CLAMP) cell = min(max(cell, 0), n - 2);   // skipped when the whole chunk is known to be interior
-    t = g - cell_to_double(cell);
+    t = g - (XUCVT ? (double)cell : cell_to_double(cell));
     return cell;
 }
 
@@ -116,7 +118,9 @@ __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
 // the thread interpolates 9 columns once along dimension 0 and every state blends two neighbouring
 // columns.  Same operations on the same operands as the generic path (bit-identical results),
 // 18 shared-memory loads and ~61 fp64 instructions per 8 updates instead of 32 and ~120.
-template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int WR_STATES>
+// W0C: the window pitch (rows per column) as a compile-time constant when it is one of the common
+// values (0 = read it from the parameters); turns the second-column offset into an immediate.
+template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int WR_STATES, int W0C = 0>
 __global__ void __launch_bounds__(WNT, OCC)
 k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
                const __grid_constant__ CUtensorMap tmap) {
@@ -151,26 +155,28 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         mbar_init(&mbar[1], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    __syncthreads();   // mbarrier init visible to every thread
-
     // extrema of the state-indexed tables over this tile: precomputed on the host per tile index
-    // (no in-kernel reduction, no barrier that waits on global loads)
-    double tmm[8];
-    {
+    // (no in-kernel reduction).  Long control loops keep them in shared memory (registers are the
+    // scarce resource there); the small-control CHAIN kernels keep them in registers so that no
+    // warp waits on another warp's global load.
+    __shared__ double tmm_s[8];
+    double tmm_r[8];
+    auto tmm_load = [&](int k) -> double {
         const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
-        const int ta0 = d0.src_a == 0 ? ti : tj, ta1 = d1.src_a == 0 ? ti : tj;
-        tmm[0] = __ldg(tm + wp.tmm_off[0][0] + 2 * ta0); tmm[1] = __ldg(tm + wp.tmm_off[0][0] + 2 * ta0 + 1);
-        tmm[4] = __ldg(tm + wp.tmm_off[1][0] + 2 * ta1); tmm[5] = __ldg(tm + wp.tmm_off[1][0] + 2 * ta1 + 1);
-        tmm[2] = tmm[3] = tmm[6] = tmm[7] = 0.0;
-        if (d0.Tb) {
-            const int tb = d0.src_b == 0 ? ti : tj;
-            tmm[2] = __ldg(tm + wp.tmm_off[0][1] + 2 * tb); tmm[3] = __ldg(tm + wp.tmm_off[0][1] + 2 * tb + 1);
-        }
-        if (d1.Tb) {
-            const int tb = d1.src_b == 0 ? ti : tj;
-            tmm[6] = __ldg(tm + wp.tmm_off[1][1] + 2 * tb); tmm[7] = __ldg(tm + wp.tmm_off[1][1] + 2 * tb + 1);
-        }
+        const int d = k >> 2, ab = (k >> 1) & 1, mx = k & 1;
+        const DimParams &dd = d == 0 ? d0 : d1;
+        if (ab == 1 && !dd.Tb) return 0.0;
+        const int src = ab == 0 ? dd.src_a : dd.src_b;
+        return __ldg(tm + wp.tmm_off[d][ab] + 2 * (src == 0 ? ti : tj) + mx);
+    };
+    if (CHAIN) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) tmm_r[k] = tmm_load(k);
+    } else if (tid < 8) {
+        tmm_s[tid] = tmm_load(tid);
     }
+    __syncthreads();   // mbarrier init (and tmm_s) visible to every thread
+    const double *tmm = CHAIN ? tmm_r : tmm_s;
 
     // window origin of chunk ch: the cell of the smallest query, formed with the kernel's own
     // association so that the bound is exact
@@ -237,7 +243,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
         chain_ok = __all_sync(0xffffffffu, chain_ok);
     }
 
-    const int W0 = wp.win0;
+    const int W0 = W0C ? W0C : wp.win0;
     // the control loop over one staged chunk; CLAMP = false when every query of the chunk falls in
     // an interior cell (decided from the same exact bounds that place the window)
     auto chunk_loop = [&](auto clamp_tag, int ch, const double *__restrict__ Wb) {
@@ -277,7 +283,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
                     int cell0, cell1;
                     if (HC0) cell0 = locate_uniform<CLAMP>(base0[m] + bu0, n0, t0[u]);
                     else { cell0 = cellK0[m]; t0[u] = tK0[m]; }
-                    if (HC1) cell1 = locate_uniform<CLAMP>(base1[m] + bu1, n1, t1[u]);
+                    if (HC1) cell1 = locate_uniform<CLAMP, true>(base1[m] + bu1, n1, t1[u]);
                     else { cell1 = cellK1[m]; t1[u] = tK1[m]; }
                     off[u] = cell1 * W0 + cell0;      // Wb already carries the window origin
                 }
@@ -331,6 +337,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
             }
         }
         if (sp.n_peers) {
+#pragma unroll   // keeps best[] in registers (a rolled loop would index it dynamically)
             for (int m = 0; m < WR_STATES; ++m)
                 if (jbase + m < j_hi) { const int gi[2] = {i, jbase + m}; peer_store<2>(sp, prob, gi, best[m]); }
         }
@@ -375,6 +382,16 @@ void minmax_range(const double *v, int lo, int hi, double &mn, double &mx) {
 template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int R = 8>
 static bool window_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                       cudaStream_t st, bool set_attr_only) {
+    if (HC0 && HC1 && BATCH == 4 && OCC == 2 && R == 8) {   // the long-control-loop kernel: pitch 48 specialisation
+        auto fn48 = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48>;
+        if (set_attr_only) {
+            if (cudaFuncSetAttribute((const void *)fn48, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) != cudaSuccess)
+                return false;
+        } else if (ws->wp.win0 == 48) {
+            fn48<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+            return true;
+        }
+    }
     auto fn = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R>;
     if (set_attr_only)
         return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) ==
