@@ -268,3 +268,50 @@ def test_kirk_scaled_full_size_spot_check(bellman, oracle_lib):
     Jo, Io = oracle_lib.stage_points(d, JN, pts)
     assert np.array_equal(Ig[pts], Io) and np.array_equal(Jg[pts], Jo)
     sw.close()
+
+
+def test_api_error_paths(bellman):
+    """Status codes across the ABI: NOT_RUN, STATE, BAD_ARG — and that a failed call leaves the
+    handle usable."""
+    obj = bellman.Dynamic_Solver()
+    obj.dx, obj.du, obj.N = 16, 8, 6
+    d = bellman.tables.kirk_desc(obj.A, obj.B, obj.Q, obj.R, obj.N, obj.x_min, obj.x_max, obj.dx, obj.u_min,
+                                 obj.u_max, obj.du, store_J_all=False, store_idx_all=False)
+    sw = bellman.Sweep(d)
+    assert sw.current_stage == 6
+    with pytest.raises(bellman.BellmanError) as e:       # idx of the terminal stage does not exist
+        sw.get_idx(6)
+    assert e.value.code == -1
+    sw.run(2)
+    with pytest.raises(bellman.BellmanError) as e:       # stage 5 was computed but not stored
+        sw.get_J(5)
+    assert e.value.code == -5
+    with pytest.raises(bellman.BellmanError) as e:       # stage 2 not computed yet
+        sw.get_J(2)
+    assert e.value.code == -5
+    with pytest.raises(bellman.BellmanError) as e:       # would pass stage 1
+        sw.run(10)
+    assert e.value.code == -6
+    with pytest.raises(bellman.BellmanError) as e:       # rollout needs store_idx_all
+        sw.rollout(obj.A, obj.B, d.meta["U_mesh"], [[0.0, 0.0]])
+    assert e.value.code == -6
+    sw.run(3)                                            # still usable
+    assert sw.current_stage == 1 and np.isfinite(sw.get_J()).all()
+    sw.set_J(None)                                       # resume from a fresh terminal cost
+    assert sw.current_stage == 6
+    sw.close()
+
+
+def test_resume_from_saved_stage(bellman, oracle_lib):
+    """Checkpoint / resume: J of an intermediate stage fed back through set_J continues the sweep
+    bit-identically (the state of a sweep is one J array)."""
+    sp = bellman.Solver_position()
+    d = bellman.tables.stack_problems(sp._axis_descs())
+    a = bellman.Sweep(d).run(20)
+    J_mid = a.get_J()
+    a.run(15)
+    b = bellman.Sweep(d)
+    b.set_J(J_mid)                     # stage counter restarts at N; only the values matter (time-invariant tables)
+    b.run(15)
+    assert np.array_equal(a.get_J(), b.get_J()) and np.array_equal(a.get_idx(), b.get_idx())
+    a.close(); b.close()
