@@ -344,6 +344,136 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_stage_chain: the CHAIN structure (see k_stage_window) as a kernel of its own for problems with
+// at most MAXC controls (Solver_attitude: 3 torque levels).  Every control's window is in flight
+// from the first instruction (one TMA box per control, one mbarrier), there is no chunk loop, no
+// ring reuse and a single __syncthreads per tile; window origins are computed once by thread 0 and
+// broadcast through shared memory.  Same operations on the same operands as the generic path.
+// ---------------------------------------------------------------------------------------------
+template <int R, int MAXC>
+__global__ void __launch_bounds__(WNT, 4)
+k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
+              const __grid_constant__ CUtensorMap tmap) {
+    constexpr int WT1 = (WNT / 32) * R;
+    extern __shared__ __align__(128) double ring[];    // C windows, win0 x win1 doubles each
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int org[MAXC][2];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int prob = blockIdx.y;
+    const int ti = wp.tj_fastest ? blockIdx.x / wp.ntile1 : blockIdx.x % wp.ntile0;
+    const int tj = wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0;
+    const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
+    const int n0 = d0.n, n1 = d1.n, C = sp.C, W0 = wp.win0;
+    const int win_elems = wp.win0 * wp.win1;
+    const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
+    const int j_lo = d1.own_lo + tj * WT1, j_hi = min(j_lo + WT1, d1.own_lo + d1.own_n);
+    const double *Tc0 = d0.Tc + (size_t)prob * C;
+    const double *rr = sp.r + (size_t)prob * C;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        // smallest query of the tile per control, formed with the kernel's own association
+        const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
+        const double *cm = wp.cmm + (size_t)prob * wp.nchunks * 4;
+        double lo0 = __ldg(tm + wp.tmm_off[0][0] + 2 * ti);                      // Ta_0 is indexed by the row
+        if (d0.Tb) lo0 = lo0 + __ldg(tm + wp.tmm_off[0][1] + 2 * ti);            // (and so is Tb_0 in CHAIN problems)
+        double lo1 = __ldg(tm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? ti : tj));
+        if (d1.Tb) lo1 = lo1 + __ldg(tm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? ti : tj));
+        const int c0 = cell_uniform(lo1, n1);
+        mbar_expect_tx(&mbar, (uint32_t)(C * win_elems) * 8u);
+        for (int c = 0; c < C; ++c) {
+            int r0 = cell_uniform(lo0 + __ldg(cm + 4 * c), n0);     // chunk size is 1: cmm[c] = Tc_0[c]
+            r0 -= (r0 - d0.ext_lo) & 1;                              // TMA: even innermost coordinate
+            org[c][0] = r0;
+            org[c][1] = c0;
+            for (int b = 0; b < wp.boxes; ++b)
+                tma_load_3d(ring + (size_t)c * win_elems + (size_t)b * wp.box1 * W0, &tmap, &mbar, r0 - d0.ext_lo,
+                            c0 - d1.ext_lo + b * wp.box1, prob);
+        }
+    }
+
+    // this thread's R states: row i, columns jbase .. jbase+R-1 (loads overlap the TMA latency)
+    const int i = min(i_lo + lane, i_hi - 1);
+    const int jbase = j_lo + wrp * R;
+    const double2 *rpk = reinterpret_cast<const double2 *>(wp.rowpack + (size_t)prob * n0 + i);
+    const double2 rp01 = __ldg(rpk), rp23 = __ldg(rpk + 1);
+    const double2 *cpk = reinterpret_cast<const double2 *>(wp.colpack + (size_t)prob * n1);
+    const double base0 = rp01.x;                     // CHAIN: no column part in dimension 0
+    double gs[R], tK1[R], best[R];
+    int arg[R], cellK1[R];
+    bool chain_ok = true;
+#pragma unroll
+    for (int m = 0; m < R; ++m) {
+        const int j = min(jbase + m, j_hi - 1);
+        const double2 cp01 = __ldg(cpk + 2 * j), cp23 = __ldg(cpk + 2 * j + 1);
+        const double b1 = wp.col1_zero ? rp01.y : rp01.y + cp01.y;
+        gs[m] = rp23.x + cp23.x;
+        cellK1[m] = locate_uniform<true, true>(b1, n1, tK1[m]);
+        best[m] = __longlong_as_double(0x7ff0000000000000LL);
+        arg[m] = 0;
+        if (m) chain_ok = chain_ok && (cellK1[m] == cellK1[0] + m);
+    }
+    chain_ok = __all_sync(0xffffffffu, chain_ok);
+
+    __syncthreads();          // org[] and the mbarrier are visible
+    mbar_wait(&mbar, 0);
+
+    for (int c = 0; c < C; ++c) {
+        const double rc = __ldg(rr + c);
+        double t0;
+        const int cell0 = locate_uniform<true, false>(base0 + __ldg(Tc0 + c), n0, t0);
+        const double *__restrict__ Wb = ring + (size_t)c * win_elems - (org[c][1] * W0 + org[c][0]);
+        if (chain_ok) {
+            const double *p = Wb + (cellK1[0] * W0 + cell0);
+            double a[R + 1];
+#pragma unroll
+            for (int k = 0; k <= R; ++k) {
+                const double lo = p[k * W0], hi = p[k * W0 + 1];
+                a[k] = fma(t0, hi - lo, lo);
+            }
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const double v = fma(tK1[m], a[m + 1] - a[m], a[m]);
+                const double tot = (gs[m] + rc) + v;
+                if (tot < best[m]) { best[m] = tot; arg[m] = c; }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < R; ++m) {
+                const double *p = Wb + (cellK1[m] * W0 + cell0);
+                const double v00 = p[0], v10 = p[1], v01 = p[W0], v11 = p[W0 + 1];
+                const double a = fma(t0, v10 - v00, v00);
+                const double b = fma(t0, v11 - v01, v01);
+                const double v = fma(tK1[m], b - a, a);
+                const double tot = (gs[m] + rc) + v;
+                if (tot < best[m]) { best[m] = tot; arg[m] = c; }
+            }
+        }
+    }
+
+    if (i_lo + lane < i_hi) {
+        double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
+                     (long long)(jbase - d1.ext_lo) * d1.stride;
+        int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
+                      (long long)(jbase - d1.own_lo) * d0.own_n;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            if (jbase + m < j_hi) {
+                jo[(long long)m * d1.stride] = best[m];
+                io[(long long)m * d0.own_n] = arg[m];
+            }
+        }
+        if (sp.n_peers) {
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                if (jbase + m < j_hi) { const int gi[2] = {i, jbase + m}; peer_store<2>(sp, prob, gi, best[m]); }
+        }
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -365,7 +495,8 @@ struct WindowState {
     WindowParams wp{};
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
-    bool hc0 = false, hc1 = false, chain = false;
+    bool hc0 = false, hc1 = false, chain = false, lean = false;
+    size_t lean_smem = 0;
     int batch = 4, occ = 2, rstates = 8;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
@@ -492,10 +623,15 @@ void window_setup(bellman_handle *h) {
     const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
     int best_cc = 0, best_w0 = 0, best_w1 = 0;
     double best_score = -1.0;
+    const bool lean_cfg = chain_cfg && rstates == 4 && hp.C <= 4 && !std::getenv("BELLMAN_WIN_NOLEAN");
     std::vector<int> cands;
-    for (int cc : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32})
-        if (cc <= hp.C) cands.push_back(cc);
-    if (hp.C <= 32 && std::find(cands.begin(), cands.end(), hp.C) == cands.end()) cands.push_back(hp.C);
+    if (lean_cfg) {
+        cands.push_back(1);                       // k_stage_chain: one window per control, all in flight
+    } else {
+        for (int cc : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32})
+            if (cc <= hp.C) cands.push_back(cc);
+        if (hp.C <= 32 && std::find(cands.begin(), cands.end(), hp.C) == cands.end()) cands.push_back(hp.C);
+    }
     for (int cc : cands) {
         int w0, w1;
         window_extents(h, cc, wt1, w0, w1);
@@ -650,6 +786,14 @@ void window_setup(bellman_handle *h) {
         if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
     }
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { delete ws; return; }
+    ws->lean = lean_cfg && wp.cchunk == 1 && wp.nchunks <= 4;
+    if (ws->lean) {
+        ws->lean_smem = (size_t)wp.nchunks * slot_bytes(wp.win0, wp.win1);
+        if (ws->lean_smem > 56 * 1024 ||
+            cudaFuncSetAttribute((const void *)k_stage_chain<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)ws->lean_smem) != cudaSuccess)
+            ws->lean = false;
+    }
     if (!ws->hc0 && !ws->hc1) { delete ws; return; }   // no control dependence at all: nothing to stage for
     h->wstate = ws;
     h->wcfg.tile0 = WT0; h->wcfg.tile1 = wt1; h->wcfg.cchunk = wp.cchunk;
@@ -671,7 +815,8 @@ cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     const WindowParams &wp = ws->wp;
     const dim3 grid((unsigned)(wp.ntile0 * wp.ntile1), (unsigned)sp.P);
     const CUtensorMap &map = ws->maps[slot_next];
-    window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
+    if (ws->lean) k_stage_chain<4, 4><<<grid, WNT, ws->lean_smem, st>>>(sp, wp, map);
+    else window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
     return cudaGetLastError();
 }
 
