@@ -372,23 +372,28 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     const double *Tc0 = d0.Tc + (size_t)prob * C;
     const double *rr = sp.r + (size_t)prob * C;
 
-    if (tid == 0) {
-        mbar_init(&mbar, 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        // smallest query of the tile per control, formed with the kernel's own association
-        const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
-        const double *cm = wp.cmm + (size_t)prob * wp.nchunks * 4;
-        double lo0 = __ldg(tm + wp.tmm_off[0][0] + 2 * ti);                      // Ta_0 is indexed by the row
-        if (d0.Tb) lo0 = lo0 + __ldg(tm + wp.tmm_off[0][1] + 2 * ti);            // (and so is Tb_0 in CHAIN problems)
-        double lo1 = __ldg(tm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? ti : tj));
-        if (d1.Tb) lo1 = lo1 + __ldg(tm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? ti : tj));
-        const int c0 = cell_uniform(lo1, n1);
-        mbar_expect_tx(&mbar, (uint32_t)(C * win_elems) * 8u);
-        for (int c = 0; c < C; ++c) {
+    // lanes 0..C-1 of warp 0 each place and issue one control's window (their table loads overlap)
+    if (wrp == 0) {
+        if (lane == 0) {
+            mbar_init(&mbar, (uint32_t)C);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane < C) {
+            const int c = lane;
+            // smallest query of the tile for this control, formed with the kernel's own association
+            const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
+            const double *cm = wp.cmm + (size_t)prob * wp.nchunks * 4;
+            double lo0 = __ldg(tm + wp.tmm_off[0][0] + 2 * ti);                  // Ta_0 is indexed by the row
+            if (d0.Tb) lo0 = lo0 + __ldg(tm + wp.tmm_off[0][1] + 2 * ti);        // (and so is Tb_0 in CHAIN problems)
+            double lo1 = __ldg(tm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? ti : tj));
+            if (d1.Tb) lo1 = lo1 + __ldg(tm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? ti : tj));
+            const int c0 = cell_uniform(lo1, n1);
             int r0 = cell_uniform(lo0 + __ldg(cm + 4 * c), n0);     // chunk size is 1: cmm[c] = Tc_0[c]
             r0 -= (r0 - d0.ext_lo) & 1;                              // TMA: even innermost coordinate
             org[c][0] = r0;
             org[c][1] = c0;
+            mbar_expect_tx(&mbar, (uint32_t)win_elems * 8u);
             for (int b = 0; b < wp.boxes; ++b)
                 tma_load_3d(ring + (size_t)c * win_elems + (size_t)b * wp.box1 * W0, &tmap, &mbar, r0 - d0.ext_lo,
                             c0 - d1.ext_lo + b * wp.box1, prob);
@@ -405,10 +410,12 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     double gs[R], tK1[R], best[R];
     int arg[R], cellK1[R];
     bool chain_ok = true;
+    const bool full = jbase + R <= j_hi;             // warp-uniform: all R columns exist
+    const double2 *cpb = cpk + 2 * (size_t)min(jbase, j_hi - 1);
 #pragma unroll
     for (int m = 0; m < R; ++m) {
-        const int j = min(jbase + m, j_hi - 1);
-        const double2 cp01 = __ldg(cpk + 2 * j), cp23 = __ldg(cpk + 2 * j + 1);
+        const int jo_ = full ? m : min(jbase + m, j_hi - 1) - min(jbase, j_hi - 1);
+        const double2 cp01 = __ldg(cpb + 2 * jo_), cp23 = __ldg(cpb + 2 * jo_ + 1);
         const double b1 = wp.col1_zero ? rp01.y : rp01.y + cp01.y;
         gs[m] = rp23.x + cp23.x;
         cellK1[m] = locate_uniform<true, true>(b1, n1, tK1[m]);
@@ -459,12 +466,16 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
                      (long long)(jbase - d1.ext_lo) * d1.stride;
         int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
                       (long long)(jbase - d1.own_lo) * d0.own_n;
+        const long long sj = d1.stride;
+        const int si = d0.own_n;
 #pragma unroll
         for (int m = 0; m < R; ++m) {
-            if (jbase + m < j_hi) {
-                jo[(long long)m * d1.stride] = best[m];
-                io[(long long)m * d0.own_n] = arg[m];
+            if (full || jbase + m < j_hi) {
+                *jo = best[m];
+                *io = arg[m];
             }
+            jo += sj;
+            io += si;
         }
         if (sp.n_peers) {
 #pragma unroll
