@@ -395,7 +395,7 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
             org[c][1] = c0;
             mbar_expect_tx(&mbar, (uint32_t)win_elems * 8u);
             for (int b = 0; b < wp.boxes; ++b)
-                tma_load_3d(ring + (size_t)c * win_elems + (size_t)b * wp.box1 * W0, &tmap, &mbar, r0 - d0.ext_lo,
+                tma_load_3d(ring + (size_t)c * wp.buf_doubles + (size_t)b * wp.box1 * W0, &tmap, &mbar, r0 - d0.ext_lo,
                             c0 - d1.ext_lo + b * wp.box1, prob);
         }
     }
@@ -432,7 +432,7 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
         const double rc = __ldg(rr + c);
         double t0;
         const int cell0 = locate_uniform<true, false>(base0 + __ldg(Tc0 + c), n0, t0);
-        const double *__restrict__ Wb = ring + (size_t)c * win_elems - (org[c][1] * W0 + org[c][0]);
+        const double *__restrict__ Wb = ring + (size_t)c * wp.buf_doubles - (org[c][1] * W0 + org[c][0]);
         if (chain_ok) {
             const double *p = Wb + (cellK1[0] * W0 + cell0);
             double a[R + 1];
@@ -610,8 +610,8 @@ static void window_extents(const bellman_handle *h, int cchunk, int wt1, int &w0
     }
 }
 
-// bytes of one ring slot (w0 is a multiple of 16, so this is a multiple of 128)
-static size_t slot_bytes(int w0, int w1) { return (size_t)w0 * w1 * 8; }
+// bytes of one ring slot, rounded up to the 128-byte alignment TMA needs for its destination
+static size_t slot_bytes(int w0, int w1) { return ((size_t)w0 * w1 * 8 + 127) / 128 * 128; }
 
 void window_setup(bellman_handle *h) {
     h->wcfg.valid = false;
@@ -646,7 +646,10 @@ void window_setup(bellman_handle *h) {
     for (int cc : cands) {
         int w0, w1;
         window_extents(h, cc, wt1, w0, w1);
-        w0 = (w0 + 1 + 15) / 16 * 16;             // +1: the window origin is rounded down to an even row
+        // +1: the window origin is rounded down to an even row.  Pitch: a multiple of 16 doubles keeps
+        // the generic gathers conflict-free when a warp straddles columns; the CHAIN kernel reads
+        // whole columns per warp, so any even pitch is conflict-free and the window can be tight
+        w0 = lean_cfg ? (w0 + 1 + 1) / 2 * 2 : (w0 + 1 + 15) / 16 * 16;
         if (w0 > 256) continue;
         const int boxes = (w1 + 255) / 256;
         const int box1 = (w1 + boxes - 1) / boxes;
@@ -797,7 +800,7 @@ void window_setup(bellman_handle *h) {
         if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
     }
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { delete ws; return; }
-    ws->lean = lean_cfg && wp.cchunk == 1 && wp.nchunks <= 4;
+    ws->lean = lean_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1;
     if (ws->lean) {
         ws->lean_smem = (size_t)wp.nchunks * slot_bytes(wp.win0, wp.win1);
         if (ws->lean_smem > 56 * 1024 ||
