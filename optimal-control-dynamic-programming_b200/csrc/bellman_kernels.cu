@@ -66,12 +66,22 @@ template <int D>
 struct FixedDims {
     double t[D];
     long long off;      // element offset contributed by the control-independent dimensions
+    int ro[1 << (D - 1)];   // element offsets of the 2^(D-1) dimension-0 pairs relative to the base corner
+                            // (exact when the J slab has fewer than 2^31 elements: SMALL kernels)
 };
 
 template <int D>
 __device__ __forceinline__ void locate_fixed(const Prob<D> &pb, const StageParams &sp, const double (&base)[D],
                                              FixedDims<D> &fx) {
     fx.off = 0;
+#pragma unroll
+    for (int k = 0; k < (1 << (D - 1)); ++k) {
+        int r = 0;
+#pragma unroll
+        for (int d = 1; d < D; ++d)
+            if (k & (1 << (d - 1))) r += (int)sp.dim[d].stride;
+        fx.ro[k] = r;
+    }
 #pragma unroll
     for (int d = 0; d < D; ++d) {
         fx.t[d] = 0.0;
@@ -86,7 +96,7 @@ __device__ __forceinline__ void locate_fixed(const Prob<D> &pb, const StageParam
 // one (state, control) evaluation: returns the interpolated J_{k+1}(x')
 // COHERENT: read J_{k+1} with ld.global.cg (L2 only).  Needed when J_{k+1} was written earlier in
 // the SAME kernel by other SMs (persistent multi-stage kernel); L1 is not coherent across SMs.
-template <int D, bool COHERENT = false>
+template <int D, bool COHERENT = false, bool SMALL = true>
 __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams &sp,
                                             const double *__restrict__ Jn, const double (&base)[D],
                                             const FixedDims<D> &fx, int c) {
@@ -105,13 +115,23 @@ __device__ __forceinline__ double interp_at(const Prob<D> &pb, const StageParams
     }
     const double *__restrict__ p = Jn + o;
     double v[1 << D];
+    if (SMALL) {
+        // 32-bit corner offsets precomputed per thread: one address computation per dimension-0 pair
 #pragma unroll
-    for (int m = 0; m < (1 << D); ++m) {
-        long long oo = 0;
+        for (int k = 0; k < (1 << (D - 1)); ++k) {
+            const double *q = p + fx.ro[k];
+            v[2 * k] = COHERENT ? __ldcg(q) : __ldg(q);
+            v[2 * k + 1] = COHERENT ? __ldcg(q + 1) : __ldg(q + 1);
+        }
+    } else {
 #pragma unroll
-        for (int d = 0; d < D; ++d)
-            if (m & (1 << d)) oo += sp.dim[d].stride;
-        v[m] = COHERENT ? __ldcg(p + oo) : __ldg(p + oo);
+        for (int m = 0; m < (1 << D); ++m) {
+            long long oo = 0;
+#pragma unroll
+            for (int d = 0; d < D; ++d)
+                if (m & (1 << d)) oo += sp.dim[d].stride;
+            v[m] = COHERENT ? __ldcg(p + oo) : __ldg(p + oo);
+        }
     }
 #pragma unroll
     for (int d = 0; d < D; ++d)               // dimension 0 reduced first
@@ -137,26 +157,43 @@ __device__ __forceinline__ long long decompose(const StageParams &sp, long long 
     return o;
 }
 
+// gi[k] for a run-time k without indexing the register array dynamically (that would put it in
+// local memory)
+template <int D>
+__device__ __forceinline__ int pick(const int (&gi)[D], int k) {
+    int v = gi[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) v = (k == d) ? gi[d] : v;
+    return v;
+}
+template <int D>
+__device__ __forceinline__ const double *pickp(const double *const (&q)[D], int k) {
+    const double *v = q[0];
+#pragma unroll
+    for (int d = 1; d < D; ++d) v = (k == d) ? q[d] : v;
+    return v;
+}
+
 template <int D>
 __device__ __forceinline__ double state_terms(const Prob<D> &pb, const StageParams &sp,
                                               const int (&gi)[D], double (&base)[D]) {
 #pragma unroll
     for (int d = 0; d < D; ++d) {
-        double b = __ldg(pb.Ta[d] + gi[sp.dim[d].src_a]);
-        if (pb.Tb[d]) b = b + __ldg(pb.Tb[d] + gi[sp.dim[d].src_b]);
+        double b = __ldg(pb.Ta[d] + pick<D>(gi, sp.dim[d].src_a));
+        if (pb.Tb[d]) b = b + __ldg(pb.Tb[d] + pick<D>(gi, sp.dim[d].src_b));
         base[d] = b;
     }
-    double gs = __ldg(pb.q[sp.q_order[0]] + gi[sp.q_order[0]]);
+    double gs = __ldg(pickp<D>(pb.q, sp.q_order[0]) + pick<D>(gi, sp.q_order[0]));
 #pragma unroll
-    for (int m = 1; m < D; ++m) gs = gs + __ldg(pb.q[sp.q_order[m]] + gi[sp.q_order[m]]);
+    for (int m = 1; m < D; ++m) gs = gs + __ldg(pickp<D>(pb.q, sp.q_order[m]) + pick<D>(gi, sp.q_order[m]));
     return gs;
 }
 
 // ---------------------------------------------------------------------------------------------
 // K_direct: one thread per state
 // ---------------------------------------------------------------------------------------------
-template <int D>
-__global__ void __launch_bounds__(BLOCK)
+template <int D, bool SMALL>
+__global__ void __launch_bounds__(BLOCK, 3)
 k_stage_direct(const __grid_constant__ StageParams sp) {
     const int prob = blockIdx.y;
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
@@ -175,7 +212,7 @@ k_stage_direct(const __grid_constant__ StageParams sp) {
     int arg = 0;
 #pragma unroll 2
     for (int c = 0; c < sp.C; ++c) {
-        const double v = interp_at<D>(pb, sp, Jn, base, fx, c);
+        const double v = interp_at<D, false, SMALL>(pb, sp, Jn, base, fx, c);
         const double tot = (gs + __ldg(pb.r + c)) + v;
         if (tot < best) { best = tot; arg = c; }
     }
@@ -393,10 +430,14 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
 // ---------------------------------------------------------------------------------------------
 cudaError_t launch_stage_direct(const StageParams &sp, cudaStream_t st) {
     const dim3 grid((unsigned)((sp.S_own + BLOCK - 1) / BLOCK), (unsigned)sp.P);
-    switch (sp.D) {
-        case 2: k_stage_direct<2><<<grid, BLOCK, 0, st>>>(sp); break;
-        case 3: k_stage_direct<3><<<grid, BLOCK, 0, st>>>(sp); break;
-        case 4: k_stage_direct<4><<<grid, BLOCK, 0, st>>>(sp); break;
+    const bool small = sp.S_ext < (1LL << 31);     // 32-bit corner offsets are exact
+    switch (sp.D * 2 + (small ? 1 : 0)) {
+        case 4: k_stage_direct<2, false><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 5: k_stage_direct<2, true><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 6: k_stage_direct<3, false><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 7: k_stage_direct<3, true><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 8: k_stage_direct<4, false><<<grid, BLOCK, 0, st>>>(sp); break;
+        case 9: k_stage_direct<4, true><<<grid, BLOCK, 0, st>>>(sp); break;
         default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -418,6 +459,7 @@ static cudaError_t splitc_D(const StageParams &sp, int L, cudaStream_t st) {
 }
 
 cudaError_t launch_stage_splitc(const StageParams &sp, int lanes_per_state, cudaStream_t st) {
+    if (sp.S_ext >= (1LL << 31)) return launch_stage_direct(sp, st);   // 32-bit corner offsets only
     switch (sp.D) {
         case 2: return splitc_D<2>(sp, lanes_per_state, st);
         case 3: return splitc_D<3>(sp, lanes_per_state, st);
