@@ -193,7 +193,7 @@ __device__ __forceinline__ double state_terms(const Prob<D> &pb, const StagePara
 // K_direct: one thread per state
 // ---------------------------------------------------------------------------------------------
 template <int D, bool SMALL>
-__global__ void __launch_bounds__(BLOCK, 3)
+__global__ void __launch_bounds__(BLOCK, 4)
 k_stage_direct(const __grid_constant__ StageParams sp) {
     const int prob = blockIdx.y;
     const long long s = (long long)blockIdx.x * BLOCK + threadIdx.x;
