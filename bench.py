@@ -41,8 +41,8 @@ WORKLOADS = {
 }
 DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch, from the committed
-# `ncu --set full` capture of the same command (profiles/r01_window_kirk_scaled_ncu_raw.csv)
-NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": 548.5e6 + 767.9e6}
+# `ncu --set full` capture of the same command (profiles/r01_window_kirk_ncu_raw.csv)
+NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": 548.0e6 + 772.5e6}
 
 
 def make_desc(bb, name):
@@ -146,6 +146,27 @@ def cpu_sample_rate(d, seconds_target, threads=0):
     pts = rng.integers(0, S, size=n)
     t0 = time.perf_counter(); cbind.stage_points(d, Jn, pts); dt = time.perf_counter() - t0
     return n * d.C / dt, cores, "%d random states x %d controls of one stage (%.1f s)" % (n, d.C, dt), dt
+
+
+def cpu_reference_shaped_rate(bb, name):
+    """The array-at-a-time numpy restatement (oracle/matlab_literal.py: S x C temporaries, one
+    interpolation, one add, one min per stage — the shape of the reference's own MATLAB code) on a
+    down-scaled grid of the same problem; single process, numpy's own threading."""
+    from oracle import matlab_literal as ml
+    w = WORKLOADS[name]
+    if w["kind"] != "kirk":
+        return None
+    dx, du = min(w["dx"], 256), min(w["du"], 256)
+    L = ml.DynamicSolverLiteral(N=4, dx=dx, du=du)
+    L.setup()
+    t0 = time.perf_counter()
+    n = 2
+    for _ in range(n):
+        JF = L.F(L.X_next_M1, L.X_next_M2)
+        L.F.Values, _idx = ml.ml_min_last(JF + L.J_current_state)
+    dt = time.perf_counter() - t0
+    return {"value": n * dx * dx * du / dt, "unit": UNIT, "kind": "port (numpy, reference-shaped)",
+            "sample": "%dx%d states x %d controls, %d stages (%.1f s)" % (dx, dx, du, n, dt)}
 
 
 def run_reference_arm(args):
@@ -359,7 +380,8 @@ def main():
     cpu = None
     if not args.no_cpu_baseline and world == 1:
         r, cores, sample, _ = cpu_sample_rate(d, 12.0)
-        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+               "reference_shaped": cpu_reference_shaped_rate(bb, args.workload)}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,

@@ -87,3 +87,29 @@ def test_mex_gateway_compiles():
     for f in ("Dynamic_Solver.m", "Solver_position.m", "Solver_attitude.m", "Solver_pos_att.m"):
         src = open(os.path.join(mdir, f)).read()
         assert src.startswith("classdef " + f[:-2] + " < handle") and "bellman_mex('create'" in src
+
+
+def test_degenerate_inputs_rejected_before_any_cuda_call(bellman):
+    """Empty / degenerate inputs: every grid needs >= 2 points, C >= 1, N >= 2.  Validation runs
+    before the library touches CUDA, so the code is BAD_ARG (-1) with or without a GPU."""
+    t = bellman.tables
+    o = bellman.Dynamic_Solver()
+
+    def base():
+        return t.kirk_desc(o.A, o.B, o.Q, o.R, 4, -1.0, 1.0, 8, -1.0, 1.0, 5)
+
+    d1 = base()
+    d1.n = [1, 8]
+    for tab in (d1.grid, d1.Ta, d1.q):
+        tab[0] = tab[0][:, :1]
+    d1.Ta[1] = d1.Ta[1][:, :1]
+    d2 = base()
+    d2.C = 0
+    d3 = base()
+    d3.N = 1
+    d4 = base()
+    d4.q_order = [0, 0]
+    for d in (d1, d2, d3, d4):
+        with pytest.raises(bellman.BellmanError) as e:
+            bellman.Sweep(d)
+        assert e.value.code == -1, str(e.value)

@@ -315,3 +315,49 @@ def test_resume_from_saved_stage(bellman, oracle_lib):
     b.run(15)
     assert np.array_equal(a.get_J(), b.get_J()) and np.array_equal(a.get_idx(), b.get_idx())
     a.close(); b.close()
+
+
+def test_window_kernel_multi_stage_medium(bellman, oracle_lib):
+    """TMA-staged kernel over several stages on a grid with many tiles (1024 x 768 x 64): complete
+    comparison of J and argmin with the oracle."""
+    obj = bellman.Dynamic_Solver()
+    t = bellman.tables
+    n0, n1, C = 1024, 768, 64
+    s0, s1, u = t.linspace(-2.5, 3.0, n0), t.linspace(-2.5, 3.0, n1), t.linspace(-40.0, 10.0, C)
+    A, B = obj.A, obj.B.ravel()
+    row = lambda x: np.ascontiguousarray(x).reshape(1, -1)
+    d = t.Desc(n=[n0, n1], C=C, N=5, grid=[row(s0), row(s1)], src_a=[0, 0], src_b=[1, 1],
+               Ta=[row(A[0, 0] * s0), row(A[1, 0] * s0)], Tb=[row(A[0, 1] * s1), row(A[1, 1] * s1)],
+               Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
+               q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u)).validate()
+    sw = bellman.Sweep(d).run(3)
+    assert sw.last_kernel == "window"
+    ora = oracle_lib.sweep(d, n_stages=3)
+    assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "window 1024x768x64")
+    sw.close()
+
+
+def test_attitude_x4_full_size_spot_check(bellman, oracle_lib):
+    """config 3 (reference grid refined 4x per dimension: 3 axes x 4000 x 1200 x 3 controls): two
+    stages at full size with the lean CHAIN kernel, 60k sampled states per axis against the oracle's
+    pointwise evaluator (the second stage is seeded with the GPU's own first-stage J)."""
+    sa = bellman.Solver_attitude()
+    sa.n_mesh_w, sa.n_mesh_t = 4000, 1200
+    d = bellman.tables.stack_problems(sa._axis_descs())
+    rng = np.random.default_rng(7)
+    JN = rng.normal(size=(3, d.S)) * 0.1
+    sw = bellman.Sweep(d)
+    sw.set_J(JN)
+    sw.run(1)
+    assert sw.last_kernel == "window"
+    J1, I1 = sw.get_J(), sw.get_idx()
+    sw.run(1)
+    J2, I2 = sw.get_J(), sw.get_idx()
+    for p in range(3):
+        pts = rng.integers(0, d.S, size=60_000)
+        pts[:4] = [0, 3999, d.S - 4000, d.S - 1]
+        Jo, Io = oracle_lib.stage_points(d, JN[p], pts, p=p)
+        assert np.array_equal(I1[p][pts], Io) and np.array_equal(J1[p][pts], Jo)
+        Jo, Io = oracle_lib.stage_points(d, J1[p], pts, p=p)
+        assert np.array_equal(I2[p][pts], Io) and np.array_equal(J2[p][pts], Jo)
+    sw.close()
