@@ -171,6 +171,12 @@ int  bellman_halo_mode(const bellman_handle *h);
 
 /* sweep */
 int  bellman_set_J(bellman_handle *h, const double *J_host /*[P][S] global, NULL = zeros*/);
+/* Resume / load a saved controller: make `stage` (1..N) the current stage with value function
+ * J_host ([P][S] global, NULL = zeros) and, optionally, its policy idx_host ([P][S_own], 0-based;
+ * must be NULL for the terminal stage N).  This is the inverse of bellman_get_J / bellman_get_idx:
+ * what Solver_pos_att.m:291 saves (F_gI.Values, U_Optimal_id) can be put back, the sweep continued
+ * with bellman_run, or the policy queried with bellman_policy_lookup (Solver_pos_att.m:849-882). */
+int  bellman_set_stage(bellman_handle *h, int32_t stage, const double *J_host, const int32_t *idx_host);
 int  bellman_stage(bellman_handle *h);                      /* one backward stage, default opts */
 int  bellman_run(bellman_handle *h, int32_t n_stages, const bellman_run_opts *opts);
 int  bellman_current_stage(const bellman_handle *h);        /* stage number of the current J    */
@@ -195,6 +201,31 @@ const char *bellman_last_kernel(const bellman_handle *h);
 int  bellman_rollout(bellman_handle *h, const double *A, const double *B, const double *u_values,
                      const double *x0, int32_t batch, int32_t mode, int32_t ssu_stage,
                      double *X_out, double *U_out);
+
+/* ---- consumers of the sweep's output ("next" rows: policy lookup and simplified-plant rollout) ---- */
+
+/* Batched 'nearest' policy lookup — griddedInterpolant({s1,..}, U_vector(idx), 'nearest') of
+ * Solver_position.m:144-146, Solver_attitude.m:249-251, Solver_pos_att.m:851-861 evaluated at
+ * `batch` query states of problem `prob`: x is [D][batch] column-major (batch slowest),
+ * idx_out[batch] receives the 0-based control index stored at the nearest grid node of `stage`
+ * (clamped outside the grid; an exact midpoint goes to the upper node — MATLAB's tie side is
+ * undocumented).  Single rank only. */
+int  bellman_policy_lookup(bellman_handle *h, int32_t prob, int32_t stage, const double *x,
+                           int32_t batch, int32_t *idx_out);
+
+/* Batched rollout of the SIMPLIFIED plant of the two-state axis problems under the nearest policy
+ * (attitude-control/test/test_simplified.m:129-151 and its next_stage_states :273-310; the same
+ * plant Solver_position discretises, position-control/Solver_position.m:152-186):
+ *     c      = nearest-policy index at (x_0, x_1)               stage k if time_varying, else `stage`
+ *     x_r'   = x_r + u_inc[c]                                    r = rate_dim (the state the control drives)
+ *     x_o'   = x_o + h*(k1 + 2*k2 + 2*k3 + k4)/6,  k1 = x_r, k2 = x_r + k1*h/2, k3 = x_r + k2*h/2, k4 = x_r + k3*h
+ * with MATLAB's operation order.  D = 2; x0 is [2][batch], X_out [2][n_steps+1][batch] (batch
+ * slowest), C_out [n_steps][batch] the applied control indices.  Needs store_idx_all when
+ * time_varying.  Single rank only. */
+int  bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t time_varying, int32_t stage,
+                          int32_t rate_dim, double h_step, const double *u_inc /*[C]*/,
+                          const double *x0, int32_t batch, int32_t n_steps, double *X_out,
+                          int32_t *C_out);
 
 #ifdef __cplusplus
 }

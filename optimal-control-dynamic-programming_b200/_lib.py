@@ -51,9 +51,9 @@ class CSlab(C.Structure):
 EXPORTS = [
     "bellman_version", "bellman_last_error", "bellman_query_locate", "bellman_plan_slabs",
     "bellman_create", "bellman_destroy", "bellman_get_unique_id", "bellman_comm_init", "bellman_halo_mode",
-    "bellman_set_J", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
+    "bellman_set_J", "bellman_set_stage", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
-    "bellman_last_kernel", "bellman_rollout",
+    "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
 ]
 
 _lib = None
@@ -78,6 +78,7 @@ def load():
     lib.bellman_run.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CRunOpts)]
     lib.bellman_stage.argtypes = [C.c_void_p]
     lib.bellman_set_J.argtypes = [C.c_void_p, _dp]
+    lib.bellman_set_stage.argtypes = [C.c_void_p, C.c_int32, _dp, _ip]
     lib.bellman_get_J.argtypes = [C.c_void_p, C.c_int32, _dp]
     lib.bellman_get_idx.argtypes = [C.c_void_p, C.c_int32, _ip]
     lib.bellman_current_stage.argtypes = [C.c_void_p]
@@ -90,6 +91,9 @@ def load():
     lib.bellman_query_locate.argtypes = [C.POINTER(CDesc), _ip]
     lib.bellman_plan_slabs.argtypes = [C.POINTER(CDesc), C.c_int32, C.c_int32, C.POINTER(CSlab)]
     lib.bellman_rollout.argtypes = [C.c_void_p, _dp, _dp, _dp, _dp, C.c_int32, C.c_int32, C.c_int32, _dp, _dp]
+    lib.bellman_policy_lookup.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _ip]
+    lib.bellman_rollout_axis.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp,
+                                         _dp, C.c_int32, C.c_int32, _dp, _ip]
     _lib = lib
     return lib
 
@@ -183,6 +187,12 @@ class Sweep:
         if rc != 0:
             raise BellmanError(rc, self.lib.bellman_last_error(self.h).decode())
 
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.bellman_destroy(self.h)
@@ -209,6 +219,15 @@ class Sweep:
         else:
             J = _f64(J).reshape(self.desc.P, self.desc.S)
             self._check(self.lib.bellman_set_J(self.h, J.ctypes.data_as(_dp)))
+
+    def set_stage(self, stage, J=None, idx=None):
+        """Resume from / load a saved controller: J [P, S] (global) and 0-based idx [P, S_own] of ``stage``."""
+        Jp = _dp() if J is None else _f64(J).reshape(self.desc.P, self.desc.S)
+        ip = _ip()
+        if idx is not None:
+            idx = np.ascontiguousarray(idx, dtype=np.int32).reshape(self.desc.P, -1)
+            ip = idx.ctypes.data_as(_ip)
+        self._check(self.lib.bellman_set_stage(self.h, int(stage), Jp if J is None else Jp.ctypes.data_as(_dp), ip))
 
     def run(self, n_stages=None, kernel=KERNEL_AUTO, check_period=0, check_tol=0.0, use_graph=False,
             sync_each_stage=False):
@@ -272,3 +291,26 @@ class Sweep:
                                              int(mode), int(ssu_stage), X.ctypes.data_as(_dp),
                                              U.ctypes.data_as(_dp)))
         return X, U
+
+    def policy_lookup(self, x, prob=0, stage=None):
+        """'nearest' policy lookup at states x [batch, D] of problem ``prob``: 0-based control index."""
+        stage = self.current_stage if stage is None else stage
+        x = _f64(x).reshape(-1, self.desc.D)
+        out = np.empty(len(x), dtype=np.int32)
+        self._check(self.lib.bellman_policy_lookup(self.h, int(prob), int(stage), x.ctypes.data_as(_dp), len(x),
+                                                   out.ctypes.data_as(_ip)))
+        return out
+
+    def rollout_axis(self, u_inc, x0, n_steps, h_step, rate_dim, prob=0, time_varying=False, stage=None):
+        """Simplified-plant rollout under the nearest policy (two-state axis problems).
+        x0 [batch, 2] -> X [batch, n_steps+1, 2], control indices [batch, n_steps]."""
+        stage = self.current_stage if stage is None else stage
+        x0 = _f64(x0).reshape(-1, 2)
+        batch = len(x0)
+        X = np.empty((batch, n_steps + 1, 2))
+        Cc = np.empty((batch, n_steps), dtype=np.int32)
+        ui = _f64(u_inc)
+        self._check(self.lib.bellman_rollout_axis(self.h, int(prob), int(bool(time_varying)), int(stage), int(rate_dim),
+                                                  float(h_step), ui.ctypes.data_as(_dp), x0.ctypes.data_as(_dp), batch,
+                                                  int(n_steps), X.ctypes.data_as(_dp), Cc.ctypes.data_as(_ip)))
+        return X, Cc

@@ -282,12 +282,9 @@ static void slab_geometry(const bellman_handle *h, long long &inner, long long &
     for (int k = p + 1; k < h->hp.D; ++k) outer *= h->hp.n[k];
 }
 
-extern "C" int bellman_set_J(bellman_handle *h, const double *J_host) {
-    if (!h) return BELLMAN_ERR_BAD_ARG;
+static int upload_J(bellman_handle *h, int stage, const double *J_host) {
     const HostProblem &hp = h->hp;
-    h->cur_stage = hp.N;
-    h->check_log.clear();
-    double *dst = h->J_ptr(hp.N);
+    double *dst = h->J_ptr(stage);
     if (!J_host) {
         CUDA_TRY(h, cudaMemsetAsync(dst, 0, h->slot_elems_J() * sizeof(double), h->stream));
     } else {
@@ -302,6 +299,34 @@ extern "C" int bellman_set_J(bellman_handle *h, const double *J_host) {
                                           (size_t)outer, cudaMemcpyHostToDevice, h->stream));
         }
     }
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_set_J(bellman_handle *h, const double *J_host) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    h->cur_stage = h->hp.N;
+    h->check_log.clear();
+    int rc = upload_J(h, h->hp.N, J_host);
+    if (rc != BELLMAN_OK) return rc;
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->J_set = true;
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_set_stage(bellman_handle *h, int32_t stage, const double *J_host, const int32_t *idx_host) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    const HostProblem &hp = h->hp;
+    if (stage < 1 || stage > hp.N || (stage == hp.N && idx_host)) {
+        h->err = "bellman_set_stage: stage must be in 1..N (and the terminal stage N has no policy)";
+        return BELLMAN_ERR_BAD_ARG;
+    }
+    h->cur_stage = stage;
+    h->check_log.clear();
+    int rc = upload_J(h, stage, J_host);
+    if (rc != BELLMAN_OK) return rc;
+    if (idx_host)
+        CUDA_TRY(h, cudaMemcpyAsync(h->idx_ptr(stage), idx_host, h->slot_elems_idx() * sizeof(int32_t),
+                                    cudaMemcpyHostToDevice, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->J_set = true;
     return BELLMAN_OK;
@@ -744,6 +769,100 @@ extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double 
     RT(cudaMemcpyAsync(U_out, d_U, sizeof(double) * (size_t)N * batch, cudaMemcpyDeviceToHost, h->stream));
     RT(cudaStreamSynchronize(h->stream));
 #undef RT
+    cleanup();
+    return BELLMAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// consumers of the sweep's output: nearest-policy lookup, simplified-plant axis rollout
+// ---------------------------------------------------------------------------------------------
+static int fill_policy_params(bellman_handle *h, int prob, PolicyParams &pp) {
+    const HostProblem &hp = h->hp;
+    if (prob < 0 || prob >= hp.P) { h->err = "problem index out of range"; return BELLMAN_ERR_BAD_ARG; }
+    if (h->nranks != 1) { h->err = "policy lookup / rollout run on a single rank"; return BELLMAN_ERR_BAD_ARG; }
+    std::memset(&pp, 0, sizeof(pp));
+    pp.D = hp.D;
+    for (int d = 0; d < hp.D; ++d) {
+        const DimParams &dp = h->sp.dim[d];
+        pp.grid[d] = dp.grid + (size_t)prob * dp.n;
+        pp.rinv[d] = dp.rinv + (size_t)prob * dp.n;
+        pp.lut[d] = dp.lut + (size_t)prob * (dp.lut_n + 1);
+        pp.inv_h[d] = hp.inv_h[d][prob];
+        pp.off[d] = hp.off[d][prob];
+        pp.lut_invw[d] = hp.lut_invw[d][prob];
+        pp.mode[d] = hp.mode[(size_t)prob * hp.D + d];
+        pp.n[d] = hp.n[d];
+        pp.lut_n[d] = hp.lut_n[d];
+    }
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_policy_lookup(bellman_handle *h, int32_t prob, int32_t stage, const double *x,
+                                     int32_t batch, int32_t *idx_out) {
+    if (!h || !x || !idx_out || batch < 1) return BELLMAN_ERR_BAD_ARG;
+    PolicyParams pp;
+    int rc = fill_policy_params(h, prob, pp);
+    if (rc != BELLMAN_OK) return rc;
+    rc = stage_available(h, stage, h->store_idx_all, true);
+    if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const HostProblem &hp = h->hp;
+    double *d_x = nullptr;
+    int32_t *d_o = nullptr;
+    auto cleanup = [&]() { cudaFree(d_x); cudaFree(d_o); };
+#define PT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
+    PT(cudaMalloc(&d_x, sizeof(double) * (size_t)hp.D * batch));
+    PT(cudaMalloc(&d_o, sizeof(int32_t) * (size_t)batch));
+    PT(cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)hp.D * batch, cudaMemcpyHostToDevice, h->stream));
+    pp.batch = batch;
+    pp.idx = h->idx_ptr(stage) + (size_t)prob * h->S_own;
+    pp.x = d_x;
+    pp.idx_out = d_o;
+    PT(launch_policy_lookup(pp, h->stream));
+    PT(cudaMemcpyAsync(idx_out, d_o, sizeof(int32_t) * (size_t)batch, cudaMemcpyDeviceToHost, h->stream));
+    PT(cudaStreamSynchronize(h->stream));
+    cleanup();
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t time_varying, int32_t stage,
+                                    int32_t rate_dim, double h_step, const double *u_inc, const double *x0,
+                                    int32_t batch, int32_t n_steps, double *X_out, int32_t *C_out) {
+    if (!h || !u_inc || !x0 || !X_out || !C_out || batch < 1 || n_steps < 1) return BELLMAN_ERR_BAD_ARG;
+    const HostProblem &hp = h->hp;
+    if (hp.D != 2 || rate_dim < 0 || rate_dim > 1) { h->err = "axis rollout needs D = 2 and rate_dim in {0,1}"; return BELLMAN_ERR_BAD_ARG; }
+    PolicyParams pp;
+    int rc = fill_policy_params(h, prob, pp);
+    if (rc != BELLMAN_OK) return rc;
+    if (time_varying) {
+        if (!h->store_idx_all) { h->err = "time-varying rollout needs store_idx_all"; return BELLMAN_ERR_STATE; }
+        if (h->cur_stage != 1) { h->err = "time-varying rollout needs a completed sweep"; return BELLMAN_ERR_NOT_RUN; }
+        if (n_steps > hp.N - 1) { h->err = "n_steps exceeds the horizon"; return BELLMAN_ERR_BAD_ARG; }
+    } else {
+        rc = stage_available(h, stage, h->store_idx_all, true);
+        if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    double *d_x = nullptr, *d_X = nullptr, *d_u = nullptr;
+    int32_t *d_c = nullptr;
+    auto cleanup = [&]() { cudaFree(d_x); cudaFree(d_X); cudaFree(d_u); cudaFree(d_c); };
+    PT(cudaMalloc(&d_x, sizeof(double) * 2 * (size_t)batch));
+    PT(cudaMalloc(&d_X, sizeof(double) * 2 * (size_t)(n_steps + 1) * batch));
+    PT(cudaMalloc(&d_u, sizeof(double) * (size_t)hp.C));
+    PT(cudaMalloc(&d_c, sizeof(int32_t) * (size_t)n_steps * batch));
+    PT(cudaMemcpyAsync(d_x, x0, sizeof(double) * 2 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
+    PT(cudaMemcpyAsync(d_u, u_inc, sizeof(double) * (size_t)hp.C, cudaMemcpyHostToDevice, h->stream));
+    pp.batch = batch;
+    pp.time_varying = time_varying; pp.stage = stage; pp.rate_dim = rate_dim; pp.n_steps = n_steps;
+    pp.h_step = h_step;
+    pp.idx = (time_varying ? h->d_idx : h->idx_ptr(stage)) + (size_t)prob * h->S_own;
+    pp.idx_stage_stride = (long long)h->slot_elems_idx();
+    pp.u_inc = d_u; pp.x = d_x; pp.X_out = d_X; pp.idx_out = d_c;
+    PT(launch_rollout_axis(pp, h->stream));
+    PT(cudaMemcpyAsync(X_out, d_X, sizeof(double) * 2 * (size_t)(n_steps + 1) * batch, cudaMemcpyDeviceToHost, h->stream));
+    PT(cudaMemcpyAsync(C_out, d_c, sizeof(int32_t) * (size_t)n_steps * batch, cudaMemcpyDeviceToHost, h->stream));
+    PT(cudaStreamSynchronize(h->stream));
+#undef PT
     cleanup();
     return BELLMAN_OK;
 }

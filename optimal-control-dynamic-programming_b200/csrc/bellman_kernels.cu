@@ -423,6 +423,61 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
     U[rp.N - 1] = 0.0;
 }
 
+// ---------------------------------------------------------------------------------------------
+// nearest-policy lookup and simplified-plant axis rollout
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ int nearest_node(const PolicyParams &pp, int d, double x) {
+    double t;
+    const double q = pp.mode[d] == BELLMAN_LOCATE_UNIFORM ? fma(x, pp.inv_h[d], pp.off[d]) : x;
+    const int cell = locate(pp.grid[d], pp.rinv[d], pp.n[d], pp.mode[d], pp.lut[d], pp.lut_n[d], pp.lut_invw[d], q, t);
+    const double lo = pp.grid[d][cell], hi = pp.grid[d][cell + 1];
+    return cell + ((x - lo) >= (hi - x) ? 1 : 0);      // exact midpoint -> upper node
+}
+
+__device__ __forceinline__ int policy_at(const PolicyParams &pp, const int32_t *idx, const double *x) {
+    long long o = 0, st = 1;
+    for (int d = 0; d < pp.D; ++d) {
+        o += (long long)nearest_node(pp, d, x[d]) * st;
+        st *= pp.n[d];
+    }
+    return idx[o];
+}
+
+__global__ void __launch_bounds__(128) k_policy_lookup(const __grid_constant__ PolicyParams pp) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pp.batch) return;
+    double x[MAXD];
+    for (int d = 0; d < pp.D; ++d) x[d] = pp.x[(size_t)b * pp.D + d];
+    pp.idx_out[b] = policy_at(pp, pp.idx, x);
+}
+
+__global__ void __launch_bounds__(128) k_rollout_axis(const __grid_constant__ PolicyParams pp) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pp.batch) return;
+    double x[2] = {pp.x[2 * (size_t)b], pp.x[2 * (size_t)b + 1]};
+    double *X = pp.X_out + (size_t)b * 2 * (pp.n_steps + 1);
+    int32_t *Cc = pp.idx_out + (size_t)b * pp.n_steps;
+    const int r = pp.rate_dim, o = 1 - r;
+    const double h = pp.h_step;
+    X[0] = x[0];
+    X[1] = x[1];
+    for (int k = 1; k <= pp.n_steps; ++k) {
+        const int32_t *idx = pp.idx + (pp.time_varying ? (size_t)(k - 1) * pp.idx_stage_stride : 0);
+        const int c = policy_at(pp, idx, x);
+        Cc[k - 1] = c;
+        const double k1 = x[r];
+        const double k2 = x[r] + (k1 * h) / 2;
+        const double k3 = x[r] + (k2 * h) / 2;
+        const double k4 = x[r] + k3 * h;
+        const double xo = x[o] + (h * (((k1 + 2 * k2) + 2 * k3) + k4)) / 6;
+        const double xr = x[r] + pp.u_inc[c];
+        x[r] = xr;
+        x[o] = xo;
+        X[2 * k] = x[0];
+        X[2 * k + 1] = x[1];
+    }
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -520,6 +575,16 @@ cudaError_t launch_sweep_persistent(const StageParams &sp, double *J_base, int32
 
 cudaError_t launch_rollout(const RolloutParams &rp, cudaStream_t st) {
     k_rollout<<<(rp.batch + 127) / 128, 128, 0, st>>>(rp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_policy_lookup(const PolicyParams &pp, cudaStream_t st) {
+    k_policy_lookup<<<(pp.batch + 127) / 128, 128, 0, st>>>(pp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st) {
+    k_rollout_axis<<<(pp.batch + 127) / 128, 128, 0, st>>>(pp);
     return cudaGetLastError();
 }
 

@@ -51,4 +51,23 @@ struct RolloutParams {
 };
 cudaError_t launch_rollout(const RolloutParams &rp, cudaStream_t st);
 
+// nearest-policy lookup / simplified-plant axis rollout (consumers of the sweep's output)
+struct PolicyParams {
+    const double *grid[MAXD], *rinv[MAXD];   // problem `prob` already applied
+    const int32_t *lut[MAXD];
+    double inv_h[MAXD], off[MAXD], lut_invw[MAXD];
+    int mode[MAXD], n[MAXD], lut_n[MAXD];
+    int D, batch;
+    const int32_t *idx;        // [S] policy of one stage, or [N][S_slot] when time varying
+    long long idx_stage_stride;
+    int time_varying, stage, rate_dim, n_steps;
+    double h_step;
+    const double *u_inc;       // [C]
+    const double *x;           // [D][batch]
+    int32_t *idx_out;          // lookup: [batch]; rollout: [n_steps][batch]
+    double *X_out;             // rollout: [2][n_steps+1][batch]
+};
+cudaError_t launch_policy_lookup(const PolicyParams &pp, cudaStream_t st);
+cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st);
+
 }  // namespace bellman

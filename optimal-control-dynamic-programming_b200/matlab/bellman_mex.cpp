@@ -224,6 +224,40 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
                               (int32_t)batch, (int32_t)mxGetScalar(prhs[7]), (int32_t)mxGetScalar(prhs[8]),
                               mxGetPr(plhs[0]), mxGetPr(U)), h);
         if (nlhs > 1) plhs[1] = U;
+    } else if (cmd == "set_stage") {
+        // bellman_mex('set_stage', h, stage, J, U_Optimal_id)   (J [] = zeros; U_Optimal_id 1-based, [] = none)
+        if (nrhs < 3) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: bellman_mex('set_stage', h, stage, J, idx)");
+        const double *J = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? mxGetPr(prhs[3]) : nullptr;
+        std::vector<int32_t> idx;
+        if (nrhs > 4 && !mxIsEmpty(prhs[4])) {
+            const size_t n = mxGetNumberOfElements(prhs[4]);
+            if (n != sh.S_own * sh.P || !mxIsDouble(prhs[4])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "idx must be a double array with one entry per state");
+            idx.resize(n);
+            for (size_t k = 0; k < n; ++k) idx[k] = (int32_t)mxGetPr(prhs[4])[k] - 1;
+        }
+        check(bellman_set_stage(h, (int32_t)mxGetScalar(prhs[2]), J, idx.empty() ? nullptr : idx.data()), h);
+    } else if (cmd == "policy_lookup") {
+        // id = bellman_mex('policy_lookup', h, prob, stage, X)   X is D-by-batch; id is 1-based like U_Optimal_id
+        if (nrhs < 5) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: id = bellman_mex('policy_lookup', h, prob, stage, X)");
+        const size_t batch = mxGetN(prhs[4]);
+        plhs[0] = mxCreateNumericMatrix(1, batch, mxINT32_CLASS, mxREAL);
+        int32_t *p = static_cast<int32_t *>(mxGetData(plhs[0]));
+        check(bellman_policy_lookup(h, (int32_t)mxGetScalar(prhs[2]) - 1, (int32_t)mxGetScalar(prhs[3]), mxGetPr(prhs[4]),
+                                    (int32_t)batch, p), h);
+        for (size_t k = 0; k < batch; ++k) p[k] += 1;
+    } else if (cmd == "rollout_axis") {
+        // [X,id] = bellman_mex('rollout_axis', h, prob, time_varying, stage, rate_dim, h_step, u_inc, X0, n_steps)
+        if (nrhs < 10) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,id] = bellman_mex('rollout_axis', h, prob, time_varying, stage, rate_dim, h_step, u_inc, X0, n_steps)");
+        const size_t batch = mxGetN(prhs[8]);
+        const int n_steps = (int)mxGetScalar(prhs[9]);
+        plhs[0] = mxCreateDoubleMatrix(2, (size_t)(n_steps + 1) * batch, mxREAL);   // [2][n_steps+1][batch]
+        mxArray *id = mxCreateNumericMatrix((size_t)n_steps, batch, mxINT32_CLASS, mxREAL);
+        int32_t *p = static_cast<int32_t *>(mxGetData(id));
+        check(bellman_rollout_axis(h, (int32_t)mxGetScalar(prhs[2]) - 1, (int32_t)mxGetScalar(prhs[3]),
+                                   (int32_t)mxGetScalar(prhs[4]), (int32_t)mxGetScalar(prhs[5]) - 1, mxGetScalar(prhs[6]),
+                                   mxGetPr(prhs[7]), mxGetPr(prhs[8]), (int32_t)batch, n_steps, mxGetPr(plhs[0]), p), h);
+        for (size_t k = 0; k < (size_t)n_steps * batch; ++k) p[k] += 1;
+        if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
     } else {
         mexErrMsgIdAndTxt("bellman:BAD_ARG", "unknown command '%s'", cmd.c_str());
     }

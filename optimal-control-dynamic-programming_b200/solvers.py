@@ -166,9 +166,26 @@ class _AxisSolverBase:
         self.sweep_stats = sw.stats()
         return self
 
+    def get_optimal_path_simplified(self, X0, n_steps=None):
+        """Closed loop on the SIMPLIFIED plant under the kept nearest policy — the per-axis loop of
+        attitude-control/test/test_simplified.m:129-151 (policy held at its final sweep stage, as
+        U*_Opt is after simplified_run), run on the GPU for a batch of initial states.
+        X0 is [batch, 3, 2] (or [3, 2]): per axis the two states in grid order.  Returns
+        X [batch, 3, n_steps+1, 2] and U [batch, 3, n_steps] (control VALUES)."""
+        sw, d = self._sweep, self._desc
+        X0 = np.asarray(X0, dtype=np.float64).reshape(-1, d.P, 2)
+        n_steps = d.N - 1 if n_steps is None else int(n_steps)
+        X = np.empty((len(X0), d.P, n_steps + 1, 2))
+        U = np.empty((len(X0), d.P, n_steps))
+        for p in range(d.P):
+            Xp, Cp = sw.rollout_axis(d.Tc[self._rate_dim][p], X0[:, p], n_steps, self.h, self._rate_dim, prob=p)
+            X[:, p], U[:, p] = Xp, np.asarray(self.U_vector)[Cp]
+        return X, U
+
 
 class Solver_position(_AxisSolverBase):
     """position-control/Solver_position.m — three independent (x, v) axes, three thrust levels."""
+    _rate_dim = 1
 
     def __init__(self):
         # Solver_position.m:46-92
@@ -201,6 +218,7 @@ class Solver_position(_AxisSolverBase):
 
 class Solver_attitude(_AxisSolverBase):
     """attitude-control/Solver_attitude.m — simplified_run: three (w, theta) axes, three torques."""
+    _rate_dim = 0
 
     def __init__(self):
         # Solver_attitude.m:103-193
@@ -277,6 +295,8 @@ class Solver_pos_att:
         self.check_period = 50          # Solver_pos_att.m:273
         self.check_tol = 1e-2           # :269
         self.controllers = {}
+        self._channel_ctl = {}
+        self._lookup_sweeps = {}
 
     def _grids(self, ch):
         th = ((self.theta1_min, self.theta1_max), (self.theta2_min, self.theta2_max),
@@ -320,9 +340,106 @@ class Solver_pos_att:
         }
         sw.close()
         if file_name:
-            import scipy.io
-            scipy.io.savemat(file_name, {k: v for k, v in ctl.items() if k not in ("stats",)})
+            self.save_controller(file_name, ctl)
         return ctl
+
+    # -- controller files (Solver_pos_att.m:291 save, :849-882 set_controller) -------------------
+    @staticmethod
+    def save_controller(file_name, ctl):
+        """Write the variables the reference saves (:291).  F_gI is written as a struct with the two
+        griddedInterpolant properties set_controller reads (GridVectors, Values), so MATLAB's
+        ``C = load(file); C.F_gI.GridVectors`` works on it unchanged."""
+        import scipy.io
+        gv = np.empty((1, 4), dtype=object)
+        for k in range(4):
+            gv[0, k] = np.asarray(ctl["GridVectors"][k], dtype=np.float64).reshape(1, -1)
+        scipy.io.savemat(file_name, {
+            "F_gI": {"GridVectors": gv, "Values": ctl["F_gI_Values"]},
+            "U_Optimal_id": np.asarray(ctl["U_Optimal_id"], dtype=np.float64),
+            "f0_allcomb": ctl["f0_allcomb"], "f1_allcomb": ctl["f1_allcomb"],
+            "f6_allcomb": ctl["f6_allcomb"], "f7_allcomb": ctl["f7_allcomb"],
+            "stop_stage": float(ctl.get("stop_stage", 0)),
+        }, do_compression=True)
+
+    @staticmethod
+    def load_controller(file_name):
+        import scipy.io
+        m = scipy.io.loadmat(file_name, squeeze_me=False, struct_as_record=False)
+        F = m["F_gI"][0, 0]
+        gv = [np.asarray(g, dtype=np.float64).ravel() for g in F.GridVectors.ravel()]
+        ctl = {"GridVectors": gv, "F_gI_Values": np.asarray(F.Values, dtype=np.float64),
+               "U_Optimal_id": np.asarray(m["U_Optimal_id"]).astype(np.int32)}
+        for k in ("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb"):
+            ctl[k] = np.asarray(m[k], dtype=np.float64).ravel()
+        if "stop_stage" in m:
+            ctl["stop_stage"] = int(m["stop_stage"].ravel()[0])
+        return ctl
+
+    _channel_thrusters = {"x": (0, 1, 6, 7), "y": (2, 3, 8, 9), "z": (4, 5, 10, 11)}
+
+    def set_controller(self, file, channel):
+        """Solver_pos_att.m:849-882: ``file`` is a controller .mat (or the dict
+        calculate_one_channel_U_Opt returns); installs Opt_F_Thr* 'nearest' policies of the channel."""
+        if channel not in self._channel_thrusters:
+            raise ValueError("wrong channel, must be one of x-y-z values")
+        ctl = file if isinstance(file, dict) else self.load_controller(file)
+        uid = np.asarray(ctl["U_Optimal_id"]).astype(np.int64) - 1
+        for name, thr in zip(("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb"), self._channel_thrusters[channel]):
+            setattr(self, "Opt_F_Thr%d" % thr, NearestPolicy(ctl["GridVectors"], np.asarray(ctl[name]).ravel()[uid]))
+        self._channel_ctl[channel] = ctl
+        return self
+
+    def get_thruster_on_off_optimal(self, x, v, t, w, R0=None, V0=None, q=None):
+        """Solver_pos_att.m:404-449 for one state: x, v relative position / velocity, t, w the body
+        angles / rates (3-vectors).  With R0, V0, q given, x and v are first taken from the RSW frame
+        to the body frame (:411-415, :825-847).  Returns the twelve thruster levels f0..f11."""
+        x = np.asarray(x, dtype=np.float64).ravel()
+        v = np.asarray(v, dtype=np.float64).ravel()
+        if R0 is not None:
+            M = self.ECI2body(q) @ self.RSW2ECI(R0, V0)
+            x, v = M @ x, M @ v
+        f = np.zeros(12)
+        ang = {"x": 1, "y": 2, "z": 0}                                  # t_y/w_y, t_z/w_z, t_x/w_x
+        for ci, ch in enumerate("xyz"):
+            a = ang[ch]
+            for thr in self._channel_thrusters[ch]:
+                f[thr] = float(getattr(self, "Opt_F_Thr%d" % thr)(x[ci], v[ci], t[a], w[a]))
+        return f
+
+    def thruster_lookup_batch(self, channel, states):
+        """The same 'nearest' lookup for a BATCH of channel states [batch, 4] = (x, v, theta, w) on the
+        GPU (bellman_policy_lookup): returns [batch, 4] levels of the channel's four thrusters."""
+        ctl = self._channel_ctl[channel]
+        ch = "xyz".index(channel)
+        sw = self._lookup_sweeps.get(channel)
+        if sw is None:
+            d = self.channel_desc(ch)
+            for k in range(4):
+                if not np.array_equal(d.grid[k][0], ctl["GridVectors"][k]):
+                    raise ValueError("controller grid differs from this object's mesh settings")
+            sw = self._lookup_sweeps[channel] = Sweep(d, device=self.device)
+            stage = max(1, min(int(ctl.get("stop_stage", 1)) or 1, d.N - 1))
+            sw.set_stage(stage, None, np.asarray(ctl["U_Optimal_id"]).astype(np.int32).ravel(order="F") - 1)
+        c = sw.policy_lookup(states)
+        return np.stack([np.asarray(ctl[k]).ravel()[c] for k in ("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb")], 1)
+
+    @staticmethod
+    def ECI2body(q):                                                     # :825-829
+        q1, q2, q3, q4 = (float(a) for a in np.asarray(q).ravel())
+        return np.array([
+            [1 - 2 * (q2 ** 2 + q3 ** 2), 2 * (q1 * q2 + q3 * q4), 2 * (q1 * q3 - q2 * q4)],
+            [2 * (q2 * q1 - q3 * q4), 1 - 2 * (q1 ** 2 + q3 ** 2), 2 * (q2 * q3 + q1 * q4)],
+            [2 * (q3 * q1 + q2 * q4), 2 * (q3 * q2 - q1 * q4), 1 - 2 * (q1 ** 2 + q2 ** 2)]])
+
+    @staticmethod
+    def RSW2ECI(pos, vel):                                               # :831-847
+        pos = np.asarray(pos, dtype=np.float64).ravel()
+        vel = np.asarray(vel, dtype=np.float64).ravel()
+        R = pos / np.linalg.norm(pos)
+        h = np.cross(pos, vel)
+        W = h / np.linalg.norm(h)
+        S = np.cross(W, R)
+        return np.column_stack([R, S, W])
 
     def simplified_run(self, save=False, failure_mode=True, n_stages=None):
         """Solver_pos_att.m:197-242: x, y, z channels, then the x-channel failure mode."""

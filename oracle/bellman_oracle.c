@@ -362,3 +362,69 @@ int oracle_num_threads(void)
     return 1;
 #endif
 }
+
+/* ---- consumers of the sweep's output ------------------------------------------------------- */
+
+/* nearest grid node of dimension d (clamped; an exact midpoint goes to the upper node) */
+static int nearest_node(const dimtab *g, double x)
+{
+    double t;
+    const int cell = locate_state(g, x, &t);
+    return cell + ((x - g->s[cell]) >= (g->s[cell + 1] - x) ? 1 : 0);
+}
+
+/* griddedInterpolant({s1,..}, U_vector(idx), 'nearest') at `batch` states of problem p
+ * (Solver_position.m:144-146, Solver_attitude.m:249-251, Solver_pos_att.m:851-861):
+ * x is [D][batch] (batch slowest), idx the [S] policy of one stage, idx_out[batch]. */
+int oracle_policy_lookup(const bellman_desc *d, const int32_t *modes, int p, const int32_t *idx,
+                         const double *x, int batch, int32_t *idx_out)
+{
+    const int D = d->D;
+    dimtab g[MAXD];
+    for (int k = 0; k < D; ++k) dimtab_init(&g[k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * D + k]);
+    for (int b = 0; b < batch; ++b) {
+        int64_t o = 0, st = 1;
+        for (int k = 0; k < D; ++k) { o += nearest_node(&g[k], x[(size_t)b * D + k]) * st; st *= d->n[k]; }
+        idx_out[b] = idx[o];
+    }
+    for (int k = 0; k < D; ++k) free(g[k].rinv);
+    return 0;
+}
+
+/* Simplified-plant rollout under the nearest policy, attitude-control/test/test_simplified.m:129-151
+ * with next_stage_states / RK4_w / RK4_t of :273-310 (the plant Solver_position discretises too):
+ *   c = nearest policy;  x_r' = x_r + u_inc[c];
+ *   x_o' = x_o + h*(k1 + 2*k2 + 2*k3 + k4)/6,  k1 = x_r, k2 = x_r + k1*h/2, k3 = x_r + k2*h/2, k4 = x_r + k3*h
+ * idx: [S] (fixed policy) or [n_steps][stride] (time varying, slot k-1 = stage k).
+ * x0 [2][batch]; X_out [2][n_steps+1][batch]; C_out [n_steps][batch]. */
+int oracle_rollout_axis(const bellman_desc *d, const int32_t *modes, int p, const int32_t *idx,
+                        int64_t idx_stage_stride, int time_varying, int rate_dim, double h,
+                        const double *u_inc, const double *x0, int batch, int n_steps,
+                        double *X_out, int32_t *C_out)
+{
+    if (d->D != 2) return -1;
+    dimtab g[2];
+    for (int k = 0; k < 2; ++k) dimtab_init(&g[k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * 2 + k]);
+    const int r = rate_dim, o = 1 - rate_dim;
+    for (int b = 0; b < batch; ++b) {
+        double x[2] = {x0[2 * (size_t)b], x0[2 * (size_t)b + 1]};
+        double *X = X_out + (size_t)b * 2 * (n_steps + 1);
+        int32_t *Cc = C_out + (size_t)b * n_steps;
+        X[0] = x[0]; X[1] = x[1];
+        for (int k = 1; k <= n_steps; ++k) {
+            const int32_t *id = idx + (time_varying ? (size_t)(k - 1) * idx_stage_stride : 0);
+            const int c = id[nearest_node(&g[0], x[0]) + (int64_t)nearest_node(&g[1], x[1]) * d->n[0]];
+            Cc[k - 1] = c;
+            const double k1 = x[r];
+            const double k2 = x[r] + (k1 * h) / 2;
+            const double k3 = x[r] + (k2 * h) / 2;
+            const double k4 = x[r] + k3 * h;
+            const double xo = x[o] + (h * (((k1 + 2 * k2) + 2 * k3) + k4)) / 6;
+            const double xr = x[r] + u_inc[c];
+            x[r] = xr; x[o] = xo;
+            X[2 * k] = x[0]; X[2 * k + 1] = x[1];
+        }
+    }
+    free(g[0].rinv); free(g[1].rinv);
+    return 0;
+}

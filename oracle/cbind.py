@@ -170,3 +170,39 @@ def stage_points(d, J_next_p, states, p=0, modes=None):
                                    Io.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
     return Jo, Io
+
+
+def policy_lookup(d, idx_p, x, p=0, modes=None):
+    """Nearest-policy lookup: idx_p [S] policy of problem p, x [batch, D].  Returns idx0 [batch]."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    x = _arr(x).reshape(-1, len(d.n))
+    ia = np.ascontiguousarray(idx_p, dtype=np.int32).ravel()
+    out = np.zeros(len(x), dtype=np.int32)
+    rc = lib().oracle_policy_lookup(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(p),
+                                    ia.ctypes.data_as(C.POINTER(C.c_int32)), x.ctypes.data_as(_dp),
+                                    C.c_int(len(x)), out.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return out
+
+
+def rollout_axis(d, idx, u_inc, x0, n_steps, h, rate_dim, p=0, time_varying=False, modes=None):
+    """Simplified-plant rollout.  idx: [S] or, time varying, [n_steps(+), S] (row k-1 = stage k).
+    x0 [batch, 2].  Returns X [batch, n_steps+1, 2], Cidx [batch, n_steps]."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    x0 = _arr(x0).reshape(-1, 2)
+    batch = len(x0)
+    ia = np.ascontiguousarray(idx, dtype=np.int32)
+    stride = ia.shape[-1] if time_varying else 0
+    X = np.zeros((batch, n_steps + 1, 2))
+    Cc = np.zeros((batch, n_steps), dtype=np.int32)
+    ui = _arr(u_inc)
+    rc = lib().oracle_rollout_axis(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(p),
+                                   ia.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int64(stride),
+                                   C.c_int(int(time_varying)), C.c_int(rate_dim), C.c_double(h),
+                                   ui.ctypes.data_as(_dp), x0.ctypes.data_as(_dp), C.c_int(batch),
+                                   C.c_int(n_steps), X.ctypes.data_as(_dp),
+                                   Cc.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return X, Cc

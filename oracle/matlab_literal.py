@@ -342,3 +342,33 @@ class SolverPosAttLiteral:
                 if abs(e) < tol:
                     break
         return F.Values, idx, grids, k_stop, log
+
+
+# --- simplified-plant simulation under the nearest policy ---------------------------------------
+def simplified_axis_rollout_literal(s_a, s_b, U_opt_values, rate_dim, k_of_u, h, x0, n_steps):
+    """attitude-control/test/test_simplified.m:129-151 for ONE axis, literally: every step builds
+    griddedInterpolant({s_a, s_b}, U_Opt(:,:,k), 'nearest'), evaluates it at the state, then applies
+    next_stage_states (:273-310).  ``U_opt_values`` is [n_a, n_b] (fixed policy) or
+    [n_a, n_b, n_steps] (time varying, control VALUES like U*_Opt); ``rate_dim`` is the state the
+    control drives (0 for attitude's (w, theta), 1 for position's (x, v)); ``k_of_u`` maps the
+    control value to the slope of the rate state (U/J or U/Mass).  Returns X [n_steps+1, 2], U [n_steps]."""
+    X = np.zeros((n_steps + 1, 2))
+    U = np.zeros(n_steps)
+    X[0] = x0
+    r, o = rate_dim, 1 - rate_dim
+    tv = np.ndim(U_opt_values) == 3
+    for k in range(n_steps):
+        FU = GriddedInterpolantNearest([s_a, s_b], U_opt_values[:, :, k] if tv else U_opt_values)
+        u = float(FU(np.array(X[k, 0]), np.array(X[k, 1])))
+        U[k] = u
+        w = X[k, r]
+        kk = k_of_u(u)                                                          # RK4_w: four equal slopes
+        w_new = w + h * (kk + 2 * kk + 2 * kk + kk) / 6
+        k1 = w                                                                  # RK4_t
+        k2 = w + k1 * h / 2
+        k3 = w + k2 * h / 2
+        k4 = w + k3 * h
+        t_new = X[k, o] + h * (k1 + 2 * k2 + 2 * k3 + k4) / 6
+        X[k + 1, r] = w_new
+        X[k + 1, o] = t_new
+    return X, U

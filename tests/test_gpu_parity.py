@@ -361,3 +361,116 @@ def test_attitude_x4_full_size_spot_check(bellman, oracle_lib):
         Jo, Io = oracle_lib.stage_points(d, J1[p], pts, p=p)
         assert np.array_equal(I2[p][pts], Io) and np.array_equal(J2[p][pts], Jo)
     sw.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# "next" rows: consumers of the sweep output (policy lookup, simplified-plant rollout, controller
+# save / set_controller round trip, resume from a saved stage)
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_policy_lookup_matches_oracle(bellman, oracle_lib):
+    rng = np.random.default_rng(11)
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 9, 8, 7, 6
+    d = sp.channel_desc(1)
+    with bellman.Sweep(d) as sw:
+        sw.run(6)
+        idx = sw.get_idx()[0]
+        lo = np.array([d.grid[k][0][0] for k in range(4)]); hi = np.array([d.grid[k][0][-1] for k in range(4)])
+        x = rng.uniform(lo - 0.3 * (hi - lo), hi + 0.3 * (hi - lo), size=(4096, 4))
+        x[:len(d.grid[3][0])] = np.stack([np.resize(d.grid[k][0], len(d.grid[3][0])) for k in range(4)], 1)  # nodes
+        x[100] = [0.5 * (d.grid[k][0][1] + d.grid[k][0][2]) for k in range(4)]                                  # midpoints
+        got = sw.policy_lookup(x)
+    want = oracle_lib.policy_lookup(d, idx, x)
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("which", ["attitude", "position"])
+def test_rollout_axis_matches_oracle(bellman, oracle_lib, which):
+    t = bellman.tables
+    rng = np.random.default_rng(5)
+    N, h = 60, 0.01
+    if which == "attitude":
+        d = t.attitude_axis_desc(t.deg2rad(-0.7), t.deg2rad(0.7), 24, -5.0, 5.0, 20, [-0.01, 0.0, 0.01], 2.5,
+                                 6.0, 6.0, 0.1, h, N)
+        rate = 0
+    else:
+        d = t.position_axis_desc(-0.5, 0.5, 21, -0.5, 0.5, 17, [-0.26, 0.0, 0.26], 4.16, 6.0, 6.0, 0.1, h, N)
+        rate = 1
+    u_inc = d.Tc[rate][0]
+    lo = np.array([d.grid[k][0][0] for k in range(2)]); hi = np.array([d.grid[k][0][-1] for k in range(2)])
+    x0 = rng.uniform(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), size=(257, 2))
+    d.store_idx_all = True
+    with bellman.Sweep(d) as sw:
+        sw.run()
+        idx_all = np.stack([sw.get_idx(k)[0] for k in range(1, N)])
+        Xg, Cg = sw.rollout_axis(u_inc, x0, N - 1, h, rate, time_varying=True)
+        Xf, Cf = sw.rollout_axis(u_inc, x0, 150, h, rate, stage=1)
+    Xo, Co = oracle_lib.rollout_axis(d, idx_all, u_inc, x0, N - 1, h, rate, time_varying=True)
+    assert np.array_equal(Cg, Co) and np.array_equal(Xg, Xo)
+    Xo, Co = oracle_lib.rollout_axis(d, idx_all[0], u_inc, x0, 150, h, rate)
+    assert np.array_equal(Cf, Co) and np.array_equal(Xf, Xo)
+
+
+@pytest.mark.gpu
+def test_axis_solver_simplified_closed_loop(bellman, oracle_lib):
+    """facade: Solver_attitude.simplified_run then the test_simplified.m loop on the GPU vs the literal loop."""
+    from oracle import matlab_literal as ml
+    sa = bellman.Solver_attitude()
+    sa.n_mesh_w, sa.n_mesh_t, sa.T_final, sa.h = 40, 30, 0.5, 0.01
+    sa.simplified_run()
+    X0 = np.array([[[0.05, 0.1], [-0.2, -0.05], [0.0, 0.3]]])
+    X, U = sa.get_optimal_path_simplified(X0, n_steps=120)
+    d = sa._desc
+    for p in range(3):
+        J = (sa.J1, sa.J2, sa.J3)[p]
+        Uopt = np.asarray(sa.U_vector)[sa.U_idx[p] - 1]
+        Xl, Ul = ml.simplified_axis_rollout_literal(d.grid[0][p], d.grid[1][p], Uopt, 0, lambda u: u / J, sa.h, X0[0, p], 120)
+        assert np.array_equal(U[0, p], Ul)
+        assert np.array_equal(X[0, p], Xl)
+
+
+@pytest.mark.gpu
+def test_pos_att_controller_file_round_trip(bellman, oracle_lib, tmp_path):
+    rng = np.random.default_rng(2)
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 8, 7, 6, 5
+    f = str(tmp_path / "channel_y_controller_1.mat")
+    ctl = sp.calculate_one_channel_U_Opt(1, file_name=f, n_stages=7)
+    back = sp.load_controller(f)
+    assert np.array_equal(back["U_Optimal_id"], ctl["U_Optimal_id"])
+    assert np.array_equal(back["F_gI_Values"], ctl["F_gI_Values"])
+    for k in range(4):
+        assert np.array_equal(back["GridVectors"][k], ctl["GridVectors"][k])
+    sp.set_controller(f, "y")
+    with pytest.raises(ValueError):
+        sp.set_controller(f, "w")
+    d = sp.channel_desc(1)
+    lo = np.array([d.grid[k][0][0] for k in range(4)]); hi = np.array([d.grid[k][0][-1] for k in range(4)])
+    x = rng.uniform(lo - 0.1 * (hi - lo), hi + 0.1 * (hi - lo), size=(300, 4))
+    F = sp.thruster_lookup_batch("y", x)                                    # GPU, after set_stage
+    c = oracle_lib.policy_lookup(d, (ctl["U_Optimal_id"] - 1).ravel(order="F"), x)
+    for j, (name, thr) in enumerate(zip(("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb"), (2, 3, 8, 9))):
+        assert np.array_equal(F[:, j], ctl[name][c])
+        host = getattr(sp, "Opt_F_Thr%d" % thr)(x[:, 0], x[:, 1], x[:, 2], x[:, 3])      # host NearestPolicy
+        assert np.array_equal(host, F[:, j])
+
+
+@pytest.mark.gpu
+def test_resume_from_saved_stage(bellman, oracle_lib):
+    """bellman_set_stage: J of stage k put back on a fresh handle continues to the same bits."""
+    d = bellman.tables.kirk_desc([[0.9974, 0.0539], [-0.1078, 1.1591]], [0.0013, 0.0539], [[0.25, 0.0], [0.0, 0.05]],
+                                 0.05, 20, -2.5, 3.0, 48, -40.0, 10.0, 40, store_J_all=False, store_idx_all=False)
+    with bellman.Sweep(d) as a:
+        a.run(8)
+        Jk, k = a.get_J(), a.current_stage
+        a.run(6)
+        Jend, iend = a.get_J(), a.get_idx()
+    with bellman.Sweep(d) as b:
+        b.set_stage(k, Jk)
+        assert b.current_stage == k
+        b.run(6)
+        assert np.array_equal(b.get_J(), Jend) and np.array_equal(b.get_idx(), iend)
+        with pytest.raises(bellman.BellmanError):
+            b.set_stage(d.N, None, np.zeros(d.S, dtype=np.int32))
