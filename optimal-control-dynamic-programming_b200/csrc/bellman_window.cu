@@ -53,6 +53,10 @@ struct WindowParams {
     // rowpack[p][i] = {row_0, row_1, qrow, 0},  colpack[p][j] = {col_0, col_1, qcol, 0}
     const double4 *rowpack, *colpack;
     int col0_zero, col1_zero;  // the column part of dimension 0 / 1 is absent (all zeros)
+    // k_stage_strip: colq[p][j] = {col_1, qcol} (one 16-byte load per column), strip_r = columns
+    // walked by one warp
+    const double2 *colq;
+    int strip_r;
 };
 
 // --- PTX wrappers ------------------------------------------------------------------------------
@@ -86,6 +90,14 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
             "r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
+}
+
+// shared-memory load by 32-bit address (keeps the address arithmetic in 32-bit integer registers).
+// Not volatile: the caller orders it after the mbarrier wait through a data dependence.
+__device__ __forceinline__ double lds_f64(uint32_t addr) {
+    double v;
+    asm("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr));
+    return v;
 }
 
 // UNIFORM locate of include/bellman.h: the tables are pre-scaled to cell units on the host, so the
@@ -485,6 +497,184 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_stage_strip: the CHAIN problems (dimension-0 query = row part + control, dimension-1 query
+// independent of the control: Solver_attitude, 3 torque levels) with the loops turned inside out.
+// A warp owns 32 rows x strip_r columns and WALKS the columns: everything that depends on the row
+// only — the dimension-0 cell and weight of every control, the window base pointers, r[c] — is
+// computed once per thread and kept in registers; per column a thread does one 16-byte table load,
+// one locate, and per control two shared-memory loads and the three lerps of the generic path (the
+// dimension-0 lerp of the lower column is the upper column's of the previous step whenever the cells
+// are consecutive, which they are except at the clamped grid edge).  No per-state arrays, so the
+// strip length costs no registers and the per-thread prologue is amortised over strip_r x C updates
+// (k_stage_chain: 54 instructions per update, half of them prologue/epilogue — profiles/r01).
+// Same operations on the same operands as the generic path ⇒ bit-identical results.
+// All C windows of the tile (32+ rows x NW*strip_r+ columns) are in flight from the first instruction.
+// ---------------------------------------------------------------------------------------------
+template <int NW, int CC, int OCC, bool PEER>
+__global__ void __launch_bounds__(NW * 32, OCC)
+k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
+              const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) double ring[];    // CC windows, win0 x win1 doubles each
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ int org[CC];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int prob = blockIdx.y;
+    const int R = wp.strip_r, WT1 = NW * R;
+    const int ti = wp.tj_fastest ? blockIdx.x / wp.ntile1 : blockIdx.x % wp.ntile0;
+    const int tj = wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0;
+    const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
+    const int n0 = d0.n, n1 = d1.n, W0 = wp.win0;
+    const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
+    const int j_lo = d1.own_lo + tj * WT1, j_hi = min(j_lo + WT1, d1.own_lo + d1.own_n);
+    const double *Tc0 = d0.Tc + (size_t)prob * CC;
+    const double *rr = sp.r + (size_t)prob * CC;
+
+    // lanes 0..C-1 of warp 0 each place and issue one control's window (their table loads overlap)
+    if (wrp == 0) {
+        if (lane == 0) {
+            mbar_init(&mbar, (uint32_t)CC);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        __syncwarp();
+        if (lane < CC) {
+            const int c = lane;
+            const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
+            double lo0 = __ldg(tm + wp.tmm_off[0][0] + 2 * ti);
+            if (d0.Tb) lo0 = lo0 + __ldg(tm + wp.tmm_off[0][1] + 2 * ti);
+            double lo1 = __ldg(tm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? ti : tj));
+            if (d1.Tb) lo1 = lo1 + __ldg(tm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? ti : tj));
+            const int c0 = cell_uniform(lo1, n1);
+            int r0 = cell_uniform(lo0 + __ldg(Tc0 + c), n0);
+            r0 -= (r0 - d0.ext_lo) & 1;                              // TMA: even innermost coordinate
+            org[c] = c0 * W0 + r0;
+            mbar_expect_tx(&mbar, (uint32_t)(wp.win0 * wp.win1) * 8u);
+            tma_load_3d(ring + (size_t)c * wp.buf_doubles, &tmap, &mbar, r0 - d0.ext_lo, c0 - d1.ext_lo, prob);
+        }
+    }
+
+    // row constants of this thread
+    const int i = min(i_lo + lane, i_hi - 1);
+    const double2 *rpk = reinterpret_cast<const double2 *>(wp.rowpack + (size_t)prob * n0 + i);
+    const double2 rp01 = __ldg(rpk);
+    const double qrow = __ldg(reinterpret_cast<const double *>(rpk + 1));
+    double t0[CC], rc[CC];
+    int cell0[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) {
+        rc[c] = __ldg(rr + c);
+        cell0[c] = locate_uniform<true, false>(rp01.x + __ldg(Tc0 + c), n0, t0[c]);
+    }
+    const int jb = j_lo + wrp * R;
+    const int jcnt = min(R, j_hi - jb);                  // warp-uniform; <= 0 for a ragged last tile
+    const double2 *cq = wp.colq + (size_t)prob * n1 + jb;
+    double2 cd = jcnt > 0 ? __ldg(cq) : make_double2(0.0, 0.0);
+    const bool row_ok = i_lo + lane < i_hi;
+    double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
+                 (long long)(jb - d1.ext_lo) * d1.stride;
+    int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
+                  (long long)(jb - d1.own_lo) * d0.own_n;
+    const long long sj = d1.stride;
+    const long long si = d0.own_n;
+
+    __syncthreads();          // org[] and the mbarrier are visible
+    mbar_wait(&mbar, 0);
+
+    if (jcnt <= 0) return;    // ragged last tile: this warp has no columns (no barrier follows)
+
+    // shared-memory byte addresses (32-bit): window of control c shifted so that cell1 * pitch is
+    // this row's lower-left corner.  `base` passes through a volatile asm placed after the wait, so
+    // no window load can be scheduled above it.
+    uint32_t base = smem_u32(ring);
+    asm volatile("" : "+r"(base)::"memory");
+    const uint32_t pitch = (uint32_t)W0 * 8u;
+    uint32_t pc[CC];
+#pragma unroll
+    for (int c = 0; c < CC; ++c) pc[c] = base + 8u * (uint32_t)(c * wp.buf_doubles + (cell0[c] - org[c]));
+
+    // dimension-0 lerp of one window column for every control
+    auto column = [&](uint32_t o, double (&a)[CC]) {
+        double lo[CC], hi[CC];
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+            lo[c] = lds_f64(pc[c] + o);
+            hi[c] = lds_f64(pc[c] + o + 8);
+        }
+#pragma unroll
+        for (int c = 0; c < CC; ++c) a[c] = fma(t0[c], hi[c] - lo[c], lo[c]);
+    };
+    // the lower column of the first state; after that the lower column of a state is the upper
+    // column of the previous one whenever the cells are consecutive — always, except at the clamped
+    // grid edge or when rounding makes a query skip a cell
+    double ahi[CC];
+    int prev;
+    {
+        double t1;
+        prev = locate_uniform<true, true>(rp01.y + cd.x, n1, t1) - 1;
+        column((uint32_t)(prev + 1) * pitch, ahi);
+    }
+    auto finish = [&](int mm, double gs, double t1, const double (&alo)[CC], const double (&a)[CC]) {
+        double best = __longlong_as_double(0x7ff0000000000000LL);
+        int arg = 0;
+#pragma unroll
+        for (int c = 0; c < CC; ++c) {
+            const double v = fma(t1, a[c] - alo[c], alo[c]);
+            const double tot = (gs + rc[c]) + v;
+            if (tot < best) { best = tot; arg = c; }
+        }
+        if (row_ok) {
+            *jo = best;
+            *io = arg;
+            if (PEER) { const int gi[2] = {i, jb + mm}; peer_store<2>(sp, prob, gi, best); }
+        }
+        jo += sj;
+        io += si;
+    };
+    // Chained columns.  `lower` holds the dimension-0 lerps of window column cell1 (computed by the
+    // previous step), `upper` receives those of column cell1 + 1.  Whether every lane's cell really
+    // was the successor of its previous one is only accumulated in `bad` — no branch between the
+    // columns, so two of them interleave — and checked once per strip: a strip that fails (clamped
+    // grid edge, a query that skipped a cell through rounding) or that is ragged is redone by the
+    // generic loop below, which overwrites what the chained pass stored.
+    int m = 0;
+    if (jcnt == R) {
+        bool bad = false;
+        int expect = prev + 1;
+        auto step = [&](double (&lower)[CC], double (&upper)[CC]) {
+            const double2 cdn = __ldg(cq + m + 1);                      // next column's tables (colq is padded)
+            double t1;
+            const int cell1 = locate_uniform<true, true>(rp01.y + cd.x, n1, t1);
+            bad = bad || cell1 != expect;
+            column((uint32_t)cell1 * pitch + pitch, upper);
+            finish(m, qrow + cd.y, t1, lower, upper);
+            expect = cell1 + 1;
+            cd = cdn;
+            ++m;
+        };
+        double bhi[CC];
+#pragma unroll 1
+        while (m < R) {             // strip_r is even
+            step(ahi, bhi);
+            step(bhi, ahi);         // registers ping-pong, no copies
+        }
+        if (!__any_sync(0xffffffffu, bad)) return;
+        jo -= (long long)R * sj;
+        io -= (long long)R * si;
+        m = 0;
+    }
+    // generic columns: both window columns are read
+#pragma unroll 1
+    for (; m < jcnt; ++m) {
+        const double2 cdc = __ldg(cq + m);
+        double t1, alo[CC];
+        const int cell1 = locate_uniform<true, true>(rp01.y + cdc.x, n1, t1);
+        column((uint32_t)cell1 * pitch, alo);
+        column((uint32_t)cell1 * pitch + pitch, ahi);
+        finish(m, qrow + cdc.y, t1, alo, ahi);
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -506,8 +696,10 @@ struct WindowState {
     WindowParams wp{};
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
-    bool hc0 = false, hc1 = false, chain = false, lean = false;
+    bool hc0 = false, hc1 = false, chain = false, lean = false, strip = false;
     size_t lean_smem = 0;
+    int strip_nw = 4;
+    void *d_colq = nullptr;
     int batch = 4, occ = 2, rstates = 8;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
@@ -564,6 +756,49 @@ static bool window_dispatch(const WindowState *ws, const StageParams *sp, const 
     if (ws->hc0 && ws->chain) return window_go_hc<true, false, true>(ws, sp, map, grid, st, sa);
     if (ws->hc0) return window_go_hc<true, false, false>(ws, sp, map, grid, st, sa);
     return window_go_hc<false, true, false>(ws, sp, map, grid, st, sa);
+}
+
+template <int NW, int CC, int OCC>
+static bool strip_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid, cudaStream_t st,
+                     bool set_attr_only) {
+    auto fn = k_stage_strip<NW, CC, OCC, false>;
+    auto fnp = k_stage_strip<NW, CC, OCC, true>;      // multi-GPU: halo states also go to the neighbours
+    if (set_attr_only)
+        return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ws->lean_smem) == cudaSuccess &&
+               cudaFuncSetAttribute((const void *)fnp, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)ws->lean_smem) == cudaSuccess;
+    if (sp->n_peers) fnp<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+    else fn<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+    return true;
+}
+static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
+                           cudaStream_t st, bool sa) {
+    const int C = ws->wp.nchunks;   // chunk size 1: one window per control
+    if (ws->strip_nw == 8) {
+        switch (C) {
+            case 1: return strip_go<8, 1, 3>(ws, sp, map, grid, st, sa);
+            case 2: return strip_go<8, 2, 3>(ws, sp, map, grid, st, sa);
+            case 3: return strip_go<8, 3, 3>(ws, sp, map, grid, st, sa);
+            default: return strip_go<8, 4, 3>(ws, sp, map, grid, st, sa);
+        }
+    }
+    if (ws->occ == 3) {   // BELLMAN_WIN_OCC=3: fewer CTAs per SM, more registers (experiments)
+        switch (C) {
+            case 3: return strip_go<4, 3, 5>(ws, sp, map, grid, st, sa);
+            default: break;
+        }
+    }
+    switch (C) {
+        case 1: return strip_go<4, 1, 7>(ws, sp, map, grid, st, sa);
+        case 2: return strip_go<4, 2, 7>(ws, sp, map, grid, st, sa);
+        case 3: return strip_go<4, 3, 7>(ws, sp, map, grid, st, sa);
+        default: return strip_go<4, 4, 7>(ws, sp, map, grid, st, sa);
+    }
+}
+static void window_teardown_state(WindowState *ws) {
+    cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp); cudaFree(ws->d_colq);
+    delete ws;
 }
 
 // Exact worst-case window extents for a given chunk size: replays, on the host, the bound the
@@ -628,13 +863,18 @@ void window_setup(bellman_handle *h) {
     const bool chain_cfg = hp.has_c[0] && !hp.has_c[1] && hp.src_a[0] == 0 && (!hp.has_b[0] || hp.src_b[0] == 0) &&
                            !std::getenv("BELLMAN_WIN_NOCHAIN");
     const int rstates = (chain_cfg && hp.C <= 8 && !std::getenv("BELLMAN_WIN_R8")) ? 4 : 8;
-    const int wt1 = tile1_of(rstates);
+    // k_stage_strip geometry: NW warps per CTA, each walking strip_r columns (tile 32 x NW*strip_r)
+    const bool lean_cfg = chain_cfg && rstates == 4 && hp.C <= 4 && !std::getenv("BELLMAN_WIN_NOLEAN");
+    const bool strip_cfg = lean_cfg && !std::getenv("BELLMAN_WIN_NOSTRIP");
+    int strip_nw = 4, strip_r = 8;
+    if (const char *e = std::getenv("BELLMAN_STRIP_NW")) strip_nw = std::atoi(e) == 8 ? 8 : 4;
+    if (const char *e = std::getenv("BELLMAN_STRIP_R")) strip_r = std::max(2, std::min(64, std::atoi(e) / 2 * 2));
+    const int wt1 = strip_cfg ? strip_nw * strip_r : tile1_of(rstates);
 
     // pick the chunk size: most updates per staged byte among configs that keep two CTAs per SM
     const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
     int best_cc = 0, best_w0 = 0, best_w1 = 0;
     double best_score = -1.0;
-    const bool lean_cfg = chain_cfg && rstates == 4 && hp.C <= 4 && !std::getenv("BELLMAN_WIN_NOLEAN");
     std::vector<int> cands;
     if (lean_cfg) {
         cands.push_back(1);                       // k_stage_chain: one window per control, all in flight
@@ -691,7 +931,7 @@ void window_setup(bellman_handle *h) {
     // dimension-0 query independent of the dimension-1 index, dimension 1 independent of the control
     ws->chain = chain_cfg;
     ws->rstates = rstates;
-    if (hp.q_order[0] != 0 && hp.q_order[0] != 1) { delete ws; return; }
+    if (hp.q_order[0] != 0 && hp.q_order[0] != 1) { window_teardown_state(ws); return; }
 
     // per-chunk control min/max and interleaved (grid, rinv) tables
     std::vector<double> cmm((size_t)hp.P * wp.nchunks * 4, 0.0);
@@ -706,7 +946,7 @@ void window_setup(bellman_handle *h) {
         return cudaMalloc(dptr, v.size() * sizeof(double)) == cudaSuccess &&
                cudaMemcpy(*dptr, v.data(), v.size() * sizeof(double), cudaMemcpyHostToDevice) == cudaSuccess;
     };
-    if (!upload(cmm, &ws->d_cmm)) { delete ws; return; }
+    if (!upload(cmm, &ws->d_cmm)) { window_teardown_state(ws); return; }
     wp.cmm = static_cast<const double *>(ws->d_cmm);
 
     // canonical packed state tables
@@ -741,12 +981,17 @@ void window_setup(bellman_handle *h) {
         // zero that is skipped, otherwise -0.0 + 0.0 would flip a sign; rows are always added, so
         // require the row part to exist (true for every reference class)
         for (int d = 0; d < 2; ++d)
-            if (hp.src_a[d] != 0 && !(hp.has_b[d] && hp.src_b[d] == 0)) { delete ws; return; }
-        if (!upload(rowp, &ws->d_rowp) || !upload(colp, &ws->d_colp)) { delete ws; return; }
+            if (hp.src_a[d] != 0 && !(hp.has_b[d] && hp.src_b[d] == 0)) { window_teardown_state(ws); return; }
+        if (!upload(rowp, &ws->d_rowp) || !upload(colp, &ws->d_colp)) { window_teardown_state(ws); return; }
         wp.rowpack = static_cast<const double4 *>(ws->d_rowp);
         wp.colpack = static_cast<const double4 *>(ws->d_colp);
         wp.col0_zero = colz[0] ? 1 : 0;
         wp.col1_zero = colz[1] ? 1 : 0;
+        std::vector<double> colq((size_t)hp.P * hp.n[1] * 2 + 2, 0.0);   // +1 entry: the strip kernel prefetches one ahead
+        for (size_t k = 0; k < (size_t)hp.P * hp.n[1]; ++k) { colq[2 * k] = colp[4 * k + 1]; colq[2 * k + 1] = colp[4 * k + 2]; }
+        if (!upload(colq, &ws->d_colq)) { window_teardown_state(ws); return; }
+        wp.colq = static_cast<const double2 *>(ws->d_colq);
+        wp.strip_r = strip_r;
     }
 
     // per-tile-index extrema of the state-indexed tables (read by the kernel instead of reducing per tile)
@@ -774,7 +1019,7 @@ void window_setup(bellman_handle *h) {
                                      tmm[(size_t)p * off + wp.tmm_off[d][ab] + 2 * t],
                                      tmm[(size_t)p * off + wp.tmm_off[d][ab] + 2 * t + 1]);
                 }
-        if (!upload(tmm, &ws->d_tmm)) { delete ws; return; }
+        if (!upload(tmm, &ws->d_tmm)) { window_teardown_state(ws); return; }
         wp.tmm = static_cast<const double *>(ws->d_tmm);
     }
 
@@ -790,7 +1035,7 @@ void window_setup(bellman_handle *h) {
         CUresult r = enc(&ws->maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, base, gdim, gstr, box, estr,
                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                          CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) { delete ws; return; }
+        if (r != CUDA_SUCCESS) { window_teardown_state(ws); return; }
     }
     {
         const char *eb = std::getenv("BELLMAN_WIN_BATCH"), *eo = std::getenv("BELLMAN_WIN_OCC");
@@ -799,8 +1044,15 @@ void window_setup(bellman_handle *h) {
         if (ws->batch != 2 && ws->batch != 4 && ws->batch != 8) ws->batch = 4;
         if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
     }
-    if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { delete ws; return; }
-    ws->lean = lean_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1;
+    if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { window_teardown_state(ws); return; }
+    ws->strip = strip_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1 && !wp.col1_zero;
+    if (ws->strip) {
+        ws->strip_nw = strip_nw;
+        ws->lean_smem = (size_t)wp.nchunks * slot_bytes(wp.win0, wp.win1);
+        if (ws->lean_smem > 200 * 1024 || !strip_dispatch(ws, nullptr, nullptr, dim3(), nullptr, true)) ws->strip = false;
+        if (!ws->strip && wt1 != tile1_of(rstates)) { window_teardown_state(ws); return; }
+    }
+    ws->lean = !ws->strip && lean_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1;
     if (ws->lean) {
         ws->lean_smem = (size_t)wp.nchunks * slot_bytes(wp.win0, wp.win1);
         if (ws->lean_smem > 56 * 1024 ||
@@ -808,7 +1060,7 @@ void window_setup(bellman_handle *h) {
                                  (int)ws->lean_smem) != cudaSuccess)
             ws->lean = false;
     }
-    if (!ws->hc0 && !ws->hc1) { delete ws; return; }   // no control dependence at all: nothing to stage for
+    if (!ws->hc0 && !ws->hc1) { window_teardown_state(ws); return; }   // no control dependence at all: nothing to stage for
     h->wstate = ws;
     h->wcfg.tile0 = WT0; h->wcfg.tile1 = wt1; h->wcfg.cchunk = wp.cchunk;
     h->wcfg.win0 = wp.win0; h->wcfg.win1 = wp.win1;
@@ -818,8 +1070,7 @@ void window_setup(bellman_handle *h) {
 void window_teardown(bellman_handle *h) {
     auto *ws = static_cast<WindowState *>(h->wstate);
     if (!ws) return;
-    cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp);
-    delete ws;
+    window_teardown_state(ws);
     h->wstate = nullptr;
 }
 
@@ -829,7 +1080,8 @@ cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     const WindowParams &wp = ws->wp;
     const dim3 grid((unsigned)(wp.ntile0 * wp.ntile1), (unsigned)sp.P);
     const CUtensorMap &map = ws->maps[slot_next];
-    if (ws->lean) k_stage_chain<4, 4><<<grid, WNT, ws->lean_smem, st>>>(sp, wp, map);
+    if (ws->strip) strip_dispatch(ws, &sp, &map, grid, st, false);
+    else if (ws->lean) k_stage_chain<4, 4><<<grid, WNT, ws->lean_smem, st>>>(sp, wp, map);
     else window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
     return cudaGetLastError();
 }
