@@ -519,17 +519,19 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     __shared__ __align__(8) uint64_t mbar;
     __shared__ int org[CC];
 
+    // grid = (fast tile index, slow tile index, problem): no division to decode the tile; every
+    // element offset fits 32 bits (checked by the planner), so addresses cost one IMAD.WIDE each
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
-    const int prob = blockIdx.y;
+    const uint32_t prob = blockIdx.z;
     const int R = wp.strip_r, WT1 = NW * R;
-    const int ti = wp.tj_fastest ? blockIdx.x / wp.ntile1 : blockIdx.x % wp.ntile0;
-    const int tj = wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0;
+    const int ti = wp.tj_fastest ? blockIdx.y : blockIdx.x;
+    const int tj = wp.tj_fastest ? blockIdx.x : blockIdx.y;
     const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
     const int n0 = d0.n, n1 = d1.n, W0 = wp.win0;
     const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
     const int j_lo = d1.own_lo + tj * WT1, j_hi = min(j_lo + WT1, d1.own_lo + d1.own_n);
-    const double *Tc0 = d0.Tc + (size_t)prob * CC;
-    const double *rr = sp.r + (size_t)prob * CC;
+    const double *Tc0 = d0.Tc + prob * (uint32_t)CC;
+    const double *rr = sp.r + prob * (uint32_t)CC;
 
     // lanes 0..C-1 of warp 0 each place and issue one control's window (their table loads overlap)
     if (wrp == 0) {
@@ -540,7 +542,7 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
         __syncwarp();
         if (lane < CC) {
             const int c = lane;
-            const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
+            const double *tm = wp.tmm + prob * (uint32_t)wp.tmm_stride;
             double lo0 = __ldg(tm + wp.tmm_off[0][0] + 2 * ti);
             if (d0.Tb) lo0 = lo0 + __ldg(tm + wp.tmm_off[0][1] + 2 * ti);
             double lo1 = __ldg(tm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? ti : tj));
@@ -550,13 +552,13 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
             r0 -= (r0 - d0.ext_lo) & 1;                              // TMA: even innermost coordinate
             org[c] = c0 * W0 + r0;
             mbar_expect_tx(&mbar, (uint32_t)(wp.win0 * wp.win1) * 8u);
-            tma_load_3d(ring + (size_t)c * wp.buf_doubles, &tmap, &mbar, r0 - d0.ext_lo, c0 - d1.ext_lo, prob);
+            tma_load_3d(ring + (uint32_t)(c * wp.buf_doubles), &tmap, &mbar, r0 - d0.ext_lo, c0 - d1.ext_lo, (int)prob);
         }
     }
 
     // row constants of this thread
     const int i = min(i_lo + lane, i_hi - 1);
-    const double2 *rpk = reinterpret_cast<const double2 *>(wp.rowpack + (size_t)prob * n0 + i);
+    const double2 *rpk = reinterpret_cast<const double2 *>(wp.rowpack + (prob * (uint32_t)n0 + (uint32_t)i));
     const double2 rp01 = __ldg(rpk);
     const double qrow = __ldg(reinterpret_cast<const double *>(rpk + 1));
     double t0[CC], rc[CC];
@@ -568,15 +570,12 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     }
     const int jb = j_lo + wrp * R;
     const int jcnt = min(R, j_hi - jb);                  // warp-uniform; <= 0 for a ragged last tile
-    const double2 *cq = wp.colq + (size_t)prob * n1 + jb;
+    const double2 *cq = wp.colq + (prob * (uint32_t)n1 + (uint32_t)jb);
     double2 cd = jcnt > 0 ? __ldg(cq) : make_double2(0.0, 0.0);
     const bool row_ok = i_lo + lane < i_hi;
-    double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
-                 (long long)(jb - d1.ext_lo) * d1.stride;
-    int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
-                  (long long)(jb - d1.own_lo) * d0.own_n;
-    const long long sj = d1.stride;
-    const long long si = d0.own_n;
+    const uint32_t sj = (uint32_t)d1.stride, si = (uint32_t)d0.own_n;
+    uint32_t jo = prob * (uint32_t)sp.S_ext + (uint32_t)(i - d0.ext_lo) * (uint32_t)d0.stride + (uint32_t)(jb - d1.ext_lo) * sj;
+    uint32_t io = prob * (uint32_t)sp.S_own + (uint32_t)(i - d0.own_lo) + (uint32_t)(jb - d1.own_lo) * si;
 
     __syncthreads();          // org[] and the mbarrier are visible
     mbar_wait(&mbar, 0);
@@ -592,6 +591,7 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     uint32_t pc[CC];
 #pragma unroll
     for (int c = 0; c < CC; ++c) pc[c] = base + 8u * (uint32_t)(c * wp.buf_doubles + (cell0[c] - org[c]));
+
 
     // dimension-0 lerp of one window column for every control
     auto column = [&](uint32_t o, double (&a)[CC]) {
@@ -624,9 +624,9 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
             if (tot < best) { best = tot; arg = c; }
         }
         if (row_ok) {
-            *jo = best;
-            *io = arg;
-            if (PEER) { const int gi[2] = {i, jb + mm}; peer_store<2>(sp, prob, gi, best); }
+            sp.J_out[jo] = best;
+            sp.idx_out[io] = arg;
+            if (PEER) { const int gi[2] = {i, jb + mm}; peer_store<2>(sp, (int)prob, gi, best); }
         }
         jo += sj;
         io += si;
@@ -659,8 +659,8 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
             step(bhi, ahi);         // registers ping-pong, no copies
         }
         if (!__any_sync(0xffffffffu, bad)) return;
-        jo -= (long long)R * sj;
-        io -= (long long)R * si;
+        jo -= (uint32_t)R * sj;
+        io -= (uint32_t)R * si;
         m = 0;
     }
     // generic columns: both window columns are read
@@ -1045,7 +1045,9 @@ void window_setup(bellman_handle *h) {
         if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
     }
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { window_teardown_state(ws); return; }
-    ws->strip = strip_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1 && !wp.col1_zero;
+    ws->strip = strip_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1 && !wp.col1_zero &&
+                (uint64_t)hp.P * (uint64_t)h->S_ext < (1ull << 31) && wp.ntile0 <= 65535 && wp.ntile1 <= 65535 &&
+                hp.P <= 65535;
     if (ws->strip) {
         ws->strip_nw = strip_nw;
         ws->lean_smem = (size_t)wp.nchunks * slot_bytes(wp.win0, wp.win1);
@@ -1080,7 +1082,10 @@ cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     const WindowParams &wp = ws->wp;
     const dim3 grid((unsigned)(wp.ntile0 * wp.ntile1), (unsigned)sp.P);
     const CUtensorMap &map = ws->maps[slot_next];
-    if (ws->strip) strip_dispatch(ws, &sp, &map, grid, st, false);
+    if (ws->strip) {
+        const dim3 g3(wp.tj_fastest ? wp.ntile1 : wp.ntile0, wp.tj_fastest ? wp.ntile0 : wp.ntile1, (unsigned)sp.P);
+        strip_dispatch(ws, &sp, &map, g3, st, false);
+    }
     else if (ws->lean) k_stage_chain<4, 4><<<grid, WNT, ws->lean_smem, st>>>(sp, wp, map);
     else window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
     return cudaGetLastError();
