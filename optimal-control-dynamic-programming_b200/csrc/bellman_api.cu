@@ -181,7 +181,8 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
         h->slabs.assign(1, bellman_slab{0, 0, 0, 0});
     }
     h->S_ext = 1; h->S_own = 1;
-    h->ld0 = (h->part_dim == 0) ? ((h->ext_n[0] + 1) & ~1) : h->ext_n[0];
+    // D = 2 grids (the TMA-staged kernels) and dimension-0 slabs keep an even leading dimension
+    h->ld0 = (hp.D == 2 || h->part_dim == 0) ? ((h->ext_n[0] + 1) & ~1) : h->ext_n[0];
     for (int k = 0; k < hp.D; ++k) {
         h->stride[k] = h->S_ext;
         h->S_ext *= (k == 0) ? h->ld0 : h->ext_n[k];
@@ -294,6 +295,13 @@ static int upload_J(bellman_handle *h, int stage, const double *J_host) {
         const size_t S = (size_t)hp.S();
         for (int pr = 0; pr < hp.P; ++pr) {
             const double *src = J_host + (size_t)pr * S + (size_t)h->ext_lo[p] * inner;
+            if (p >= 1 && h->ld0 != hp.n[0]) {
+                // padded leading dimension (D = 2, slab along dimension 1): copy row by row
+                CUDA_TRY(h, cudaMemcpy2DAsync(dst + (size_t)pr * h->S_ext, (size_t)h->ld0 * 8, src, (size_t)hp.n[0] * 8,
+                                              (size_t)hp.n[0] * 8, (size_t)h->ext_n[p], cudaMemcpyHostToDevice,
+                                              h->stream));
+                continue;
+            }
             CUDA_TRY(h, cudaMemcpy2DAsync(dst + (size_t)pr * h->S_ext, (size_t)h->row_elems(p) * 8, src,
                                           (size_t)hp.n[p] * inner * 8, (size_t)h->ext_n[p] * inner * 8,
                                           (size_t)outer, cudaMemcpyHostToDevice, h->stream));
@@ -351,6 +359,12 @@ extern "C" int bellman_get_J(bellman_handle *h, int32_t stage, double *out) {
     const int p = h->part_dim < 0 ? hp.D - 1 : h->part_dim;
     const double *src0 = h->J_ptr(stage);
     for (int pr = 0; pr < hp.P; ++pr) {
+        if (p >= 1 && h->ld0 != hp.n[0]) {   // padded leading dimension: row by row
+            const double *srcp = src0 + (size_t)pr * h->S_ext + (size_t)(h->own_lo[p] - h->ext_lo[p]) * h->ld0;
+            CUDA_TRY(h, cudaMemcpy2DAsync(out + (size_t)pr * h->S_own, (size_t)hp.n[0] * 8, srcp, (size_t)h->ld0 * 8,
+                                          (size_t)hp.n[0] * 8, (size_t)h->own_n[p], cudaMemcpyDeviceToHost, h->stream));
+            continue;
+        }
         const double *src = src0 + (size_t)pr * h->S_ext + (size_t)(h->own_lo[p] - h->ext_lo[p]) * inner;
         CUDA_TRY(h, cudaMemcpy2DAsync(out + (size_t)pr * h->S_own, (size_t)h->own_n[p] * inner * 8, src,
                                       (size_t)h->row_elems(p) * 8, (size_t)h->own_n[p] * inner * 8,
@@ -507,6 +521,7 @@ static int exchange_halo(bellman_handle *h, int stage) {
     double *J = h->J_ptr(stage);
     const bellman_slab &me = h->slabs[h->rank];
     const long long row = h->row_elems(p);   // stored elements per outer index
+    if (p >= 1) inner = inner / hp.n[0] * h->ld0;   // device stride of one index along p (leading dim may be padded)
     ncclResult_t r = api->GroupStart();
     for (int q = 0; q < h->nranks && r == ncclSuccess; ++q) {
         if (q == h->rank) continue;
@@ -580,7 +595,7 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
     CUDA_TRY(h, cudaSetDevice(h->device));
     int lanes = 1;
     const int kernel = pick_kernel(h, o.kernel, lanes);
-    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? "window" : kernel == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
+    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? window_variant(h) : kernel == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
     h->last_launches = 0;
     h->last_ms_exchange = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xev;

@@ -18,12 +18,12 @@ struct bellman_handle {
     std::vector<bellman_slab> slabs;
     int own_n[bellman::MAXD], own_lo[bellman::MAXD], ext_lo[bellman::MAXD], ext_n[bellman::MAXD];
     long long stride[bellman::MAXD];
-    // leading dimension of the J arrays (elements): ext_n[0], rounded up to even when dimension 0
-    // is the partitioned one so that TMA's 16-byte stride rule holds for any slab width
+    // leading dimension of the J arrays (elements): ext_n[0], rounded up to even for D = 2 grids and
+    // for dimension-0 slabs so that TMA's 16-byte stride rule holds for any grid / slab width
     int ld0 = 1;
     long long row_elems(int p) const {   // stored elements per outer index of a slab along dim p
         long long inner = 1;
-        for (int k = 0; k < p; ++k) inner *= hp.n[k];
+        for (int k = 0; k < p; ++k) inner *= (k == 0 ? ld0 : hp.n[k]);
         return p == 0 ? (long long)ld0 : (long long)ext_n[p] * inner;
     }
     long long S_ext = 0, S_own = 0;
@@ -73,6 +73,8 @@ namespace bellman {
 // tensor map per J slot).  Leaves wcfg.valid = false when the problem does not qualify.
 void window_setup(bellman_handle *h);
 void window_teardown(bellman_handle *h);
+// "window:strip" / "window:chain" / "window:ring-chain" / "window:ring": which TMA-staged kernel runs
+const char *window_variant(const bellman_handle *h);
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next,
                                      cudaStream_t st);
 }  // namespace bellman

@@ -114,6 +114,19 @@ __device__ __forceinline__ double cell_to_double(int cell) {
 }
 // XUCVT: take (double)cell from the conversion pipe (I2F.F64) instead of the fp64 pipe.  The hot
 // loop uses one of each per update so that neither pipe carries both conversions.
+// locate_magic: floor on the fp64 pipe for queries known to be interior (|g| < 2^31, no clamp).
+// M = 2^52 + 2^51: g + M rounded toward -inf is floor(g) + M exactly (ulp 1 in [2^52, 2^53)), its low
+// word is floor(g) in two's complement, and (g + M) - M is floor(g) as a double, exactly — so
+// t = g - floor(g) is the same exact difference the conversion path forms.  Three DADDs (64
+// lanes/clk/SM) instead of F2I + I2F (16 lanes/clk/SM each, issued through the same MIO queue as the
+// shared-memory loads).
+__device__ __forceinline__ int locate_magic(double g, double &t) {
+    const double M = 6755399441055744.0;
+    const double s = __dadd_rd(g, M);
+    t = g - (s - M);
+    return __double2loint(s);
+}
+
 template <bool CLAMP = true, bool XUCVT = false>
 __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
     int cell = __double2int_rd(g);
@@ -132,7 +145,9 @@ __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
 // 18 shared-memory loads and ~61 fp64 instructions per 8 updates instead of 32 and ~120.
 // W0C: the window pitch (rows per column) as a compile-time constant when it is one of the common
 // values (0 = read it from the parameters); turns the second-column offset into an immediate.
-template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int WR_STATES, int W0C = 0>
+// LOC: how the interior (unclamped) control loop locates — 0: dim 0 F2I + bit-trick, dim 1 F2I + I2F;
+// 1: dim 0 on the fp64 pipe (locate_magic), dim 1 F2I + I2F; 2: both on the fp64 pipe.
+template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int WR_STATES, int W0C = 0, int LOC = 0>
 __global__ void __launch_bounds__(WNT, OCC)
 k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
                const __grid_constant__ CUtensorMap tmap) {
@@ -293,9 +308,11 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
                 for (int u = 0; u < BATCH; ++u) {
                     const int m = mb + u;
                     int cell0, cell1;
-                    if (HC0) cell0 = locate_uniform<CLAMP>(base0[m] + bu0, n0, t0[u]);
+                    if (HC0) cell0 = (!CLAMP && LOC >= 1) ? locate_magic(base0[m] + bu0, t0[u])
+                                                          : locate_uniform<CLAMP>(base0[m] + bu0, n0, t0[u]);
                     else { cell0 = cellK0[m]; t0[u] = tK0[m]; }
-                    if (HC1) cell1 = locate_uniform<CLAMP, true>(base1[m] + bu1, n1, t1[u]);
+                    if (HC1) cell1 = (!CLAMP && LOC >= 2) ? locate_magic(base1[m] + bu1, t1[u])
+                                                          : locate_uniform<CLAMP, true>(base1[m] + bu1, n1, t1[u]);
                     else { cell1 = cellK1[m]; t1[u] = tK1[m]; }
                     off[u] = cell1 * W0 + cell0;      // Wb already carries the window origin
                 }
@@ -700,7 +717,7 @@ struct WindowState {
     size_t lean_smem = 0;
     int strip_nw = 4;
     void *d_colq = nullptr;
-    int batch = 4, occ = 2, rstates = 8;
+    int batch = 4, occ = 2, rstates = 8, loc = 0;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
 
@@ -718,11 +735,16 @@ static bool window_go(const WindowState *ws, const StageParams *sp, const CUtens
                       cudaStream_t st, bool set_attr_only) {
     if (HC0 && HC1 && BATCH == 4 && OCC == 2 && R == 8) {   // the long-control-loop kernel: pitch 48 specialisation
         auto fn48 = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48>;
+        auto fn48a = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48, 1>;
+        auto fn48b = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48, 2>;
         if (set_attr_only) {
-            if (cudaFuncSetAttribute((const void *)fn48, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) != cudaSuccess)
-                return false;
+            for (const void *f : {(const void *)fn48, (const void *)fn48a, (const void *)fn48b})
+                if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) != cudaSuccess)
+                    return false;
         } else if (ws->wp.win0 == 48) {
-            fn48<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+            if (ws->loc == 2) fn48b<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+            else if (ws->loc == 1) fn48a<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+            else fn48<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
             return true;
         }
     }
@@ -1043,6 +1065,8 @@ void window_setup(bellman_handle *h) {
         ws->occ = eo ? std::atoi(eo) : 2;
         if (ws->batch != 2 && ws->batch != 4 && ws->batch != 8) ws->batch = 4;
         if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
+        ws->loc = 2;
+        if (const char *el = std::getenv("BELLMAN_WIN_LOC")) ws->loc = std::atoi(el);
     }
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { window_teardown_state(ws); return; }
     ws->strip = strip_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1 && !wp.col1_zero &&
@@ -1074,6 +1098,12 @@ void window_teardown(bellman_handle *h) {
     if (!ws) return;
     window_teardown_state(ws);
     h->wstate = nullptr;
+}
+
+const char *window_variant(const bellman_handle *h) {
+    auto *ws = static_cast<const WindowState *>(h->wstate);
+    if (!ws) return "window";
+    return ws->strip ? "window:strip" : ws->lean ? "window:chain" : ws->chain ? "window:ring-chain" : "window:ring";
 }
 
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st) {

@@ -76,7 +76,7 @@ def test_kirk_reference_size_first_stages(bellman, oracle_lib, kernel):
     ora = oracle_lib.sweep(d, n_stages=6, keep_all=True)
     sw = bellman.Sweep(d).run(6, kernel=KERNELS[kernel])
     if kernel != "auto":
-        assert sw.last_kernel == kernel
+        assert sw.last_kernel.split(":")[0] == kernel
     for k in range(d.N - 6, d.N):
         assert_stage_equal(sw.get_J(k), sw.get_idx(k), ora["J_all"][k - 1], ora["idx_all"][k - 1], f"stage {k}")
     sw.close()
@@ -100,7 +100,7 @@ def test_window_kernel_random_terminal_cost(bellman, oracle_lib, shape):
     sw = bellman.Sweep(d)
     sw.set_J(JN)
     sw.run(4, kernel=KERNELS["window"])
-    assert sw.last_kernel == "window"
+    assert sw.last_kernel.split(":")[0] == "window"
     ora = oracle_lib.sweep(d, n_stages=4, J_N=JN)
     assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"window {shape}")
     sw.close()
@@ -155,7 +155,7 @@ def test_attitude_reference_size(bellman, oracle_lib):
     ora = oracle_lib.sweep(d, n_stages=12)
     for kernel in ("direct", "window"):
         sw = bellman.Sweep(d).run(12, kernel=KERNELS[kernel])
-        assert sw.last_kernel == kernel
+        assert sw.last_kernel.split(":")[0] == kernel
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "attitude " + kernel)
         sw.close()
 
@@ -331,7 +331,7 @@ def test_window_kernel_multi_stage_medium(bellman, oracle_lib):
                Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
                q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u)).validate()
     sw = bellman.Sweep(d).run(3)
-    assert sw.last_kernel == "window"
+    assert sw.last_kernel.split(":")[0] == "window"
     ora = oracle_lib.sweep(d, n_stages=3)
     assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "window 1024x768x64")
     sw.close()
@@ -349,7 +349,7 @@ def test_attitude_x4_full_size_spot_check(bellman, oracle_lib):
     sw = bellman.Sweep(d)
     sw.set_J(JN)
     sw.run(1)
-    assert sw.last_kernel == "window"
+    assert sw.last_kernel.split(":")[0] == "window"
     J1, I1 = sw.get_J(), sw.get_idx()
     sw.run(1)
     J2, I2 = sw.get_J(), sw.get_idx()
@@ -458,7 +458,7 @@ def test_pos_att_controller_file_round_trip(bellman, oracle_lib, tmp_path):
 
 
 @pytest.mark.gpu
-def test_resume_from_saved_stage(bellman, oracle_lib):
+def test_set_stage_resume_and_errors(bellman, oracle_lib):
     """bellman_set_stage: J of stage k put back on a fresh handle continues to the same bits."""
     d = bellman.tables.kirk_desc([[0.9974, 0.0539], [-0.1078, 1.1591]], [0.0013, 0.0539], [[0.25, 0.0], [0.0, 0.05]],
                                  0.05, 20, -2.5, 3.0, 48, -40.0, 10.0, 40, store_J_all=False, store_idx_all=False)
@@ -498,3 +498,23 @@ def test_dynamic_solver_archive_and_compare_data(bellman, golden, tmp_path):
         bellman.Dynamic_Solver.compare_data(bellman.Dynamic_Solver(), b)
     # the archive agrees with the reference's own saved run: u_star exact, J_star within 1e-12
     assert np.array_equal(b.u_star[:, :, :golden["N"] - 1], golden["u_star"][:, :, :golden["N"] - 1])
+
+
+@pytest.mark.parametrize("shape", [(77, 45, 3), (130, 37, 2), (64, 64, 4), (33, 9, 3), (200, 150, 1)])
+def test_strip_kernel_ragged_random(bellman, oracle_lib, shape):
+    """k_stage_strip (attitude-type problems, <= 4 controls): ragged tiles, clamped edges, rough J,
+    three stacked axes with different ranges, several stages."""
+    t = bellman.tables
+    rng = np.random.default_rng(shape[0])
+    n_w, n_t, C = shape
+    U = np.linspace(-0.11, 0.11, C) if C > 1 else np.array([0.05])
+    descs = [t.attitude_axis_desc(-0.9, 0.9, n_w, -ang, ang, n_t, U, J, 6.0, 6.0, 4.0, 0.02, 6)
+             for ang, J in ((30.0, 0.0285), (20.0, 0.0283), (35.0, 0.0245))]
+    d = t.stack_problems(descs)
+    JN = rng.normal(size=(3, d.S)) * 3
+    ora = oracle_lib.sweep(d, n_stages=4, J_N=JN)
+    with bellman.Sweep(d) as sw:
+        sw.set_J(JN)
+        sw.run(4, kernel=KERNELS["window"])
+        assert sw.last_kernel == "window:strip"
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"strip {shape}")
