@@ -90,7 +90,9 @@ typedef enum bellman_status {
 
 enum { BELLMAN_LOCATE_UNIFORM = 0, BELLMAN_LOCATE_SEARCH = 1 };
 enum { BELLMAN_KERNEL_AUTO = 0, BELLMAN_KERNEL_DIRECT = 1, BELLMAN_KERNEL_WINDOW = 2,
-       BELLMAN_KERNEL_SPLITC = 3 };
+       BELLMAN_KERNEL_SPLITC = 3, BELLMAN_KERNEL_TILE = 4 };
+/* WINDOW and TILE both ask for the TMA-staged kernel of the problem's dimensionality (D = 2: the
+   window kernels; D = 3 / 4: the tile kernel) and fall back to DIRECT when it does not apply. */
 
 typedef struct bellman_handle bellman_handle;
 
@@ -190,7 +192,7 @@ int  bellman_owned_range(const bellman_handle *h, bellman_slab *out);
    total ms, number of stage-kernel launches, and ms spent in halo exchange */
 int  bellman_last_run_stats(const bellman_handle *h, double *ms_total, int64_t *kernel_launches,
                             double *ms_exchange);
-/* name of the stage kernel the last run used: "direct", "splitc", "persistent", or "window:<variant>"
+/* name of the stage kernel the last run used: "direct", "splitc", "persistent", "tile", or "window:<variant>"
    (variant = strip | chain | ring-chain | ring, the TMA-staged D = 2 kernels) */
 const char *bellman_last_kernel(const bellman_handle *h);
 

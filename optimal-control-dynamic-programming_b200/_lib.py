@@ -14,7 +14,7 @@ MAXD = 4
 _dp = C.POINTER(C.c_double)
 _ip = C.POINTER(C.c_int32)
 
-KERNEL_AUTO, KERNEL_DIRECT, KERNEL_WINDOW, KERNEL_SPLITC = 0, 1, 2, 3
+KERNEL_AUTO, KERNEL_DIRECT, KERNEL_WINDOW, KERNEL_SPLITC, KERNEL_TILE = 0, 1, 2, 3, 4
 LOCATE_UNIFORM, LOCATE_SEARCH = 0, 1
 
 STATUS = {0: "OK", -1: "BAD_ARG", -2: "CUDA", -3: "NCCL", -4: "OOM", -5: "NOT_RUN", -6: "STATE"}

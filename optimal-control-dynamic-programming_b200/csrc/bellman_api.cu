@@ -234,6 +234,7 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
     rc = bellman_set_J(h, nullptr);
     if (rc != BELLMAN_OK) return fail(rc);
     window_setup(h);   // optional fast path; leaves wcfg.valid = false when it does not apply
+    tile_setup(h);     // D = 3 / 4 counterpart
     *out = h;
     return BELLMAN_OK;
 }
@@ -256,6 +257,7 @@ extern "C" void bellman_destroy(bellman_handle *h) {
     cudaFree(h->d_tab); cudaFree(h->d_mode); cudaFree(h->d_J); cudaFree(h->d_idx);
     cudaFree(h->d_partials); cudaFree(h->d_sums);
     window_teardown(h);
+    tile_teardown(h);
     for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -559,9 +561,11 @@ static int pick_kernel(bellman_handle *h, int requested, int &lanes) {
         return L;
     };
     if (requested == BELLMAN_KERNEL_SPLITC) { lanes = std::max(2, pick_lanes()); return BELLMAN_KERNEL_SPLITC; }
-    if (requested == BELLMAN_KERNEL_WINDOW) return h->wcfg.valid ? BELLMAN_KERNEL_WINDOW : BELLMAN_KERNEL_DIRECT;
+    if (requested == BELLMAN_KERNEL_WINDOW || requested == BELLMAN_KERNEL_TILE)   // the TMA-staged kernels
+        return h->wcfg.valid ? BELLMAN_KERNEL_WINDOW : tile_valid(h) ? BELLMAN_KERNEL_TILE : BELLMAN_KERNEL_DIRECT;
     // AUTO
     if (h->wcfg.valid && states >= 148LL * 2048) return BELLMAN_KERNEL_WINDOW;
+    if (tile_valid(h) && states >= 148LL * 2048) return BELLMAN_KERNEL_TILE;
     lanes = pick_lanes();
     return lanes > 1 ? BELLMAN_KERNEL_SPLITC : BELLMAN_KERNEL_DIRECT;
 }
@@ -576,6 +580,7 @@ static int launch_one_stage(bellman_handle *h, int kernel, int lanes) {
     cudaError_t e;
     if (kernel == BELLMAN_KERNEL_SPLITC) e = launch_stage_splitc(sp, lanes, h->stream);
     else if (kernel == BELLMAN_KERNEL_WINDOW) e = window_launch_for_handle(h, sp, h->J_slot(from), h->stream);
+    else if (kernel == BELLMAN_KERNEL_TILE) e = tile_launch_for_handle(h, sp, h->J_slot(from), h->stream);
     else e = launch_stage_direct(sp, h->stream);
     if (e != cudaSuccess) { h->err = std::string("stage launch: ") + cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
     h->last_launches += 1;
@@ -595,7 +600,8 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
     CUDA_TRY(h, cudaSetDevice(h->device));
     int lanes = 1;
     const int kernel = pick_kernel(h, o.kernel, lanes);
-    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? window_variant(h) : kernel == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
+    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? window_variant(h) : kernel == BELLMAN_KERNEL_TILE ? "tile"
+                     : kernel == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
     h->last_launches = 0;
     h->last_ms_exchange = 0.0;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> xev;

@@ -49,6 +49,7 @@ struct bellman_handle {
     // window kernel state
     bellman::WindowConfig wcfg;
     void *wstate = nullptr;           // bellman_window.cu: WindowState (tensor maps, chunk tables)
+    void *tstate = nullptr;           // bellman_tile.cu: TileState (D = 3 / 4 TMA-staged tile kernel)
     // cached 2-stage CUDA graphs (ping-pong storage has period 2), keyed by the parity of the
     // slot the first stage reads and by the kernel variant
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
@@ -73,6 +74,12 @@ namespace bellman {
 // tensor map per J slot).  Leaves wcfg.valid = false when the problem does not qualify.
 void window_setup(bellman_handle *h);
 void window_teardown(bellman_handle *h);
+// bellman_tile.cu: the D = 3 / 4 tile kernel (one TMA box per state tile); tstate stays null when
+// the problem is not a narrow stencil
+void tile_setup(bellman_handle *h);
+void tile_teardown(bellman_handle *h);
+bool tile_valid(const bellman_handle *h);
+cudaError_t tile_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st);
 // "window:strip" / "window:chain" / "window:ring-chain" / "window:ring": which TMA-staged kernel runs
 const char *window_variant(const bellman_handle *h);
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next,

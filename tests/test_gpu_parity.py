@@ -8,7 +8,7 @@ from conftest import to_grid
 
 pytestmark = pytest.mark.gpu
 
-KERNELS = {"direct": 1, "splitc": 3, "auto": 0, "window": 2}
+KERNELS = {"direct": 1, "splitc": 3, "auto": 0, "window": 2, "tile": 4}
 
 
 def golden_desc(bellman, g):
@@ -518,3 +518,56 @@ def test_strip_kernel_ragged_random(bellman, oracle_lib, shape):
         sw.run(4, kernel=KERNELS["window"])
         assert sw.last_kernel == "window:strip"
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"strip {shape}")
+
+
+@pytest.mark.parametrize("failure", [False, True])
+def test_tile_kernel_pos_att_reference_size(bellman, oracle_lib, failure):
+    """k_stage_tile (TMA box per 4-D state tile) on config 5 at the reference's own size (30x30x20x15 x 9)."""
+    sp = bellman.Solver_pos_att()
+    d = sp.channel_desc(0, failure=failure)
+    ora = oracle_lib.sweep(d, n_stages=6)
+    with bellman.Sweep(d) as sw:
+        sw.run(6, kernel=KERNELS["tile"])
+        assert sw.last_kernel == "tile"
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "pos-att tile")
+
+
+@pytest.mark.parametrize("mesh", [(34, 9, 7, 5), (10, 8, 6, 4), (66, 3, 2, 9), (64, 16, 8, 8)])
+def test_tile_kernel_ragged_random(bellman, oracle_lib, mesh):
+    """ragged tiles in every dimension, clamped edges, rough terminal cost, all three channels, D = 4 and D = 3."""
+    t = bellman.tables
+    rng = np.random.default_rng(mesh[0])
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = mesh
+    for ch in range(3):
+        d = sp.channel_desc(ch)
+        JN = rng.normal(size=(1, d.S)) * 2
+        ora = oracle_lib.sweep(d, n_stages=3, J_N=JN)
+        with bellman.Sweep(d) as sw:
+            sw.set_J(JN)
+            sw.run(3, kernel=KERNELS["tile"])
+            assert sw.last_kernel == "tile"
+            assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"tile {mesh} ch{ch}")
+    d4 = sp.channel_desc(2)
+    d3 = t.Desc(n=d4.n[:3], C=d4.C, N=6, grid=d4.grid[:3], src_a=[0, 1, 2], src_b=[1, -1, -1],
+                Ta=d4.Ta[:3], Tb=[d4.Tb[0], None, None], Tc=[None, d4.Tc[1], d4.Tc[3]],
+                q_order=[2, 0, 1], q=d4.q[:3], r=d4.r).validate()
+    JN = rng.normal(size=(1, d3.S))
+    ora = oracle_lib.sweep(d3, n_stages=3, J_N=JN)
+    with bellman.Sweep(d3) as sw:
+        sw.set_J(JN)
+        sw.run(3, kernel=KERNELS["tile"])
+        assert sw.last_kernel == "tile"
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"tile D=3 {mesh}")
+
+
+def test_tile_kernel_falls_back_when_not_a_stencil(bellman, oracle_lib):
+    """odd leading dimension (TMA stride rule) -> the request for the staged kernel runs the direct kernel."""
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 9, 8, 7, 5
+    d = sp.channel_desc(1)
+    ora = oracle_lib.sweep(d, n_stages=2)
+    with bellman.Sweep(d) as sw:
+        sw.run(2, kernel=KERNELS["tile"])
+        assert sw.last_kernel == "direct"
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "tile fallback")
