@@ -301,6 +301,144 @@ k_stage_tile(const __grid_constant__ StageParams sp, const __grid_constant__ Til
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// k_stage_tile_pa: the tile kernel specialised for the structure of Solver_pos_att's channel
+// (pos-att/Solver_pos_att.m:299-328): two coupled (position, rate) blocks,
+//     x'_0 = Ta_0[i0] + Tb_0[i1]      (control independent)      x'_1 = Ta_1[i1] + Tc_1[c]   (table)
+//     x'_2 = Ta_2[i2] + Tb_2[i3]      (control independent)      x'_3 = Ta_3[i3] + Tc_3[c]   (table)
+// A warp owns (i2, i3) pairs of the tile and walks i1; lanes run along i0.  What depends on (i2, i3)
+// only — the dimension-2 cell/weight, the dimension-3 table row — is hoisted out of the i1 loop;
+// per state a thread locates dimension 0 once; per (state, control) it reads two table entries
+// {t, box byte offset}, 16 shared-memory corners and does the 15 lerps.  No run-time structure
+// checks inside the loops (k_stage_tile: 229 instructions per update, this kernel: see profiles/).
+// Same operations on the same operands as k_stage_direct ⇒ bit-identical results.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TNT, 2)
+k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ TileParams tp,
+                const __grid_constant__ CUtensorMap tmap) {
+    constexpr int D = 4;
+    extern __shared__ __align__(128) double box[];
+    __shared__ __align__(8) uint64_t mbar;
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const uint32_t prob = blockIdx.z;
+    int ti[D];
+    ti[0] = blockIdx.x % tp.ntile[0];
+    ti[1] = blockIdx.x / tp.ntile[0];
+    ti[2] = blockIdx.y % tp.ntile[2];
+    ti[3] = blockIdx.y / tp.ntile[2];
+    int t_lo[D], t_hi[D], org[D];
+#pragma unroll
+    for (int d = 0; d < D; ++d) {
+        t_lo[d] = sp.dim[d].own_lo + ti[d] * tp.T[d];
+        t_hi[d] = min(t_lo[d] + tp.T[d], sp.dim[d].own_lo + sp.dim[d].own_n);
+        org[d] = t_lo[d] + tp.lo[d];
+    }
+    org[0] -= (org[0] - sp.dim[0].ext_lo) & 1;
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_expect_tx(&mbar, (uint32_t)tp.box_elems * 8u);
+        tma_load_5d(box, &tmap, &mbar, org[0] - sp.dim[0].ext_lo, org[1] - sp.dim[1].ext_lo, org[2] - sp.dim[2].ext_lo,
+                    org[3] - sp.dim[3].ext_lo, (int)prob);
+    }
+
+    const int C = sp.C;
+    const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1], &d2 = sp.dim[2], &d3 = sp.dim[3];
+    const double *rr = sp.r + prob * (uint32_t)C;
+    const int mode0 = __ldg(d0.mode + prob), mode2 = __ldg(d2.mode + prob);
+    const double *g0 = d0.grid + prob * (uint32_t)d0.n, *ri0 = d0.rinv + prob * (uint32_t)d0.n;
+    const double *g2 = d2.grid + prob * (uint32_t)d2.n, *ri2 = d2.rinv + prob * (uint32_t)d2.n;
+
+    // this lane's row (dimension 0): table entries that depend on i0 only
+    const int i0 = min(t_lo[0] + lane, t_hi[0] - 1);
+    const bool row_ok = t_lo[0] + lane < t_hi[0];
+    const double ta0 = __ldg(d0.Ta + prob * (uint32_t)d0.n_a + i0);
+    const double q0 = __ldg(d0.q + prob * (uint32_t)d0.n + i0);
+    const int qo0 = sp.q_order[0], qo1 = sp.q_order[1], qo2 = sp.q_order[2], qo3 = sp.q_order[3];
+
+    // byte offsets of the 8 dimension-0 pairs relative to the base corner
+    uint32_t ro[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        ro[k] = 8u * (uint32_t)((k & 1 ? tp.bstride[1] : 0) + (k & 2 ? tp.bstride[2] : 0) + (k & 4 ? tp.bstride[3] : 0));
+
+    __syncthreads();
+    mbar_wait(&mbar, 0);
+    uint32_t base = smem_u32(box);
+    asm volatile("" : "+r"(base)::"memory");
+    // fold the box origin of every dimension into the base address (table offsets are absolute cells * stride)
+    base -= 8u * (uint32_t)(org[0] * tp.bstride[0] + org[1] * tp.bstride[1] + org[2] * tp.bstride[2] + org[3] * tp.bstride[3]);
+
+    const int n1t = t_hi[1] - t_lo[1];
+    const int npair = tp.T[2] * tp.T[3];
+#pragma unroll 1
+    for (int pq = wrp; pq < npair; pq += TNT / 32) {
+        const int i2 = t_lo[2] + pq % tp.T[2], i3 = t_lo[3] + pq / tp.T[2];
+        if (i2 >= t_hi[2] || i3 >= t_hi[3]) continue;          // warp-uniform: ragged tile
+        // dimension 2 (control independent): located once per pair
+        double b2 = __ldg(d2.Ta + prob * (uint32_t)d2.n_a + i2);
+        if (d2.Tb) b2 = b2 + __ldg(d2.Tb + prob * (uint32_t)d2.n_b + i3);
+        double t2;
+        const int cell2 = locate_near(g2, ri2, d2.n, mode2, i2, b2, t2);
+        const uint32_t off2 = base + 8u * (uint32_t)(cell2 * tp.bstride[2]);
+        const double2 *lt3 = tp.lt[3] + (prob * (uint32_t)d3.n + (uint32_t)i3) * (uint32_t)C;
+        const double q2 = __ldg(d2.q + prob * (uint32_t)d2.n + i2), q3 = __ldg(d3.q + prob * (uint32_t)d3.n + i3);
+        long long jo = (long long)prob * sp.S_ext + (long long)(i0 - d0.ext_lo) * d0.stride +
+                       (long long)(t_lo[1] - d1.ext_lo) * d1.stride + (long long)(i2 - d2.ext_lo) * d2.stride +
+                       (long long)(i3 - d3.ext_lo) * d3.stride;
+        long long io = (long long)prob * sp.S_own + (long long)(i0 - d0.own_lo) * tp.own_stride[0] +
+                       (long long)(t_lo[1] - d1.own_lo) * tp.own_stride[1] + (long long)(i2 - d2.own_lo) * tp.own_stride[2] +
+                       (long long)(i3 - d3.own_lo) * tp.own_stride[3];
+#pragma unroll 1
+        for (int j1 = 0; j1 < n1t; ++j1) {
+            const int i1 = t_lo[1] + j1;
+            // dimension 0 (control independent, lane specific)
+            double b0 = ta0;
+            if (d0.Tb) b0 = b0 + __ldg(d0.Tb + prob * (uint32_t)d0.n_b + i1);
+            double t0;
+            const int cell0 = locate_near(g0, ri0, d0.n, mode0, i0, b0, t0);
+            const uint32_t off02 = off2 + 8u * (uint32_t)cell0;          // bstride[0] = 1
+            const double2 *lt1 = tp.lt[1] + (prob * (uint32_t)d1.n + (uint32_t)i1) * (uint32_t)C;
+            // stage cost of the state: q terms summed in q_order
+            const double q1 = __ldg(d1.q + prob * (uint32_t)d1.n + i1);
+            auto qsel = [&](int o) { return o == 0 ? q0 : o == 1 ? q1 : o == 2 ? q2 : q3; };
+            const double gs = ((qsel(qo0) + qsel(qo1)) + qsel(qo2)) + qsel(qo3);
+
+            double best = __longlong_as_double(0x7ff0000000000000LL);
+            int arg = 0;
+#pragma unroll 3
+            for (int c = 0; c < C; ++c) {
+                const double2 e1 = __ldg(lt1 + c), e3 = __ldg(lt3 + c);
+                const uint32_t o = off02 + (uint32_t)__double2loint(e1.y) + (uint32_t)__double2loint(e3.y);
+                double v[16];
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    v[2 * k] = lds_f64(o + ro[k]);
+                    v[2 * k + 1] = lds_f64(o + ro[k] + 8);
+                }
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = fma(t0, v[2 * m + 1] - v[2 * m], v[2 * m]);      // dimension 0 first
+#pragma unroll
+                for (int m = 0; m < 4; ++m) v[m] = fma(e1.x, v[2 * m + 1] - v[2 * m], v[2 * m]);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) v[m] = fma(t2, v[2 * m + 1] - v[2 * m], v[2 * m]);
+                const double val = fma(e3.x, v[1] - v[0], v[0]);
+                const double tot = (gs + __ldg(rr + c)) + val;
+                if (tot < best) { best = tot; arg = c; }
+            }
+            if (row_ok) {
+                sp.J_out[jo] = best;
+                sp.idx_out[io] = arg;
+                if (sp.n_peers) { const int gi[4] = {i0, i1, i2, i3}; peer_store<4>(sp, (int)prob, gi, best); }
+            }
+            jo += d1.stride;
+            io += tp.own_stride[1];
+        }
+    }
+}
+
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                     const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
                                     CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -318,6 +456,7 @@ PFN_encodeTiled get_encode() {
 }
 
 struct TileState {
+    bool pa = false;                 // k_stage_tile_pa applies (table entries hold box byte offsets)
     TileParams tp{};
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
@@ -436,6 +575,14 @@ void tile_setup(bellman_handle *h) {
     for (int d = 0; d < D; ++d)
         if (tp.box[d] > 256) { delete ts; return; }
 
+    // structure of Solver_pos_att's channel: dims 0 / 2 control independent with Tb from dims 1 / 3
+    // (or absent), dims 1 / 3 control dependent on their own index only
+    ts->pa = D == 4 && !std::getenv("BELLMAN_TILE_GENERIC");
+    for (int d = 0; d < D && ts->pa; ++d) {
+        if (hp.src_a[d] != d) ts->pa = false;
+        if (d % 2 == 0 && (hp.has_c[d] || (hp.has_b[d] && hp.src_b[d] != d + 1))) ts->pa = false;
+        if (d % 2 == 1 && (!hp.has_c[d] || (hp.has_b[d] && hp.src_b[d] != d))) ts->pa = false;
+    }
     // locate tables of the (own index, control) dimensions, built with the normative operations
     // (this file is compiled with -ffp-contract=off on the host side: one rounding per operation)
     for (int d = 0; d < MAXD; ++d) tp.lt[d] = nullptr;
@@ -454,7 +601,8 @@ void tile_setup(bellman_handle *h) {
                     const int cell = host_locate(hp, p, d, xq);
                     const double t = uni ? xq - (double)cell : (xq - sgrid[cell]) * ri[cell];
                     double cb;
-                    const long long bits = (long long)(unsigned int)cell;
+                    // generic kernel: the cell; pos-att kernel: its byte offset inside the box
+                    const long long bits = (long long)(unsigned int)(ts->pa ? cell * tp.bstride[d] * 8 : cell);
                     std::memcpy(&cb, &bits, 8);
                     tab[(((size_t)p * nd + i) * hp.C + c) * 2] = t;
                     tab[(((size_t)p * nd + i) * hp.C + c) * 2 + 1] = cb;
@@ -469,8 +617,8 @@ void tile_setup(bellman_handle *h) {
         tp.lt[d] = static_cast<const double2 *>(ts->d_lt[d]);
     }
     if (std::getenv("BELLMAN_TILE_DEBUG"))
-        std::fprintf(stderr, "bellman tile: T = %d %d %d %d, stencil lo = %d %d %d %d hi = %d %d %d %d, box = %d %d %d %d (%zu KB), tables = %d%d%d%d\n",
-                     tp.T[0], tp.T[1], tp.T[2], tp.T[3], lo[0], lo[1], lo[2], lo[3], hi[0], hi[1], hi[2], hi[3], tp.box[0],
+        std::fprintf(stderr, "bellman tile%s: T = %d %d %d %d, stencil lo = %d %d %d %d hi = %d %d %d %d, box = %d %d %d %d (%zu KB), tables = %d%d%d%d\n",
+                     ts->pa ? " (pos-att kernel)" : "", tp.T[0], tp.T[1], tp.T[2], tp.T[3], lo[0], lo[1], lo[2], lo[3], hi[0], hi[1], hi[2], hi[3], tp.box[0],
                      tp.box[1], tp.box[2], tp.box[3], ts->smem / 1024, tp.lt[0] != nullptr, tp.lt[1] != nullptr,
                      tp.lt[2] != nullptr, tp.lt[3] != nullptr);
 
@@ -490,7 +638,7 @@ void tile_setup(bellman_handle *h) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete ts; return; }
     }
-    const void *fn = D == 4 ? (const void *)k_stage_tile<4> : (const void *)k_stage_tile<3>;
+    const void *fn = ts->pa ? (const void *)k_stage_tile_pa : D == 4 ? (const void *)k_stage_tile<4> : (const void *)k_stage_tile<3>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts->smem) != cudaSuccess) {
         delete ts;
         return;
@@ -505,7 +653,8 @@ cudaError_t tile_launch_for_handle(bellman_handle *h, const StageParams &sp, int
     if (!ts) return cudaErrorNotSupported;
     const TileParams &tp = ts->tp;
     const dim3 grid((unsigned)(tp.ntile[0] * tp.ntile[1]), (unsigned)(tp.ntile[2] * tp.ntile[3]), (unsigned)sp.P);
-    if (h->hp.D == 4) k_stage_tile<4><<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
+    if (ts->pa) k_stage_tile_pa<<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
+    else if (h->hp.D == 4) k_stage_tile<4><<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
     else k_stage_tile<3><<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
     return cudaGetLastError();
 }
