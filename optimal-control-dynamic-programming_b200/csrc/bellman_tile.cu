@@ -313,7 +313,8 @@ k_stage_tile(const __grid_constant__ StageParams sp, const __grid_constant__ Til
 // checks inside the loops (k_stage_tile: 229 instructions per update, this kernel: see profiles/).
 // Same operations on the same operands as k_stage_direct ⇒ bit-identical results.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TNT, 2)
+template <int NT, int UNROLL>
+__global__ void __launch_bounds__(NT, 2)
 k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ TileParams tp,
                 const __grid_constant__ CUtensorMap tmap) {
     constexpr int D = 4;
@@ -374,7 +375,7 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
     const int n1t = t_hi[1] - t_lo[1];
     const int npair = tp.T[2] * tp.T[3];
 #pragma unroll 1
-    for (int pq = wrp; pq < npair; pq += TNT / 32) {
+    for (int pq = wrp; pq < npair; pq += NT / 32) {
         const int i2 = t_lo[2] + pq % tp.T[2], i3 = t_lo[3] + pq / tp.T[2];
         if (i2 >= t_hi[2] || i3 >= t_hi[3]) continue;          // warp-uniform: ragged tile
         // dimension 2 (control independent): located once per pair
@@ -408,7 +409,7 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
 
             double best = __longlong_as_double(0x7ff0000000000000LL);
             int arg = 0;
-#pragma unroll 3
+#pragma unroll UNROLL
             for (int c = 0; c < C; ++c) {
                 const double2 e1 = __ldg(lt1 + c), e3 = __ldg(lt3 + c);
                 const uint32_t o = off02 + (uint32_t)__double2loint(e1.y) + (uint32_t)__double2loint(e3.y);
@@ -457,6 +458,7 @@ PFN_encodeTiled get_encode() {
 
 struct TileState {
     bool pa = false;                 // k_stage_tile_pa applies (table entries hold box byte offsets)
+    int nt = 512;                    // threads per CTA of k_stage_tile_pa (512 x 64 registers: 32 warps per SM)
     TileParams tp{};
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
@@ -638,7 +640,8 @@ void tile_setup(bellman_handle *h) {
                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { delete ts; return; }
     }
-    const void *fn = ts->pa ? (const void *)k_stage_tile_pa : D == 4 ? (const void *)k_stage_tile<4> : (const void *)k_stage_tile<3>;
+    ts->nt = std::getenv("BELLMAN_TILE_NT") ? std::atoi(std::getenv("BELLMAN_TILE_NT")) : 512;
+    const void *fn = ts->pa ? (ts->nt == 512 ? (const void *)k_stage_tile_pa<512, 1> : (const void *)k_stage_tile_pa<256, 3>) : D == 4 ? (const void *)k_stage_tile<4> : (const void *)k_stage_tile<3>;
     if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts->smem) != cudaSuccess) {
         delete ts;
         return;
@@ -653,7 +656,8 @@ cudaError_t tile_launch_for_handle(bellman_handle *h, const StageParams &sp, int
     if (!ts) return cudaErrorNotSupported;
     const TileParams &tp = ts->tp;
     const dim3 grid((unsigned)(tp.ntile[0] * tp.ntile[1]), (unsigned)(tp.ntile[2] * tp.ntile[3]), (unsigned)sp.P);
-    if (ts->pa) k_stage_tile_pa<<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
+    if (ts->pa && ts->nt == 512) k_stage_tile_pa<512, 1><<<grid, 512, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
+    else if (ts->pa) k_stage_tile_pa<256, 3><<<grid, 256, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
     else if (h->hp.D == 4) k_stage_tile<4><<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
     else k_stage_tile<3><<<grid, TNT, ts->smem, st>>>(sp, tp, ts->maps[slot_next]);
     return cudaGetLastError();

@@ -55,7 +55,7 @@ def check(d, kind, part_dim, rank, world, local):
     sw.comm_init(ids[0])
     n_stages = 6
     ok = True
-    for kernel in (bb.KERNEL_DIRECT, bb.KERNEL_AUTO):
+    for kernel in (bb.KERNEL_DIRECT, bb.KERNEL_AUTO, bb.KERNEL_WINDOW):   # WINDOW: strip / tile kernels with peer stores
         sw.set_J(None)
         sw.run(n_stages, kernel=kernel)
         J, idx = sw.get_J(), sw.get_idx()
