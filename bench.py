@@ -42,7 +42,9 @@ WORKLOADS = {
 DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch, from the committed
 # `ncu --set full` capture of the same command (profiles/r01_window_kirk_ncu_raw.csv)
-NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": 548.0e6 + 772.5e6}
+NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": 548.0e6 + 772.5e6,          # profiles/r01_window_kirk_summary.txt
+               "attitude_x16_3x16000x4800x3": 1.8434e9 + 2.7178e9,       # profiles/r01_strip_att16_summary.txt
+               "pos_att_x4_120x120x80x60x9": 3.5679e9 + 2.4639e9}        # profiles/r01_tile_posatt4_summary.txt
 
 
 def make_desc(bb, name):
@@ -205,7 +207,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "window", "splitc"])
+    ap.add_argument("--kernel", default="auto", choices=["auto", "direct", "window", "splitc", "tile"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (N = 1 default run)")
@@ -271,7 +273,7 @@ def main():
         sw.close()
         part_dim = d.D - 1
         sw = open_sweep(part_dim)
-    kernel = {"auto": bb.KERNEL_AUTO, "direct": bb.KERNEL_DIRECT, "window": bb.KERNEL_WINDOW,
+    kernel = {"auto": bb.KERNEL_AUTO, "direct": bb.KERNEL_DIRECT, "window": bb.KERNEL_WINDOW, "tile": bb.KERNEL_TILE,
               "splitc": bb.KERNEL_SPLITC}[args.kernel]
     use_graph = d.S * d.P < 4_000_000 and world == 1
 
