@@ -46,6 +46,7 @@ struct TileParams {
     // (x'_d = Ta_d[i_d] (+ Tb_d[i_d]) + Tc_d[c]: v' = v + h a(u), w' = w + h alpha(u)) are located once
     // per handle: lt[d][(p * n_d + i) * C + c] = {t, cell as raw bits}; null for the other dimensions
     const double2 *lt[MAXD];
+    int pf_dist;                // k_stage_tile_pa: L2 prefetch distance in CTAs (0 = off)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -83,6 +84,12 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, u
             "r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
         : "memory");
+}
+// TMA prefetch of a box into L2 (no shared memory, no barrier)
+__device__ __forceinline__ void tma_prefetch_5d(const CUtensorMap *map, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.prefetch.tensor.5d.L2.global.tile [%0, {%1, %2, %3, %4, %5}];" ::"l"(map), "r"(c0), "r"(c1),
+                 "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
 }
 __device__ __forceinline__ double lds_f64(uint32_t addr) {
     double v;
@@ -343,6 +350,22 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
         mbar_expect_tx(&mbar, (uint32_t)tp.box_elems * 8u);
         tma_load_5d(box, &tmap, &mbar, org[0] - sp.dim[0].ext_lo, org[1] - sp.dim[1].ext_lo, org[2] - sp.dim[2].ext_lo,
                     org[3] - sp.dim[3].ext_lo, (int)prob);
+        // warm L2 with the box of the tile pf_dist CTAs ahead in launch order (about one wave): the CTA
+        // that takes this one's place then waits for L2, not DRAM
+        if (tp.pf_dist) {
+            const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + (unsigned)tp.pf_dist;
+            if (lin < gridDim.x * gridDim.y * gridDim.z) {
+                const unsigned bx = lin % gridDim.x, rest = lin / gridDim.x;
+                const unsigned by = rest % gridDim.y, pz = rest / gridDim.y;
+                const int p0 = (int)(bx % tp.ntile[0]), p1 = (int)(bx / tp.ntile[0]);
+                const int p2 = (int)(by % tp.ntile[2]), p3 = (int)(by / tp.ntile[2]);
+                int o0 = p0 * tp.T[0] + tp.lo[0] + sp.dim[0].own_lo - sp.dim[0].ext_lo;
+                o0 -= o0 & 1;
+                tma_prefetch_5d(&tmap, o0, p1 * tp.T[1] + tp.lo[1] + sp.dim[1].own_lo - sp.dim[1].ext_lo,
+                                p2 * tp.T[2] + tp.lo[2] + sp.dim[2].own_lo - sp.dim[2].ext_lo,
+                                p3 * tp.T[3] + tp.lo[3] + sp.dim[3].own_lo - sp.dim[3].ext_lo, (int)pz);
+            }
+        }
     }
 
     const int C = sp.C;
@@ -570,6 +593,7 @@ void tile_setup(bellman_handle *h) {
     }
     tp.box_elems = bs;
     ts->smem = (size_t)bs * 8;
+    tp.pf_dist = std::getenv("BELLMAN_TILE_PF") ? std::atoi(std::getenv("BELLMAN_TILE_PF")) : 148 * 2;   // one wave of 2 CTAs per SM
     if ((long long)tp.ntile[0] * tp.ntile[1] > 2147483647LL || (long long)tp.ntile[2] * tp.ntile[3] > 65535 || hp.P > 65535) {
         delete ts;
         return;

@@ -57,6 +57,7 @@ struct WindowParams {
     // walked by one warp
     const double2 *colq;
     int strip_r;
+    int pf_dist;               // k_stage_strip: L2 prefetch distance in CTAs (0 = off)
 };
 
 // --- PTX wrappers ------------------------------------------------------------------------------
@@ -90,6 +91,13 @@ __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, u
             "r"(smem_u32(dst)),
         "l"(map), "r"(smem_u32(bar)), "r"(x), "r"(y), "r"(z)
         : "memory");
+}
+
+// TMA prefetch of a box into L2 (no shared memory, no barrier): used to warm L2 for the tile a later
+// CTA on this SM will stage, so that its TMA load sees L2 latency instead of DRAM latency
+__device__ __forceinline__ void tma_prefetch_3d(const CUtensorMap *map, int x, int y, int z) {
+    asm volatile("cp.async.bulk.prefetch.tensor.3d.L2.global.tile [%0, {%1, %2, %3}];" ::"l"(map), "r"(x), "r"(y), "r"(z)
+                 : "memory");
 }
 
 // shared-memory load by 32-bit address (keeps the address arithmetic in 32-bit integer registers).
@@ -570,6 +578,25 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
             org[c] = c0 * W0 + r0;
             mbar_expect_tx(&mbar, (uint32_t)(wp.win0 * wp.win1) * 8u);
             tma_load_3d(ring + (uint32_t)(c * wp.buf_doubles), &tmap, &mbar, r0 - d0.ext_lo, c0 - d1.ext_lo, (int)prob);
+            // warm L2 with the same control's window of the tile pf_dist CTAs ahead in launch order (about
+            // one wave: the CTA that will take this one's place): its TMA then sees L2, not DRAM, latency
+            if (wp.pf_dist) {
+                const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + (unsigned)wp.pf_dist;
+                if (lin < gridDim.x * gridDim.y * gridDim.z) {
+                    const unsigned bx = lin % gridDim.x, rest = lin / gridDim.x;
+                    const unsigned by = rest % gridDim.y, pz = rest / gridDim.y;
+                    const int pti = wp.tj_fastest ? (int)by : (int)bx, ptj = wp.tj_fastest ? (int)bx : (int)by;
+                    const double *ptm = wp.tmm + pz * (uint32_t)wp.tmm_stride;
+                    double plo0 = __ldg(ptm + wp.tmm_off[0][0] + 2 * pti);
+                    if (d0.Tb) plo0 = plo0 + __ldg(ptm + wp.tmm_off[0][1] + 2 * pti);
+                    double plo1 = __ldg(ptm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? pti : ptj));
+                    if (d1.Tb) plo1 = plo1 + __ldg(ptm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? pti : ptj));
+                    const int pc0 = cell_uniform(plo1, n1);
+                    int pr0 = cell_uniform(plo0 + __ldg(d0.Tc + pz * (uint32_t)CC + c), n0);
+                    pr0 -= (pr0 - d0.ext_lo) & 1;
+                    tma_prefetch_3d(&tmap, pr0 - d0.ext_lo, pc0 - d1.ext_lo, (int)pz);
+                }
+            }
         }
     }
 
@@ -805,6 +832,14 @@ static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const C
             default: return strip_go<8, 4, 3>(ws, sp, map, grid, st, sa);
         }
     }
+    if (ws->strip_nw == 2) {   // 64-thread CTAs: half the window per CTA, twice the CTAs per SM
+        switch (C) {
+            case 1: return strip_go<2, 1, 14>(ws, sp, map, grid, st, sa);
+            case 2: return strip_go<2, 2, 14>(ws, sp, map, grid, st, sa);
+            case 3: return strip_go<2, 3, 14>(ws, sp, map, grid, st, sa);
+            default: return strip_go<2, 4, 14>(ws, sp, map, grid, st, sa);
+        }
+    }
     if (ws->occ == 3) {   // BELLMAN_WIN_OCC=3: fewer CTAs per SM, more registers (experiments)
         switch (C) {
             case 3: return strip_go<4, 3, 5>(ws, sp, map, grid, st, sa);
@@ -889,7 +924,7 @@ void window_setup(bellman_handle *h) {
     const bool lean_cfg = chain_cfg && rstates == 4 && hp.C <= 4 && !std::getenv("BELLMAN_WIN_NOLEAN");
     const bool strip_cfg = lean_cfg && !std::getenv("BELLMAN_WIN_NOSTRIP");
     int strip_nw = 4, strip_r = 8;
-    if (const char *e = std::getenv("BELLMAN_STRIP_NW")) strip_nw = std::atoi(e) == 8 ? 8 : 4;
+    if (const char *e = std::getenv("BELLMAN_STRIP_NW")) strip_nw = std::atoi(e) == 8 ? 8 : std::atoi(e) == 2 ? 2 : 4;
     if (const char *e = std::getenv("BELLMAN_STRIP_R")) strip_r = std::max(2, std::min(64, std::atoi(e) / 2 * 2));
     const int wt1 = strip_cfg ? strip_nw * strip_r : tile1_of(rstates);
 
@@ -1014,6 +1049,7 @@ void window_setup(bellman_handle *h) {
         if (!upload(colq, &ws->d_colq)) { window_teardown_state(ws); return; }
         wp.colq = static_cast<const double2 *>(ws->d_colq);
         wp.strip_r = strip_r;
+        wp.pf_dist = std::getenv("BELLMAN_STRIP_PF") ? std::atoi(std::getenv("BELLMAN_STRIP_PF")) : 148 * 7;   // one wave of 7 CTAs per SM
     }
 
     // per-tile-index extrema of the state-indexed tables (read by the kernel instead of reducing per tile)
