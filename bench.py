@@ -38,6 +38,7 @@ WORKLOADS = {
     "attitude_x16_3x16000x4800x3": dict(kind="attitude", n_w=16000, n_t=4800),
     "pos_att_ref_30x30x20x15x9": dict(kind="pos_att", scale=1),
     "pos_att_x4_120x120x80x60x9": dict(kind="pos_att", scale=4),
+    "pos_att_x8_1ch_240x240x160x120x9": dict(kind="pos_att", scale=8, channels=1),   # single-GPU slice of configs[4]
 }
 DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch, from the committed
@@ -64,7 +65,7 @@ def make_desc(bb, name):
         s = bb.Solver_pos_att()
         k = w["scale"]
         s.n_mesh_x, s.n_mesh_v, s.n_mesh_t, s.n_mesh_w = 30 * k, 30 * k, 20 * k, 15 * k
-        return t.stack_problems([s.channel_desc(c) for c in range(3)])
+        return t.stack_problems([s.channel_desc(c) for c in range(w.get("channels", 3))])
     raise ValueError(name)
 
 
