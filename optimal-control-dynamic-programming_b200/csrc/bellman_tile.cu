@@ -47,6 +47,10 @@ struct TileParams {
     // per handle: lt[d][(p * n_d + i) * C + c] = {t, cell as raw bits}; null for the other dimensions
     const double2 *lt[MAXD];
     int pf_dist;                // k_stage_tile_pa: L2 prefetch distance in CTAs (0 = off)
+    // k_stage_tile_pa: the control-independent dimensions d = 0, 2 (x'_d = Ta_d[i_d] + Tb_d[i_{d+1}]) are
+    // located once per handle too: ft[d/2][(p * n_{d+1} + i_{d+1}) * n_d + i_d] = {t, box byte offset}
+    const double2 *ft[2];
+    int q_identity;             // q_order == {0, 1, 2, 3}
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -371,14 +375,10 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
     const int C = sp.C;
     const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1], &d2 = sp.dim[2], &d3 = sp.dim[3];
     const double *rr = sp.r + prob * (uint32_t)C;
-    const int mode0 = __ldg(d0.mode + prob), mode2 = __ldg(d2.mode + prob);
-    const double *g0 = d0.grid + prob * (uint32_t)d0.n, *ri0 = d0.rinv + prob * (uint32_t)d0.n;
-    const double *g2 = d2.grid + prob * (uint32_t)d2.n, *ri2 = d2.rinv + prob * (uint32_t)d2.n;
 
     // this lane's row (dimension 0): table entries that depend on i0 only
     const int i0 = min(t_lo[0] + lane, t_hi[0] - 1);
     const bool row_ok = t_lo[0] + lane < t_hi[0];
-    const double ta0 = __ldg(d0.Ta + prob * (uint32_t)d0.n_a + i0);
     const double q0 = __ldg(d0.q + prob * (uint32_t)d0.n + i0);
     const int qo0 = sp.q_order[0], qo1 = sp.q_order[1], qo2 = sp.q_order[2], qo3 = sp.q_order[3];
 
@@ -401,12 +401,10 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
     for (int pq = wrp; pq < npair; pq += NT / 32) {
         const int i2 = t_lo[2] + pq % tp.T[2], i3 = t_lo[3] + pq / tp.T[2];
         if (i2 >= t_hi[2] || i3 >= t_hi[3]) continue;          // warp-uniform: ragged tile
-        // dimension 2 (control independent): located once per pair
-        double b2 = __ldg(d2.Ta + prob * (uint32_t)d2.n_a + i2);
-        if (d2.Tb) b2 = b2 + __ldg(d2.Tb + prob * (uint32_t)d2.n_b + i3);
-        double t2;
-        const int cell2 = locate_near(g2, ri2, d2.n, mode2, i2, b2, t2);
-        const uint32_t off2 = base + 8u * (uint32_t)(cell2 * tp.bstride[2]);
+        // dimension 2 (control independent): one table entry per (i2, i3) pair
+        const double2 e2 = __ldg(tp.ft[1] + (prob * (uint32_t)d3.n + (uint32_t)i3) * (uint32_t)d2.n + (uint32_t)i2);
+        const double t2 = e2.x;
+        const uint32_t off2 = base + (uint32_t)__double2loint(e2.y);
         const double2 *lt3 = tp.lt[3] + (prob * (uint32_t)d3.n + (uint32_t)i3) * (uint32_t)C;
         const double q2 = __ldg(d2.q + prob * (uint32_t)d2.n + i2), q3 = __ldg(d3.q + prob * (uint32_t)d3.n + i3);
         long long jo = (long long)prob * sp.S_ext + (long long)(i0 - d0.ext_lo) * d0.stride +
@@ -418,17 +416,20 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
 #pragma unroll 1
         for (int j1 = 0; j1 < n1t; ++j1) {
             const int i1 = t_lo[1] + j1;
-            // dimension 0 (control independent, lane specific)
-            double b0 = ta0;
-            if (d0.Tb) b0 = b0 + __ldg(d0.Tb + prob * (uint32_t)d0.n_b + i1);
-            double t0;
-            const int cell0 = locate_near(g0, ri0, d0.n, mode0, i0, b0, t0);
-            const uint32_t off02 = off2 + 8u * (uint32_t)cell0;          // bstride[0] = 1
+            // dimension 0 (control independent, lane specific): one coalesced table entry per state
+            const double2 e0 = __ldg(tp.ft[0] + (prob * (uint32_t)d1.n + (uint32_t)i1) * (uint32_t)d0.n + (uint32_t)i0);
+            const double t0 = e0.x;
+            const uint32_t off02 = off2 + (uint32_t)__double2loint(e0.y);
             const double2 *lt1 = tp.lt[1] + (prob * (uint32_t)d1.n + (uint32_t)i1) * (uint32_t)C;
             // stage cost of the state: q terms summed in q_order
             const double q1 = __ldg(d1.q + prob * (uint32_t)d1.n + i1);
-            auto qsel = [&](int o) { return o == 0 ? q0 : o == 1 ? q1 : o == 2 ? q2 : q3; };
-            const double gs = ((qsel(qo0) + qsel(qo1)) + qsel(qo2)) + qsel(qo3);
+            double gs;
+            if (tp.q_identity) {
+                gs = ((q0 + q1) + q2) + q3;
+            } else {
+                auto qsel = [&](int o) { return o == 0 ? q0 : o == 1 ? q1 : o == 2 ? q2 : q3; };
+                gs = ((qsel(qo0) + qsel(qo1)) + qsel(qo2)) + qsel(qo3);
+            }
 
             double best = __longlong_as_double(0x7ff0000000000000LL);
             int arg = 0;
@@ -486,7 +487,8 @@ struct TileState {
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
     void *d_lt[MAXD] = {nullptr, nullptr, nullptr, nullptr};
-    ~TileState() { for (void *p : d_lt) cudaFree(p); }
+    void *d_ft[2] = {nullptr, nullptr};
+    ~TileState() { for (void *p : d_lt) cudaFree(p); for (void *p : d_ft) cudaFree(p); }
 };
 
 // Exact stencil bounds of dimension d: min / max over every state and control of
@@ -593,7 +595,7 @@ void tile_setup(bellman_handle *h) {
     }
     tp.box_elems = bs;
     ts->smem = (size_t)bs * 8;
-    tp.pf_dist = std::getenv("BELLMAN_TILE_PF") ? std::atoi(std::getenv("BELLMAN_TILE_PF")) : 148 * 2;   // one wave of 2 CTAs per SM
+    tp.pf_dist = std::getenv("BELLMAN_TILE_PF") ? std::atoi(std::getenv("BELLMAN_TILE_PF")) : 0;   // measured: +1 % on large grids, -45 % on L2-resident ones
     if ((long long)tp.ntile[0] * tp.ntile[1] > 2147483647LL || (long long)tp.ntile[2] * tp.ntile[3] > 65535 || hp.P > 65535) {
         delete ts;
         return;
@@ -641,6 +643,35 @@ void tile_setup(bellman_handle *h) {
             return;
         }
         tp.lt[d] = static_cast<const double2 *>(ts->d_lt[d]);
+    }
+    tp.ft[0] = tp.ft[1] = nullptr;
+    tp.q_identity = (hp.q_order[0] == 0 && hp.q_order[1] == 1 && hp.q_order[2] == 2 && hp.q_order[3] == 3) ? 1 : 0;
+    for (int k = 0; k < 2 && ts->pa; ++k) {
+        const int d = 2 * k, e = d + 1, nd = hp.n[d], ne = hp.n[e];
+        std::vector<double> tab((size_t)hp.P * ne * nd * 2);
+        for (int p = 0; p < hp.P; ++p) {
+            const double *sgrid = hp.grid[d].data() + (size_t)p * nd, *ri = hp.rinv[d].data() + (size_t)p * nd;
+            const bool uni = hp.mode[(size_t)p * hp.D + d] == BELLMAN_LOCATE_UNIFORM;
+            for (int ie = 0; ie < ne; ++ie)
+                for (int i = 0; i < nd; ++i) {
+                    double xq = hp.Ta[d][(size_t)p * nd + i];
+                    if (hp.has_b[d]) xq = xq + hp.Tb[d][(size_t)p * ne + ie];
+                    const int cell = host_locate(hp, p, d, xq);
+                    const double t = uni ? xq - (double)cell : (xq - sgrid[cell]) * ri[cell];
+                    double cb;
+                    const long long bits = (long long)(unsigned int)(cell * tp.bstride[d] * 8);
+                    std::memcpy(&cb, &bits, 8);
+                    const size_t o = (((size_t)p * ne + ie) * nd + i) * 2;
+                    tab[o] = t;
+                    tab[o + 1] = cb;
+                }
+        }
+        if (cudaMalloc(&ts->d_ft[k], tab.size() * 8) != cudaSuccess ||
+            cudaMemcpy(ts->d_ft[k], tab.data(), tab.size() * 8, cudaMemcpyHostToDevice) != cudaSuccess) {
+            delete ts;
+            return;
+        }
+        tp.ft[k] = static_cast<const double2 *>(ts->d_ft[k]);
     }
     if (std::getenv("BELLMAN_TILE_DEBUG"))
         std::fprintf(stderr, "bellman tile%s: T = %d %d %d %d, stencil lo = %d %d %d %d hi = %d %d %d %d, box = %d %d %d %d (%zu KB), tables = %d%d%d%d\n",

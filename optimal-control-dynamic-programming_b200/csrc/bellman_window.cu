@@ -1050,6 +1050,10 @@ void window_setup(bellman_handle *h) {
         wp.colq = static_cast<const double2 *>(ws->d_colq);
         wp.strip_r = strip_r;
         wp.pf_dist = std::getenv("BELLMAN_STRIP_PF") ? std::atoi(std::getenv("BELLMAN_STRIP_PF")) : 148 * 7;   // one wave of 7 CTAs per SM
+        // only grids of many waves: on small (L2-resident) grids the prefetch is pure extra TMA traffic
+        if (!std::getenv("BELLMAN_STRIP_PF") &&
+            (long long)((h->own_n[0] + WT0 - 1) / WT0) * ((h->own_n[1] + wt1 - 1) / wt1) * hp.P < 4LL * 148 * 7)
+            wp.pf_dist = 0;
     }
 
     // per-tile-index extrema of the state-indexed tables (read by the kernel instead of reducing per tile)
