@@ -347,7 +347,7 @@ def main():
     achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
     # secondary bound: fp64 pipe, 64 lanes/clk/SM x 148 SMs at the clock seen
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp64_ops_per_update = 15.0     # window kernel, SASS-counted: 13 DADD/DFMA/DSETP + 2 DADD (exact int->double)
+    fp64_ops_per_update = 17.0     # window kernel interior loop, SASS-counted: 13 DADD (incl. 2 x 3 for the fp64-pipe floor) + 3 DFMA + 1 DSETP
     fp64_peak = 64 * 148 * mhz * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
