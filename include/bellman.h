@@ -157,6 +157,12 @@ int  bellman_query_locate(const bellman_desc *d, int32_t mode_out[/*P*D*/]);
 int  bellman_plan_slabs(const bellman_desc *d, int32_t part_dim, int32_t nranks,
                         bellman_slab slabs_out[/*nranks*/]);
 
+/* Exact stencil bounds per dimension: over every state and control, cell(x'_d) - i_d lies in
+ * [lo_out[d], hi_out[d]] (i_d = the state's own index along d; the upper interpolation corner is one
+ * further).  The D = 3 / 4 tile kernel sizes its shared-memory box with these.  lo > hi marks a
+ * dimension whose query does not depend on the state's own index (no bounded stencil). */
+int  bellman_query_stencil(const bellman_desc *d, int32_t lo_out[/*D*/], int32_t hi_out[/*D*/]);
+
 /* lifecycle */
 int  bellman_create(const bellman_desc *d, bellman_handle **out);
 void bellman_destroy(bellman_handle *h);

@@ -49,7 +49,7 @@ class CSlab(C.Structure):
 
 # every symbol include/bellman.h declares
 EXPORTS = [
-    "bellman_version", "bellman_last_error", "bellman_query_locate", "bellman_plan_slabs",
+    "bellman_version", "bellman_last_error", "bellman_query_locate", "bellman_plan_slabs", "bellman_query_stencil",
     "bellman_create", "bellman_destroy", "bellman_get_unique_id", "bellman_comm_init", "bellman_halo_mode",
     "bellman_set_J", "bellman_set_stage", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
@@ -140,6 +140,18 @@ def query_locate(d):
     if rc != 0:
         raise BellmanError(rc, "bellman_query_locate")
     return modes.reshape(d.P, d.D)
+
+
+def query_stencil(d):
+    """Exact per-dimension bounds (lo, hi) of cell(x'_d) - i_d over every state and control.  Host-only."""
+    lib = load()
+    cd, keep = to_cdesc(d)
+    lo = np.zeros(d.D, dtype=np.int32)
+    hi = np.zeros(d.D, dtype=np.int32)
+    rc = lib.bellman_query_stencil(C.byref(cd), lo.ctypes.data_as(_ip), hi.ctypes.data_as(_ip))
+    if rc != 0:
+        raise BellmanError(rc, "bellman_query_stencil")
+    return lo, hi
 
 
 def plan_slabs(d, part_dim, nranks):

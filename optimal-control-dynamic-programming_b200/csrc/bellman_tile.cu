@@ -528,6 +528,22 @@ bool stencil_reach(const HostProblem &hp, int d, int &lo, int &hi) {
 
 }  // namespace
 
+}  // namespace bellman
+
+// host-only: the exact stencil bounds the tile kernel sizes its box with (include/bellman.h)
+extern "C" int bellman_query_stencil(const bellman_desc *d, int32_t *lo_out, int32_t *hi_out) {
+    bellman::HostProblem hp;
+    if (!bellman::load_problem(d, hp).empty() || !lo_out || !hi_out) return BELLMAN_ERR_BAD_ARG;
+    for (int k = 0; k < hp.D; ++k) {
+        int lo = 0, hi = 0;
+        if (bellman::stencil_reach(hp, k, lo, hi)) { lo_out[k] = lo; hi_out[k] = hi; }
+        else { lo_out[k] = 1; hi_out[k] = -1; }          // lo > hi: x'_k does not depend on the own index
+    }
+    return BELLMAN_OK;
+}
+
+namespace bellman {
+
 void tile_teardown(bellman_handle *h) {
     delete static_cast<TileState *>(h->tstate);
     h->tstate = nullptr;

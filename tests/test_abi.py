@@ -113,3 +113,58 @@ def test_degenerate_inputs_rejected_before_any_cuda_call(bellman):
         with pytest.raises(bellman.BellmanError) as e:
             bellman.Sweep(d)
         assert e.value.code == -1, str(e.value)
+
+
+def _brute_stencil(d, p=0):
+    """cell(x'_k) - i_k over every state and control, by the exact bin rule in state units (numpy)."""
+    out = []
+    for k in range(d.D):
+        s = d.grid[k][p]
+        n = [len(d.grid[j][p]) for j in range(d.D)]
+        sa, sb = d.src_a[k], d.src_b[k]
+        if sa != k and sb != k:
+            out.append(None)
+            continue
+        ta = d.Ta[k][p]
+        x = ta[:, None, None] if sa == k else ta[None, :, None]
+        own = np.arange(n[k])[:, None, None]
+        if d.Tb[k] is not None and sb >= 0:
+            tb = d.Tb[k][p]
+            if sb == k and sa == k:
+                x = (ta + tb)[:, None, None]
+            elif sb == k:
+                x = ta[None, :, None] + tb[:, None, None]
+            else:
+                x = x + tb[None, :, None]
+        if d.Tc[k] is not None:
+            x = x + d.Tc[k][p][None, None, :]
+        cell = np.clip(np.searchsorted(s, x, side="right") - 1, 0, len(s) - 2)
+        off = cell - own
+        out.append((int(off.min()), int(off.max())))
+    return out
+
+
+def test_query_stencil_matches_brute_force(bellman):
+    """bellman_query_stencil (host-only): the bounds the tile kernel sizes its box with are safe
+    (contain every query) and tight; exact for SEARCH dimensions."""
+    t = bellman.tables
+    sp = bellman.Solver_pos_att()
+    descs = []
+    for mesh in ((30, 30, 20, 15), (12, 10, 8, 15), (34, 9, 7, 5), (64, 32, 16, 40)):
+        sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = mesh
+        descs += [sp.channel_desc(c) for c in range(3)]
+    descs.append(t.attitude_axis_desc(-0.9, 0.9, 200, -30.0, 30.0, 120, [-0.11, 0.0, 0.11], 0.0285, 6.0, 6.0, 4.0, 0.02, 6))
+    descs.append(t.position_axis_desc(-0.5, 0.5, 200, -0.5, 0.5, 200, [-0.26, 0.0, 0.26], 4.16, 6.0, 6.0, 0.1, 0.005, 6))
+    descs.append(t.kirk_desc([[0.9974, 0.0539], [-0.1078, 1.1591]], [0.0013, 0.0539], [[0.25, 0.0], [0.0, 0.05]],
+                             0.05, 5, -2.5, 3.0, 64, -40.0, 10.0, 33))
+    for d in descs:
+        lo, hi = bellman.query_stencil(d)
+        modes = bellman.query_locate(d)[0]
+        for k, b in enumerate(_brute_stencil(d)):
+            if b is None:
+                assert lo[k] > hi[k]
+                continue
+            assert lo[k] <= b[0] and hi[k] >= b[1], (d.meta.get("class"), k, lo[k], hi[k], b)      # safe
+            assert lo[k] >= b[0] - 1 and hi[k] <= b[1] + 1, (d.meta.get("class"), k, lo[k], hi[k], b)  # tight
+            if modes[k] != 0:                                                                        # SEARCH: exact
+                assert (lo[k], hi[k]) == b
