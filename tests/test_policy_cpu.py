@@ -51,3 +51,60 @@ def test_oracle_policy_lookup_matches_nearest_interpolant(bellman, oracle_lib):
     want = F(*[x[:, k] for k in range(4)])
     got = oracle_lib.policy_lookup(d, idx, x)
     assert np.array_equal(got, want)
+
+
+def test_controller_file_round_trip_cpu(bellman, oracle_lib, tmp_path):
+    """Solver_pos_att.save_controller / load_controller / set_controller / get_thruster_on_off_optimal
+    (Solver_pos_att.m:291, :849-882, :404-449) with a controller produced by the oracle: no GPU involved."""
+    rng = np.random.default_rng(7)
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 8, 7, 6, 5
+    ctls = {}
+    for ci, ch in enumerate("xyz"):
+        d = sp.channel_desc(ci)
+        out = oracle_lib.sweep(d, n_stages=5)
+        shape = tuple(d.n)
+        ctl = {"GridVectors": [d.grid[k][0] for k in range(4)],
+               "F_gI_Values": out["J_last"][0].reshape(shape, order="F"),
+               "U_Optimal_id": out["idx_last"][0].reshape(shape, order="F") + 1,
+               "f0_allcomb": d.meta["f0_allcomb"], "f1_allcomb": d.meta["f1_allcomb"],
+               "f6_allcomb": d.meta["f6_allcomb"], "f7_allcomb": d.meta["f7_allcomb"], "stop_stage": d.N - 5}
+        f = str(tmp_path / ("channel_%s_controller_1.mat" % ch))
+        sp.save_controller(f, ctl)
+        back = sp.load_controller(f)
+        assert np.array_equal(back["U_Optimal_id"], ctl["U_Optimal_id"])
+        assert np.array_equal(back["F_gI_Values"], ctl["F_gI_Values"]) and back["stop_stage"] == ctl["stop_stage"]
+        sp.set_controller(f, ch)
+        ctls[ch] = (d, ctl)
+    # one state, all twelve thrusters, against the oracle's nearest lookup per channel
+    for _ in range(50):
+        x = rng.uniform(-0.25, 0.25, 3); v = rng.uniform(-0.12, 0.12, 3)
+        t = rng.uniform(-0.1, 0.1, 3); w = rng.uniform(-0.04, 0.04, 3)
+        f = sp.get_thruster_on_off_optimal(x, v, t, w)
+        ang = {"x": 1, "y": 2, "z": 0}
+        for ci, ch in enumerate("xyz"):
+            d, ctl = ctls[ch]
+            q = np.array([[x[ci], v[ci], t[ang[ch]], w[ang[ch]]]])
+            c = oracle_lib.policy_lookup(d, (ctl["U_Optimal_id"] - 1).ravel(order="F"), q)[0]
+            for name, thr in zip(("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb"), sp._channel_thrusters[ch]):
+                assert f[thr] == ctl[name][c]
+    # frame change (:411-415): identity attitude, RSW axes aligned with ECI for R0 = e1, V0 = e2
+    f1 = sp.get_thruster_on_off_optimal([0.01, -0.02, 0.03], [0.0, 0.01, 0.0], [0, 0, 0], [0, 0, 0],
+                                        R0=[7000.0, 0, 0], V0=[0, 7.5, 0], q=[0, 0, 0, 1])
+    f2 = sp.get_thruster_on_off_optimal([0.01, -0.02, 0.03], [0.0, 0.01, 0.0], [0, 0, 0], [0, 0, 0])
+    assert np.array_equal(f1, f2)
+
+
+def test_dynamic_solver_archive_cpu(bellman, golden, tmp_path):
+    """Dynamic_Solver.save / load / compare_data (Dynamic_Solver.m:266-280) on the reference's stored run."""
+    a = bellman.Dynamic_Solver()
+    a.N, a.dx, a.du = golden["N"], golden["dx"], golden["du"]
+    a.J_star, a.u_star = golden["J_star"], golden["u_star"]
+    a.s_r = golden["X1_mesh"][:, 0]
+    f = str(tmp_path / "obj_1_copy.mat")
+    a.save(f)
+    b = bellman.Dynamic_Solver.load(f)
+    assert b.N == a.N and np.array_equal(b.s_r, a.s_r) and np.array_equal(b.u_star, a.u_star)
+    assert bellman.Dynamic_Solver.compare_data(a, b)
+    b.J_star = b.J_star.copy(); b.J_star[0, 0, 0] += 1e-9
+    assert not bellman.Dynamic_Solver.compare_data(a, b)
