@@ -578,25 +578,6 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
             org[c] = c0 * W0 + r0;
             mbar_expect_tx(&mbar, (uint32_t)(wp.win0 * wp.win1) * 8u);
             tma_load_3d(ring + (uint32_t)(c * wp.buf_doubles), &tmap, &mbar, r0 - d0.ext_lo, c0 - d1.ext_lo, (int)prob);
-            // warm L2 with the same control's window of the tile pf_dist CTAs ahead in launch order (about
-            // one wave: the CTA that will take this one's place): its TMA then sees L2, not DRAM, latency
-            if (wp.pf_dist) {
-                const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + (unsigned)wp.pf_dist;
-                if (lin < gridDim.x * gridDim.y * gridDim.z) {
-                    const unsigned bx = lin % gridDim.x, rest = lin / gridDim.x;
-                    const unsigned by = rest % gridDim.y, pz = rest / gridDim.y;
-                    const int pti = wp.tj_fastest ? (int)by : (int)bx, ptj = wp.tj_fastest ? (int)bx : (int)by;
-                    const double *ptm = wp.tmm + pz * (uint32_t)wp.tmm_stride;
-                    double plo0 = __ldg(ptm + wp.tmm_off[0][0] + 2 * pti);
-                    if (d0.Tb) plo0 = plo0 + __ldg(ptm + wp.tmm_off[0][1] + 2 * pti);
-                    double plo1 = __ldg(ptm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? pti : ptj));
-                    if (d1.Tb) plo1 = plo1 + __ldg(ptm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? pti : ptj));
-                    const int pc0 = cell_uniform(plo1, n1);
-                    int pr0 = cell_uniform(plo0 + __ldg(d0.Tc + pz * (uint32_t)CC + c), n0);
-                    pr0 -= (pr0 - d0.ext_lo) & 1;
-                    tma_prefetch_3d(&tmap, pr0 - d0.ext_lo, pc0 - d1.ext_lo, (int)pz);
-                }
-            }
         }
     }
 
@@ -622,6 +603,28 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     uint32_t io = prob * (uint32_t)sp.S_own + (uint32_t)(i - d0.own_lo) + (uint32_t)(jb - d1.own_lo) * si;
 
     __syncthreads();          // org[] and the mbarrier are visible
+    if (wrp == 0 && lane < CC) {
+        const int c = lane;
+        // warm L2 with the same control's window of the tile pf_dist CTAs ahead in launch order (about
+        // one wave: the CTA that will take this one's place): its TMA then sees L2, not DRAM, latency
+        if (wp.pf_dist) {
+            const unsigned lin = blockIdx.x + gridDim.x * (blockIdx.y + gridDim.y * blockIdx.z) + (unsigned)wp.pf_dist;
+            if (lin < gridDim.x * gridDim.y * gridDim.z) {
+                const unsigned bx = lin % gridDim.x, rest = lin / gridDim.x;
+                const unsigned by = rest % gridDim.y, pz = rest / gridDim.y;
+                const int pti = wp.tj_fastest ? (int)by : (int)bx, ptj = wp.tj_fastest ? (int)bx : (int)by;
+                const double *ptm = wp.tmm + pz * (uint32_t)wp.tmm_stride;
+                double plo0 = __ldg(ptm + wp.tmm_off[0][0] + 2 * pti);
+                if (d0.Tb) plo0 = plo0 + __ldg(ptm + wp.tmm_off[0][1] + 2 * pti);
+                double plo1 = __ldg(ptm + wp.tmm_off[1][0] + 2 * (d1.src_a == 0 ? pti : ptj));
+                if (d1.Tb) plo1 = plo1 + __ldg(ptm + wp.tmm_off[1][1] + 2 * (d1.src_b == 0 ? pti : ptj));
+                const int pc0 = cell_uniform(plo1, n1);
+                int pr0 = cell_uniform(plo0 + __ldg(d0.Tc + pz * (uint32_t)CC + c), n0);
+                pr0 -= (pr0 - d0.ext_lo) & 1;
+                tma_prefetch_3d(&tmap, pr0 - d0.ext_lo, pc0 - d1.ext_lo, (int)pz);
+            }
+        }
+    }
     mbar_wait(&mbar, 0);
 
     if (jcnt <= 0) return;    // ragged last tile: this warp has no columns (no barrier follows)
