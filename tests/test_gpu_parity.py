@@ -571,3 +571,26 @@ def test_tile_kernel_falls_back_when_not_a_stencil(bellman, oracle_lib):
         sw.run(2, kernel=KERNELS["tile"])
         assert sw.last_kernel == "direct"
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "tile fallback")
+
+
+@pytest.mark.parametrize("env", [{"BELLMAN_STRIP_R": "16"}, {"BELLMAN_STRIP_R": "4", "BELLMAN_STRIP_NW": "8"},
+                                 {"BELLMAN_STRIP_R": "12", "BELLMAN_STRIP_NW": "2", "BELLMAN_STRIP_PF": "5"},
+                                 {"BELLMAN_WIN_NOSTRIP": "1"}])
+def test_strip_kernel_geometries(bellman, oracle_lib, monkeypatch, env):
+    """every strip geometry the planner can pick (strip length 16 is the default on large grids), the
+    L2 prefetch with a distance that stays inside a small grid, and the k_stage_chain fallback."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    t = bellman.tables
+    rng = np.random.default_rng(9)
+    U = np.array([-0.11, 0.0, 0.11])
+    descs = [t.attitude_axis_desc(-0.9, 0.9, 150, -ang, ang, 100, U, J, 6.0, 6.0, 4.0, 0.02, 6)
+             for ang, J in ((30.0, 0.0285), (20.0, 0.0283), (35.0, 0.0245))]
+    d = t.stack_problems(descs)
+    JN = rng.normal(size=(3, d.S)) * 3
+    ora = oracle_lib.sweep(d, n_stages=3, J_N=JN)
+    with bellman.Sweep(d) as sw:
+        sw.set_J(JN)
+        sw.run(3, kernel=KERNELS["window"])
+        assert sw.last_kernel == ("window:chain" if "BELLMAN_WIN_NOSTRIP" in env else "window:strip")
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"strip {env}")
