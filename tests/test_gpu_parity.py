@@ -594,3 +594,22 @@ def test_strip_kernel_geometries(bellman, oracle_lib, monkeypatch, env):
         sw.run(3, kernel=KERNELS["window"])
         assert sw.last_kernel == ("window:chain" if "BELLMAN_WIN_NOSTRIP" in env else "window:strip")
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"strip {env}")
+
+
+@pytest.mark.parametrize("env", [{"BELLMAN_TILE_NT": "256"}, {"BELLMAN_TILE_GENERIC": "1"}, {"BELLMAN_TILE": "2,2,4"},
+                                 {"BELLMAN_TILE_PF": "3"}, {"BELLMAN_TILE": "1,8,2", "BELLMAN_TILE_NT": "256"}])
+def test_tile_kernel_variants(bellman, oracle_lib, monkeypatch, env):
+    """the 256-thread form, the generic (run-time structure) tile kernel, forced tile shapes and the L2 prefetch."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(4)
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 40, 12, 10, 14
+    d = bellman.tables.stack_problems([sp.channel_desc(c) for c in range(3)])
+    JN = rng.normal(size=(3, d.S)) * 2
+    ora = oracle_lib.sweep(d, n_stages=3, J_N=JN)
+    with bellman.Sweep(d) as sw:
+        sw.set_J(JN)
+        sw.run(3, kernel=KERNELS["tile"])
+        assert sw.last_kernel == "tile"
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"tile {env}")
