@@ -613,3 +613,29 @@ def test_tile_kernel_variants(bellman, oracle_lib, monkeypatch, env):
         sw.run(3, kernel=KERNELS["tile"])
         assert sw.last_kernel == "tile"
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"tile {env}")
+
+
+def test_pos_att_x4_full_size_spot_check(bellman, oracle_lib):
+    """the bench's pos-att workload at full size (one channel of 120 x 120 x 80 x 60 x 9; the thrusters
+    move w by up to +-5 cells per stage here, so the tile kernel's box is much wider than in the small
+    tests): two stages with the tile kernel, 60k sampled states against the oracle's pointwise evaluator."""
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 120, 120, 80, 60
+    d = sp.channel_desc(0)
+    lo, hi = bellman.query_stencil(d)
+    assert hi[3] - lo[3] >= 6                      # the wide stencil this test is about
+    rng = np.random.default_rng(11)
+    JN = rng.normal(size=(1, d.S)) * 0.1
+    with bellman.Sweep(d) as sw:
+        sw.set_J(JN)
+        sw.run(1)
+        assert sw.last_kernel == "tile"
+        J1, I1 = sw.get_J(), sw.get_idx()
+        sw.run(1)
+        J2, I2 = sw.get_J(), sw.get_idx()
+    pts = rng.integers(0, d.S, size=60_000)
+    pts[:4] = [0, 119, d.S - 120, d.S - 1]
+    Jo, Io = oracle_lib.stage_points(d, JN[0], pts)
+    assert np.array_equal(I1[0][pts], Io) and np.array_equal(J1[0][pts], Jo)
+    Jo, Io = oracle_lib.stage_points(d, J1[0], pts)
+    assert np.array_equal(I2[0][pts], Io) and np.array_equal(J2[0][pts], Jo)
