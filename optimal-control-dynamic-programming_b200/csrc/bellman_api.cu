@@ -229,12 +229,19 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
     h->n_partials = 592;
     TRY_RC(cu(cudaMalloc(&h->d_partials, 2 * h->n_partials * sizeof(double)), "cudaMalloc"));
     TRY_RC(cu(cudaMalloc(&h->d_sums, 2 * sizeof(double)), "cudaMalloc"));
+    if (h->nranks > 1) {
+        // scratch of bellman_comm_init (IPC handle all-gather) and the stage barrier: allocated here so
+        // that an allocation failure is a clean create() error and never skips a collective
+        TRY_RC(cu(cudaMalloc(&h->d_comm_scratch, sizeof(cudaIpcMemHandle_t) * (size_t)(h->nranks + 1) + 16), "cudaMalloc"));
+        TRY_RC(cu(cudaMalloc(&h->d_barrier, 2 * sizeof(double)), "cudaMalloc"));
+    }
 #undef TRY_RC
     h->cur_stage = hp.N;
     rc = bellman_set_J(h, nullptr);
     if (rc != BELLMAN_OK) return fail(rc);
     window_setup(h);   // optional fast path; leaves wcfg.valid = false when it does not apply
     tile_setup(h);     // D = 3 / 4 counterpart
+    stream_setup(h);   // D = 4, Solver_pos_att's channel structure: streaming factorised kernel
     *out = h;
     return BELLMAN_OK;
 }
@@ -249,6 +256,7 @@ extern "C" void bellman_destroy(bellman_handle *h) {
         for (double *pj : h->peer_J) if (pj) cudaIpcCloseMemHandle(pj);
     }
     cudaFree(h->d_barrier);
+    cudaFree(h->d_comm_scratch);
     if (h->comm) {
         std::string e;
         NcclApi *api = nccl_api(e);
@@ -258,6 +266,7 @@ extern "C" void bellman_destroy(bellman_handle *h) {
     cudaFree(h->d_partials); cudaFree(h->d_sums);
     window_teardown(h);
     tile_teardown(h);
+    stream_teardown(h);
     for (auto &g : h->graph_exec) if (g) cudaGraphExecDestroy(g);
     if (h->ev0) cudaEventDestroy(h->ev0);
     if (h->ev1) cudaEventDestroy(h->ev1);
@@ -421,14 +430,14 @@ static void setup_fused_halo(bellman_handle *h, NcclApi *api) {
     cudaIpcMemHandle_t mine;
     std::memset(&mine, 0, sizeof(mine));
     if (ok && cudaIpcGetMemHandle(&mine, h->d_J) != cudaSuccess) { ok = 0; cudaGetLastError(); }
-    unsigned char *d_buf = nullptr;
     const size_t hb = sizeof(cudaIpcMemHandle_t);
-    if (cudaMalloc(&d_buf, hb * (n + 1) + 16) != cudaSuccess) return;
-    if (cudaMalloc(&h->d_barrier, 2 * sizeof(double)) != cudaSuccess) { cudaFree(d_buf); return; }
-    cudaMemcpyAsync(d_buf + hb * n, &mine, hb, cudaMemcpyHostToDevice, h->stream);
+    // the scratch buffers were allocated by bellman_create (a failing cudaMalloc is reported there,
+    // before any collective), so every rank always reaches both collectives below
+    unsigned char *gbuf = h->d_comm_scratch;
+    cudaMemcpyAsync(gbuf + hb * n, &mine, hb, cudaMemcpyHostToDevice, h->stream);
     std::vector<cudaIpcMemHandle_t> all(n);
-    bool comm_ok = api->AllGather(d_buf + hb * n, d_buf, hb, ncclChar, h->comm, h->stream) == ncclSuccess;
-    cudaMemcpyAsync(all.data(), d_buf, hb * n, cudaMemcpyDeviceToHost, h->stream);
+    bool comm_ok = api->AllGather(gbuf + hb * n, gbuf, hb, ncclChar, h->comm, h->stream) == ncclSuccess;
+    cudaMemcpyAsync(all.data(), gbuf, hb * n, cudaMemcpyDeviceToHost, h->stream);
     cudaStreamSynchronize(h->stream);
     h->peer_J.assign(n, nullptr);
     if (ok && comm_ok) {
@@ -447,7 +456,6 @@ static void setup_fused_halo(bellman_handle *h, NcclApi *api) {
         cudaMemcpyAsync(&flag, h->d_barrier, sizeof(double), cudaMemcpyDeviceToHost, h->stream);
         cudaStreamSynchronize(h->stream);
     }
-    cudaFree(d_buf);
     if (flag < 0.5) {
         for (double *&pj : h->peer_J) if (pj) { cudaIpcCloseMemHandle(pj); pj = nullptr; }
         return;
@@ -472,7 +480,8 @@ static void fill_peers(const bellman_handle *h, StageParams &sp, int out_stage) 
             ph.stride[d] = st;
             if (d < hp.D) {
                 int ext = (d == h->part_dim) ? (o.ext_hi - o.ext_lo) : hp.n[d];
-                if (d == 0 && h->part_dim == 0) ext = (ext + 1) & ~1;   // the neighbour's padded leading dimension
+                // the neighbour's padded leading dimension: same rule as bellman_create's ld0
+                if (d == 0 && (hp.D == 2 || h->part_dim == 0)) ext = (ext + 1) & ~1;
                 st *= ext;
             }
         }
@@ -562,10 +571,10 @@ static int pick_kernel(bellman_handle *h, int requested, int &lanes) {
     };
     if (requested == BELLMAN_KERNEL_SPLITC) { lanes = std::max(2, pick_lanes()); return BELLMAN_KERNEL_SPLITC; }
     if (requested == BELLMAN_KERNEL_WINDOW || requested == BELLMAN_KERNEL_TILE)   // the TMA-staged kernels
-        return h->wcfg.valid ? BELLMAN_KERNEL_WINDOW : tile_valid(h) ? BELLMAN_KERNEL_TILE : BELLMAN_KERNEL_DIRECT;
+        return h->wcfg.valid ? BELLMAN_KERNEL_WINDOW : (tile_valid(h) || stream_valid(h)) ? BELLMAN_KERNEL_TILE : BELLMAN_KERNEL_DIRECT;
     // AUTO
     if (h->wcfg.valid && states >= 148LL * 2048) return BELLMAN_KERNEL_WINDOW;
-    if (tile_valid(h) && states >= 148LL * 2048) return BELLMAN_KERNEL_TILE;
+    if ((tile_valid(h) || stream_valid(h)) && states >= 148LL * 2048) return BELLMAN_KERNEL_TILE;
     lanes = pick_lanes();
     return lanes > 1 ? BELLMAN_KERNEL_SPLITC : BELLMAN_KERNEL_DIRECT;
 }
@@ -580,7 +589,9 @@ static int launch_one_stage(bellman_handle *h, int kernel, int lanes) {
     cudaError_t e;
     if (kernel == BELLMAN_KERNEL_SPLITC) e = launch_stage_splitc(sp, lanes, h->stream);
     else if (kernel == BELLMAN_KERNEL_WINDOW) e = window_launch_for_handle(h, sp, h->J_slot(from), h->stream);
-    else if (kernel == BELLMAN_KERNEL_TILE) e = tile_launch_for_handle(h, sp, h->J_slot(from), h->stream);
+    else if (kernel == BELLMAN_KERNEL_TILE)
+        e = stream_valid(h) ? stream_launch_for_handle(h, sp, h->J_slot(from), h->stream)
+                            : tile_launch_for_handle(h, sp, h->J_slot(from), h->stream);
     else e = launch_stage_direct(sp, h->stream);
     if (e != cudaSuccess) { h->err = std::string("stage launch: ") + cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
     h->last_launches += 1;
@@ -600,7 +611,7 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
     CUDA_TRY(h, cudaSetDevice(h->device));
     int lanes = 1;
     const int kernel = pick_kernel(h, o.kernel, lanes);
-    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? window_variant(h) : kernel == BELLMAN_KERNEL_TILE ? "tile"
+    h->last_kernel = kernel == BELLMAN_KERNEL_WINDOW ? window_variant(h) : kernel == BELLMAN_KERNEL_TILE ? (stream_valid(h) ? "stream" : "tile")
                      : kernel == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
     h->last_launches = 0;
     h->last_ms_exchange = 0.0;
@@ -622,8 +633,9 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
             if (next_check >= 1) span = std::min(span, h->cur_stage - next_check);
         }
         // small single-GPU problems: the whole span in ONE cooperative launch (grid barrier per stage)
-        if (o.use_graph && h->nranks == 1 && !o.sync_each_stage && span >= 2 && o.kernel != BELLMAN_KERNEL_DIRECT &&
-            o.kernel != BELLMAN_KERNEL_WINDOW && !std::getenv("BELLMAN_NO_PERSISTENT")) {
+        // (only under BELLMAN_KERNEL_AUTO: an explicitly requested kernel is never silently replaced)
+        if (o.use_graph && h->nranks == 1 && !o.sync_each_stage && span >= 2 && o.kernel == BELLMAN_KERNEL_AUTO &&
+            !std::getenv("BELLMAN_NO_PERSISTENT")) {
             int L = 1;
             const long long states = h->S_own * hp.P;
             // only when a stage is launch-latency sized (< ~2M updates); bigger stages want every

@@ -46,10 +46,12 @@ struct bellman_handle {
     bool fused_halo = false;
     std::vector<double *> peer_J;
     double *d_barrier = nullptr;
+    unsigned char *d_comm_scratch = nullptr;   // IPC-handle all-gather buffer (partitioned handles)
     // window kernel state
     bellman::WindowConfig wcfg;
     void *wstate = nullptr;           // bellman_window.cu: WindowState (tensor maps, chunk tables)
     void *tstate = nullptr;           // bellman_tile.cu: TileState (D = 3 / 4 TMA-staged tile kernel)
+    void *sstate = nullptr;           // bellman_stream.cu: StreamState (D = 4 streaming factorised kernel)
     // cached 2-stage CUDA graphs (ping-pong storage has period 2), keyed by the parity of the
     // slot the first stage reads and by the kernel variant
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};
@@ -80,6 +82,12 @@ void tile_setup(bellman_handle *h);
 void tile_teardown(bellman_handle *h);
 bool tile_valid(const bellman_handle *h);
 cudaError_t tile_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st);
+// bellman_stream.cu: the streaming, factorised D = 4 kernel for Solver_pos_att's channel structure;
+// sstate stays null when the problem does not have that structure
+void stream_setup(bellman_handle *h);
+void stream_teardown(bellman_handle *h);
+bool stream_valid(const bellman_handle *h);
+cudaError_t stream_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st);
 // "window:strip" / "window:chain" / "window:ring-chain" / "window:ring": which TMA-staged kernel runs
 const char *window_variant(const bellman_handle *h);
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next,

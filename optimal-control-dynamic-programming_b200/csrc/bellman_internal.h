@@ -39,6 +39,9 @@ int host_locate(const HostProblem &hp, int p, int d, double x);
 // touched by states whose index along `dim` lies in [own_lo, own_hi)
 void reach_range(const HostProblem &hp, int dim, int own_lo, int own_hi, int &ext_lo, int &ext_hi);
 std::string plan_slabs(const HostProblem &hp, int part_dim, int nranks, bellman_slab *out);
+// exact stencil bounds of dimension d (bellman_tile.cu): over every state and control,
+// cell(x'_d) - i_d in [lo, hi]; false when x'_d does not depend on the state's own index
+bool stencil_reach(const HostProblem &hp, int d, int &lo, int &hi);
 
 // ---------------------------------------------------------------------------------------------
 // Kernel parameter block (passed by value; device pointers address problem 0, rows are P-strided)

@@ -256,6 +256,9 @@ k_stage_splitc(const __grid_constant__ StageParams sp) {
         const int oa = __shfl_xor_sync(0xffffffffu, arg, w, L);
         if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
     }
+    // no control had tot < +inf (every total +inf or NaN): first index, as the serial loop of
+    // k_stage_direct / the oracle / MATLAB's min leave it
+    if (arg == 0x7fffffff) arg = 0;
     if (live && lane == 0) {
         sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
         sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
@@ -335,6 +338,7 @@ k_sweep_persistent(const __grid_constant__ StageParams sp, const __grid_constant
             const int oa = __shfl_xor_sync(0xffffffffu, arg, w);
             if (ob < best || (ob == best && oa < arg)) { best = ob; arg = oa; }
         }
+        if (arg == 0x7fffffff) arg = 0;   // all totals +inf / NaN: first index (see k_stage_splitc)
         if (live && lane == 0) {
             Jo[o_self] = best;
             Io[s] = arg;

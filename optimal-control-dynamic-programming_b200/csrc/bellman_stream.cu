@@ -1,0 +1,546 @@
+// bellman_stream.cu — the D = 4 stage of Solver_pos_att's channel sweep (pos-att/Solver_pos_att.m:
+// 244-297; `[F_gI.Values, U_Optimal_id] = min(J_current + F_gI(x', v', theta', w'), [], 5)` at :272)
+// as a STREAMING, FACTORISED kernel.
+//
+// Structure of the channel (pos-att/Solver_pos_att.m:299-328), two coupled (position, rate) blocks:
+//     x'_0 = Ta_0[i0] + Tb_0[i1]   (control independent)     x'_1 = Ta_1[i1] + Tc_1[c]
+//     x'_2 = Ta_2[i2] + Tb_2[i3]   (control independent)     x'_3 = Ta_3[i3] + Tc_3[c]
+// The normative 4-linear interpolation (include/bellman.h) reduces dimension 0 first, then 1, 2, 3.
+// Its first two levels do not depend on (i2, i3), and the second depends on the control only through
+// Tc_1[c], which takes few distinct values (5 for the 9 thruster combinations: net force 0, +-T, +-2T):
+//     H[m1][m2][m3]  = lerp0( J[c0, m1, m2, m3], J[c0+1, m1, m2, m3];  t0(i0,i1) )
+//     K[f][m2][m3]   = lerp1( H[c1(f)], H[c1(f)+1];  t1(i1, f) )              f = class of Tc_1[c]
+// are shared by every state of the (i0, i1) column and every control of class f.  Per (state, control)
+// only  lerp2 x 2  and  lerp3  remain.  Same operations on the same operands as k_stage_direct, so the
+// results are bit-identical — the factorisation only removes recomputation: 27 + ~12 lerps per state
+// instead of 135, 18 + ~15 shared-memory accesses instead of 144 (k_stage_tile_pa).
+//
+// A CTA owns a patch of T0 x T1 = 32 (i0, i1) columns (one per lane), T2 values of i2 (one per
+// consumer warp) and WALKS i3.  Per step
+//   * one TMA box (cp.async.bulk.tensor.5d) brings the J_{k+1} slab of ONE new dimension-3 node
+//     (B0 x B1 x B2 doubles) into a small ring,
+//   * warp j turns slab row m2 = j into K[f][j][node] for every class f (ring of W3 = stencil + 2 nodes
+//     in shared memory, laid out [node][f][m2][lane]: conflict-free),
+//   * consumer warp w finishes the state (i0, i1, i2 = w, i3): per control it reads the two K values of
+//     the UPPER dimension-3 node (the lower node's pair is the previous step's upper pair, kept in
+//     registers whenever the cells advance by exactly one — a host-built flag per step says so).
+// Ring slot byte offsets of every (i3, control) come from a host table, so the loop has no modular
+// arithmetic.  One __syncthreads per step.
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <type_traits>
+#include <vector>
+
+#include "bellman_handle.h"
+#include "bellman_internal.h"
+
+namespace bellman {
+
+namespace {
+
+constexpr int SMAXF = 6;        // control classes of dimension 1 the kernel keeps in registers
+constexpr int SMAXJ = 4;        // slab ring depth (TMA boxes in flight)
+
+struct StreamParams {
+    int T0, T0_log2, T1, T2, T3;    // tile: T0 * T1 = 32 columns, T2 consumer warps, T3 steps per CTA
+    int ntile[MAXD];
+    int lo[MAXD];                   // stencil lower bounds: cell(x'_d) - i_d >= lo[d]
+    int B0, B1, B2;                 // slab extents (nodes)
+    int NH1;                        // dimension-1 nodes a column needs (2 or 3)
+    int NF1;                        // dimension-1 control classes
+    int span3;                      // dimension-3 nodes a step needs: hi3 - lo3 + 2
+    int W3;                         // K ring slots = span3 + 1
+    int NJ;                         // slab ring slots
+    int slab_doubles;               // doubles per slab slot (128-byte aligned)
+    int ring_doubles;               // W3 * NF1 * B2 * 32
+    int own_stride[MAXD];           // strides of the owned index space (idx_out)
+    uint32_t allmask;               // (1 << C) - 1
+    const double2 *ft0;             // [(p n1 + i1) n0 + i0] = {t0, cell0}
+    const double2 *k1;              // [(p n1 + i1) NF1 + f]  = {t1, cell1 - (i1 + lo1)}
+    const double2 *ft2;             // [(p n3 + i3) n2 + i2] = {t2, cell2 | chain flag << 32}
+    const double2 *lt3;             // [(p n3 + i3) C + c]    = {t3, ring offset of the lower node | upper << 32}
+    const uint32_t *flag3;          // [p n3 + i3]: bit c set when cell3(i3, c) == cell3(i3 - 1, c) + 1
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
+                                            int c3, int c4) {
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];" ::
+            "r"(smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+        : "memory");
+}
+
+template <int C>
+__global__ void __launch_bounds__(384, 1)
+k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ StreamParams tp,
+               const __grid_constant__ CUtensorMap tmap) {
+    extern __shared__ __align__(128) double smem[];
+    __shared__ __align__(8) uint64_t mbar[SMAXJ];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, NW = blockDim.x >> 5;
+    const uint32_t prob = blockIdx.z;
+    const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1], &d2 = sp.dim[2], &d3 = sp.dim[3];
+    const int tx = blockIdx.x % tp.ntile[0], ty = blockIdx.x / tp.ntile[0];
+    const int tz = blockIdx.y % tp.ntile[2], tw = blockIdx.y / tp.ntile[2];
+    const int a0 = d0.own_lo + tx * tp.T0, h0 = min(a0 + tp.T0, d0.own_lo + d0.own_n);
+    const int a1 = d1.own_lo + ty * tp.T1, h1 = min(a1 + tp.T1, d1.own_lo + d1.own_n);
+    const int a2 = d2.own_lo + tz * tp.T2, h2 = min(a2 + tp.T2, d2.own_lo + d2.own_n);
+    const int a3 = d3.own_lo + tw * tp.T3, h3 = min(a3 + tp.T3, d3.own_lo + d3.own_n);
+    int org0 = a0 + tp.lo[0];
+    org0 -= (org0 - d0.ext_lo) & 1;                      // TMA: 16-byte aligned innermost coordinate
+    const int org1 = a1 + tp.lo[1], org2 = a2 + tp.lo[2], m3_first = a3 + tp.lo[3];
+    const int T3n = h3 - a3;
+    const int n_prod = T3n + tp.span3 - 1;               // dimension-3 nodes this CTA turns into K
+    const int n_iter = T3n + tp.span3;                   // node `it` is produced in iteration it, step it - span3 consumed
+    const int NJ = tp.NJ;
+
+    double *ringK = smem;
+    double *slabs = smem + tp.ring_doubles;
+    const uint32_t slab_bytes = (uint32_t)(tp.B0 * tp.B1 * tp.B2) * 8u;
+    auto issue = [&](int node, int slot) {               // thread 0 only
+        mbar_expect_tx(&mbar[slot], slab_bytes);
+        tma_load_5d(slabs + (size_t)slot * tp.slab_doubles, &tmap, &mbar[slot], org0 - d0.ext_lo, org1 - d1.ext_lo,
+                    org2 - d2.ext_lo, m3_first + node - d3.ext_lo, (int)prob);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < NJ; ++s) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        for (int s = 0; s < NJ && s < n_prod; ++s) issue(s, s);
+    }
+
+    // ---- this lane's (i0, i1) column: everything the producer role needs, for the whole walk ----
+    const int l0 = lane & (tp.T0 - 1), l1 = lane >> tp.T0_log2;
+    const bool ok01 = (a0 + l0 < h0) && (a1 + l1 < h1);
+    const int i0 = min(a0 + l0, h0 - 1), i1 = min(a1 + l1, h1 - 1);
+    const double2 e0 = __ldg(tp.ft0 + ((size_t)prob * d1.n + i1) * d0.n + i0);
+    const double t0 = e0.x;
+    const int offA = (__double2loint(e0.y) - org0) + tp.B0 * (i1 - a1);       // doubles, inside a slab row m2
+    double t1[SMAXF];
+    uint32_t selbits = 0;
+#pragma unroll
+    for (int f = 0; f < SMAXF; ++f) {
+        t1[f] = 0.0;
+        if (f < tp.NF1) {
+            const double2 e = __ldg(tp.k1 + ((size_t)prob * d1.n + i1) * tp.NF1 + f);
+            t1[f] = e.x;
+            selbits |= (uint32_t)__double2loint(e.y) << f;
+        }
+    }
+    const int B01 = tp.B0 * tp.B1;
+    const int cls_stride = tp.B2 * 32;                   // doubles between classes inside a ring slot
+    const int slot_stride = tp.NF1 * cls_stride;
+
+    // ---- consumer role: warp w finishes the states (i0, i1, a2 + w, i3) ----
+    const int i2 = a2 + wrp;
+    const bool cons = wrp < tp.T2 && i2 < h2;
+    const int i2c = min(i2, h2 - 1);
+    double a_up[C], d_up[C], rc[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { a_up[c] = 0.0; d_up[c] = 0.0; rc[c] = __ldg(sp.r + prob * (uint32_t)C + c); }
+    const double q0 = __ldg(d0.q + (size_t)prob * d0.n + i0), q1 = __ldg(d1.q + (size_t)prob * d1.n + i1);
+    const double q2 = __ldg(d2.q + (size_t)prob * d2.n + i2c);
+    const double *q3p = d3.q + (size_t)prob * d3.n;
+    const int qo0 = sp.q_order[0], qo1 = sp.q_order[1], qo2 = sp.q_order[2], qo3 = sp.q_order[3];
+    const double2 *ft2p = tp.ft2 + (size_t)prob * d3.n * d2.n + i2c;
+    const double2 *lt3p = tp.lt3 + (size_t)prob * d3.n * C;
+    const uint32_t *flag3p = tp.flag3 + (size_t)prob * d3.n;
+    long long jo = (long long)prob * sp.S_ext + (long long)(i0 - d0.ext_lo) * d0.stride +
+                   (long long)(i1 - d1.ext_lo) * d1.stride + (long long)(i2c - d2.ext_lo) * d2.stride +
+                   (long long)(a3 - d3.ext_lo) * d3.stride;
+    long long io = (long long)prob * sp.S_own + (long long)(i0 - d0.own_lo) * tp.own_stride[0] +
+                   (long long)(i1 - d1.own_lo) * tp.own_stride[1] + (long long)(i2c - d2.own_lo) * tp.own_stride[2] +
+                   (long long)(a3 - d3.own_lo) * tp.own_stride[3];
+
+    __syncthreads();          // mbarriers initialised
+
+    int slotJ = 0, phaseJ = 0, slotK = 0;
+#pragma unroll 1
+    for (int it = 0; it < n_iter; ++it) {
+        // ---- produce: slab row m2 = j of node `it`  ->  K[f][j] of ring slot slotK ----
+        if (it < n_prod) {
+            if (wrp < tp.B2) mbar_wait(&mbar[slotJ], (uint32_t)phaseJ);
+            const double *slab = slabs + (size_t)slotJ * tp.slab_doubles + offA;
+            double *kout = ringK + slotK * slot_stride + lane;
+            for (int j = wrp; j < tp.B2; j += NW) {
+                const double *p = slab + j * B01;
+                const double lo0 = p[0], hi0 = p[1], lo1 = p[tp.B0], hi1 = p[tp.B0 + 1];
+                const double H0 = fma(t0, hi0 - lo0, lo0);
+                const double H1 = fma(t0, hi1 - lo1, lo1);
+                const double dA = H1 - H0;
+                double dB = 0.0;
+                if (tp.NH1 == 3) {
+                    const double lo2 = p[2 * tp.B0], hi2 = p[2 * tp.B0 + 1];
+                    const double H2 = fma(t0, hi2 - lo2, lo2);
+                    dB = H2 - H1;
+                }
+#pragma unroll
+                for (int f = 0; f < SMAXF; ++f)
+                    if (f < tp.NF1) {
+                        const bool s = (selbits >> f) & 1u;
+                        kout[f * cls_stride + j * 32] = fma(t1[f], s ? dB : dA, s ? H1 : H0);
+                    }
+            }
+        }
+        // ---- consume: step i3 = a3 + it - span3 (its nodes were produced in earlier iterations) ----
+        if (cons && it >= tp.span3) {
+            const int i3 = a3 + it - tp.span3;
+            const double2 e2 = __ldg(ft2p + (size_t)i3 * d2.n);
+            const double t2 = e2.x;
+            const uint32_t f3 = __ldg(flag3p + i3);
+            const bool fast = it > tp.span3 && __double2hiint(e2.y) != 0 && f3 == tp.allmask;
+            const double *kb = ringK + ((__double2loint(e2.y) - org2) * 32 + lane);
+            const double q3 = __ldg(q3p + i3);
+            auto qsel = [&](int o) { return o == 0 ? q0 : o == 1 ? q1 : o == 2 ? q2 : q3; };
+            const double gs = ((qsel(qo0) + qsel(qo1)) + qsel(qo2)) + qsel(qo3);
+            const double2 *l3 = lt3p + (size_t)i3 * C;
+            double best = __longlong_as_double(0x7ff0000000000000LL);
+            int arg = 0;
+            auto body = [&](auto fast_tag) {
+                constexpr bool FAST = decltype(fast_tag)::value;
+#pragma unroll
+                for (int c = 0; c < C; ++c) {
+                    const double2 e3 = __ldg(l3 + c);
+                    double alo, dlo;
+                    if (FAST) {
+                        alo = a_up[c];
+                        dlo = d_up[c];
+                    } else {
+                        const int olo = __double2loint(e3.y);
+                        alo = kb[olo];
+                        dlo = kb[olo + 32] - alo;
+                    }
+                    const int oup = __double2hiint(e3.y);
+                    const double au = kb[oup];
+                    const double du = kb[oup + 32] - au;
+                    const double vlo = fma(t2, dlo, alo), vup = fma(t2, du, au);      // dimension 2
+                    const double val = fma(e3.x, vup - vlo, vlo);                     // dimension 3
+                    const double tot = (gs + rc[c]) + val;
+                    if (tot < best) { best = tot; arg = c; }
+                    a_up[c] = au;
+                    d_up[c] = du;
+                }
+            };
+            if (fast) body(std::true_type{});
+            else body(std::false_type{});
+            if (ok01) {
+                sp.J_out[jo] = best;
+                sp.idx_out[io] = arg;
+                if (sp.n_peers) { const int gi[4] = {i0, i1, i2, i3}; peer_store<4>(sp, (int)prob, gi, best); }
+            }
+            jo += d3.stride;
+            io += tp.own_stride[3];
+        }
+        __syncthreads();      // K of node `it` visible; slab slot slotJ and ring slot (it + 1) % W3 free
+        if (tid == 0 && it + NJ < n_prod) issue(it + NJ, slotJ);
+        if (++slotJ == NJ) { slotJ = 0; phaseJ ^= 1; }
+        if (++slotK == tp.W3) slotK = 0;
+    }
+}
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                    const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                    CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                    CUtensorMapFloatOOBfill);
+PFN_encodeTiled get_encode() {
+    static PFN_encodeTiled fn = nullptr;
+    if (fn) return fn;
+    void *p = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) != cudaSuccess ||
+        qr != cudaDriverEntryPointSuccess)
+        return nullptr;
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+    return fn;
+}
+
+struct StreamState {
+    StreamParams tp{};
+    std::vector<CUtensorMap> maps;   // one per J slot
+    size_t smem = 0;
+    int nthreads = 0, C = 0;
+    void *d_tab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    ~StreamState() { for (void *p : d_tab) cudaFree(p); }
+};
+
+double pack_bits(uint32_t lo, uint32_t hi) {
+    const uint64_t b = (uint64_t)lo | ((uint64_t)hi << 32);
+    double d;
+    std::memcpy(&d, &b, 8);
+    return d;
+}
+
+template <int C>
+bool stream_attr(size_t smem) {
+    return cudaFuncSetAttribute((const void *)k_stage_stream<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
+           cudaSuccess;
+}
+
+}  // namespace
+
+void stream_teardown(bellman_handle *h) {
+    delete static_cast<StreamState *>(h->sstate);
+    h->sstate = nullptr;
+}
+
+bool stream_valid(const bellman_handle *h) { return h->sstate != nullptr; }
+
+void stream_setup(bellman_handle *h) {
+    h->sstate = nullptr;
+    const HostProblem &hp = h->hp;
+    if (hp.D != 4 || std::getenv("BELLMAN_NO_STREAM") || std::getenv("BELLMAN_NO_TILE")) return;
+    if (hp.C != 6 && hp.C != 9) return;               // instantiated control counts (9 combinations, 6 in failure mode)
+    if (h->ld0 % 2) return;                           // TMA global strides: multiples of 16 bytes
+    // structure of Solver_pos_att's channel (same test as k_stage_tile_pa)
+    for (int d = 0; d < 4; ++d) {
+        if (hp.src_a[d] != d) return;
+        if (d % 2 == 0 && (hp.has_c[d] || (hp.has_b[d] && hp.src_b[d] != d + 1))) return;
+        if (d % 2 == 1 && (!hp.has_c[d] || (hp.has_b[d] && hp.src_b[d] != d))) return;
+    }
+    PFN_encodeTiled enc = get_encode();
+    if (!enc) return;
+    int lo[4], hi[4];
+    for (int d = 0; d < 4; ++d) {
+        if (!stencil_reach(hp, d, lo[d], hi[d])) return;
+        lo[d] = std::min(lo[d], 0);
+        hi[d] = std::max(hi[d], 0);
+    }
+    if (hi[0] - lo[0] > 6 || hi[1] - lo[1] > 1 || hi[2] - lo[2] > 4 || hi[3] - lo[3] > 40) return;
+    const int C = hp.C, P = hp.P;
+    // classes of dimension 1: controls whose Tc_1 entries are bit-identical in every problem
+    std::vector<int> cls(C, -1);
+    int NF1 = 0;
+    for (int c = 0; c < C; ++c) {
+        for (int e = 0; e < c && cls[c] < 0; ++e) {
+            bool same = true;
+            for (int p = 0; p < P && same; ++p)
+                same = std::memcmp(&hp.Tc[1][(size_t)p * C + c], &hp.Tc[1][(size_t)p * C + e], 8) == 0;
+            if (same) cls[c] = cls[e];
+        }
+        if (cls[c] < 0) cls[c] = NF1++;
+    }
+    if (NF1 > SMAXF) return;
+
+    auto *ss = new StreamState();
+    StreamParams &tp = ss->tp;
+    ss->C = C;
+    int fT1 = 0, fT2 = 0, fT3 = 0, fNJ = 0;
+    if (const char *e = std::getenv("BELLMAN_STREAM")) std::sscanf(e, "%d,%d,%d,%d", &fT1, &fT2, &fT3, &fNJ);
+    tp.T1 = (fT1 == 1 || fT1 == 2 || fT1 == 4) ? fT1 : 2;
+    tp.T0 = 32 / tp.T1;
+    tp.T0_log2 = tp.T1 == 1 ? 5 : tp.T1 == 2 ? 4 : 3;
+    tp.NJ = (fNJ >= 2 && fNJ <= SMAXJ) ? fNJ : 3;
+    for (int d = 0; d < 4; ++d) tp.lo[d] = lo[d];
+    tp.B0 = (tp.T0 + hi[0] - lo[0] + 1 + 1 + 1) / 2 * 2;          // +1: even origin; even extent
+    tp.B1 = tp.T1 + hi[1] - lo[1] + 1;
+    tp.NH1 = hi[1] - lo[1] + 2;
+    tp.NF1 = NF1;
+    tp.span3 = hi[3] - lo[3] + 2;
+    tp.W3 = tp.span3 + 1;
+    const int w2 = hi[2] - lo[2] + 1;
+    auto smem_of = [&](int T2) {
+        const int B2 = T2 + w2;
+        const size_t slab = ((size_t)tp.B0 * tp.B1 * B2 * 8 + 127) / 128 * 128;
+        return (size_t)tp.W3 * NF1 * B2 * 256 + (size_t)tp.NJ * slab;
+    };
+    int T2 = 0;
+    if (fT2 > 0) {
+        T2 = fT2;
+    } else {
+        double best = -1.0;
+        for (int t : {2, 3, 4, 6, 8, 10}) {
+            if (t + w2 > 12) continue;
+            const size_t sm = smem_of(t) + 1024;
+            if (sm > 225 * 1024) continue;
+            const double score = (double)t / (t + w2) * (2 * sm <= 226 * 1024 ? 1.0 : 0.75);
+            if (score > best) { best = score; T2 = t; }
+        }
+    }
+    if (T2 < 1 || T2 + w2 > 12 || smem_of(T2) + 1024 > 225 * 1024) { delete ss; return; }
+    tp.T2 = T2;
+    tp.B2 = T2 + w2;
+    tp.slab_doubles = (int)((((size_t)tp.B0 * tp.B1 * tp.B2 * 8 + 127) / 128 * 128) / 8);
+    tp.ring_doubles = tp.W3 * NF1 * tp.B2 * 32;
+    ss->smem = smem_of(T2);
+    ss->nthreads = 32 * tp.B2;
+    // steps per CTA: the whole owned range unless that leaves the GPU short of CTAs; chunks are
+    // multiples of W3 so that a node's ring slot does not depend on the chunk (host table lt3)
+    tp.ntile[0] = (h->own_n[0] + tp.T0 - 1) / tp.T0;
+    tp.ntile[1] = (h->own_n[1] + tp.T1 - 1) / tp.T1;
+    tp.ntile[2] = (h->own_n[2] + tp.T2 - 1) / tp.T2;
+    {
+        const long long base_ctas = (long long)tp.ntile[0] * tp.ntile[1] * tp.ntile[2] * P;
+        int T3 = h->own_n[3];
+        if (fT3 > 0) T3 = std::max(tp.W3, fT3 / tp.W3 * tp.W3);
+        else
+            while (base_ctas * ((h->own_n[3] + T3 - 1) / T3) < 2LL * 148 * 2 && T3 > 4 * tp.W3)
+                T3 = std::max(4 * tp.W3, (T3 / 2 + tp.W3 - 1) / tp.W3 * tp.W3);
+        tp.T3 = std::min(T3, h->own_n[3]);
+        if (tp.T3 < h->own_n[3] && tp.T3 % tp.W3) tp.T3 = h->own_n[3];
+    }
+    tp.ntile[3] = (h->own_n[3] + tp.T3 - 1) / tp.T3;
+    if ((long long)tp.ntile[0] * tp.ntile[1] > 2147483647LL || (long long)tp.ntile[2] * tp.ntile[3] > 65535 || P > 65535) {
+        delete ss;
+        return;
+    }
+    {
+        int os = 1;
+        for (int d = 0; d < 4; ++d) { tp.own_stride[d] = os; os *= h->own_n[d]; }
+    }
+    tp.allmask = (1u << C) - 1u;
+
+    // ---- host tables, built with the normative operations (one rounding per operation) ----
+    auto locate_t = [&](int p, int d, double xq, int &cell) {
+        const int nd = hp.n[d];
+        const double *sgrid = hp.grid[d].data() + (size_t)p * nd, *ri = hp.rinv[d].data() + (size_t)p * nd;
+        cell = host_locate(hp, p, d, xq);
+        return hp.mode[(size_t)p * hp.D + d] == BELLMAN_LOCATE_UNIFORM ? xq - (double)cell : (xq - sgrid[cell]) * ri[cell];
+    };
+    const int n0 = hp.n[0], n1 = hp.n[1], n2 = hp.n[2], n3 = hp.n[3];
+    std::vector<double> ft0((size_t)P * n1 * n0 * 2), k1((size_t)P * n1 * NF1 * 2), ft2((size_t)P * n3 * n2 * 2),
+        lt3((size_t)P * n3 * C * 2);
+    std::vector<uint32_t> flag3((size_t)P * n3, 0u);
+    std::vector<int> rep(NF1, 0);                     // a representative control of every class
+    for (int c = C - 1; c >= 0; --c) rep[cls[c]] = c;
+    const int own_lo3 = h->own_lo[3];
+    for (int p = 0; p < P; ++p) {
+        for (int i1 = 0; i1 < n1; ++i1) {
+            for (int i0 = 0; i0 < n0; ++i0) {
+                double xq = hp.Ta[0][(size_t)p * n0 + i0];
+                if (hp.has_b[0]) xq = xq + hp.Tb[0][(size_t)p * n1 + i1];
+                int cell;
+                const double t = locate_t(p, 0, xq, cell);
+                const size_t o = (((size_t)p * n1 + i1) * n0 + i0) * 2;
+                ft0[o] = t;
+                ft0[o + 1] = pack_bits((uint32_t)cell, 0);
+            }
+            double b = hp.Ta[1][(size_t)p * n1 + i1];
+            if (hp.has_b[1]) b = b + hp.Tb[1][(size_t)p * n1 + i1];
+            for (int f = 0; f < NF1; ++f) {
+                int cell;
+                const double t = locate_t(p, 1, b + hp.Tc[1][(size_t)p * C + rep[f]], cell);
+                const int sel = cell - (i1 + lo[1]);
+                if (sel < 0 || sel > tp.NH1 - 2) { delete ss; return; }      // cannot happen: lo/hi are exact bounds
+                const size_t o = (((size_t)p * n1 + i1) * NF1 + f) * 2;
+                k1[o] = t;
+                k1[o + 1] = pack_bits((uint32_t)sel, 0);
+            }
+        }
+        std::vector<int> prev2(n2, 0), prev3(C, 0);
+        for (int i3 = 0; i3 < n3; ++i3) {
+            for (int i2 = 0; i2 < n2; ++i2) {
+                double xq = hp.Ta[2][(size_t)p * n2 + i2];
+                if (hp.has_b[2]) xq = xq + hp.Tb[2][(size_t)p * n3 + i3];
+                int cell;
+                const double t = locate_t(p, 2, xq, cell);
+                const size_t o = (((size_t)p * n3 + i3) * n2 + i2) * 2;
+                ft2[o] = t;
+                ft2[o + 1] = pack_bits((uint32_t)cell, (i3 > 0 && cell == prev2[i2]) ? 1u : 0u);
+                prev2[i2] = cell;
+            }
+            double b = hp.Ta[3][(size_t)p * n3 + i3];
+            if (hp.has_b[3]) b = b + hp.Tb[3][(size_t)p * n3 + i3];
+            uint32_t fl = 0;
+            for (int c = 0; c < C; ++c) {
+                int cell;
+                const double t = locate_t(p, 3, b + hp.Tc[3][(size_t)p * C + c], cell);
+                // ring slot of a node: (node - first node of the rank's walk) mod W3; chunk starts are
+                // multiples of W3 steps, so this is the same in every chunk
+                auto slot_off = [&](int node) {
+                    int s = (node - (own_lo3 + lo[3])) % tp.W3;
+                    if (s < 0) s += tp.W3;
+                    return (uint32_t)((s * NF1 + cls[c]) * tp.B2 * 32);
+                };
+                const size_t o = (((size_t)p * n3 + i3) * C + c) * 2;
+                lt3[o] = t;
+                lt3[o + 1] = pack_bits(slot_off(cell), slot_off(cell + 1));
+                if (i3 > 0 && cell == prev3[c] + 1) fl |= 1u << c;
+                prev3[c] = cell;
+            }
+            flag3[(size_t)p * n3 + i3] = fl;
+        }
+    }
+    auto upload = [&](const void *src, size_t bytes, void **dst) {
+        return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
+    };
+    if (!upload(ft0.data(), ft0.size() * 8, &ss->d_tab[0]) || !upload(k1.data(), k1.size() * 8, &ss->d_tab[1]) ||
+        !upload(ft2.data(), ft2.size() * 8, &ss->d_tab[2]) || !upload(lt3.data(), lt3.size() * 8, &ss->d_tab[3]) ||
+        !upload(flag3.data(), flag3.size() * 4, &ss->d_tab[4])) {
+        cudaGetLastError();
+        delete ss;
+        return;
+    }
+    tp.ft0 = static_cast<const double2 *>(ss->d_tab[0]);
+    tp.k1 = static_cast<const double2 *>(ss->d_tab[1]);
+    tp.ft2 = static_cast<const double2 *>(ss->d_tab[2]);
+    tp.lt3 = static_cast<const double2 *>(ss->d_tab[3]);
+    tp.flag3 = static_cast<const uint32_t *>(ss->d_tab[4]);
+
+    // one tensor map per J slot: [P][n3][n2][n1][ld0] fp64, box = B0 x B1 x B2 x 1 x 1
+    const int nslots = h->store_J_all ? hp.N : 2;
+    ss->maps.resize(nslots);
+    for (int s = 0; s < nslots; ++s) {
+        cuuint64_t gdim[5], gstr[4];
+        cuuint32_t box[5] = {(cuuint32_t)tp.B0, (cuuint32_t)tp.B1, (cuuint32_t)tp.B2, 1, 1}, estr[5] = {1, 1, 1, 1, 1};
+        for (int d = 0; d < 4; ++d) gdim[d] = (cuuint64_t)h->ext_n[d];
+        gdim[4] = (cuuint64_t)P;
+        for (int d = 1; d < 4; ++d) gstr[d - 1] = (cuuint64_t)h->stride[d] * 8;
+        gstr[3] = (cuuint64_t)h->S_ext * 8;
+        void *base = h->d_J + (size_t)s * h->slot_elems_J();
+        if (enc(&ss->maps[s], CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 5, base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) {
+            delete ss;
+            return;
+        }
+    }
+    if (!(C == 9 ? stream_attr<9>(ss->smem) : stream_attr<6>(ss->smem))) {
+        cudaGetLastError();
+        delete ss;
+        return;
+    }
+    if (std::getenv("BELLMAN_TILE_DEBUG"))
+        std::fprintf(stderr,
+                     "bellman stream: T = %d %d %d %d, lo = %d %d %d %d hi = %d %d %d %d, slab = %d %d %d, NF1 = %d, W3 = %d, "
+                     "smem = %zu KB, %d threads, grid = %d x %d x %d\n",
+                     tp.T0, tp.T1, tp.T2, tp.T3, lo[0], lo[1], lo[2], lo[3], hi[0], hi[1], hi[2], hi[3], tp.B0, tp.B1, tp.B2, NF1,
+                     tp.W3, ss->smem / 1024, ss->nthreads, tp.ntile[0] * tp.ntile[1], tp.ntile[2] * tp.ntile[3], P);
+    h->sstate = ss;
+}
+
+cudaError_t stream_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st) {
+    auto *ss = static_cast<StreamState *>(h->sstate);
+    if (!ss) return cudaErrorNotSupported;
+    const StreamParams &tp = ss->tp;
+    const dim3 grid((unsigned)(tp.ntile[0] * tp.ntile[1]), (unsigned)(tp.ntile[2] * tp.ntile[3]), (unsigned)sp.P);
+    if (ss->C == 9) k_stage_stream<9><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    else k_stage_stream<6><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    return cudaGetLastError();
+}
+
+}  // namespace bellman

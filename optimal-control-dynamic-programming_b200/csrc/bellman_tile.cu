@@ -491,6 +491,8 @@ struct TileState {
     ~TileState() { for (void *p : d_lt) cudaFree(p); for (void *p : d_ft) cudaFree(p); }
 };
 
+}  // namespace
+
 // Exact stencil bounds of dimension d: min / max over every state and control of
 // cell(x'_d) - i_d.  Floating-point addition is monotone in each argument, so for a fixed own index
 // the extreme queries are (Ta[i] + min Tb) + min Tc and (Ta[i] + max Tb) + max Tc, formed with the
@@ -525,8 +527,6 @@ bool stencil_reach(const HostProblem &hp, int d, int &lo, int &hi) {
     }
     return true;
 }
-
-}  // namespace
 
 }  // namespace bellman
 

@@ -129,7 +129,17 @@ static void cmd_create(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[
     (void)nlhs;
 }
 
-struct Shape { size_t S_own, P; };
+// what the gateway needs to size and check every array argument of a handle
+struct Shape { size_t S_own, P, S_global; int N, C, D; };
+
+// a real double array with exactly `want` elements (the reference hands `single` arrays around,
+// e.g. zeros(...,'single') in Solver_pos_att.m:265 — those must be cast by the caller, not read as
+// doubles here)
+static const double *need_doubles(const mxArray *a, size_t want, const char *what) {
+    if (!a || !mxIsDouble(a) || mxIsComplex(a) || mxGetNumberOfElements(a) != want)
+        mexErrMsgIdAndTxt("bellman:BAD_ARG", "%s must be a real double array with %d elements", what, (int)want);
+    return mxGetPr(a);
+}
 static std::vector<std::pair<bellman_handle *, Shape>> g_shapes;
 
 static Shape shape_of(bellman_handle *h) {
@@ -155,9 +165,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         bellman_owned_range(h, &sl);
         const int D = (int)mxGetNumberOfElements(nn);
         const int pd = (int)field_scalar(s, "part_dim", 0) - 1;
-        size_t S = 1;
-        for (int k = 0; k < D; ++k) S *= (k == pd) ? (size_t)(sl.own_hi - sl.own_lo) : (size_t)mxGetPr(nn)[k];
-        g_shapes.push_back({h, Shape{S, (size_t)field_scalar(s, "P", 1)}});
+        size_t S = 1, Sg = 1;
+        for (int k = 0; k < D; ++k) {
+            S *= (k == pd) ? (size_t)(sl.own_hi - sl.own_lo) : (size_t)mxGetPr(nn)[k];
+            Sg *= (size_t)mxGetPr(nn)[k];
+        }
+        g_shapes.push_back({h, Shape{S, (size_t)field_scalar(s, "P", 1), Sg, (int)field_scalar(s, "N", 0),
+                                     (int)field_scalar(s, "C", 0), D}});
         return;
     }
     if (nrhs < 2) mexErrMsgIdAndTxt("bellman:BAD_ARG", "missing handle");
@@ -170,7 +184,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         for (size_t i = 0; i < g_shapes.size(); ++i) if (g_shapes[i].first == h) { g_shapes.erase(g_shapes.begin() + i); break; }
         if (g_live.empty()) mexUnlock();
     } else if (cmd == "set_J") {
-        const double *J = (nrhs > 2 && !mxIsEmpty(prhs[2])) ? mxGetPr(prhs[2]) : nullptr;
+        const double *J = (nrhs > 2 && !mxIsEmpty(prhs[2])) ? need_doubles(prhs[2], sh.S_global * sh.P, "J") : nullptr;
         check(bellman_set_J(h, J), h);
     } else if (cmd == "run") {
         if (nrhs < 3) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: bellman_mex('run', h, n_stages, opts)");
@@ -217,7 +231,13 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         // [X,U] = bellman_mex('rollout', h, N, A, B, u_values, X0, mode, ssu_stage)
         if (nrhs < 9) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,U] = bellman_mex('rollout', h, N, A, B, u_values, X0, mode, ssu_stage)");
         const int N = (int)mxGetScalar(prhs[2]);
+        if (N != sh.N) mexErrMsgIdAndTxt("bellman:BAD_ARG", "rollout: N = %d differs from the handle's horizon %d", N, sh.N);
         const size_t batch = mxGetNumberOfElements(prhs[6]) / 2;
+        if (batch < 1 || !mxIsDouble(prhs[6]) || mxGetNumberOfElements(prhs[6]) != 2 * batch)
+            mexErrMsgIdAndTxt("bellman:BAD_ARG", "rollout: X0 must be a 2-by-batch double array");
+        need_doubles(prhs[3], 4, "A");
+        need_doubles(prhs[4], 2, "B");
+        need_doubles(prhs[5], (size_t)sh.C, "u_values");
         plhs[0] = mxCreateDoubleMatrix(2, (size_t)N * batch, mxREAL);     // [2][N][batch]
         mxArray *U = mxCreateDoubleMatrix((size_t)N, batch, mxREAL);
         check(bellman_rollout(h, mxGetPr(prhs[3]), mxGetPr(prhs[4]), mxGetPr(prhs[5]), mxGetPr(prhs[6]),
@@ -227,7 +247,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     } else if (cmd == "set_stage") {
         // bellman_mex('set_stage', h, stage, J, U_Optimal_id)   (J [] = zeros; U_Optimal_id 1-based, [] = none)
         if (nrhs < 3) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: bellman_mex('set_stage', h, stage, J, idx)");
-        const double *J = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? mxGetPr(prhs[3]) : nullptr;
+        const double *J = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? need_doubles(prhs[3], sh.S_global * sh.P, "J") : nullptr;
         std::vector<int32_t> idx;
         if (nrhs > 4 && !mxIsEmpty(prhs[4])) {
             const size_t n = mxGetNumberOfElements(prhs[4]);
@@ -240,6 +260,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         // id = bellman_mex('policy_lookup', h, prob, stage, X)   X is D-by-batch; id is 1-based like U_Optimal_id
         if (nrhs < 5) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: id = bellman_mex('policy_lookup', h, prob, stage, X)");
         const size_t batch = mxGetN(prhs[4]);
+        need_doubles(prhs[4], (size_t)sh.D * batch, "X (D-by-batch)");
         plhs[0] = mxCreateNumericMatrix(1, batch, mxINT32_CLASS, mxREAL);
         int32_t *p = static_cast<int32_t *>(mxGetData(plhs[0]));
         check(bellman_policy_lookup(h, (int32_t)mxGetScalar(prhs[2]) - 1, (int32_t)mxGetScalar(prhs[3]), mxGetPr(prhs[4]),
@@ -250,6 +271,9 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         if (nrhs < 10) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,id] = bellman_mex('rollout_axis', h, prob, time_varying, stage, rate_dim, h_step, u_inc, X0, n_steps)");
         const size_t batch = mxGetN(prhs[8]);
         const int n_steps = (int)mxGetScalar(prhs[9]);
+        if (n_steps < 1) mexErrMsgIdAndTxt("bellman:BAD_ARG", "rollout_axis: n_steps must be positive");
+        need_doubles(prhs[7], (size_t)sh.C, "u_inc");
+        need_doubles(prhs[8], 2 * batch, "X0 (2-by-batch)");
         plhs[0] = mxCreateDoubleMatrix(2, (size_t)(n_steps + 1) * batch, mxREAL);   // [2][n_steps+1][batch]
         mxArray *id = mxCreateNumericMatrix((size_t)n_steps, batch, mxINT32_CLASS, mxREAL);
         int32_t *p = static_cast<int32_t *>(mxGetData(id));

@@ -36,6 +36,7 @@ size_t mxGetNumberOfElements(const mxArray *a);
 size_t mxGetM(const mxArray *a);
 size_t mxGetN(const mxArray *a);
 int mxIsDouble(const mxArray *a);
+int mxIsComplex(const mxArray *a);
 void mxDestroyArray(mxArray *a);
 int mxIsStruct(const mxArray *a);
 int mxIsCell(const mxArray *a);

@@ -520,21 +520,34 @@ def test_strip_kernel_ragged_random(bellman, oracle_lib, shape):
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"strip {shape}")
 
 
+FAMILIES = ["stream", "tile"]   # k_stage_stream (default for Solver_pos_att's structure) / k_stage_tile_pa
+
+
+def pick_family(monkeypatch, family):
+    if family == "tile":
+        monkeypatch.setenv("BELLMAN_NO_STREAM", "1")
+
+
+@pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("failure", [False, True])
-def test_tile_kernel_pos_att_reference_size(bellman, oracle_lib, failure):
-    """k_stage_tile (TMA box per 4-D state tile) on config 5 at the reference's own size (30x30x20x15 x 9)."""
+def test_tile_kernel_pos_att_reference_size(bellman, oracle_lib, monkeypatch, failure, family):
+    """the TMA-staged D = 4 kernels on config 5 at the reference's own size (30x30x20x15 x 9; 6 controls
+    in failure mode): the streaming factorised kernel and the one-box-per-tile kernel."""
+    pick_family(monkeypatch, family)
     sp = bellman.Solver_pos_att()
     d = sp.channel_desc(0, failure=failure)
     ora = oracle_lib.sweep(d, n_stages=6)
     with bellman.Sweep(d) as sw:
         sw.run(6, kernel=KERNELS["tile"])
-        assert sw.last_kernel == "tile"
-        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "pos-att tile")
+        assert sw.last_kernel == family
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "pos-att " + family)
 
 
+@pytest.mark.parametrize("family", FAMILIES)
 @pytest.mark.parametrize("mesh", [(34, 9, 7, 5), (10, 8, 6, 4), (66, 3, 2, 9), (64, 16, 8, 8)])
-def test_tile_kernel_ragged_random(bellman, oracle_lib, mesh):
+def test_tile_kernel_ragged_random(bellman, oracle_lib, monkeypatch, mesh, family):
     """ragged tiles in every dimension, clamped edges, rough terminal cost, all three channels, D = 4 and D = 3."""
+    pick_family(monkeypatch, family)
     t = bellman.tables
     rng = np.random.default_rng(mesh[0])
     sp = bellman.Solver_pos_att()
@@ -546,8 +559,8 @@ def test_tile_kernel_ragged_random(bellman, oracle_lib, mesh):
         with bellman.Sweep(d) as sw:
             sw.set_J(JN)
             sw.run(3, kernel=KERNELS["tile"])
-            assert sw.last_kernel == "tile"
-            assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"tile {mesh} ch{ch}")
+            assert sw.last_kernel == family
+            assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"{family} {mesh} ch{ch}")
     d4 = sp.channel_desc(2)
     d3 = t.Desc(n=d4.n[:3], C=d4.C, N=6, grid=d4.grid[:3], src_a=[0, 1, 2], src_b=[1, -1, -1],
                 Ta=d4.Ta[:3], Tb=[d4.Tb[0], None, None], Tc=[None, d4.Tc[1], d4.Tc[3]],
@@ -600,6 +613,7 @@ def test_strip_kernel_geometries(bellman, oracle_lib, monkeypatch, env):
                                  {"BELLMAN_TILE_PF": "3"}, {"BELLMAN_TILE": "1,8,2", "BELLMAN_TILE_NT": "256"}])
 def test_tile_kernel_variants(bellman, oracle_lib, monkeypatch, env):
     """the 256-thread form, the generic (run-time structure) tile kernel, forced tile shapes and the L2 prefetch."""
+    monkeypatch.setenv("BELLMAN_NO_STREAM", "1")
     for k, v in env.items():
         monkeypatch.setenv(k, v)
     rng = np.random.default_rng(4)
@@ -615,10 +629,33 @@ def test_tile_kernel_variants(bellman, oracle_lib, monkeypatch, env):
         assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"tile {env}")
 
 
-def test_pos_att_x4_full_size_spot_check(bellman, oracle_lib):
+@pytest.mark.parametrize("env", [{"BELLMAN_STREAM": "1,2,0,2"}, {"BELLMAN_STREAM": "2,3,8,4"}, {"BELLMAN_STREAM": "4,4,0,3"},
+                                 {"BELLMAN_STREAM": "2,8,4,3"}, {"BELLMAN_STREAM": "2,10,0,2"}])
+def test_stream_kernel_variants(bellman, oracle_lib, monkeypatch, env):
+    """k_stage_stream with forced geometry "T1,T2,T3,NJ": 32x1 / 16x2 / 8x4 column patches, 2..10 consumer
+    warps, the walk cut into chunks (T3, a multiple of the ring length), slab rings of 2..4 boxes; rough
+    terminal cost, three channels with different grids, several stages (ping-pong slots)."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(4)
+    sp = bellman.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 40, 12, 10, 14
+    d = bellman.tables.stack_problems([sp.channel_desc(c) for c in range(3)])
+    JN = rng.normal(size=(3, d.S)) * 2
+    ora = oracle_lib.sweep(d, n_stages=3, J_N=JN)
+    with bellman.Sweep(d) as sw:
+        sw.set_J(JN)
+        sw.run(3, kernel=KERNELS["tile"])
+        assert sw.last_kernel == "stream"
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"stream {env}")
+
+
+@pytest.mark.parametrize("family", FAMILIES)
+def test_pos_att_x4_full_size_spot_check(bellman, oracle_lib, monkeypatch, family):
     """the bench's pos-att workload at full size (one channel of 120 x 120 x 80 x 60 x 9; the thrusters
     move w by up to +-5 cells per stage here, so the tile kernel's box is much wider than in the small
     tests): two stages with the tile kernel, 60k sampled states against the oracle's pointwise evaluator."""
+    pick_family(monkeypatch, family)
     sp = bellman.Solver_pos_att()
     sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 120, 120, 80, 60
     d = sp.channel_desc(0)
@@ -629,7 +666,7 @@ def test_pos_att_x4_full_size_spot_check(bellman, oracle_lib):
     with bellman.Sweep(d) as sw:
         sw.set_J(JN)
         sw.run(1)
-        assert sw.last_kernel == "tile"
+        assert sw.last_kernel == family
         J1, I1 = sw.get_J(), sw.get_idx()
         sw.run(1)
         J2, I2 = sw.get_J(), sw.get_idx()
