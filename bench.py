@@ -39,18 +39,29 @@ WORKLOADS = {
     "pos_att_ref_30x30x20x15x9": dict(kind="pos_att", scale=1),
     "pos_att_x4_120x120x80x60x9": dict(kind="pos_att", scale=4),
     "pos_att_x8_1ch_240x240x160x120x9": dict(kind="pos_att", scale=8, channels=1),   # single-GPU slice of configs[4]
+    # BASELINE.json configs[4]: the coupled position+attitude grid sized to fill the HBM of the GPUs it runs
+    # on.  One channel, 480 x 480 x (160 per GPU) x 120 states = 4.4e9 states (88 GB of J + argmin) PER GPU;
+    # the theta range grows with the GPU count (constant resolution), the grid is cut into theta slabs.
+    "pos_att_cfg5_480x480x160Nx120x9": dict(kind="pos_att_cfg5", n=(480, 480, 160, 120)),
 }
 DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch, from the committed
-# `ncu --set full` capture of the same command (profiles/r01_window_kirk_ncu_raw.csv)
-NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": 548.0e6 + 772.5e6,          # profiles/r01_window_kirk_summary.txt
-               "attitude_x16_3x16000x4800x3": 1.8434e9 + 2.7178e9,       # profiles/r01_strip_att16_summary.txt
-               "pos_att_x4_120x120x80x60x9": 3.5679e9 + 2.4639e9}        # profiles/r01_tile_posatt4_summary.txt
+# dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch.  NOT measured by this run (a
+# run under ncu is never a bench value): constants copied from the committed `ncu --set full` captures of
+# the same command, each with the file it comes from; reported as roofline.traffic + traffic_source.
+NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": (548.0e6 + 772.5e6, "profiles/r01_window_kirk_summary.txt"),
+               "attitude_x16_3x16000x4800x3": (1.8434e9 + 2.7178e9, "profiles/r01_strip_att16_summary.txt"),
+               "pos_att_x4_120x120x80x60x9": (2.1758e9 + 2.4519e9, "profiles/r02_stream_posatt4_summary.txt")}
 
 
-def make_desc(bb, name):
+def make_desc(bb, name, world=1):
     w = WORKLOADS[name]
     t = bb.tables
+    if w["kind"] == "pos_att_cfg5":
+        s = bb.Solver_pos_att()
+        nx, nv, nt, nw = w["n"]
+        s.n_mesh_x, s.n_mesh_v, s.n_mesh_t, s.n_mesh_w = nx, nv, nt * world, nw
+        s.theta1_min, s.theta1_max = s.theta1_min * world, s.theta1_max * world   # constant resolution: the range grows with the GPUs
+        return s.channel_desc(0)
     if w["kind"] == "kirk":
         o = bb.Dynamic_Solver()
         return t.kirk_desc(o.A, o.B, o.Q, o.R, w["N"], o.x_min, o.x_max, w["dx"], o.u_min, o.u_max, w["du"],
@@ -200,6 +211,82 @@ def run_reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def cpu_slab_rate(d, seconds_target, threads=0):
+    """The oracle on a CONTIGUOUS slab of states (whole rows of the last dimension, all problems): the
+    cache-friendly counterpart of cpu_sample_rate's random states.  Needs the full J arrays on the host, so
+    only for grids up to 2^28 states.  Returns (updates/s, cores, description) or None."""
+    from oracle import cbind
+    if d.S * d.P > 2 ** 28:
+        return None
+    cbind.set_threads(threads or len(os.sched_getaffinity(0)))
+    cores = cbind.num_threads()
+    rng = np.random.default_rng(1)
+    Jn = rng.normal(size=(d.P, d.S))
+    pd = d.D - 1
+    per_index = d.S // d.n[pd] * d.P * d.C                      # updates per index of the last dimension
+    t0 = time.perf_counter(); cbind.stage(d, Jn, part_dim=pd, own_lo=0, own_hi=1); dt = time.perf_counter() - t0
+    width = int(min(d.n[pd], max(1, per_index / max(dt, 1e-9) * seconds_target / per_index)))
+    lo = (d.n[pd] - width) // 2
+    t0 = time.perf_counter(); cbind.stage(d, Jn, part_dim=pd, own_lo=lo, own_hi=lo + width); dt = time.perf_counter() - t0
+    return width * per_index / dt, cores, "contiguous slab: %d of %d indices of dimension %d, all %d problems (%.1f s)" % (
+        width, d.n[pd], pd, d.P, dt)
+
+
+def sharded_parity(bb, sw, d, rank, world, part_dim, kernel, n_points=3000):
+    """Outside the timed region: two stages from a zero terminal cost on the (sharded) handle, then this
+    rank's states of the SECOND stage are compared bit for bit with the oracle's pointwise evaluator, which
+    rebuilds J of the first stage in closed form (so this works at grid sizes no host array could hold).
+    The second stage reads the halo values the NEIGHBOURS stored during the first one, so the sample is
+    concentrated on the slab faces.  Returns True when every sampled state matches."""
+    from oracle import cbind
+    cbind.build()
+    cbind.set_threads(len(os.sched_getaffinity(0)) // max(1, min(world, 8)) or 1)
+    sw.set_J(None)
+    sw.run(2, kernel=kernel)
+    rng = np.random.default_rng(100 + rank)
+    own = [(0, n) for n in d.n]
+    if world > 1:
+        own[part_dim] = (sw.slab[0], sw.slab[1])
+    coords = []
+    for k, (lo, hi) in enumerate(own):
+        c = rng.integers(lo, hi, size=n_points)
+        if world > 1 and k == part_dim:        # two thirds of the sample within 4 indices of a slab face
+            m = n_points // 3
+            c[:m] = np.minimum(lo + rng.integers(0, 4, size=m), hi - 1)
+            c[m:2 * m] = np.maximum(hi - 1 - rng.integers(0, 4, size=m), lo)
+        coords.append(c.astype(np.int64))
+    lin = np.zeros(n_points, dtype=np.int64)
+    stride = 1
+    for k in range(d.D):
+        lin += coords[k] * stride
+        stride *= d.n[k]
+    ok = True
+    for p in range(d.P):
+        Jg, Ig = sw.get_points(lin, prob=p)
+        Jo, Io = cbind.stage_points(d, None, lin, p=p)
+        ok = ok and bool(np.array_equal(Jg, Jo) and np.array_equal(Ig, Io))
+    return ok
+
+
+def rollout_rate(bb, local):
+    """get_optimal_path rollouts of the default Kirk problem (100 x 100 x 1000, N = 200) from a
+    64 x 64 lattice of initial states, one GPU thread per x0, through bellman_rollout (host buffers)."""
+    o = bb.Dynamic_Solver()
+    d = o._build()
+    sw = bb.Sweep(d, device=local).run()
+    g = np.linspace(o.x_min, o.x_max, 64)
+    x0 = np.stack(np.meshgrid(g, g, indexing="ij"), axis=-1).reshape(-1, 2)
+    sw.rollout(o.A, o.B, d.meta["U_mesh"], x0)                 # warm-up
+    t0 = time.perf_counter()
+    reps = 5
+    for _ in range(reps):
+        sw.rollout(o.A, o.B, d.meta["U_mesh"], x0)
+    dt = (time.perf_counter() - t0) / reps
+    sw.close()
+    return {"x0": len(x0), "steps": d.N - 1, "ms": dt * 1e3, "trajectories_per_s": len(x0) / dt,
+            "state_steps_per_s": len(x0) * (d.N - 1) / dt, "call": "bellman_rollout (host x0 in, X and U out)"}
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -246,22 +333,26 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    d = make_desc(bb, args.workload)
+    d = make_desc(bb, args.workload, world)
     # slab dimension: the one whose halo is smallest (host-side reach analysis, no GPU needed)
-    part_dim = -1
-    if world > 1:
+    def pick_part_dim(dd):
+        if world == 1:
+            return -1
         best = None
-        for pd in range(d.D):
+        for pd in range(dd.D):
             try:
-                sl = bb.plan_slabs(d, pd, world)
+                sl = bb.plan_slabs(dd, pd, world)
             except bb.BellmanError:
                 continue
             cost = max((e - c) / max(b - a, 1) for a, b, c, e in sl)
             if best is None or cost < best[0] - 1e-9:
                 best = (cost, pd)
-        part_dim = best[1]
-    def open_sweep(pd):
-        s = bb.Sweep(d, device=local, part_dim=pd, rank=rank, nranks=world)
+        return best[1]
+
+    part_dim = pick_part_dim(d)
+
+    def open_sweep(pd, dd=None):
+        s = bb.Sweep(dd if dd is not None else d, device=local, part_dim=pd, rank=rank, nranks=world)
         if world > 1:
             ids = [bb.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -332,16 +423,61 @@ def main():
                "d2h_bytes_per_step": int(own * 12), "steps": Ke,
                "call": "bellman_set_J(host) + bellman_run(1) + bellman_get_J(host) + bellman_get_idx(host)"}
 
-    if rank != 0:
+    # ---- outside the timed region: bit-exact spot check of this rank's slab against the oracle -------
+    def all_ok(flag):
+        if world == 1:
+            return bool(flag)
+        t = torch.tensor([1 if flag else 0], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MIN)
+        return int(t.item()) == 1
+
+    parity = {"main": "pass" if all_ok(sharded_parity(bb, sw, d, rank, world, part_dim, kernel)) else "FAIL"}
+    main_kernel, main_halo, main_launches = sw.last_kernel, (sw.halo_mode if world > 1 else None), st["launches"]
+
+    # ---- configs[4]: the pos-att grid sized to the HBM of the GPUs in use (weak scaling: 4.4e9 states per GPU)
+    cfg5 = None
+    if not args.no_others and args.workload == DEFAULT_WORKLOAD:
         sw.close()
+        sw = None
+        name5 = "pos_att_cfg5_480x480x160Nx120x9"
+        free_b, _tot = torch.cuda.mem_get_info()
+        d5 = make_desc(bb, name5, world)
+        need = d5.S // world * 21 * 1.05
+        fits = all_ok(free_b > need + (4 << 30))
+        if fits:
+            pd5 = pick_part_dim(d5)
+            s5 = open_sweep(pd5, d5)
+            s5.run(3)
+            barrier()
+            s5.run(5)
+            barrier()
+            t5 = s5.stats()
+            ms5 = max_over_ranks(t5["ms"]) / 5
+            mx5 = max_over_ranks(t5["ms_exchange"]) / 5
+            ok5 = all_ok(sharded_parity(bb, s5, d5, rank, world, pd5, bb.KERNEL_AUTO, n_points=1500))
+            parity["cfg5"] = "pass" if ok5 else "FAIL"
+            peak5, _ = measured_peak_gbs()
+            cfg5 = {"workload": name5, "grid": d5.n, "controls": d5.C, "states_per_gpu": d5.S // world,
+                    "scaling": "weak", "partition": "dim %d slabs over %d ranks" % (pd5, world) if world > 1 else "none",
+                    "halo": s5.halo_mode if world > 1 else None, "kernel": s5.last_kernel, "ms_per_step": ms5,
+                    "exchange_ms_per_step": mx5, "value": d5.S * d5.C / (ms5 * 1e-3), "unit": UNIT,
+                    "hbm_frac": d5.S // world * 20 / (ms5 * 1e-3) / 1e9 / peak5,
+                    "bytes_per_gpu": int(d5.S // world * 20), "sharded_parity": parity["cfg5"]}
+            s5.close()
+        else:
+            cfg5 = {"workload": name5, "skipped": "needs %.0f GB per GPU, %.0f GB free" % (need / 1e9, free_b / 1e9)}
+
+    if rank != 0:
+        if sw is not None:
+            sw.close()
         if world > 1:
             dist.destroy_process_group()
         return
 
     # ---- roofline of the stage kernel ---------------------------------------------------------
     peak, peak_src = measured_peak_gbs()
-    kernel_name = sw.last_kernel
-    halo_mode = sw.halo_mode if world > 1 else None
+    kernel_name = main_kernel
+    halo_mode = main_halo
     bytes_per_launch = (S_all / world) * (16 + 4)          # read J_{k+1}, write J_k, write int32 argmin
     ms_kernel = (ms_dev - ms_x) / K
     achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
@@ -350,7 +486,8 @@ def main():
     fp64_ops_per_update = 17.0     # window kernel interior loop, SASS-counted: 13 DADD (incl. 2 x 3 for the fp64-pipe floor) + 3 DFMA + 1 DSETP
     fp64_peak = 64 * 148 * mhz * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": NCU_TRAFFIC.get(args.workload), "peak_source": peak_src,
+                "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0],
+                "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1], "peak_source": peak_src,
                 "bytes_per_launch": bytes_per_launch, "kernel_ms": ms_kernel, "kernel": kernel_name,
                 "fp64_secondary": {"ops_per_update": fp64_ops_per_update,
                                    "achieved_ops_per_s": value / world * fp64_ops_per_update,
@@ -362,8 +499,6 @@ def main():
     # the small-control ones are where the HBM roofline is the relevant bound
     others = {}
     if world == 1 and not args.no_others and args.workload == DEFAULT_WORKLOAD:
-        sw.close()
-        sw = None
         for name, steps in (("attitude_x16_3x16000x4800x3", 20), ("attitude_x4_3x4000x1200x3", 40),
                             ("position_3x201x201x3", 400), ("kirk_default_100x100x1000", 40),
                             ("pos_att_x4_120x120x80x60x9", 5)):
@@ -386,13 +521,18 @@ def main():
             roofline["hbm_bound_workload"] = {
                 "workload": "attitude_x16_3x16000x4800x3", "kernel": hb["kernel"], "kernel_ms": hb["ms_per_step"],
                 "achieved": hb["hbm_frac"] * peak, "peak": peak, "unit": "GB/s", "frac": hb["hbm_frac"],
-                "bytes_per_launch": 3 * 16000 * 4800 * 20, "traffic": NCU_TRAFFIC.get("attitude_x16_3x16000x4800x3")}
+                "bytes_per_launch": 3 * 16000 * 4800 * 20, "traffic": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][0],
+                "traffic_source": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][1]}
+        others["rollout_64x64_x0"] = rollout_rate(bb, local)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
-        r, cores, sample, _ = cpu_sample_rate(d, 12.0)
+        r, cores, sample, _ = cpu_sample_rate(d, 8.0)
         cpu = {"value": r, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                "reference_shaped": cpu_reference_shaped_rate(bb, args.workload)}
+        slab = cpu_slab_rate(d, 6.0)
+        if slab:
+            cpu["contiguous_slab"] = {"value": slab[0], "unit": UNIT, "cores": slab[1], "sample": slab[2]}
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -401,20 +541,23 @@ def main():
                        "step": "one backward stage over the whole grid",
                        "partition": ("dim %d slabs over %d ranks; halo: %s" % (
                            part_dim, world,
-                           "stored into peer memory by the stage kernel (NVLink P2P) + 1-element all-reduce barrier"
+                           "stored into peer memory by the stage kernel (NVLink P2P); stages ordered by neighbour-only release/acquire flags"
                            if halo_mode == "p2p" else "grouped ncclSend/ncclRecv after each stage"))
                        if world > 1 else "none",
                        "l2": "J_{k+1} (%.0f MB) exceeds the 126 MB L2; no flush needed" % (S_all * 8 / 1e6)
                        if S_all * 8 > 130e6 else "inputs fit L2 (stage-to-stage reuse is the workload)",
                        "cuda_graph": bool(use_graph)},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(main_launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K,
+            "sharded_parity": parity["main"], "parity_checks": parity, "cfg5": cfg5,
             "other_workloads": others}
     print(json.dumps(line), flush=True)
     if sw is not None:
         sw.close()
     if world > 1:
         dist.destroy_process_group()
+    if "FAIL" in parity.values():
+        raise SystemExit("sharded parity check FAILED: %s" % parity)
 
 
 if __name__ == "__main__":

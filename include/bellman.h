@@ -172,7 +172,8 @@ void bellman_destroy(bellman_handle *h);
 int  bellman_get_unique_id(void *id128_out);
 int  bellman_comm_init(bellman_handle *h, const void *id128);
 /* 1: halo states are stored straight into the neighbours' J buffers by the stage kernel (CUDA IPC
- * peer memory over NVLink) and a stage ends with a 1-element all-reduce barrier;
+ * peer memory over NVLink); stages are ordered by neighbour-only release/acquire flags (each rank
+ * publishes its stage count into its neighbours and waits for theirs), no collective per stage;
  * 0: grouped ncclSend/ncclRecv of the halo ranges after every stage (fallback, or BELLMAN_NO_P2P=1);
  * valid after bellman_comm_init */
 int  bellman_halo_mode(const bellman_handle *h);
@@ -190,6 +191,11 @@ int  bellman_run(bellman_handle *h, int32_t n_stages, const bellman_run_opts *op
 int  bellman_current_stage(const bellman_handle *h);        /* stage number of the current J    */
 int  bellman_get_J(bellman_handle *h, int32_t stage, double *J_host_out /*[P][S_own]*/);
 int  bellman_get_idx(bellman_handle *h, int32_t stage, int32_t *idx_host_out /*[P][S_own]*/);
+/* J and (idx_out != NULL) argmin of `stage` at listed states of problem `prob`: states[m] is a GLOBAL
+ * linear index (dimension 0 fastest) and must lie in this rank's owned range.  For spot checks and
+ * sub-array reads at grid sizes whose full arrays are impractical to copy to the host. */
+int  bellman_get_points(bellman_handle *h, int32_t stage, int32_t prob, const int64_t *states, int64_t n,
+                        double *J_out, int32_t *idx_out);
 int  bellman_get_check_log(const bellman_handle *h, double *out /*[max][3]: stage,sumJ,sumIdx*/,
                            int32_t max_entries);
 int  bellman_owned_range(const bellman_handle *h, bellman_slab *out);
@@ -235,6 +241,33 @@ int  bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t time_varying,
                           int32_t rate_dim, double h_step, const double *u_inc /*[C]*/,
                           const double *x0, int32_t batch, int32_t n_steps, double *X_out,
                           int32_t *C_out);
+
+/* Orbital forward simulation of Solver_position.get_optimal_path (position-control/Solver_position.m:
+ * 189-224): every stage k the three axis policies are evaluated at the nearest grid node,
+ *     a_x = U1_Opt(x1, v1), a_y = U2_Opt(x2, v2), a_z = U3_Opt(x3, v3)                    (:215-217)
+ * and the relative-motion equations of :259-309 (the target orbit propagated with the universal
+ * Kepler equation, position-control/private/kepler_U.m, f_and_g.m, fDot_and_gDot.m, stumpC.m,
+ * stumpS.m; update_RV_target :333-361) are integrated from tspan(k) to tspan(k+1) = k*h by the
+ * adaptive Runge-Kutta-Fehlberg 4(5) of position-control/private/rkf45.m:49-118 (first step
+ * (tf-t0)/100, growth <= 4x, stop below 16*eps(t)).  One GPU thread per initial state.
+ * Needs D = 2 and P >= 3 (problems 0..2 = the x, y, z axes), the policy of `stage` available.
+ * y0 is [6][batch] (dr, dv of each trajectory, batch slowest); X_out [6][n_steps/stride_out + 1][batch],
+ * C_out [3][n_steps/stride_out][batch] (0-based control index of each axis at the stored stages),
+ * warn_out [batch] (may be NULL) counts rkf45 calls that stopped on the minimum step size.
+ * The transcendental functions are CUDA's: results agree with the CPU restatement to a tolerance. */
+typedef struct bellman_orbit_opts {
+    int32_t struct_size;     /* = sizeof(bellman_orbit_opts)                                   */
+    int32_t n_steps;         /* stages to simulate (reference: ceil(T_final/h) - 1)            */
+    int32_t stride_out;      /* store every stride_out-th stage; n_steps %% stride_out == 0    */
+    int32_t max_rkf_steps;   /* bound on rkf45 iterations per stage, 0 = 100000               */
+    double  mu;              /* gravitational parameter (398600)                               */
+    double  R0[3], V0[3];    /* target state vector at t = 0 (get_target_R0V0, :313-331)       */
+    double  h;               /* stage length obj.h                                             */
+    double  tol;             /* rkf45 tolerance (rkf45.m:62: 1e-8)                             */
+} bellman_orbit_opts;
+int  bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bellman_orbit_opts *o,
+                           const double *u_values /*[C]*/, const double *y0, int32_t batch,
+                           double *X_out, int32_t *C_out, int32_t *warn_out);
 
 #ifdef __cplusplus
 }

@@ -43,6 +43,12 @@ class CRunOpts(C.Structure):
                 ("check_tol", C.c_double), ("use_graph", C.c_int32), ("sync_each_stage", C.c_int32)]
 
 
+class COrbitOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_steps", C.c_int32), ("stride_out", C.c_int32),
+                ("max_rkf_steps", C.c_int32), ("mu", C.c_double), ("R0", C.c_double * 3), ("V0", C.c_double * 3),
+                ("h", C.c_double), ("tol", C.c_double)]
+
+
 class CSlab(C.Structure):
     _fields_ = [("own_lo", C.c_int32), ("own_hi", C.c_int32), ("ext_lo", C.c_int32), ("ext_hi", C.c_int32)]
 
@@ -54,6 +60,7 @@ EXPORTS = [
     "bellman_set_J", "bellman_set_stage", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
+    "bellman_rollout_orbit", "bellman_get_points",
 ]
 
 _lib = None
@@ -94,6 +101,8 @@ def load():
     lib.bellman_policy_lookup.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _ip]
     lib.bellman_rollout_axis.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp,
                                          _dp, C.c_int32, C.c_int32, _dp, _ip]
+    lib.bellman_get_points.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, _dp, _ip]
+    lib.bellman_rollout_orbit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(COrbitOpts), _dp, _dp, C.c_int32, _dp, _ip, _ip]
     _lib = lib
     return lib
 
@@ -273,6 +282,16 @@ class Sweep:
         self._check(self.lib.bellman_get_J(self.h, int(stage), out.ctypes.data_as(_dp)))
         return out
 
+    def get_points(self, states, prob=0, stage=None, with_idx=True):
+        """J (and argmin) of ``stage`` at GLOBAL linear state indices that lie in this rank's slab."""
+        stage = self.current_stage if stage is None else stage
+        st = np.ascontiguousarray(states, dtype=np.int64)
+        J = np.empty(len(st), dtype=np.float64)
+        I = np.empty(len(st), dtype=np.int32) if with_idx else None
+        self._check(self.lib.bellman_get_points(self.h, int(stage), int(prob), st.ctypes.data_as(C.POINTER(C.c_int64)),
+                                                len(st), J.ctypes.data_as(_dp), I.ctypes.data_as(_ip) if with_idx else _ip()))
+        return J, I
+
     def get_idx(self, stage=None, out=None):
         """0-based argmin control index of ``stage``: [P, S_own] int32."""
         stage = self.current_stage if stage is None else stage
@@ -326,3 +345,22 @@ class Sweep:
                                                   float(h_step), ui.ctypes.data_as(_dp), x0.ctypes.data_as(_dp), batch,
                                                   int(n_steps), X.ctypes.data_as(_dp), Cc.ctypes.data_as(_ip)))
         return X, Cc
+
+    def rollout_orbit(self, u_values, y0, n_steps, h_step, R0, V0, mu=398600.0, tol=1e-8, stride_out=1, stage=None):
+        """Orbital forward simulation of Solver_position.get_optimal_path (Solver_position.m:189-224):
+        y0 [batch, 6] -> X [batch, n_steps/stride_out + 1, 6], control indices [batch, n_steps/stride_out, 3],
+        rkf45 minimum-step warnings [batch]."""
+        stage = self.current_stage if stage is None else stage
+        y0 = _f64(y0).reshape(-1, 6)
+        batch = len(y0)
+        n_out = int(n_steps) // int(stride_out)
+        X = np.empty((batch, n_out + 1, 6))
+        Cc = np.empty((batch, n_out, 3), dtype=np.int32)
+        W = np.empty(batch, dtype=np.int32)
+        o = COrbitOpts(C.sizeof(COrbitOpts), int(n_steps), int(stride_out), 0, float(mu), (C.c_double * 3)(*R0),
+                       (C.c_double * 3)(*V0), float(h_step), float(tol))
+        uv = _f64(u_values)
+        self._check(self.lib.bellman_rollout_orbit(self.h, int(stage), C.byref(o), uv.ctypes.data_as(_dp),
+                                                   y0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp),
+                                                   Cc.ctypes.data_as(_ip), W.ctypes.data_as(_ip)))
+        return X, Cc, W

@@ -223,7 +223,11 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
     h->store_idx_all = d->store_idx_all != 0;
     const size_t nJ = (h->store_J_all ? (size_t)hp.N : 2) * h->slot_elems_J();
     const size_t nI = (h->store_idx_all ? (size_t)hp.N : 1) * h->slot_elems_idx();
-    TRY_RC(cu(cudaMalloc(&h->d_J, nJ * sizeof(double)), "cudaMalloc(J)"));
+    // + 256 bytes: the halo flag words (one uint32 per rank) live in the tail of the J allocation, so the
+    // single CUDA IPC handle of that allocation also maps them into the neighbours
+    TRY_RC(cu(cudaMalloc(&h->d_J, nJ * sizeof(double) + 256), "cudaMalloc(J)"));
+    TRY_RC(cu(cudaMemsetAsync(h->d_J + nJ, 0, 256, h->stream), "cudaMemset(flags)"));
+    h->d_flags = reinterpret_cast<uint32_t *>(h->d_J + nJ);
     TRY_RC(cu(cudaMalloc(&h->d_idx, nI * sizeof(int32_t)), "cudaMalloc(idx)"));
     TRY_RC(cu(cudaMemsetAsync(h->d_idx, 0, nI * sizeof(int32_t), h->stream), "cudaMemset(idx)"));
     h->n_partials = 592;
@@ -463,6 +467,104 @@ static void setup_fused_halo(bellman_handle *h, NcclApi *api) {
     h->fused_halo = true;
 }
 
+// per-problem stride of rank q's J arrays (same padding rule as bellman_create)
+static long long peer_S_ext(const bellman_handle *h, int q) {
+    const HostProblem &hp = h->hp;
+    const bellman_slab &o = h->slabs[q];
+    long long st = 1;
+    for (int d = 0; d < hp.D; ++d) {
+        int ext = (d == h->part_dim) ? (o.ext_hi - o.ext_lo) : hp.n[d];
+        if (d == 0 && (hp.D == 2 || h->part_dim == 0)) ext = (ext + 1) & ~1;
+        st *= ext;
+    }
+    return st;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fused halo mode, stage-to-stage ordering without a collective: neighbour-only release/acquire flags.
+// Rank r owns flags[0..nranks): flags[q] = number of stages rank q has COMPLETED (stage kernel done,
+// hence every store it made into r's halo).  After its stage kernel a rank runs k_halo_signal, which
+// publishes its stage count into the flag word it owns inside every neighbour (st.release.sys over
+// NVLink); before the next stage kernel it runs k_halo_wait, which spins (ld.acquire.sys) until every
+// neighbour's count has reached the stage it depends on.  Only ranks whose slabs exchange halo are
+// coupled; a rank never waits for the far end of the chain, and there is no NCCL launch per stage.
+// Read-after-write: my next stage reads halo values the neighbour stored during its previous stage.
+// Write-after-read: the neighbour's next stage overwrites (ping-pong slot) halo values my previous
+// stage was still reading — it only starts that stage after seeing MY count, so both directions are
+// covered by waiting on the union of "reads from me" and "I read from".
+// ---------------------------------------------------------------------------------------------
+struct HaloFlagArgs {
+    uint32_t *remote[MAX_PEERS];        // signal: my word inside neighbour e
+    const uint32_t *local[MAX_PEERS];   // wait: neighbour e's word inside my allocation
+    int n;
+    uint32_t seq;
+    unsigned int *timeout_flag;         // set to 1 when a wait gives up (a neighbour stopped progressing)
+    unsigned long long timeout_ns;
+};
+
+__global__ void k_halo_signal(const HaloFlagArgs a) {
+    const int e = threadIdx.x;
+    if (e >= a.n) return;
+    __threadfence_system();
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(a.remote[e]), "r"(a.seq) : "memory");
+}
+
+__global__ void k_halo_wait(const HaloFlagArgs a) {
+    const int e = threadIdx.x;
+    if (e >= a.n) return;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        uint32_t v;
+        asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(a.local[e]) : "memory");
+        if ((int32_t)(v - a.seq) >= 0) break;
+        __nanosleep(200);
+        unsigned long long t1;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+        if (t1 - t0 > a.timeout_ns) { atomicExch(a.timeout_flag, 1u); break; }
+    }
+    __threadfence_system();
+}
+
+static void halo_flag_args(const bellman_handle *h, HaloFlagArgs &a, uint32_t seq) {
+    a.n = 0;
+    a.seq = seq;
+    a.timeout_flag = reinterpret_cast<unsigned int *>(h->d_flags + 48);     // a word of the tail no rank owns
+    a.timeout_ns = 30ull * 1000000000ull;
+    const bellman_slab &me = h->slabs[h->rank];
+    const size_t nslots = h->store_J_all ? (size_t)h->hp.N : 2;
+    for (int q = 0; q < h->nranks && a.n < MAX_PEERS; ++q) {
+        if (q == h->rank) continue;
+        const bellman_slab &o = h->slabs[q];
+        const bool reads_me = std::max(o.ext_lo, me.own_lo) < std::min(o.ext_hi, me.own_hi);
+        const bool i_read = std::max(me.ext_lo, o.own_lo) < std::min(me.ext_hi, o.own_hi);
+        if (!reads_me && !i_read) continue;
+        // the neighbour's flag words sit right after its J slots
+        double *tail = h->peer_J[q] + nslots * (size_t)h->hp.P * (size_t)peer_S_ext(h, q);
+        a.remote[a.n] = reinterpret_cast<uint32_t *>(tail) + h->rank;
+        a.local[a.n] = h->d_flags + q;
+        ++a.n;
+    }
+}
+
+static int halo_signal(bellman_handle *h) {
+    HaloFlagArgs a;
+    halo_flag_args(h, a, h->halo_seq);
+    if (a.n == 0) return BELLMAN_OK;
+    k_halo_signal<<<1, 32, 0, h->stream>>>(a);
+    if (cudaGetLastError() != cudaSuccess) { h->err = "halo signal launch failed"; return BELLMAN_ERR_CUDA; }
+    return BELLMAN_OK;
+}
+
+static int halo_wait(bellman_handle *h) {
+    HaloFlagArgs a;
+    halo_flag_args(h, a, h->halo_seq);
+    if (a.n == 0) return BELLMAN_OK;
+    k_halo_wait<<<1, 32, 0, h->stream>>>(a);
+    if (cudaGetLastError() != cudaSuccess) { h->err = "halo wait launch failed"; return BELLMAN_ERR_CUDA; }
+    return BELLMAN_OK;
+}
+
 static void fill_peers(const bellman_handle *h, StageParams &sp, int out_stage) {
     sp.n_peers = 0;
     sp.part_dim = h->part_dim < 0 ? 0 : h->part_dim;
@@ -491,8 +593,8 @@ static void fill_peers(const bellman_handle *h, StageParams &sp, int out_stage) 
     }
 }
 
-// fused mode: the neighbours' stores into my halo are complete once every rank's stage kernel
-// has finished; a 1-element all-reduce on the stream is the barrier
+// a 1-element all-reduce on the stream: the all-ranks barrier used once, before the peer mappings are
+// closed in bellman_destroy (the per-stage ordering uses the neighbour flags above)
 static int stage_barrier(bellman_handle *h) {
     NcclApi *api = nccl_api(h->err);
     if (!api) return BELLMAN_ERR_NCCL;
@@ -700,7 +802,16 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
                 CUDA_TRY(h, cudaEventCreate(&a));
                 CUDA_TRY(h, cudaEventCreate(&b));
                 CUDA_TRY(h, cudaEventRecord(a, h->stream));
-                rc = h->fused_halo ? stage_barrier(h) : exchange_halo(h, h->cur_stage);
+                if (h->fused_halo) {
+                    // my stage count goes to the neighbours; then wait until theirs has reached it.  The
+                    // wait sits right behind the signal (not in front of the next launch) so that
+                    // bellman_run returns with every halo of the last stage in place.
+                    h->halo_seq += 1;
+                    rc = halo_signal(h);
+                    if (rc == BELLMAN_OK) rc = halo_wait(h);
+                } else {
+                    rc = exchange_halo(h, h->cur_stage);
+                }
                 if (rc != BELLMAN_OK) return rc;
                 CUDA_TRY(h, cudaEventRecord(b, h->stream));
                 xev.emplace_back(a, b);
@@ -733,6 +844,11 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
     }
     CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->fused_halo && done > 0) {
+        unsigned int timed_out = 0;
+        CUDA_TRY(h, cudaMemcpy(&timed_out, h->d_flags + 48, sizeof(timed_out), cudaMemcpyDeviceToHost));
+        if (timed_out) { h->err = "halo flag wait timed out: a neighbour rank stopped progressing"; return BELLMAN_ERR_NCCL; }
+    }
     float ms = 0.f;
     CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
     h->last_ms = ms;
@@ -897,5 +1013,130 @@ extern "C" int bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t tim
     PT(cudaStreamSynchronize(h->stream));
 #undef PT
     cleanup();
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bellman_orbit_opts *o,
+                                     const double *u_values, const double *y0, int32_t batch, double *X_out,
+                                     int32_t *C_out, int32_t *warn_out) {
+    if (!h || !o || !u_values || !y0 || !X_out || !C_out || batch < 1) return BELLMAN_ERR_BAD_ARG;
+    if (o->struct_size != (int32_t)sizeof(bellman_orbit_opts)) { h->err = "bellman_orbit_opts.struct_size mismatch"; return BELLMAN_ERR_BAD_ARG; }
+    const HostProblem &hp = h->hp;
+    if (hp.D != 2 || hp.P < 3) { h->err = "orbit rollout needs D = 2 and P >= 3 (the x, y, z axis problems)"; return BELLMAN_ERR_BAD_ARG; }
+    if (o->n_steps < 1 || o->stride_out < 1 || o->n_steps % o->stride_out) { h->err = "n_steps must be a positive multiple of stride_out"; return BELLMAN_ERR_BAD_ARG; }
+    int rc = stage_available(h, stage, h->store_idx_all, true);
+    if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    OrbitParams op;
+    std::memset(&op, 0, sizeof(op));
+    for (int p = 0; p < 3; ++p) {
+        rc = fill_policy_params(h, p, op.pol[p]);
+        if (rc != BELLMAN_OK) return rc;
+        op.pol[p].idx = h->idx_ptr(stage) + (size_t)p * h->S_own;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int n_out = o->n_steps / o->stride_out;
+    double *d_u = nullptr, *d_y = nullptr, *d_X = nullptr;
+    int32_t *d_c = nullptr, *d_w = nullptr;
+    auto cleanup = [&]() { cudaFree(d_u); cudaFree(d_y); cudaFree(d_X); cudaFree(d_c); cudaFree(d_w); };
+#define OT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return _e == cudaErrorMemoryAllocation ? BELLMAN_ERR_OOM : BELLMAN_ERR_CUDA; } } while (0)
+    OT(cudaMalloc(&d_u, sizeof(double) * (size_t)hp.C));
+    OT(cudaMalloc(&d_y, sizeof(double) * 6 * (size_t)batch));
+    OT(cudaMalloc(&d_X, sizeof(double) * 6 * (size_t)(n_out + 1) * batch));
+    OT(cudaMalloc(&d_c, sizeof(int32_t) * 3 * (size_t)n_out * batch));
+    OT(cudaMalloc(&d_w, sizeof(int32_t) * (size_t)batch));
+    OT(cudaMemcpyAsync(d_u, u_values, sizeof(double) * (size_t)hp.C, cudaMemcpyHostToDevice, h->stream));
+    OT(cudaMemcpyAsync(d_y, y0, sizeof(double) * 6 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
+    op.mu = o->mu;
+    for (int k = 0; k < 3; ++k) { op.R0[k] = o->R0[k]; op.V0[k] = o->V0[k]; }
+    op.h = o->h; op.tol = o->tol;
+    op.n_steps = o->n_steps; op.batch = batch; op.stride_out = o->stride_out;
+    op.max_rkf = o->max_rkf_steps > 0 ? o->max_rkf_steps : 100000;
+    op.u_values = d_u; op.y0 = d_y; op.X_out = d_X; op.C_out = d_c; op.warn_out = d_w;
+    OT(launch_rollout_orbit(op, h->stream));
+    OT(cudaMemcpyAsync(X_out, d_X, sizeof(double) * 6 * (size_t)(n_out + 1) * batch, cudaMemcpyDeviceToHost, h->stream));
+    OT(cudaMemcpyAsync(C_out, d_c, sizeof(int32_t) * 3 * (size_t)n_out * batch, cudaMemcpyDeviceToHost, h->stream));
+    if (warn_out) OT(cudaMemcpyAsync(warn_out, d_w, sizeof(int32_t) * (size_t)batch, cudaMemcpyDeviceToHost, h->stream));
+    OT(cudaStreamSynchronize(h->stream));
+#undef OT
+    cleanup();
+    return BELLMAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// point reads: J and argmin of listed states (spot checks at grid sizes whose arrays do not fit the host)
+// ---------------------------------------------------------------------------------------------
+struct PointArgs {
+    const double *J;          // stage slot, problem applied
+    const int32_t *idx;       // stage slot, problem applied (nullptr: skip)
+    const long long *states;  // global linear indices (dimension 0 fastest)
+    long long n;
+    int D;
+    int ng[MAXD], own_lo[MAXD], own_n[MAXD], ext_lo[MAXD];
+    long long stride[MAXD];
+    double *J_out;
+    int32_t *idx_out;
+    int *bad;                 // set when a state is outside the owned range
+};
+
+__global__ void k_get_points(const PointArgs a) {
+    const long long m = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (m >= a.n) return;
+    long long s = a.states[m], jo = 0, io = 0, os = 1;
+    bool ok = s >= 0;
+    for (int d = 0; d < a.D; ++d) {
+        const int g = (int)(s % a.ng[d]);
+        s /= a.ng[d];
+        ok = ok && g >= a.own_lo[d] && g < a.own_lo[d] + a.own_n[d];
+        jo += (long long)(g - a.ext_lo[d]) * a.stride[d];
+        io += (long long)(g - a.own_lo[d]) * os;
+        os *= a.own_n[d];
+    }
+    ok = ok && s == 0;
+    if (!ok) { *a.bad = 1; return; }
+    a.J_out[m] = a.J[jo];
+    if (a.idx) a.idx_out[m] = a.idx[io];
+}
+
+extern "C" int bellman_get_points(bellman_handle *h, int32_t stage, int32_t prob, const int64_t *states, int64_t n,
+                                  double *J_out, int32_t *idx_out) {
+    if (!h || !states || !J_out || n < 1) return BELLMAN_ERR_BAD_ARG;
+    const HostProblem &hp = h->hp;
+    if (prob < 0 || prob >= hp.P) { h->err = "problem index out of range"; return BELLMAN_ERR_BAD_ARG; }
+    int rc = stage_available(h, stage, h->store_J_all, false);
+    if (rc == BELLMAN_OK && idx_out) rc = stage_available(h, stage, h->store_idx_all, true);
+    if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    long long *d_s = nullptr;
+    double *d_J = nullptr;
+    int32_t *d_i = nullptr;
+    int *d_bad = nullptr;
+    auto cleanup = [&]() { cudaFree(d_s); cudaFree(d_J); cudaFree(d_i); cudaFree(d_bad); };
+#define GT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
+    GT(cudaMalloc(&d_s, sizeof(long long) * (size_t)n));
+    GT(cudaMalloc(&d_J, sizeof(double) * (size_t)n));
+    GT(cudaMalloc(&d_i, sizeof(int32_t) * (size_t)n));
+    GT(cudaMalloc(&d_bad, sizeof(int)));
+    GT(cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream));
+    GT(cudaMemcpyAsync(d_s, states, sizeof(long long) * (size_t)n, cudaMemcpyHostToDevice, h->stream));
+    PointArgs a;
+    std::memset(&a, 0, sizeof(a));
+    a.J = h->J_ptr(stage) + (size_t)prob * h->S_ext;
+    a.idx = idx_out ? h->idx_ptr(stage) + (size_t)prob * h->S_own : nullptr;
+    a.states = d_s; a.n = n; a.D = hp.D;
+    for (int d = 0; d < hp.D; ++d) {
+        a.ng[d] = hp.n[d]; a.own_lo[d] = h->own_lo[d]; a.own_n[d] = h->own_n[d]; a.ext_lo[d] = h->ext_lo[d];
+        a.stride[d] = h->stride[d];
+    }
+    a.J_out = d_J; a.idx_out = d_i; a.bad = d_bad;
+    k_get_points<<<(unsigned)((n + 255) / 256), 256, 0, h->stream>>>(a);
+    GT(cudaGetLastError());
+    int bad = 0;
+    GT(cudaMemcpyAsync(J_out, d_J, sizeof(double) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    if (idx_out) GT(cudaMemcpyAsync(idx_out, d_i, sizeof(int32_t) * (size_t)n, cudaMemcpyDeviceToHost, h->stream));
+    GT(cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    GT(cudaStreamSynchronize(h->stream));
+#undef GT
+    cleanup();
+    if (bad) { h->err = "bellman_get_points: a state lies outside this rank's owned range"; return BELLMAN_ERR_BAD_ARG; }
     return BELLMAN_OK;
 }

@@ -46,6 +46,8 @@ struct bellman_handle {
     bool fused_halo = false;
     std::vector<double *> peer_J;
     double *d_barrier = nullptr;
+    uint32_t *d_flags = nullptr;      // tail of the J allocation: flags[q] = stages rank q has completed (fused halo)
+    uint32_t halo_seq = 0;            // stages this rank has completed since bellman_comm_init
     unsigned char *d_comm_scratch = nullptr;   // IPC-handle all-gather buffer (partitioned handles)
     // window kernel state
     bellman::WindowConfig wcfg;

@@ -482,6 +482,182 @@ __global__ void __launch_bounds__(128) k_rollout_axis(const __grid_constant__ Po
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Orbital forward simulation of Solver_position.get_optimal_path (position-control/Solver_position.m:
+// 189-224): per stage, the three axis policies U{1,2,3}_Opt are looked up at the nearest grid node and
+// the relative-motion equations (:259-309, the target orbit propagated by the universal Kepler
+// equation, private/kepler_U.m, f_and_g.m, fDot_and_gDot.m, stumpC.m, stumpS.m) are integrated over
+// one stage by Runge-Kutta-Fehlberg 4(5) with adaptive steps (private/rkf45.m:49-118).  One thread
+// per initial state.  Operation order as oracle/bellman_oracle.c restates it; cos/sin/cosh/sinh/pow
+// are CUDA's, so parity with the oracle is a tolerance, not bit equality.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double stumpC(double z) {
+    if (z > 0) return (1 - cos(sqrt(z))) / z;
+    if (z < 0) return (cosh(sqrt(-z)) - 1) / (-z);
+    return 0.5;
+}
+__device__ __forceinline__ double stumpS(double z) {
+    if (z > 0) { const double s = sqrt(z); return (s - sin(s)) / pow(s, 3.0); }
+    if (z < 0) { const double s = sqrt(-z); return (sinh(s) - s) / pow(s, 3.0); }
+    return 1.0 / 6;
+}
+struct OrbitTarget { double mu, smu, r0, vr0, alpha; double R0[3], V0[3]; };
+
+__device__ double kepler_U(const OrbitTarget &tg, double dt) {
+    const double ro = tg.r0, vro = tg.vr0, a = tg.alpha, smu = tg.smu;
+    double x = smu * fabs(a) * dt;
+    int n = 0;
+    double ratio = 1;
+    while (fabs(ratio) > 1.e-8 && n <= 1000) {
+        n = n + 1;
+        const double x2 = x * x;
+        const double Cz = stumpC(a * x2);
+        const double Sz = stumpS(a * x2);
+        const double F = ro * vro / smu * x2 * Cz + (1 - a * ro) * pow(x, 3.0) * Sz + ro * x - smu * dt;
+        const double dFdx = ro * vro / smu * x * (1 - a * x2 * Sz) + (1 - a * ro) * x2 * Cz + ro;
+        ratio = F / dFdx;
+        x = x - ratio;
+    }
+    return x;
+}
+
+__device__ void orbit_rates(const OrbitTarget &tg, const double (&acc)[3], double t, const double (&y)[6], double (&dydt)[6]) {
+    // update_RV_target (:333-361)
+    const double x = kepler_U(tg, t);
+    const double z = tg.alpha * (x * x);
+    const double f = 1 - x * x / tg.r0 * stumpC(z);
+    const double g = t - 1 / tg.smu * pow(x, 3.0) * stumpS(z);
+    double R[3], V[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) R[k] = f * tg.R0[k] + g * tg.V0[k];
+    const double r2 = sqrt(R[0] * R[0] + R[1] * R[1] + R[2] * R[2]);
+    const double fdot = tg.smu / r2 / tg.r0 * (z * stumpS(z) - 1) * x;
+    const double gdot = 1 - x * x / r2 * stumpC(z);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) V[k] = fdot * tg.R0[k] + gdot * tg.V0[k];
+    // rates (:288-308)
+    const double norm_R = pow((R[0] * R[0] + R[1] * R[1]) + R[2] * R[2], .5);
+    const double RdotV = (R[0] * V[0] + R[1] * V[1]) + R[2] * V[2];
+    const double c0 = R[1] * V[2] - R[2] * V[1], c1 = R[2] * V[0] - R[0] * V[2], c2 = R[0] * V[1] - R[1] * V[0];
+    const double H = pow((c0 * c0 + c1 * c1) + c2 * c2, .5);
+    const double mu = tg.mu;
+    const double nR2 = norm_R * norm_R, nR3 = pow(norm_R, 3.0), nR4 = pow(norm_R, 4.0), H2 = H * H;
+    dydt[0] = y[3]; dydt[1] = y[4]; dydt[2] = y[5];
+    dydt[3] = (2 * mu / nR3 + H2 / nR4) * y[0] - 2 * RdotV / nR4 * H * y[1] + 2 * H / nR2 * y[4] + acc[0];
+    dydt[4] = -(mu / nR3 - H2 / nR4) * y[1] + 2 * RdotV / nR4 * H * y[0] - 2 * H / nR2 * y[3] + acc[1];
+    dydt[5] = -mu / nR3 * y[2] + acc[2];
+}
+
+__device__ __forceinline__ double eps_of(double t) {   // MATLAB eps(t)
+    t = fabs(t);
+    if (t < 2.2250738585072014e-308) return 4.9406564584124654e-324;
+    int e;
+    frexp(t, &e);
+    return ldexp(1.0, e - 53);
+}
+
+__global__ void __launch_bounds__(64) k_rollout_orbit(const __grid_constant__ OrbitParams op) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= op.batch) return;
+    const double ra[6] = {0, 1. / 4, 3. / 8, 12. / 13, 1, 1. / 2};
+    const double rb[6][5] = {{0, 0, 0, 0, 0},
+                             {1. / 4, 0, 0, 0, 0},
+                             {3. / 32, 9. / 32, 0, 0, 0},
+                             {1932. / 2197, -7200. / 2197, 7296. / 2197, 0, 0},
+                             {439. / 216, -8, 3680. / 513, -845. / 4104, 0},
+                             {-8. / 27, 2, -3544. / 2565, 1859. / 4104, -11. / 40}};
+    const double c4[6] = {25. / 216, 0, 1408. / 2565, 2197. / 4104, -1. / 5, 0};
+    const double c5[6] = {16. / 135, 0, 6656. / 12825, 28561. / 56430, -9. / 50, 2. / 55};
+    OrbitTarget tg;
+    tg.mu = op.mu;
+    tg.smu = sqrt(op.mu);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { tg.R0[k] = op.R0[k]; tg.V0[k] = op.V0[k]; }
+    tg.r0 = sqrt(tg.R0[0] * tg.R0[0] + tg.R0[1] * tg.R0[1] + tg.R0[2] * tg.R0[2]);
+    const double v0 = sqrt(tg.V0[0] * tg.V0[0] + tg.V0[1] * tg.V0[1] + tg.V0[2] * tg.V0[2]);
+    tg.vr0 = (tg.R0[0] * tg.V0[0] + tg.R0[1] * tg.V0[1] + tg.R0[2] * tg.V0[2]) / tg.r0;
+    tg.alpha = 2 / tg.r0 - v0 * v0 / tg.mu;
+
+    double y[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k) y[k] = op.y0[(size_t)b * 6 + k];
+    const int n_out = op.n_steps / op.stride_out;
+    double *X = op.X_out + (size_t)b * 6 * (n_out + 1);
+    int32_t *Cc = op.C_out + (size_t)b * 3 * n_out;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) X[k] = y[k];
+    int warns = 0;
+    for (int ks = 1; ks <= op.n_steps; ++ks) {
+        double acc[3];
+        int ci[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {       // a_x = U1_Opt(x1, v1) ... (:215-217)
+            const double xq[2] = {y[p], y[3 + p]};
+            ci[p] = policy_at(op.pol[p], op.pol[p].idx, xq);
+            acc[p] = op.u_values[ci[p]];
+        }
+        if ((ks - 1) % op.stride_out == 0) {
+            const int o = (ks - 1) / op.stride_out;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) Cc[(size_t)o * 3 + p] = ci[p];
+        }
+        // rkf45(@rates, [tspan(k), tspan(k+1)], X(:,k)) (:222), rkf45.m:67-118
+        const double t0 = (double)(ks - 1) * op.h, tf = (double)ks * op.h;
+        double t = t0, hh = (tf - t0) / 100, f[6][6], yi[6], yin[6];
+        int iters = 0;
+        while (t < tf && iters++ < op.max_rkf) {
+            const double hmin = 16 * eps_of(t);
+            const double ti = t;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) yi[k] = y[k];
+#pragma unroll
+            for (int i = 0; i < 6; ++i) {
+                const double t_inner = ti + ra[i] * hh;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) yin[k] = yi[k];
+#pragma unroll
+                for (int j = 0; j < 5; ++j)
+                    if (j < i) {
+#pragma unroll
+                        for (int k = 0; k < 6; ++k) yin[k] = yin[k] + hh * rb[i][j] * f[j][k];
+                    }
+                orbit_rates(tg, acc, t_inner, yin, f[i]);
+            }
+            double te_max = 0, ymax = 0;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+                double te = 0;
+#pragma unroll
+                for (int i = 0; i < 6; ++i) te = te + (hh * f[i][k]) * (c4[i] - c5[i]);
+                te_max = fmax(te_max, fabs(te));
+                ymax = fmax(ymax, fabs(y[k]));
+            }
+            const double te_allowed = op.tol * fmax(ymax, 1.0);
+            const double delta = pow(te_allowed / (te_max + 2.220446049250313e-16), 1. / 5);
+            if (te_max <= te_allowed) {
+                hh = fmin(hh, tf - t);
+                t = t + hh;
+#pragma unroll
+                for (int k = 0; k < 6; ++k) {
+                    double sacc = 0;
+#pragma unroll
+                    for (int i = 0; i < 6; ++i) sacc = sacc + (hh * f[i][k]) * c5[i];
+                    y[k] = yi[k] + sacc;
+                }
+            }
+            hh = fmin(delta * hh, 4 * hh);
+            if (hh < hmin) { ++warns; break; }
+        }
+        if (ks % op.stride_out == 0) {
+            double *Xk = X + (size_t)(ks / op.stride_out) * 6;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) Xk[k] = y[k];
+        }
+    }
+    if (op.warn_out) op.warn_out[b] = warns;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -589,6 +765,11 @@ cudaError_t launch_policy_lookup(const PolicyParams &pp, cudaStream_t st) {
 
 cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st) {
     k_rollout_axis<<<(pp.batch + 127) / 128, 128, 0, st>>>(pp);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rollout_orbit(const OrbitParams &op, cudaStream_t st) {
+    k_rollout_orbit<<<(op.batch + 63) / 64, 64, 0, st>>>(op);
     return cudaGetLastError();
 }
 

@@ -68,6 +68,20 @@ struct PolicyParams {
     double *X_out;             // rollout: [2][n_steps+1][batch]
 };
 cudaError_t launch_policy_lookup(const PolicyParams &pp, cudaStream_t st);
+
+// orbital forward simulation of Solver_position.get_optimal_path (one thread per initial state)
+struct OrbitParams {
+    PolicyParams pol[3];       // nearest policy of axis p (D = 2; .idx = policy of the requested stage)
+    double mu, R0[3], V0[3];   // gravitational parameter, target state vector at t = 0
+    double h, tol;             // stage length, rkf45 tolerance
+    int n_steps, batch, stride_out, max_rkf;
+    const double *u_values;    // [C]
+    const double *y0;          // [batch][6]
+    double *X_out;             // [batch][n_steps / stride_out + 1][6]
+    int32_t *C_out;            // [batch][n_steps / stride_out][3]
+    int32_t *warn_out;         // [batch] rkf45 calls that stopped on the minimum step size
+};
+cudaError_t launch_rollout_orbit(const OrbitParams &op, cudaStream_t st);
 cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st);
 
 }  // namespace bellman

@@ -44,7 +44,7 @@ namespace bellman {
 
 namespace {
 
-constexpr int SMAXF = 6;        // control classes of dimension 1 the kernel keeps in registers
+
 constexpr int SMAXJ = 4;        // slab ring depth (TMA boxes in flight)
 
 struct StreamParams {
@@ -55,17 +55,24 @@ struct StreamParams {
     int NH1;                        // dimension-1 nodes a column needs (2 or 3)
     int NF1;                        // dimension-1 control classes
     int span3;                      // dimension-3 nodes a step needs: hi3 - lo3 + 2
-    int W3;                         // K ring slots = span3 + 1
+    int W3;                         // K ring slots = span3 + 2
     int NJ;                         // slab ring slots
+    int NP;                         // 0: every warp produces (plane j = warp) and warps < T2 also consume;
+                                    // > 0: warp specialisation — warps < T2 only consume, the NP warps after them
+                                    // share the B2 planes
     int slab_doubles;               // doubles per slab slot (128-byte aligned)
     int ring_doubles;               // W3 * NF1 * B2 * 32
     int own_stride[MAXD];           // strides of the owned index space (idx_out)
     uint32_t allmask;               // (1 << C) - 1
+    double rc[4][12];               // control-cost term r[p][c] (constant bank: no registers, no loads)
     const double2 *ft0;             // [(p n1 + i1) n0 + i0] = {t0, cell0}
     const double2 *k1;              // [(p n1 + i1) NF1 + f]  = {t1, cell1 - (i1 + lo1)}
     const double2 *ft2;             // [(p n3 + i3) n2 + i2] = {t2, cell2 | chain flag << 32}
-    const double2 *lt3;             // [(p n3 + i3) C + c]    = {t3, ring offset of the lower node | upper << 32}
-    const uint32_t *flag3;          // [p n3 + i3]: bit c set when cell3(i3, c) == cell3(i3 - 1, c) + 1
+    // one record per (p, i3), blk3_bytes long: { double q3; uint32 flag3 (bit c: cell3(i3, c) ==
+    // cell3(i3 - 1, c) + 1); uint32 pad; double t3[C]; uint32 up3[C] (ring BYTE offset of the UPPER node's
+    // pair of control c; the lower node is one slot before) } — one cursor walks everything a step needs
+    const unsigned char *blk3;
+    int blk3_bytes;
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -75,18 +82,32 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+// Waits for the phase of `parity` to complete.  try_wait carries a suspend-time hint, so a waiting warp
+// sleeps in hardware instead of competing for issue slots.  Bounded: a wait that outlives ~2^22 timed-out
+// polls (seconds — a protocol bug or a lost TMA, never a legitimate state) traps, so the launch fails with
+// an error instead of hanging the GPU.
+__device__ __forceinline__ uint32_t mbar_try(uint32_t addr, uint32_t parity) {
+    uint32_t done;
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "WAIT_%=:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra DONE_%=;\n"
-        "bra WAIT_%=;\n"
-        "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
-        "r"(parity)
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
         : "memory");
+    return done;
+}
+__device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try(addr, parity); ++spins)
+        if (spins > (1u << 22)) asm volatile("trap;");
+}
+__device__ __forceinline__ void mbar_wait32(uint32_t addr, uint32_t parity) {
+    if (!mbar_try(addr, parity)) mbar_wait_slow(addr, parity);
+}
+__device__ __forceinline__ void mbar_arrive32(uint32_t addr) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(addr) : "memory");
 }
 __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, uint64_t *bar, int c0, int c1, int c2,
                                             int c3, int c4) {
@@ -97,12 +118,35 @@ __device__ __forceinline__ void tma_load_5d(void *dst, const CUtensorMap *map, u
         : "memory");
 }
 
-template <int C>
+// shared-memory accesses by 32-bit address.  volatile + "memory": the K ring is rewritten every step, so
+// these must stay ordered with the barriers (and are never merged across iterations)
+__device__ __forceinline__ double lds64(uint32_t addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts64(uint32_t addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+// C controls, NF classes of dimension 1 (compile time: the per-control and per-class values live in registers)
+template <int C, int NF>
 __global__ void __launch_bounds__(384, 1)
 k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ StreamParams tp,
                const __grid_constant__ CUtensorMap tmap) {
     extern __shared__ __align__(128) double smem[];
-    __shared__ __align__(8) uint64_t mbar[SMAXJ];
+    // slab[s]: TMA completion of slab ring slot s.  full[it & 3]: every producer warp arrives after writing
+    // node `it` into the K ring; empty[it & 3]: every consumer warp arrives after finishing the step of
+    // iteration `it`.  The ring has one slot more than a step needs, so a warp only ever waits for what the
+    // OTHER warps did an iteration ago:
+    //   consume(it) waits full of it - 1  (reads nodes it - span3 .. it - 1)
+    //   produce(it) waits empty of it - 2 (overwrites node it - W3 = it - span3 - 2, last read by the step of it - 2)
+    // Four barriers of each kind although warps are at most two iterations apart: with two, a producer-only
+    // warp that is slow to poll empty(it - 2) could find the barrier already completed AGAIN for iteration
+    // `it` (the consumers only need its node it - 1 to get that far) and would wait for a parity that never
+    // comes; the completion after next on the same barrier (it + 2) needs that warp's own node it + 1.
+    __shared__ __align__(8) uint64_t mbar_all[SMAXJ + 8];
+    uint64_t *const mbar_slab = mbar_all, *const mbar_full = mbar_all + SMAXJ, *const mbar_empty = mbar_all + SMAXJ + 4;
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5, NW = blockDim.x >> 5;
     const uint32_t prob = blockIdx.z;
@@ -117,20 +161,28 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
     org0 -= (org0 - d0.ext_lo) & 1;                      // TMA: 16-byte aligned innermost coordinate
     const int org1 = a1 + tp.lo[1], org2 = a2 + tp.lo[2], m3_first = a3 + tp.lo[3];
     const int T3n = h3 - a3;
-    const int n_prod = T3n + tp.span3 - 1;               // dimension-3 nodes this CTA turns into K
-    const int n_iter = T3n + tp.span3;                   // node `it` is produced in iteration it, step it - span3 consumed
+    const int span3 = tp.span3;
+    const int n_prod = T3n + span3 - 1;                  // dimension-3 nodes this CTA turns into K
+    const int n_iter = T3n + span3;                      // node `it` is produced in iteration it, step it - span3 consumed
     const int NJ = tp.NJ;
+    const int n_cons = min(tp.T2, h2 - a2);              // consumer warps with a row of states
 
-    double *ringK = smem;
-    double *slabs = smem + tp.ring_doubles;
+    uint32_t ring32 = smem_u32(smem);
+    asm volatile("" : "+r"(ring32));             // opaque: kept in a register, not rebuilt from special registers
+    const uint32_t slabs32 = ring32 + 8u * (uint32_t)tp.ring_doubles;
+    const uint32_t slab_stride = 8u * (uint32_t)tp.slab_doubles;
     const uint32_t slab_bytes = (uint32_t)(tp.B0 * tp.B1 * tp.B2) * 8u;
-    auto issue = [&](int node, int slot) {               // thread 0 only
-        mbar_expect_tx(&mbar[slot], slab_bytes);
-        tma_load_5d(slabs + (size_t)slot * tp.slab_doubles, &tmap, &mbar[slot], org0 - d0.ext_lo, org1 - d1.ext_lo,
-                    org2 - d2.ext_lo, m3_first + node - d3.ext_lo, (int)prob);
+    auto issue = [&](int node, int slot) {               // one thread only; slot = node % NJ
+        mbar_expect_tx(&mbar_slab[slot], slab_bytes);
+        tma_load_5d(smem + tp.ring_doubles + (size_t)slot * tp.slab_doubles, &tmap, &mbar_slab[slot], org0 - d0.ext_lo,
+                    org1 - d1.ext_lo, org2 - d2.ext_lo, m3_first + node - d3.ext_lo, (int)prob);
     };
     if (tid == 0) {
-        for (int s = 0; s < NJ; ++s) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < NJ; ++s) mbar_init(&mbar_slab[s], 1);
+        for (int b = 0; b < 4; ++b) {
+            mbar_init(&mbar_full[b], (uint32_t)(tp.NP > 0 ? tp.NP : tp.B2));
+            mbar_init(&mbar_empty[b], (uint32_t)n_cons);
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         for (int s = 0; s < NJ && s < n_prod; ++s) issue(s, s);
     }
@@ -141,126 +193,220 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
     const int i0 = min(a0 + l0, h0 - 1), i1 = min(a1 + l1, h1 - 1);
     const double2 e0 = __ldg(tp.ft0 + ((size_t)prob * d1.n + i1) * d0.n + i0);
     const double t0 = e0.x;
-    const int offA = (__double2loint(e0.y) - org0) + tp.B0 * (i1 - a1);       // doubles, inside a slab row m2
-    double t1[SMAXF];
+    double t1[NF];
     uint32_t selbits = 0;
 #pragma unroll
-    for (int f = 0; f < SMAXF; ++f) {
-        t1[f] = 0.0;
-        if (f < tp.NF1) {
-            const double2 e = __ldg(tp.k1 + ((size_t)prob * d1.n + i1) * tp.NF1 + f);
-            t1[f] = e.x;
-            selbits |= (uint32_t)__double2loint(e.y) << f;
-        }
+    for (int f = 0; f < NF; ++f) {
+        const double2 e = __ldg(tp.k1 + ((size_t)prob * d1.n + i1) * NF + f);
+        t1[f] = e.x;
+        selbits |= (uint32_t)__double2loint(e.y) << f;
     }
-    const int B01 = tp.B0 * tp.B1;
-    const int cls_stride = tp.B2 * 32;                   // doubles between classes inside a ring slot
-    const int slot_stride = tp.NF1 * cls_stride;
+    const uint32_t row_b = 8u * (uint32_t)tp.B0;                  // bytes between slab rows m1
+    const uint32_t node2_b = row_b * (uint32_t)tp.B1;             // bytes between slab planes m2
+    const uint32_t cls_b = 256u * (uint32_t)tp.B2;                // bytes between classes inside a ring slot
+    const uint32_t slot_b = cls_b * (uint32_t)NF;                 // bytes between ring slots
+    const uint32_t ring_b = slot_b * (uint32_t)tp.W3;
+    const bool nh3 = tp.NH1 == 3;
+    // producer: lower-left corner of this column inside slab plane m2 = wrp, and where its K values go
+    // producer warps: all of them (plane j = wrp, stride NW), or — specialised — warps T2 .. T2 + NP - 1
+    const bool prod = tp.NP > 0 ? wrp >= tp.T2 : wrp < tp.B2;
+    const int pj0 = tp.NP > 0 ? wrp - tp.T2 : wrp, pjs = tp.NP > 0 ? tp.NP : NW;
+    const uint32_t pA0 = slabs32 + 8u * (uint32_t)((__double2loint(e0.y) - org0) + tp.B0 * (i1 - a1)) + node2_b * (uint32_t)pj0;
+    const uint32_t kout0 = ring32 + 8u * (uint32_t)(pj0 * 32 + lane);
 
     // ---- consumer role: warp w finishes the states (i0, i1, a2 + w, i3) ----
     const int i2 = a2 + wrp;
-    const bool cons = wrp < tp.T2 && i2 < h2;
+    const bool cons = wrp < n_cons;
     const int i2c = min(i2, h2 - 1);
-    double a_up[C], d_up[C], rc[C];
+    const double *rc = tp.rc[prob];              // constant bank, warp-uniform
+    // stage cost: the q terms are summed in q_order; dimension 3's term changes every step, the partial
+    // sums that do not involve it are formed once (same association as the normative left-to-right sum)
+    int qpos = 0;
+    double qa = 0.0, qb = 0.0, qc = 0.0;
+    {
+        const double qv0 = __ldg(d0.q + (size_t)prob * d0.n + i0), qv1 = __ldg(d1.q + (size_t)prob * d1.n + i1),
+                     qv2 = __ldg(d2.q + (size_t)prob * d2.n + i2c);
+        int k = 0;
 #pragma unroll
-    for (int c = 0; c < C; ++c) { a_up[c] = 0.0; d_up[c] = 0.0; rc[c] = __ldg(sp.r + prob * (uint32_t)C + c); }
-    const double q0 = __ldg(d0.q + (size_t)prob * d0.n + i0), q1 = __ldg(d1.q + (size_t)prob * d1.n + i1);
-    const double q2 = __ldg(d2.q + (size_t)prob * d2.n + i2c);
-    const double *q3p = d3.q + (size_t)prob * d3.n;
-    const int qo0 = sp.q_order[0], qo1 = sp.q_order[1], qo2 = sp.q_order[2], qo3 = sp.q_order[3];
+        for (int m = 0; m < 4; ++m) {
+            const int o = sp.q_order[m];
+            if (o == 3) { qpos = m; continue; }
+            const double v = o == 0 ? qv0 : o == 1 ? qv1 : qv2;
+            if (k == 0) qa = v; else if (k == 1) qb = v; else qc = v;
+            ++k;
+        }
+        if (qpos >= 2) qa = qa + qb;                     // (qa + qb) precedes dimension 3's term
+        if (qpos == 3) qa = qa + qc;
+    }
     const double2 *ft2p = tp.ft2 + (size_t)prob * d3.n * d2.n + i2c;
-    const double2 *lt3p = tp.lt3 + (size_t)prob * d3.n * C;
-    const uint32_t *flag3p = tp.flag3 + (size_t)prob * d3.n;
     long long jo = (long long)prob * sp.S_ext + (long long)(i0 - d0.ext_lo) * d0.stride +
                    (long long)(i1 - d1.ext_lo) * d1.stride + (long long)(i2c - d2.ext_lo) * d2.stride +
                    (long long)(a3 - d3.ext_lo) * d3.stride;
     long long io = (long long)prob * sp.S_own + (long long)(i0 - d0.own_lo) * tp.own_stride[0] +
                    (long long)(i1 - d1.own_lo) * tp.own_stride[1] + (long long)(i2c - d2.own_lo) * tp.own_stride[2] +
                    (long long)(a3 - d3.own_lo) * tp.own_stride[3];
+    // tables of the NEXT step, fetched right after a step's stores: they travel while the warp runs its
+    // producer role, so no global-memory latency is left on the step itself
+    double2 e2n = make_double2(0.0, 0.0);
+    double t3n[C], q3n = 0.0;
+    uint32_t up3n[C], f3n = 0;
+    // two cursors advance by one step (one i3) per prefetch: no index arithmetic in the loop
+    const double2 *c_ft2 = ft2p + (size_t)a3 * d2.n;
+    const unsigned char *c_blk = tp.blk3 + ((size_t)prob * d3.n + a3) * (size_t)tp.blk3_bytes;
+    const int ft2_step = d2.n, blk_step = tp.blk3_bytes;
+    auto prefetch = [&]() {
+        e2n = __ldg(c_ft2);
+        const double2 hdr = __ldg(reinterpret_cast<const double2 *>(c_blk));
+        q3n = hdr.x;
+        f3n = (uint32_t)__double2loint(hdr.y);
+        const double *t3p = reinterpret_cast<const double *>(c_blk + 16);
+        const uint32_t *u3p = reinterpret_cast<const uint32_t *>(c_blk + 16 + 8 * C);
+#pragma unroll
+        for (int c = 0; c < C; ++c) { t3n[c] = __ldg(t3p + c); up3n[c] = __ldg(u3p + c); }
+        c_ft2 += ft2_step;
+        c_blk += blk_step;
+    };
+#pragma unroll
+    for (int c = 0; c < C; ++c) { t3n[c] = 0.0; up3n[c] = 0; }
+    if (cons) prefetch();
 
     __syncthreads();          // mbarriers initialised
 
-    int slotJ = 0, phaseJ = 0, slotK = 0;
-#pragma unroll 1
-    for (int it = 0; it < n_iter; ++it) {
-        // ---- produce: slab row m2 = j of node `it`  ->  K[f][j] of ring slot slotK ----
-        if (it < n_prod) {
-            if (wrp < tp.B2) mbar_wait(&mbar[slotJ], (uint32_t)phaseJ);
-            const double *slab = slabs + (size_t)slotJ * tp.slab_doubles + offA;
-            double *kout = ringK + slotK * slot_stride + lane;
-            for (int j = wrp; j < tp.B2; j += NW) {
-                const double *p = slab + j * B01;
-                const double lo0 = p[0], hi0 = p[1], lo1 = p[tp.B0], hi1 = p[tp.B0 + 1];
+    uint32_t bar_slab = smem_u32(&mbar_slab[0]);
+    asm volatile("" : "+r"(bar_slab));
+    const uint32_t bar_full = bar_slab + 8u * SMAXJ, bar_empty = bar_full + 32u;   // mbar_slab / mbar_full / mbar_empty are one array
+    uint32_t slotK_b = 0;                     // byte offset of ring slot it % W3
+    uint32_t slab_b = 0, slab_i = 0, slab_ph = 0;   // slab ring slot of node `it`: byte offset, index, phase parity
+    const uint32_t slab_ring_b = slab_stride * (uint32_t)NJ;
+    const int emp_from = span3 + 2;           // first iteration whose producer has a step (it - 2) to wait for
+
+    // ---- produce: slab plane m2 = j of node `it`  ->  K[f][j] of ring slot it % W3 ----
+    auto produce = [&](int it) {
+        if (prod) {
+            if (it >= emp_from) mbar_wait32(bar_empty + 8u * (uint32_t)((it - 2) & 3), (uint32_t)(((it - emp_from) >> 2) & 1));
+            mbar_wait32(bar_slab + 8u * slab_i, slab_ph);
+            uint32_t pA = pA0 + slab_b, ko = kout0 + slotK_b;
+            for (int j = pj0; j < tp.B2; j += pjs) {
+                const double lo0 = lds64(pA), hi0 = lds64(pA + 8), lo1 = lds64(pA + row_b), hi1 = lds64(pA + row_b + 8);
+                double lo2 = 0.0, hi2 = 0.0;
+                if (nh3) { lo2 = lds64(pA + 2 * row_b); hi2 = lds64(pA + 2 * row_b + 8); }
                 const double H0 = fma(t0, hi0 - lo0, lo0);
                 const double H1 = fma(t0, hi1 - lo1, lo1);
-                const double dA = H1 - H0;
-                double dB = 0.0;
-                if (tp.NH1 == 3) {
-                    const double lo2 = p[2 * tp.B0], hi2 = p[2 * tp.B0 + 1];
-                    const double H2 = fma(t0, hi2 - lo2, lo2);
-                    dB = H2 - H1;
-                }
+                const double H2 = fma(t0, hi2 - lo2, lo2);
+                const double dA = H1 - H0, dB = H2 - H1;
 #pragma unroll
-                for (int f = 0; f < SMAXF; ++f)
-                    if (f < tp.NF1) {
-                        const bool s = (selbits >> f) & 1u;
-                        kout[f * cls_stride + j * 32] = fma(t1[f], s ? dB : dA, s ? H1 : H0);
-                    }
+                for (int f = 0; f < NF; ++f) {
+                    const bool sl = (selbits >> f) & 1u;
+                    sts64(ko + (uint32_t)f * cls_b, fma(t1[f], sl ? dB : dA, sl ? H1 : H0));
+                }
+                pA += node2_b * (uint32_t)pjs;
+                ko += 256u * (uint32_t)pjs;
             }
+            __syncwarp();
+            if (lane == 0) mbar_arrive32(bar_full + 8u * (uint32_t)(it & 3));
         }
-        // ---- consume: step i3 = a3 + it - span3 (its nodes were produced in earlier iterations) ----
-        if (cons && it >= tp.span3) {
-            const int i3 = a3 + it - tp.span3;
-            const double2 e2 = __ldg(ft2p + (size_t)i3 * d2.n);
-            const double t2 = e2.x;
-            const uint32_t f3 = __ldg(flag3p + i3);
-            const bool fast = it > tp.span3 && __double2hiint(e2.y) != 0 && f3 == tp.allmask;
-            const double *kb = ringK + ((__double2loint(e2.y) - org2) * 32 + lane);
-            const double q3 = __ldg(q3p + i3);
-            auto qsel = [&](int o) { return o == 0 ? q0 : o == 1 ? q1 : o == 2 ? q2 : q3; };
-            const double gs = ((qsel(qo0) + qsel(qo1)) + qsel(qo2)) + qsel(qo3);
-            const double2 *l3 = lt3p + (size_t)i3 * C;
-            double best = __longlong_as_double(0x7ff0000000000000LL);
-            int arg = 0;
-            auto body = [&](auto fast_tag) {
-                constexpr bool FAST = decltype(fast_tag)::value;
+        slab_b += slab_stride;
+        ++slab_i;
+        if (slab_b == slab_ring_b) { slab_b = 0; slab_i = 0; slab_ph ^= 1u; }
+    };
+    // every producer is done with node it - 1: its K values are visible, its slab slot is free again
+    // The slab slot is refilled by the LAST warp (a producer-only warp: it has the time), so no consumer
+    // carries the TMA issue on its critical path.
+    const bool tma_warp = wrp == NW - 1;
+    int iss_slot = 0;                          // slab slot of node it - 1 (the one sync_prev(it) refills)
+    auto sync_prev = [&](int it) {
+        if (cons || tma_warp) {
+            mbar_wait32(bar_full + 8u * (uint32_t)((it - 1) & 3), (uint32_t)(((it - 1) >> 2) & 1));
+            if (tma_warp && lane == 0 && it - 1 + NJ < n_prod) issue(it - 1 + NJ, iss_slot);
+        }
+        if (++iss_slot == NJ) iss_slot = 0;
+    };
+    // ---- consume: step i3 = a3 + it - span3.  (alo, dlo) hold the pairs the previous step read as its
+    // UPPER node, (aup, dup) receive this step's — the caller alternates two register sets, nothing is copied
+    double *Jp = sp.J_out + jo;
+    int32_t *Ip = sp.idx_out + io;
+    auto consume = [&](int it, double (&alo)[C], double (&dlo)[C], double (&aup)[C], double (&dup)[C]) {
+        if (cons) {
+            const double t2 = e2n.x;
+            const bool fast = it > span3 && __double2hiint(e2n.y) != 0 && f3n == tp.allmask;
+            const uint32_t kb = ring32 + 8u * (uint32_t)((__double2loint(e2n.y) - org2) * 32 + lane);
+            double gs = qa + q3n;                         // q_order: see qpos above
+            if (qpos <= 2) gs = gs + (qpos == 2 ? qc : qb);
+            if (qpos <= 1) gs = gs + qc;
+            double bu[C];
+#pragma unroll
+            for (int c = 0; c < C; ++c) {                 // the upper node's pair of every control
+                const uint32_t p = kb + up3n[c];
+                aup[c] = lds64(p);
+                bu[c] = lds64(p + 256);
+            }
+            if (!fast) {                                  // first step, clamped edge: the lower node's pairs too
 #pragma unroll
                 for (int c = 0; c < C; ++c) {
-                    const double2 e3 = __ldg(l3 + c);
-                    double alo, dlo;
-                    if (FAST) {
-                        alo = a_up[c];
-                        dlo = d_up[c];
-                    } else {
-                        const int olo = __double2loint(e3.y);
-                        alo = kb[olo];
-                        dlo = kb[olo + 32] - alo;
-                    }
-                    const int oup = __double2hiint(e3.y);
-                    const double au = kb[oup];
-                    const double du = kb[oup + 32] - au;
-                    const double vlo = fma(t2, dlo, alo), vup = fma(t2, du, au);      // dimension 2
-                    const double val = fma(e3.x, vup - vlo, vlo);                     // dimension 3
-                    const double tot = (gs + rc[c]) + val;
-                    if (tot < best) { best = tot; arg = c; }
-                    a_up[c] = au;
-                    d_up[c] = du;
+                    // the lower node sits one ring slot before the upper one (wrapping)
+                    const uint32_t p = kb + (up3n[c] >= slot_b ? up3n[c] - slot_b : up3n[c] + (ring_b - slot_b));
+                    alo[c] = lds64(p);
+                    dlo[c] = lds64(p + 256) - alo[c];
                 }
-            };
-            if (fast) body(std::true_type{});
-            else body(std::false_type{});
-            if (ok01) {
-                sp.J_out[jo] = best;
-                sp.idx_out[io] = arg;
-                if (sp.n_peers) { const int gi[4] = {i0, i1, i2, i3}; peer_store<4>(sp, (int)prob, gi, best); }
             }
-            jo += d3.stride;
-            io += tp.own_stride[3];
+            // two serial first-index-wins chains (controls [0, CH) and [CH, C)), merged at the end: half the
+            // dependent compare latency of one chain; the higher-indexed half only wins when strictly smaller
+            constexpr int CH = (C + 1) / 2;
+            double best = __longlong_as_double(0x7ff0000000000000LL), best2 = best;
+            int arg = 0, arg2 = CH;
+#pragma unroll
+            for (int c = 0; c < C; ++c) {
+                dup[c] = bu[c] - aup[c];
+                const double vlo = fma(t2, dlo[c], alo[c]), vup = fma(t2, dup[c], aup[c]);   // dimension 2
+                const double val = fma(t3n[c], vup - vlo, vlo);                              // dimension 3
+                const double tot = (gs + rc[c]) + val;
+                if (c < CH) { if (tot < best) { best = tot; arg = c; } }
+                else { if (tot < best2) { best2 = tot; arg2 = c; } }
+            }
+            if (best2 < best) { best = best2; arg = arg2; }
+            if (ok01) {
+                *Jp = best;
+                *Ip = arg;
+                if (sp.n_peers) { const int gi[4] = {i0, i1, i2, a3 + it - span3}; peer_store<4>(sp, (int)prob, gi, best); }
+            }
+            Jp += d3.stride;
+            Ip += tp.own_stride[3];
+            __syncwarp();
+            if (lane == 0) mbar_arrive32(bar_empty + 8u * (uint32_t)(it & 3));
+            if (it + 1 < n_iter) prefetch();
         }
-        __syncthreads();      // K of node `it` visible; slab slot slotJ and ring slot (it + 1) % W3 free
-        if (tid == 0 && it + NJ < n_prod) issue(it + NJ, slotJ);
-        if (++slotJ == NJ) { slotJ = 0; phaseJ ^= 1; }
-        if (++slotK == tp.W3) slotK = 0;
+    };
+    auto advance = [&]() {
+        slotK_b += slot_b;
+        if (slotK_b == ring_b) slotK_b = 0;
+    };
+    double A0[C], D0[C], A1[C], D1[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c) { A0[c] = 0.0; D0[c] = 0.0; A1[c] = 0.0; D1[c] = 0.0; }
+    // prologue: the first span3 nodes (no step can run yet)
+    int it = 0;
+#pragma unroll 1
+    for (; it < span3; ++it) {
+        produce(it);
+        if (it >= 1) sync_prev(it);
+        advance();
+    }
+    // steady state, two iterations per trip so that the register sets alternate without copies
+#pragma unroll 1
+    for (; it + 1 < n_iter; it += 2) {
+        produce(it);                          // it < n_prod always holds here (it <= n_iter - 2)
+        sync_prev(it);
+        consume(it, A0, D0, A1, D1);
+        advance();
+        if (it + 1 < n_prod) produce(it + 1);
+        sync_prev(it + 1);
+        consume(it + 1, A1, D1, A0, D0);
+        advance();
+    }
+    if (it < n_iter) {                        // odd count: the last step (it == n_prod: nothing left to produce)
+        if (it < n_prod) produce(it);
+        sync_prev(it);
+        consume(it, A0, D0, A1, D1);
     }
 }
 
@@ -285,7 +431,7 @@ struct StreamState {
     std::vector<CUtensorMap> maps;   // one per J slot
     size_t smem = 0;
     int nthreads = 0, C = 0;
-    void *d_tab[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    void *d_tab[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     ~StreamState() { for (void *p : d_tab) cudaFree(p); }
 };
 
@@ -296,9 +442,9 @@ double pack_bits(uint32_t lo, uint32_t hi) {
     return d;
 }
 
-template <int C>
+template <int C, int NF>
 bool stream_attr(size_t smem) {
-    return cudaFuncSetAttribute((const void *)k_stage_stream<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
+    return cudaFuncSetAttribute((const void *)k_stage_stream<C, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
            cudaSuccess;
 }
 
@@ -316,6 +462,7 @@ void stream_setup(bellman_handle *h) {
     const HostProblem &hp = h->hp;
     if (hp.D != 4 || std::getenv("BELLMAN_NO_STREAM") || std::getenv("BELLMAN_NO_TILE")) return;
     if (hp.C != 6 && hp.C != 9) return;               // instantiated control counts (9 combinations, 6 in failure mode)
+    if (hp.P > 4) return;                             // r[p][c] travels in the kernel parameters
     if (h->ld0 % 2) return;                           // TMA global strides: multiples of 16 bytes
     // structure of Solver_pos_att's channel (same test as k_stage_tile_pa)
     for (int d = 0; d < 4; ++d) {
@@ -345,13 +492,13 @@ void stream_setup(bellman_handle *h) {
         }
         if (cls[c] < 0) cls[c] = NF1++;
     }
-    if (NF1 > SMAXF) return;
+    if (!((C == 9 && NF1 == 5) || (C == 6 && NF1 == 4))) return;   // the instantiated (controls, classes) pairs
 
     auto *ss = new StreamState();
     StreamParams &tp = ss->tp;
     ss->C = C;
-    int fT1 = 0, fT2 = 0, fT3 = 0, fNJ = 0;
-    if (const char *e = std::getenv("BELLMAN_STREAM")) std::sscanf(e, "%d,%d,%d,%d", &fT1, &fT2, &fT3, &fNJ);
+    int fT1 = 0, fT2 = 0, fT3 = 0, fNJ = 0, fNP = -1;
+    if (const char *e = std::getenv("BELLMAN_STREAM")) std::sscanf(e, "%d,%d,%d,%d,%d", &fT1, &fT2, &fT3, &fNJ, &fNP);
     tp.T1 = (fT1 == 1 || fT1 == 2 || fT1 == 4) ? fT1 : 2;
     tp.T0 = 32 / tp.T1;
     tp.T0_log2 = tp.T1 == 1 ? 5 : tp.T1 == 2 ? 4 : 3;
@@ -362,7 +509,7 @@ void stream_setup(bellman_handle *h) {
     tp.NH1 = hi[1] - lo[1] + 2;
     tp.NF1 = NF1;
     tp.span3 = hi[3] - lo[3] + 2;
-    tp.W3 = tp.span3 + 1;
+    tp.W3 = tp.span3 + 2;                                        // one slot of slack: warps run up to an iteration apart
     const int w2 = hi[2] - lo[2] + 1;
     auto smem_of = [&](int T2) {
         const int B2 = T2 + w2;
@@ -388,7 +535,9 @@ void stream_setup(bellman_handle *h) {
     tp.slab_doubles = (int)((((size_t)tp.B0 * tp.B1 * tp.B2 * 8 + 127) / 128 * 128) / 8);
     tp.ring_doubles = tp.W3 * NF1 * tp.B2 * 32;
     ss->smem = smem_of(T2);
-    ss->nthreads = 32 * tp.B2;
+    tp.NP = fNP >= 0 ? std::min(fNP, tp.B2) : 0;
+    if (tp.NP > 0 && T2 + tp.NP > 12) tp.NP = 12 - T2;
+    ss->nthreads = tp.NP > 0 ? 32 * (T2 + tp.NP) : 32 * tp.B2;
     // steps per CTA: the whole owned range unless that leaves the GPU short of CTAs; chunks are
     // multiples of W3 so that a node's ring slot does not depend on the chunk (host table lt3)
     tp.ntile[0] = (h->own_n[0] + tp.T0 - 1) / tp.T0;
@@ -414,6 +563,8 @@ void stream_setup(bellman_handle *h) {
         for (int d = 0; d < 4; ++d) { tp.own_stride[d] = os; os *= h->own_n[d]; }
     }
     tp.allmask = (1u << C) - 1u;
+    for (int p = 0; p < P; ++p)
+        for (int c = 0; c < C; ++c) tp.rc[p][c] = hp.r[(size_t)p * C + c];
 
     // ---- host tables, built with the normative operations (one rounding per operation) ----
     auto locate_t = [&](int p, int d, double xq, int &cell) {
@@ -424,8 +575,10 @@ void stream_setup(bellman_handle *h) {
     };
     const int n0 = hp.n[0], n1 = hp.n[1], n2 = hp.n[2], n3 = hp.n[3];
     std::vector<double> ft0((size_t)P * n1 * n0 * 2), k1((size_t)P * n1 * NF1 * 2), ft2((size_t)P * n3 * n2 * 2),
-        lt3((size_t)P * n3 * C * 2);
+        lt3((size_t)P * n3 * C);
+    std::vector<uint32_t> up3((size_t)P * n3 * C, 0u);
     std::vector<uint32_t> flag3((size_t)P * n3, 0u);
+    tp.blk3_bytes = (16 + 12 * C + 15) / 16 * 16;
     std::vector<int> rep(NF1, 0);                     // a representative control of every class
     for (int c = C - 1; c >= 0; --c) rep[cls[c]] = c;
     const int own_lo3 = h->own_lo[3];
@@ -475,11 +628,11 @@ void stream_setup(bellman_handle *h) {
                 auto slot_off = [&](int node) {
                     int s = (node - (own_lo3 + lo[3])) % tp.W3;
                     if (s < 0) s += tp.W3;
-                    return (uint32_t)((s * NF1 + cls[c]) * tp.B2 * 32);
+                    return (uint32_t)((s * NF1 + cls[c]) * tp.B2 * 256);   // byte offset inside the K ring
                 };
-                const size_t o = (((size_t)p * n3 + i3) * C + c) * 2;
+                const size_t o = ((size_t)p * n3 + i3) * C + c;
                 lt3[o] = t;
-                lt3[o + 1] = pack_bits(slot_off(cell), slot_off(cell + 1));
+                up3[o] = slot_off(cell + 1);
                 if (i3 > 0 && cell == prev3[c] + 1) fl |= 1u << c;
                 prev3[c] = cell;
             }
@@ -489,9 +642,16 @@ void stream_setup(bellman_handle *h) {
     auto upload = [&](const void *src, size_t bytes, void **dst) {
         return cudaMalloc(dst, bytes) == cudaSuccess && cudaMemcpy(*dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess;
     };
+    std::vector<unsigned char> blk((size_t)P * n3 * tp.blk3_bytes, 0);
+    for (size_t r = 0; r < (size_t)P * n3; ++r) {
+        unsigned char *b = blk.data() + r * tp.blk3_bytes;
+        std::memcpy(b, &hp.q[3][r], 8);
+        std::memcpy(b + 8, &flag3[r], 4);
+        std::memcpy(b + 16, &lt3[r * C], 8 * (size_t)C);
+        std::memcpy(b + 16 + 8 * C, &up3[r * C], 4 * (size_t)C);
+    }
     if (!upload(ft0.data(), ft0.size() * 8, &ss->d_tab[0]) || !upload(k1.data(), k1.size() * 8, &ss->d_tab[1]) ||
-        !upload(ft2.data(), ft2.size() * 8, &ss->d_tab[2]) || !upload(lt3.data(), lt3.size() * 8, &ss->d_tab[3]) ||
-        !upload(flag3.data(), flag3.size() * 4, &ss->d_tab[4])) {
+        !upload(ft2.data(), ft2.size() * 8, &ss->d_tab[2]) || !upload(blk.data(), blk.size(), &ss->d_tab[3])) {
         cudaGetLastError();
         delete ss;
         return;
@@ -499,8 +659,7 @@ void stream_setup(bellman_handle *h) {
     tp.ft0 = static_cast<const double2 *>(ss->d_tab[0]);
     tp.k1 = static_cast<const double2 *>(ss->d_tab[1]);
     tp.ft2 = static_cast<const double2 *>(ss->d_tab[2]);
-    tp.lt3 = static_cast<const double2 *>(ss->d_tab[3]);
-    tp.flag3 = static_cast<const uint32_t *>(ss->d_tab[4]);
+    tp.blk3 = static_cast<const unsigned char *>(ss->d_tab[3]);
 
     // one tensor map per J slot: [P][n3][n2][n1][ld0] fp64, box = B0 x B1 x B2 x 1 x 1
     const int nslots = h->store_J_all ? hp.N : 2;
@@ -519,7 +678,7 @@ void stream_setup(bellman_handle *h) {
             return;
         }
     }
-    if (!(C == 9 ? stream_attr<9>(ss->smem) : stream_attr<6>(ss->smem))) {
+    if (!(C == 9 ? stream_attr<9, 5>(ss->smem) : stream_attr<6, 4>(ss->smem))) {
         cudaGetLastError();
         delete ss;
         return;
@@ -527,9 +686,9 @@ void stream_setup(bellman_handle *h) {
     if (std::getenv("BELLMAN_TILE_DEBUG"))
         std::fprintf(stderr,
                      "bellman stream: T = %d %d %d %d, lo = %d %d %d %d hi = %d %d %d %d, slab = %d %d %d, NF1 = %d, W3 = %d, "
-                     "smem = %zu KB, %d threads, grid = %d x %d x %d\n",
+                     "smem = %zu KB, %d threads (NP = %d), grid = %d x %d x %d\n",
                      tp.T0, tp.T1, tp.T2, tp.T3, lo[0], lo[1], lo[2], lo[3], hi[0], hi[1], hi[2], hi[3], tp.B0, tp.B1, tp.B2, NF1,
-                     tp.W3, ss->smem / 1024, ss->nthreads, tp.ntile[0] * tp.ntile[1], tp.ntile[2] * tp.ntile[3], P);
+                     tp.W3, ss->smem / 1024, ss->nthreads, tp.NP, tp.ntile[0] * tp.ntile[1], tp.ntile[2] * tp.ntile[3], P);
     h->sstate = ss;
 }
 
@@ -538,8 +697,8 @@ cudaError_t stream_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     if (!ss) return cudaErrorNotSupported;
     const StreamParams &tp = ss->tp;
     const dim3 grid((unsigned)(tp.ntile[0] * tp.ntile[1]), (unsigned)(tp.ntile[2] * tp.ntile[3]), (unsigned)sp.P);
-    if (ss->C == 9) k_stage_stream<9><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
-    else k_stage_stream<6><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    if (ss->C == 9) k_stage_stream<9, 5><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    else k_stage_stream<6, 4><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
     return cudaGetLastError();
 }
 

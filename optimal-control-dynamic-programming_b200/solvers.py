@@ -240,6 +240,43 @@ class Solver_position(_AxisSolverBase):
         return ds
 
 
+    # --- orbital forward simulation (Solver_position.m:189-361) ------------------------------------
+    mu = 398600.0                                                      # :192
+
+    @staticmethod
+    def sv_from_coe(coe, mu):
+        """position-control/private/sv_from_coe.m:31-66 — state vector from [h e RA incl w TA]."""
+        h, e, RA, incl, w, TA = (float(x) for x in coe)
+        rp = (h ** 2 / mu) * (1 / (1 + e * np.cos(TA))) * (np.cos(TA) * np.array([1.0, 0, 0]) + np.sin(TA) * np.array([0, 1.0, 0]))
+        vp = (mu / h) * (-np.sin(TA) * np.array([1.0, 0, 0]) + (e + np.cos(TA)) * np.array([0, 1.0, 0]))
+        R3_W = np.array([[np.cos(RA), np.sin(RA), 0], [-np.sin(RA), np.cos(RA), 0], [0, 0, 1.0]])
+        R1_i = np.array([[1.0, 0, 0], [0, np.cos(incl), np.sin(incl)], [0, -np.sin(incl), np.cos(incl)]])
+        R3_w = np.array([[np.cos(w), np.sin(w), 0], [-np.sin(w), np.cos(w), 0], [0, 0, 1.0]])
+        Q_pX = (R3_w @ R1_i @ R3_W).T
+        return Q_pX @ rp, Q_pX @ vp
+
+    def get_target_R0V0(self):
+        """:313-331 — target A: perigee altitude 300 km, e = 0.1, equatorial, at perigee."""
+        RE, e = 6378.0, 0.1
+        rp = RE + 300
+        ra = rp * (1 + e) / (1 - e)
+        h_ = np.sqrt(2 * self.mu * rp * ra / (ra + rp))
+        return self.sv_from_coe([h_, e, 0.0, 0.0, 0.0, 0.0], self.mu)
+
+    def get_optimal_path(self, y0=None, n_steps=None, stride_out=1, tol=1e-8):
+        """:189-224 on the GPU for a batch of initial relative states y0 [batch, 6] (default the
+        reference's single [-1 0 0 0 0 0]): nearest policy per axis, one rkf45 call per stage.
+        Returns X_ode45 [batch, n_steps/stride_out + 1, 6] and F_Opt_history [batch, n_steps/stride_out, 3]."""
+        sw = self._sweep
+        y0 = np.array([[-1.0, 0, 0, 0, 0, 0]]) if y0 is None else np.asarray(y0, dtype=np.float64).reshape(-1, 6)
+        N = int(np.ceil(self.T_final / self.h))                        # :206
+        n_steps = N - 1 if n_steps is None else int(n_steps)
+        R0, V0 = self.get_target_R0V0()
+        X, Cc, W = sw.rollout_orbit(self.U_vector, y0, n_steps, self.h, R0, V0, mu=self.mu, tol=tol, stride_out=stride_out)
+        self.rkf45_warnings = W
+        return X, np.asarray(self.U_vector)[Cc]
+
+
 class Solver_attitude(_AxisSolverBase):
     """attitude-control/Solver_attitude.m — simplified_run: three (w, theta) axes, three torques."""
     _rate_dim = 0

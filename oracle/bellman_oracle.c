@@ -106,7 +106,25 @@ static void dimtab_init(dimtab *g, const double *s, int n, int mode)
     g->off = -(s[0] * g->inv_h);
 }
 
-/* one state of one problem: the normative operation order of include/bellman.h */
+/* J_{N-1} of one node when the terminal cost J_N is identically zero (Dynamic_Solver.m:83-84 and the
+ * zeros(...) interpolants of the other classes): every corner is 0, every lerp fma(t, 0 - 0, 0) = +0,
+ * so the stage reduces to min_c ((gs + r[c]) + 0.0) — evaluated here exactly as eval_state would.
+ * Lets a spot check of stage N-2 run at grid sizes whose J arrays do not fit the host. */
+static double first_stage_value(const bellman_desc *d, const double *const *q, const double *r, int64_t s)
+{
+    const int D = d->D;
+    int i[MAXD] = {0, 0, 0, 0};
+    for (int k = 0; k < D; ++k) { i[k] = (int)(s % d->n[k]); s /= d->n[k]; }
+    double gs = q[d->q_order[0]][i[d->q_order[0]]];
+    for (int m = 1; m < D; ++m) gs = gs + q[d->q_order[m]][i[d->q_order[m]]];
+    /* min_c ((gs + r[c]) + 0.0): rounding is monotone, so the minimum is attained at the smallest r[c] */
+    double rmin = r[0];
+    for (int c = 1; c < d->C; ++c) if (r[c] < rmin) rmin = r[c];
+    return (gs + rmin) + 0.0;
+}
+
+/* one state of one problem: the normative operation order of include/bellman.h
+ * (Jn == NULL: J_{k+1} is the first stage from a zero terminal cost, evaluated on the fly) */
 static void eval_state(const bellman_desc *d, const dimtab *g, const double *const *Ta,
                        const double *const *Tb, const double *const *Tc, const double *const *q,
                        const double *r, const int64_t *stride, const double *Jn, int64_t s,
@@ -139,7 +157,7 @@ static void eval_state(const bellman_desc *d, const dimtab *g, const double *con
         for (int m = 0; m < (1 << D); ++m) {
             int64_t oo = o;
             for (int k = 0; k < D; ++k) if (m & (1 << k)) oo += stride[k];
-            v[m] = Jn[oo];
+            v[m] = Jn ? Jn[oo] : first_stage_value(d, q, r, oo);
         }
         for (int k = 0; k < D; ++k)                       /* dimension 0 reduced first */
             for (int m = 0; m < (1 << (D - 1 - k)); ++m)
@@ -426,5 +444,236 @@ int oracle_rollout_axis(const bellman_desc *d, const int32_t *modes, int p, cons
         }
     }
     free(g[0].rinv); free(g[1].rinv);
+    return 0;
+}
+
+/* =============================================================================================
+ * Orbital forward simulation of Solver_position.get_optimal_path.
+ *
+ * Restates, operation by operation (left-to-right association as MATLAB evaluates it):
+ *   position-control/private/stumpC.m:11-17, stumpS.m:11-17      Stumpff functions C(z), S(z)
+ *   position-control/private/kepler_U.m:25-44                    Newton iteration on the universal Kepler equation
+ *   position-control/private/f_and_g.m:21-27, fDot_and_gDot.m:23-29   Lagrange coefficients
+ *   position-control/private/sv_from_coe.m:31-66                 state vector from orbital elements
+ *   position-control/private/rkf45.m:49-118                      Runge-Kutta-Fehlberg 4(5), adaptive step
+ *   position-control/Solver_position.m:189-224                   stage loop: nearest policy, one rkf45 call per stage
+ *   position-control/Solver_position.m:259-309 (rates), :313-331 (get_target_R0V0), :333-361 (update_RV_target)
+ * The private/*.m files use bare-CR line endings (read them with tr '\r' '\n').
+ *
+ * PARITY UNPINNED: the reference stores no output of this path and MATLAB cannot run here.  Details
+ * MATLAB does not document and this restatement fixes: dot products / matrix-vector products are
+ * summed left to right (MATLAB calls BLAS), norm() is sqrt of the left-to-right sum of squares,
+ * tspan(k) = (k-1)*h, x^n is pow(x, n) except x^2 = x*x.  cos/sin/cosh/sinh/pow come from the C
+ * library here and from CUDA's math library on the GPU, so GPU-vs-oracle parity for this path is a
+ * tolerance (tests/test_gpu_orbit.py), not bit equality.
+ * ============================================================================================= */
+static double stumpC(double z)
+{
+    if (z > 0) return (1 - cos(sqrt(z))) / z;
+    if (z < 0) return (cosh(sqrt(-z)) - 1) / (-z);
+    return 0.5;
+}
+
+static double stumpS(double z)
+{
+    if (z > 0) { const double s = sqrt(z); return (s - sin(s)) / pow(s, 3); }
+    if (z < 0) { const double s = sqrt(-z); return (sinh(s) - s) / pow(s, 3); }
+    return 1.0 / 6;
+}
+
+/* kepler_U.m:25-44; *n_iter receives the iteration count */
+double oracle_kepler_U(double mu, double dt, double ro, double vro, double a, int *n_iter)
+{
+    const double error = 1.e-8;
+    const int nMax = 1000;
+    const double smu = sqrt(mu);
+    double x = smu * fabs(a) * dt;
+    int n = 0;
+    double ratio = 1;
+    while (fabs(ratio) > error && n <= nMax) {
+        n = n + 1;
+        const double x2 = x * x;
+        const double C = stumpC(a * x2);
+        const double S = stumpS(a * x2);
+        const double F = ro * vro / smu * x2 * C + (1 - a * ro) * pow(x, 3) * S + ro * x - smu * dt;
+        const double dFdx = ro * vro / smu * x * (1 - a * x2 * S) + (1 - a * ro) * x2 * C + ro;
+        ratio = F / dFdx;
+        x = x - ratio;
+    }
+    if (n_iter) *n_iter = n;
+    return x;
+}
+
+/* Solver_position.m:333-361 (update_RV_target) with f_and_g.m / fDot_and_gDot.m inlined */
+void oracle_update_RV_target(double mu, const double *R0, const double *V0, double t, double *R2, double *V2)
+{
+    const double r0 = sqrt(R0[0] * R0[0] + R0[1] * R0[1] + R0[2] * R0[2]);
+    const double v0 = sqrt(V0[0] * V0[0] + V0[1] * V0[1] + V0[2] * V0[2]);
+    const double vr0 = (R0[0] * V0[0] + R0[1] * V0[1] + R0[2] * V0[2]) / r0;
+    const double alpha = 2 / r0 - v0 * v0 / mu;
+    const double x = oracle_kepler_U(mu, t, r0, vr0, alpha, NULL);
+    const double z = alpha * (x * x);
+    const double f = 1 - x * x / r0 * stumpC(z);
+    const double g = t - 1 / sqrt(mu) * pow(x, 3) * stumpS(z);
+    for (int k = 0; k < 3; ++k) R2[k] = f * R0[k] + g * V0[k];
+    const double r2 = sqrt(R2[0] * R2[0] + R2[1] * R2[1] + R2[2] * R2[2]);
+    const double fdot = sqrt(mu) / r2 / r0 * (z * stumpS(z) - 1) * x;
+    const double gdot = 1 - x * x / r2 * stumpC(z);
+    for (int k = 0; k < 3; ++k) V2[k] = fdot * R0[k] + gdot * V0[k];
+}
+
+/* sv_from_coe.m:31-66; coe = [h e RA incl w TA] */
+void oracle_sv_from_coe(const double *coe, double mu, double *r, double *v)
+{
+    const double h = coe[0], e = coe[1], RA = coe[2], incl = coe[3], w = coe[4], TA = coe[5];
+    const double krp = (h * h / mu) * (1 / (1 + e * cos(TA)));
+    const double rp[3] = {krp * (cos(TA) * 1 + sin(TA) * 0), krp * (cos(TA) * 0 + sin(TA) * 1), krp * (cos(TA) * 0 + sin(TA) * 0)};
+    const double kvp = mu / h;
+    const double vp[3] = {kvp * (-sin(TA) * 1 + (e + cos(TA)) * 0), kvp * (-sin(TA) * 0 + (e + cos(TA)) * 1),
+                          kvp * (-sin(TA) * 0 + (e + cos(TA)) * 0)};
+    const double R3W[3][3] = {{cos(RA), sin(RA), 0}, {-sin(RA), cos(RA), 0}, {0, 0, 1}};
+    const double R1i[3][3] = {{1, 0, 0}, {0, cos(incl), sin(incl)}, {0, -sin(incl), cos(incl)}};
+    const double R3w[3][3] = {{cos(w), sin(w), 0}, {-sin(w), cos(w), 0}, {0, 0, 1}};
+    double A[3][3], Q[3][3];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) A[i][j] = (R3w[i][0] * R1i[0][j] + R3w[i][1] * R1i[1][j]) + R3w[i][2] * R1i[2][j];
+    for (int i = 0; i < 3; ++i)
+        for (int j = 0; j < 3; ++j) Q[i][j] = (A[i][0] * R3W[0][j] + A[i][1] * R3W[1][j]) + A[i][2] * R3W[2][j];
+    for (int i = 0; i < 3; ++i) {      /* Q_pX = Q' */
+        r[i] = (Q[0][i] * rp[0] + Q[1][i] * rp[1]) + Q[2][i] * rp[2];
+        v[i] = (Q[0][i] * vp[0] + Q[1][i] * vp[1]) + Q[2][i] * vp[2];
+    }
+}
+
+/* Solver_position.m:313-331 */
+void oracle_get_target_R0V0(double mu, double *R0, double *V0)
+{
+    const double RE = 6378;
+    const double rp = RE + 300, e = 0.1;
+    const double ra = rp * (1 + e) / (1 - e);
+    const double h_ = sqrt(2 * mu * rp * ra / (ra + rp));
+    const double coe[6] = {h_, e, 0, 0, 0, 0};
+    oracle_sv_from_coe(coe, mu, R0, V0);
+}
+
+typedef struct { double mu; const double *R0, *V0; double a[3]; } orbit_ctx;
+
+/* Solver_position.m:259-309 (rates) */
+static void orbit_rates(const orbit_ctx *c, double t, const double *y, double *dydt)
+{
+    double R[3], V[3];
+    oracle_update_RV_target(c->mu, c->R0, c->V0, t, R, V);
+    const double norm_R = pow((R[0] * R[0] + R[1] * R[1]) + R[2] * R[2], .5);
+    const double RdotV = (R[0] * V[0] + R[1] * V[1]) + R[2] * V[2];
+    const double cr[3] = {R[1] * V[2] - R[2] * V[1], R[2] * V[0] - R[0] * V[2], R[0] * V[1] - R[1] * V[0]};
+    const double H = pow((cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2], .5);
+    const double dx = y[0], dy = y[1], dz = y[2], dvx = y[3], dvy = y[4], dvz = y[5];
+    const double mu = c->mu;
+    const double nR2 = norm_R * norm_R, nR3 = pow(norm_R, 3), nR4 = pow(norm_R, 4), H2 = H * H;
+    const double dax = (2 * mu / nR3 + H2 / nR4) * dx - 2 * RdotV / nR4 * H * dy + 2 * H / nR2 * dvy + c->a[0];
+    const double day = -(mu / nR3 - H2 / nR4) * dy + 2 * RdotV / nR4 * H * dx - 2 * H / nR2 * dvx + c->a[1];
+    const double daz = -mu / nR3 * dz + c->a[2];
+    dydt[0] = dvx; dydt[1] = dvy; dydt[2] = dvz; dydt[3] = dax; dydt[4] = day; dydt[5] = daz;
+}
+
+static double eps_of(double t)   /* MATLAB eps(t): spacing of doubles at |t| */
+{
+    t = fabs(t);
+    if (t < 2.2250738585072014e-308) return 4.9406564584124654e-324;
+    int e;
+    frexp(t, &e);
+    return ldexp(1.0, e - 53);
+}
+
+/* rkf45.m:49-118 for a 6-state system; returns the last row of yout in y, the number of accepted
+ * steps, and 1 in *warned when the step size fell below hmin (rkf45.m:113-117) */
+static int orbit_rkf45(const orbit_ctx *c, double t0, double tf, double *y, double tol, int max_steps, int *warned)
+{
+    static const double a[6] = {0, 1. / 4, 3. / 8, 12. / 13, 1, 1. / 2};
+    static const double b[6][5] = {{0, 0, 0, 0, 0},
+                                   {1. / 4, 0, 0, 0, 0},
+                                   {3. / 32, 9. / 32, 0, 0, 0},
+                                   {1932. / 2197, -7200. / 2197, 7296. / 2197, 0, 0},
+                                   {439. / 216, -8, 3680. / 513, -845. / 4104, 0},
+                                   {-8. / 27, 2, -3544. / 2565, 1859. / 4104, -11. / 40}};
+    static const double c4[6] = {25. / 216, 0, 1408. / 2565, 2197. / 4104, -1. / 5, 0};
+    static const double c5[6] = {16. / 135, 0, 6656. / 12825, 28561. / 56430, -9. / 50, 2. / 55};
+    double t = t0, h = (tf - t0) / 100, f[6][6], yi[6], yin[6];
+    int accepted = 0, iters = 0;
+    *warned = 0;
+    while (t < tf && iters++ < max_steps) {
+        const double hmin = 16 * eps_of(t);
+        const double ti = t;
+        memcpy(yi, y, sizeof(yi));
+        for (int i = 0; i < 6; ++i) {
+            const double t_inner = ti + a[i] * h;
+            memcpy(yin, yi, sizeof(yin));
+            for (int j = 0; j < i; ++j)
+                for (int k = 0; k < 6; ++k) yin[k] = yin[k] + h * b[i][j] * f[j][k];
+            orbit_rates(c, t_inner, yin, f[i]);
+        }
+        double te_max = 0, ymax = 0;
+        for (int k = 0; k < 6; ++k) {
+            double te = 0;
+            for (int i = 0; i < 6; ++i) te = te + (h * f[i][k]) * (c4[i] - c5[i]);
+            te_max = fmax(te_max, fabs(te));
+            ymax = fmax(ymax, fabs(y[k]));
+        }
+        const double te_allowed = tol * fmax(ymax, 1.0);
+        const double delta = pow(te_allowed / (te_max + 2.220446049250313e-16), 1. / 5);
+        if (te_max <= te_allowed) {
+            h = fmin(h, tf - t);
+            t = t + h;
+            for (int k = 0; k < 6; ++k) {
+                double s = 0;
+                for (int i = 0; i < 6; ++i) s = s + (h * f[i][k]) * c5[i];
+                y[k] = yi[k] + s;
+            }
+            ++accepted;
+        }
+        h = fmin(delta * h, 4 * h);
+        if (h < hmin) { *warned = 1; break; }
+    }
+    return accepted;
+}
+
+/* Solver_position.m:206-224: the stage loop.  The three axis policies are the nearest-node
+ * interpolants U{1,2,3}_Opt = griddedInterpolant({s_x, s_v}, U_vector(U_idx), 'nearest') (:144-146)
+ * given as problems 0..2 of `d` with idx [3][S] (0-based control indices) and u_values [C].
+ * y0 [6][batch]; X_out [6][n_steps+1][batch]; C_out [3][n_steps][batch]; warn_out [batch] counts the
+ * rkf45 calls that stopped on the minimum step size. */
+int oracle_rollout_orbit(const bellman_desc *d, const int32_t *modes, const int32_t *idx, const double *u_values,
+                         double mu, const double *R0, const double *V0, double h, int n_steps, double tol,
+                         const double *y0, int batch, double *X_out, int32_t *C_out, int32_t *warn_out)
+{
+    if (d->D != 2 || d->P < 3) return -1;
+    dimtab g[3][2];
+    for (int p = 0; p < 3; ++p)
+        for (int k = 0; k < 2; ++k) dimtab_init(&g[p][k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * 2 + k]);
+    const int64_t S = (int64_t)d->n[0] * d->n[1];
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < batch; ++b) {
+        double y[6];
+        for (int k = 0; k < 6; ++k) y[k] = y0[(size_t)b * 6 + k];
+        double *X = X_out + (size_t)b * 6 * (n_steps + 1);
+        int32_t *Cc = C_out + (size_t)b * 3 * n_steps;
+        memcpy(X, y, sizeof(y));
+        orbit_ctx c = {mu, R0, V0, {0, 0, 0}};
+        int warns = 0;
+        for (int ks = 1; ks <= n_steps; ++ks) {
+            for (int p = 0; p < 3; ++p) {     /* a_x = U1_Opt(x1, v1) ... :215-217 */
+                const int ci = idx[(size_t)p * S + nearest_node(&g[p][0], y[p]) + (int64_t)nearest_node(&g[p][1], y[3 + p]) * d->n[0]];
+                Cc[(size_t)(ks - 1) * 3 + p] = ci;
+                c.a[p] = u_values[ci];
+            }
+            int w;
+            orbit_rkf45(&c, (double)(ks - 1) * h, (double)ks * h, y, tol, 100000, &w);
+            warns += w;
+            memcpy(X + (size_t)ks * 6, y, sizeof(y));
+        }
+        if (warn_out) warn_out[b] = warns;
+    }
+    for (int p = 0; p < 3; ++p)
+        for (int k = 0; k < 2; ++k) free(g[p][k].rinv);
     return 0;
 }

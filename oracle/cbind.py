@@ -157,15 +157,18 @@ def set_threads(n):
 
 
 def stage_points(d, J_next_p, states, p=0, modes=None):
-    """Evaluate only the listed linear state indices of problem ``p``.  Returns (J, idx0)."""
+    """Evaluate only the listed linear state indices of problem ``p``.  Returns (J, idx0).
+    J_next_p = None: J_{k+1} is the first stage from a zero terminal cost, evaluated on the fly (a
+    spot check of the SECOND stage at grid sizes whose arrays do not fit the host)."""
     cd, keep = to_cdesc(d)
     modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
-    Jn = _arr(J_next_p).ravel()
+    Jn = None if J_next_p is None else _arr(J_next_p).ravel()
     st = np.ascontiguousarray(states, dtype=np.int64)
     Jo = np.zeros(len(st))
     Io = np.zeros(len(st), dtype=np.int32)
     rc = lib().oracle_stage_points(C.byref(cd), modes.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(p),
-                                   Jn.ctypes.data_as(_dp), st.ctypes.data_as(C.POINTER(C.c_int64)),
+                                   Jn.ctypes.data_as(_dp) if Jn is not None else _dp(),
+                                   st.ctypes.data_as(C.POINTER(C.c_int64)),
                                    C.c_int64(len(st)), Jo.ctypes.data_as(_dp),
                                    Io.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
@@ -206,3 +209,52 @@ def rollout_axis(d, idx, u_inc, x0, n_steps, h, rate_dim, p=0, time_varying=Fals
                                    Cc.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
     return X, Cc
+
+
+def target_R0V0(mu=398600.0):
+    """Solver_position.get_target_R0V0 (position-control/Solver_position.m:313-331)."""
+    R0, V0 = (C.c_double * 3)(), (C.c_double * 3)()
+    lib().oracle_get_target_R0V0(C.c_double(mu), R0, V0)
+    return np.array(R0[:]), np.array(V0[:])
+
+
+def kepler_U(mu, dt, ro, vro, a):
+    fn = lib().oracle_kepler_U
+    fn.restype = C.c_double
+    n = C.c_int()
+    x = fn(C.c_double(mu), C.c_double(dt), C.c_double(ro), C.c_double(vro), C.c_double(a), C.byref(n))
+    return x, n.value
+
+
+def update_RV_target(mu, R0, V0, t):
+    R, V = (C.c_double * 3)(), (C.c_double * 3)()
+    lib().oracle_update_RV_target(C.c_double(mu), (C.c_double * 3)(*R0), (C.c_double * 3)(*V0), C.c_double(t), R, V)
+    return np.array(R[:]), np.array(V[:])
+
+
+def sv_from_coe(coe, mu):
+    r, v = (C.c_double * 3)(), (C.c_double * 3)()
+    lib().oracle_sv_from_coe((C.c_double * 6)(*coe), C.c_double(mu), r, v)
+    return np.array(r[:]), np.array(v[:])
+
+
+def rollout_orbit(d, idx, u_values, y0, n_steps, h, R0, V0, mu=398600.0, tol=1e-8, modes=None):
+    """Solver_position.get_optimal_path's stage loop (Solver_position.m:206-224) for a batch.
+    idx [3, S] 0-based policies of the x, y, z axes; y0 [batch, 6].
+    Returns X [batch, n_steps+1, 6], control indices [batch, n_steps, 3], rkf45 warnings [batch]."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    y0 = _arr(y0).reshape(-1, 6)
+    batch = len(y0)
+    ia = np.ascontiguousarray(idx, dtype=np.int32)
+    X = np.zeros((batch, n_steps + 1, 6))
+    Cc = np.zeros((batch, n_steps, 3), dtype=np.int32)
+    W = np.zeros(batch, dtype=np.int32)
+    uv = _arr(u_values)
+    ip = C.POINTER(C.c_int32)
+    rc = lib().oracle_rollout_orbit(C.byref(cd), modes.ctypes.data_as(ip), ia.ctypes.data_as(ip), uv.ctypes.data_as(_dp),
+                                    C.c_double(mu), (C.c_double * 3)(*R0), (C.c_double * 3)(*V0), C.c_double(h),
+                                    C.c_int(n_steps), C.c_double(tol), y0.ctypes.data_as(_dp), C.c_int(batch),
+                                    X.ctypes.data_as(_dp), Cc.ctypes.data_as(ip), W.ctypes.data_as(ip))
+    assert rc == 0
+    return X, Cc, W

@@ -22,6 +22,18 @@ def make(kind):
         o = bb.Dynamic_Solver()
         return bb.tables.kirk_desc(o.A, o.B, o.Q, o.R, 12, o.x_min, o.x_max, 256, o.u_min, o.u_max, 48,
                                    store_J_all=False, store_idx_all=False)
+    if kind == "kirk_odd":
+        # odd leading dimension: D = 2 grids pad it to even (TMA stride rule), which the neighbours'
+        # peer-store addressing must reproduce for BOTH partition dimensions
+        o = bb.Dynamic_Solver()
+        t = bb.tables
+        s0, s1, u = t.linspace(-2.5, 3.0, 255), t.linspace(-2.5, 3.0, 120), t.linspace(-40.0, 10.0, 24)
+        A, B = o.A, o.B.ravel()
+        row = lambda x: np.ascontiguousarray(x).reshape(1, -1)
+        return t.Desc(n=[255, 120], C=24, N=12, grid=[row(s0), row(s1)], src_a=[0, 0], src_b=[1, 1],
+                      Ta=[row(A[0, 0] * s0), row(A[1, 0] * s0)], Tb=[row(A[0, 1] * s1), row(A[1, 1] * s1)],
+                      Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
+                      q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u)).validate()
     if kind == "attitude":
         s = bb.Solver_attitude()
         s.n_mesh_w, s.n_mesh_t = 400, 120

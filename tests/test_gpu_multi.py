@@ -16,7 +16,7 @@ def _ngpu():
 
 
 @pytest.mark.parametrize("halo", ["fused_p2p", "nccl_sendrecv"])
-@pytest.mark.parametrize("kind", ["kirk", "attitude", "pos_att"])
+@pytest.mark.parametrize("kind", ["kirk", "kirk_odd", "attitude", "pos_att"])
 def test_slab_partitioned_sweep_over_nccl(kind, halo):
     n = _ngpu()
     if n < 2:

@@ -630,10 +630,12 @@ def test_tile_kernel_variants(bellman, oracle_lib, monkeypatch, env):
 
 
 @pytest.mark.parametrize("env", [{"BELLMAN_STREAM": "1,2,0,2"}, {"BELLMAN_STREAM": "2,3,8,4"}, {"BELLMAN_STREAM": "4,4,0,3"},
-                                 {"BELLMAN_STREAM": "2,8,4,3"}, {"BELLMAN_STREAM": "2,10,0,2"}])
+                                 {"BELLMAN_STREAM": "2,8,4,3"}, {"BELLMAN_STREAM": "2,10,0,2"},
+                                 {"BELLMAN_STREAM": "2,4,0,3,2"}, {"BELLMAN_STREAM": "2,8,0,3,4"}, {"BELLMAN_STREAM": "1,3,8,2,1"}])
 def test_stream_kernel_variants(bellman, oracle_lib, monkeypatch, env):
-    """k_stage_stream with forced geometry "T1,T2,T3,NJ": 32x1 / 16x2 / 8x4 column patches, 2..10 consumer
-    warps, the walk cut into chunks (T3, a multiple of the ring length), slab rings of 2..4 boxes; rough
+    """k_stage_stream with forced geometry "T1,T2,T3,NJ[,NP]": 32x1 / 16x2 / 8x4 column patches, 2..10 consumer
+    warps, the walk cut into chunks (T3, a multiple of the ring length), slab rings of 2..4 boxes, warp
+    specialisation (NP dedicated producer warps); rough
     terminal cost, three channels with different grids, several stages (ping-pong slots)."""
     for k, v in env.items():
         monkeypatch.setenv(k, v)
