@@ -212,24 +212,24 @@ def run_reference_arm(args):
 
 
 def cpu_slab_rate(d, seconds_target, threads=0):
-    """The oracle on a CONTIGUOUS slab of states (whole rows of the last dimension, all problems): the
-    cache-friendly counterpart of cpu_sample_rate's random states.  Needs the full J arrays on the host, so
-    only for grids up to 2^28 states.  Returns (updates/s, cores, description) or None."""
+    """The oracle on a CONTIGUOUS block of states of problem 0 (consecutive linear indices: whole rows of
+    the grid, cache-friendly), the counterpart of cpu_sample_rate's random states.  Needs J_{k+1} on the
+    host, so only for grids up to 2^28 states.  Returns (updates/s, cores, description) or None."""
     from oracle import cbind
-    if d.S * d.P > 2 ** 28:
+    if d.S > 2 ** 28:
         return None
     cbind.set_threads(threads or len(os.sched_getaffinity(0)))
     cores = cbind.num_threads()
     rng = np.random.default_rng(1)
-    Jn = rng.normal(size=(d.P, d.S))
-    pd = d.D - 1
-    per_index = d.S // d.n[pd] * d.P * d.C                      # updates per index of the last dimension
-    t0 = time.perf_counter(); cbind.stage(d, Jn, part_dim=pd, own_lo=0, own_hi=1); dt = time.perf_counter() - t0
-    width = int(min(d.n[pd], max(1, per_index / max(dt, 1e-9) * seconds_target / per_index)))
-    lo = (d.n[pd] - width) // 2
-    t0 = time.perf_counter(); cbind.stage(d, Jn, part_dim=pd, own_lo=lo, own_hi=lo + width); dt = time.perf_counter() - t0
-    return width * per_index / dt, cores, "contiguous slab: %d of %d indices of dimension %d, all %d problems (%.1f s)" % (
-        width, d.n[pd], pd, d.P, dt)
+    Jn = rng.normal(size=d.S)
+    n = min(d.S, 20000)
+    lo = (d.S - n) // 2
+    t0 = time.perf_counter(); cbind.stage_points(d, Jn, np.arange(lo, lo + n)); dt = time.perf_counter() - t0
+    n = int(min(d.S, max(n, n / max(dt, 1e-9) * seconds_target)))
+    lo = (d.S - n) // 2
+    t0 = time.perf_counter(); cbind.stage_points(d, Jn, np.arange(lo, lo + n)); dt = time.perf_counter() - t0
+    return n * d.C / dt, cores, "%d consecutive states (%.1f rows of dimension 0) x %d controls of one stage (%.1f s)" % (
+        n, n / d.n[0], d.C, dt)
 
 
 def sharded_parity(bb, sw, d, rank, world, part_dim, kernel, n_points=3000):
@@ -299,6 +299,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (N = 1 default run)")
+    ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal slabs (no trial-run balancing)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -351,8 +352,8 @@ def main():
 
     part_dim = pick_part_dim(d)
 
-    def open_sweep(pd, dd=None):
-        s = bb.Sweep(dd if dd is not None else d, device=local, part_dim=pd, rank=rank, nranks=world)
+    def open_sweep(pd, dd=None, cuts=None):
+        s = bb.Sweep(dd if dd is not None else d, device=local, part_dim=pd, rank=rank, nranks=world, part_cuts=cuts)
         if world > 1:
             ids = [bb.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -374,6 +375,37 @@ def main():
     K, W = args.steps, args.warmup
     if W + K + 2 > d.N - 1:
         raise SystemExit("steps+warmup exceed the horizon of this workload")
+
+    # ---- slab balancing (untimed): the cost per index along the slab dimension is not uniform (clamped
+    # queries, halo stores), so equal slabs leave the fastest rank waiting for the slowest at every stage.
+    # Two trial rounds of 2 stages: per-rank kernel time -> new boundaries (bellman_desc.part_cuts)
+    # proportional to the measured speed, multiples of 32 indices.
+    cuts = None
+    if world > 1 and not args.no_balance:
+        n_p = d.n[part_dim]
+        for _round in range(2):
+            sw.run(2, kernel=kernel)
+            stt = sw.stats()
+            t_mine = torch.tensor([stt["ms"] - stt["ms_exchange"], float(sw.slab[1] - sw.slab[0])], dtype=torch.float64, device="cuda")
+            allt = [torch.zeros_like(t_mine) for _ in range(world)]
+            dist.all_gather(allt, t_mine)
+            ms_r = np.array([float(t[0]) for t in allt])
+            rows_r = np.array([float(t[1]) for t in allt])
+            speed = rows_r / ms_r
+            want = n_p * speed / speed.sum()
+            edges = np.concatenate([[0.0], np.cumsum(want)])
+            new = [int(round(e / 32.0)) * 32 for e in edges]
+            new[0], new[-1] = 0, n_p
+            if any(b - a < 64 for a, b in zip(new[:-1], new[1:])) or new == (cuts or []):
+                break
+            cuts = new
+            sw.close()
+            try:
+                sw = open_sweep(part_dim, cuts=cuts)
+            except bb.BellmanError:
+                cuts = None
+                sw = open_sweep(part_dim)
+                break
 
     # ---- device-resident throughput ("value") ------------------------------------------------
     sw.run(W, kernel=kernel, use_graph=use_graph)                      # untimed warm-up stages
@@ -546,7 +578,7 @@ def main():
                        if world > 1 else "none",
                        "l2": "J_{k+1} (%.0f MB) exceeds the 126 MB L2; no flush needed" % (S_all * 8 / 1e6)
                        if S_all * 8 > 130e6 else "inputs fit L2 (stage-to-stage reuse is the workload)",
-                       "cuda_graph": bool(use_graph)},
+                       "slab_cuts": cuts, "cuda_graph": bool(use_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(main_launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K,
             "sharded_parity": parity["main"], "parity_checks": parity, "cfg5": cfg5,

@@ -131,6 +131,10 @@ typedef struct bellman_desc {
     int32_t part_dim;
     int32_t rank;
     int32_t nranks;
+    /* optional explicit slab boundaries along part_dim: rank r owns [part_cuts[r], part_cuts[r+1]),
+       part_cuts[0] = 0, part_cuts[nranks] = n[part_dim], strictly increasing; NULL = equal slabs.  Lets
+       the host balance slabs whose cost per index differs (e.g. from per-rank times of a trial run). */
+    const int32_t *part_cuts;
 } bellman_desc;
 
 typedef struct bellman_run_opts {
@@ -177,6 +181,16 @@ int  bellman_comm_init(bellman_handle *h, const void *id128);
  * 0: grouped ncclSend/ncclRecv of the halo ranges after every stage (fallback, or BELLMAN_NO_P2P=1);
  * valid after bellman_comm_init */
 int  bellman_halo_mode(const bellman_handle *h);
+
+/* Single-process multi-GPU (one host thread drives every GPU — what a MATLAB interpreter calling
+ * run(obj) needs): create n handles with part_dim >= 0, nranks = n, rank = r and device = the GPU of
+ * slab r (several slabs may share one GPU), call bellman_group_init once, then run them TOGETHER with
+ * bellman_group_run (bellman_run refuses such handles: a slab cannot advance alone).  No NCCL: the
+ * stage kernels store halo values straight into the neighbouring slabs' buffers (CUDA peer access)
+ * and stages are ordered by neighbour flags.  set_J / get_J / get_idx / get_points work per handle.
+ * The check log (opts->check_period) holds the sums over all slabs, in every handle. */
+int  bellman_group_init(bellman_handle **handles, int32_t n);
+int  bellman_group_run(bellman_handle **handles, int32_t n, int32_t n_stages, const bellman_run_opts *opts);
 
 /* sweep */
 int  bellman_set_J(bellman_handle *h, const double *J_host /*[P][S] global, NULL = zeros*/);

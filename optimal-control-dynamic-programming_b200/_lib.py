@@ -35,6 +35,7 @@ class CDesc(C.Structure):
         ("q_order", C.c_int32 * MAXD), ("q", _dp * MAXD), ("r", _dp),
         ("store_J_all", C.c_int32), ("store_idx_all", C.c_int32), ("device", C.c_int32),
         ("part_dim", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
+        ("part_cuts", C.POINTER(C.c_int32)),
     ]
 
 
@@ -60,7 +61,7 @@ EXPORTS = [
     "bellman_set_J", "bellman_set_stage", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
-    "bellman_rollout_orbit", "bellman_get_points",
+    "bellman_rollout_orbit", "bellman_get_points", "bellman_group_init", "bellman_group_run",
 ]
 
 _lib = None
@@ -101,6 +102,8 @@ def load():
     lib.bellman_policy_lookup.argtypes = [C.c_void_p, C.c_int32, C.c_int32, _dp, C.c_int32, _ip]
     lib.bellman_rollout_axis.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_double, _dp,
                                          _dp, C.c_int32, C.c_int32, _dp, _ip]
+    lib.bellman_group_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
+    lib.bellman_group_run.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.POINTER(CRunOpts)]
     lib.bellman_get_points.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, _dp, _ip]
     lib.bellman_rollout_orbit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(COrbitOpts), _dp, _dp, C.c_int32, _dp, _ip, _ip]
     _lib = lib
@@ -111,7 +114,7 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1):
+def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None):
     """tables.Desc -> (CDesc, keepalive)."""
     cd = CDesc()
     keep = []
@@ -137,6 +140,11 @@ def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1):
     cd.store_J_all = int(bool(d.store_J_all))
     cd.store_idx_all = int(bool(d.store_idx_all))
     cd.device, cd.part_dim, cd.rank, cd.nranks = int(device), int(part_dim), int(rank), int(nranks)
+    if part_cuts is not None:
+        pc = np.ascontiguousarray(part_cuts, dtype=np.int32)
+        assert len(pc) == nranks + 1
+        keep.append(pc)
+        cd.part_cuts = pc.ctypes.data_as(_ip)
     return cd, keep
 
 
@@ -163,10 +171,10 @@ def query_stencil(d):
     return lo, hi
 
 
-def plan_slabs(d, part_dim, nranks):
+def plan_slabs(d, part_dim, nranks, part_cuts=None):
     """Slab plan [(own_lo, own_hi, ext_lo, ext_hi)] per rank from the exact reach analysis.  Host-only."""
     lib = load()
-    cd, keep = to_cdesc(d)
+    cd, keep = to_cdesc(d, nranks=nranks, part_cuts=part_cuts)
     slabs = (CSlab * nranks)()
     rc = lib.bellman_plan_slabs(C.byref(cd), part_dim, nranks, slabs)
     if rc != 0:
@@ -186,10 +194,10 @@ def get_unique_id():
 class Sweep:
     """One ``bellman_handle``: device-resident tables + J/idx storage for a (batched) problem."""
 
-    def __init__(self, desc, device=-1, part_dim=-1, rank=0, nranks=1):
+    def __init__(self, desc, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None):
         self.lib = load()
         self.desc = desc
-        cd, keep = to_cdesc(desc, device, part_dim, rank, nranks)
+        cd, keep = to_cdesc(desc, device, part_dim, rank, nranks, part_cuts)
         h = C.c_void_p()
         rc = self.lib.bellman_create(C.byref(cd), C.byref(h))
         if rc != 0:
@@ -364,3 +372,81 @@ class Sweep:
                                                    y0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp),
                                                    Cc.ctypes.data_as(_ip), W.ctypes.data_as(_ip)))
         return X, Cc, W
+
+
+class SweepGroup:
+    """Single-process multi-GPU: n slabs of one problem, driven together by ONE host thread
+    (bellman_group_init / bellman_group_run).  ``devices`` lists the GPU of every slab; several slabs
+    may share a GPU (``devices=[0, 0]`` exercises the sharded path on a single-GPU box)."""
+
+    def __init__(self, desc, devices, part_dim=None, part_cuts=None):
+        self.desc = desc
+        n = len(devices)
+        if part_dim is None:           # the dimension with the smallest halo, from the host-side reach analysis
+            best = None
+            for pd in range(desc.D):
+                try:
+                    sl = plan_slabs(desc, pd, n, part_cuts)
+                except BellmanError:
+                    continue
+                cost = max((e - c) / max(b - a, 1) for a, b, c, e in sl)
+                if best is None or cost < best[0] - 1e-9:
+                    best = (cost, pd)
+            part_dim = best[1]
+        self.part_dim = part_dim
+        self.slabs = [Sweep(desc, device=dev, part_dim=part_dim, rank=r, nranks=n, part_cuts=part_cuts)
+                      for r, dev in enumerate(devices)]
+        self.lib = self.slabs[0].lib
+        self._arr = (C.c_void_p * n)(*[s.h for s in self.slabs])
+        rc = self.lib.bellman_group_init(self._arr, n)
+        if rc != 0:
+            raise BellmanError(rc, self.lib.bellman_last_error(self.slabs[0].h).decode())
+
+    def set_J(self, J=None):
+        for s in self.slabs:
+            s.set_J(J)
+
+    def run(self, n_stages=None, kernel=KERNEL_AUTO, check_period=0, check_tol=0.0):
+        if n_stages is None:
+            n_stages = self.current_stage - 1
+        o = CRunOpts(C.sizeof(CRunOpts), kernel, check_period, check_tol, 0, 0)
+        rc = self.lib.bellman_group_run(self._arr, len(self.slabs), int(n_stages), C.byref(o))
+        if rc != 0:
+            msgs = [self.lib.bellman_last_error(s.h).decode() for s in self.slabs]
+            raise BellmanError(rc, "; ".join(m for m in msgs if m))
+        return self
+
+    @property
+    def current_stage(self):
+        return self.slabs[0].current_stage
+
+    @property
+    def last_kernel(self):
+        return self.slabs[0].last_kernel
+
+    def stats(self):
+        return self.slabs[0].stats()
+
+    def _gather(self, parts):
+        """Stitch per-slab [P, S_own] arrays (slabs along part_dim) into the global [P, S]."""
+        d, pd = self.desc, self.part_dim
+        inner = int(np.prod(d.n[:pd]))
+        outer = int(np.prod(d.n[pd + 1:]))
+        out = np.empty((d.P, outer, d.n[pd], inner), dtype=parts[0].dtype)
+        for s, a in zip(self.slabs, parts):
+            lo, hi = s.slab[0], s.slab[1]
+            out[:, :, lo:hi, :] = a.reshape(d.P, outer, hi - lo, inner)
+        return out.reshape(d.P, d.S)
+
+    def get_J(self, stage=None):
+        return self._gather([s.get_J(stage) for s in self.slabs])
+
+    def get_idx(self, stage=None):
+        return self._gather([s.get_idx(stage) for s in self.slabs])
+
+    def check_log(self):
+        return self.slabs[0].check_log()
+
+    def close(self):
+        for s in self.slabs:
+            s.close()

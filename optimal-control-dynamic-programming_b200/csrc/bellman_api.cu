@@ -253,7 +253,7 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
 extern "C" void bellman_destroy(bellman_handle *h) {
     if (!h) return;
     if (h->stream) cudaStreamSynchronize(h->stream);
-    if (h->fused_halo) {
+    if (h->fused_halo && !h->group_mode) {
         // nobody may still be storing into my J when it is freed
         stage_barrier(h);
         cudaStreamSynchronize(h->stream);
@@ -624,7 +624,7 @@ extern "C" int bellman_comm_init(bellman_handle *h, const void *id128) {
 // after stage `stage` has been written into its slot: fill the halo part of that slot
 static int exchange_halo(bellman_handle *h, int stage) {
     if (h->nranks <= 1) return BELLMAN_OK;
-    if (!h->comm) { h->err = "partitioned handle needs bellman_comm_init before running"; return BELLMAN_ERR_STATE; }
+    if (!h->comm) { h->err = "partitioned handle needs bellman_comm_init (or bellman_group_init) before running"; return BELLMAN_ERR_STATE; }
     NcclApi *api = nccl_api(h->err);
     if (!api) return BELLMAN_ERR_NCCL;
     const HostProblem &hp = h->hp;
@@ -709,6 +709,7 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
         o = *opts;
     }
     if (h->cur_stage - n_stages < 1) { h->err = "run would pass stage 1"; return BELLMAN_ERR_STATE; }
+    if (h->group_mode && h->nranks > 1) { h->err = "handles of a single-process group run through bellman_group_run"; return BELLMAN_ERR_STATE; }
     const HostProblem &hp = h->hp;
     CUDA_TRY(h, cudaSetDevice(h->device));
     int lanes = 1;
@@ -1138,5 +1139,139 @@ extern "C" int bellman_get_points(bellman_handle *h, int32_t stage, int32_t prob
 #undef GT
     cleanup();
     if (bad) { h->err = "bellman_get_points: a state lies outside this rank's owned range"; return BELLMAN_ERR_BAD_ARG; }
+    return BELLMAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Single-process multi-GPU: ONE host thread drives every slab (SURVEY 8b "one host thread drives all
+// GPUs" — what a MATLAB interpreter calling run(obj) through the MEX gateway needs).  The handles are
+// created with part_dim >= 0, nranks = n, rank = position in the array, device = the GPU of that slab
+// (several slabs may share a GPU).  No NCCL: the slabs' J buffers are in one address space, so the
+// stage kernels store halo values straight into the neighbours' buffers (peer access between devices)
+// and stages are ordered by the same neighbour flags as the multi-process fused mode.
+// ---------------------------------------------------------------------------------------------
+extern "C" int bellman_group_init(bellman_handle **hs, int32_t n) {
+    if (!hs || n < 1) return BELLMAN_ERR_BAD_ARG;
+    for (int r = 0; r < n; ++r) {
+        bellman_handle *h = hs[r];
+        if (!h) return BELLMAN_ERR_BAD_ARG;
+        if (h->nranks != n || h->rank != r || (n > 1 && h->part_dim != hs[0]->part_dim) || h->hp.S() != hs[0]->hp.S() ||
+            h->store_J_all != hs[0]->store_J_all) {
+            h->err = "bellman_group_init: handle r must be rank r of n, all on the same problem and partition dimension";
+            return BELLMAN_ERR_BAD_ARG;
+        }
+        if (n - 1 > MAX_PEERS) { h->err = "too many slabs for the fused halo"; return BELLMAN_ERR_BAD_ARG; }
+    }
+    for (int r = 0; r < n; ++r) {
+        bellman_handle *h = hs[r];
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        h->peer_J.assign(n, nullptr);
+        for (int q = 0; q < n; ++q) {
+            if (q == r) continue;
+            if (hs[q]->device != h->device) {
+                int can = 0;
+                CUDA_TRY(h, cudaDeviceCanAccessPeer(&can, h->device, hs[q]->device));
+                if (!can) { h->err = "no peer access between the devices of the group"; return BELLMAN_ERR_CUDA; }
+                cudaError_t e = cudaDeviceEnablePeerAccess(hs[q]->device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { h->err = cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
+                cudaGetLastError();
+            }
+            h->peer_J[q] = hs[q]->d_J;
+        }
+        h->fused_halo = n > 1;
+        h->group_mode = true;
+    }
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_group_run(bellman_handle **hs, int32_t n, int32_t n_stages, const bellman_run_opts *opts) {
+    if (!hs || n < 1 || n_stages < 0) return BELLMAN_ERR_BAD_ARG;
+    bellman_run_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) {
+        if (opts->struct_size != (int32_t)sizeof(bellman_run_opts)) { hs[0]->err = "bellman_run_opts.struct_size mismatch"; return BELLMAN_ERR_BAD_ARG; }
+        o = *opts;
+    }
+    std::vector<int> kernel(n), lanes(n, 1);
+    for (int r = 0; r < n; ++r) {
+        bellman_handle *h = hs[r];
+        if (!h->group_mode) { h->err = "bellman_group_run needs bellman_group_init first"; return BELLMAN_ERR_STATE; }
+        if (h->cur_stage != hs[0]->cur_stage) { h->err = "the slabs of a group must be at the same stage"; return BELLMAN_ERR_STATE; }
+        if (h->cur_stage - n_stages < 1) { h->err = "run would pass stage 1"; return BELLMAN_ERR_STATE; }
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        kernel[r] = pick_kernel(h, o.kernel, lanes[r]);
+        h->last_kernel = kernel[r] == BELLMAN_KERNEL_WINDOW ? window_variant(h) : kernel[r] == BELLMAN_KERNEL_TILE
+                             ? (stream_valid(h) ? "stream" : "tile") : kernel[r] == BELLMAN_KERNEL_SPLITC ? "splitc" : "direct";
+        h->last_launches = 0;
+        h->last_ms_exchange = 0.0;
+        CUDA_TRY(h, cudaEventRecord(h->ev0, h->stream));
+    }
+    double fsum_prev = hs[0]->check_log.empty() ? 0.0 : hs[0]->check_log[hs[0]->check_log.size() - 2];
+    bool stop = false;
+    for (int s = 0; s < n_stages && !stop; ++s) {
+        // every slab's stage, signal and wait go to its own stream; the host thread never blocks here
+        for (int r = 0; r < n; ++r) {
+            bellman_handle *h = hs[r];
+            CUDA_TRY(h, cudaSetDevice(h->device));
+            int rc = launch_one_stage(h, kernel[r], lanes[r]);
+            if (rc != BELLMAN_OK) return rc;
+            h->cur_stage -= 1;
+            if (n > 1) {
+                h->halo_seq += 1;
+                rc = halo_signal(h);
+                if (rc == BELLMAN_OK) rc = halo_wait(h);
+                if (rc != BELLMAN_OK) return rc;
+            }
+        }
+        const int cur = hs[0]->cur_stage;
+        if (o.check_period > 0 && cur % o.check_period == 0) {
+            double tot[2] = {0.0, 0.0};
+            for (int r = 0; r < n; ++r) {
+                bellman_handle *h = hs[r];
+                CUDA_TRY(h, cudaSetDevice(h->device));
+                StageParams sp = h->sp;
+                sp.J_out = h->J_ptr(cur);
+                sp.idx_out = h->idx_ptr(cur);
+                cudaError_t e = launch_check_sums(sp, h->d_partials, h->n_partials, h->d_sums, h->stream);
+                if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
+            }
+            for (int r = 0; r < n; ++r) {     // slab sums added in rank order (deterministic)
+                bellman_handle *h = hs[r];
+                double sums[2];
+                CUDA_TRY(h, cudaSetDevice(h->device));
+                CUDA_TRY(h, cudaMemcpyAsync(sums, h->d_sums, sizeof(sums), cudaMemcpyDeviceToHost, h->stream));
+                CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+                tot[0] += sums[0];
+                tot[1] += sums[1];
+            }
+            for (int r = 0; r < n; ++r) {
+                hs[r]->check_log.push_back((double)cur);
+                hs[r]->check_log.push_back(tot[0]);
+                hs[r]->check_log.push_back(tot[1]);
+            }
+            if (std::fabs(tot[0] - fsum_prev) < o.check_tol) stop = true;
+            fsum_prev = tot[0];
+        }
+    }
+    double ms_max = 0.0;
+    for (int r = 0; r < n; ++r) {
+        bellman_handle *h = hs[r];
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaEventRecord(h->ev1, h->stream));
+    }
+    for (int r = 0; r < n; ++r) {
+        bellman_handle *h = hs[r];
+        CUDA_TRY(h, cudaSetDevice(h->device));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+        ms_max = std::max(ms_max, (double)ms);
+        if (n > 1) {
+            unsigned int timed_out = 0;
+            CUDA_TRY(h, cudaMemcpy(&timed_out, h->d_flags + 48, sizeof(timed_out), cudaMemcpyDeviceToHost));
+            if (timed_out) { h->err = "halo flag wait timed out: a slab of the group stopped progressing"; return BELLMAN_ERR_NCCL; }
+        }
+    }
+    for (int r = 0; r < n; ++r) hs[r]->last_ms = ms_max;
     return BELLMAN_OK;
 }

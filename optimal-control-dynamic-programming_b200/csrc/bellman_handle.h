@@ -44,6 +44,7 @@ struct bellman_handle {
     ncclComm_t comm = nullptr;
     // fused halo mode: neighbours' J allocations mapped through CUDA IPC (index = rank, own = nullptr)
     bool fused_halo = false;
+    bool group_mode = false;          // slab of a single-process group (bellman_group_init): peers are plain pointers, no NCCL
     std::vector<double *> peer_J;
     double *d_barrier = nullptr;
     uint32_t *d_flags = nullptr;      // tail of the J allocation: flags[q] = stages rank q has completed (fused halo)

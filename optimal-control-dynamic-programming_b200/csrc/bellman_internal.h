@@ -28,6 +28,7 @@ struct HostProblem {
     std::vector<double> lut_invw[MAXD];
     int lut_n[MAXD] = {0, 0, 0, 0};
     std::vector<int32_t> mode;                    // [P][D]
+    std::vector<int32_t> part_cuts;               // explicit slab boundaries (empty: equal slabs)
     int64_t S() const { int64_t s = 1; for (int d = 0; d < D; ++d) s *= n[d]; return s; }
 };
 

@@ -30,6 +30,8 @@ std::string load_problem(const bellman_desc *d, HostProblem &hp) {
     if (d->N < 2) return "N must be >= 2";
     if (!d->r) return "r table is NULL";
     hp.D = d->D; hp.C = d->C; hp.P = d->P; hp.N = d->N;
+    hp.part_cuts.clear();
+    if (d->part_cuts && d->nranks >= 1) hp.part_cuts.assign(d->part_cuts, d->part_cuts + d->nranks + 1);
     for (int k = 0; k < hp.D; ++k) {
         if (d->n[k] < 2) return "every grid needs >= 2 points";
         hp.n[k] = d->n[k];
@@ -171,8 +173,16 @@ std::string plan_slabs(const HostProblem &hp, int part_dim, int nranks, bellman_
     if (nranks < 1) return "nranks must be >= 1";
     const int n = hp.n[part_dim];
     if (nranks > n) return "more ranks than grid points along part_dim";
+    const bool cuts = !hp.part_cuts.empty();
+    if (cuts) {
+        if ((int)hp.part_cuts.size() != nranks + 1 || hp.part_cuts[0] != 0 || hp.part_cuts[nranks] != n)
+            return "part_cuts must hold nranks + 1 boundaries from 0 to n[part_dim]";
+        for (int r = 0; r < nranks; ++r)
+            if (hp.part_cuts[r + 1] <= hp.part_cuts[r]) return "part_cuts must be strictly increasing";
+    }
     for (int r = 0; r < nranks; ++r) {
-        const int lo = (int)((int64_t)n * r / nranks), hi = (int)((int64_t)n * (r + 1) / nranks);
+        const int lo = cuts ? hp.part_cuts[r] : (int)((int64_t)n * r / nranks);
+        const int hi = cuts ? hp.part_cuts[r + 1] : (int)((int64_t)n * (r + 1) / nranks);
         out[r].own_lo = lo;
         out[r].own_hi = hi;
         int elo, ehi;

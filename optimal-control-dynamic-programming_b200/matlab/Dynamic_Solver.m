@@ -51,6 +51,7 @@ classdef Dynamic_Solver < handle
         store_J_star = true
         device = -1
         kernel = 0
+        n_gpus = 1      % > 1: slabs over this many GPUs from this one process (keeps stage 1 only: F, u_star_idx)
         handle_ = uint64(0)
     end
 
@@ -95,6 +96,14 @@ classdef Dynamic_Solver < handle
             if obj.handle_ ~= 0, bellman_mex('destroy', obj.handle_); obj.handle_ = uint64(0); end
             d = obj.build_desc();
             [obj.X1_mesh, obj.X2_mesh] = ndgrid(obj.s_r, obj.s_r);
+            if obj.n_gpus > 1
+                tic
+                [Jv, iv, st] = bellman_sweep_multi(d, obj.N - 1, obj.n_gpus, struct('kernel', obj.kernel));
+                fprintf('%d stages on %d GPUs - %f seconds (device %.3f ms, %s kernel)\n', obj.N - 1, obj.n_gpus, toc, st.ms, st.kernel)
+                obj.u_star_idx = double(reshape(iv, [obj.dx, obj.dx]));
+                obj.F = struct('GridVectors', {{obj.s_r, obj.s_r}}, 'Values', reshape(Jv, [obj.dx, obj.dx]));
+                return
+            end
             obj.handle_ = bellman_mex('create', d);
             tic
             bellman_mex('run', obj.handle_, obj.N - 1, struct('kernel', obj.kernel));

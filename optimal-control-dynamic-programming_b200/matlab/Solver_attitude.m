@@ -43,6 +43,7 @@ classdef Solver_attitude < handle
         F_Values
         U_idx
         device = -1
+        n_gpus = 1      % > 1: the grid is cut into slabs over this many GPUs, driven from this one process
     end
 
     methods
@@ -88,14 +89,19 @@ classdef Solver_attitude < handle
             d.q  = {(s_w.^2)*Qw, qt};
             d.r  = (U.^2)*R;
             d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
-            hnd = bellman_mex('create', d);
-            tic
-            bellman_mex('run', hnd, n_stages, struct());
-            fprintf('%d stages - %f seconds\n', n_stages, toc)
             sz = [obj.n_mesh_w, obj.n_mesh_t, 3];
-            obj.F_Values = reshape(bellman_mex('get_J', hnd), sz);
-            obj.U_idx = double(reshape(bellman_mex('get_idx', hnd), sz));
-            bellman_mex('destroy', hnd);
+            tic
+            if obj.n_gpus > 1
+                [Jv, iv] = bellman_sweep_multi(d, n_stages, obj.n_gpus, struct());
+                obj.F_Values = reshape(Jv, sz);  obj.U_idx = double(reshape(iv, sz));
+            else
+                hnd = bellman_mex('create', d);
+                bellman_mex('run', hnd, n_stages, struct());
+                obj.F_Values = reshape(bellman_mex('get_J', hnd), sz);
+                obj.U_idx = double(reshape(bellman_mex('get_idx', hnd), sz));
+                bellman_mex('destroy', hnd);
+            end
+            fprintf('%d stages - %f seconds\n', n_stages, toc)
             obj.U1_Opt = griddedInterpolant({s_w.', s_t(:,1).'}, obj.U_vector(obj.U_idx(:,:,1)), 'nearest');
             obj.U2_Opt = griddedInterpolant({s_w.', s_t(:,2).'}, obj.U_vector(obj.U_idx(:,:,2)), 'nearest');
             obj.U3_Opt = griddedInterpolant({s_w.', s_t(:,3).'}, obj.U_vector(obj.U_idx(:,:,3)), 'nearest');

@@ -36,6 +36,7 @@ classdef Solver_position < handle
         F_Values        % J at the last computed stage, n_x x n_v x 3
         U_idx           % argmin (1-based), n_x x n_v x 3
         device = -1
+        n_gpus = 1      % > 1: the grid is cut into slabs over this many GPUs, driven from this one process
     end
 
     methods
@@ -76,14 +77,19 @@ classdef Solver_position < handle
             d.q  = {(s_x.^2)*Qx, (s_v.^2)*Qv};       % column a = Q_a * s.^2 (one product per element)
             d.r  = (U.^2)*R;
             d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
-            hnd = bellman_mex('create', d);
-            tic
-            bellman_mex('run', hnd, n_stages, struct('use_graph', 1));
-            fprintf('%d stages - %f seconds\n', n_stages, toc)
             sz = [numel(s_x), numel(s_v), 3];
-            obj.F_Values = reshape(bellman_mex('get_J', hnd), sz);
-            obj.U_idx = double(reshape(bellman_mex('get_idx', hnd), sz));
-            bellman_mex('destroy', hnd);
+            tic
+            if obj.n_gpus > 1
+                [Jv, iv] = bellman_sweep_multi(d, n_stages, obj.n_gpus, struct());
+                obj.F_Values = reshape(Jv, sz);  obj.U_idx = double(reshape(iv, sz));
+            else
+                hnd = bellman_mex('create', d);
+                bellman_mex('run', hnd, n_stages, struct('use_graph', 1));
+                obj.F_Values = reshape(bellman_mex('get_J', hnd), sz);
+                obj.U_idx = double(reshape(bellman_mex('get_idx', hnd), sz));
+                bellman_mex('destroy', hnd);
+            end
+            fprintf('%d stages - %f seconds\n', n_stages, toc)
             obj.U1_Opt = griddedInterpolant({s_x.', s_v.'}, obj.U_vector(obj.U_idx(:,:,1)), 'nearest');
             obj.U2_Opt = griddedInterpolant({s_x.', s_v.'}, obj.U_vector(obj.U_idx(:,:,2)), 'nearest');
             obj.U3_Opt = griddedInterpolant({s_x.', s_v.'}, obj.U_vector(obj.U_idx(:,:,3)), 'nearest');

@@ -11,6 +11,10 @@
 //   s      = bellman_mex('stats', h)                  struct: ms, launches, ms_exchange, kernel
 //   [X,U]  = bellman_mex('rollout', h, N, A, B, u_values, X0, mode, ssu_stage)   X0: 2 x batch,
 //                                                     X: 2 x (N*batch), U: N x batch
+//   pd     = bellman_mex('plan', desc, n)             slab dimension (1-based) with the smallest halo for n slabs
+//   r      = bellman_mex('owned_range', h)            [own_lo own_hi) along the slab dimension, 0-based
+//            bellman_mex('group_init', hs)            hs: uint64 vector of handles = slabs 1..n of ONE problem
+//            bellman_mex('group_run', hs, n_stages, opts)   all slabs together, from this one host thread
 //            bellman_mex('destroy', h)
 //   v      = bellman_mex('version')
 //
@@ -80,10 +84,8 @@ static const double *cell_table(const mxArray *s, const char *name, int d, size_
     return mxGetPr(e);
 }
 
-static void cmd_create(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
-    if (nrhs != 2 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: h = bellman_mex('create', desc)");
-    const mxArray *s = prhs[1];
-    bellman_desc d;
+// desc struct -> bellman_desc (pointers into the MATLAB arrays: valid for the duration of the call)
+static void fill_desc(const mxArray *s, bellman_desc &d) {
     std::memset(&d, 0, sizeof(d));
     d.struct_size = (int32_t)sizeof(d);
     const mxArray *nn = mxGetField(s, 0, "n");
@@ -120,6 +122,12 @@ static void cmd_create(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[
     d.part_dim = (int32_t)field_scalar(s, "part_dim", 0) - 1;
     d.rank = (int32_t)field_scalar(s, "rank", 0);
     d.nranks = (int32_t)field_scalar(s, "nranks", 1);
+}
+
+static void cmd_create(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
+    if (nrhs != 2 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: h = bellman_mex('create', desc)");
+    bellman_desc d;
+    fill_desc(prhs[1], d);
     bellman_handle *h = nullptr;
     check(bellman_create(&d, &h), nullptr);
     if (g_live.empty()) { mexLock(); mexAtExit(at_exit); }
@@ -155,6 +163,54 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
     mxFree(c);
 
     if (cmd == "version") { plhs[0] = mxCreateDoubleScalar(bellman_version()); return; }
+    if (cmd == "plan") {
+        // pd = bellman_mex('plan', desc, n): the dimension whose slabs need the smallest halo (host-only)
+        if (nrhs != 3 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: pd = bellman_mex('plan', desc, n)");
+        bellman_desc d;
+        fill_desc(prhs[1], d);
+        const int n = (int)mxGetScalar(prhs[2]);
+        if (n < 1 || n > 64) mexErrMsgIdAndTxt("bellman:BAD_ARG", "n must be 1..64");
+        std::vector<bellman_slab> sl((size_t)n);
+        int best = -1;
+        double best_cost = 0.0;
+        for (int pd = 0; pd < d.D; ++pd) {
+            if (bellman_plan_slabs(&d, pd, n, sl.data()) != BELLMAN_OK) continue;
+            double cost = 0.0;
+            for (const bellman_slab &m : sl) {
+                const double c = (double)((m.ext_hi - m.ext_lo) - (m.own_hi - m.own_lo)) / (double)(m.own_hi - m.own_lo);
+                if (c > cost) cost = c;
+            }
+            if (best < 0 || cost < best_cost - 1e-9) { best = pd; best_cost = cost; }
+        }
+        if (best < 0) mexErrMsgIdAndTxt("bellman:BAD_ARG", "no dimension can be cut into %d slabs", n);
+        plhs[0] = mxCreateDoubleScalar(best + 1);
+        return;
+    }
+    if (cmd == "group_init" || cmd == "group_run") {
+        if (nrhs < 2 || !mxIsClass(prhs[1], "uint64")) mexErrMsgIdAndTxt("bellman:BAD_ARG", "hs must be a uint64 vector of handles");
+        const size_t n = mxGetNumberOfElements(prhs[1]);
+        std::vector<bellman_handle *> hs(n);
+        for (size_t k = 0; k < n; ++k) {
+            hs[k] = reinterpret_cast<bellman_handle *>(static_cast<uint64_t *>(mxGetData(prhs[1]))[k]);
+            if (!g_live.count(hs[k])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "stale or foreign handle");
+        }
+        if (cmd == "group_init") { check(bellman_group_init(hs.data(), (int32_t)n), hs[0]); return; }
+        if (nrhs < 3) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: bellman_mex('group_run', hs, n_stages, opts)");
+        bellman_run_opts o;
+        std::memset(&o, 0, sizeof(o));
+        o.struct_size = (int32_t)sizeof(o);
+        if (nrhs > 3 && mxIsStruct(prhs[3])) {
+            o.kernel = (int32_t)field_scalar(prhs[3], "kernel", 0);
+            o.check_period = (int32_t)field_scalar(prhs[3], "check_period", 0);
+            o.check_tol = field_scalar(prhs[3], "check_tol", 0.0);
+        }
+        const int rc = bellman_group_run(hs.data(), (int32_t)n, (int32_t)mxGetScalar(prhs[2]), &o);
+        if (rc != BELLMAN_OK)
+            for (bellman_handle *h : hs)
+                if (bellman_last_error(h)[0]) check(rc, h);
+        check(rc, hs[0]);
+        return;
+    }
     if (cmd == "create") {
         cmd_create(nlhs, plhs, nrhs, prhs);
         bellman_handle *h = reinterpret_cast<bellman_handle *>(*static_cast<uint64_t *>(mxGetData(plhs[0])));
@@ -201,6 +257,12 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         check(bellman_run(h, (int32_t)mxGetScalar(prhs[2]), &o), h);
     } else if (cmd == "stage") {
         check(bellman_stage(h), h);
+    } else if (cmd == "owned_range") {
+        bellman_slab sl;
+        check(bellman_owned_range(h, &sl), h);
+        plhs[0] = mxCreateDoubleMatrix(1, 2, mxREAL);
+        mxGetPr(plhs[0])[0] = sl.own_lo;
+        mxGetPr(plhs[0])[1] = sl.own_hi;
     } else if (cmd == "current_stage") {
         plhs[0] = mxCreateDoubleScalar(bellman_current_stage(h));
     } else if (cmd == "get_J") {

@@ -19,6 +19,7 @@ Deviations from the shipped reference (all documented in SURVEY.md 2.3):
 import numpy as np
 
 from . import tables
+from ._lib import SweepGroup  # noqa: E402
 from ._lib import KERNEL_AUTO, Sweep
 
 
@@ -166,6 +167,8 @@ class _AxisSolverBase:
     device = -1
     kernel = KERNEL_AUTO
     use_graph = True
+    n_gpus = 1          # > 1: the grid is cut into slabs over this many GPUs, driven from this one process
+    devices = None      # GPU of every slab (default 0 .. n_gpus-1)
 
     def _axis_descs(self):
         raise NotImplementedError
@@ -174,11 +177,22 @@ class _AxisSolverBase:
         descs = self._axis_descs()
         d = tables.stack_problems(descs)
         self._desc = d
-        sw = self._sweep = Sweep(d, device=self.device)
         todo = d.N - 1 if n_stages is None else int(n_stages)
-        sw.run(todo, kernel=self.kernel, use_graph=self.use_graph)
-        J = sw.get_J()
-        idx = sw.get_idx()
+        if self.n_gpus > 1:
+            # one host thread, n slabs (bellman_group_run); the kept policy is then gathered into an
+            # unsharded handle so that lookups and rollouts work exactly as after a one-GPU sweep
+            grp = SweepGroup(d, self.devices or list(range(self.n_gpus)))
+            grp.run(todo, kernel=self.kernel)
+            J, idx, stage, stats = grp.get_J(), grp.get_idx(), grp.current_stage, grp.stats()
+            grp.close()
+            sw = self._sweep = Sweep(d, device=self.device)
+            sw.set_stage(stage, J, idx)
+        else:
+            sw = self._sweep = Sweep(d, device=self.device)
+            sw.run(todo, kernel=self.kernel, use_graph=self.use_graph)
+            J = sw.get_J()
+            idx = sw.get_idx()
+            stats = sw.stats()
         shape = tuple(d.n)
         self.F_Values = [_unflatten(J[p], shape) for p in range(d.P)]
         self.U_idx = [_unflatten(idx[p], shape) + 1 for p in range(d.P)]
@@ -187,7 +201,7 @@ class _AxisSolverBase:
             grids = [d.grid[k][p] for k in range(d.D)]
             pol.append(NearestPolicy(grids, np.asarray(self.U_vector)[self.U_idx[p] - 1]))
         self.U1_Opt, self.U2_Opt, self.U3_Opt = pol
-        self.sweep_stats = sw.stats()
+        self.sweep_stats = stats
         return self
 
     def get_optimal_path_simplified(self, X0, n_steps=None):
