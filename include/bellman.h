@@ -135,6 +135,11 @@ typedef struct bellman_desc {
        part_cuts[0] = 0, part_cuts[nranks] = n[part_dim], strictly increasing; NULL = equal slabs.  Lets
        the host balance slabs whose cost per index differs (e.g. from per-rank times of a trial run). */
     const int32_t *part_cuts;
+    /* bytes per stored argmin on the device: 0 or 4 = int32 (default), 2 = uint16 (C <= 65536),
+       1 = uint8 (C <= 256).  Only the device storage changes (store_idx_all on the 8192^2 x 512 grid:
+       53 GB as int32, 13 GB as uint8; 17 instead of 20 bytes of traffic per state and stage); every
+       entry point still takes and returns 0-based int32 indices. */
+    int32_t idx_bytes;
 } bellman_desc;
 
 typedef struct bellman_run_opts {

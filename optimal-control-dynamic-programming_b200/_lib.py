@@ -35,7 +35,7 @@ class CDesc(C.Structure):
         ("q_order", C.c_int32 * MAXD), ("q", _dp * MAXD), ("r", _dp),
         ("store_J_all", C.c_int32), ("store_idx_all", C.c_int32), ("device", C.c_int32),
         ("part_dim", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-        ("part_cuts", C.POINTER(C.c_int32)),
+        ("part_cuts", C.POINTER(C.c_int32)), ("idx_bytes", C.c_int32),
     ]
 
 
@@ -114,7 +114,7 @@ def _f64(a):
     return np.ascontiguousarray(a, dtype=np.float64)
 
 
-def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None):
+def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None, idx_bytes=0):
     """tables.Desc -> (CDesc, keepalive)."""
     cd = CDesc()
     keep = []
@@ -140,6 +140,7 @@ def to_cdesc(d, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None):
     cd.store_J_all = int(bool(d.store_J_all))
     cd.store_idx_all = int(bool(d.store_idx_all))
     cd.device, cd.part_dim, cd.rank, cd.nranks = int(device), int(part_dim), int(rank), int(nranks)
+    cd.idx_bytes = int(idx_bytes or getattr(d, "idx_bytes", 0) or 0)
     if part_cuts is not None:
         pc = np.ascontiguousarray(part_cuts, dtype=np.int32)
         assert len(pc) == nranks + 1
@@ -194,10 +195,12 @@ def get_unique_id():
 class Sweep:
     """One ``bellman_handle``: device-resident tables + J/idx storage for a (batched) problem."""
 
-    def __init__(self, desc, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None):
+    def __init__(self, desc, device=-1, part_dim=-1, rank=0, nranks=1, part_cuts=None, idx_bytes=0):
+        """idx_bytes: device storage of the argmin (0 / 4 = int32, 2 = uint16, 1 = uint8); every call
+        still takes and returns int32 indices."""
         self.lib = load()
         self.desc = desc
-        cd, keep = to_cdesc(desc, device, part_dim, rank, nranks, part_cuts)
+        cd, keep = to_cdesc(desc, device, part_dim, rank, nranks, part_cuts, idx_bytes)
         h = C.c_void_p()
         rc = self.lib.bellman_create(C.byref(cd), C.byref(h))
         if rc != 0:
@@ -379,7 +382,7 @@ class SweepGroup:
     (bellman_group_init / bellman_group_run).  ``devices`` lists the GPU of every slab; several slabs
     may share a GPU (``devices=[0, 0]`` exercises the sharded path on a single-GPU box)."""
 
-    def __init__(self, desc, devices, part_dim=None, part_cuts=None):
+    def __init__(self, desc, devices, part_dim=None, part_cuts=None, idx_bytes=0):
         self.desc = desc
         n = len(devices)
         if part_dim is None:           # the dimension with the smallest halo, from the host-side reach analysis
@@ -394,7 +397,7 @@ class SweepGroup:
                     best = (cost, pd)
             part_dim = best[1]
         self.part_dim = part_dim
-        self.slabs = [Sweep(desc, device=dev, part_dim=part_dim, rank=r, nranks=n, part_cuts=part_cuts)
+        self.slabs = [Sweep(desc, device=dev, part_dim=part_dim, rank=r, nranks=n, part_cuts=part_cuts, idx_bytes=idx_bytes)
                       for r, dev in enumerate(devices)]
         self.lib = self.slabs[0].lib
         self._arr = (C.c_void_p * n)(*[s.h for s in self.slabs])

@@ -124,6 +124,7 @@ static int upload_tables(bellman_handle *h) {
     StageParams &sp = h->sp;
     std::memset(&sp, 0, sizeof(sp));
     sp.D = D; sp.C = hp.C; sp.P = P;
+    sp.idx_bytes = hp.idx_bytes;
     sp.S_ext = h->S_ext; sp.S_own = h->S_own;
     for (int d = 0; d < D; ++d) {
         DimParams &dp = sp.dim[d];
@@ -228,8 +229,8 @@ extern "C" int bellman_create(const bellman_desc *d, bellman_handle **out) {
     TRY_RC(cu(cudaMalloc(&h->d_J, nJ * sizeof(double) + 256), "cudaMalloc(J)"));
     TRY_RC(cu(cudaMemsetAsync(h->d_J + nJ, 0, 256, h->stream), "cudaMemset(flags)"));
     h->d_flags = reinterpret_cast<uint32_t *>(h->d_J + nJ);
-    TRY_RC(cu(cudaMalloc(&h->d_idx, nI * sizeof(int32_t)), "cudaMalloc(idx)"));
-    TRY_RC(cu(cudaMemsetAsync(h->d_idx, 0, nI * sizeof(int32_t), h->stream), "cudaMemset(idx)"));
+    TRY_RC(cu(cudaMalloc(&h->d_idx, nI * (size_t)hp.idx_bytes), "cudaMalloc(idx)"));
+    TRY_RC(cu(cudaMemsetAsync(h->d_idx, 0, nI * (size_t)hp.idx_bytes, h->stream), "cudaMemset(idx)"));
     h->n_partials = 592;
     TRY_RC(cu(cudaMalloc(&h->d_partials, 2 * h->n_partials * sizeof(double)), "cudaMalloc"));
     TRY_RC(cu(cudaMalloc(&h->d_sums, 2 * sizeof(double)), "cudaMalloc"));
@@ -347,9 +348,20 @@ extern "C" int bellman_set_stage(bellman_handle *h, int32_t stage, const double 
     h->check_log.clear();
     int rc = upload_J(h, stage, J_host);
     if (rc != BELLMAN_OK) return rc;
-    if (idx_host)
-        CUDA_TRY(h, cudaMemcpyAsync(h->idx_ptr(stage), idx_host, h->slot_elems_idx() * sizeof(int32_t),
-                                    cudaMemcpyHostToDevice, h->stream));
+    std::vector<unsigned char> narrow;
+    if (idx_host) {
+        const size_t ne = h->slot_elems_idx();
+        const void *src = idx_host;
+        if (hp.idx_bytes != 4) {           // the device stores 1 or 2 bytes per index
+            narrow.resize(ne * (size_t)hp.idx_bytes);
+            for (size_t k = 0; k < ne; ++k) {
+                if (idx_host[k] < 0 || idx_host[k] >= hp.C) { h->err = "bellman_set_stage: control index out of range"; return BELLMAN_ERR_BAD_ARG; }
+                idx_store(narrow.data(), hp.idx_bytes, (long long)k, idx_host[k]);
+            }
+            src = narrow.data();
+        }
+        CUDA_TRY(h, cudaMemcpyAsync(h->idx_ptr(stage), src, ne * (size_t)hp.idx_bytes, cudaMemcpyHostToDevice, h->stream));
+    }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->J_set = true;
     return BELLMAN_OK;
@@ -393,9 +405,14 @@ extern "C" int bellman_get_idx(bellman_handle *h, int32_t stage, int32_t *out) {
     if (!h || !out) return BELLMAN_ERR_BAD_ARG;
     int rc = stage_available(h, stage, h->store_idx_all, true);
     if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
-    CUDA_TRY(h, cudaMemcpyAsync(out, h->idx_ptr(stage), h->slot_elems_idx() * sizeof(int32_t),
-                                cudaMemcpyDeviceToHost, h->stream));
+    const size_t ne = h->slot_elems_idx();
+    const int ib = h->hp.idx_bytes;
+    // narrow storage lands in the tail of the caller's int32 buffer and is widened in place, front to back
+    unsigned char *raw = reinterpret_cast<unsigned char *>(out) + ne * (size_t)(4 - ib);
+    CUDA_TRY(h, cudaMemcpyAsync(raw, h->idx_ptr(stage), ne * (size_t)ib, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (ib != 4)
+        for (size_t k = 0; k < ne; ++k) out[k] = idx_load(raw, ib, (long long)k);
     return BELLMAN_OK;
 }
 
@@ -910,7 +927,7 @@ extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double 
     rp.mode0 = hp.mode[0]; rp.mode1 = hp.mode[1];
     rp.n0 = hp.n[0]; rp.n1 = hp.n[1]; rp.N = N; rp.C = hp.C; rp.batch = batch;
     rp.mode = mode; rp.ssu_stage = ssu_stage;
-    rp.idx_all = h->d_idx; rp.u_values = d_u;
+    rp.idx_all = h->d_idx; rp.idx_bytes = hp.idx_bytes; rp.u_values = d_u;
     for (int i = 0; i < 4; ++i) rp.A[i] = A[i];
     rp.B[0] = B[0]; rp.B[1] = B[1];
     rp.x0 = d_x0; rp.X_out = d_X; rp.U_out = d_U;
@@ -944,6 +961,7 @@ static int fill_policy_params(bellman_handle *h, int prob, PolicyParams &pp) {
         pp.n[d] = hp.n[d];
         pp.lut_n[d] = hp.lut_n[d];
     }
+    pp.idx_bytes = hp.idx_bytes;
     return BELLMAN_OK;
 }
 
@@ -965,7 +983,7 @@ extern "C" int bellman_policy_lookup(bellman_handle *h, int32_t prob, int32_t st
     PT(cudaMalloc(&d_o, sizeof(int32_t) * (size_t)batch));
     PT(cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)hp.D * batch, cudaMemcpyHostToDevice, h->stream));
     pp.batch = batch;
-    pp.idx = h->idx_ptr(stage) + (size_t)prob * h->S_own;
+    pp.idx = h->idx_ptr(stage, prob);
     pp.x = d_x;
     pp.idx_out = d_o;
     PT(launch_policy_lookup(pp, h->stream));
@@ -1005,7 +1023,7 @@ extern "C" int bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t tim
     pp.batch = batch;
     pp.time_varying = time_varying; pp.stage = stage; pp.rate_dim = rate_dim; pp.n_steps = n_steps;
     pp.h_step = h_step;
-    pp.idx = (time_varying ? h->d_idx : h->idx_ptr(stage)) + (size_t)prob * h->S_own;
+    pp.idx = time_varying ? h->idx_ptr(1, prob) : h->idx_ptr(stage, prob);    // time varying: slot 0 = stage 1 (store_idx_all)
     pp.idx_stage_stride = (long long)h->slot_elems_idx();
     pp.u_inc = d_u; pp.x = d_x; pp.X_out = d_X; pp.idx_out = d_c;
     PT(launch_rollout_axis(pp, h->stream));
@@ -1032,7 +1050,7 @@ extern "C" int bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bel
     for (int p = 0; p < 3; ++p) {
         rc = fill_policy_params(h, p, op.pol[p]);
         if (rc != BELLMAN_OK) return rc;
-        op.pol[p].idx = h->idx_ptr(stage) + (size_t)p * h->S_own;
+        op.pol[p].idx = h->idx_ptr(stage, p);
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int n_out = o->n_steps / o->stride_out;
@@ -1068,7 +1086,8 @@ extern "C" int bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bel
 // ---------------------------------------------------------------------------------------------
 struct PointArgs {
     const double *J;          // stage slot, problem applied
-    const int32_t *idx;       // stage slot, problem applied (nullptr: skip)
+    const int32_t *idx;       // stage slot, problem applied (nullptr: skip); idx_bytes per element
+    int idx_bytes;
     const long long *states;  // global linear indices (dimension 0 fastest)
     long long n;
     int D;
@@ -1095,7 +1114,7 @@ __global__ void k_get_points(const PointArgs a) {
     ok = ok && s == 0;
     if (!ok) { *a.bad = 1; return; }
     a.J_out[m] = a.J[jo];
-    if (a.idx) a.idx_out[m] = a.idx[io];
+    if (a.idx) a.idx_out[m] = idx_load(a.idx, a.idx_bytes, io);
 }
 
 extern "C" int bellman_get_points(bellman_handle *h, int32_t stage, int32_t prob, const int64_t *states, int64_t n,
@@ -1122,7 +1141,8 @@ extern "C" int bellman_get_points(bellman_handle *h, int32_t stage, int32_t prob
     PointArgs a;
     std::memset(&a, 0, sizeof(a));
     a.J = h->J_ptr(stage) + (size_t)prob * h->S_ext;
-    a.idx = idx_out ? h->idx_ptr(stage) + (size_t)prob * h->S_own : nullptr;
+    a.idx = idx_out ? h->idx_ptr(stage, prob) : nullptr;
+    a.idx_bytes = hp.idx_bytes;
     a.states = d_s; a.n = n; a.D = hp.D;
     for (int d = 0; d < hp.D; ++d) {
         a.ng[d] = hp.n[d]; a.own_lo[d] = h->own_lo[d]; a.own_n[d] = h->own_n[d]; a.ext_lo[d] = h->ext_lo[d];

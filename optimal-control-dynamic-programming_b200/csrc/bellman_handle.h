@@ -70,7 +70,11 @@ struct bellman_handle {
     int J_slot(int stage) const { return store_J_all ? stage - 1 : ((hp.N - stage) & 1); }
     int idx_slot(int stage) const { return store_idx_all ? stage - 1 : 0; }
     double *J_ptr(int stage) const { return d_J + (size_t)J_slot(stage) * slot_elems_J(); }
-    int32_t *idx_ptr(int stage) const { return d_idx + (size_t)idx_slot(stage) * slot_elems_idx(); }
+    // idx storage is idx_bytes per element (hp.idx_bytes); pointers stay typed int32_t*, offsets are in elements
+    int32_t *idx_ptr(int stage, int prob = 0) const {
+        return reinterpret_cast<int32_t *>(reinterpret_cast<char *>(d_idx) +
+                                           ((size_t)idx_slot(stage) * slot_elems_idx() + (size_t)prob * (size_t)S_own) * (size_t)hp.idx_bytes);
+    }
 };
 
 

@@ -29,6 +29,7 @@ struct HostProblem {
     int lut_n[MAXD] = {0, 0, 0, 0};
     std::vector<int32_t> mode;                    // [P][D]
     std::vector<int32_t> part_cuts;               // explicit slab boundaries (empty: equal slabs)
+    int idx_bytes = 4;                            // device storage of the argmin
     int64_t S() const { int64_t s = 1; for (int d = 0; d < D; ++d) s *= n[d]; return s; }
 };
 
@@ -88,8 +89,26 @@ struct StageParams {
     int D, C, P;
     int q_order[MAXD];
     int n_peers, part_dim;
+    int idx_bytes;            // bytes per stored argmin: 4 (int32), 2 (uint16) or 1 (uint8); idx_out is typed int32_t* regardless
     PeerHalo peer[MAX_PEERS];
 };
+
+// argmin storage of 1 / 2 / 4 bytes behind one element-indexed interface (o = element offset)
+#ifdef __CUDACC__
+#define BELLMAN_HD __host__ __device__ __forceinline__
+#else
+#define BELLMAN_HD inline
+#endif
+BELLMAN_HD void idx_store(void *base, int bytes, long long o, int v) {
+    if (bytes == 4) static_cast<int32_t *>(base)[o] = v;
+    else if (bytes == 1) static_cast<unsigned char *>(base)[o] = (unsigned char)v;
+    else static_cast<unsigned short *>(base)[o] = (unsigned short)v;
+}
+BELLMAN_HD int idx_load(const void *base, int bytes, long long o) {
+    if (bytes == 4) return static_cast<const int32_t *>(base)[o];
+    if (bytes == 1) return static_cast<const unsigned char *>(base)[o];
+    return static_cast<const unsigned short *>(base)[o];
+}
 
 #ifdef __CUDACC__
 // store `v` (the new J of global state gi) into every neighbour whose halo covers it

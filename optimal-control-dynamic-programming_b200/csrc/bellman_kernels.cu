@@ -217,7 +217,7 @@ k_stage_direct(const __grid_constant__ StageParams sp) {
         if (tot < best) { best = tot; arg = c; }
     }
     sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
-    sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
+    idx_store(sp.idx_out, sp.idx_bytes, (long long)prob * sp.S_own + s, arg);
     if (sp.n_peers) peer_store<D>(sp, prob, gi, best);
 }
 
@@ -261,7 +261,7 @@ k_stage_splitc(const __grid_constant__ StageParams sp) {
     if (arg == 0x7fffffff) arg = 0;
     if (live && lane == 0) {
         sp.J_out[(size_t)prob * sp.S_ext + o_self] = best;
-        sp.idx_out[(size_t)prob * sp.S_own + s] = arg;
+        idx_store(sp.idx_out, sp.idx_bytes, (long long)prob * sp.S_own + s, arg);
         if (sp.n_peers) peer_store<D>(sp, prob, gi, best);
     }
 }
@@ -324,7 +324,7 @@ k_sweep_persistent(const __grid_constant__ StageParams sp, const __grid_constant
         const int js_to = pp.store_J_all ? to - 1 : ((pp.N - to) & 1);
         const double *__restrict__ Jn = pp.J_base + (size_t)js_from * pp.J_slot_elems + (size_t)prob * sp.S_ext;
         double *Jo = pp.J_base + (size_t)js_to * pp.J_slot_elems + (size_t)prob * sp.S_ext;
-        int32_t *Io = pp.idx_base + (size_t)(pp.store_idx_all ? to - 1 : 0) * pp.idx_slot_elems + (size_t)prob * sp.S_own;
+        const long long Io = (long long)(pp.store_idx_all ? to - 1 : 0) * pp.idx_slot_elems + (long long)prob * sp.S_own;
 
         double best = __longlong_as_double(0x7ff0000000000000LL);
         int arg = 0x7fffffff;
@@ -341,7 +341,7 @@ k_sweep_persistent(const __grid_constant__ StageParams sp, const __grid_constant
         if (arg == 0x7fffffff) arg = 0;   // all totals +inf / NaN: first index (see k_stage_splitc)
         if (live && lane == 0) {
             Jo[o_self] = best;
-            Io[s] = arg;
+            idx_store(pp.idx_base, sp.idx_bytes, Io + s, arg);
         }
         if (it + 1 < pp.n_stages) grid_barrier(pp.barrier, (unsigned int)(it + 1) * gridDim.x);
     }
@@ -364,7 +364,7 @@ k_check_partials(const __grid_constant__ StageParams sp, double *__restrict__ pa
         int gi[D];
         const long long o = decompose<D>(sp, s, gi);
         sj += sp.J_out[(size_t)prob * sp.S_ext + o];
-        si += (double)(sp.idx_out[(size_t)prob * sp.S_own + s] + 1);
+        si += (double)(idx_load(sp.idx_out, sp.idx_bytes, (long long)prob * sp.S_own + s) + 1);
     }
 #pragma unroll
     for (int w = 16; w >= 1; w >>= 1) {
@@ -404,7 +404,7 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
     X[1] = x2;
     for (int k = 1; k <= rp.N - 1; ++k) {
         const int st = rp.mode == 1 ? rp.ssu_stage : k;
-        const int32_t *__restrict__ id = rp.idx_all + (size_t)(st - 1) * S;
+        const long long ib = (long long)(st - 1) * S;      // element offset of the stage's policy
         double t0, t1;
         // a free state is brought to kernel units first (include/bellman.h, bellman_rollout)
         const int c0 = locate(rp.grid0, rp.rinv0, rp.n0, rp.mode0, rp.lut0, rp.lut_n0, rp.lut_invw0,
@@ -412,8 +412,9 @@ __global__ void __launch_bounds__(128) k_rollout(const __grid_constant__ Rollout
         const int c1 = locate(rp.grid1, rp.rinv1, rp.n1, rp.mode1, rp.lut1, rp.lut_n1, rp.lut_invw1,
                               rp.mode1 == BELLMAN_LOCATE_UNIFORM ? fma(x2, rp.inv_h1, rp.off1) : x2, t1);
         const long long o = c0 + (long long)c1 * rp.n0;
-        const double v00 = rp.u_values[id[o]], v10 = rp.u_values[id[o + 1]];
-        const double v01 = rp.u_values[id[o + rp.n0]], v11 = rp.u_values[id[o + rp.n0 + 1]];
+        auto uat = [&](long long e) { return rp.u_values[idx_load(rp.idx_all, rp.idx_bytes, ib + e)]; };
+        const double v00 = uat(o), v10 = uat(o + 1);
+        const double v01 = uat(o + rp.n0), v11 = uat(o + rp.n0 + 1);
         const double a = fma(t0, v10 - v00, v00), bb = fma(t0, v11 - v01, v01);
         const double u = fma(t1, bb - a, a);
         U[k - 1] = u;
@@ -438,13 +439,14 @@ __device__ __forceinline__ int nearest_node(const PolicyParams &pp, int d, doubl
     return cell + ((x - lo) >= (hi - x) ? 1 : 0);      // exact midpoint -> upper node
 }
 
-__device__ __forceinline__ int policy_at(const PolicyParams &pp, const int32_t *idx, const double *x) {
+// `ibase` = element offset of the policy inside pp.idx (0, or the stage offset when time varying)
+__device__ __forceinline__ int policy_at(const PolicyParams &pp, long long ibase, const double *x) {
     long long o = 0, st = 1;
     for (int d = 0; d < pp.D; ++d) {
         o += (long long)nearest_node(pp, d, x[d]) * st;
         st *= pp.n[d];
     }
-    return idx[o];
+    return idx_load(pp.idx, pp.idx_bytes, ibase + o);
 }
 
 __global__ void __launch_bounds__(128) k_policy_lookup(const __grid_constant__ PolicyParams pp) {
@@ -452,7 +454,7 @@ __global__ void __launch_bounds__(128) k_policy_lookup(const __grid_constant__ P
     if (b >= pp.batch) return;
     double x[MAXD];
     for (int d = 0; d < pp.D; ++d) x[d] = pp.x[(size_t)b * pp.D + d];
-    pp.idx_out[b] = policy_at(pp, pp.idx, x);
+    pp.idx_out[b] = policy_at(pp, 0, x);
 }
 
 __global__ void __launch_bounds__(128) k_rollout_axis(const __grid_constant__ PolicyParams pp) {
@@ -466,8 +468,7 @@ __global__ void __launch_bounds__(128) k_rollout_axis(const __grid_constant__ Po
     X[0] = x[0];
     X[1] = x[1];
     for (int k = 1; k <= pp.n_steps; ++k) {
-        const int32_t *idx = pp.idx + (pp.time_varying ? (size_t)(k - 1) * pp.idx_stage_stride : 0);
-        const int c = policy_at(pp, idx, x);
+        const int c = policy_at(pp, pp.time_varying ? (long long)(k - 1) * pp.idx_stage_stride : 0, x);
         Cc[k - 1] = c;
         const double k1 = x[r];
         const double k2 = x[r] + (k1 * h) / 2;
@@ -594,7 +595,7 @@ __global__ void __launch_bounds__(64) k_rollout_orbit(const __grid_constant__ Or
 #pragma unroll
         for (int p = 0; p < 3; ++p) {       // a_x = U1_Opt(x1, v1) ... (:215-217)
             const double xq[2] = {y[p], y[3 + p]};
-            ci[p] = policy_at(op.pol[p], op.pol[p].idx, xq);
+            ci[p] = policy_at(op.pol[p], 0, xq);
             acc[p] = op.u_values[ci[p]];
         }
         if ((ks - 1) % op.stride_out == 0) {

@@ -42,7 +42,8 @@ struct RolloutParams {
     int lut_n0, lut_n1;
     double lut_invw0, lut_invw1;
     int mode0, mode1, n0, n1, N, C, batch, mode, ssu_stage;
-    const int32_t *idx_all;   // [N][S]
+    const int32_t *idx_all;   // [N][S], idx_bytes per element
+    int idx_bytes;
     const double *u_values;   // [C]
     double A[4], B[2];
     const double *x0;         // [batch][2]
@@ -58,7 +59,8 @@ struct PolicyParams {
     double inv_h[MAXD], off[MAXD], lut_invw[MAXD];
     int mode[MAXD], n[MAXD], lut_n[MAXD];
     int D, batch;
-    const int32_t *idx;        // [S] policy of one stage, or [N][S_slot] when time varying
+    const int32_t *idx;        // [S] policy of one stage, or [N][S_slot] when time varying (idx_bytes per element)
+    int idx_bytes;
     long long idx_stage_stride;
     int time_varying, stage, rate_dim, n_steps;
     double h_step;

@@ -30,6 +30,9 @@ std::string load_problem(const bellman_desc *d, HostProblem &hp) {
     if (d->N < 2) return "N must be >= 2";
     if (!d->r) return "r table is NULL";
     hp.D = d->D; hp.C = d->C; hp.P = d->P; hp.N = d->N;
+    hp.idx_bytes = d->idx_bytes == 0 ? 4 : d->idx_bytes;
+    if (hp.idx_bytes != 1 && hp.idx_bytes != 2 && hp.idx_bytes != 4) return "idx_bytes must be 0, 1, 2 or 4";
+    if ((hp.idx_bytes == 1 && d->C > 256) || (hp.idx_bytes == 2 && d->C > 65536)) return "idx_bytes too small for C controls";
     hp.part_cuts.clear();
     if (d->part_cuts && d->nranks >= 1) hp.part_cuts.assign(d->part_cuts, d->part_cuts + d->nranks + 1);
     for (int k = 0; k < hp.D; ++k) {

@@ -324,7 +324,7 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
     // ---- consume: step i3 = a3 + it - span3.  (alo, dlo) hold the pairs the previous step read as its
     // UPPER node, (aup, dup) receive this step's — the caller alternates two register sets, nothing is copied
     double *Jp = sp.J_out + jo;
-    int32_t *Ip = sp.idx_out + io;
+    long long Io = io;
     auto consume = [&](int it, double (&alo)[C], double (&dlo)[C], double (&aup)[C], double (&dup)[C]) {
         if (cons) {
             const double t2 = e2n.x;
@@ -366,11 +366,11 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
             if (best2 < best) { best = best2; arg = arg2; }
             if (ok01) {
                 *Jp = best;
-                *Ip = arg;
+                idx_store(sp.idx_out, sp.idx_bytes, Io, arg);
                 if (sp.n_peers) { const int gi[4] = {i0, i1, i2, a3 + it - span3}; peer_store<4>(sp, (int)prob, gi, best); }
             }
             Jp += d3.stride;
-            Ip += tp.own_stride[3];
+            Io += tp.own_stride[3];
             __syncwarp();
             if (lane == 0) mbar_arrive32(bar_empty + 8u * (uint32_t)(it & 3));
             if (it + 1 < n_iter) prefetch();

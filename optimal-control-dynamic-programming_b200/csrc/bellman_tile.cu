@@ -306,7 +306,7 @@ k_stage_tile(const __grid_constant__ StageParams sp, const __grid_constant__ Til
                 io += (long long)(gi[d] - sp.dim[d].own_lo) * tp.own_stride[d];
             }
             sp.J_out[jo] = best;
-            sp.idx_out[io] = arg;
+            idx_store(sp.idx_out, sp.idx_bytes, io, arg);
             if (sp.n_peers) peer_store<D>(sp, prob, gi, best);
         }
     }
@@ -455,7 +455,7 @@ k_stage_tile_pa(const __grid_constant__ StageParams sp, const __grid_constant__ 
             }
             if (row_ok) {
                 sp.J_out[jo] = best;
-                sp.idx_out[io] = arg;
+                idx_store(sp.idx_out, sp.idx_bytes, io, arg);
                 if (sp.n_peers) { const int gi[4] = {i0, i1, i2, i3}; peer_store<4>(sp, (int)prob, gi, best); }
             }
             jo += d1.stride;

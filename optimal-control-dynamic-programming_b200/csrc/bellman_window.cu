@@ -364,13 +364,13 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
     if (i_lo + lane < i_hi) {
         double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
                      (long long)(jbase - d1.ext_lo) * d1.stride;
-        int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
+        long long io = (long long)prob * sp.S_own + (long long)(i - d0.own_lo) +
                       (long long)(jbase - d1.own_lo) * d0.own_n;
 #pragma unroll
         for (int m = 0; m < WR_STATES; ++m) {
             if (jbase + m < j_hi) {
                 jo[(long long)m * d1.stride] = best[m];
-                io[(long long)m * d0.own_n] = arg[m];
+                idx_store(sp.idx_out, sp.idx_bytes, io + (long long)m * d0.own_n, arg[m]);
             }
         }
         if (sp.n_peers) {
@@ -501,7 +501,7 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     if (i_lo + lane < i_hi) {
         double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
                      (long long)(jbase - d1.ext_lo) * d1.stride;
-        int32_t *io = sp.idx_out + (size_t)prob * sp.S_own + (long long)(i - d0.own_lo) +
+        long long io = (long long)prob * sp.S_own + (long long)(i - d0.own_lo) +
                       (long long)(jbase - d1.own_lo) * d0.own_n;
         const long long sj = d1.stride;
         const int si = d0.own_n;
@@ -509,7 +509,7 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
         for (int m = 0; m < R; ++m) {
             if (full || jbase + m < j_hi) {
                 *jo = best[m];
-                *io = arg[m];
+                idx_store(sp.idx_out, sp.idx_bytes, io, arg[m]);
             }
             jo += sj;
             io += si;
@@ -672,7 +672,7 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
         }
         if (row_ok) {
             sp.J_out[jo] = best;
-            sp.idx_out[io] = arg;
+            idx_store(sp.idx_out, sp.idx_bytes, io, arg);
             if (PEER) { const int gi[2] = {i, jb + mm}; peer_store<2>(sp, (int)prob, gi, best); }
         }
         jo += sj;

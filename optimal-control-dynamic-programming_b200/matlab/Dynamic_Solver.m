@@ -89,6 +89,7 @@ classdef Dynamic_Solver < handle
             d.q  = {obj.Q(1)*s.^2, obj.Q(4)*s.^2};
             d.r  = obj.R*u.^2;
             d.store_J_all = obj.store_J_star;  d.store_idx_all = 1;
+            d.idx_bytes = 1 + (obj.du > 256) + 2*(obj.du > 65536);   % u_star of every stage stays on the device: 1 or 2 bytes per state
             d.device = obj.device;
         end
 

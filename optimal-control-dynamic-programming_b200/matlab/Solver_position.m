@@ -36,6 +36,7 @@ classdef Solver_position < handle
         F_Values        % J at the last computed stage, n_x x n_v x 3
         U_idx           % argmin (1-based), n_x x n_v x 3
         device = -1
+        last_desc_ = struct()
         n_gpus = 1      % > 1: the grid is cut into slabs over this many GPUs, driven from this one process
     end
 
@@ -77,6 +78,7 @@ classdef Solver_position < handle
             d.q  = {(s_x.^2)*Qx, (s_v.^2)*Qv};       % column a = Q_a * s.^2 (one product per element)
             d.r  = (U.^2)*R;
             d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
+            obj.last_desc_ = d;
             sz = [numel(s_x), numel(s_v), 3];
             tic
             if obj.n_gpus > 1
@@ -94,6 +96,31 @@ classdef Solver_position < handle
             obj.U2_Opt = griddedInterpolant({s_x.', s_v.'}, obj.U_vector(obj.U_idx(:,:,2)), 'nearest');
             obj.U3_Opt = griddedInterpolant({s_x.', s_v.'}, obj.U_vector(obj.U_idx(:,:,3)), 'nearest');
             fprintf('stage calculation complete!\n')
+        end
+
+        function [X_ode45, F_Opt_history] = get_optimal_path(obj, Y0)
+            % Solver_position.m:189-311 of the reference: nearest policy per axis, then one rkf45 call per
+            % stage on the relative-motion equations (target orbit by the universal Kepler equation), run
+            % on the GPU for every column of Y0 (6 x batch; default the reference's [-1 0 0 0 0 0]').
+            if nargin < 2, Y0 = [-1 0 0 0 0 0].'; end
+            mu = 398600;  RE = 6378;  rp = RE + 300;  e = 0.1;            % get_target_R0V0, :313-331
+            ra = rp*(1 + e)/(1 - e);
+            h_ = sqrt(2*mu*rp*ra/(ra + rp));
+            R0 = (h_^2/mu)*(1/(1 + e))*[1 0 0];  V0 = (mu/h_)*[0 (e + 1) 0];   % sv_from_coe at TA = RA = incl = w = 0
+            N = ceil(obj.T_final/obj.h);
+            d = obj.last_desc_;  d.store_J_all = 0;  d.store_idx_all = 0;
+            hnd = bellman_mex('create', d);
+            bellman_mex('set_stage', hnd, 1, reshape(obj.F_Values, [], 3), reshape(obj.U_idx, [], 3));
+            o = struct('n_steps', N - 1, 'stride_out', 1, 'mu', mu, 'R0', R0, 'V0', V0, 'h', obj.h, 'tol', 1e-8);
+            [X, id] = bellman_mex('rollout_orbit', hnd, 1, o, obj.U_vector(:), Y0);
+            bellman_mex('destroy', hnd);
+            batch = size(Y0, 2);
+            X_ode45 = reshape(X, 6, N, batch);
+            F_Opt_history = reshape(obj.U_vector(id), 3, N - 1, batch);
+            T_ode45 = (0:N-1)*obj.h;
+            figure; hold on; grid on; plot(T_ode45, X_ode45(1:3,:,1)); legend('x1','x2','x3')
+            figure; hold on; grid on; plot(T_ode45, X_ode45(4:6,:,1)); legend('v1','v2','v3')
+            figure; hold on; grid on; plot(T_ode45(1:end-1), F_Opt_history(:,:,1)); legend('u1','u2','u3')
         end
 
         function v = sym_linspace(~, a, b, n)

@@ -15,6 +15,9 @@
 //   r      = bellman_mex('owned_range', h)            [own_lo own_hi) along the slab dimension, 0-based
 //            bellman_mex('group_init', hs)            hs: uint64 vector of handles = slabs 1..n of ONE problem
 //            bellman_mex('group_run', hs, n_stages, opts)   all slabs together, from this one host thread
+//   [X,id,w] = bellman_mex('rollout_orbit', h, stage, o, u_values, Y0)   Solver_position.get_optimal_path:
+//                                                     o: struct n_steps, stride_out, mu, R0, V0, h, tol; Y0: 6 x batch;
+//                                                     X: 6 x ((n_steps/stride_out+1)*batch), id (1-based): 3 x (n_out*batch)
 //            bellman_mex('destroy', h)
 //   v      = bellman_mex('version')
 //
@@ -122,6 +125,7 @@ static void fill_desc(const mxArray *s, bellman_desc &d) {
     d.part_dim = (int32_t)field_scalar(s, "part_dim", 0) - 1;
     d.rank = (int32_t)field_scalar(s, "rank", 0);
     d.nranks = (int32_t)field_scalar(s, "nranks", 1);
+    d.idx_bytes = (int32_t)field_scalar(s, "idx_bytes", 0);     // device storage of the argmin: 0/4 int32, 2 uint16, 1 uint8
 }
 
 static void cmd_create(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
@@ -344,6 +348,32 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
                                    mxGetPr(prhs[7]), mxGetPr(prhs[8]), (int32_t)batch, n_steps, mxGetPr(plhs[0]), p), h);
         for (size_t k = 0; k < (size_t)n_steps * batch; ++k) p[k] += 1;
         if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
+    } else if (cmd == "rollout_orbit") {
+        if (nrhs < 6 || !mxIsStruct(prhs[3])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,id,w] = bellman_mex('rollout_orbit', h, stage, o, u_values, Y0)");
+        bellman_orbit_opts o;
+        std::memset(&o, 0, sizeof(o));
+        o.struct_size = (int32_t)sizeof(o);
+        o.n_steps = (int32_t)field_scalar(prhs[3], "n_steps", 0);
+        o.stride_out = (int32_t)field_scalar(prhs[3], "stride_out", 1);
+        o.mu = field_scalar(prhs[3], "mu", 398600.0);
+        o.h = field_scalar(prhs[3], "h", 0.0);
+        o.tol = field_scalar(prhs[3], "tol", 1e-8);
+        const double *R0 = need_doubles(mxGetField(prhs[3], 0, "R0"), 3, "o.R0"), *V0 = need_doubles(mxGetField(prhs[3], 0, "V0"), 3, "o.V0");
+        for (int k = 0; k < 3; ++k) { o.R0[k] = R0[k]; o.V0[k] = V0[k]; }
+        if (o.n_steps < 1 || o.stride_out < 1 || o.n_steps % o.stride_out) mexErrMsgIdAndTxt("bellman:BAD_ARG", "n_steps must be a positive multiple of stride_out");
+        const size_t batch = mxGetN(prhs[5]);
+        need_doubles(prhs[4], (size_t)sh.C, "u_values");
+        need_doubles(prhs[5], 6 * batch, "Y0 (6-by-batch)");
+        const size_t n_out = (size_t)(o.n_steps / o.stride_out);
+        plhs[0] = mxCreateDoubleMatrix(6, (n_out + 1) * batch, mxREAL);
+        mxArray *id = mxCreateNumericMatrix(3, n_out * batch, mxINT32_CLASS, mxREAL);
+        mxArray *w = mxCreateNumericMatrix(1, batch, mxINT32_CLASS, mxREAL);
+        int32_t *pi = static_cast<int32_t *>(mxGetData(id));
+        check(bellman_rollout_orbit(h, (int32_t)mxGetScalar(prhs[2]), &o, mxGetPr(prhs[4]), mxGetPr(prhs[5]), (int32_t)batch,
+                                    mxGetPr(plhs[0]), pi, static_cast<int32_t *>(mxGetData(w))), h);
+        for (size_t k = 0; k < 3 * n_out * batch; ++k) pi[k] += 1;
+        if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
+        if (nlhs > 2) plhs[2] = w; else mxDestroyArray(w);
     } else {
         mexErrMsgIdAndTxt("bellman:BAD_ARG", "unknown command '%s'", cmd.c_str());
     }

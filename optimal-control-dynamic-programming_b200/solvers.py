@@ -95,7 +95,8 @@ class Dynamic_Solver:
         d = self._build()
         if self._sweep is not None:
             self._sweep.close()
-        sw = self._sweep = Sweep(d, device=self.device)
+        # u_star of every stage stays on the device: one or two bytes per state are enough for du controls
+        sw = self._sweep = Sweep(d, device=self.device, idx_bytes=1 if d.C <= 256 else 2 if d.C <= 65536 else 4)
         sw.run(d.N - 1, kernel=self.kernel, sync_each_stage=self.verbose)
         if self.verbose:
             st = sw.stats()

@@ -23,7 +23,7 @@ class CDesc(C.Structure):
         ("q_order", C.c_int32 * MAXD), ("q", _dp * MAXD), ("r", _dp),
         ("store_J_all", C.c_int32), ("store_idx_all", C.c_int32), ("device", C.c_int32),
         ("part_dim", C.c_int32), ("rank", C.c_int32), ("nranks", C.c_int32),
-        ("part_cuts", C.POINTER(C.c_int32)),
+        ("part_cuts", C.POINTER(C.c_int32)), ("idx_bytes", C.c_int32),
     ]
 
 
