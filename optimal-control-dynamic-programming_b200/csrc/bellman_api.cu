@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -18,6 +20,26 @@
 using namespace bellman;
 
 static thread_local std::string g_create_error;
+
+namespace bellman {
+bool raise_smem_limit(const void *fn, size_t bytes) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> limit;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return false;
+    std::lock_guard<std::mutex> lock(mu);
+    size_t &cur = limit[{dev, fn}];
+    if (bytes <= cur) return true;
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    cur = bytes;
+    return true;
+}
+
+}  // namespace bellman
+
 
 #define CUDA_TRY(h, expr)                                                                     \
     do {                                                                                      \

@@ -127,6 +127,12 @@ __device__ __forceinline__ void peer_store(const StageParams &sp, int prob, cons
 }
 #endif
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION (per device), not of a
+// handle: two handles that plan different window sizes for the same kernel (uneven slabs of a group,
+// two sweeps alive in one process) must not lower each other's limit.  Keeps the maximum ever asked
+// for per (device, function) and only raises the attribute.  Returns false when CUDA refuses.
+bool raise_smem_limit(const void *fn, size_t bytes);
+
 // window (TMA-staged) kernel configuration for D = 2
 struct WindowConfig {
     int tile0 = 0, tile1 = 0;     // states per CTA tile

@@ -57,6 +57,8 @@ struct StreamParams {
     int span3;                      // dimension-3 nodes a step needs: hi3 - lo3 + 2
     int W3;                         // K ring slots = span3 + 2
     int NJ;                         // slab ring slots
+    int debug_sync;                 // BELLMAN_STREAM_DEBUG_SYNC=1: an extra __syncthreads() per iteration (racecheck runs:
+                                    // the tool does not model mbarrier arrive / try_wait pairs between warps)
     int NP;                         // 0: every warp produces (plane j = warp) and warps < T2 also consume;
                                     // > 0: warp specialisation — warps < T2 only consume, the NP warps after them
                                     // share the B2 planes
@@ -390,6 +392,7 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
         produce(it);
         if (it >= 1) sync_prev(it);
         advance();
+        if (tp.debug_sync) __syncthreads();
     }
     // steady state, two iterations per trip so that the register sets alternate without copies
 #pragma unroll 1
@@ -398,10 +401,12 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
         sync_prev(it);
         consume(it, A0, D0, A1, D1);
         advance();
+        if (tp.debug_sync) __syncthreads();
         if (it + 1 < n_prod) produce(it + 1);
         sync_prev(it + 1);
         consume(it + 1, A1, D1, A0, D0);
         advance();
+        if (tp.debug_sync) __syncthreads();
     }
     if (it < n_iter) {                        // odd count: the last step (it == n_prod: nothing left to produce)
         if (it < n_prod) produce(it);
@@ -444,8 +449,7 @@ double pack_bits(uint32_t lo, uint32_t hi) {
 
 template <int C, int NF>
 bool stream_attr(size_t smem) {
-    return cudaFuncSetAttribute((const void *)k_stage_stream<C, NF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) ==
-           cudaSuccess;
+    return raise_smem_limit((const void *)k_stage_stream<C, NF>, smem);
 }
 
 }  // namespace
@@ -503,6 +507,7 @@ void stream_setup(bellman_handle *h) {
     tp.T0 = 32 / tp.T1;
     tp.T0_log2 = tp.T1 == 1 ? 5 : tp.T1 == 2 ? 4 : 3;
     tp.NJ = (fNJ >= 2 && fNJ <= SMAXJ) ? fNJ : 3;
+    tp.debug_sync = std::getenv("BELLMAN_STREAM_DEBUG_SYNC") ? 1 : 0;
     for (int d = 0; d < 4; ++d) tp.lo[d] = lo[d];
     tp.B0 = (tp.T0 + hi[0] - lo[0] + 1 + 1 + 1) / 2 * 2;          // +1: even origin; even extent
     tp.B1 = tp.T1 + hi[1] - lo[1] + 1;

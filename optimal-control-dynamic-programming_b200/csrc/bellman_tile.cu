@@ -713,7 +713,7 @@ void tile_setup(bellman_handle *h) {
     }
     ts->nt = std::getenv("BELLMAN_TILE_NT") ? std::atoi(std::getenv("BELLMAN_TILE_NT")) : 512;
     const void *fn = ts->pa ? (ts->nt == 512 ? (const void *)k_stage_tile_pa<512, 1> : (const void *)k_stage_tile_pa<256, 3>) : D == 4 ? (const void *)k_stage_tile<4> : (const void *)k_stage_tile<3>;
-    if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ts->smem) != cudaSuccess) {
+    if (!raise_smem_limit(fn, ts->smem)) {
         delete ts;
         return;
     }

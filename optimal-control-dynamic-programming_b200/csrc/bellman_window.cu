@@ -769,7 +769,7 @@ static bool window_go(const WindowState *ws, const StageParams *sp, const CUtens
         auto fn48b = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48, 2>;
         if (set_attr_only) {
             for (const void *f : {(const void *)fn48, (const void *)fn48a, (const void *)fn48b})
-                if (cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) != cudaSuccess)
+                if (!raise_smem_limit(f, ws->smem))
                     return false;
         } else if (ws->wp.win0 == 48) {
             if (ws->loc == 2) fn48b<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
@@ -778,10 +778,15 @@ static bool window_go(const WindowState *ws, const StageParams *sp, const CUtens
             return true;
         }
     }
+    if (HC0 && HC1 && !CHAIN && R == 4) {   // BELLMAN_WIN_R4 experiment: runtime pitch, both floors on the fp64 pipe
+        auto fnr = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 0, 2>;
+        if (set_attr_only) return raise_smem_limit((const void *)fnr, ws->smem);
+        fnr<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+        return true;
+    }
     auto fn = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R>;
     if (set_attr_only)
-        return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ws->smem) ==
-               cudaSuccess;
+        return raise_smem_limit((const void *)fn, ws->smem);
     fn<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
     return true;
 }
@@ -792,6 +797,10 @@ static bool window_go_hc(const WindowState *ws, const StageParams *sp, const CUt
         if (ws->occ == 3) return window_go<HC0, HC1, CHAIN, 2, 3, 4>(ws, sp, map, grid, st, sa);
         if (ws->occ == 1) return window_go<HC0, HC1, CHAIN, 2, 4, 4>(ws, sp, map, grid, st, sa);
         return window_go<HC0, HC1, CHAIN, 4, 4, 4>(ws, sp, map, grid, st, sa);
+    }
+    if (!CHAIN && HC0 && HC1 && ws->rstates == 4) {      // BELLMAN_WIN_R4 experiment: 3 or 4 CTAs per SM
+        if (ws->occ == 4) return window_go<HC0, HC1, CHAIN, 4, 4, 4>(ws, sp, map, grid, st, sa);
+        return window_go<HC0, HC1, CHAIN, 4, 3, 4>(ws, sp, map, grid, st, sa);
     }
     if (ws->occ == 1) {
         if (ws->batch == 8) return window_go<HC0, HC1, CHAIN, 8, 1>(ws, sp, map, grid, st, sa);
@@ -816,10 +825,8 @@ static bool strip_go(const WindowState *ws, const StageParams *sp, const CUtenso
     auto fn = k_stage_strip<NW, CC, OCC, false>;
     auto fnp = k_stage_strip<NW, CC, OCC, true>;      // multi-GPU: halo states also go to the neighbours
     if (set_attr_only)
-        return cudaFuncSetAttribute((const void *)fn, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)ws->lean_smem) == cudaSuccess &&
-               cudaFuncSetAttribute((const void *)fnp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)ws->lean_smem) == cudaSuccess;
+        return raise_smem_limit((const void *)fn, ws->lean_smem) &&
+               raise_smem_limit((const void *)fnp, ws->lean_smem);
     if (sp->n_peers) fnp<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
     else fn<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
     return true;
@@ -922,7 +929,10 @@ void window_setup(bellman_handle *h) {
     // small-control CHAIN problems run 4 states per thread (see k_stage_window)
     const bool chain_cfg = hp.has_c[0] && !hp.has_c[1] && hp.src_a[0] == 0 && (!hp.has_b[0] || hp.src_b[0] == 0) &&
                            !std::getenv("BELLMAN_WIN_NOCHAIN");
-    const int rstates = (chain_cfg && hp.C <= 8 && !std::getenv("BELLMAN_WIN_R8")) ? 4 : 8;
+    // BELLMAN_WIN_R4=1: 4 states per thread for the long-control-loop kernel too (tile 32 x 32, half the
+    // registers, more CTAs per SM) — experiment knob
+    const bool r4_all = std::getenv("BELLMAN_WIN_R4") != nullptr;
+    const int rstates = ((chain_cfg && hp.C <= 8 && !std::getenv("BELLMAN_WIN_R8")) || (r4_all && !chain_cfg)) ? 4 : 8;
     // k_stage_strip geometry: NW warps per CTA, each walking strip_r columns (tile 32 x NW*strip_r)
     const bool lean_cfg = chain_cfg && rstates == 4 && hp.C <= 4 && !std::getenv("BELLMAN_WIN_NOLEAN");
     const bool strip_cfg = lean_cfg && !std::getenv("BELLMAN_WIN_NOSTRIP");
@@ -945,6 +955,7 @@ void window_setup(bellman_handle *h) {
         for (int cc : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32})
             if (cc <= hp.C) cands.push_back(cc);
         if (hp.C <= 32 && std::find(cands.begin(), cands.end(), hp.C) == cands.end()) cands.push_back(hp.C);
+        if (const char *e = std::getenv("BELLMAN_WIN_CC")) { cands.clear(); cands.push_back(std::max(1, std::min(hp.C, std::atoi(e)))); }
     }
     for (int cc : cands) {
         int w0, w1;
@@ -1128,8 +1139,7 @@ void window_setup(bellman_handle *h) {
     if (ws->lean) {
         ws->lean_smem = (size_t)wp.nchunks * slot_bytes(wp.win0, wp.win1);
         if (ws->lean_smem > 56 * 1024 ||
-            cudaFuncSetAttribute((const void *)k_stage_chain<4, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)ws->lean_smem) != cudaSuccess)
+            !raise_smem_limit((const void *)k_stage_chain<4, 4>, ws->lean_smem))
             ws->lean = false;
     }
     if (!ws->hc0 && !ws->hc1) { window_teardown_state(ws); return; }   // no control dependence at all: nothing to stage for

@@ -106,3 +106,22 @@ def test_facade_n_gpus(bellman, oracle_lib):
     Xa, Ua = a.get_optimal_path_simplified(x0, n_steps=15)
     Xb, Ub = b.get_optimal_path_simplified(x0, n_steps=15)
     assert np.array_equal(Xa, Xb) and np.array_equal(Ua, Ub)
+
+
+def test_handles_with_different_window_sizes_coexist(bellman, oracle_lib):
+    """The dynamic shared-memory limit belongs to the kernel FUNCTION, not to a handle: slabs (or two
+    sweeps) that plan different window sizes for the same kernel must not lower each other's limit
+    (96 x 96 Kirk grid cut in two: the two slabs' halos, hence their windows, differ)."""
+    o = bellman.Dynamic_Solver()
+    small = bellman.tables.kirk_desc(o.A, o.B, o.Q, o.R, 6, o.x_min, o.x_max, 96, o.u_min, o.u_max, 24,
+                                     store_J_all=False, store_idx_all=False)
+    _check(bellman, oracle_lib, small, 2, None, "staged", n_stages=3, want="window:ring")
+    big = _kirk(bellman, n0=512, n1=384, C=64)
+    a = bellman.Sweep(big)
+    b = bellman.Sweep(small)          # created later, plans a smaller window for the same kernel
+    a.run(2, kernel=KERNELS["staged"])
+    b.run(2, kernel=KERNELS["staged"])
+    oa, ob = oracle_lib.sweep(big, n_stages=2), oracle_lib.sweep(small, n_stages=2)
+    assert np.array_equal(a.get_J(), oa["J_last"]) and np.array_equal(b.get_J(), ob["J_last"])
+    a.close()
+    b.close()
