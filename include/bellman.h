@@ -243,7 +243,8 @@ int  bellman_rollout(bellman_handle *h, const double *A, const double *B, const 
  * `batch` query states of problem `prob`: x is [D][batch] column-major (batch slowest),
  * idx_out[batch] receives the 0-based control index stored at the nearest grid node of `stage`
  * (clamped outside the grid; an exact midpoint goes to the upper node — MATLAB's tie side is
- * undocumented).  Single rank only. */
+ * undocumented).  On a partitioned handle the rank that owns the nearest node answers and every
+ * other rank writes -1, so the element-wise maximum over the ranks is the lookup. */
 int  bellman_policy_lookup(bellman_handle *h, int32_t prob, int32_t stage, const double *x,
                            int32_t batch, int32_t *idx_out);
 

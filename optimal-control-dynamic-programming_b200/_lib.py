@@ -450,6 +450,11 @@ class SweepGroup:
     def check_log(self):
         return self.slabs[0].check_log()
 
+    def policy_lookup(self, x, prob=0, stage=None):
+        """'nearest' policy lookup on the sharded policy: the slab that owns the nearest node answers,
+        the others return -1; the element-wise maximum is the lookup."""
+        return np.max(np.stack([s.policy_lookup(x, prob=prob, stage=stage) for s in self.slabs]), axis=0)
+
     def close(self):
         for s in self.slabs:
             s.close()

@@ -968,7 +968,6 @@ extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double 
 static int fill_policy_params(bellman_handle *h, int prob, PolicyParams &pp) {
     const HostProblem &hp = h->hp;
     if (prob < 0 || prob >= hp.P) { h->err = "problem index out of range"; return BELLMAN_ERR_BAD_ARG; }
-    if (h->nranks != 1) { h->err = "policy lookup / rollout run on a single rank"; return BELLMAN_ERR_BAD_ARG; }
     std::memset(&pp, 0, sizeof(pp));
     pp.D = hp.D;
     for (int d = 0; d < hp.D; ++d) {
@@ -982,6 +981,8 @@ static int fill_policy_params(bellman_handle *h, int prob, PolicyParams &pp) {
         pp.mode[d] = hp.mode[(size_t)prob * hp.D + d];
         pp.n[d] = hp.n[d];
         pp.lut_n[d] = hp.lut_n[d];
+        pp.own_lo[d] = h->own_lo[d];
+        pp.own_n[d] = h->own_n[d];
     }
     pp.idx_bytes = hp.idx_bytes;
     return BELLMAN_OK;
@@ -1021,6 +1022,7 @@ extern "C" int bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t tim
     if (!h || !u_inc || !x0 || !X_out || !C_out || batch < 1 || n_steps < 1) return BELLMAN_ERR_BAD_ARG;
     const HostProblem &hp = h->hp;
     if (hp.D != 2 || rate_dim < 0 || rate_dim > 1) { h->err = "axis rollout needs D = 2 and rate_dim in {0,1}"; return BELLMAN_ERR_BAD_ARG; }
+    if (h->nranks != 1) { h->err = "rollouts cross slab boundaries: gather the policy into an unsharded handle (bellman_set_stage) first"; return BELLMAN_ERR_BAD_ARG; }
     PolicyParams pp;
     int rc = fill_policy_params(h, prob, pp);
     if (rc != BELLMAN_OK) return rc;
@@ -1064,6 +1066,7 @@ extern "C" int bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bel
     if (o->struct_size != (int32_t)sizeof(bellman_orbit_opts)) { h->err = "bellman_orbit_opts.struct_size mismatch"; return BELLMAN_ERR_BAD_ARG; }
     const HostProblem &hp = h->hp;
     if (hp.D != 2 || hp.P < 3) { h->err = "orbit rollout needs D = 2 and P >= 3 (the x, y, z axis problems)"; return BELLMAN_ERR_BAD_ARG; }
+    if (h->nranks != 1) { h->err = "rollouts cross slab boundaries: gather the policy into an unsharded handle (bellman_set_stage) first"; return BELLMAN_ERR_BAD_ARG; }
     if (o->n_steps < 1 || o->stride_out < 1 || o->n_steps % o->stride_out) { h->err = "n_steps must be a positive multiple of stride_out"; return BELLMAN_ERR_BAD_ARG; }
     int rc = stage_available(h, stage, h->store_idx_all, true);
     if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }

@@ -439,12 +439,15 @@ __device__ __forceinline__ int nearest_node(const PolicyParams &pp, int d, doubl
     return cell + ((x - lo) >= (hi - x) ? 1 : 0);      // exact midpoint -> upper node
 }
 
-// `ibase` = element offset of the policy inside pp.idx (0, or the stage offset when time varying)
+// `ibase` = element offset of the policy inside pp.idx (0, or the stage offset when time varying).
+// On a partitioned handle a state whose nearest node another rank owns yields -1 (the owner answers).
 __device__ __forceinline__ int policy_at(const PolicyParams &pp, long long ibase, const double *x) {
     long long o = 0, st = 1;
     for (int d = 0; d < pp.D; ++d) {
-        o += (long long)nearest_node(pp, d, x[d]) * st;
-        st *= pp.n[d];
+        const int node = nearest_node(pp, d, x[d]) - pp.own_lo[d];
+        if (node < 0 || node >= pp.own_n[d]) return -1;
+        o += (long long)node * st;
+        st *= pp.own_n[d];
     }
     return idx_load(pp.idx, pp.idx_bytes, ibase + o);
 }

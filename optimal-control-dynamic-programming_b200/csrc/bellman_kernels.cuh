@@ -58,6 +58,7 @@ struct PolicyParams {
     const int32_t *lut[MAXD];
     double inv_h[MAXD], off[MAXD], lut_invw[MAXD];
     int mode[MAXD], n[MAXD], lut_n[MAXD];
+    int own_lo[MAXD], own_n[MAXD];   // owned index range per dimension (the whole grid unless partitioned)
     int D, batch;
     const int32_t *idx;        // [S] policy of one stage, or [N][S_slot] when time varying (idx_bytes per element)
     int idx_bytes;

@@ -102,6 +102,17 @@ def test_facade_n_gpus(bellman, oracle_lib):
     b.simplified_run(n_stages=20)
     for p in range(3):
         assert np.array_equal(a.U_idx[p], b.U_idx[p]) and np.array_equal(a.F_Values[p], b.F_Values[p])
+    # nearest lookup straight on the SHARDED policy (owner answers, the other slabs say -1)
+    grp = bellman.SweepGroup(a._desc, _devices(3), part_dim=0)
+    grp.run(20)
+    xq = np.random.default_rng(5).uniform(-1.0, 1.0, size=(500, 2)) * [1.0, 0.6]
+    for p in range(3):
+        assert np.array_equal(grp.policy_lookup(xq, prob=p), a._sweep.policy_lookup(xq, prob=p))
+    parts = [s.policy_lookup(xq, prob=0) for s in grp.slabs]
+    assert all(np.sum(np.stack(parts) >= 0, axis=0) == 1)          # exactly one owner per query
+    with pytest.raises(bellman.BellmanError):
+        grp.slabs[0].rollout_axis(a._desc.Tc[0][0], xq[:4], 5, 0.005, 0)
+    grp.close()
     x0 = np.tile(np.array([[0.1, -0.05]]), (3, 1))[None]
     Xa, Ua = a.get_optimal_path_simplified(x0, n_steps=15)
     Xb, Ub = b.get_optimal_path_simplified(x0, n_steps=15)
