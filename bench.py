@@ -300,6 +300,8 @@ def main():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (N = 1 default run)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal slabs (no trial-run balancing)")
+    ap.add_argument("--idx-bytes", type=int, default=4, choices=[1, 2, 4],
+                    help="device storage of the argmin (4 = int32, the canonical 20 B/state of SURVEY 8d)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -353,7 +355,8 @@ def main():
     part_dim = pick_part_dim(d)
 
     def open_sweep(pd, dd=None, cuts=None):
-        s = bb.Sweep(dd if dd is not None else d, device=local, part_dim=pd, rank=rank, nranks=world, part_cuts=cuts)
+        s = bb.Sweep(dd if dd is not None else d, device=local, part_dim=pd, rank=rank, nranks=world, part_cuts=cuts,
+                     idx_bytes=args.idx_bytes)
         if world > 1:
             ids = [bb.get_unique_id() if rank == 0 else None]
             dist.broadcast_object_list(ids, src=0)
@@ -510,7 +513,7 @@ def main():
     peak, peak_src = measured_peak_gbs()
     kernel_name = main_kernel
     halo_mode = main_halo
-    bytes_per_launch = (S_all / world) * (16 + 4)          # read J_{k+1}, write J_k, write int32 argmin
+    bytes_per_launch = (S_all / world) * (16 + args.idx_bytes)   # read J_{k+1}, write J_k, write the argmin (int32 unless --idx-bytes)
     ms_kernel = (ms_dev - ms_x) / K
     achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
     # secondary bound: fp64 pipe, 64 lanes/clk/SM x 148 SMs at the clock seen
@@ -520,7 +523,7 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0],
                 "traffic_source": NCU_TRAFFIC.get(args.workload, (None, None))[1], "peak_source": peak_src,
-                "bytes_per_launch": bytes_per_launch, "kernel_ms": ms_kernel, "kernel": kernel_name,
+                "bytes_per_launch": bytes_per_launch, "idx_bytes": args.idx_bytes, "kernel_ms": ms_kernel, "kernel": kernel_name,
                 "fp64_secondary": {"ops_per_update": fp64_ops_per_update,
                                    "achieved_ops_per_s": value / world * fp64_ops_per_update,
                                    "peak_ops_per_s": fp64_peak,

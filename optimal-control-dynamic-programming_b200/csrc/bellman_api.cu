@@ -104,6 +104,19 @@ extern "C" const char *bellman_last_error(const bellman_handle *h) {
     return h ? h->err.c_str() : g_create_error.c_str();
 }
 
+// argmin storage narrower than int32: conversion to / from the ABI's int32 happens on the device
+__global__ void k_widen_idx(const void *src, int bytes, long long n, int32_t *dst) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x)
+        dst[k] = idx_load(src, bytes, k);
+}
+__global__ void k_narrow_idx(const int32_t *src, int bytes, long long n, void *dst, int C, int *bad) {
+    for (long long k = blockIdx.x * (long long)blockDim.x + threadIdx.x; k < n; k += (long long)gridDim.x * blockDim.x) {
+        const int v = src[k];
+        if (v < 0 || v >= C) *bad = 1;
+        idx_store(dst, bytes, k, v);
+    }
+}
+
 static int upload_tables(bellman_handle *h) {
     HostProblem &hp = h->hp;
     const int D = hp.D, P = hp.P;
@@ -370,19 +383,24 @@ extern "C" int bellman_set_stage(bellman_handle *h, int32_t stage, const double 
     h->check_log.clear();
     int rc = upload_J(h, stage, J_host);
     if (rc != BELLMAN_OK) return rc;
-    std::vector<unsigned char> narrow;
     if (idx_host) {
         const size_t ne = h->slot_elems_idx();
-        const void *src = idx_host;
-        if (hp.idx_bytes != 4) {           // the device stores 1 or 2 bytes per index
-            narrow.resize(ne * (size_t)hp.idx_bytes);
-            for (size_t k = 0; k < ne; ++k) {
-                if (idx_host[k] < 0 || idx_host[k] >= hp.C) { h->err = "bellman_set_stage: control index out of range"; return BELLMAN_ERR_BAD_ARG; }
-                idx_store(narrow.data(), hp.idx_bytes, (long long)k, idx_host[k]);
-            }
-            src = narrow.data();
+        if (hp.idx_bytes == 4) {
+            CUDA_TRY(h, cudaMemcpyAsync(h->idx_ptr(stage), idx_host, ne * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream));
+        } else {                           // the device stores 1 or 2 bytes per index: narrow there
+            int32_t *tmp = nullptr;
+            int *d_bad = nullptr, bad = 0;
+            CUDA_TRY(h, cudaMalloc(&tmp, ne * sizeof(int32_t) + sizeof(int)));
+            d_bad = reinterpret_cast<int *>(tmp + ne);
+            cudaMemsetAsync(d_bad, 0, sizeof(int), h->stream);
+            cudaMemcpyAsync(tmp, idx_host, ne * sizeof(int32_t), cudaMemcpyHostToDevice, h->stream);
+            k_narrow_idx<<<592, 256, 0, h->stream>>>(tmp, hp.idx_bytes, (long long)ne, h->idx_ptr(stage), hp.C, d_bad);
+            cudaMemcpyAsync(&bad, d_bad, sizeof(int), cudaMemcpyDeviceToHost, h->stream);
+            cudaError_t e = cudaStreamSynchronize(h->stream);
+            cudaFree(tmp);
+            if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
+            if (bad) { h->err = "bellman_set_stage: control index out of range"; return BELLMAN_ERR_BAD_ARG; }
         }
-        CUDA_TRY(h, cudaMemcpyAsync(h->idx_ptr(stage), src, ne * (size_t)hp.idx_bytes, cudaMemcpyHostToDevice, h->stream));
     }
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     h->J_set = true;
@@ -429,12 +447,18 @@ extern "C" int bellman_get_idx(bellman_handle *h, int32_t stage, int32_t *out) {
     if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
     const size_t ne = h->slot_elems_idx();
     const int ib = h->hp.idx_bytes;
-    // narrow storage lands in the tail of the caller's int32 buffer and is widened in place, front to back
-    unsigned char *raw = reinterpret_cast<unsigned char *>(out) + ne * (size_t)(4 - ib);
-    CUDA_TRY(h, cudaMemcpyAsync(raw, h->idx_ptr(stage), ne * (size_t)ib, cudaMemcpyDeviceToHost, h->stream));
-    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    if (ib != 4)
-        for (size_t k = 0; k < ne; ++k) out[k] = idx_load(raw, ib, (long long)k);
+    if (ib == 4) {
+        CUDA_TRY(h, cudaMemcpyAsync(out, h->idx_ptr(stage), ne * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+        return BELLMAN_OK;
+    }
+    int32_t *tmp = nullptr;                // widened on the device, then copied as int32
+    CUDA_TRY(h, cudaMalloc(&tmp, ne * sizeof(int32_t)));
+    k_widen_idx<<<592, 256, 0, h->stream>>>(h->idx_ptr(stage), ib, (long long)ne, tmp);
+    cudaMemcpyAsync(out, tmp, ne * sizeof(int32_t), cudaMemcpyDeviceToHost, h->stream);
+    cudaError_t e = cudaStreamSynchronize(h->stream);
+    cudaFree(tmp);
+    if (e != cudaSuccess) { h->err = cudaGetErrorString(e); return BELLMAN_ERR_CUDA; }
     return BELLMAN_OK;
 }
 

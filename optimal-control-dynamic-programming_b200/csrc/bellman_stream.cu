@@ -132,7 +132,7 @@ __device__ __forceinline__ void sts64(uint32_t addr, double v) {
 }
 
 // C controls, NF classes of dimension 1 (compile time: the per-control and per-class values live in registers)
-template <int C, int NF>
+template <int C, int NF, bool IDX32>
 __global__ void __launch_bounds__(384, 1)
 k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ StreamParams tp,
                const __grid_constant__ CUtensorMap tmap) {
@@ -368,7 +368,8 @@ k_stage_stream(const __grid_constant__ StageParams sp, const __grid_constant__ S
             if (best2 < best) { best = best2; arg = arg2; }
             if (ok01) {
                 *Jp = best;
-                idx_store(sp.idx_out, sp.idx_bytes, Io, arg);
+                if (IDX32) sp.idx_out[Io] = arg;          // the default int32 store stays branch-free in the step loop
+                else idx_store(sp.idx_out, sp.idx_bytes, Io, arg);
                 if (sp.n_peers) { const int gi[4] = {i0, i1, i2, a3 + it - span3}; peer_store<4>(sp, (int)prob, gi, best); }
             }
             Jp += d3.stride;
@@ -449,7 +450,8 @@ double pack_bits(uint32_t lo, uint32_t hi) {
 
 template <int C, int NF>
 bool stream_attr(size_t smem) {
-    return raise_smem_limit((const void *)k_stage_stream<C, NF>, smem);
+    return raise_smem_limit((const void *)k_stage_stream<C, NF, true>, smem) &&
+           raise_smem_limit((const void *)k_stage_stream<C, NF, false>, smem);
 }
 
 }  // namespace
@@ -699,8 +701,11 @@ cudaError_t stream_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     if (!ss) return cudaErrorNotSupported;
     const StreamParams &tp = ss->tp;
     const dim3 grid((unsigned)(tp.ntile[0] * tp.ntile[1]), (unsigned)(tp.ntile[2] * tp.ntile[3]), (unsigned)sp.P);
-    if (ss->C == 9) k_stage_stream<9, 5><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
-    else k_stage_stream<6, 4><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    const bool i32 = sp.idx_bytes == 4;
+    if (ss->C == 9 && i32) k_stage_stream<9, 5, true><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    else if (ss->C == 9) k_stage_stream<9, 5, false><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    else if (i32) k_stage_stream<6, 4, true><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
+    else k_stage_stream<6, 4, false><<<grid, ss->nthreads, ss->smem, st>>>(sp, tp, ss->maps[slot_next]);
     return cudaGetLastError();
 }
 

@@ -536,7 +536,9 @@ k_stage_chain(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
 // Same operations on the same operands as the generic path ⇒ bit-identical results.
 // All C windows of the tile (32+ rows x NW*strip_r+ columns) are in flight from the first instruction.
 // ---------------------------------------------------------------------------------------------
-template <int NW, int CC, int OCC, bool PEER>
+// IDX32: the argmin is stored as int32 (the default); false = 1- or 2-byte storage, decided at run time.
+// A template parameter because the store sits in the branch-free column loop.
+template <int NW, int CC, int OCC, bool PEER, bool IDX32>
 __global__ void __launch_bounds__(NW * 32, OCC)
 k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
               const __grid_constant__ CUtensorMap tmap) {
@@ -600,7 +602,11 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     const bool row_ok = i_lo + lane < i_hi;
     const uint32_t sj = (uint32_t)d1.stride, si = (uint32_t)d0.own_n;
     uint32_t jo = prob * (uint32_t)sp.S_ext + (uint32_t)(i - d0.ext_lo) * (uint32_t)d0.stride + (uint32_t)(jb - d1.ext_lo) * sj;
-    uint32_t io = prob * (uint32_t)sp.S_own + (uint32_t)(i - d0.own_lo) + (uint32_t)(jb - d1.own_lo) * si;
+    // argmin store: byte offset into idx_out (1, 2 or 4 bytes per element, decided once per thread)
+    const uint32_t ibytes = (uint32_t)sp.idx_bytes;
+    const bool i1 = ibytes == 1;
+    char *const ibase = reinterpret_cast<char *>(sp.idx_out);
+    uint32_t io = prob * (uint32_t)sp.S_own + (uint32_t)(i - d0.own_lo) + (uint32_t)(jb - d1.own_lo) * si;   // elements
 
     __syncthreads();          // org[] and the mbarrier are visible
     if (wrp == 0 && lane < CC) {
@@ -672,7 +678,13 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
         }
         if (row_ok) {
             sp.J_out[jo] = best;
-            idx_store(sp.idx_out, sp.idx_bytes, io, arg);
+            if (IDX32) {
+                sp.idx_out[io] = arg;
+            } else {
+                char *const ip = ibase + (size_t)io * ibytes;
+                if (i1) *reinterpret_cast<unsigned char *>(ip) = (unsigned char)arg;
+                else *reinterpret_cast<unsigned short *>(ip) = (unsigned short)arg;
+            }
             if (PEER) { const int gi[2] = {i, jb + mm}; peer_store<2>(sp, (int)prob, gi, best); }
         }
         jo += sj;
@@ -822,13 +834,20 @@ static bool window_dispatch(const WindowState *ws, const StageParams *sp, const 
 template <int NW, int CC, int OCC>
 static bool strip_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid, cudaStream_t st,
                      bool set_attr_only) {
-    auto fn = k_stage_strip<NW, CC, OCC, false>;
-    auto fnp = k_stage_strip<NW, CC, OCC, true>;      // multi-GPU: halo states also go to the neighbours
+    auto fn = k_stage_strip<NW, CC, OCC, false, true>;
+    auto fnp = k_stage_strip<NW, CC, OCC, true, true>;      // multi-GPU: halo states also go to the neighbours
+    auto fnn = k_stage_strip<NW, CC, OCC, false, false>;    // 1- / 2-byte argmin storage
+    auto fnpn = k_stage_strip<NW, CC, OCC, true, false>;
     if (set_attr_only)
-        return raise_smem_limit((const void *)fn, ws->lean_smem) &&
-               raise_smem_limit((const void *)fnp, ws->lean_smem);
-    if (sp->n_peers) fnp<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
-    else fn<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+        return raise_smem_limit((const void *)fn, ws->lean_smem) && raise_smem_limit((const void *)fnp, ws->lean_smem) &&
+               raise_smem_limit((const void *)fnn, ws->lean_smem) && raise_smem_limit((const void *)fnpn, ws->lean_smem);
+    if (sp->idx_bytes == 4) {
+        if (sp->n_peers) fnp<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+        else fn<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+    } else {
+        if (sp->n_peers) fnpn<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+        else fnn<<<grid, NW * 32, ws->lean_smem, st>>>(*sp, ws->wp, *map);
+    }
     return true;
 }
 static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
