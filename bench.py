@@ -50,7 +50,7 @@ DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
 # the same command, each with the file it comes from; reported as roofline.traffic + traffic_source.
 NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": (548.0e6 + 772.5e6, "profiles/r01_window_kirk_summary.txt"),
                "attitude_x16_3x16000x4800x3": (1.8434e9 + 2.7178e9, "profiles/r01_strip_att16_summary.txt"),
-               "pos_att_x4_120x120x80x60x9": (2.1758e9 + 2.4519e9, "profiles/r02_stream_posatt4_summary.txt")}
+               "pos_att_x4_120x120x80x60x9": (2.0363e9 + 2.4638e9, "profiles/r02_stream_posatt_x4_summary.txt")}
 
 
 def make_desc(bb, name, world=1):

@@ -135,6 +135,17 @@ __device__ __forceinline__ int locate_magic(double g, double &t) {
     return __double2loint(s);
 }
 
+// The clamped locate without the conversion pipe, for queries known to satisfy |g| < 2^31 (the host checks
+// the bound): floor from the low word of g +(rd) M as above, clamp on the integer pipe, (double)cell by the
+// bit trick.  Same cell and the same exact difference g - cell as locate_uniform<true> — F2I.F64 / I2F.F64
+// occupy a scheduler's conversion pipe for 8 cycles per warp instruction, a DADD the fp64 pipe for 2.
+__device__ __forceinline__ int locate_magic_clamp(double g, int n, double &t) {
+    const double M = 6755399441055744.0;
+    const int cell = min(max(__double2loint(__dadd_rd(g, M)), 0), n - 2);
+    t = g - cell_to_double(cell);
+    return cell;
+}
+
 template <bool CLAMP = true, bool XUCVT = false>
 __device__ __forceinline__ int locate_uniform(double g, int n, double &t) {
     int cell = __double2int_rd(g);
@@ -382,6 +393,200 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
 }
 
 // ---------------------------------------------------------------------------------------------
+// k_stage_wide: the long-control-loop case (both dimensions depend on the control, e.g. Dynamic_Solver's
+// x' = A x + B u) re-cut for instruction-level parallelism.  Same tile (32 x 64), same window ring and
+// same operations per update as k_stage_window, but
+//   * 512 threads own 4 states each instead of 256 threads owning 8: the per-state registers (two query
+//     bases, the state cost, best, argmin = 9 per state) drop from 72 to 36 of the 128 a thread may
+//     hold, which is what lets the four updates of a control interleave instruction by instruction (in
+//     k_stage_window ptxas serialises them to stay under 128: ~7 cycles per issued instruction per warp);
+//   * the control tables Tc_0, Tc_1, r come from the constant bank (a 12 KB kernel parameter) instead of
+//     three global loads and ten address instructions per control;
+//   * shared-memory addresses are 32-bit (two IMADs per update).
+// One CTA per SM (16 warps), NS ring slots.
+// ---------------------------------------------------------------------------------------------
+constexpr int WIDE_NT = 512, WIDE_R = 4, WIDE_MAXC = 512;
+struct WideTables {
+    double tc0[WIDE_MAXC], tc1[WIDE_MAXC], r[WIDE_MAXC];   // [P * C] each
+};
+
+template <int NS, int W0C, bool IDX32>
+__global__ void __launch_bounds__(WIDE_NT, 1)
+k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
+             const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WideTables tb) {
+    constexpr int R = WIDE_R, WT1 = (WIDE_NT / 32) * R;
+    extern __shared__ __align__(128) double ring[];
+    __shared__ __align__(8) uint64_t mbar[NS];
+    __shared__ double tmm_s[8];
+
+    const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
+    const int prob = blockIdx.y;
+    const int ti = wp.tj_fastest ? blockIdx.x / wp.ntile1 : blockIdx.x % wp.ntile0;
+    const int tj = wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0;
+    const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
+    const int n0 = d0.n, n1 = d1.n;
+    const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
+    const int j_lo = d1.own_lo + tj * WT1, j_hi = min(j_lo + WT1, d1.own_lo + d1.own_n);
+    const uint32_t win_bytes = (uint32_t)(wp.win0 * wp.win1) * 8u;
+    const double *cmm = wp.cmm + (size_t)prob * wp.nchunks * 4;
+    const int pc = prob * sp.C;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (tid < 8) {
+        const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
+        const int d = tid >> 2, ab = (tid >> 1) & 1, mx = tid & 1;
+        const DimParams &dd = d == 0 ? d0 : d1;
+        double v = 0.0;
+        if (!(ab == 1 && !dd.Tb)) {
+            const int src = ab == 0 ? dd.src_a : dd.src_b;
+            v = __ldg(tm + wp.tmm_off[d][ab] + 2 * (src == 0 ? ti : tj) + mx);
+        }
+        tmm_s[tid] = v;
+    }
+    __syncthreads();
+
+    // exact bounds of chunk ch's queries, formed with the kernel's own association (as k_stage_window)
+    auto bounds = [&](int ch, double &lo0, double &hi0, double &lo1, double &hi1) {
+        lo0 = tmm_s[0]; hi0 = tmm_s[1]; lo1 = tmm_s[4]; hi1 = tmm_s[5];
+        if (d0.Tb) { lo0 = lo0 + tmm_s[2]; hi0 = hi0 + tmm_s[3]; }
+        if (d1.Tb) { lo1 = lo1 + tmm_s[6]; hi1 = hi1 + tmm_s[7]; }
+        lo0 = lo0 + __ldg(cmm + 4 * ch); hi0 = hi0 + __ldg(cmm + 4 * ch + 1);
+        lo1 = lo1 + __ldg(cmm + 4 * ch + 2); hi1 = hi1 + __ldg(cmm + 4 * ch + 3);
+    };
+    auto origin = [&](double lo0, double lo1, int &r0, int &c0) {
+        r0 = cell_uniform(lo0, n0);
+        r0 -= (r0 - d0.ext_lo) & 1;                  // TMA: even innermost coordinate
+        c0 = cell_uniform(lo1, n1);
+    };
+    auto issue = [&](int ch) {   // thread 0 only
+        double lo0, hi0, lo1, hi1;
+        bounds(ch, lo0, hi0, lo1, hi1);
+        int r0, c0;
+        origin(lo0, lo1, r0, c0);
+        const int s = ch % NS;
+        mbar_expect_tx(&mbar[s], win_bytes);
+        double *dst = ring + s * wp.buf_doubles;
+        for (int b = 0; b < wp.boxes; ++b)
+            tma_load_3d(dst + (size_t)b * wp.box1 * wp.win0, &tmap, &mbar[s], r0 - d0.ext_lo,
+                        c0 - d1.ext_lo + b * wp.box1, prob);
+    };
+    if (tid == 0)
+        for (int ch = 0; ch < NS && ch < wp.nchunks; ++ch) issue(ch);
+
+    // this thread's states: row i, columns jbase .. jbase + 3
+    const int i = min(i_lo + lane, i_hi - 1);
+    const int jbase = j_lo + wrp * R;
+    double base0[R], base1[R], gs[R], best[R];
+    int arg[R];
+    {
+        const double2 *rpk = reinterpret_cast<const double2 *>(wp.rowpack + (size_t)prob * n0 + i);
+        const double2 rp01 = __ldg(rpk), rp23 = __ldg(rpk + 1);
+        const double2 *cpk = reinterpret_cast<const double2 *>(wp.colpack + (size_t)prob * n1);
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            const int j = min(jbase + m, j_hi - 1);
+            const double2 cp01 = __ldg(cpk + 2 * j), cp23 = __ldg(cpk + 2 * j + 1);
+            base0[m] = wp.col0_zero ? rp01.x : rp01.x + cp01.x;
+            base1[m] = wp.col1_zero ? rp01.y : rp01.y + cp01.y;
+            gs[m] = rp23.x + cp23.x;
+            best[m] = __longlong_as_double(0x7ff0000000000000LL);
+            arg[m] = 0;
+        }
+    }
+
+    const uint32_t PB = (uint32_t)(W0C ? W0C : wp.win0) * 8u;      // window pitch in bytes
+    const uint32_t ring_u32 = smem_u32(ring);
+
+    // MODE 0: every query of the chunk falls in an interior cell (no clamp); 1: clamped, |g| < 2^30 (no
+    // conversion instructions); 2: clamped, conversion pipe (queries beyond 2^30 cells: never in practice)
+    auto chunk_loop = [&](auto mode_tag, int ch, uint32_t wb) {
+        constexpr int MODE = decltype(mode_tag)::value;
+        const int c_end = min(sp.C, (ch + 1) * wp.cchunk);
+#pragma unroll 2
+        for (int c = ch * wp.cchunk; c < c_end; ++c) {
+            const double bu0 = tb.tc0[pc + c], bu1 = tb.tc1[pc + c], rc = tb.r[pc + c];
+            uint32_t a[R];
+            double t0[R], t1[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                int cell0, cell1;
+                if (MODE == 2) {
+                    cell0 = locate_uniform<true>(base0[u] + bu0, n0, t0[u]);
+                    cell1 = locate_uniform<true, true>(base1[u] + bu1, n1, t1[u]);
+                } else if (MODE == 1) {
+                    cell0 = locate_magic_clamp(base0[u] + bu0, n0, t0[u]);
+                    cell1 = locate_magic_clamp(base1[u] + bu1, n1, t1[u]);
+                } else {
+                    cell0 = locate_magic(base0[u] + bu0, t0[u]);
+                    cell1 = locate_magic(base1[u] + bu1, t1[u]);
+                }
+                a[u] = (uint32_t)cell1 * PB + ((uint32_t)cell0 * 8u + wb);
+            }
+            double v00[R], v10[R], v01[R], v11[R];
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                v00[u] = lds_f64(a[u]);
+                v10[u] = lds_f64(a[u] + 8u);
+                v01[u] = lds_f64(a[u] + PB);
+                v11[u] = lds_f64(a[u] + PB + 8u);
+            }
+#pragma unroll
+            for (int u = 0; u < R; ++u) {
+                const double x = fma(t0[u], v10[u] - v00[u], v00[u]);
+                const double y = fma(t0[u], v11[u] - v01[u], v01[u]);
+                const double v = fma(t1[u], y - x, x);
+                const double tot = (gs[u] + rc) + v;
+                if (tot < best[u]) { best[u] = tot; arg[u] = c; }
+            }
+        }
+    };
+
+    for (int ch = 0; ch < wp.nchunks; ++ch) {
+        double lo0, hi0, lo1, hi1;
+        bounds(ch, lo0, hi0, lo1, hi1);
+        const bool interior = lo0 >= 0.0 && hi0 < (double)(n0 - 1) && lo1 >= 0.0 && hi1 < (double)(n1 - 1);
+        int r0, c0;
+        origin(lo0, lo1, r0, c0);
+        const int s = ch % NS;
+        mbar_wait(&mbar[s], (uint32_t)(ch / NS) & 1u);
+        // byte address of window element (cell0 = 0, cell1 = 0); passes through a volatile asm placed after
+        // the wait so that no window load is scheduled above it
+        uint32_t wb = ring_u32 + (uint32_t)(s * wp.buf_doubles) * 8u - ((uint32_t)c0 * PB + (uint32_t)r0 * 8u);
+        asm volatile("" : "+r"(wb)::"memory");
+        const double BIG = 1073741824.0;
+        if (interior) chunk_loop(std::integral_constant<int, 0>{}, ch, wb);
+        else if (lo0 > -BIG && hi0 < BIG && lo1 > -BIG && hi1 < BIG) chunk_loop(std::integral_constant<int, 1>{}, ch, wb);
+        else chunk_loop(std::integral_constant<int, 2>{}, ch, wb);
+        __syncthreads();   // every thread is done with this slot
+        if (tid == 0 && ch + NS < wp.nchunks) issue(ch + NS);
+    }
+
+    if (i_lo + lane < i_hi) {
+        double *jo = sp.J_out + (size_t)prob * sp.S_ext + (long long)(i - d0.ext_lo) * d0.stride +
+                     (long long)(jbase - d1.ext_lo) * d1.stride;
+        const long long io = (long long)prob * sp.S_own + (long long)(i - d0.own_lo) +
+                             (long long)(jbase - d1.own_lo) * d0.own_n;
+#pragma unroll
+        for (int m = 0; m < R; ++m) {
+            if (jbase + m < j_hi) {
+                jo[(long long)m * d1.stride] = best[m];
+                if (IDX32) sp.idx_out[io + (long long)m * d0.own_n] = arg[m];
+                else idx_store(sp.idx_out, sp.idx_bytes, io + (long long)m * d0.own_n, arg[m]);
+            }
+        }
+        if (sp.n_peers) {
+#pragma unroll
+            for (int m = 0; m < R; ++m)
+                if (jbase + m < j_hi) { const int gi[2] = {i, jbase + m}; peer_store<2>(sp, prob, gi, best[m]); }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // k_stage_chain: the CHAIN structure (see k_stage_window) as a kernel of its own for problems with
 // at most MAXC controls (Solver_attitude: 3 torque levels).  Every control's window is in flight
 // from the first instruction (one TMA box per control, one mbarrier), there is no chunk loop, no
@@ -599,6 +804,12 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     const int jcnt = min(R, j_hi - jb);                  // warp-uniform; <= 0 for a ragged last tile
     const double2 *cq = wp.colq + (prob * (uint32_t)n1 + (uint32_t)jb);
     double2 cd = jcnt > 0 ? __ldg(cq) : make_double2(0.0, 0.0);
+    constexpr int PF = OCC == 5 ? 2 : 1;                 // column-table prefetch distance (2 only where registers allow)
+    constexpr bool MAGIC = OCC == 5;                     // experiment: dimension-1 locate without conversion instructions
+    auto locate1 = [&](double g, double &t) -> int {
+        return MAGIC ? locate_magic_clamp(g, n1, t) : locate_uniform<true, true>(g, n1, t);
+    };
+    double2 cd1 = PF == 2 && jcnt > 0 ? __ldg(cq + 1) : make_double2(0.0, 0.0);
     const bool row_ok = i_lo + lane < i_hi;
     const uint32_t sj = (uint32_t)d1.stride, si = (uint32_t)d0.own_n;
     uint32_t jo = prob * (uint32_t)sp.S_ext + (uint32_t)(i - d0.ext_lo) * (uint32_t)d0.stride + (uint32_t)(jb - d1.ext_lo) * sj;
@@ -664,7 +875,7 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     int prev;
     {
         double t1;
-        prev = locate_uniform<true, true>(rp01.y + cd.x, n1, t1) - 1;
+        prev = locate1(rp01.y + cd.x, t1) - 1;
         column((uint32_t)(prev + 1) * pitch, ahi);
     }
     auto finish = [&](int mm, double gs, double t1, const double (&alo)[CC], const double (&a)[CC]) {
@@ -701,14 +912,14 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
         bool bad = false;
         int expect = prev + 1;
         auto step = [&](double (&lower)[CC], double (&upper)[CC]) {
-            const double2 cdn = __ldg(cq + m + 1);                      // next column's tables (colq is padded)
+            const double2 cdn = __ldg(cq + m + PF);                     // a later column's tables (colq is padded)
             double t1;
-            const int cell1 = locate_uniform<true, true>(rp01.y + cd.x, n1, t1);
+            const int cell1 = locate1(rp01.y + cd.x, t1);
             bad = bad || cell1 != expect;
             column((uint32_t)cell1 * pitch + pitch, upper);
             finish(m, qrow + cd.y, t1, lower, upper);
             expect = cell1 + 1;
-            cd = cdn;
+            if (PF == 2) { cd = cd1; cd1 = cdn; } else cd = cdn;
             ++m;
         };
         double bhi[CC];
@@ -727,7 +938,7 @@ k_stage_strip(const __grid_constant__ StageParams sp, const __grid_constant__ Wi
     for (; m < jcnt; ++m) {
         const double2 cdc = __ldg(cq + m);
         double t1, alo[CC];
-        const int cell1 = locate_uniform<true, true>(rp01.y + cdc.x, n1, t1);
+        const int cell1 = locate1(rp01.y + cdc.x, t1);
         column((uint32_t)cell1 * pitch, alo);
         column((uint32_t)cell1 * pitch + pitch, ahi);
         finish(m, qrow + cdc.y, t1, alo, ahi);
@@ -760,6 +971,9 @@ struct WindowState {
     int strip_nw = 4;
     void *d_colq = nullptr;
     int batch = 4, occ = 2, rstates = 8, loc = 0;
+    WideTables *wide = nullptr;     // k_stage_wide: host copy of the constant-bank control tables (null = not used)
+    int wide_ns = 2;
+    size_t wide_smem = 0;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
 
@@ -882,8 +1096,28 @@ static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const C
         default: return strip_go<4, 4, 7>(ws, sp, map, grid, st, sa);
     }
 }
+template <int NS>
+static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid, cudaStream_t st,
+                    bool set_attr_only) {
+    auto f48 = k_stage_wide<NS, 48, true>, f48n = k_stage_wide<NS, 48, false>;
+    auto f0 = k_stage_wide<NS, 0, true>, f0n = k_stage_wide<NS, 0, false>;
+    if (set_attr_only) {
+        for (const void *f : {(const void *)f48, (const void *)f48n, (const void *)f0, (const void *)f0n})
+            if (!raise_smem_limit(f, ws->wide_smem)) return false;
+        return true;
+    }
+    const bool i32 = sp->idx_bytes == 4;
+    if (ws->wp.win0 == 48) (i32 ? f48 : f48n)<<<grid, WIDE_NT, ws->wide_smem, st>>>(*sp, ws->wp, *map, *ws->wide);
+    else (i32 ? f0 : f0n)<<<grid, WIDE_NT, ws->wide_smem, st>>>(*sp, ws->wp, *map, *ws->wide);
+    return true;
+}
+static bool wide_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
+                          cudaStream_t st, bool sa) {
+    return ws->wide_ns == 3 ? wide_go<3>(ws, sp, map, grid, st, sa) : wide_go<2>(ws, sp, map, grid, st, sa);
+}
 static void window_teardown_state(WindowState *ws) {
     cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp); cudaFree(ws->d_colq);
+    delete ws->wide;
     delete ws;
 }
 
@@ -963,8 +1197,12 @@ void window_setup(bellman_handle *h) {
         strip_r = 16;   // many waves even with 32 x 64 tiles: longer strips amortise the per-thread prologue (measured +2 %)
     const int wt1 = strip_cfg ? strip_nw * strip_r : tile1_of(rstates);
 
+    // k_stage_wide (one 512-thread CTA per SM) takes the long-control-loop problems whose control tables fit
+    // its constant-bank parameter; it may use the whole shared memory of an SM for its two ring slots
+    const bool wide_cfg = hp.has_c[0] && hp.has_c[1] && !chain_cfg && rstates == 8 &&
+                          (long long)hp.P * hp.C <= WIDE_MAXC && !std::getenv("BELLMAN_NO_WIDE");
     // pick the chunk size: most updates per staged byte among configs that keep two CTAs per SM
-    const size_t budget2 = 110 * 1024, budget1 = 220 * 1024;
+    const size_t budget2 = wide_cfg ? 220 * 1024 : 110 * 1024, budget1 = 220 * 1024;
     int best_cc = 0, best_w0 = 0, best_w1 = 0;
     double best_score = -1.0;
     std::vector<int> cands;
@@ -1080,7 +1318,7 @@ void window_setup(bellman_handle *h) {
         wp.colpack = static_cast<const double4 *>(ws->d_colp);
         wp.col0_zero = colz[0] ? 1 : 0;
         wp.col1_zero = colz[1] ? 1 : 0;
-        std::vector<double> colq((size_t)hp.P * hp.n[1] * 2 + 2, 0.0);   // +1 entry: the strip kernel prefetches one ahead
+        std::vector<double> colq((size_t)hp.P * hp.n[1] * 2 + 4, 0.0);   // +2 entries: the strip kernel prefetches up to two ahead
         for (size_t k = 0; k < (size_t)hp.P * hp.n[1]; ++k) { colq[2 * k] = colp[4 * k + 1]; colq[2 * k + 1] = colp[4 * k + 2]; }
         if (!upload(colq, &ws->d_colq)) { window_teardown_state(ws); return; }
         wp.colq = static_cast<const double2 *>(ws->d_colq);
@@ -1162,6 +1400,22 @@ void window_setup(bellman_handle *h) {
             ws->lean = false;
     }
     if (!ws->hc0 && !ws->hc1) { window_teardown_state(ws); return; }   // no control dependence at all: nothing to stage for
+    // k_stage_wide takes the long-control-loop problems whose control tables fit its constant-bank parameter
+    if (wide_cfg && !ws->strip && !ws->lean) {
+        ws->wide_ns = std::getenv("BELLMAN_WIDE_NS") && std::atoi(std::getenv("BELLMAN_WIDE_NS")) == 3 ? 3 : 2;
+        if ((size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1) > 225 * 1024) ws->wide_ns = 2;
+        ws->wide_smem = (size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1);
+        if (ws->wide_smem <= 225 * 1024) {
+            ws->wide = new WideTables();
+            std::memset(ws->wide, 0, sizeof(WideTables));
+            for (size_t k = 0; k < (size_t)hp.P * hp.C; ++k) {
+                ws->wide->tc0[k] = hp.Tc[0][k];
+                ws->wide->tc1[k] = hp.Tc[1][k];
+                ws->wide->r[k] = hp.r[k];
+            }
+            if (!wide_dispatch(ws, nullptr, nullptr, dim3(), nullptr, true)) { delete ws->wide; ws->wide = nullptr; }
+        }
+    }
     h->wstate = ws;
     h->wcfg.tile0 = WT0; h->wcfg.tile1 = wt1; h->wcfg.cchunk = wp.cchunk;
     h->wcfg.win0 = wp.win0; h->wcfg.win1 = wp.win1;
@@ -1178,7 +1432,8 @@ void window_teardown(bellman_handle *h) {
 const char *window_variant(const bellman_handle *h) {
     auto *ws = static_cast<const WindowState *>(h->wstate);
     if (!ws) return "window";
-    return ws->strip ? "window:strip" : ws->lean ? "window:chain" : ws->chain ? "window:ring-chain" : "window:ring";
+    return ws->strip ? "window:strip" : ws->lean ? "window:chain" : ws->wide ? "window:wide" :
+           ws->chain ? "window:ring-chain" : "window:ring";
 }
 
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st) {
@@ -1192,6 +1447,7 @@ cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, i
         strip_dispatch(ws, &sp, &map, g3, st, false);
     }
     else if (ws->lean) k_stage_chain<4, 4><<<grid, WNT, ws->lean_smem, st>>>(sp, wp, map);
+    else if (ws->wide) wide_dispatch(ws, &sp, &map, grid, st, false);
     else window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
     return cudaGetLastError();
 }

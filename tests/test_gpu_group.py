@@ -49,7 +49,7 @@ def _check(bellman, oracle_lib, d, n_slabs, part_dim, kernel, n_stages=5, part_c
 @pytest.mark.parametrize("kernel", ["direct", "staged"])
 def test_group_kirk(bellman, oracle_lib, n_slabs, part_dim, kernel):
     d = _kirk(bellman)
-    _check(bellman, oracle_lib, d, n_slabs, part_dim, kernel, want="window:ring" if kernel == "staged" else "direct")
+    _check(bellman, oracle_lib, d, n_slabs, part_dim, kernel, want="window:wide" if kernel == "staged" else "direct")
 
 
 def test_group_kirk_odd_leading_dimension_and_uneven_cuts(bellman, oracle_lib):
@@ -126,7 +126,7 @@ def test_handles_with_different_window_sizes_coexist(bellman, oracle_lib):
     o = bellman.Dynamic_Solver()
     small = bellman.tables.kirk_desc(o.A, o.B, o.Q, o.R, 6, o.x_min, o.x_max, 96, o.u_min, o.u_max, 24,
                                      store_J_all=False, store_idx_all=False)
-    _check(bellman, oracle_lib, small, 2, None, "staged", n_stages=3, want="window:ring")
+    _check(bellman, oracle_lib, small, 2, None, "staged", n_stages=3, want="window:wide")
     big = _kirk(bellman, n0=512, n1=384, C=64)
     a = bellman.Sweep(big)
     b = bellman.Sweep(small)          # created later, plans a smaller window for the same kernel

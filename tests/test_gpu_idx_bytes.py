@@ -23,7 +23,7 @@ def _cases(bellman):
 def test_every_stage_kernel_with_narrow_idx(bellman, oracle_lib, monkeypatch, idx_bytes):
     kirk, att, pa = _cases(bellman)
     runs = [("direct", kirk, dict(kernel=1), "direct"), ("splitc", kirk, dict(kernel=3), "splitc"),
-            ("persistent", kirk, dict(use_graph=True), "persistent"), ("ring", kirk, dict(kernel=2), "window:ring"),
+            ("persistent", kirk, dict(use_graph=True), "persistent"), ("wide", kirk, dict(kernel=2), "window:wide"),
             ("strip", att, dict(kernel=2), "window:strip"), ("stream", pa, dict(kernel=4), "stream")]
     for name, d, kw, want in runs:
         ora = oracle_lib.sweep(d, n_stages=4)
@@ -37,7 +37,8 @@ def test_every_stage_kernel_with_narrow_idx(bellman, oracle_lib, monkeypatch, id
             assert np.array_equal(Ip, ora["idx_last"][d.P - 1][pts]) and np.array_equal(Jp, ora["J_last"][d.P - 1][pts])
     monkeypatch.setenv("BELLMAN_NO_STREAM", "1")
     monkeypatch.setenv("BELLMAN_WIN_NOSTRIP", "1")
-    for name, d, want in (("tile", pa, "tile"), ("chain", att, "window:chain")):
+    monkeypatch.setenv("BELLMAN_NO_WIDE", "1")
+    for name, d, want in (("tile", pa, "tile"), ("chain", att, "window:chain"), ("ring", kirk, "window:ring")):
         ora = oracle_lib.sweep(d, n_stages=3)
         with bellman.Sweep(d, idx_bytes=idx_bytes) as sw:
             sw.run(3, kernel=2)

@@ -82,9 +82,24 @@ def test_kirk_reference_size_first_stages(bellman, oracle_lib, kernel):
     sw.close()
 
 
+WINDOW_VARIANTS = ["wide", "ring", "wide3"]   # k_stage_wide (default), k_stage_window, 3-slot ring
+
+
+def _window_variant(monkeypatch, variant):
+    """Selects the long-control-loop window kernel; returns the name bellman_last_kernel must report."""
+    if variant == "ring":
+        monkeypatch.setenv("BELLMAN_NO_WIDE", "1")
+        return "window:ring"
+    if variant == "wide3":
+        monkeypatch.setenv("BELLMAN_WIDE_NS", "3")
+    return "window:wide"
+
+
+@pytest.mark.parametrize("variant", WINDOW_VARIANTS)
 @pytest.mark.parametrize("shape", [(256, 192, 64), (130, 70, 33), (64, 64, 1), (34, 1000, 9)])
-def test_window_kernel_random_terminal_cost(bellman, oracle_lib, shape):
+def test_window_kernel_random_terminal_cost(bellman, oracle_lib, monkeypatch, shape, variant):
     """TMA-staged kernel: ragged tiles, chunk tails, rough J_N, several stages (ping-pong buffers)."""
+    want = _window_variant(monkeypatch, variant)
     n0, n1, C = shape
     rng = np.random.default_rng(5)
     t = bellman.tables
@@ -100,7 +115,7 @@ def test_window_kernel_random_terminal_cost(bellman, oracle_lib, shape):
     sw = bellman.Sweep(d)
     sw.set_J(JN)
     sw.run(4, kernel=KERNELS["window"])
-    assert sw.last_kernel.split(":")[0] == "window"
+    assert sw.last_kernel == want
     ora = oracle_lib.sweep(d, n_stages=4, J_N=JN)
     assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], f"window {shape}")
     sw.close()
@@ -245,10 +260,12 @@ def test_exact_ties_pick_first_index(bellman, oracle_lib):
         sw.close()
 
 
-def test_kirk_scaled_full_size_spot_check(bellman, oracle_lib):
+@pytest.mark.parametrize("variant", ["wide", "ring"])
+def test_kirk_scaled_full_size_spot_check(bellman, oracle_lib, monkeypatch, variant):
     """config 4 (8192 x 8192 x 512): one stage from a seeded smooth+rough J_N at full size, checked
     on 100k sampled states against the oracle's pointwise evaluator, plus size-independent
     properties: every argmin is a valid index and J_k = tot(argmin) exactly."""
+    want = _window_variant(monkeypatch, variant)
     obj = bellman.Dynamic_Solver()
     obj.dx, obj.du, obj.N = 8192, 512, 200
     obj.store_J_star = False
@@ -261,6 +278,7 @@ def test_kirk_scaled_full_size_spot_check(bellman, oracle_lib):
     sw = bellman.Sweep(d)
     sw.set_J(JN.reshape(1, -1))
     sw.run(1)
+    assert sw.last_kernel == want
     Jg, Ig = sw.get_J()[0], sw.get_idx()[0]
     assert Ig.min() >= 0 and Ig.max() < 512
     pts = rng.integers(0, d.S, size=100_000)
@@ -317,9 +335,11 @@ def test_resume_from_saved_stage(bellman, oracle_lib):
     a.close(); b.close()
 
 
-def test_window_kernel_multi_stage_medium(bellman, oracle_lib):
+@pytest.mark.parametrize("variant", WINDOW_VARIANTS)
+def test_window_kernel_multi_stage_medium(bellman, oracle_lib, monkeypatch, variant):
     """TMA-staged kernel over several stages on a grid with many tiles (1024 x 768 x 64): complete
     comparison of J and argmin with the oracle."""
+    want = _window_variant(monkeypatch, variant)
     obj = bellman.Dynamic_Solver()
     t = bellman.tables
     n0, n1, C = 1024, 768, 64
@@ -331,7 +351,7 @@ def test_window_kernel_multi_stage_medium(bellman, oracle_lib):
                Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
                q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u)).validate()
     sw = bellman.Sweep(d).run(3)
-    assert sw.last_kernel.split(":")[0] == "window"
+    assert sw.last_kernel == want
     ora = oracle_lib.sweep(d, n_stages=3)
     assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "window 1024x768x64")
     sw.close()
