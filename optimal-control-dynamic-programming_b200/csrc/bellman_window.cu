@@ -405,7 +405,7 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
 //   * shared-memory addresses are 32-bit (two IMADs per update).
 // One CTA per SM (16 warps), NS ring slots.
 // ---------------------------------------------------------------------------------------------
-constexpr int WIDE_NT = 512, WIDE_R = 4, WIDE_MAXC = 512;
+constexpr int WIDE_NT = 512, WIDE_R = 4, WIDE_MAXC = 512, WIDE_MAXCH = 128;
 struct WideTables {
     double tc0[WIDE_MAXC], tc1[WIDE_MAXC], r[WIDE_MAXC];   // [P * C] each
 };
@@ -417,7 +417,7 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     constexpr int R = WIDE_R, WT1 = (WIDE_NT / 32) * R;
     extern __shared__ __align__(128) double ring[];
     __shared__ __align__(8) uint64_t mbar[NS];
-    __shared__ double tmm_s[8];
+    __shared__ int4 cinfo[WIDE_MAXCH];
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int prob = blockIdx.y;
@@ -436,43 +436,42 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
         for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (tid < 8) {
+    // Chunk table, one entry per chunk, built once per CTA by the first nchunks threads: the window origin
+    // (TMA coordinates and element offset) and how the chunk's queries may be located.  The bounds are exact:
+    // per-tile / per-chunk table extrema summed with the kernel's own association (as k_stage_window).
+    //   mode 0: every query falls in an interior cell (no clamp); 1: clamped, |g| < 2^30 (no conversion
+    //   instructions); 2: clamped, conversion pipe (queries beyond 2^30 cells: never in practice)
+    if (tid < wp.nchunks) {
         const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
-        const int d = tid >> 2, ab = (tid >> 1) & 1, mx = tid & 1;
-        const DimParams &dd = d == 0 ? d0 : d1;
-        double v = 0.0;
-        if (!(ab == 1 && !dd.Tb)) {
+        auto tmm_load = [&](int k) -> double {
+            const int d = k >> 2, ab = (k >> 1) & 1, mx = k & 1;
+            const DimParams &dd = d == 0 ? d0 : d1;
+            if (ab == 1 && !dd.Tb) return 0.0;
             const int src = ab == 0 ? dd.src_a : dd.src_b;
-            v = __ldg(tm + wp.tmm_off[d][ab] + 2 * (src == 0 ? ti : tj) + mx);
-        }
-        tmm_s[tid] = v;
+            return __ldg(tm + wp.tmm_off[d][ab] + 2 * (src == 0 ? ti : tj) + mx);
+        };
+        double lo0 = tmm_load(0), hi0 = tmm_load(1), lo1 = tmm_load(4), hi1 = tmm_load(5);
+        if (d0.Tb) { lo0 = lo0 + tmm_load(2); hi0 = hi0 + tmm_load(3); }
+        if (d1.Tb) { lo1 = lo1 + tmm_load(6); hi1 = hi1 + tmm_load(7); }
+        lo0 = lo0 + __ldg(cmm + 4 * tid); hi0 = hi0 + __ldg(cmm + 4 * tid + 1);
+        lo1 = lo1 + __ldg(cmm + 4 * tid + 2); hi1 = hi1 + __ldg(cmm + 4 * tid + 3);
+        int r0 = cell_uniform(lo0, n0);
+        r0 -= (r0 - d0.ext_lo) & 1;                  // TMA: even innermost coordinate
+        const int c0 = cell_uniform(lo1, n1);
+        const double BIG = 1073741824.0;
+        const bool interior = lo0 >= 0.0 && hi0 < (double)(n0 - 1) && lo1 >= 0.0 && hi1 < (double)(n1 - 1);
+        const bool small = lo0 > -BIG && hi0 < BIG && lo1 > -BIG && hi1 < BIG;
+        cinfo[tid] = make_int4(r0 - d0.ext_lo, c0 - d1.ext_lo, c0 * (W0C ? W0C : wp.win0) + r0, interior ? 0 : small ? 1 : 2);
     }
     __syncthreads();
 
-    // exact bounds of chunk ch's queries, formed with the kernel's own association (as k_stage_window)
-    auto bounds = [&](int ch, double &lo0, double &hi0, double &lo1, double &hi1) {
-        lo0 = tmm_s[0]; hi0 = tmm_s[1]; lo1 = tmm_s[4]; hi1 = tmm_s[5];
-        if (d0.Tb) { lo0 = lo0 + tmm_s[2]; hi0 = hi0 + tmm_s[3]; }
-        if (d1.Tb) { lo1 = lo1 + tmm_s[6]; hi1 = hi1 + tmm_s[7]; }
-        lo0 = lo0 + __ldg(cmm + 4 * ch); hi0 = hi0 + __ldg(cmm + 4 * ch + 1);
-        lo1 = lo1 + __ldg(cmm + 4 * ch + 2); hi1 = hi1 + __ldg(cmm + 4 * ch + 3);
-    };
-    auto origin = [&](double lo0, double lo1, int &r0, int &c0) {
-        r0 = cell_uniform(lo0, n0);
-        r0 -= (r0 - d0.ext_lo) & 1;                  // TMA: even innermost coordinate
-        c0 = cell_uniform(lo1, n1);
-    };
     auto issue = [&](int ch) {   // thread 0 only
-        double lo0, hi0, lo1, hi1;
-        bounds(ch, lo0, hi0, lo1, hi1);
-        int r0, c0;
-        origin(lo0, lo1, r0, c0);
+        const int4 ci = cinfo[ch];
         const int s = ch % NS;
         mbar_expect_tx(&mbar[s], win_bytes);
         double *dst = ring + s * wp.buf_doubles;
         for (int b = 0; b < wp.boxes; ++b)
-            tma_load_3d(dst + (size_t)b * wp.box1 * wp.win0, &tmap, &mbar[s], r0 - d0.ext_lo,
-                        c0 - d1.ext_lo + b * wp.box1, prob);
+            tma_load_3d(dst + (size_t)b * wp.box1 * wp.win0, &tmap, &mbar[s], ci.x, ci.y + b * wp.box1, prob);
     };
     if (tid == 0)
         for (int ch = 0; ch < NS && ch < wp.nchunks; ++ch) issue(ch);
@@ -546,20 +545,15 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     };
 
     for (int ch = 0; ch < wp.nchunks; ++ch) {
-        double lo0, hi0, lo1, hi1;
-        bounds(ch, lo0, hi0, lo1, hi1);
-        const bool interior = lo0 >= 0.0 && hi0 < (double)(n0 - 1) && lo1 >= 0.0 && hi1 < (double)(n1 - 1);
-        int r0, c0;
-        origin(lo0, lo1, r0, c0);
+        const int4 ci = cinfo[ch];
         const int s = ch % NS;
         mbar_wait(&mbar[s], (uint32_t)(ch / NS) & 1u);
         // byte address of window element (cell0 = 0, cell1 = 0); passes through a volatile asm placed after
         // the wait so that no window load is scheduled above it
-        uint32_t wb = ring_u32 + (uint32_t)(s * wp.buf_doubles) * 8u - ((uint32_t)c0 * PB + (uint32_t)r0 * 8u);
+        uint32_t wb = ring_u32 + (uint32_t)(s * wp.buf_doubles) * 8u - (uint32_t)ci.z * 8u;
         asm volatile("" : "+r"(wb)::"memory");
-        const double BIG = 1073741824.0;
-        if (interior) chunk_loop(std::integral_constant<int, 0>{}, ch, wb);
-        else if (lo0 > -BIG && hi0 < BIG && lo1 > -BIG && hi1 < BIG) chunk_loop(std::integral_constant<int, 1>{}, ch, wb);
+        if (ci.w == 0) chunk_loop(std::integral_constant<int, 0>{}, ch, wb);
+        else if (ci.w == 1) chunk_loop(std::integral_constant<int, 1>{}, ch, wb);
         else chunk_loop(std::integral_constant<int, 2>{}, ch, wb);
         __syncthreads();   // every thread is done with this slot
         if (tid == 0 && ch + NS < wp.nchunks) issue(ch + NS);
@@ -1201,6 +1195,7 @@ void window_setup(bellman_handle *h) {
     // its constant-bank parameter; it may use the whole shared memory of an SM for its two ring slots
     const bool wide_cfg = hp.has_c[0] && hp.has_c[1] && !chain_cfg && rstates == 8 &&
                           (long long)hp.P * hp.C <= WIDE_MAXC && !std::getenv("BELLMAN_NO_WIDE");
+    // (chunks of 1..3 controls are not offered to it: its per-CTA chunk table holds WIDE_MAXCH entries)
     // pick the chunk size: most updates per staged byte among configs that keep two CTAs per SM
     const size_t budget2 = wide_cfg ? 220 * 1024 : 110 * 1024, budget1 = 220 * 1024;
     int best_cc = 0, best_w0 = 0, best_w1 = 0;
@@ -1209,7 +1204,7 @@ void window_setup(bellman_handle *h) {
     if (lean_cfg) {
         cands.push_back(1);                       // k_stage_chain: one window per control, all in flight
     } else {
-        for (int cc : {1, 2, 3, 4, 6, 8, 12, 16, 24, 32})
+        for (int cc : {1, 2, 3, 4, 6, 8, 12, 16, 20, 24, 26, 28, 32})
             if (cc <= hp.C) cands.push_back(cc);
         if (hp.C <= 32 && std::find(cands.begin(), cands.end(), hp.C) == cands.end()) cands.push_back(hp.C);
         if (const char *e = std::getenv("BELLMAN_WIN_CC")) { cands.clear(); cands.push_back(std::max(1, std::min(hp.C, std::atoi(e)))); }
@@ -1401,7 +1396,7 @@ void window_setup(bellman_handle *h) {
     }
     if (!ws->hc0 && !ws->hc1) { window_teardown_state(ws); return; }   // no control dependence at all: nothing to stage for
     // k_stage_wide takes the long-control-loop problems whose control tables fit its constant-bank parameter
-    if (wide_cfg && !ws->strip && !ws->lean) {
+    if (wide_cfg && !ws->strip && !ws->lean && wp.nchunks <= WIDE_MAXCH) {
         ws->wide_ns = std::getenv("BELLMAN_WIDE_NS") && std::atoi(std::getenv("BELLMAN_WIDE_NS")) == 3 ? 3 : 2;
         if ((size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1) > 225 * 1024) ws->wide_ns = 2;
         ws->wide_smem = (size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1);

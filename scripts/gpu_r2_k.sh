@@ -11,7 +11,7 @@ tail -n 5 gpurun_out/k_pytest.log
 if [ $rc -ne 0 ]; then echo "tests failed rc=$rc"; exit 1; fi
 B="python bench.py --no-cpu-baseline --no-e2e --no-others --steps 10 --warmup 3"
 : > gpurun_out/k_bench.log
-for cc in default 8 12 16 24 32; do
+for cc in default 16 20 24 26 28; do
   echo "== kirk wide cc=$cc" >> gpurun_out/k_bench.log
   if [ $cc = default ]; then timeout 300 $B >> gpurun_out/k_bench.log 2>&1
   else BELLMAN_WIN_CC=$cc timeout 300 $B >> gpurun_out/k_bench.log 2>&1; fi

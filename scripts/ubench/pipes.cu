@@ -34,6 +34,12 @@ __global__ void k(double *out, const double *in, int *iout, long long *cyc) {
                            int c = __double2int_rd(x + a[u]); a[u] = y - (double)c; q[u] += c; }                        // 2 LDS + F2I + I2F + 2 DADD
             if (T == 13) { a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; q[u] += __double2int_rd(a[u]); }      // 3 DADD + F2I
             if (T == 14) { a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] += sm[(threadIdx.x & 31) + ((q[u] >> 5) & 127) * 32]; q[u] += 7; }  // 4 DADD + LDS
+            if (T == 16) { a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1;
+                           const int o = (threadIdx.x & 31) + ((q[u] >> 5) & 63) * 32; a[u] += sm[o]; a[u] += sm[o + 2048]; q[u] += 7; }  // 9 DADD + 2 LDS.64
+            if (T == 17) { a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1;
+                           const double2 v = reinterpret_cast<const double2 *>(sm)[(threadIdx.x & 31) + ((q[u] >> 5) & 63) * 32]; a[u] += v.x; a[u] += v.y; q[u] += 7; }  // 9 DADD + 1 LDS.128
+            if (T == 18) { a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; a[u] = a[u] + c2; a[u] = a[u] + c1; q[u] += 7; }  // 9 DADD
+            if (T == 19) { const double2 v = reinterpret_cast<const double2 *>(sm)[(threadIdx.x & 31) + ((q[u] >> 5) & 63) * 32]; q[u] += __double2loint(v.x) + __double2loint(v.y); }  // LDS.128 alone
             if (T == 15) { int c = __double2int_rd(a[u]); a[u] = a[u] - (double)c; q[u] += c; }                         // F2I + I2F + DADD
         }
     }
@@ -59,6 +65,7 @@ int main() {
     for (int w : {8, 16}) {
         run<10>("LDS.64 conflict-free + IADD", w, 2); run<11>("LDS.64 + F2I", w, 2); run<12>("2 LDS + F2I + I2F + 2 DADD", w, 6);
         run<13>("3 DADD + F2I", w, 4); run<14>("4 DADD + LDS", w, 5); run<15>("F2I + I2F + DADD", w, 3);
+        run<18>("9 DADD", w, 9); run<16>("9 DADD + 2 LDS.64", w, 11); run<17>("9 DADD + 1 LDS.128", w, 10); run<19>("LDS.128 conflict-free", w, 1);
         printf("\n");
     }
     return 0;
