@@ -84,6 +84,31 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// bounded wait (traps instead of hanging if a phase never completes) and plain arrive
+__device__ __forceinline__ uint32_t mbar_try_hint(uint32_t addr, uint32_t parity) {
+    uint32_t done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    return done;
+}
+__device__ __noinline__ void mbar_wait_slow_w(uint32_t addr, uint32_t parity) {
+    for (uint32_t spins = 0; !mbar_try_hint(addr, parity); ++spins)
+        if (spins > (1u << 22)) asm volatile("trap;");
+}
+__device__ __forceinline__ void mbar_wait_bounded(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    if (!mbar_try_hint(addr, parity)) mbar_wait_slow_w(addr, parity);
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void tma_load_3d(void *dst, const CUtensorMap *map, uint64_t *bar, int x, int y,
                                             int z) {
     asm volatile(
@@ -410,13 +435,17 @@ struct WideTables {
     double tc0[WIDE_MAXC], tc1[WIDE_MAXC], r[WIDE_MAXC];   // [P * C] each
 };
 
-template <int NS, int W0C, bool IDX32>
+// BAR: a CTA barrier ends every chunk (all 16 warps drain and refill their pipelines together).  Otherwise
+// the slot is handed back through an `empty` mbarrier (one arrival per warp) and the warp whose turn it is
+// (chunk index mod 16) waits for it and issues the refill, so the other warps run on into the next chunk
+// and their pipeline bubbles no longer coincide.
+template <int NS, int W0C, bool IDX32, bool BAR>
 __global__ void __launch_bounds__(WIDE_NT, 1)
 k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
              const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WideTables tb) {
     constexpr int R = WIDE_R, WT1 = (WIDE_NT / 32) * R;
     extern __shared__ __align__(128) double ring[];
-    __shared__ __align__(8) uint64_t mbar[NS];
+    __shared__ __align__(8) uint64_t mbar[NS], empty[NS];
     __shared__ int4 cinfo[WIDE_MAXCH];
 
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
@@ -433,7 +462,7 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
 
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < NS; ++s) mbar_init(&mbar[s], 1);
+        for (int s = 0; s < NS; ++s) { mbar_init(&mbar[s], 1); mbar_init(&empty[s], WIDE_NT / 32); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     // Chunk table, one entry per chunk, built once per CTA by the first nchunks threads: the window origin
@@ -547,7 +576,7 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     for (int ch = 0; ch < wp.nchunks; ++ch) {
         const int4 ci = cinfo[ch];
         const int s = ch % NS;
-        mbar_wait(&mbar[s], (uint32_t)(ch / NS) & 1u);
+        mbar_wait_bounded(&mbar[s], (uint32_t)(ch / NS) & 1u);
         // byte address of window element (cell0 = 0, cell1 = 0); passes through a volatile asm placed after
         // the wait so that no window load is scheduled above it
         uint32_t wb = ring_u32 + (uint32_t)(s * wp.buf_doubles) * 8u - (uint32_t)ci.z * 8u;
@@ -555,8 +584,20 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
         if (ci.w == 0) chunk_loop(std::integral_constant<int, 0>{}, ch, wb);
         else if (ci.w == 1) chunk_loop(std::integral_constant<int, 1>{}, ch, wb);
         else chunk_loop(std::integral_constant<int, 2>{}, ch, wb);
-        __syncthreads();   // every thread is done with this slot
-        if (tid == 0 && ch + NS < wp.nchunks) issue(ch + NS);
+        if (BAR) {
+            __syncthreads();   // every thread is done with this slot
+            if (tid == 0 && ch + NS < wp.nchunks) issue(ch + NS);
+        } else if (ch + NS < wp.nchunks) {
+            __syncwarp();      // every lane's window loads of this chunk have returned (their values were consumed)
+            if (lane == 0) {
+                mbar_arrive(&empty[s]);
+                if (wrp == (ch & (WIDE_NT / 32 - 1))) {
+                    mbar_wait_bounded(&empty[s], (uint32_t)(ch / NS) & 1u);
+                    issue(ch + NS);
+                }
+            }
+            __syncwarp();
+        }
     }
 
     if (i_lo + lane < i_hi) {
@@ -966,7 +1007,8 @@ struct WindowState {
     void *d_colq = nullptr;
     int batch = 4, occ = 2, rstates = 8, loc = 0;
     WideTables *wide = nullptr;     // k_stage_wide: host copy of the constant-bank control tables (null = not used)
-    int wide_ns = 2;
+    int wide_ns = 2;                // ring slots
+    bool wide_bar = false;          // BELLMAN_WIDE_BARRIER=1: a CTA barrier per chunk instead of the empty-slot mbarriers
     size_t wide_smem = 0;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
 };
@@ -1090,11 +1132,11 @@ static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const C
         default: return strip_go<4, 4, 7>(ws, sp, map, grid, st, sa);
     }
 }
-template <int NS>
+template <bool BAR>
 static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid, cudaStream_t st,
                     bool set_attr_only) {
-    auto f48 = k_stage_wide<NS, 48, true>, f48n = k_stage_wide<NS, 48, false>;
-    auto f0 = k_stage_wide<NS, 0, true>, f0n = k_stage_wide<NS, 0, false>;
+    auto f48 = k_stage_wide<2, 48, true, BAR>, f48n = k_stage_wide<2, 48, false, BAR>;
+    auto f0 = k_stage_wide<2, 0, true, BAR>, f0n = k_stage_wide<2, 0, false, BAR>;
     if (set_attr_only) {
         for (const void *f : {(const void *)f48, (const void *)f48n, (const void *)f0, (const void *)f0n})
             if (!raise_smem_limit(f, ws->wide_smem)) return false;
@@ -1107,7 +1149,7 @@ static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensor
 }
 static bool wide_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                           cudaStream_t st, bool sa) {
-    return ws->wide_ns == 3 ? wide_go<3>(ws, sp, map, grid, st, sa) : wide_go<2>(ws, sp, map, grid, st, sa);
+    return ws->wide_bar ? wide_go<true>(ws, sp, map, grid, st, sa) : wide_go<false>(ws, sp, map, grid, st, sa);
 }
 static void window_teardown_state(WindowState *ws) {
     cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp); cudaFree(ws->d_colq);
@@ -1397,8 +1439,7 @@ void window_setup(bellman_handle *h) {
     if (!ws->hc0 && !ws->hc1) { window_teardown_state(ws); return; }   // no control dependence at all: nothing to stage for
     // k_stage_wide takes the long-control-loop problems whose control tables fit its constant-bank parameter
     if (wide_cfg && !ws->strip && !ws->lean && wp.nchunks <= WIDE_MAXCH) {
-        ws->wide_ns = std::getenv("BELLMAN_WIDE_NS") && std::atoi(std::getenv("BELLMAN_WIDE_NS")) == 3 ? 3 : 2;
-        if ((size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1) > 225 * 1024) ws->wide_ns = 2;
+        ws->wide_bar = std::getenv("BELLMAN_WIDE_BARRIER") != nullptr;
         ws->wide_smem = (size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1);
         if (ws->wide_smem <= 225 * 1024) {
             ws->wide = new WideTables();

@@ -82,7 +82,7 @@ def test_kirk_reference_size_first_stages(bellman, oracle_lib, kernel):
     sw.close()
 
 
-WINDOW_VARIANTS = ["wide", "ring", "wide3"]   # k_stage_wide (default), k_stage_window, 3-slot ring
+WINDOW_VARIANTS = ["wide", "ring", "wide_bar"]   # k_stage_wide (default), k_stage_window, k_stage_wide with a CTA barrier per chunk
 
 
 def _window_variant(monkeypatch, variant):
@@ -90,8 +90,8 @@ def _window_variant(monkeypatch, variant):
     if variant == "ring":
         monkeypatch.setenv("BELLMAN_NO_WIDE", "1")
         return "window:ring"
-    if variant == "wide3":
-        monkeypatch.setenv("BELLMAN_WIDE_NS", "3")
+    if variant == "wide_bar":
+        monkeypatch.setenv("BELLMAN_WIDE_BARRIER", "1")
     return "window:wide"
 
 
