@@ -37,13 +37,16 @@ def main():
     sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 20, 6, 6, 9
     pa = sp.channel_desc(0)
     ok = True
-    ok &= check("window ring (Kirk)", kirk, 3, bb.KERNEL_WINDOW, "window:wide", JN=rng.normal(size=(1, kirk.S)))
+    ok &= check("window wide (Kirk)", kirk, 3, bb.KERNEL_WINDOW, "window:wide", JN=rng.normal(size=(1, kirk.S)))
+    os.environ["BELLMAN_NO_WIDE"] = "1"
+    ok &= check("window ring (Kirk)", kirk, 3, bb.KERNEL_WINDOW, "window:ring", JN=rng.normal(size=(1, kirk.S)))
+    del os.environ["BELLMAN_NO_WIDE"]
     ok &= check("strip (attitude)", att, 3, bb.KERNEL_WINDOW, "window:strip")
     ok &= check("stream (pos-att)", pa, 3, bb.KERNEL_TILE, "stream", JN=rng.normal(size=(1, pa.S)))
     os.environ["BELLMAN_NO_STREAM"] = "1"
     ok &= check("tile (pos-att)", pa, 2, bb.KERNEL_TILE, "tile")
     del os.environ["BELLMAN_NO_STREAM"]
-    ok &= check("group x2 window ring", kirk, 3, bb.KERNEL_WINDOW, "window:wide", group=2)
+    ok &= check("group x2 window wide", kirk, 3, bb.KERNEL_WINDOW, "window:wide", group=2)
     ok &= check("group x2 stream", pa, 3, bb.KERNEL_TILE, "stream", group=2)
     ok &= check("persistent (position-like)", kirk, 5, bb.KERNEL_AUTO, "splitc")
     print("SANITIZE_SMALL", "PASS" if ok else "FAIL", flush=True)
