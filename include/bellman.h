@@ -206,6 +206,19 @@ int  bellman_set_J(bellman_handle *h, const double *J_host /*[P][S] global, NULL
  * with bellman_run, or the policy queried with bellman_policy_lookup (Solver_pos_att.m:849-882). */
 int  bellman_set_stage(bellman_handle *h, int32_t stage, const double *J_host, const int32_t *idx_host);
 int  bellman_stage(bellman_handle *h);                      /* one backward stage, default opts */
+/* One backward stage driven from HOST buffers, with the copies overlapped with the kernel: equivalent to
+ *   bellman_set_J(h, J_next_host); bellman_run(h, 1, opts); bellman_get_J(h, N-1, J_out_host);
+ *   bellman_get_idx(h, N-1, idx_out_host)
+ * (the per-stage host round trip of a MATLAB loop that keeps F.Values on the host, Dynamic_Solver.m:86-102),
+ * same results bit for bit.  J_next_host NULL = continue from the J already on the device (plain
+ * bellman_run(1) + the two reads); J_out_host / idx_out_host may be NULL.  Where the stage kernel can run a
+ * range of tiles (k_stage_wide: D = 2, P = 1, one rank, int32 indices) the grid is processed in 8 slabs of
+ * dimension 1: J_{k+1} goes up in column chunks, a slab starts as soon as the highest column it can query
+ * has arrived (exact reach analysis), and finished slabs go down while later ones compute.  Every other
+ * configuration runs the plain sequence.  Pinned host memory is needed for the overlap (pageable memory
+ * works, serialised by the driver). */
+int  bellman_stage_host(bellman_handle *h, const double *J_next_host, double *J_out_host, int32_t *idx_out_host,
+                        const bellman_run_opts *opts);
 int  bellman_run(bellman_handle *h, int32_t n_stages, const bellman_run_opts *opts);
 int  bellman_current_stage(const bellman_handle *h);        /* stage number of the current J    */
 int  bellman_get_J(bellman_handle *h, int32_t stage, double *J_host_out /*[P][S_own]*/);

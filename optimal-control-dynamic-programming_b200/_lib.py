@@ -58,7 +58,7 @@ class CSlab(C.Structure):
 EXPORTS = [
     "bellman_version", "bellman_last_error", "bellman_query_locate", "bellman_plan_slabs", "bellman_query_stencil",
     "bellman_create", "bellman_destroy", "bellman_get_unique_id", "bellman_comm_init", "bellman_halo_mode",
-    "bellman_set_J", "bellman_set_stage", "bellman_stage", "bellman_run", "bellman_current_stage", "bellman_get_J",
+    "bellman_set_J", "bellman_set_stage", "bellman_stage", "bellman_stage_host", "bellman_run", "bellman_current_stage", "bellman_get_J",
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
     "bellman_rollout_orbit", "bellman_get_points", "bellman_group_init", "bellman_group_run",
@@ -85,6 +85,7 @@ def load():
     lib.bellman_destroy.restype = None
     lib.bellman_run.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CRunOpts)]
     lib.bellman_stage.argtypes = [C.c_void_p]
+    lib.bellman_stage_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.bellman_set_J.argtypes = [C.c_void_p, _dp]
     lib.bellman_set_stage.argtypes = [C.c_void_p, C.c_int32, _dp, _ip]
     lib.bellman_get_J.argtypes = [C.c_void_p, C.c_int32, _dp]
@@ -271,6 +272,23 @@ class Sweep:
 
     def stage(self):
         self._check(self.lib.bellman_stage(self.h))
+
+    def stage_host(self, J_next=None, J_out=None, idx_out=None, kernel=KERNEL_AUTO):
+        """One stage from host arrays with the copies overlapped with the kernel (bellman_stage_host):
+        ``J_next`` [P, S] (None = continue from the device's J), results into ``J_out`` [P, S_own] /
+        ``idx_out`` (allocated when None).  Arrays may be numpy or (pinned) torch CPU tensors' numpy views."""
+        if J_next is not None:
+            J_next = np.ascontiguousarray(J_next, dtype=np.float64)
+            if J_next.size != self.desc.P * self.desc.S:
+                raise ValueError("J_next must hold P*S values")
+        if J_out is None:
+            J_out = np.empty((self.desc.P, self.S_own), dtype=np.float64)
+        if idx_out is None:
+            idx_out = np.empty((self.desc.P, self.S_own), dtype=np.int32)
+        o = CRunOpts(C.sizeof(CRunOpts), kernel, 0, 0.0, 0, 0)
+        self._check(self.lib.bellman_stage_host(self.h, None if J_next is None else J_next.ctypes.data, J_out.ctypes.data,
+                                                idx_out.ctypes.data, C.byref(o)))
+        return J_out, idx_out
 
     @property
     def current_stage(self):

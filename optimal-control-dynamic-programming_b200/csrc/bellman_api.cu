@@ -928,6 +928,122 @@ extern "C" int bellman_run(bellman_handle *h, int32_t n_stages, const bellman_ru
 
 extern "C" int bellman_stage(bellman_handle *h) { return bellman_run(h, 1, nullptr); }
 
+// ---------------------------------------------------------------------------------------------
+// One stage with host buffers, pipelined (the host <-> device copies of bellman_set_J / bellman_get_J /
+// bellman_get_idx overlapped with the stage kernel).  The grid is cut into slabs of dimension-1 tiles.
+// J_{k+1} goes up in column chunks on a copy stream; slab s is launched as soon as the chunk holding the
+// highest column it can query (exact reach analysis) has arrived; its J_k and argmin go down on a second
+// copy stream while later slabs compute.  Only k_stage_wide can run a tile range; every other
+// configuration takes the plain sequence, with identical results.
+// ---------------------------------------------------------------------------------------------
+extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, double *J_out_host,
+                                  int32_t *idx_out_host, const bellman_run_opts *opts) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    const HostProblem &hp = h->hp;
+    bellman_run_opts o;
+    std::memset(&o, 0, sizeof(o));
+    if (opts) {
+        if (opts->struct_size != (int32_t)sizeof(bellman_run_opts)) { h->err = "bellman_run_opts.struct_size mismatch"; return BELLMAN_ERR_BAD_ARG; }
+        o = *opts;
+    }
+    int lanes = 1, tile1 = 0;
+    const int ntile1 = window_wide_tiles(h, &tile1);
+    const bool pipelined = ntile1 >= 8 && h->nranks == 1 && hp.P == 1 && hp.D == 2 && hp.idx_bytes == 4 &&
+                           (o.kernel == BELLMAN_KERNEL_AUTO || o.kernel == BELLMAN_KERNEL_WINDOW) &&
+                           pick_kernel(h, o.kernel, lanes) == BELLMAN_KERNEL_WINDOW && o.check_period == 0 &&
+                           !std::getenv("BELLMAN_NO_HOST_PIPELINE");
+    if (!pipelined) {
+        int rc = BELLMAN_OK;
+        if (J_next_host) rc = bellman_set_J(h, J_next_host);
+        if (rc == BELLMAN_OK) rc = bellman_run(h, 1, opts);
+        if (rc == BELLMAN_OK && J_out_host) rc = bellman_get_J(h, h->cur_stage, J_out_host);
+        if (rc == BELLMAN_OK && idx_out_host) rc = bellman_get_idx(h, h->cur_stage, idx_out_host);
+        return rc;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    if (J_next_host) { h->cur_stage = hp.N; h->check_log.clear(); }
+    else if (!h->J_set) { h->err = "bellman_stage_host: no J_{k+1} on the device and none given"; return BELLMAN_ERR_STATE; }
+    if (h->cur_stage < 2) { h->err = "run would pass stage 1"; return BELLMAN_ERR_STATE; }
+    const int from = h->cur_stage, to = from - 1;
+    const int n0 = hp.n[0], n1 = hp.n[1];
+    const int NSLAB = 8;
+    const int tps = (ntile1 + NSLAB - 1) / NSLAB;                  // tiles per slab
+    const int nslab = (ntile1 + tps - 1) / tps;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev_in(nslab, nullptr), ev_k(nslab, nullptr);
+    int rc = BELLMAN_OK;
+    auto cleanup = [&]() {
+        for (auto e : ev_in) if (e) cudaEventDestroy(e);
+        for (auto e : ev_k) if (e) cudaEventDestroy(e);
+        if (s_in) cudaStreamDestroy(s_in);
+        if (s_out) cudaStreamDestroy(s_out);
+    };
+#define ST(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = std::string("bellman_stage_host: ") + cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
+    ST(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+    ST(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    for (int s = 0; s < nslab; ++s) {
+        ST(cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
+        ST(cudaEventCreateWithFlags(&ev_k[s], cudaEventDisableTiming));
+    }
+    ST(cudaEventRecord(h->ev0, h->stream));
+    // columns [c_lo, c_hi) of slab s (whole tiles)
+    auto col_lo = [&](int s) { return std::min(n1, s * tps * tile1); };
+    double *dJ_next = h->J_ptr(from), *dJ_out = h->J_ptr(to);
+    int32_t *d_idx = h->idx_ptr(to);
+    if (J_next_host) {
+        for (int s = 0; s < nslab; ++s) {
+            const int c0 = col_lo(s), c1 = col_lo(s + 1);
+            ST(cudaMemcpy2DAsync(dJ_next + (size_t)c0 * h->ld0, (size_t)h->ld0 * 8, J_next_host + (size_t)c0 * n0,
+                                 (size_t)n0 * 8, (size_t)n0 * 8, (size_t)(c1 - c0), cudaMemcpyHostToDevice, s_in));
+            ST(cudaEventRecord(ev_in[s], s_in));
+        }
+    }
+    StageParams sp = h->sp;
+    sp.J_next = dJ_next;
+    sp.J_out = dJ_out;
+    sp.idx_out = d_idx;
+    sp.n_peers = 0;
+    h->last_kernel = window_variant(h);
+    h->last_launches = 0;
+    h->last_ms_exchange = 0.0;
+    int waited = -1;
+    for (int s = 0; s < nslab; ++s) {
+        const int c0 = col_lo(s), c1 = col_lo(s + 1);
+        if (J_next_host) {
+            // highest J_{k+1} column any state of this slab can touch, plus the window's fixed extent (the TMA
+            // box is loaded whole); the stream waits for the chunk that holds it
+            int rlo = 0, rhi = 0;
+            reach_range(hp, 1, c0, c1, rlo, rhi);
+            const int top = std::min(n1 - 1, rhi + h->wcfg.win1);
+            int need = nslab - 1;
+            for (int q = 0; q < nslab; ++q) if (top < col_lo(q + 1)) { need = q; break; }
+            if (need > waited) { ST(cudaStreamWaitEvent(h->stream, ev_in[need], 0)); waited = need; }
+        }
+        ST(window_launch_tile_range(h, sp, h->J_slot(from), h->stream, s * tps, std::min(tps, ntile1 - s * tps)));
+        h->last_launches += 1;
+        ST(cudaEventRecord(ev_k[s], h->stream));
+        if (J_out_host || idx_out_host) ST(cudaStreamWaitEvent(s_out, ev_k[s], 0));
+        if (J_out_host)
+            ST(cudaMemcpy2DAsync(J_out_host + (size_t)c0 * n0, (size_t)n0 * 8, dJ_out + (size_t)c0 * h->ld0, (size_t)h->ld0 * 8,
+                                 (size_t)n0 * 8, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s_out));
+        if (idx_out_host)
+            ST(cudaMemcpyAsync(idx_out_host + (size_t)c0 * n0, d_idx + (size_t)c0 * n0, (size_t)(c1 - c0) * n0 * sizeof(int32_t),
+                               cudaMemcpyDeviceToHost, s_out));
+    }
+    ST(cudaEventRecord(h->ev1, h->stream));
+    ST(cudaStreamSynchronize(s_in));
+    ST(cudaStreamSynchronize(h->stream));
+    ST(cudaStreamSynchronize(s_out));
+    float ms = 0.f;
+    ST(cudaEventElapsedTime(&ms, h->ev0, h->ev1));
+#undef ST
+    h->last_ms = ms;
+    h->cur_stage = to;
+    h->J_set = true;
+    cleanup();
+    return rc;
+}
+
 extern "C" int bellman_last_run_stats(const bellman_handle *h, double *ms_total, int64_t *kernel_launches,
                                       double *ms_exchange) {
     if (!h) return BELLMAN_ERR_BAD_ARG;

@@ -97,6 +97,8 @@ bool stream_valid(const bellman_handle *h);
 cudaError_t stream_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st);
 // "window:strip" / "window:chain" / "window:ring-chain" / "window:ring": which TMA-staged kernel runs
 const char *window_variant(const bellman_handle *h);
+cudaError_t window_launch_tile_range(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st, int tj0, int ntj);
+int window_wide_tiles(const bellman_handle *h, int *tile1);
 cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, int slot_next,
                                      cudaStream_t st);
 }  // namespace bellman

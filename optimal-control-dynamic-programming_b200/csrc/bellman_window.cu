@@ -58,6 +58,7 @@ struct WindowParams {
     const double2 *colq;
     int strip_r;
     int pf_dist;               // k_stage_strip: L2 prefetch distance in CTAs (0 = off)
+    int tj_off;                // k_stage_wide: first dimension-1 tile of this launch (ntile1 = tiles launched)
 };
 
 // --- PTX wrappers ------------------------------------------------------------------------------
@@ -451,7 +452,7 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     const int tid = threadIdx.x, lane = tid & 31, wrp = tid >> 5;
     const int prob = blockIdx.y;
     const int ti = wp.tj_fastest ? blockIdx.x / wp.ntile1 : blockIdx.x % wp.ntile0;
-    const int tj = wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0;
+    const int tj = wp.tj_off + (wp.tj_fastest ? blockIdx.x % wp.ntile1 : blockIdx.x / wp.ntile0);
     const DimParams &d0 = sp.dim[0], &d1 = sp.dim[1];
     const int n0 = d0.n, n1 = d1.n;
     const int i_lo = d0.own_lo + ti * WT0, i_hi = min(i_lo + WT0, d0.own_lo + d0.own_n);
@@ -1134,7 +1135,8 @@ static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const C
 }
 template <bool BAR>
 static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid, cudaStream_t st,
-                    bool set_attr_only) {
+                    bool set_attr_only, const WindowParams *wpo = nullptr) {
+    const WindowParams &wpl = wpo ? *wpo : ws->wp;
     auto f48 = k_stage_wide<2, 48, true, BAR>, f48n = k_stage_wide<2, 48, false, BAR>;
     auto f0 = k_stage_wide<2, 0, true, BAR>, f0n = k_stage_wide<2, 0, false, BAR>;
     if (set_attr_only) {
@@ -1143,13 +1145,13 @@ static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensor
         return true;
     }
     const bool i32 = sp->idx_bytes == 4;
-    if (ws->wp.win0 == 48) (i32 ? f48 : f48n)<<<grid, WIDE_NT, ws->wide_smem, st>>>(*sp, ws->wp, *map, *ws->wide);
-    else (i32 ? f0 : f0n)<<<grid, WIDE_NT, ws->wide_smem, st>>>(*sp, ws->wp, *map, *ws->wide);
+    if (wpl.win0 == 48) (i32 ? f48 : f48n)<<<grid, WIDE_NT, ws->wide_smem, st>>>(*sp, wpl, *map, *ws->wide);
+    else (i32 ? f0 : f0n)<<<grid, WIDE_NT, ws->wide_smem, st>>>(*sp, wpl, *map, *ws->wide);
     return true;
 }
 static bool wide_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
-                          cudaStream_t st, bool sa) {
-    return ws->wide_bar ? wide_go<true>(ws, sp, map, grid, st, sa) : wide_go<false>(ws, sp, map, grid, st, sa);
+                          cudaStream_t st, bool sa, const WindowParams *wpo = nullptr) {
+    return ws->wide_bar ? wide_go<true>(ws, sp, map, grid, st, sa, wpo) : wide_go<false>(ws, sp, map, grid, st, sa, wpo);
 }
 static void window_teardown_state(WindowState *ws) {
     cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp); cudaFree(ws->d_colq);
@@ -1486,6 +1488,28 @@ cudaError_t window_launch_for_handle(bellman_handle *h, const StageParams &sp, i
     else if (ws->wide) wide_dispatch(ws, &sp, &map, grid, st, false);
     else window_dispatch(ws, &sp, &map, nullptr, grid, st, false);
     return cudaGetLastError();
+}
+
+// k_stage_wide over the dimension-1 tiles [tj0, tj0 + ntj) only (bellman_stage_host runs a stage slab by slab
+// while the host copies overlap).  Returns cudaErrorNotSupported when the handle does not use that kernel.
+cudaError_t window_launch_tile_range(bellman_handle *h, const StageParams &sp, int slot_next, cudaStream_t st,
+                                     int tj0, int ntj) {
+    auto *ws = static_cast<WindowState *>(h->wstate);
+    if (!ws || !h->wcfg.valid || !ws->wide || ws->strip || ws->lean) return cudaErrorNotSupported;
+    WindowParams wpl = ws->wp;
+    if (tj0 < 0 || ntj < 1 || tj0 + ntj > wpl.ntile1) return cudaErrorInvalidValue;
+    wpl.tj_off = tj0;
+    wpl.ntile1 = ntj;
+    const dim3 grid((unsigned)(wpl.ntile0 * ntj), (unsigned)sp.P);
+    wide_dispatch(ws, &sp, &ws->maps[slot_next], grid, st, false, &wpl);
+    return cudaGetLastError();
+}
+// tile geometry of the wide kernel (0 when the handle does not use it)
+int window_wide_tiles(const bellman_handle *h, int *tile1) {
+    auto *ws = static_cast<const WindowState *>(h->wstate);
+    if (!ws || !h->wcfg.valid || !ws->wide || ws->strip || ws->lean) return 0;
+    if (tile1) *tile1 = (WIDE_NT / 32) * WIDE_R;
+    return ws->wp.ntile1;
 }
 
 }  // namespace bellman

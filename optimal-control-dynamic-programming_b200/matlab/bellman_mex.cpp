@@ -261,6 +261,16 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         check(bellman_run(h, (int32_t)mxGetScalar(prhs[2]), &o), h);
     } else if (cmd == "stage") {
         check(bellman_stage(h), h);
+    } else if (cmd == "stage_host") {
+        // [J, idx] = bellman_mex('stage_host', h, J_next)   one stage from / to MATLAB arrays, copies overlapped
+        // with the kernel (J_next [] = continue from the device's J); idx is 1-based like min()'s second output
+        const double *J = (nrhs > 2 && !mxIsEmpty(prhs[2])) ? need_doubles(prhs[2], sh.S_global * sh.P, "J_next") : nullptr;
+        plhs[0] = mxCreateDoubleMatrix(sh.S_own, sh.P, mxREAL);
+        mxArray *I = mxCreateNumericMatrix(sh.S_own, sh.P, mxINT32_CLASS, mxREAL);
+        int32_t *p = static_cast<int32_t *>(mxGetData(I));
+        check(bellman_stage_host(h, J, mxGetPr(plhs[0]), p, nullptr), h);
+        for (size_t k = 0; k < sh.S_own * sh.P; ++k) p[k] += 1;
+        if (nlhs > 1) plhs[1] = I; else mxDestroyArray(I);
     } else if (cmd == "owned_range") {
         bellman_slab sl;
         check(bellman_owned_range(h, &sl), h);

@@ -698,3 +698,50 @@ def test_pos_att_x4_full_size_spot_check(bellman, oracle_lib, monkeypatch, famil
     assert np.array_equal(I1[0][pts], Io) and np.array_equal(J1[0][pts], Jo)
     Jo, Io = oracle_lib.stage_points(d, J1[0], pts)
     assert np.array_equal(I2[0][pts], Io) and np.array_equal(J2[0][pts], Jo)
+
+
+@pytest.mark.gpu
+def test_stage_host_pipelined_equals_sequence_and_oracle(bellman, oracle_lib, monkeypatch):
+    """bellman_stage_host: the slab-pipelined path (k_stage_wide, 8 slabs of tiles, copies on side streams)
+    gives bit for bit what set_J + run(1) + get_J + get_idx give, and what the oracle gives; ragged tile
+    counts, a rough J, continuing from the device's J (J_next = None), and the fallback for kernels that
+    cannot run a tile range."""
+    obj = bellman.Dynamic_Solver()
+    t = bellman.tables
+    rng = np.random.default_rng(11)
+    for n0, n1, C in ((256, 1024, 48), (130, 777, 33)):
+        s0, s1, u = t.linspace(-2.5, 3.0, n0), t.linspace(-2.5, 3.0, n1), t.linspace(-40.0, 10.0, C)
+        A, B = obj.A, obj.B.ravel()
+        row = lambda x: np.ascontiguousarray(x).reshape(1, -1)
+        d = t.Desc(n=[n0, n1], C=C, N=6, grid=[row(s0), row(s1)], src_a=[0, 0], src_b=[1, 1],
+                   Ta=[row(A[0, 0] * s0), row(A[1, 0] * s0)], Tb=[row(A[0, 1] * s1), row(A[1, 1] * s1)],
+                   Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
+                   q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u),
+                   store_J_all=False, store_idx_all=False).validate()
+        ntile1 = -(-n1 // 64)
+        n_slabs = -(-ntile1 // -(-ntile1 // 8))
+        JN = rng.normal(size=(1, d.S)) * 3
+        ora = oracle_lib.sweep(d, n_stages=2, J_N=JN, keep_all=True)
+        with bellman.Sweep(d) as sw:
+            J1, I1 = sw.stage_host(JN, kernel=KERNELS["window"])
+            assert sw.last_kernel == "window:wide" and sw.current_stage == d.N - 1
+            assert sw.stats()["launches"] == n_slabs   # really went slab by slab
+            assert_stage_equal(J1, I1, ora["J_all"][d.N - 2], ora["idx_all"][d.N - 2], "stage_host first stage")
+            J2, I2 = sw.stage_host(None, kernel=KERNELS["window"])      # continue from the device's J
+            assert sw.current_stage == d.N - 2
+            assert_stage_equal(J2, I2, ora["J_all"][d.N - 3], ora["idx_all"][d.N - 3], "stage_host second stage")
+            sw.set_J(JN); sw.run(1, kernel=KERNELS["window"])
+            assert np.array_equal(sw.get_J(), J1) and np.array_equal(sw.get_idx(), I1)
+    # fallback: strip kernel (attitude) and a forced direct kernel go through the plain sequence
+    sa = bellman.Solver_attitude()
+    sa.n_mesh_w, sa.n_mesh_t = 400, 120
+    da = t.stack_problems(sa._axis_descs())
+    oa = oracle_lib.sweep(da, n_stages=1)
+    with bellman.Sweep(da) as sw:
+        J, I = sw.stage_host(np.zeros((da.P, da.S)))
+        assert_stage_equal(J, I, oa["J_last"], oa["idx_last"], "stage_host fallback")
+    monkeypatch.setenv("BELLMAN_NO_HOST_PIPELINE", "1")
+    with bellman.Sweep(d) as sw:
+        J, I = sw.stage_host(JN, kernel=KERNELS["window"])
+        assert sw.stats()["launches"] == 1
+        assert np.array_equal(J, J1) and np.array_equal(I, I1)
