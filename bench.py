@@ -168,6 +168,29 @@ def cpu_reference_shaped_rate(bb, name):
     down-scaled grid of the same problem; single process, numpy's own threading."""
     from oracle import matlab_literal as ml
     w = WORKLOADS[name]
+    kind = "port (numpy, reference-shaped)"
+    if w["kind"] in ("position", "attitude"):
+        # one axis at reference size (Solver_position.m:132-141 / Solver_attitude.m:236-247), a few stages
+        L = ml.SolverPositionLiteral() if w["kind"] == "position" else ml.SolverAttitudeLiteral()
+        grids, nxt, J_current = L.axis_arrays(0)
+        F = ml.GriddedInterpolantLinear(grids, np.zeros((len(grids[0]), len(grids[1]))))
+        n, t0 = 0, time.perf_counter()
+        while n < 3 or time.perf_counter() - t0 < 2.0:
+            F.Values, _idx = ml.ml_min_last(J_current + F(*nxt))
+            n += 1
+        dt = time.perf_counter() - t0
+        return {"value": n * J_current.size / dt, "unit": UNIT, "kind": kind,
+                "sample": "one axis at reference size, %s states x %d controls, %d stages (%.1f s)"
+                          % ("x".join(str(len(g)) for g in grids), J_current.shape[-1], n, dt)}
+    if w["kind"] in ("pos_att", "pos_att_cfg5"):
+        L = ml.SolverPosAttLiteral()       # one channel at reference size (Solver_pos_att.m:270-286)
+        t0 = time.perf_counter()
+        n = 3
+        grids = L.calculate_one_channel(0, n_stages=n, check=False)[2]
+        dt = time.perf_counter() - t0
+        S = int(np.prod([len(g) for g in grids]))
+        return {"value": n * S * 9 / dt, "unit": UNIT, "kind": kind,
+                "sample": "one channel at reference size (%d states x 9 controls), %d stages incl. set-up (%.1f s)" % (S, n, dt)}
     if w["kind"] != "kirk":
         return None
     dx, du = min(w["dx"], 256), min(w["du"], 256)
@@ -179,7 +202,7 @@ def cpu_reference_shaped_rate(bb, name):
         JF = L.F(L.X_next_M1, L.X_next_M2)
         L.F.Values, _idx = ml.ml_min_last(JF + L.J_current_state)
     dt = time.perf_counter() - t0
-    return {"value": n * dx * dx * du / dt, "unit": UNIT, "kind": "port (numpy, reference-shaped)",
+    return {"value": n * dx * dx * du / dt, "unit": UNIT, "kind": kind,
             "sample": "%dx%d states x %d controls, %d stages (%.1f s)" % (dx, dx, du, n, dt)}
 
 
@@ -586,6 +609,10 @@ def main():
         slab = cpu_slab_rate(d, 6.0)
         if slab:
             cpu["contiguous_slab"] = {"value": slab[0], "unit": UNIT, "cores": slab[1], "sample": slab[2]}
+        # the reference-shaped CPU rate of the small-control classes measured above (position, attitude, pos-att)
+        for name in ("position_3x201x201x3", "attitude_x16_3x16000x4800x3", "pos_att_x4_120x120x80x60x9"):
+            if name in others:
+                others[name]["cpu_reference_shaped"] = cpu_reference_shaped_rate(bb, name)
 
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
