@@ -745,3 +745,27 @@ def test_stage_host_pipelined_equals_sequence_and_oracle(bellman, oracle_lib, mo
         J, I = sw.stage_host(JN, kernel=KERNELS["window"])
         assert sw.stats()["launches"] == 1
         assert np.array_equal(J, J1) and np.array_equal(I, I1)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["wide", "ring"])
+def test_window_kernel_stacked_problems(bellman, oracle_lib, monkeypatch, variant):
+    """Three different linear systems stacked into one descriptor (P = 3, per-problem control tables in
+    k_stage_wide's constant-bank parameter, per-problem tile extrema and chunk bounds), rough terminal cost."""
+    want = _window_variant(monkeypatch, variant)
+    obj = bellman.Dynamic_Solver()
+    t = bellman.tables
+    descs = []
+    for k, scale in enumerate((1.0, 0.7, 1.3)):
+        A = np.array(obj.A, dtype=np.float64).reshape(2, 2) * np.array([[1.0, scale], [scale, 1.0]])
+        B = np.array(obj.B, dtype=np.float64).ravel() * (1.0 + 0.5 * k)
+        descs.append(t.kirk_desc(A, B, obj.Q, obj.R, 5, obj.x_min, obj.x_max, 200, obj.u_min, obj.u_max, 40,
+                                 store_J_all=False, store_idx_all=False))
+    d = t.stack_problems(descs)
+    JN = np.random.default_rng(3).normal(size=(d.P, d.S)) * 2
+    ora = oracle_lib.sweep(d, n_stages=3, J_N=JN)
+    with bellman.Sweep(d) as sw:
+        sw.set_J(JN)
+        sw.run(3, kernel=KERNELS["window"])
+        assert sw.last_kernel == want
+        assert_stage_equal(sw.get_J(), sw.get_idx(), ora["J_last"], ora["idx_last"], "stacked " + variant)
