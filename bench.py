@@ -48,7 +48,7 @@ DEFAULT_WORKLOAD = "kirk_scaled_8192x8192x512"
 # dram__bytes_read.sum + dram__bytes_write.sum of ONE stage-kernel launch.  NOT measured by this run (a
 # run under ncu is never a bench value): constants copied from the committed `ncu --set full` captures of
 # the same command, each with the file it comes from; reported as roofline.traffic + traffic_source.
-NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": (548.0e6 + 772.5e6, "profiles/r01_window_kirk_summary.txt"),
+NCU_TRAFFIC = {"kirk_scaled_8192x8192x512": (544.82e6 + 766.83e6, "profiles/r02_wide_kirk_summary.txt"),
                "attitude_x16_3x16000x4800x3": (1.8434e9 + 2.7178e9, "profiles/r01_strip_att16_summary.txt"),
                "pos_att_x4_120x120x80x60x9": (2.0363e9 + 2.4638e9, "profiles/r02_stream_posatt_x4_summary.txt")}
 
@@ -344,7 +344,22 @@ def main():
             raise SystemExit("--gpus %d needs torchrun --nproc-per-node %d" % (args.gpus, args.gpus))
         args.gpus = world
     torch.cuda.set_device(local)
+    numa = None
     if world > 1:
+        # one process per GPU: keep the host thread (and so the pinned buffers it first touches) on the CPUs
+        # local to this rank's GPU, so the e2e copies do not cross the socket interconnect
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            hdl = pynvml.nvmlDeviceGetHandleByIndex(local)
+            words = pynvml.nvmlDeviceGetCpuAffinity(hdl, (os.cpu_count() + 63) // 64)
+            cpus = {64 * w + b for w, m in enumerate(words) for b in range(64) if (m >> b) & 1}
+            cpus &= os.sched_getaffinity(0)
+            if cpus:
+                os.sched_setaffinity(0, cpus)
+                numa = len(cpus)
+        except Exception:      # no NVML / not permitted: run unbound
+            numa = None
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     def barrier():
@@ -466,11 +481,16 @@ def main():
         pin_in[:] = np.random.default_rng(7).normal(size=S_all) if S_all <= (1 << 27) else 0.0
         seq_call = "bellman_set_J(host) + bellman_run(1) + bellman_get_J(host) + bellman_get_idx(host)"
 
+        brk = [0.0, 0.0, 0.0, 0.0]      # host time inside each blocking call of the sequential round trip
+
         def step_sequential():
-            sw.set_J(pin_in.reshape(d.P, -1))
-            sw.run(1, kernel=kernel)
-            sw.get_J(out=pin_J)
-            sw.get_idx(out=pin_I)
+            t = [time.perf_counter()]
+            sw.set_J(pin_in.reshape(d.P, -1)); t.append(time.perf_counter())
+            sw.run(1, kernel=kernel); t.append(time.perf_counter())
+            sw.get_J(out=pin_J); t.append(time.perf_counter())
+            sw.get_idx(out=pin_I); t.append(time.perf_counter())
+            for k in range(4):
+                brk[k] += t[k + 1] - t[k]
 
         def step_pipelined():       # one ABI call; copies overlap the kernel where the stage kernel can run tile ranges
             sw.stage_host(pin_in.reshape(d.P, -1), pin_J, pin_I, kernel=kernel)
@@ -485,6 +505,7 @@ def main():
             return max_over_ranks(time.perf_counter() - t0)
 
         dt_seq = timed(step_sequential)
+        brk_ms = [round(x / (Ke + 1) * 1e3, 3) for x in brk]
         ref_J, ref_I = pin_J.copy(), pin_I.copy()
         dt = timed(step_pipelined)
         same = bool(np.array_equal(ref_J, pin_J) and np.array_equal(ref_I, pin_I))
@@ -494,7 +515,8 @@ def main():
         e2e = {"value": upd_per_step * Ke / dt, "unit": UNIT, "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": int(own * 12), "steps": Ke, "ms_per_step": dt / Ke * 1e3,
                "call": "bellman_stage_host(J_next host in, J and idx host out)",
-               "sequential": {"value": upd_per_step * Ke / dt_seq, "ms_per_step": dt_seq / Ke * 1e3, "call": seq_call},
+               "sequential": {"value": upd_per_step * Ke / dt_seq, "ms_per_step": dt_seq / Ke * 1e3, "call": seq_call,
+                              "rank0_ms_set_J_run_get_J_get_idx": brk_ms},
                "matches_sequential": same}
 
     # ---- outside the timed region: bit-exact spot check of this rank's slab against the oracle -------
@@ -629,7 +651,7 @@ def main():
                        "slab_cuts": cuts, "cuda_graph": bool(use_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(main_launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K,
-            "sharded_parity": parity["main"], "parity_checks": parity, "cfg5": cfg5,
+            "sharded_parity": parity["main"], "parity_checks": parity, "cfg5": cfg5, "host_cpus_bound_per_rank": numa,
             "other_workloads": others}
     print(json.dumps(line), flush=True)
     if sw is not None:
