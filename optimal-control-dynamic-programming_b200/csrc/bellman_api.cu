@@ -948,7 +948,10 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     }
     int lanes = 1, tile1 = 0;
     const int ntile1 = window_wide_tiles(h, &tile1);
-    const bool pipelined = ntile1 >= 8 && h->nranks == 1 && hp.P == 1 && hp.D == 2 && hp.idx_bytes == 4 &&
+    // sharded handles: slabs along dimension 0 only (the tile ranges run along dimension 1), halo through the
+    // peer stores + neighbour flags
+    const bool shard_ok = h->nranks == 1 || (h->part_dim == 0 && h->fused_halo && !h->group_mode);
+    const bool pipelined = ntile1 >= 8 && shard_ok && hp.P == 1 && hp.D == 2 && hp.idx_bytes == 4 &&
                            (o.kernel == BELLMAN_KERNEL_AUTO || o.kernel == BELLMAN_KERNEL_WINDOW) &&
                            pick_kernel(h, o.kernel, lanes) == BELLMAN_KERNEL_WINDOW && o.check_period == 0 &&
                            !std::getenv("BELLMAN_NO_HOST_PIPELINE");
@@ -966,6 +969,7 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     if (h->cur_stage < 2) { h->err = "run would pass stage 1"; return BELLMAN_ERR_STATE; }
     const int from = h->cur_stage, to = from - 1;
     const int n0 = hp.n[0], n1 = hp.n[1];
+    const int e0 = h->ext_lo[0], en0 = h->ext_n[0], o0 = h->own_lo[0], on0 = h->own_n[0];   // rows held / owned
     const int NSLAB = 8;
     const int tps = (ntile1 + NSLAB - 1) / NSLAB;                  // tiles per slab
     const int nslab = (ntile1 + tps - 1) / tps;
@@ -993,8 +997,8 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     if (J_next_host) {
         for (int s = 0; s < nslab; ++s) {
             const int c0 = col_lo(s), c1 = col_lo(s + 1);
-            ST(cudaMemcpy2DAsync(dJ_next + (size_t)c0 * h->ld0, (size_t)h->ld0 * 8, J_next_host + (size_t)c0 * n0,
-                                 (size_t)n0 * 8, (size_t)n0 * 8, (size_t)(c1 - c0), cudaMemcpyHostToDevice, s_in));
+            ST(cudaMemcpy2DAsync(dJ_next + (size_t)c0 * h->ld0, (size_t)h->ld0 * 8, J_next_host + (size_t)c0 * n0 + e0,
+                                 (size_t)n0 * 8, (size_t)en0 * 8, (size_t)(c1 - c0), cudaMemcpyHostToDevice, s_in));
             ST(cudaEventRecord(ev_in[s], s_in));
         }
     }
@@ -1002,7 +1006,7 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     sp.J_next = dJ_next;
     sp.J_out = dJ_out;
     sp.idx_out = d_idx;
-    sp.n_peers = 0;
+    fill_peers(h, sp, to);
     h->last_kernel = window_variant(h);
     h->last_launches = 0;
     h->last_ms_exchange = 0.0;
@@ -1024,11 +1028,19 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
         ST(cudaEventRecord(ev_k[s], h->stream));
         if (J_out_host || idx_out_host) ST(cudaStreamWaitEvent(s_out, ev_k[s], 0));
         if (J_out_host)
-            ST(cudaMemcpy2DAsync(J_out_host + (size_t)c0 * n0, (size_t)n0 * 8, dJ_out + (size_t)c0 * h->ld0, (size_t)h->ld0 * 8,
-                                 (size_t)n0 * 8, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s_out));
+            ST(cudaMemcpy2DAsync(J_out_host + (size_t)c0 * on0, (size_t)on0 * 8, dJ_out + (size_t)c0 * h->ld0 + (o0 - e0),
+                                 (size_t)h->ld0 * 8, (size_t)on0 * 8, (size_t)(c1 - c0), cudaMemcpyDeviceToHost, s_out));
         if (idx_out_host)
-            ST(cudaMemcpyAsync(idx_out_host + (size_t)c0 * n0, d_idx + (size_t)c0 * n0, (size_t)(c1 - c0) * n0 * sizeof(int32_t),
+            ST(cudaMemcpyAsync(idx_out_host + (size_t)c0 * on0, d_idx + (size_t)c0 * on0, (size_t)(c1 - c0) * on0 * sizeof(int32_t),
                                cudaMemcpyDeviceToHost, s_out));
+    }
+    if (h->nranks > 1) {
+        // as bellman_run: my stage count goes to the neighbours, then wait until theirs has reached it (their
+        // peer stores of this stage are then in my halo rows)
+        h->halo_seq += 1;
+        rc = halo_signal(h);
+        if (rc == BELLMAN_OK) rc = halo_wait(h);
+        if (rc != BELLMAN_OK) { cleanup(); return rc; }
     }
     ST(cudaEventRecord(h->ev1, h->stream));
     ST(cudaStreamSynchronize(s_in));
@@ -1041,6 +1053,11 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     h->cur_stage = to;
     h->J_set = true;
     cleanup();
+    if (h->fused_halo && h->nranks > 1) {
+        unsigned int timed_out = 0;
+        CUDA_TRY(h, cudaMemcpy(&timed_out, h->d_flags + 48, sizeof(timed_out), cudaMemcpyDeviceToHost));
+        if (timed_out) { h->err = "halo flag wait timed out: a neighbour rank stopped progressing"; return BELLMAN_ERR_NCCL; }
+    }
     return rc;
 }
 

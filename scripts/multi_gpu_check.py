@@ -34,6 +34,17 @@ def make(kind):
                       Ta=[row(A[0, 0] * s0), row(A[1, 0] * s0)], Tb=[row(A[0, 1] * s1), row(A[1, 1] * s1)],
                       Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
                       q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u)).validate()
+    if kind == "kirk_host":
+        o = bb.Dynamic_Solver()
+        t = bb.tables
+        s0, s1, u = t.linspace(-2.5, 3.0, 256), t.linspace(-2.5, 3.0, 1024), t.linspace(-40.0, 10.0, 48)
+        A, B = o.A, o.B.ravel()
+        row = lambda x: np.ascontiguousarray(x).reshape(1, -1)
+        return t.Desc(n=[256, 1024], C=48, N=8, grid=[row(s0), row(s1)], src_a=[0, 0], src_b=[1, 1],
+                      Ta=[row(A[0, 0] * s0), row(A[1, 0] * s0)], Tb=[row(A[0, 1] * s1), row(A[1, 1] * s1)],
+                      Tc=[row(B[0] * u), row(B[1] * u)], q_order=[0, 1],
+                      q=[row(0.25 * s0 * s0), row(0.05 * s1 * s1)], r=row(0.05 * u * u),
+                      store_J_all=False, store_idx_all=False).validate()
     if kind == "attitude":
         s = bb.Solver_attitude()
         s.n_mesh_w, s.n_mesh_t = 400, 120
@@ -51,6 +62,9 @@ def main():
     d = make(kind)
     ok = True
     for part_dim in ((d.D - 1, 0) if kind != "pos_att" else (d.D - 1, 2)):
+        if kind == "kirk_host":
+            ok = check_stage_host(d, part_dim, rank, world, local) and ok
+            continue
         ok = check(d, kind, part_dim, rank, world, local) and ok
     t = torch.tensor([1 if ok else 0], device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
@@ -81,6 +95,33 @@ def check(d, kind, part_dim, rank, world, local):
         print(f"rank {rank}/{world} {kind} part_dim={part_dim} kernel={sw.last_kernel} slab={sw.slab} "
               f"halo={os.environ.get('BELLMAN_NO_P2P') and 'nccl' or 'auto'} "
               f"{'OK' if good else 'MISMATCH'} exchange_ms={sw.stats()['ms_exchange']:.3f}", flush=True)
+        ok = ok and good
+    sw.close()
+    return ok
+
+
+def check_stage_host(d, part_dim, rank, world, local):
+    """bellman_stage_host on a sharded handle: three stages driven from host arrays (the first from a rough
+    J_N, the next two continuing from the device's J, so they read the halo rows the neighbours stored),
+    slab-pipelined for row slabs (part_dim 0), the plain sequence for column slabs."""
+    sw = bb.Sweep(d, device=local, part_dim=part_dim, rank=rank, nranks=world)
+    ids = [bb.get_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ids, src=0)
+    sw.comm_init(ids[0])
+    JN = np.random.default_rng(5).normal(size=(1, d.S)) * 3
+    ref = cbind.sweep(d, n_stages=3, J_N=JN, keep_all=True)
+    lo, hi = sw.slab[0], sw.slab[1]
+    inner = int(np.prod(d.n[:part_dim]))
+    n_p = d.n[part_dim]
+    ok = True
+    for k in range(3):
+        J, idx = sw.stage_host(JN if k == 0 else None, kernel=bb.KERNEL_WINDOW)
+        stage = d.N - 1 - k
+        Jr = ref["J_all"][stage - 1].reshape(d.P, -1, n_p, inner)[:, :, lo:hi, :].reshape(d.P, -1)
+        Ir = ref["idx_all"][stage - 1].reshape(d.P, -1, n_p, inner)[:, :, lo:hi, :].reshape(d.P, -1)
+        good = bool(np.array_equal(J, Jr) and np.array_equal(idx, Ir)) and sw.current_stage == stage
+        print(f"rank {rank}/{world} stage_host part_dim={part_dim} stage={stage} kernel={sw.last_kernel} "
+              f"launches={sw.stats()['launches']} halo_mode={sw.halo_mode} {'OK' if good else 'MISMATCH'}", flush=True)
         ok = ok and good
     sw.close()
     return ok
