@@ -608,6 +608,8 @@ def test_tile_kernel_falls_back_when_not_a_stencil(bellman, oracle_lib):
 
 @pytest.mark.parametrize("env", [{"BELLMAN_STRIP_R": "16"}, {"BELLMAN_STRIP_R": "4", "BELLMAN_STRIP_NW": "8"},
                                  {"BELLMAN_STRIP_R": "12", "BELLMAN_STRIP_NW": "2", "BELLMAN_STRIP_PF": "5"},
+                                 {"BELLMAN_WIN_OCC": "3"},      # 5-CTA register budget: 2-ahead table prefetch, conversion-free locate
+                                 {"BELLMAN_WIN_OCC": "3", "BELLMAN_STRIP_R": "6"},
                                  {"BELLMAN_WIN_NOSTRIP": "1"}])
 def test_strip_kernel_geometries(bellman, oracle_lib, monkeypatch, env):
     """every strip geometry the planner can pick (strip length 16 is the default on large grids), the
