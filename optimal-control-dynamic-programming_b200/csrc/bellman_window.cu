@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdlib>
 #include <cstring>
 #include <limits>
@@ -1009,6 +1010,7 @@ struct WindowState {
     int batch = 4, occ = 2, rstates = 8, loc = 0;
     WideTables *wide = nullptr;     // k_stage_wide: host copy of the constant-bank control tables (null = not used)
     int wide_ns = 2;                // ring slots
+    bool strip_magic_ok = false;    // dimension-1 queries of the strip kernel stay below 2^30 cells
     bool wide_bar = false;          // BELLMAN_WIDE_BARRIER=1: a CTA barrier per chunk instead of the empty-slot mbarriers
     size_t wide_smem = 0;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
@@ -1120,7 +1122,7 @@ static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const C
             default: return strip_go<2, 4, 14>(ws, sp, map, grid, st, sa);
         }
     }
-    if (ws->occ == 3) {   // BELLMAN_WIN_OCC=3: fewer CTAs per SM, more registers (experiments)
+    if (ws->occ == 3 && ws->strip_magic_ok) {   // BELLMAN_WIN_OCC=3: fewer CTAs per SM, more registers (experiments)
         switch (C) {
             case 3: return strip_go<4, 3, 5>(ws, sp, map, grid, st, sa);
             default: break;
@@ -1360,6 +1362,11 @@ void window_setup(bellman_handle *h) {
         std::vector<double> colq((size_t)hp.P * hp.n[1] * 2 + 4, 0.0);   // +2 entries: the strip kernel prefetches up to two ahead
         for (size_t k = 0; k < (size_t)hp.P * hp.n[1]; ++k) { colq[2 * k] = colp[4 * k + 1]; colq[2 * k + 1] = colp[4 * k + 2]; }
         if (!upload(colq, &ws->d_colq)) { window_teardown_state(ws); return; }
+        // the strip kernel's conversion-free locate (5-CTA variant) needs dimension-1 queries below 2^30 cells
+        double q1 = 0.0, q1r = 0.0;
+        for (size_t k = 0; k < (size_t)hp.P * hp.n[1]; ++k) q1 = std::max(q1, std::fabs(colp[4 * k + 1]));
+        for (size_t k = 0; k < (size_t)hp.P * hp.n[0]; ++k) q1r = std::max(q1r, std::fabs(rowp[4 * k + 1]));
+        ws->strip_magic_ok = q1 + q1r < 1073741824.0;
         wp.colq = static_cast<const double2 *>(ws->d_colq);
         wp.strip_r = strip_r;
         wp.pf_dist = std::getenv("BELLMAN_STRIP_PF") ? std::atoi(std::getenv("BELLMAN_STRIP_PF")) : 148 * 7;   // one wave of 7 CTAs per SM
