@@ -206,6 +206,15 @@ def cpu_reference_shaped_rate(bb, name):
             "sample": "%dx%d states x %d controls, %d stages (%.1f s)" % (dx, dx, du, n, dt)}
 
 
+def workload_config(name, d):
+    """The `config` object, identical in both arms (the driver compares them)."""
+    S_all = d.S * d.P
+    return {"workload": name, "grid": d.n, "controls": d.C, "problems": d.P,
+            "step": "one backward stage over the whole grid",
+            "l2": "J_{k+1} (%.0f MB) exceeds the 126 MB L2; no flush needed" % (S_all * 8 / 1e6)
+            if S_all * 8 > 130e6 else "inputs fit L2 (stage-to-stage reuse is the workload)"}
+
+
 def run_reference_arm(args):
     """--impl reference: the CPU implementation of the path on the box's host cores.  MATLAB is not
     installable (no toolchain, no network), so this is the oracle port, all host threads."""
@@ -227,8 +236,8 @@ def run_reference_arm(args):
             "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * S_all * d.C / value, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "grid": d.n, "controls": d.C, "problems": d.P,
-                       "note": "ms_per_step extrapolated from the sample to one full stage"},
+            "config": workload_config(args.workload, d),
+            "run": {"note": "ms_per_step extrapolated from the sample to one full stage"},
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -639,16 +648,13 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms_dev / K, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "grid": d.n, "controls": d.C, "problems": d.P,
-                       "step": "one backward stage over the whole grid",
-                       "partition": ("dim %d slabs over %d ranks; halo: %s" % (
-                           part_dim, world,
-                           "stored into peer memory by the stage kernel (NVLink P2P); stages ordered by neighbour-only release/acquire flags"
-                           if halo_mode == "p2p" else "grouped ncclSend/ncclRecv after each stage"))
-                       if world > 1 else "none",
-                       "l2": "J_{k+1} (%.0f MB) exceeds the 126 MB L2; no flush needed" % (S_all * 8 / 1e6)
-                       if S_all * 8 > 130e6 else "inputs fit L2 (stage-to-stage reuse is the workload)",
-                       "slab_cuts": cuts, "cuda_graph": bool(use_graph)},
+            "config": workload_config(args.workload, d),
+            "run": {"partition": ("dim %d slabs over %d ranks; halo: %s" % (
+                        part_dim, world,
+                        "stored into peer memory by the stage kernel (NVLink P2P); stages ordered by neighbour-only release/acquire flags"
+                        if halo_mode == "p2p" else "grouped ncclSend/ncclRecv after each stage"))
+                    if world > 1 else "none",
+                    "slab_cuts": cuts, "cuda_graph": bool(use_graph)},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(main_launches), "roofline": roofline,
             "cpu_baseline": cpu, "wall_ms": wall_ms, "exchange_ms_per_step": ms_x / K,
             "sharded_parity": parity["main"], "parity_checks": parity, "cfg5": cfg5, "host_cpus_bound_per_rank": numa,

@@ -28,7 +28,7 @@ for f in ("gpurun_out/m${N}_bench.json", "gpurun_out/m${N}_bench_equal.json"):
     for l in open(f):
         if l.startswith("{"):
             d = json.loads(l)
-            print(f, {k: d[k] for k in ("value", "ms_per_step", "exchange_ms_per_step", "sharded_parity")}, d["config"].get("slab_cuts"))
+            print(f, {k: d[k] for k in ("value", "ms_per_step", "exchange_ms_per_step", "sharded_parity")}, d.get("run", d["config"]).get("slab_cuts"))
             print("  cfg5", d.get("cfg5"))
             print("  e2e", d.get("e2e"))
 PY

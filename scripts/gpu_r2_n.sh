@@ -25,7 +25,7 @@ import json
 for l in open("gpurun_out/n${N}_bench.json"):
     if l.startswith("{"):
         d = json.loads(l)
-        print({k: d[k] for k in ("value", "ms_per_step", "exchange_ms_per_step", "sharded_parity", "parity_checks", "host_cpus_bound_per_rank")}, d["config"].get("slab_cuts"))
+        print({k: d[k] for k in ("value", "ms_per_step", "exchange_ms_per_step", "sharded_parity", "parity_checks", "host_cpus_bound_per_rank")}, d.get("run", d["config"]).get("slab_cuts"))
         print("  cfg5", d.get("cfg5"))
         print("  e2e", d.get("e2e"))
 PY
