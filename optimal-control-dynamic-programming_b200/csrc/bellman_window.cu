@@ -166,10 +166,11 @@ __device__ __forceinline__ int locate_magic(double g, double &t) {
 // the bound): floor from the low word of g +(rd) M as above, clamp on the integer pipe, (double)cell by the
 // bit trick.  Same cell and the same exact difference g - cell as locate_uniform<true> — F2I.F64 / I2F.F64
 // occupy a scheduler's conversion pipe for 8 cycles per warp instruction, a DADD the fp64 pipe for 2.
+template <bool XUCVT = false>
 __device__ __forceinline__ int locate_magic_clamp(double g, int n, double &t) {
     const double M = 6755399441055744.0;
     const int cell = min(max(__double2loint(__dadd_rd(g, M)), 0), n - 2);
-    t = g - cell_to_double(cell);
+    t = g - (XUCVT ? (double)cell : cell_to_double(cell));   // XUCVT: one I2F.F64 instead of the bit trick's DADD
     return cell;
 }
 
@@ -432,6 +433,10 @@ k_stage_window(const __grid_constant__ StageParams sp, const __grid_constant__ W
 //   * shared-memory addresses are 32-bit (two IMADs per update).
 // One CTA per SM (16 warps), NS ring slots.
 // ---------------------------------------------------------------------------------------------
+#ifndef WIDE_UNROLL
+#define WIDE_UNROLL 2      // controls per iteration of k_stage_wide's loop (measured: 1 -> +4 %, 4 -> same as 2)
+#endif
+constexpr int WIDE_UNROLL_N = WIDE_UNROLL;
 constexpr int WIDE_NT = 512, WIDE_R = 4, WIDE_MAXC = 512, WIDE_MAXCH = 128;
 struct WideTables {
     double tc0[WIDE_MAXC], tc1[WIDE_MAXC], r[WIDE_MAXC];   // [P * C] each
@@ -441,7 +446,10 @@ struct WideTables {
 // the slot is handed back through an `empty` mbarrier (one arrival per warp) and the warp whose turn it is
 // (chunk index mod 16) waits for it and issues the refill, so the other warps run on into the next chunk
 // and their pipeline bubbles no longer coincide.
-template <int NS, int W0C, bool IDX32, bool BAR>
+// XU: how many of the two floor(g)-as-double values of an interior update come from the conversion pipe
+// (I2F.F64 of the cell the low word of g +(rd) M already holds) instead of the fp64 pipe's `s - M`: the
+// same exact value, one DADD fewer per dimension on the pipe that bounds the kernel.
+template <int NS, int W0C, bool IDX32, bool BAR, int XU = 0>
 __global__ void __launch_bounds__(WIDE_NT, 1)
 k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ WindowParams wp,
              const __grid_constant__ CUtensorMap tmap, const __grid_constant__ WideTables tb) {
@@ -536,7 +544,7 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     auto chunk_loop = [&](auto mode_tag, int ch, uint32_t wb) {
         constexpr int MODE = decltype(mode_tag)::value;
         const int c_end = min(sp.C, (ch + 1) * wp.cchunk);
-#pragma unroll 2
+#pragma unroll WIDE_UNROLL_N
         for (int c = ch * wp.cchunk; c < c_end; ++c) {
             const double bu0 = tb.tc0[pc + c], bu1 = tb.tc1[pc + c], rc = tb.r[pc + c];
             uint32_t a[R];
@@ -548,11 +556,16 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
                     cell0 = locate_uniform<true>(base0[u] + bu0, n0, t0[u]);
                     cell1 = locate_uniform<true, true>(base1[u] + bu1, n1, t1[u]);
                 } else if (MODE == 1) {
-                    cell0 = locate_magic_clamp(base0[u] + bu0, n0, t0[u]);
-                    cell1 = locate_magic_clamp(base1[u] + bu1, n1, t1[u]);
+                    cell0 = locate_magic_clamp<(XU >= 2)>(base0[u] + bu0, n0, t0[u]);
+                    cell1 = locate_magic_clamp<(XU >= 1)>(base1[u] + bu1, n1, t1[u]);
                 } else {
-                    cell0 = locate_magic(base0[u] + bu0, t0[u]);
-                    cell1 = locate_magic(base1[u] + bu1, t1[u]);
+                    const double M = 6755399441055744.0;
+                    const double g0 = base0[u] + bu0, g1 = base1[u] + bu1;
+                    const double s0 = __dadd_rd(g0, M), s1 = __dadd_rd(g1, M);
+                    cell0 = __double2loint(s0);
+                    cell1 = __double2loint(s1);
+                    t0[u] = g0 - (XU >= 2 ? (double)cell0 : s0 - M);
+                    t1[u] = g1 - (XU >= 1 ? (double)cell1 : s1 - M);
                 }
                 a[u] = (uint32_t)cell1 * PB + ((uint32_t)cell0 * 8u + wb);
             }
@@ -1011,6 +1024,7 @@ struct WindowState {
     WideTables *wide = nullptr;     // k_stage_wide: host copy of the constant-bank control tables (null = not used)
     int wide_ns = 2;                // ring slots
     bool strip_magic_ok = false;    // dimension-1 queries of the strip kernel stay below 2^30 cells
+    int wide_xu = 1;                // BELLMAN_WIDE_XU=0|1|2: weights of that many dimensions through I2F (k_stage_wide's XU)
     bool wide_bar = false;          // BELLMAN_WIDE_BARRIER=1: a CTA barrier per chunk instead of the empty-slot mbarriers
     size_t wide_smem = 0;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;
@@ -1135,12 +1149,12 @@ static bool strip_dispatch(const WindowState *ws, const StageParams *sp, const C
         default: return strip_go<4, 4, 7>(ws, sp, map, grid, st, sa);
     }
 }
-template <bool BAR>
+template <bool BAR, int XU = 0>
 static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid, cudaStream_t st,
                     bool set_attr_only, const WindowParams *wpo = nullptr) {
     const WindowParams &wpl = wpo ? *wpo : ws->wp;
-    auto f48 = k_stage_wide<2, 48, true, BAR>, f48n = k_stage_wide<2, 48, false, BAR>;
-    auto f0 = k_stage_wide<2, 0, true, BAR>, f0n = k_stage_wide<2, 0, false, BAR>;
+    auto f48 = k_stage_wide<2, 48, true, BAR, XU>, f48n = k_stage_wide<2, 48, false, BAR, XU>;
+    auto f0 = k_stage_wide<2, 0, true, BAR, XU>, f0n = k_stage_wide<2, 0, false, BAR, XU>;
     if (set_attr_only) {
         for (const void *f : {(const void *)f48, (const void *)f48n, (const void *)f0, (const void *)f0n})
             if (!raise_smem_limit(f, ws->wide_smem)) return false;
@@ -1153,7 +1167,10 @@ static bool wide_go(const WindowState *ws, const StageParams *sp, const CUtensor
 }
 static bool wide_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                           cudaStream_t st, bool sa, const WindowParams *wpo = nullptr) {
-    return ws->wide_bar ? wide_go<true>(ws, sp, map, grid, st, sa, wpo) : wide_go<false>(ws, sp, map, grid, st, sa, wpo);
+    if (ws->wide_bar) return wide_go<true>(ws, sp, map, grid, st, sa, wpo);
+    if (ws->wide_xu == 1) return wide_go<false, 1>(ws, sp, map, grid, st, sa, wpo);
+    if (ws->wide_xu == 2) return wide_go<false, 2>(ws, sp, map, grid, st, sa, wpo);
+    return wide_go<false>(ws, sp, map, grid, st, sa, wpo);
 }
 static void window_teardown_state(WindowState *ws) {
     cudaFree(ws->d_cmm); cudaFree(ws->d_tmm); cudaFree(ws->d_rowp); cudaFree(ws->d_colp); cudaFree(ws->d_colq);
@@ -1449,6 +1466,7 @@ void window_setup(bellman_handle *h) {
     // k_stage_wide takes the long-control-loop problems whose control tables fit its constant-bank parameter
     if (wide_cfg && !ws->strip && !ws->lean && wp.nchunks <= WIDE_MAXCH) {
         ws->wide_bar = std::getenv("BELLMAN_WIDE_BARRIER") != nullptr;
+        if (const char *e = std::getenv("BELLMAN_WIDE_XU")) ws->wide_xu = std::max(0, std::min(2, std::atoi(e)));
         ws->wide_smem = (size_t)ws->wide_ns * slot_bytes(wp.win0, wp.win1);
         if (ws->wide_smem <= 225 * 1024) {
             ws->wide = new WideTables();
