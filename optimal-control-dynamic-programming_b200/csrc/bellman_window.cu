@@ -1020,7 +1020,7 @@ struct WindowState {
     size_t lean_smem = 0;
     int strip_nw = 4;
     void *d_colq = nullptr;
-    int batch = 4, occ = 2, rstates = 8, loc = 0;
+    int occ = 2, rstates = 8;
     WideTables *wide = nullptr;     // k_stage_wide: host copy of the constant-bank control tables (null = not used)
     int wide_ns = 2;                // ring slots
     bool strip_magic_ok = false;    // dimension-1 queries of the strip kernel stay below 2^30 cells
@@ -1043,25 +1043,13 @@ template <bool HC0, bool HC1, bool CHAIN, int BATCH, int OCC, int R = 8>
 static bool window_go(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                       cudaStream_t st, bool set_attr_only) {
     if (HC0 && HC1 && BATCH == 4 && OCC == 2 && R == 8) {   // the long-control-loop kernel: pitch 48 specialisation
-        auto fn48 = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48>;
-        auto fn48a = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48, 1>;
-        auto fn48b = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48, 2>;
+        auto fn48 = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 48, 2>;
         if (set_attr_only) {
-            for (const void *f : {(const void *)fn48, (const void *)fn48a, (const void *)fn48b})
-                if (!raise_smem_limit(f, ws->smem))
-                    return false;
+            if (!raise_smem_limit((const void *)fn48, ws->smem)) return false;
         } else if (ws->wp.win0 == 48) {
-            if (ws->loc == 2) fn48b<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
-            else if (ws->loc == 1) fn48a<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
-            else fn48<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
+            fn48<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
             return true;
         }
-    }
-    if (HC0 && HC1 && !CHAIN && R == 4) {   // BELLMAN_WIN_R4 experiment: runtime pitch, both floors on the fp64 pipe
-        auto fnr = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R, 0, 2>;
-        if (set_attr_only) return raise_smem_limit((const void *)fnr, ws->smem);
-        fnr<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
-        return true;
     }
     auto fn = k_stage_window<HC0, HC1, CHAIN, BATCH, OCC, R>;
     if (set_attr_only)
@@ -1069,25 +1057,13 @@ static bool window_go(const WindowState *ws, const StageParams *sp, const CUtens
     fn<<<grid, WNT, ws->smem, st>>>(*sp, ws->wp, *map);
     return true;
 }
+// (round 1 also instantiated BATCH 2 / 8, one CTA per SM, the conversion-pipe locate variants and a 4-states-per-
+// thread form of the long-control-loop kernel as experiment knobs; none beat this configuration — DESIGN.md section 4 —
+// and they were dropped to keep the build short)
 template <bool HC0, bool HC1, bool CHAIN>
 static bool window_go_hc(const WindowState *ws, const StageParams *sp, const CUtensorMap *map, dim3 grid,
                          cudaStream_t st, bool sa) {
-    if (CHAIN && ws->rstates == 4) {
-        if (ws->occ == 3) return window_go<HC0, HC1, CHAIN, 2, 3, 4>(ws, sp, map, grid, st, sa);
-        if (ws->occ == 1) return window_go<HC0, HC1, CHAIN, 2, 4, 4>(ws, sp, map, grid, st, sa);
-        return window_go<HC0, HC1, CHAIN, 4, 4, 4>(ws, sp, map, grid, st, sa);
-    }
-    if (!CHAIN && HC0 && HC1 && ws->rstates == 4) {      // BELLMAN_WIN_R4 experiment: 3 or 4 CTAs per SM
-        if (ws->occ == 4) return window_go<HC0, HC1, CHAIN, 4, 4, 4>(ws, sp, map, grid, st, sa);
-        return window_go<HC0, HC1, CHAIN, 4, 3, 4>(ws, sp, map, grid, st, sa);
-    }
-    if (ws->occ == 1) {
-        if (ws->batch == 8) return window_go<HC0, HC1, CHAIN, 8, 1>(ws, sp, map, grid, st, sa);
-        if (ws->batch == 2) return window_go<HC0, HC1, CHAIN, 2, 1>(ws, sp, map, grid, st, sa);
-        return window_go<HC0, HC1, CHAIN, 4, 1>(ws, sp, map, grid, st, sa);
-    }
-    if (ws->batch == 8) return window_go<HC0, HC1, CHAIN, 8, 2>(ws, sp, map, grid, st, sa);
-    if (ws->batch == 2) return window_go<HC0, HC1, CHAIN, 2, 2>(ws, sp, map, grid, st, sa);
+    if (CHAIN && ws->rstates == 4) return window_go<HC0, HC1, CHAIN, 4, 4, 4>(ws, sp, map, grid, st, sa);
     return window_go<HC0, HC1, CHAIN, 4, 2>(ws, sp, map, grid, st, sa);
 }
 static bool window_dispatch(const WindowState *ws, const StageParams *sp, const CUtensorMap *map,
@@ -1239,10 +1215,7 @@ void window_setup(bellman_handle *h) {
     // small-control CHAIN problems run 4 states per thread (see k_stage_window)
     const bool chain_cfg = hp.has_c[0] && !hp.has_c[1] && hp.src_a[0] == 0 && (!hp.has_b[0] || hp.src_b[0] == 0) &&
                            !std::getenv("BELLMAN_WIN_NOCHAIN");
-    // BELLMAN_WIN_R4=1: 4 states per thread for the long-control-loop kernel too (tile 32 x 32, half the
-    // registers, more CTAs per SM) — experiment knob
-    const bool r4_all = std::getenv("BELLMAN_WIN_R4") != nullptr;
-    const int rstates = ((chain_cfg && hp.C <= 8 && !std::getenv("BELLMAN_WIN_R8")) || (r4_all && !chain_cfg)) ? 4 : 8;
+    const int rstates = (chain_cfg && hp.C <= 8 && !std::getenv("BELLMAN_WIN_R8")) ? 4 : 8;
     // k_stage_strip geometry: NW warps per CTA, each walking strip_r columns (tile 32 x NW*strip_r)
     const bool lean_cfg = chain_cfg && rstates == 4 && hp.C <= 4 && !std::getenv("BELLMAN_WIN_NOLEAN");
     const bool strip_cfg = lean_cfg && !std::getenv("BELLMAN_WIN_NOSTRIP");
@@ -1437,13 +1410,9 @@ void window_setup(bellman_handle *h) {
         if (r != CUDA_SUCCESS) { window_teardown_state(ws); return; }
     }
     {
-        const char *eb = std::getenv("BELLMAN_WIN_BATCH"), *eo = std::getenv("BELLMAN_WIN_OCC");
-        ws->batch = eb ? std::atoi(eb) : 4;
+        const char *eo = std::getenv("BELLMAN_WIN_OCC");      // 3: the strip kernel's 5-CTA register budget
         ws->occ = eo ? std::atoi(eo) : 2;
-        if (ws->batch != 2 && ws->batch != 4 && ws->batch != 8) ws->batch = 4;
         if (ws->occ < 1 || ws->occ > 4) ws->occ = 2;
-        ws->loc = 2;
-        if (const char *el = std::getenv("BELLMAN_WIN_LOC")) ws->loc = std::atoi(el);
     }
     if (!window_dispatch(ws, nullptr, nullptr, nullptr, dim3(), nullptr, true)) { window_teardown_state(ws); return; }
     ws->strip = strip_cfg && wp.cchunk == 1 && wp.nchunks <= 4 && wp.boxes == 1 && !wp.col1_zero &&
