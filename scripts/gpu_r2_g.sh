@@ -1,4 +1,5 @@
 #!/bin/bash
+# (historical: the BELLMAN_WIN_R4 variant measured here lost and was removed from the library afterwards)
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
