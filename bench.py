@@ -309,11 +309,12 @@ def rollout_rate(bb, local):
     g = np.linspace(o.x_min, o.x_max, 64)
     x0 = np.stack(np.meshgrid(g, g, indexing="ij"), axis=-1).reshape(-1, 2)
     sw.rollout(o.A, o.B, d.meta["U_mesh"], x0)                 # warm-up
-    t0 = time.perf_counter()
-    reps = 5
+    reps, dts = 5, []
     for _ in range(reps):
+        t0 = time.perf_counter()
         sw.rollout(o.A, o.B, d.meta["U_mesh"], x0)
-    dt = (time.perf_counter() - t0) / reps
+        dts.append(time.perf_counter() - t0)
+    dt = float(np.median(dts))          # the call allocates and copies through pageable host arrays: take the median
     sw.close()
     return {"x0": len(x0), "steps": d.N - 1, "ms": dt * 1e3, "trajectories_per_s": len(x0) / dt,
             "state_steps_per_s": len(x0) * (d.N - 1) / dt, "call": "bellman_rollout (host x0 in, X and U out)"}
