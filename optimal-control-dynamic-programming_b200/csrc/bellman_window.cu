@@ -166,11 +166,28 @@ __device__ __forceinline__ int locate_magic(double g, double &t) {
 // the bound): floor from the low word of g +(rd) M as above, clamp on the integer pipe, (double)cell by the
 // bit trick.  Same cell and the same exact difference g - cell as locate_uniform<true> — F2I.F64 / I2F.F64
 // occupy a scheduler's conversion pipe for 8 cycles per warp instruction, a DADD the fp64 pipe for 2.
+// clamp(x, 0, hi) in one instruction (VIMNMX.RELU)
+__device__ __forceinline__ int clamp_relu(int x, int hi) {
+    int r;
+    asm("min.relu.s32 %0, %1, %2;" : "=r"(r) : "r"(x), "r"(hi));
+    return r;
+}
 template <bool XUCVT = false>
 __device__ __forceinline__ int locate_magic_clamp(double g, int n, double &t) {
     const double M = 6755399441055744.0;
-    const int cell = min(max(__double2loint(__dadd_rd(g, M)), 0), n - 2);
+    const int cell = clamp_relu(__double2loint(__dadd_rd(g, M)), n - 2);
     t = g - (XUCVT ? (double)cell : cell_to_double(cell));   // XUCVT: one I2F.F64 instead of the bit trick's DADD
+    return cell;
+}
+// one dimension of k_stage_wide's locate: CLAMPED as above, else the interior form (floor(g) as a double from
+// `s - M`, or from the conversion pipe when XUCVT)
+template <bool CLAMPED, bool XUCVT>
+__device__ __forceinline__ int locate_dim(double g, int n, double &t) {
+    if (CLAMPED) return locate_magic_clamp<XUCVT>(g, n, t);
+    const double M = 6755399441055744.0;
+    const double s = __dadd_rd(g, M);
+    const int cell = __double2loint(s);
+    t = g - (XUCVT ? (double)cell : s - M);
     return cell;
 }
 
@@ -478,8 +495,8 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     // Chunk table, one entry per chunk, built once per CTA by the first nchunks threads: the window origin
     // (TMA coordinates and element offset) and how the chunk's queries may be located.  The bounds are exact:
     // per-tile / per-chunk table extrema summed with the kernel's own association (as k_stage_window).
-    //   mode 0: every query falls in an interior cell (no clamp); 1: clamped, |g| < 2^30 (no conversion
-    //   instructions); 2: clamped, conversion pipe (queries beyond 2^30 cells: never in practice)
+    //   mode bit 0 / bit 1: dimension 0 / 1 has queries outside the interior cells and is clamped (|g| < 2^30: no
+    //   F2I); mode 4: clamped through the conversion pipe (queries beyond 2^30 cells: never in practice)
     if (tid < wp.nchunks) {
         const double *tm = wp.tmm + (size_t)prob * wp.tmm_stride;
         auto tmm_load = [&](int k) -> double {
@@ -498,9 +515,10 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
         r0 -= (r0 - d0.ext_lo) & 1;                  // TMA: even innermost coordinate
         const int c0 = cell_uniform(lo1, n1);
         const double BIG = 1073741824.0;
-        const bool interior = lo0 >= 0.0 && hi0 < (double)(n0 - 1) && lo1 >= 0.0 && hi1 < (double)(n1 - 1);
+        const bool in0 = lo0 >= 0.0 && hi0 < (double)(n0 - 1), in1 = lo1 >= 0.0 && hi1 < (double)(n1 - 1);
         const bool small = lo0 > -BIG && hi0 < BIG && lo1 > -BIG && hi1 < BIG;
-        cinfo[tid] = make_int4(r0 - d0.ext_lo, c0 - d1.ext_lo, c0 * (W0C ? W0C : wp.win0) + r0, interior ? 0 : small ? 1 : 2);
+        cinfo[tid] = make_int4(r0 - d0.ext_lo, c0 - d1.ext_lo, c0 * (W0C ? W0C : wp.win0) + r0,
+                               small ? (in0 ? 0 : 1) | (in1 ? 0 : 2) : 4);
     }
     __syncthreads();
 
@@ -539,8 +557,7 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
     const uint32_t PB = (uint32_t)(W0C ? W0C : wp.win0) * 8u;      // window pitch in bytes
     const uint32_t ring_u32 = smem_u32(ring);
 
-    // MODE 0: every query of the chunk falls in an interior cell (no clamp); 1: clamped, |g| < 2^30 (no
-    // conversion instructions); 2: clamped, conversion pipe (queries beyond 2^30 cells: never in practice)
+    // MODE: the chunk-table mode (which dimensions are clamped)
     auto chunk_loop = [&](auto mode_tag, int ch, uint32_t wb) {
         constexpr int MODE = decltype(mode_tag)::value;
         const int c_end = min(sp.C, (ch + 1) * wp.cchunk);
@@ -552,20 +569,12 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
 #pragma unroll
             for (int u = 0; u < R; ++u) {
                 int cell0, cell1;
-                if (MODE == 2) {
+                if (MODE == 4) {
                     cell0 = locate_uniform<true>(base0[u] + bu0, n0, t0[u]);
                     cell1 = locate_uniform<true, true>(base1[u] + bu1, n1, t1[u]);
-                } else if (MODE == 1) {
-                    cell0 = locate_magic_clamp<(XU >= 2)>(base0[u] + bu0, n0, t0[u]);
-                    cell1 = locate_magic_clamp<(XU >= 1)>(base1[u] + bu1, n1, t1[u]);
                 } else {
-                    const double M = 6755399441055744.0;
-                    const double g0 = base0[u] + bu0, g1 = base1[u] + bu1;
-                    const double s0 = __dadd_rd(g0, M), s1 = __dadd_rd(g1, M);
-                    cell0 = __double2loint(s0);
-                    cell1 = __double2loint(s1);
-                    t0[u] = g0 - (XU >= 2 ? (double)cell0 : s0 - M);
-                    t1[u] = g1 - (XU >= 1 ? (double)cell1 : s1 - M);
+                    cell0 = locate_dim<(MODE & 1) != 0, (XU >= 2)>(base0[u] + bu0, n0, t0[u]);
+                    cell1 = locate_dim<(MODE & 2) != 0, (XU >= 1)>(base1[u] + bu1, n1, t1[u]);
                 }
                 a[u] = (uint32_t)cell1 * PB + ((uint32_t)cell0 * 8u + wb);
             }
@@ -597,8 +606,10 @@ k_stage_wide(const __grid_constant__ StageParams sp, const __grid_constant__ Win
         uint32_t wb = ring_u32 + (uint32_t)(s * wp.buf_doubles) * 8u - (uint32_t)ci.z * 8u;
         asm volatile("" : "+r"(wb)::"memory");
         if (ci.w == 0) chunk_loop(std::integral_constant<int, 0>{}, ch, wb);
+        else if (ci.w == 2) chunk_loop(std::integral_constant<int, 2>{}, ch, wb);
         else if (ci.w == 1) chunk_loop(std::integral_constant<int, 1>{}, ch, wb);
-        else chunk_loop(std::integral_constant<int, 2>{}, ch, wb);
+        else if (ci.w == 3) chunk_loop(std::integral_constant<int, 3>{}, ch, wb);
+        else chunk_loop(std::integral_constant<int, 4>{}, ch, wb);
         if (BAR) {
             __syncthreads();   // every thread is done with this slot
             if (tid == 0 && ch + NS < wp.nchunks) issue(ch + NS);
@@ -1024,7 +1035,7 @@ struct WindowState {
     WideTables *wide = nullptr;     // k_stage_wide: host copy of the constant-bank control tables (null = not used)
     int wide_ns = 2;                // ring slots
     bool strip_magic_ok = false;    // dimension-1 queries of the strip kernel stay below 2^30 cells
-    int wide_xu = 1;                // BELLMAN_WIDE_XU=0|1|2: weights of that many dimensions through I2F (k_stage_wide's XU)
+    int wide_xu = 2;                // BELLMAN_WIDE_XU=0|1|2: weights of that many dimensions through I2F (k_stage_wide's XU)
     bool wide_bar = false;          // BELLMAN_WIDE_BARRIER=1: a CTA barrier per chunk instead of the empty-slot mbarriers
     size_t wide_smem = 0;
     void *d_cmm = nullptr, *d_tmm = nullptr, *d_rowp = nullptr, *d_colp = nullptr;

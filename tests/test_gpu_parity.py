@@ -82,7 +82,7 @@ def test_kirk_reference_size_first_stages(bellman, oracle_lib, kernel):
     sw.close()
 
 
-WINDOW_VARIANTS = ["wide", "ring", "wide_bar", "wide_xu0", "wide_xu2"]   # k_stage_wide (default), k_stage_window, k_stage_wide with a CTA barrier per chunk
+WINDOW_VARIANTS = ["wide", "ring", "wide_bar", "wide_xu0", "wide_xu1"]   # k_stage_wide (default), k_stage_window, k_stage_wide with a CTA barrier per chunk
 
 
 def _window_variant(monkeypatch, variant):
@@ -92,7 +92,7 @@ def _window_variant(monkeypatch, variant):
         return "window:ring"
     if variant == "wide_bar":
         monkeypatch.setenv("BELLMAN_WIDE_BARRIER", "1")
-    if variant.startswith("wide_xu"):      # weights of 0 / 2 dimensions through the conversion pipe (default: 1)
+    if variant.startswith("wide_xu"):      # weights of 0 / 1 dimensions through the conversion pipe (default: both)
         monkeypatch.setenv("BELLMAN_WIDE_XU", variant[-1])
     return "window:wide"
 
