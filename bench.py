@@ -591,7 +591,9 @@ def main():
     achieved = bytes_per_launch / (ms_kernel * 1e-3) / 1e9
     # secondary bound: fp64 pipe, 64 lanes/clk/SM x 148 SMs at the clock seen
     mhz = (clocks or {}).get("sm_mhz") or 1965.0
-    fp64_ops_per_update = 17.0     # window kernel interior loop, SASS-counted: 13 DADD (incl. 2 x 3 for the fp64-pipe floor) + 3 DFMA + 1 DSETP
+    # SASS-counted, interior loop: k_stage_wide issues 15 instructions per update on the fp64 pipe (11 DADD, 3 DFMA,
+    # 1 DSETP) plus 2 I2F.F64 on the conversion pipe; k_stage_window 17 on the fp64 pipe
+    fp64_ops_per_update = 15.0 if kernel_name == "window:wide" else 17.0
     fp64_peak = 64 * 148 * mhz * 1e6
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": NCU_TRAFFIC.get(args.workload, (None, None))[0],
@@ -601,7 +603,9 @@ def main():
                                    "achieved_ops_per_s": value / world * fp64_ops_per_update,
                                    "peak_ops_per_s": fp64_peak,
                                    "frac": value / world * fp64_ops_per_update / fp64_peak,
-                                   "note": "C>=16 makes the stage fp64-issue bound, not HBM bound (DESIGN.md)"}}
+                                   "conversion_pipe_ops_per_update": 2.0 if kernel_name == "window:wide" else 0.0,
+                                   "note": "C>=16 makes the stage fp64-issue bound, not HBM bound; the fp64 pipe and the "
+                                           "shared-memory loads overlap only partly (DESIGN.md section 4)"}}
 
     # other configurations of BASELINE.json, device-resident, same timing rules (N = 1 only):
     # the small-control ones are where the HBM roofline is the relevant bound
