@@ -223,7 +223,7 @@ def run_reference_arm(args):
         return
     import bellman_b200 as bb
     d = make_desc(bb, args.workload)
-    per_step = max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
+    per_step = args.ref_seconds or max(1.0, min(20.0, 120.0 / max(1, args.steps + args.warmup)))
     for _ in range(args.warmup):
         cpu_sample_rate(d, per_step)
     rates, dts = [], []
@@ -332,6 +332,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-others", action="store_true", help="skip the secondary workloads (N = 1 default run)")
+    ap.add_argument("--ref-seconds", type=float, default=0.0,
+                    help="--impl reference: CPU seconds per step (default: sized so that the run ends within minutes)")
     ap.add_argument("--no-balance", action="store_true", help="N > 1: keep equal slabs (no trial-run balancing)")
     ap.add_argument("--idx-bytes", type=int, default=4, choices=[1, 2, 4],
                     help="device storage of the argmin (4 = int32, the canonical 20 B/state of SURVEY 8d)")
