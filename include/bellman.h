@@ -237,8 +237,9 @@ int  bellman_owned_range(const bellman_handle *h, bellman_slab *out);
    total ms, number of stage-kernel launches, and ms spent in halo exchange */
 int  bellman_last_run_stats(const bellman_handle *h, double *ms_total, int64_t *kernel_launches,
                             double *ms_exchange);
-/* name of the stage kernel the last run used: "direct", "splitc", "persistent", "tile", or "window:<variant>"
-   (variant = strip | chain | ring-chain | ring, the TMA-staged D = 2 kernels) */
+/* name of the stage kernel the last run used: "direct", "splitc", "persistent", "tile", "stream" (the factorised
+   D = 4 kernel), or "window:<variant>" (variant = wide | strip | chain | ring-chain | ring, the TMA-staged D = 2
+   kernels) */
 const char *bellman_last_kernel(const bellman_handle *h);
 
 /* batched forward rollout of test/Dynamic_Solver.m:108-145 (D = 2, P = 1, store_idx_all):
