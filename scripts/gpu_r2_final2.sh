@@ -22,3 +22,12 @@ print("cfg5", d["cfg5"]["ms_per_step"], d["cfg5"]["value"])
 PY
 tail -n 3 gpurun_out/final2_bench_time.txt
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 | tail -n 1 | cut -c1-400
+B="python bench.py --no-cpu-baseline --no-e2e --no-others --steps 3 --warmup 3"
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_stage_wide -s 3 -c 1 -f -o gpurun_out/r02_wide_kirk \
+  $B > gpurun_out/final2_ncu.log 2>&1
+ncu -i gpurun_out/r02_wide_kirk.ncu-rep --page raw --csv > gpurun_out/r02_wide_kirk_raw.csv 2>/dev/null
+python scripts/ncu_summary.py gpurun_out/r02_wide_kirk_raw.csv > gpurun_out/r02_wide_kirk_summary.txt
+cat gpurun_out/r02_wide_kirk_summary.txt
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r02_launches_default_bench.csv \
+  python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/final2_launch_bench.log 2>&1
+grep -c k_stage gpurun_out/r02_launches_default_bench.csv
