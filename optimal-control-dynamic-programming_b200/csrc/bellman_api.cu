@@ -970,7 +970,8 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     const int from = h->cur_stage, to = from - 1;
     const int n0 = hp.n[0], n1 = hp.n[1];
     const int e0 = h->ext_lo[0], en0 = h->ext_n[0], o0 = h->own_lo[0], on0 = h->own_n[0];   // rows held / owned
-    const int NSLAB = 8;
+    int NSLAB = 8;                                                 // slabs of dimension-1 tiles (BELLMAN_HOST_SLABS: 2..32)
+    if (const char *e = std::getenv("BELLMAN_HOST_SLABS")) NSLAB = std::max(2, std::min(32, std::atoi(e)));
     const int tps = (ntile1 + NSLAB - 1) / NSLAB;                  // tiles per slab
     const int nslab = (ntile1 + tps - 1) / tps;
     cudaStream_t s_in = nullptr, s_out = nullptr;
