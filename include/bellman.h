@@ -213,7 +213,7 @@ int  bellman_stage(bellman_handle *h);                      /* one backward stag
  * same results bit for bit.  J_next_host NULL = continue from the J already on the device (plain
  * bellman_run(1) + the two reads); J_out_host / idx_out_host may be NULL.  Where the stage kernel can run a
  * range of tiles (k_stage_wide: D = 2, P = 1, int32 indices; one rank, or slabs along dimension 0 with the
- * peer-memory halo, every rank calling it) the grid is processed in 8 slabs of
+ * peer-memory halo, every rank calling it) the grid is processed in up to 16 slabs of
  * dimension 1: J_{k+1} goes up in column chunks, a slab starts as soon as the highest column it can query
  * has arrived (exact reach analysis), and finished slabs go down while later ones compute.  Every other
  * configuration runs the plain sequence.  Pinned host memory is needed for the overlap (pageable memory

@@ -713,6 +713,7 @@ def test_stage_host_pipelined_equals_sequence_and_oracle(bellman, oracle_lib, mo
     obj = bellman.Dynamic_Solver()
     t = bellman.tables
     rng = np.random.default_rng(11)
+    monkeypatch.setenv("BELLMAN_HOST_SLABS", "8")       # (the default adapts to the grid: 2 slabs at these sizes)
     for n0, n1, C in ((256, 1024, 48), (130, 777, 33)):
         s0, s1, u = t.linspace(-2.5, 3.0, n0), t.linspace(-2.5, 3.0, n1), t.linspace(-40.0, 10.0, C)
         A, B = obj.A, obj.B.ravel()
@@ -744,6 +745,11 @@ def test_stage_host_pipelined_equals_sequence_and_oracle(bellman, oracle_lib, mo
     with bellman.Sweep(da) as sw:
         J, I = sw.stage_host(np.zeros((da.P, da.S)))
         assert_stage_equal(J, I, oa["J_last"], oa["idx_last"], "stage_host fallback")
+    monkeypatch.delenv("BELLMAN_HOST_SLABS")
+    with bellman.Sweep(d) as sw:                        # default slab count on this small grid: 2
+        J, I = sw.stage_host(JN, kernel=KERNELS["window"])
+        assert sw.stats()["launches"] == 2
+        assert np.array_equal(J, J1) and np.array_equal(I, I1)
     monkeypatch.setenv("BELLMAN_NO_HOST_PIPELINE", "1")
     with bellman.Sweep(d) as sw:
         J, I = sw.stage_host(JN, kernel=KERNELS["window"])
