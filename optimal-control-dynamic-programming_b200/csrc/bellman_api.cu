@@ -970,11 +970,11 @@ extern "C" int bellman_stage_host(bellman_handle *h, const double *J_next_host, 
     const int from = h->cur_stage, to = from - 1;
     const int n0 = hp.n[0], n1 = hp.n[1];
     const int e0 = h->ext_lo[0], en0 = h->ext_n[0], o0 = h->own_lo[0], on0 = h->own_n[0];   // rows held / owned
-    // slabs of dimension-1 tiles: as many as keep every launch at >= ~8 waves of CTAs, at most 16 (measured on
-    // cfg 4: 8 slabs 50.0 ms per step, 16 slabs 48.1, 24 slabs 50.0); BELLMAN_HOST_SLABS overrides (2..32)
-    const long long tiles0 = (h->own_n[0] + 31) / 32;
-    int NSLAB = (int)std::max(2LL, std::min(16LL, tiles0 * ntile1 / (148 * 8)));
-    if (h->nranks > 1) NSLAB = 8;      // sharded: the copies weigh more (shared PCIe); 8 is what was measured at N = 2 and 8
+    // slabs of dimension-1 tiles: 16 while a launch keeps >= 4 waves of CTAs, else 8, else 2 (measured end to end
+    // on cfg 4: N = 1: 8 slabs 50.0 ms, 16 slabs 48.1, 24 slabs 50.0; N = 2: 4 / 8 / 16 slabs 27.0 / 25.6 / 24.8 ms;
+    // N = 8 ran with 8); BELLMAN_HOST_SLABS overrides (2..32)
+    const long long ctas = (long long)((h->own_n[0] + 31) / 32) * ntile1;
+    int NSLAB = ctas >= 16LL * 148 * 4 && ntile1 >= 16 ? 16 : ctas >= 8LL * 148 * 2 ? 8 : 2;
     if (const char *e = std::getenv("BELLMAN_HOST_SLABS")) NSLAB = std::max(2, std::min(32, std::atoi(e)));
     const int tps = (ntile1 + NSLAB - 1) / NSLAB;                  // tiles per slab
     const int nslab = (ntile1 + tps - 1) / tps;
