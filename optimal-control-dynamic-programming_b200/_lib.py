@@ -336,13 +336,19 @@ class Sweep:
             self.lib.bellman_get_check_log(self.h, out.ctypes.data_as(_dp), n)
         return out
 
-    def rollout(self, A, B, u_values, x0, mode=0, ssu_stage=1):
-        """x0: [batch, 2].  Returns X [batch, N, 2], U [batch, N]."""
+    def rollout(self, A, B, u_values, x0, mode=0, ssu_stage=1, out=None):
+        """x0: [batch, 2].  Returns X [batch, N, 2], U [batch, N] (``out=(X, U)``: preallocated, e.g. pinned, arrays)."""
         x0 = _f64(x0).reshape(-1, 2)
         batch = x0.shape[0]
         N = self.desc.N
-        X = np.empty((batch, N, 2))
-        U = np.empty((batch, N))
+        if out is not None:
+            X, U = out
+            if X.dtype != np.float64 or U.dtype != np.float64 or X.size != batch * N * 2 or U.size != batch * N \
+                    or not (X.flags.c_contiguous and U.flags.c_contiguous):
+                raise ValueError("out must be C-contiguous float64 arrays of shapes [batch, N, 2] and [batch, N]")
+        else:
+            X = np.empty((batch, N, 2))
+            U = np.empty((batch, N))
         A = _f64(np.asarray(A, dtype=np.float64).reshape(2, 2).ravel(order="F"))
         B = _f64(np.asarray(B, dtype=np.float64).ravel())
         uv = _f64(u_values)

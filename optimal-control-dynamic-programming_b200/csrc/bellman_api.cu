@@ -297,6 +297,7 @@ extern "C" void bellman_destroy(bellman_handle *h) {
     }
     cudaFree(h->d_barrier);
     cudaFree(h->d_comm_scratch);
+    cudaFree(h->d_roll);
     if (h->comm) {
         std::string e;
         NcclApi *api = nccl_api(e);
@@ -1091,13 +1092,22 @@ extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double 
     if (mode == 1 && (ssu_stage < 1 || ssu_stage > hp.N - 1)) return BELLMAN_ERR_BAD_ARG;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int N = hp.N;
-    double *d_u = nullptr, *d_x0 = nullptr, *d_X = nullptr, *d_U = nullptr;
-    auto cleanup = [&]() { cudaFree(d_u); cudaFree(d_x0); cudaFree(d_X); cudaFree(d_U); };
+    // one grow-only device buffer per handle, carved into u_values | x0 | X | U (a lattice of rollouts is called
+    // repeatedly: four cudaMalloc / cudaFree pairs per call cost more than the kernel)
+    auto cleanup = [&]() {};
 #define RT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
-    RT(cudaMalloc(&d_u, sizeof(double) * hp.C));
-    RT(cudaMalloc(&d_x0, sizeof(double) * 2 * (size_t)batch));
-    RT(cudaMalloc(&d_X, sizeof(double) * 2 * (size_t)N * batch));
-    RT(cudaMalloc(&d_U, sizeof(double) * (size_t)N * batch));
+    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+    const size_t b_u = al(sizeof(double) * hp.C), b_x0 = al(sizeof(double) * 2 * (size_t)batch),
+                 b_X = al(sizeof(double) * 2 * (size_t)N * batch), b_U = al(sizeof(double) * (size_t)N * batch);
+    if (h->d_roll_bytes < b_u + b_x0 + b_X + b_U) {
+        cudaFree(h->d_roll);
+        h->d_roll = nullptr;
+        h->d_roll_bytes = 0;
+        RT(cudaMalloc(&h->d_roll, b_u + b_x0 + b_X + b_U));
+        h->d_roll_bytes = b_u + b_x0 + b_X + b_U;
+    }
+    double *d_u = reinterpret_cast<double *>(h->d_roll), *d_x0 = reinterpret_cast<double *>(h->d_roll + b_u),
+           *d_X = reinterpret_cast<double *>(h->d_roll + b_u + b_x0), *d_U = reinterpret_cast<double *>(h->d_roll + b_u + b_x0 + b_X);
     RT(cudaMemcpyAsync(d_u, u_values, sizeof(double) * hp.C, cudaMemcpyHostToDevice, h->stream));
     RT(cudaMemcpyAsync(d_x0, x0, sizeof(double) * 2 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
     RolloutParams rp;

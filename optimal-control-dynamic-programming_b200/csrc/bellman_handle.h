@@ -50,6 +50,8 @@ struct bellman_handle {
     uint32_t *d_flags = nullptr;      // tail of the J allocation: flags[q] = stages rank q has completed (fused halo)
     uint32_t halo_seq = 0;            // stages this rank has completed since bellman_comm_init
     unsigned char *d_comm_scratch = nullptr;   // IPC-handle all-gather buffer (partitioned handles)
+    unsigned char *d_roll = nullptr;           // bellman_rollout's device buffers (grow-only, reused across calls)
+    size_t d_roll_bytes = 0;
     // window kernel state
     bellman::WindowConfig wcfg;
     void *wstate = nullptr;           // bellman_window.cu: WindowState (tensor maps, chunk tables)
