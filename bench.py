@@ -318,8 +318,16 @@ def rollout_rate(bb, local):
         sw.rollout(o.A, o.B, d.meta["U_mesh"], x0, out=(X, U))
         dts.append(time.perf_counter() - t0)
     dt = float(np.median(dts))
+    # one 'nearest' policy query per call, as a user's own simulation loop would issue them (U_Opt(x, v) per step)
+    q = np.array([[0.3, -0.2]])
+    sw.policy_lookup(q, stage=1)
+    lat = []
+    for _ in range(200):
+        t0 = time.perf_counter()
+        sw.policy_lookup(q, stage=1)
+        lat.append(time.perf_counter() - t0)
     sw.close()
-    return {"x0": len(x0), "steps": d.N - 1, "ms": dt * 1e3, "trajectories_per_s": len(x0) / dt,
+    return {"x0": len(x0), "steps": d.N - 1, "ms": dt * 1e3, "policy_lookup_single_query_us": float(np.median(lat)) * 1e6, "trajectories_per_s": len(x0) / dt,
             "state_steps_per_s": len(x0) * (d.N - 1) / dt, "call": "bellman_rollout (host x0 in, X and U out into pinned host arrays; median of %d calls)" % reps}
 
 

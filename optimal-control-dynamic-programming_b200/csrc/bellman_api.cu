@@ -1081,6 +1081,22 @@ extern "C" const char *bellman_last_kernel(const bellman_handle *h) { return h ?
 // ---------------------------------------------------------------------------------------------
 // rollout
 // ---------------------------------------------------------------------------------------------
+// One grow-only device buffer per handle for the consumers' inputs and outputs (a simulation loop calls the
+// lookup / rollout entry points over and over: cudaMalloc + cudaFree per call cost more than the kernels).
+// Returns nullptr (and sets h->err) when the allocation fails.
+static unsigned char *consumer_scratch(bellman_handle *h, size_t bytes) {
+    if (h->d_roll_bytes < bytes) {
+        cudaFree(h->d_roll);
+        h->d_roll = nullptr;
+        h->d_roll_bytes = 0;
+        const cudaError_t e = cudaMalloc(&h->d_roll, bytes);
+        if (e != cudaSuccess) { h->err = cudaGetErrorString(e); h->d_roll = nullptr; return nullptr; }
+        h->d_roll_bytes = bytes;
+    }
+    return h->d_roll;
+}
+static size_t align256(size_t b) { return (b + 255) / 256 * 256; }
+
 extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double *B, const double *u_values,
                                const double *x0, int32_t batch, int32_t mode, int32_t ssu_stage,
                                double *X_out, double *U_out) {
@@ -1092,22 +1108,14 @@ extern "C" int bellman_rollout(bellman_handle *h, const double *A, const double 
     if (mode == 1 && (ssu_stage < 1 || ssu_stage > hp.N - 1)) return BELLMAN_ERR_BAD_ARG;
     CUDA_TRY(h, cudaSetDevice(h->device));
     const int N = hp.N;
-    // one grow-only device buffer per handle, carved into u_values | x0 | X | U (a lattice of rollouts is called
-    // repeatedly: four cudaMalloc / cudaFree pairs per call cost more than the kernel)
     auto cleanup = [&]() {};
 #define RT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
-    auto al = [](size_t b) { return (b + 255) / 256 * 256; };
-    const size_t b_u = al(sizeof(double) * hp.C), b_x0 = al(sizeof(double) * 2 * (size_t)batch),
-                 b_X = al(sizeof(double) * 2 * (size_t)N * batch), b_U = al(sizeof(double) * (size_t)N * batch);
-    if (h->d_roll_bytes < b_u + b_x0 + b_X + b_U) {
-        cudaFree(h->d_roll);
-        h->d_roll = nullptr;
-        h->d_roll_bytes = 0;
-        RT(cudaMalloc(&h->d_roll, b_u + b_x0 + b_X + b_U));
-        h->d_roll_bytes = b_u + b_x0 + b_X + b_U;
-    }
-    double *d_u = reinterpret_cast<double *>(h->d_roll), *d_x0 = reinterpret_cast<double *>(h->d_roll + b_u),
-           *d_X = reinterpret_cast<double *>(h->d_roll + b_u + b_x0), *d_U = reinterpret_cast<double *>(h->d_roll + b_u + b_x0 + b_X);
+    const size_t b_u = align256(sizeof(double) * hp.C), b_x0 = align256(sizeof(double) * 2 * (size_t)batch),
+                 b_X = align256(sizeof(double) * 2 * (size_t)N * batch), b_U = align256(sizeof(double) * (size_t)N * batch);
+    unsigned char *buf = consumer_scratch(h, b_u + b_x0 + b_X + b_U);      // u_values | x0 | X | U
+    if (!buf) return BELLMAN_ERR_CUDA;
+    double *d_u = reinterpret_cast<double *>(buf), *d_x0 = reinterpret_cast<double *>(buf + b_u),
+           *d_X = reinterpret_cast<double *>(buf + b_u + b_x0), *d_U = reinterpret_cast<double *>(buf + b_u + b_x0 + b_X);
     RT(cudaMemcpyAsync(d_u, u_values, sizeof(double) * hp.C, cudaMemcpyHostToDevice, h->stream));
     RT(cudaMemcpyAsync(d_x0, x0, sizeof(double) * 2 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
     RolloutParams rp;
@@ -1170,12 +1178,13 @@ extern "C" int bellman_policy_lookup(bellman_handle *h, int32_t prob, int32_t st
     if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
     CUDA_TRY(h, cudaSetDevice(h->device));
     const HostProblem &hp = h->hp;
-    double *d_x = nullptr;
-    int32_t *d_o = nullptr;
-    auto cleanup = [&]() { cudaFree(d_x); cudaFree(d_o); };
+    auto cleanup = [&]() {};
 #define PT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
-    PT(cudaMalloc(&d_x, sizeof(double) * (size_t)hp.D * batch));
-    PT(cudaMalloc(&d_o, sizeof(int32_t) * (size_t)batch));
+    const size_t b_x = align256(sizeof(double) * (size_t)hp.D * batch);
+    unsigned char *buf = consumer_scratch(h, b_x + align256(sizeof(int32_t) * (size_t)batch));      // x | idx
+    if (!buf) return BELLMAN_ERR_CUDA;
+    double *d_x = reinterpret_cast<double *>(buf);
+    int32_t *d_o = reinterpret_cast<int32_t *>(buf + b_x);
     PT(cudaMemcpyAsync(d_x, x, sizeof(double) * (size_t)hp.D * batch, cudaMemcpyHostToDevice, h->stream));
     pp.batch = batch;
     pp.idx = h->idx_ptr(stage, prob);
@@ -1207,13 +1216,14 @@ extern "C" int bellman_rollout_axis(bellman_handle *h, int32_t prob, int32_t tim
         if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
     }
     CUDA_TRY(h, cudaSetDevice(h->device));
-    double *d_x = nullptr, *d_X = nullptr, *d_u = nullptr;
-    int32_t *d_c = nullptr;
-    auto cleanup = [&]() { cudaFree(d_x); cudaFree(d_X); cudaFree(d_u); cudaFree(d_c); };
-    PT(cudaMalloc(&d_x, sizeof(double) * 2 * (size_t)batch));
-    PT(cudaMalloc(&d_X, sizeof(double) * 2 * (size_t)(n_steps + 1) * batch));
-    PT(cudaMalloc(&d_u, sizeof(double) * (size_t)hp.C));
-    PT(cudaMalloc(&d_c, sizeof(int32_t) * (size_t)n_steps * batch));
+    auto cleanup = [&]() {};
+    const size_t b_x = align256(sizeof(double) * 2 * (size_t)batch), b_X = align256(sizeof(double) * 2 * (size_t)(n_steps + 1) * batch),
+                 b_u = align256(sizeof(double) * (size_t)hp.C), b_c = align256(sizeof(int32_t) * (size_t)n_steps * batch);
+    unsigned char *buf = consumer_scratch(h, b_x + b_X + b_u + b_c);       // x0 | X | u_inc | control indices
+    if (!buf) return BELLMAN_ERR_CUDA;
+    double *d_x = reinterpret_cast<double *>(buf), *d_X = reinterpret_cast<double *>(buf + b_x),
+           *d_u = reinterpret_cast<double *>(buf + b_x + b_X);
+    int32_t *d_c = reinterpret_cast<int32_t *>(buf + b_x + b_X + b_u);
     PT(cudaMemcpyAsync(d_x, x0, sizeof(double) * 2 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
     PT(cudaMemcpyAsync(d_u, u_inc, sizeof(double) * (size_t)hp.C, cudaMemcpyHostToDevice, h->stream));
     pp.batch = batch;
