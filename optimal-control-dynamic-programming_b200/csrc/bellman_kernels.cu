@@ -3,6 +3,7 @@
 // Compiled with -fmad=false: every written operation is rounded once, exactly as
 // include/bellman.h specifies; the only fused operations are the explicit fma() calls.
 // No tensor cores: the stage is a gather-and-reduce, not a contraction.
+#include <cstdlib>
 #include <cstdint>
 
 #include "bellman_kernels.cuh"
@@ -297,11 +298,13 @@ __device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int
     __syncthreads();
 }
 
-template <int D>
-__global__ void __launch_bounds__(BLOCK, (D == 2 ? 4 : 2))
+// PB: threads per CTA.  The grid barrier costs one atomic per CTA per stage, and for launch-latency-sized
+// problems the barrier IS the stage time, so D = 2 also exists with 1024-thread CTAs (a quarter of the arrivals).
+template <int D, int PB = BLOCK>
+__global__ void __launch_bounds__(PB, (D == 2 ? 1024 / PB : 2))
 k_sweep_persistent(const __grid_constant__ StageParams sp, const __grid_constant__ PersistParams pp) {
     const int L = pp.lanes;
-    const long long gtid = (long long)blockIdx.x * BLOCK + threadIdx.x;
+    const long long gtid = (long long)blockIdx.x * PB + threadIdx.x;
     const long long total = sp.S_own * sp.P;              // states over all problems
     long long g = gtid / L;
     const int lane = (int)(gtid % L);
@@ -725,7 +728,7 @@ int persistent_capacity_threads(int D) {
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaError_t e = cudaSuccess;
     switch (D) {
-        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<2>, BLOCK, 0); break;
+        case 2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<2>, BLOCK, 0); break;   // (the 1024-thread form holds the same number of threads)
         case 3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<3>, BLOCK, 0); break;
         case 4: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sweep_persistent<4>, BLOCK, 0); break;
         default: return 0;
@@ -749,6 +752,11 @@ cudaError_t launch_sweep_persistent(const StageParams &sp, double *J_base, int32
     const dim3 grid((unsigned)((threads + BLOCK - 1) / BLOCK));
     StageParams spc = sp;
     void *args[] = {(void *)&spc, (void *)&pp};
+    const bool small_block = std::getenv("BELLMAN_PERSIST_BLOCK256") != nullptr;
+    if (sp.D == 2 && !small_block) {
+        const dim3 grid1k((unsigned)((threads + 1023) / 1024));
+        return cudaLaunchCooperativeKernel((const void *)k_sweep_persistent<2, 1024>, grid1k, dim3(1024), args, 0, st);
+    }
     switch (sp.D) {
         case 2: return cudaLaunchCooperativeKernel((const void *)k_sweep_persistent<2>, grid, dim3(BLOCK), args, 0, st);
         case 3: return cudaLaunchCooperativeKernel((const void *)k_sweep_persistent<3>, grid, dim3(BLOCK), args, 0, st);

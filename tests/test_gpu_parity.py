@@ -123,14 +123,17 @@ def test_window_kernel_random_terminal_cost(bellman, oracle_lib, monkeypatch, sh
     sw.close()
 
 
-@pytest.mark.parametrize("graph", [False, True])
-def test_position_reference_size(bellman, oracle_lib, graph):
-    """config 2: 3 axes x 201x201 x 3 controls (Solver_position.m:49-72,84)."""
+@pytest.mark.parametrize("graph", [False, True, "block256"])
+def test_position_reference_size(bellman, oracle_lib, monkeypatch, graph):
+    """config 2: 3 axes x 201x201 x 3 controls (Solver_position.m:49-72,84); the persistent kernel with
+    1024-thread CTAs (default for D = 2) and with 256-thread CTAs."""
+    if graph == "block256":
+        monkeypatch.setenv("BELLMAN_PERSIST_BLOCK256", "1")
     sp = bellman.Solver_position()
     d = bellman.tables.stack_problems(sp._axis_descs())
     n = 61
     ora = oracle_lib.sweep(d, n_stages=n)
-    sw = bellman.Sweep(d).run(n, use_graph=graph)
+    sw = bellman.Sweep(d).run(n, use_graph=bool(graph))
     if graph:
         assert sw.last_kernel == "persistent"      # one cooperative launch, grid barrier per stage
     assert sw.current_stage == ora["stage"] == d.N - n
