@@ -677,3 +677,351 @@ int oracle_rollout_orbit(const bellman_desc *d, const int32_t *modes, const int3
         for (int k = 0; k < 2; ++k) free(g[p][k].rinv);
     return 0;
 }
+
+/* ==== 13-state / 7-state plants integrated with ode45 (second half) ===========
+ * Solver_pos_att.get_optimal_path (pos-att/Solver_pos_att.m:452-500, ode_eq :692-757,
+ * get_thruster_on_off_optimal :404-449, to_Moments_Forces :805-823, ECI2body :825-829,
+ * RSW2ECI :831-847) and Solver_attitude.get_optimal_path_simplified_testode45
+ * (attitude-control/Solver_attitude.m:1669-1705, ode_eq :1795-1851).
+ *
+ * ode45 itself is MathWorks' Dormand-Prince 5(4) driver.  It is not part of the reference repository;
+ * what is restated here is its published algorithm (Dormand & Prince 1980 tableau; step control as
+ * described by Shampine & Reichelt, "The MATLAB ODE Suite", SIAM J. Sci. Comput. 18, 1997, and as the
+ * readable ode45.m / odearguments.m shipped with MATLAB implement it) with the DEFAULT options the
+ * reference's two call sites use: RelTol 1e-3, AbsTol 1e-6, MaxStep 0.1*|tf-t0|, no InitialStep,
+ * component-wise error control, tspan = [t0 tf] (only the last row of the output is used).
+ * Parity unpinned: the reference stores no output of this path and MATLAB cannot run here. */
+typedef void (*ode_rhs)(const void *ctx, double t, const double *y, double *dydt);
+#define ODE_MAXN 13
+static const double dp_A[6] = {1. / 5, 3. / 10, 4. / 5, 8. / 9, 1, 1};
+static const double dp_B[7][6] = {                       /* dp_B[j][k]: slope j in the argument of stage k + 2 */
+    {1. / 5, 3. / 40, 44. / 45, 19372. / 6561, 9017. / 3168, 35. / 384},
+    {0, 9. / 40, -56. / 15, -25360. / 2187, -355. / 33, 0},
+    {0, 0, 32. / 9, 64448. / 6561, 46732. / 5247, 500. / 1113},
+    {0, 0, 0, -212. / 729, 49. / 176, 125. / 192},
+    {0, 0, 0, 0, -5103. / 18656, -2187. / 6784},
+    {0, 0, 0, 0, 0, 11. / 84},
+    {0, 0, 0, 0, 0, 0}};
+static const double dp_E[7] = {71. / 57600, 0, -71. / 16695, 71. / 1920, -17253. / 339200, 22. / 525, -1. / 40};
+
+/* [~, Y] = ode45(fn, [t0 tf], y); y = Y(end,:).  Returns the number of accepted steps; *nfailed counts
+ * rejected attempts; *warned = 1 when the step size reached hmin (MATLAB warns and returns early) or
+ * max_steps was hit (a bound the GPU kernel needs; never reached by the reference's plants). */
+int oracle_ode45_last(ode_rhs fn, const void *ctx, int neq, double t0, double tf, double *y, double rtol,
+                      double atol, int max_steps, int *nfailed, int *warned)
+{
+    const double pw = 1. / 5;
+    double f[7][ODE_MAXN], ys[ODE_MAXN];
+    const double htspan = fabs(tf - t0), hmax = fabs(0.1 * (tf - t0)), threshold = atol / rtol;
+    double t = t0;
+    int steps = 0, done = 0;
+    *nfailed = 0;
+    *warned = 0;
+    if (neq > ODE_MAXN) return -1;
+    fn(ctx, t, y, f[0]);
+    double hmin = 16 * eps_of(t);
+    double absh = fmin(hmax, htspan);                     /* initial step from y'(t0) */
+    double rh = 0;
+    for (int i = 0; i < neq; ++i) rh = fmax(rh, fabs(f[0][i] / fmax(fabs(y[i]), threshold)));
+    rh = rh / (0.8 * pow(rtol, pw));
+    if (absh * rh > 1) absh = 1 / rh;
+    absh = fmax(absh, hmin);
+    while (!done) {
+        if (steps >= max_steps) { *warned = 1; break; }
+        hmin = 16 * eps_of(t);
+        absh = fmin(hmax, fmax(hmin, absh));
+        double h = absh;                                  /* tdir = +1 */
+        if (1.1 * absh >= fabs(tf - t)) {                 /* stretch the step if within 10% of tf - t */
+            h = tf - t;
+            absh = fabs(h);
+            done = 1;
+        }
+        int nofailed = 1;
+        double err, tnew;
+        for (;;) {
+            for (int k = 0; k < 6; ++k) {                 /* y + f*hB(:,k), hB = h*B */
+                for (int i = 0; i < neq; ++i) {
+                    double s = 0;
+                    for (int j = 0; j <= k; ++j) s = s + f[j][i] * (h * dp_B[j][k]);
+                    ys[i] = y[i] + s;
+                }
+                if (k < 5) fn(ctx, t + h * dp_A[k], ys, f[k + 1]);
+            }
+            tnew = t + h * dp_A[5];
+            if (done) tnew = tf;                          /* hit the end point exactly */
+            fn(ctx, tnew, ys, f[6]);                      /* ys = ynew */
+            err = 0;
+            for (int i = 0; i < neq; ++i) {
+                double fe = 0;
+                for (int j = 0; j < 7; ++j) fe = fe + f[j][i] * dp_E[j];
+                err = fmax(err, fabs(fe / fmax(fmax(fabs(y[i]), fabs(ys[i])), threshold)));
+            }
+            err = absh * err;
+            if (err > rtol) {                             /* failed step */
+                ++*nfailed;
+                if (absh <= hmin) { *warned = 1; return steps; }
+                if (nofailed) {
+                    nofailed = 0;
+                    absh = fmax(hmin, absh * fmax(0.1, 0.8 * pow(rtol / err, pw)));
+                } else {
+                    absh = fmax(hmin, 0.5 * absh);
+                }
+                h = absh;
+                done = 0;
+            } else {
+                break;
+            }
+        }
+        ++steps;
+        if (!done && nofailed) {                          /* no failures: new step size */
+            const double temp = 1.25 * pow(err / rtol, pw);
+            if (temp > 0.2) absh = absh / temp;
+            else absh = 5.0 * absh;
+        }
+        t = tnew;
+        memcpy(y, ys, sizeof(double) * neq);
+        memcpy(f[0], f[6], sizeof(double) * neq);         /* first-same-as-last */
+    }
+    return steps;
+}
+
+/* test hook: ode45 on y' = lambda*y (neq components with lambda[i]) */
+static void linear_rhs(const void *ctx, double t, const double *y, double *dydt)
+{
+    const double *lam = (const double *)ctx;
+    (void)t;
+    for (int i = 0; i < (int)lam[0]; ++i) dydt[i] = lam[1 + i] * y[i];
+}
+int oracle_ode45_linear(int neq, const double *lambda, double t0, double tf, double *y, double rtol, double atol,
+                        int *nfailed, int *warned)
+{
+    double ctx[1 + ODE_MAXN];
+    ctx[0] = neq;
+    for (int i = 0; i < neq; ++i) ctx[1 + i] = lambda[i];
+    return oracle_ode45_last(linear_rhs, ctx, neq, t0, tf, y, rtol, atol, 1000000, nfailed, warned);
+}
+
+/* A\b for the symmetric inertia matrix with positive diagonal: mldivide takes the Cholesky path
+ * (A = R'R, R upper).  A is column-major 3x3. */
+typedef struct { double r11, r12, r13, r22, r23, r33; } chol3;
+static void chol3_factor(const double *A, chol3 *c)
+{
+    c->r11 = sqrt(A[0]);
+    c->r12 = A[3] / c->r11;
+    c->r13 = A[6] / c->r11;
+    c->r22 = sqrt(A[4] - c->r12 * c->r12);
+    c->r23 = (A[7] - c->r12 * c->r13) / c->r22;
+    c->r33 = sqrt(A[8] - (c->r13 * c->r13 + c->r23 * c->r23));
+}
+static void chol3_solve(const chol3 *c, const double *b, double *x)
+{
+    const double z1 = b[0] / c->r11;
+    const double z2 = (b[1] - c->r12 * z1) / c->r22;
+    const double z3 = ((b[2] - c->r13 * z1) - c->r23 * z2) / c->r33;
+    x[2] = z3 / c->r33;
+    x[1] = (z2 - c->r23 * x[2]) / c->r22;
+    x[0] = ((z1 - c->r12 * x[1]) - c->r13 * x[2]) / c->r11;
+}
+/* A\b for a general 3x3 (row-major M[i][j]): LU with partial pivoting */
+static void lu3_solve(const double M[3][3], const double *b, double *x)
+{
+    double a[3][4];
+    for (int i = 0; i < 3; ++i) { for (int j = 0; j < 3; ++j) a[i][j] = M[i][j]; a[i][3] = b[i]; }
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+        for (int i = k + 1; i < 3; ++i) if (fabs(a[i][k]) > fabs(a[p][k])) p = i;
+        if (p != k) for (int j = 0; j < 4; ++j) { const double tmp = a[k][j]; a[k][j] = a[p][j]; a[p][j] = tmp; }
+        for (int i = k + 1; i < 3; ++i) {
+            const double l = a[i][k] / a[k][k];
+            for (int j = k + 1; j < 4; ++j) a[i][j] = a[i][j] - l * a[k][j];
+        }
+    }
+    x[2] = a[2][3] / a[2][2];
+    x[1] = (a[1][3] - a[1][2] * x[2]) / a[1][1];
+    x[0] = ((a[0][3] - a[0][1] * x[1]) - a[0][2] * x[2]) / a[0][0];
+}
+static void matvec3(const double M[3][3], const double *v, double *o)
+{
+    for (int i = 0; i < 3; ++i) o[i] = (M[i][0] * v[0] + M[i][1] * v[1]) + M[i][2] * v[2];
+}
+/* Solver_pos_att.m:825-829 */
+static void eci2body(const double *q, double M[3][3])
+{
+    M[0][0] = 1 - 2 * (q[1] * q[1] + q[2] * q[2]); M[0][1] = 2 * (q[0] * q[1] + q[2] * q[3]); M[0][2] = 2 * (q[0] * q[2] - q[1] * q[3]);
+    M[1][0] = 2 * (q[1] * q[0] - q[2] * q[3]); M[1][1] = 1 - 2 * (q[0] * q[0] + q[2] * q[2]); M[1][2] = 2 * (q[1] * q[2] + q[0] * q[3]);
+    M[2][0] = 2 * (q[2] * q[0] + q[1] * q[3]); M[2][1] = 2 * (q[2] * q[1] - q[0] * q[3]); M[2][2] = 1 - 2 * (q[0] * q[0] + q[1] * q[1]);
+}
+/* Solver_pos_att.m:831-847: columns R, S, W */
+static void rsw2eci(const double *pos, const double *vel, double M[3][3])
+{
+    const double np_ = sqrt((pos[0] * pos[0] + pos[1] * pos[1]) + pos[2] * pos[2]);
+    const double c[3] = {pos[1] * vel[2] - pos[2] * vel[1], pos[2] * vel[0] - pos[0] * vel[2], pos[0] * vel[1] - pos[1] * vel[0]};
+    const double nc = sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+    const double R[3] = {pos[0] / np_, pos[1] / np_, pos[2] / np_};
+    const double W[3] = {c[0] / nc, c[1] / nc, c[2] / nc};
+    const double S[3] = {W[1] * R[2] - W[2] * R[1], W[2] * R[0] - W[0] * R[2], W[0] * R[1] - W[1] * R[0]};
+    for (int i = 0; i < 3; ++i) { M[i][0] = R[i]; M[i][1] = S[i]; M[i][2] = W[i]; }
+}
+/* obj.InertiaM\(U - cross(w, obj.InertiaM*w)); Im column-major */
+static void euler_wdot(const double *Im, const chol3 *ch, const double *U, const double *w, double *wd)
+{
+    double Iw[3], b[3];
+    for (int i = 0; i < 3; ++i) Iw[i] = (Im[i] * w[0] + Im[3 + i] * w[1]) + Im[6 + i] * w[2];
+    b[0] = U[0] - (w[1] * Iw[2] - w[2] * Iw[1]);
+    b[1] = U[1] - (w[2] * Iw[0] - w[0] * Iw[2]);
+    b[2] = U[2] - (w[0] * Iw[1] - w[1] * Iw[0]);
+    chol3_solve(ch, b, wd);
+}
+
+typedef struct { orbit_ctx o; double UM[3]; const double *Im; chol3 ch; } posatt_ctx;
+
+/* Solver_pos_att.m:696-754 (system_dynamics) */
+static void posatt_rates(const void *vc, double t, const double *X, double *Xd)
+{
+    const posatt_ctx *c = (const posatt_ctx *)vc;
+    orbit_rates(&c->o, t, X, Xd);                         /* X_dot(1:6): same expressions as Solver_position's rates */
+    const double q1 = X[6], q2 = X[7], q3 = X[8], q4 = X[9], w1 = X[10], w2 = X[11], w3 = X[12];
+    Xd[6] = 0.5 * ((w3 * q2 - w2 * q3) + w1 * q4);
+    Xd[7] = 0.5 * ((-w3 * q1 + w1 * q3) + w2 * q4);
+    Xd[8] = 0.5 * ((w2 * q1 - w1 * q2) + w3 * q4);
+    Xd[9] = 0.5 * ((-w1 * q1 - w2 * q2) - w3 * q3);
+    euler_wdot(c->Im, &c->ch, c->UM, X + 10, Xd + 10);
+}
+
+/* par = {mu, h, rtol, atol, Mass, T_dist, R0[3], V0[3], InertiaM[9] column-major} (21 doubles).
+ * d[ch], modes[ch] ([4]), idx[ch] ([S_ch], 0-based combination index), fv[ch] ([4][C_ch]: the channel's
+ * f0/f1/f6/f7_allcomb vectors) for ch = x, y, z.  y0 [13][batch]; X_out [13][n_steps+1][batch];
+ * F_out [12][n_steps][batch] (f0..f11, F_Th_Opt of :481); FM_out [6][n_steps][batch]
+ * (a_x a_y a_z U_M', Force_Moment_log of :482); warn_out [batch]. */
+int oracle_rollout_pos_att(const bellman_desc *dx, const bellman_desc *dy, const bellman_desc *dz,
+                           const int32_t *mx, const int32_t *my, const int32_t *mz,
+                           const int32_t *ix, const int32_t *iy, const int32_t *iz,
+                           const double *fx, const double *fy, const double *fz, const double *par,
+                           int n_steps, const double *y0, int batch, double *X_out, double *F_out,
+                           double *FM_out, int32_t *warn_out)
+{
+    const bellman_desc *dd[3] = {dx, dy, dz};
+    const int32_t *mm[3] = {mx, my, mz}, *ii[3] = {ix, iy, iz};
+    const double *ff[3] = {fx, fy, fz};
+    dimtab g[3][4];
+    for (int p = 0; p < 3; ++p) {
+        if (dd[p]->D != 4) return -1;
+        for (int k = 0; k < 4; ++k) dimtab_init(&g[p][k], dd[p]->grid[k], dd[p]->n[k], mm[p][k]);
+    }
+    const double mu = par[0], h = par[1], rtol = par[2], atol = par[3], Mass = par[4], T_dist = par[5];
+    const double *R0 = par + 6, *V0 = par + 9, *Im = par + 12;
+    double M1[3][3];
+    rsw2eci(R0, V0, M1);
+    static const int ang_of[3] = {1, 2, 0};               /* channel x: t_y, w_y; y: t_z, w_z; z: t_x, w_x (:432-447) */
+    static const int thr_of[3][4] = {{0, 1, 6, 7}, {2, 3, 8, 9}, {4, 5, 10, 11}};
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < batch; ++b) {
+        double y[13];
+        for (int k = 0; k < 13; ++k) y[k] = y0[(size_t)b * 13 + k];
+        double *X = X_out + (size_t)b * 13 * (n_steps + 1);
+        memcpy(X, y, sizeof(y));
+        posatt_ctx c;
+        c.o.mu = mu; c.o.R0 = R0; c.o.V0 = V0;
+        c.Im = Im;
+        chol3_factor(Im, &c.ch);
+        int warns = 0;
+        for (int ks = 1; ks <= n_steps; ++ks) {
+            double tq[3], M2[3][3], tmp[3], xb[3], vb[3], f[12];
+            for (int k = 0; k < 3; ++k) tq[k] = 2 * asin(y[6 + k]);      /* :472-474 */
+            eci2body(y + 6, M2);
+            matvec3(M1, y, tmp); matvec3(M2, tmp, xb);                   /* :414-415 */
+            matvec3(M1, y + 3, tmp); matvec3(M2, tmp, vb);
+            for (int p = 0; p < 3; ++p) {
+                const bellman_desc *d = dd[p];
+                const double xq[4] = {xb[p], vb[p], tq[ang_of[p]], y[10 + ang_of[p]]};
+                int64_t o = 0, st = 1;
+                for (int k = 0; k < 4; ++k) { o += nearest_node(&g[p][k], xq[k]) * st; st *= d->n[k]; }
+                const int ci = ii[p][o];
+                for (int m = 0; m < 4; ++m) f[thr_of[p][m]] = ff[p][(size_t)m * d->C + ci];
+            }
+            /* to_Moments_Forces :805-823 */
+            const double UMy = (((f[0] - f[1]) + f[6]) - f[7]) * T_dist;
+            const double UMz = (((f[2] - f[3]) + f[8]) - f[9]) * T_dist;
+            const double UMx = (((f[4] - f[5]) + f[10]) - f[11]) * T_dist;
+            const double ab[3] = {(((f[0] + f[1]) + f[6]) + f[7]) / Mass, (((f[2] + f[3]) + f[8]) + f[9]) / Mass,
+                                  (((f[4] + f[5]) + f[10]) + f[11]) / Mass};
+            double acc[3];
+            lu3_solve(M2, ab, tmp);
+            lu3_solve(M1, tmp, acc);
+            c.UM[0] = UMx; c.UM[1] = UMy; c.UM[2] = UMz;
+            for (int k = 0; k < 3; ++k) c.o.a[k] = acc[k];
+            if (F_out) memcpy(F_out + ((size_t)b * n_steps + (ks - 1)) * 12, f, sizeof(f));
+            if (FM_out) {
+                double *fm = FM_out + ((size_t)b * n_steps + (ks - 1)) * 6;
+                fm[0] = acc[0]; fm[1] = acc[1]; fm[2] = acc[2]; fm[3] = UMx; fm[4] = UMy; fm[5] = UMz;
+            }
+            int nf, w;
+            oracle_ode45_last(posatt_rates, &c, 13, (double)(ks - 1) * h, (double)ks * h, y, rtol, atol, 100000, &nf, &w);
+            warns += w;
+            memcpy(X + (size_t)ks * 13, y, sizeof(y));
+        }
+        if (warn_out) warn_out[b] = warns;
+    }
+    for (int p = 0; p < 3; ++p)
+        for (int k = 0; k < 4; ++k) free(g[p][k].rinv);
+    return 0;
+}
+
+typedef struct { double U[3]; const double *Im; chol3 ch; } att_ctx;
+
+/* Solver_attitude.m:1803-1849 (system_dynamics): X = (w1 w2 w3 q1 q2 q3 q4) */
+static void att_rates(const void *vc, double t, const double *X, double *Xd)
+{
+    const att_ctx *c = (const att_ctx *)vc;
+    (void)t;
+    const double x1 = X[0], x2 = X[1], x3 = X[2], x4 = X[3], x5 = X[4], x6 = X[5], x7 = X[6];
+    euler_wdot(c->Im, &c->ch, c->U, X, Xd);
+    Xd[3] = 0.5 * ((x3 * x5 - x2 * x6) + x1 * x7);
+    Xd[4] = 0.5 * ((-x3 * x4 + x1 * x6) + x2 * x7);
+    Xd[5] = 0.5 * ((x2 * x4 - x1 * x5) + x3 * x7);
+    Xd[6] = 0.5 * ((-x1 * x4 - x2 * x5) - x3 * x6);
+}
+
+/* Solver_attitude.m:1669-1705: U1(k) = FU_k(X(k), 2*asin(X(3+k))), then ode45 over one stage.
+ * d: D = 2 (w, theta), problems 0..2 = the three axes; idx [3][S]; u_values [C];
+ * par = {h, rtol, atol, InertiaM[9] column-major}.  y0 [7][batch]; X_out [7][n_steps+1][batch];
+ * C_out [3][n_steps][batch]. */
+int oracle_rollout_attitude(const bellman_desc *d, const int32_t *modes, const int32_t *idx, const double *u_values,
+                            const double *par, int n_steps, const double *y0, int batch, double *X_out,
+                            int32_t *C_out, int32_t *warn_out)
+{
+    if (d->D != 2 || d->P < 3) return -1;
+    dimtab g[3][2];
+    for (int p = 0; p < 3; ++p)
+        for (int k = 0; k < 2; ++k) dimtab_init(&g[p][k], d->grid[k] + (size_t)p * d->n[k], d->n[k], modes[p * 2 + k]);
+    const int64_t S = (int64_t)d->n[0] * d->n[1];
+    const double h = par[0], rtol = par[1], atol = par[2], *Im = par + 3;
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < batch; ++b) {
+        double y[7];
+        for (int k = 0; k < 7; ++k) y[k] = y0[(size_t)b * 7 + k];
+        double *X = X_out + (size_t)b * 7 * (n_steps + 1);
+        int32_t *Cc = C_out + (size_t)b * 3 * n_steps;
+        memcpy(X, y, sizeof(y));
+        att_ctx c;
+        c.Im = Im;
+        chol3_factor(Im, &c.ch);
+        int warns = 0;
+        for (int ks = 1; ks <= n_steps; ++ks) {
+            for (int p = 0; p < 3; ++p) {
+                const double th = 2 * asin(y[3 + p]);
+                const int ci = idx[(size_t)p * S + nearest_node(&g[p][0], y[p]) + (int64_t)nearest_node(&g[p][1], th) * d->n[0]];
+                Cc[(size_t)(ks - 1) * 3 + p] = ci;
+                c.U[p] = u_values[ci];
+            }
+            int nf, w;
+            oracle_ode45_last(att_rates, &c, 7, (double)(ks - 1) * h, (double)ks * h, y, rtol, atol, 100000, &nf, &w);
+            warns += w;
+            memcpy(X + (size_t)ks * 7, y, sizeof(y));
+        }
+        if (warn_out) warn_out[b] = warns;
+    }
+    for (int p = 0; p < 3; ++p)
+        for (int k = 0; k < 2; ++k) free(g[p][k].rinv);
+    return 0;
+}

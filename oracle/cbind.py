@@ -259,3 +259,68 @@ def rollout_orbit(d, idx, u_values, y0, n_steps, h, R0, V0, mu=398600.0, tol=1e-
                                     X.ctypes.data_as(_dp), Cc.ctypes.data_as(ip), W.ctypes.data_as(ip))
     assert rc == 0
     return X, Cc, W
+
+
+def ode45_linear(lam, t0, tf, y0, rtol=1e-3, atol=1e-6):
+    """ode45 restatement on y' = lam .* y (test hook).  Returns (y(tf), accepted steps, failed attempts, warned)."""
+    lam, y = _arr(lam), _arr(y0).copy()
+    nf, w = C.c_int(), C.c_int()
+    fn = lib().oracle_ode45_linear
+    fn.restype = C.c_int
+    n = fn(C.c_int(len(lam)), lam.ctypes.data_as(_dp), C.c_double(t0), C.c_double(tf), y.ctypes.data_as(_dp),
+           C.c_double(rtol), C.c_double(atol), C.byref(nf), C.byref(w))
+    return y, n, nf.value, w.value
+
+
+def rollout_pos_att(descs, idxs, fvals, y0, n_steps, h, R0, V0, InertiaM, Mass, T_dist, mu=398600.0,
+                    rtol=1e-3, atol=1e-6):
+    """Solver_pos_att.get_optimal_path's stage loop (Solver_pos_att.m:452-500) for a batch.
+    descs / idxs / fvals: the x, y, z channel descriptors, [S_ch] 0-based policies and [4, C_ch] thruster
+    levels (f0/f1/f6/f7_allcomb).  y0 [batch, 13].  Returns X [batch, n_steps+1, 13], F [batch, n_steps, 12],
+    FM [batch, n_steps, 6], warnings [batch]."""
+    ip = C.POINTER(C.c_int32)
+    cds, keeps, modes, ias, fvs = [], [], [], [], []
+    for d, ix, fv in zip(descs, idxs, fvals):
+        cd, keep = to_cdesc(d)
+        cds.append(cd); keeps.append(keep)
+        modes.append(locate_modes(d))
+        ias.append(np.ascontiguousarray(ix, dtype=np.int32).ravel())
+        fvs.append(_arr(fv).reshape(4, int(d.C)))
+    y0 = _arr(y0).reshape(-1, 13)
+    batch = len(y0)
+    par = _arr(np.concatenate([[mu, h, rtol, atol, Mass, T_dist], np.ravel(R0), np.ravel(V0),
+                               np.asarray(InertiaM, dtype=np.float64).ravel(order="F")]))
+    X = np.zeros((batch, n_steps + 1, 13))
+    F = np.zeros((batch, n_steps, 12))
+    FM = np.zeros((batch, n_steps, 6))
+    W = np.zeros(batch, dtype=np.int32)
+    rc = lib().oracle_rollout_pos_att(C.byref(cds[0]), C.byref(cds[1]), C.byref(cds[2]),
+                                      modes[0].ctypes.data_as(ip), modes[1].ctypes.data_as(ip), modes[2].ctypes.data_as(ip),
+                                      ias[0].ctypes.data_as(ip), ias[1].ctypes.data_as(ip), ias[2].ctypes.data_as(ip),
+                                      fvs[0].ctypes.data_as(_dp), fvs[1].ctypes.data_as(_dp), fvs[2].ctypes.data_as(_dp),
+                                      par.ctypes.data_as(_dp), C.c_int(n_steps), y0.ctypes.data_as(_dp), C.c_int(batch),
+                                      X.ctypes.data_as(_dp), F.ctypes.data_as(_dp), FM.ctypes.data_as(_dp), W.ctypes.data_as(ip))
+    assert rc == 0
+    return X, F, FM, W
+
+
+def rollout_attitude(d, idx, u_values, y0, n_steps, h, InertiaM, rtol=1e-3, atol=1e-6, modes=None):
+    """Solver_attitude.get_optimal_path_simplified_testode45 (Solver_attitude.m:1669-1705) for a batch.
+    idx [3, S]; y0 [batch, 7] = (w1 w2 w3 q1 q2 q3 q4).  Returns X [batch, n_steps+1, 7], control indices
+    [batch, n_steps, 3], warnings [batch]."""
+    cd, keep = to_cdesc(d)
+    modes = locate_modes(d) if modes is None else np.ascontiguousarray(modes, dtype=np.int32)
+    ip = C.POINTER(C.c_int32)
+    y0 = _arr(y0).reshape(-1, 7)
+    batch = len(y0)
+    ia = np.ascontiguousarray(idx, dtype=np.int32)
+    uv = _arr(u_values)
+    par = _arr(np.concatenate([[h, rtol, atol], np.asarray(InertiaM, dtype=np.float64).ravel(order="F")]))
+    X = np.zeros((batch, n_steps + 1, 7))
+    Cc = np.zeros((batch, n_steps, 3), dtype=np.int32)
+    W = np.zeros(batch, dtype=np.int32)
+    rc = lib().oracle_rollout_attitude(C.byref(cd), modes.ctypes.data_as(ip), ia.ctypes.data_as(ip), uv.ctypes.data_as(_dp),
+                                       par.ctypes.data_as(_dp), C.c_int(n_steps), y0.ctypes.data_as(_dp), C.c_int(batch),
+                                       X.ctypes.data_as(_dp), Cc.ctypes.data_as(ip), W.ctypes.data_as(ip))
+    assert rc == 0
+    return X, Cc, W
