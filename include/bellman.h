@@ -304,6 +304,54 @@ int  bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bellman_orbit
                            const double *u_values /*[C]*/, const double *y0, int32_t batch,
                            double *X_out, int32_t *C_out, int32_t *warn_out);
 
+/* Full-plant forward simulations that the reference integrates with ode45 (one GPU thread per initial
+ * state).  ode45 is restated from its published algorithm — Dormand-Prince 5(4), MATLAB's step control
+ * with the default options the reference's call sites use (RelTol 1e-3, AbsTol 1e-6, MaxStep
+ * (tf - t0)/10, initial step from y'(t0), tspan = [t0 tf], last output row taken) — parity unpinned
+ * (MATLAB cannot run here; the reference stores no output of these paths).  Results agree with the CPU
+ * restatement (oracle_rollout_pos_att / oracle_rollout_attitude) to a tolerance: pow / asin / cos / sin
+ * are CUDA's. */
+typedef struct bellman_plant_opts {
+    int32_t struct_size;     /* = sizeof(bellman_plant_opts)                                    */
+    int32_t n_steps;         /* stages to simulate (reference: N_stage - 1)                     */
+    int32_t stride_out;      /* store every stride_out-th stage; n_steps %% stride_out == 0     */
+    int32_t max_ode_steps;   /* bound on ode45 steps per stage, 0 = 100000                      */
+    double  mu;              /* gravitational parameter (398600); pos-att only                  */
+    double  R0[3], V0[3];    /* target state vector at t = 0 (get_target_R0V0); pos-att only    */
+    double  h;               /* stage length obj.h                                              */
+    double  rtol, atol;      /* ode45 RelTol / AbsTol (defaults 1e-3 / 1e-6)                    */
+    double  inertia[9];      /* obj.InertiaM, column-major (symmetric, positive diagonal)       */
+    double  mass, t_dist;    /* obj.Mass, obj.T_dist; pos-att only                              */
+} bellman_plant_opts;
+
+/* Solver_pos_att.get_optimal_path (pos-att/Solver_pos_att.m:452-500): every stage the twelve thruster
+ * levels come from the three 4-D channel policies evaluated at the nearest grid node
+ * (get_thruster_on_off_optimal :404-449, x and v first taken from the RSW frame to the body frame,
+ * :411-415, ECI2body :825-829, RSW2ECI :831-847), moments and RSW accelerations follow
+ * to_Moments_Forces (:805-823), and the 13-state plant of :696-754 — relative motion about the target
+ * orbit (universal Kepler propagation), quaternion kinematics, Euler's equations with the full inertia
+ * matrix — is integrated over [tspan(k), tspan(k+1)] by ode45 (:484).
+ * hx, hy, hz: handles of the x, y, z channel problems (D = 4, problem 0 of each, same device, one
+ * rank), the policy of stage[ch] available on each.  f_x / f_y / f_z: [4][C_ch] levels of the
+ * channel's four thrusters per control combination (f0/f1/f6/f7_allcomb, set_controller :849-882).
+ * y0 [13][batch] = (dr dv q(scalar last) w); X_out [13][n_steps/stride_out + 1][batch];
+ * F_out [12][n_out][batch] (f0..f11, F_Th_Opt :481); FM_out [6][n_out][batch] (a_x a_y a_z U_M',
+ * Force_Moment_log :482; may be NULL); warn_out [batch] (may be NULL) counts ode45 calls that stopped
+ * on the minimum step size. */
+int  bellman_rollout_pos_att(bellman_handle *hx, bellman_handle *hy, bellman_handle *hz,
+                             const int32_t stage[3], const bellman_plant_opts *o, const double *f_x,
+                             const double *f_y, const double *f_z, const double *y0, int32_t batch,
+                             double *X_out, double *F_out, double *FM_out, int32_t *warn_out);
+
+/* Solver_attitude.get_optimal_path_simplified_testode45 (attitude-control/Solver_attitude.m:1669-1705):
+ * U(k) = FU_k(X(k), 2*asin(X(3+k))) from the three axis policies (D = 2: (w, theta), problems 0..2 of
+ * h, nearest node), then ode45 over one stage on the 7-state plant of :1803-1849 (Euler's equations
+ * with the full inertia matrix + quaternion kinematics).  y0 [7][batch] = (w1 w2 w3 q1 q2 q3 q4);
+ * X_out [7][n_out + 1][batch]; C_out [3][n_out][batch] 0-based control indices; u_values [C]. */
+int  bellman_rollout_attitude(bellman_handle *h, int32_t stage, const bellman_plant_opts *o,
+                              const double *u_values, const double *y0, int32_t batch, double *X_out,
+                              int32_t *C_out, int32_t *warn_out);
+
 #ifdef __cplusplus
 }
 #endif

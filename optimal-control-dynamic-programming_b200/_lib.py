@@ -50,6 +50,13 @@ class COrbitOpts(C.Structure):
                 ("h", C.c_double), ("tol", C.c_double)]
 
 
+class CPlantOpts(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n_steps", C.c_int32), ("stride_out", C.c_int32),
+                ("max_ode_steps", C.c_int32), ("mu", C.c_double), ("R0", C.c_double * 3), ("V0", C.c_double * 3),
+                ("h", C.c_double), ("rtol", C.c_double), ("atol", C.c_double), ("inertia", C.c_double * 9),
+                ("mass", C.c_double), ("t_dist", C.c_double)]
+
+
 class CSlab(C.Structure):
     _fields_ = [("own_lo", C.c_int32), ("own_hi", C.c_int32), ("ext_lo", C.c_int32), ("ext_hi", C.c_int32)]
 
@@ -62,6 +69,7 @@ EXPORTS = [
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
     "bellman_rollout_orbit", "bellman_get_points", "bellman_group_init", "bellman_group_run",
+    "bellman_rollout_pos_att", "bellman_rollout_attitude",
 ]
 
 _lib = None
@@ -106,6 +114,9 @@ def load():
     lib.bellman_group_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
     lib.bellman_group_run.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.POINTER(CRunOpts)]
     lib.bellman_get_points.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, _dp, _ip]
+    lib.bellman_rollout_pos_att.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _ip, C.POINTER(CPlantOpts), _dp, _dp, _dp,
+                                            _dp, C.c_int32, _dp, _dp, _dp, _ip]
+    lib.bellman_rollout_attitude.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CPlantOpts), _dp, _dp, C.c_int32, _dp, _ip, _ip]
     lib.bellman_rollout_orbit.argtypes = [C.c_void_p, C.c_int32, C.POINTER(COrbitOpts), _dp, _dp, C.c_int32, _dp, _ip, _ip]
     _lib = lib
     return lib
@@ -399,6 +410,57 @@ class Sweep:
                                                    y0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp),
                                                    Cc.ctypes.data_as(_ip), W.ctypes.data_as(_ip)))
         return X, Cc, W
+
+    def rollout_attitude(self, u_values, y0, n_steps, h_step, InertiaM, rtol=1e-3, atol=1e-6, stride_out=1, stage=None):
+        """Solver_attitude.get_optimal_path_simplified_testode45 (Solver_attitude.m:1669-1705): y0 [batch, 7]
+        = (w1 w2 w3 q1 q2 q3 q4) -> X [batch, n_out + 1, 7], control indices [batch, n_out, 3], warnings [batch]."""
+        stage = self.current_stage if stage is None else stage
+        y0 = _f64(y0).reshape(-1, 7)
+        batch = len(y0)
+        n_out = int(n_steps) // int(stride_out)
+        X = np.empty((batch, n_out + 1, 7))
+        Cc = np.empty((batch, n_out, 3), dtype=np.int32)
+        W = np.empty(batch, dtype=np.int32)
+        o = _plant_opts(n_steps, stride_out, h_step, InertiaM, rtol=rtol, atol=atol)
+        uv = _f64(u_values)
+        self._check(self.lib.bellman_rollout_attitude(self.h, int(stage), C.byref(o), uv.ctypes.data_as(_dp),
+                                                      y0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp),
+                                                      Cc.ctypes.data_as(_ip), W.ctypes.data_as(_ip)))
+        return X, Cc, W
+
+
+def _plant_opts(n_steps, stride_out, h_step, InertiaM, mu=0.0, R0=(0, 0, 0), V0=(0, 0, 0), rtol=1e-3, atol=1e-6,
+                mass=0.0, t_dist=0.0):
+    im = np.asarray(InertiaM, dtype=np.float64).reshape(3, 3).ravel(order="F")
+    return CPlantOpts(C.sizeof(CPlantOpts), int(n_steps), int(stride_out), 0, float(mu), (C.c_double * 3)(*R0),
+                      (C.c_double * 3)(*V0), float(h_step), float(rtol), float(atol), (C.c_double * 9)(*im),
+                      float(mass), float(t_dist))
+
+
+def rollout_pos_att(sweeps, f_values, y0, n_steps, h_step, R0, V0, InertiaM, Mass, T_dist, mu=398600.0, rtol=1e-3,
+                    atol=1e-6, stride_out=1, stages=None):
+    """Solver_pos_att.get_optimal_path (Solver_pos_att.m:452-500) for a batch of initial states on the GPU
+    (bellman_rollout_pos_att).  sweeps: the x, y, z channel Sweeps holding their policies; f_values: per
+    channel [4, C] thruster levels (f0/f1/f6/f7_allcomb); y0 [batch, 13].
+    Returns X [batch, n_out + 1, 13], F_Th_Opt [batch, n_out, 12], Force_Moment_log [batch, n_out, 6],
+    ode45 minimum-step warnings [batch]."""
+    lib = sweeps[0].lib
+    stages = [sw.current_stage for sw in sweeps] if stages is None else list(stages)
+    y0 = _f64(y0).reshape(-1, 13)
+    batch = len(y0)
+    n_out = int(n_steps) // int(stride_out)
+    X = np.empty((batch, n_out + 1, 13))
+    F = np.empty((batch, n_out, 12))
+    FM = np.empty((batch, n_out, 6))
+    W = np.empty(batch, dtype=np.int32)
+    o = _plant_opts(n_steps, stride_out, h_step, InertiaM, mu, R0, V0, rtol, atol, Mass, T_dist)
+    fv = [_f64(f).reshape(4, -1) for f in f_values]
+    st = (C.c_int32 * 3)(*[int(s) for s in stages])
+    sweeps[0]._check(lib.bellman_rollout_pos_att(sweeps[0].h, sweeps[1].h, sweeps[2].h, st, C.byref(o),
+                                                 fv[0].ctypes.data_as(_dp), fv[1].ctypes.data_as(_dp), fv[2].ctypes.data_as(_dp),
+                                                 y0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp), F.ctypes.data_as(_dp),
+                                                 FM.ctypes.data_as(_dp), W.ctypes.data_as(_ip)))
+    return X, F, FM, W
 
 
 class SweepGroup:

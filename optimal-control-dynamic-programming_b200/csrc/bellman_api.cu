@@ -1289,6 +1289,130 @@ extern "C" int bellman_rollout_orbit(bellman_handle *h, int32_t stage, const bel
 }
 
 // ---------------------------------------------------------------------------------------------
+// full-plant forward simulations (ode45): Solver_pos_att.get_optimal_path, Solver_attitude's testode45
+// ---------------------------------------------------------------------------------------------
+static int plant_common(bellman_handle *h, const bellman_plant_opts *o, PlantParams &pl) {
+    if (o->struct_size != (int32_t)sizeof(bellman_plant_opts)) { h->err = "bellman_plant_opts.struct_size mismatch"; return BELLMAN_ERR_BAD_ARG; }
+    if (o->n_steps < 1 || o->stride_out < 1 || o->n_steps % o->stride_out) { h->err = "n_steps must be a positive multiple of stride_out"; return BELLMAN_ERR_BAD_ARG; }
+    if (!(o->h > 0) || !(o->rtol > 0) || !(o->atol > 0)) { h->err = "h, rtol, atol must be positive"; return BELLMAN_ERR_BAD_ARG; }
+    if (!(o->inertia[0] > 0 && o->inertia[4] > 0 && o->inertia[8] > 0) || o->inertia[1] != o->inertia[3] ||
+        o->inertia[2] != o->inertia[6] || o->inertia[5] != o->inertia[7]) { h->err = "inertia must be symmetric with a positive diagonal"; return BELLMAN_ERR_BAD_ARG; }
+    pl.mu = o->mu;
+    for (int k = 0; k < 3; ++k) { pl.R0[k] = o->R0[k]; pl.V0[k] = o->V0[k]; }
+    for (int k = 0; k < 9; ++k) pl.Im[k] = o->inertia[k];
+    pl.h = o->h; pl.rtol = o->rtol; pl.atol = o->atol; pl.mass = o->mass; pl.t_dist = o->t_dist;
+    pl.n_steps = o->n_steps; pl.stride_out = o->stride_out;
+    pl.max_ode = o->max_ode_steps > 0 ? o->max_ode_steps : 100000;
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_rollout_pos_att(bellman_handle *hx, bellman_handle *hy, bellman_handle *hz, const int32_t stage[3],
+                                       const bellman_plant_opts *o, const double *f_x, const double *f_y, const double *f_z,
+                                       const double *y0, int32_t batch, double *X_out, double *F_out, double *FM_out,
+                                       int32_t *warn_out) {
+    if (!hx || !hy || !hz) return BELLMAN_ERR_BAD_ARG;
+    bellman_handle *h = hx;
+    if (!stage || !o || !f_x || !f_y || !f_z || !y0 || !X_out || !F_out || batch < 1) { h->err = "null argument"; return BELLMAN_ERR_BAD_ARG; }
+    bellman_handle *hs[3] = {hx, hy, hz};
+    const double *fh[3] = {f_x, f_y, f_z};
+    PlantParams pl;
+    std::memset(&pl, 0, sizeof(pl));
+    int rc = plant_common(h, o, pl);
+    if (rc != BELLMAN_OK) return rc;
+    if (!(o->mass > 0) || !(o->mu > 0)) { h->err = "mass and mu must be positive"; return BELLMAN_ERR_BAD_ARG; }
+    for (int p = 0; p < 3; ++p) {
+        if (hs[p]->hp.D != 4) { h->err = "pos-att rollout needs three D = 4 channel handles"; return BELLMAN_ERR_BAD_ARG; }
+        if (hs[p]->nranks != 1) { h->err = "rollouts cross slab boundaries: gather the policy into an unsharded handle (bellman_set_stage) first"; return BELLMAN_ERR_BAD_ARG; }
+        if (hs[p]->device != h->device) { h->err = "the three channel handles must live on one device"; return BELLMAN_ERR_BAD_ARG; }
+        rc = fill_policy_params(hs[p], 0, pl.pol[p]);
+        if (rc != BELLMAN_OK) { h->err = hs[p]->err; return rc; }
+        rc = stage_available(hs[p], stage[p], hs[p]->store_idx_all, true);
+        if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+        pl.pol[p].idx = hs[p]->idx_ptr(stage[p], 0);
+        pl.C[p] = hs[p]->hp.C;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    CUDA_TRY(h, cudaStreamSynchronize(hy->stream));      // their policies were written on their own streams
+    CUDA_TRY(h, cudaStreamSynchronize(hz->stream));
+    const int n_out = o->n_steps / o->stride_out;
+    const size_t b_f[3] = {align256(sizeof(double) * 4 * (size_t)pl.C[0]), align256(sizeof(double) * 4 * (size_t)pl.C[1]),
+                           align256(sizeof(double) * 4 * (size_t)pl.C[2])};
+    const size_t b_y = align256(sizeof(double) * 13 * (size_t)batch), b_X = align256(sizeof(double) * 13 * (size_t)(n_out + 1) * batch),
+                 b_F = align256(sizeof(double) * 12 * (size_t)n_out * batch), b_M = align256(sizeof(double) * 6 * (size_t)n_out * batch),
+                 b_w = align256(sizeof(int32_t) * (size_t)batch);
+    unsigned char *buf = consumer_scratch(h, b_f[0] + b_f[1] + b_f[2] + b_y + b_X + b_F + b_M + b_w);
+    if (!buf) return BELLMAN_ERR_CUDA;
+    auto cleanup = [&]() {};
+#define LT(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { h->err = cudaGetErrorString(_e); cleanup(); return BELLMAN_ERR_CUDA; } } while (0)
+    unsigned char *cur = buf;
+    for (int p = 0; p < 3; ++p) {
+        LT(cudaMemcpyAsync(cur, fh[p], sizeof(double) * 4 * (size_t)pl.C[p], cudaMemcpyHostToDevice, h->stream));
+        pl.fv[p] = reinterpret_cast<const double *>(cur);
+        cur += b_f[p];
+    }
+    double *d_y = reinterpret_cast<double *>(cur); cur += b_y;
+    double *d_X = reinterpret_cast<double *>(cur); cur += b_X;
+    double *d_F = reinterpret_cast<double *>(cur); cur += b_F;
+    double *d_M = reinterpret_cast<double *>(cur); cur += b_M;
+    int32_t *d_w = reinterpret_cast<int32_t *>(cur);
+    LT(cudaMemcpyAsync(d_y, y0, sizeof(double) * 13 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
+    pl.kind = 0; pl.batch = batch;
+    pl.y0 = d_y; pl.X_out = d_X; pl.F_out = d_F; pl.FM_out = FM_out ? d_M : nullptr; pl.warn_out = d_w;
+    LT(launch_rollout_plant(pl, h->stream));
+    LT(cudaMemcpyAsync(X_out, d_X, sizeof(double) * 13 * (size_t)(n_out + 1) * batch, cudaMemcpyDeviceToHost, h->stream));
+    LT(cudaMemcpyAsync(F_out, d_F, sizeof(double) * 12 * (size_t)n_out * batch, cudaMemcpyDeviceToHost, h->stream));
+    if (FM_out) LT(cudaMemcpyAsync(FM_out, d_M, sizeof(double) * 6 * (size_t)n_out * batch, cudaMemcpyDeviceToHost, h->stream));
+    if (warn_out) LT(cudaMemcpyAsync(warn_out, d_w, sizeof(int32_t) * (size_t)batch, cudaMemcpyDeviceToHost, h->stream));
+    LT(cudaStreamSynchronize(h->stream));
+    cleanup();
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_rollout_attitude(bellman_handle *h, int32_t stage, const bellman_plant_opts *o, const double *u_values,
+                                        const double *y0, int32_t batch, double *X_out, int32_t *C_out, int32_t *warn_out) {
+    if (!h) return BELLMAN_ERR_BAD_ARG;
+    if (!o || !u_values || !y0 || !X_out || !C_out || batch < 1) { h->err = "null argument"; return BELLMAN_ERR_BAD_ARG; }
+    const HostProblem &hp = h->hp;
+    if (hp.D != 2 || hp.P < 3) { h->err = "attitude rollout needs D = 2 and P >= 3 (the three axis problems)"; return BELLMAN_ERR_BAD_ARG; }
+    if (h->nranks != 1) { h->err = "rollouts cross slab boundaries: gather the policy into an unsharded handle (bellman_set_stage) first"; return BELLMAN_ERR_BAD_ARG; }
+    PlantParams pl;
+    std::memset(&pl, 0, sizeof(pl));
+    int rc = plant_common(h, o, pl);
+    if (rc != BELLMAN_OK) return rc;
+    rc = stage_available(h, stage, h->store_idx_all, true);
+    if (rc != BELLMAN_OK) { h->err = "stage not available"; return rc; }
+    for (int p = 0; p < 3; ++p) {
+        rc = fill_policy_params(h, p, pl.pol[p]);
+        if (rc != BELLMAN_OK) return rc;
+        pl.pol[p].idx = h->idx_ptr(stage, p);
+        pl.C[p] = hp.C;
+    }
+    CUDA_TRY(h, cudaSetDevice(h->device));
+    const int n_out = o->n_steps / o->stride_out;
+    const size_t b_u = align256(sizeof(double) * (size_t)hp.C), b_y = align256(sizeof(double) * 7 * (size_t)batch),
+                 b_X = align256(sizeof(double) * 7 * (size_t)(n_out + 1) * batch), b_c = align256(sizeof(int32_t) * 3 * (size_t)n_out * batch),
+                 b_w = align256(sizeof(int32_t) * (size_t)batch);
+    unsigned char *buf = consumer_scratch(h, b_u + b_y + b_X + b_c + b_w);
+    if (!buf) return BELLMAN_ERR_CUDA;
+    auto cleanup = [&]() {};
+    double *d_u = reinterpret_cast<double *>(buf), *d_y = reinterpret_cast<double *>(buf + b_u),
+           *d_X = reinterpret_cast<double *>(buf + b_u + b_y);
+    int32_t *d_c = reinterpret_cast<int32_t *>(buf + b_u + b_y + b_X), *d_w = reinterpret_cast<int32_t *>(buf + b_u + b_y + b_X + b_c);
+    LT(cudaMemcpyAsync(d_u, u_values, sizeof(double) * (size_t)hp.C, cudaMemcpyHostToDevice, h->stream));
+    LT(cudaMemcpyAsync(d_y, y0, sizeof(double) * 7 * (size_t)batch, cudaMemcpyHostToDevice, h->stream));
+    pl.kind = 1; pl.batch = batch;
+    pl.fv[0] = d_u; pl.y0 = d_y; pl.X_out = d_X; pl.C_out = d_c; pl.warn_out = d_w;
+    LT(launch_rollout_plant(pl, h->stream));
+    LT(cudaMemcpyAsync(X_out, d_X, sizeof(double) * 7 * (size_t)(n_out + 1) * batch, cudaMemcpyDeviceToHost, h->stream));
+    LT(cudaMemcpyAsync(C_out, d_c, sizeof(int32_t) * 3 * (size_t)n_out * batch, cudaMemcpyDeviceToHost, h->stream));
+    if (warn_out) LT(cudaMemcpyAsync(warn_out, d_w, sizeof(int32_t) * (size_t)batch, cudaMemcpyDeviceToHost, h->stream));
+    LT(cudaStreamSynchronize(h->stream));
+#undef LT
+    cleanup();
+    return BELLMAN_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
 // point reads: J and argmin of listed states (spot checks at grid sizes whose arrays do not fit the host)
 // ---------------------------------------------------------------------------------------------
 struct PointArgs {

@@ -665,6 +665,336 @@ __global__ void __launch_bounds__(64) k_rollout_orbit(const __grid_constant__ Or
     if (op.warn_out) op.warn_out[b] = warns;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Full-plant forward simulations the reference integrates with ode45 (one thread per initial state):
+//   kind 0  Solver_pos_att.get_optimal_path, pos-att/Solver_pos_att.m:452-500 — per stage the twelve
+//           thruster levels from the three 4-D channel policies (:404-449, frame change :411-415,
+//           ECI2body :825-829, RSW2ECI :831-847), moments and RSW accelerations (:805-823), then
+//           ode45 over [tspan(k), tspan(k+1)] on the 13-state plant of :696-754;
+//   kind 1  Solver_attitude.get_optimal_path_simplified_testode45, attitude-control/
+//           Solver_attitude.m:1669-1705 — three 2-D axis policies at (w_k, 2*asin(q_k)), ode45 on the
+//           7-state plant of :1803-1849.
+// ode45 = Dormand-Prince 5(4) with MATLAB's published step control and default options (RelTol 1e-3,
+// AbsTol 1e-6, MaxStep (tf-t0)/10, initial step from y'(t0)); operation order as oracle_ode45_last in
+// oracle/bellman_oracle.c states it.  pow / asin / the Kepler transcendentals are CUDA's, so parity
+// with the oracle is a tolerance.
+// ---------------------------------------------------------------------------------------------
+struct Chol3 { double r11, r12, r13, r22, r23, r33; };
+__device__ __forceinline__ void chol3_factor(const double *A, Chol3 &c) {       // A column-major, symmetric
+    c.r11 = sqrt(A[0]);
+    c.r12 = A[3] / c.r11;
+    c.r13 = A[6] / c.r11;
+    c.r22 = sqrt(A[4] - c.r12 * c.r12);
+    c.r23 = (A[7] - c.r12 * c.r13) / c.r22;
+    c.r33 = sqrt(A[8] - (c.r13 * c.r13 + c.r23 * c.r23));
+}
+__device__ __forceinline__ void chol3_solve(const Chol3 &c, const double *b, double *x) {
+    const double z1 = b[0] / c.r11;
+    const double z2 = (b[1] - c.r12 * z1) / c.r22;
+    const double z3 = ((b[2] - c.r13 * z1) - c.r23 * z2) / c.r33;
+    x[2] = z3 / c.r33;
+    x[1] = (z2 - c.r23 * x[2]) / c.r22;
+    x[0] = ((z1 - c.r12 * x[1]) - c.r13 * x[2]) / c.r11;
+}
+__device__ void lu3_solve(const double (&M)[3][3], const double *b, double *x) {  // partial pivoting
+    double a[3][4];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) a[i][j] = M[i][j];
+        a[i][3] = b[i];
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        int p = k;
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) if (fabs(a[i][k]) > fabs(a[p][k])) p = i;
+#pragma unroll
+        for (int r = k + 1; r < 3; ++r)
+            if (p == r) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const double tmp = a[k][j]; a[k][j] = a[r][j]; a[r][j] = tmp; }
+            }
+#pragma unroll
+        for (int i = k + 1; i < 3; ++i) {
+            const double l = a[i][k] / a[k][k];
+#pragma unroll
+            for (int j = k + 1; j < 4; ++j) a[i][j] = a[i][j] - l * a[k][j];
+        }
+    }
+    x[2] = a[2][3] / a[2][2];
+    x[1] = (a[1][3] - a[1][2] * x[2]) / a[1][1];
+    x[0] = ((a[0][3] - a[0][1] * x[1]) - a[0][2] * x[2]) / a[0][0];
+}
+__device__ __forceinline__ void matvec3(const double (&M)[3][3], const double *v, double *o) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) o[i] = (M[i][0] * v[0] + M[i][1] * v[1]) + M[i][2] * v[2];
+}
+__device__ __forceinline__ void eci2body(const double *q, double (&M)[3][3]) {
+    M[0][0] = 1 - 2 * (q[1] * q[1] + q[2] * q[2]); M[0][1] = 2 * (q[0] * q[1] + q[2] * q[3]); M[0][2] = 2 * (q[0] * q[2] - q[1] * q[3]);
+    M[1][0] = 2 * (q[1] * q[0] - q[2] * q[3]); M[1][1] = 1 - 2 * (q[0] * q[0] + q[2] * q[2]); M[1][2] = 2 * (q[1] * q[2] + q[0] * q[3]);
+    M[2][0] = 2 * (q[2] * q[0] + q[1] * q[3]); M[2][1] = 2 * (q[2] * q[1] - q[0] * q[3]); M[2][2] = 1 - 2 * (q[0] * q[0] + q[1] * q[1]);
+}
+__device__ __forceinline__ void rsw2eci(const double *pos, const double *vel, double (&M)[3][3]) {
+    const double np_ = sqrt((pos[0] * pos[0] + pos[1] * pos[1]) + pos[2] * pos[2]);
+    const double c[3] = {pos[1] * vel[2] - pos[2] * vel[1], pos[2] * vel[0] - pos[0] * vel[2], pos[0] * vel[1] - pos[1] * vel[0]};
+    const double nc = sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+    const double R[3] = {pos[0] / np_, pos[1] / np_, pos[2] / np_};
+    const double W[3] = {c[0] / nc, c[1] / nc, c[2] / nc};
+    const double S[3] = {W[1] * R[2] - W[2] * R[1], W[2] * R[0] - W[0] * R[2], W[0] * R[1] - W[1] * R[0]};
+#pragma unroll
+    for (int i = 0; i < 3; ++i) { M[i][0] = R[i]; M[i][1] = S[i]; M[i][2] = W[i]; }
+}
+// obj.InertiaM\(U - cross(w, obj.InertiaM*w))
+__device__ __forceinline__ void euler_wdot(const double *Im, const Chol3 &ch, const double *U, const double *w, double *wd) {
+    double Iw[3], b[3];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) Iw[i] = (Im[i] * w[0] + Im[3 + i] * w[1]) + Im[6 + i] * w[2];
+    b[0] = U[0] - (w[1] * Iw[2] - w[2] * Iw[1]);
+    b[1] = U[1] - (w[2] * Iw[0] - w[0] * Iw[2]);
+    b[2] = U[2] - (w[0] * Iw[1] - w[1] * Iw[0]);
+    chol3_solve(ch, b, wd);
+}
+
+struct PosAttRhs {                         // Solver_pos_att.m:696-754
+    static constexpr int NEQ = 13;
+    OrbitTarget tg;
+    double acc[3], UM[3], Im[9];
+    Chol3 ch;
+    __device__ void operator()(double t, const double (&X)[13], double (&Xd)[13]) const {
+        double y6[6], d6[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) y6[k] = X[k];
+        orbit_rates(tg, acc, t, y6, d6);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) Xd[k] = d6[k];
+        const double q1 = X[6], q2 = X[7], q3 = X[8], q4 = X[9], w1 = X[10], w2 = X[11], w3 = X[12];
+        Xd[6] = 0.5 * ((w3 * q2 - w2 * q3) + w1 * q4);
+        Xd[7] = 0.5 * ((-w3 * q1 + w1 * q3) + w2 * q4);
+        Xd[8] = 0.5 * ((w2 * q1 - w1 * q2) + w3 * q4);
+        Xd[9] = 0.5 * ((-w1 * q1 - w2 * q2) - w3 * q3);
+        euler_wdot(Im, ch, UM, &X[10], &Xd[10]);
+    }
+};
+struct AttRhs {                            // Solver_attitude.m:1803-1849
+    static constexpr int NEQ = 7;
+    double U[3], Im[9];
+    Chol3 ch;
+    __device__ void operator()(double, const double (&X)[7], double (&Xd)[7]) const {
+        const double x1 = X[0], x2 = X[1], x3 = X[2], x4 = X[3], x5 = X[4], x6 = X[5], x7 = X[6];
+        euler_wdot(Im, ch, U, &X[0], &Xd[0]);
+        Xd[3] = 0.5 * ((x3 * x5 - x2 * x6) + x1 * x7);
+        Xd[4] = 0.5 * ((-x3 * x4 + x1 * x6) + x2 * x7);
+        Xd[5] = 0.5 * ((x2 * x4 - x1 * x5) + x3 * x7);
+        Xd[6] = 0.5 * ((-x1 * x4 - x2 * x5) - x3 * x6);
+    }
+};
+
+// [~, Y] = ode45(rhs, [t0 tf], y); y = Y(end, :).  Returns 1 when MATLAB would have warned (step size at
+// hmin) or the step bound was hit.
+template <class Rhs>
+__device__ int ode45_last(const Rhs &rhs, double t0, double tf, double (&y)[Rhs::NEQ], double rtol, double atol, int max_steps) {
+    constexpr int NEQ = Rhs::NEQ;
+    constexpr double A[6] = {1. / 5, 3. / 10, 4. / 5, 8. / 9, 1, 1};
+    constexpr double B[7][6] = {{1. / 5, 3. / 40, 44. / 45, 19372. / 6561, 9017. / 3168, 35. / 384},
+                                {0, 9. / 40, -56. / 15, -25360. / 2187, -355. / 33, 0},
+                                {0, 0, 32. / 9, 64448. / 6561, 46732. / 5247, 500. / 1113},
+                                {0, 0, 0, -212. / 729, 49. / 176, 125. / 192},
+                                {0, 0, 0, 0, -5103. / 18656, -2187. / 6784},
+                                {0, 0, 0, 0, 0, 11. / 84},
+                                {0, 0, 0, 0, 0, 0}};
+    constexpr double E[7] = {71. / 57600, 0, -71. / 16695, 71. / 1920, -17253. / 339200, 22. / 525, -1. / 40};
+    const double pw = 1. / 5;
+    double f[7][NEQ], ys[NEQ];
+    const double htspan = fabs(tf - t0), hmax = fabs(0.1 * (tf - t0)), threshold = atol / rtol;
+    double t = t0;
+    int steps = 0;
+    bool done = false;
+    rhs(t, y, f[0]);
+    double hmin = 16 * eps_of(t);
+    double absh = fmin(hmax, htspan);
+    double rh = 0;
+#pragma unroll
+    for (int i = 0; i < NEQ; ++i) rh = fmax(rh, fabs(f[0][i] / fmax(fabs(y[i]), threshold)));
+    rh = rh / (0.8 * pow(rtol, pw));
+    if (absh * rh > 1) absh = 1 / rh;
+    absh = fmax(absh, hmin);
+    while (!done) {
+        if (steps >= max_steps) return 1;
+        hmin = 16 * eps_of(t);
+        absh = fmin(hmax, fmax(hmin, absh));
+        double h = absh;
+        if (1.1 * absh >= fabs(tf - t)) {
+            h = tf - t;
+            absh = fabs(h);
+            done = true;
+        }
+        bool nofailed = true;
+        double err, tnew;
+        for (;;) {
+#pragma unroll
+            for (int k = 0; k < 6; ++k) {
+#pragma unroll
+                for (int i = 0; i < NEQ; ++i) {
+                    double s = 0;
+#pragma unroll
+                    for (int j = 0; j <= k; ++j) s = s + f[j][i] * (h * B[j][k]);
+                    ys[i] = y[i] + s;
+                }
+                if (k < 5) rhs(t + h * A[k], ys, f[k + 1]);
+            }
+            tnew = t + h * A[5];
+            if (done) tnew = tf;
+            rhs(tnew, ys, f[6]);
+            err = 0;
+#pragma unroll
+            for (int i = 0; i < NEQ; ++i) {
+                double fe = 0;
+#pragma unroll
+                for (int j = 0; j < 7; ++j) fe = fe + f[j][i] * E[j];
+                err = fmax(err, fabs(fe / fmax(fmax(fabs(y[i]), fabs(ys[i])), threshold)));
+            }
+            err = absh * err;
+            if (err > rtol) {
+                if (absh <= hmin) return 1;
+                if (nofailed) {
+                    nofailed = false;
+                    absh = fmax(hmin, absh * fmax(0.1, 0.8 * pow(rtol / err, pw)));
+                } else {
+                    absh = fmax(hmin, 0.5 * absh);
+                }
+                h = absh;
+                done = false;
+            } else {
+                break;
+            }
+        }
+        ++steps;
+        if (!done && nofailed) {
+            const double temp = 1.25 * pow(err / rtol, pw);
+            if (temp > 0.2) absh = absh / temp;
+            else absh = 5.0 * absh;
+        }
+        t = tnew;
+#pragma unroll
+        for (int i = 0; i < NEQ; ++i) { y[i] = ys[i]; f[0][i] = f[6][i]; }
+    }
+    return 0;
+}
+
+__global__ void __launch_bounds__(64) k_rollout_pos_att(const __grid_constant__ PlantParams pl) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pl.batch) return;
+    PosAttRhs rhs;
+    OrbitTarget &tg = rhs.tg;
+    tg.mu = pl.mu;
+    tg.smu = sqrt(pl.mu);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { tg.R0[k] = pl.R0[k]; tg.V0[k] = pl.V0[k]; }
+    tg.r0 = sqrt(tg.R0[0] * tg.R0[0] + tg.R0[1] * tg.R0[1] + tg.R0[2] * tg.R0[2]);
+    const double v0 = sqrt(tg.V0[0] * tg.V0[0] + tg.V0[1] * tg.V0[1] + tg.V0[2] * tg.V0[2]);
+    tg.vr0 = (tg.R0[0] * tg.V0[0] + tg.R0[1] * tg.V0[1] + tg.R0[2] * tg.V0[2]) / tg.r0;
+    tg.alpha = 2 / tg.r0 - v0 * v0 / tg.mu;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rhs.Im[k] = pl.Im[k];
+    chol3_factor(rhs.Im, rhs.ch);
+    double M1[3][3];
+    rsw2eci(pl.R0, pl.V0, M1);
+
+    double y[13];
+#pragma unroll
+    for (int k = 0; k < 13; ++k) y[k] = pl.y0[(size_t)b * 13 + k];
+    const int n_out = pl.n_steps / pl.stride_out;
+    double *X = pl.X_out + (size_t)b * 13 * (n_out + 1);
+#pragma unroll
+    for (int k = 0; k < 13; ++k) X[k] = y[k];
+    int warns = 0;
+    for (int ks = 1; ks <= pl.n_steps; ++ks) {
+        double tq[3], M2[3][3], tmp[3], xb[3], vb[3], f[12];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) tq[k] = 2 * asin(y[6 + k]);            // :472-474
+        eci2body(&y[6], M2);
+        matvec3(M1, &y[0], tmp); matvec3(M2, tmp, xb);                      // :414-415
+        matvec3(M1, &y[3], tmp); matvec3(M2, tmp, vb);
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {                                       // :432-447
+            const int a = p == 0 ? 1 : (p == 1 ? 2 : 0);                    // channel x: t_y, w_y; y: t_z, w_z; z: t_x, w_x
+            const double xq[4] = {xb[p], vb[p], tq[a], y[10 + a]};
+            const int ci = policy_at(pl.pol[p], 0, xq);
+            const double *fv = pl.fv[p];
+            const int C = pl.C[p];
+            f[2 * p] = fv[ci];                                              // thrusters (0,1,6,7), (2,3,8,9), (4,5,10,11)
+            f[2 * p + 1] = fv[C + ci];
+            f[6 + 2 * p] = fv[2 * C + ci];
+            f[7 + 2 * p] = fv[3 * C + ci];
+        }
+        // to_Moments_Forces :805-823
+        const double UMy = (((f[0] - f[1]) + f[6]) - f[7]) * pl.t_dist;
+        const double UMz = (((f[2] - f[3]) + f[8]) - f[9]) * pl.t_dist;
+        const double UMx = (((f[4] - f[5]) + f[10]) - f[11]) * pl.t_dist;
+        const double ab[3] = {(((f[0] + f[1]) + f[6]) + f[7]) / pl.mass, (((f[2] + f[3]) + f[8]) + f[9]) / pl.mass,
+                              (((f[4] + f[5]) + f[10]) + f[11]) / pl.mass};
+        lu3_solve(M2, ab, tmp);
+        lu3_solve(M1, tmp, rhs.acc);
+        rhs.UM[0] = UMx; rhs.UM[1] = UMy; rhs.UM[2] = UMz;
+        if ((ks - 1) % pl.stride_out == 0) {
+            const size_t o = (size_t)b * n_out + (ks - 1) / pl.stride_out;
+#pragma unroll
+            for (int k = 0; k < 12; ++k) pl.F_out[o * 12 + k] = f[k];
+            if (pl.FM_out) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) { pl.FM_out[o * 6 + k] = rhs.acc[k]; pl.FM_out[o * 6 + 3 + k] = rhs.UM[k]; }
+            }
+        }
+        warns += ode45_last(rhs, (double)(ks - 1) * pl.h, (double)ks * pl.h, y, pl.rtol, pl.atol, pl.max_ode);
+        if (ks % pl.stride_out == 0) {
+            double *Xk = X + (size_t)(ks / pl.stride_out) * 13;
+#pragma unroll
+            for (int k = 0; k < 13; ++k) Xk[k] = y[k];
+        }
+    }
+    if (pl.warn_out) pl.warn_out[b] = warns;
+}
+
+__global__ void __launch_bounds__(64) k_rollout_attitude(const __grid_constant__ PlantParams pl) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= pl.batch) return;
+    AttRhs rhs;
+#pragma unroll
+    for (int k = 0; k < 9; ++k) rhs.Im[k] = pl.Im[k];
+    chol3_factor(rhs.Im, rhs.ch);
+    double y[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) y[k] = pl.y0[(size_t)b * 7 + k];
+    const int n_out = pl.n_steps / pl.stride_out;
+    double *X = pl.X_out + (size_t)b * 7 * (n_out + 1);
+    int32_t *Cc = pl.C_out + (size_t)b * 3 * n_out;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) X[k] = y[k];
+    int warns = 0;
+    for (int ks = 1; ks <= pl.n_steps; ++ks) {
+        int ci[3];
+#pragma unroll
+        for (int p = 0; p < 3; ++p) {                                       // U1(k) = FU_k(X(k), 2*asin(X(3+k))) :1693-1697
+            const double xq[2] = {y[p], 2 * asin(y[3 + p])};
+            ci[p] = policy_at(pl.pol[p], 0, xq);
+            rhs.U[p] = pl.fv[0][ci[p]];
+        }
+        if ((ks - 1) % pl.stride_out == 0) {
+            const int o = (ks - 1) / pl.stride_out;
+#pragma unroll
+            for (int p = 0; p < 3; ++p) Cc[(size_t)o * 3 + p] = ci[p];
+        }
+        warns += ode45_last(rhs, (double)(ks - 1) * pl.h, (double)ks * pl.h, y, pl.rtol, pl.atol, pl.max_ode);
+        if (ks % pl.stride_out == 0) {
+            double *Xk = X + (size_t)(ks / pl.stride_out) * 7;
+#pragma unroll
+            for (int k = 0; k < 7; ++k) Xk[k] = y[k];
+        }
+    }
+    if (pl.warn_out) pl.warn_out[b] = warns;
+}
+
 }  // namespace
 
 // ---------------------------------------------------------------------------------------------
@@ -780,6 +1110,11 @@ cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+cudaError_t launch_rollout_plant(const PlantParams &pl, cudaStream_t st) {
+    if (pl.kind == 0) k_rollout_pos_att<<<(pl.batch + 63) / 64, 64, 0, st>>>(pl);
+    else k_rollout_attitude<<<(pl.batch + 63) / 64, 64, 0, st>>>(pl);
+    return cudaGetLastError();
+}
 cudaError_t launch_rollout_orbit(const OrbitParams &op, cudaStream_t st) {
     k_rollout_orbit<<<(op.batch + 63) / 64, 64, 0, st>>>(op);
     return cudaGetLastError();

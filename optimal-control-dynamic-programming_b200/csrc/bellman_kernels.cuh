@@ -87,4 +87,26 @@ struct OrbitParams {
 cudaError_t launch_rollout_orbit(const OrbitParams &op, cudaStream_t st);
 cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st);
 
+// full-plant forward simulations integrated with ode45 (one thread per initial state):
+// kind 0 = Solver_pos_att.get_optimal_path (13 states, three 4-D channel policies),
+// kind 1 = Solver_attitude.get_optimal_path_simplified_testode45 (7 states, three 2-D axis policies)
+struct PlantParams {
+    PolicyParams pol[3];       // .idx = policy of the requested stage
+    int kind;
+    int C[3];                  // controls per channel (kind 0: row length of fv[ch])
+    const double *fv[3];       // kind 0: [4][C[ch]] thruster levels f0/f1/f6/f7_allcomb; kind 1: fv[0] = u_values [C]
+    double mu, R0[3], V0[3];
+    double h, rtol, atol;      // stage length, ode45 RelTol / AbsTol
+    double Im[9];              // InertiaM, column-major
+    double mass, t_dist;
+    int n_steps, batch, stride_out, max_ode;
+    const double *y0;          // [batch][NEQ]
+    double *X_out;             // [batch][n_steps / stride_out + 1][NEQ]
+    double *F_out;             // kind 0: [batch][n_out][12] thruster levels
+    double *FM_out;            // kind 0: [batch][n_out][6] (a_x a_y a_z U_M_x U_M_y U_M_z), may be null
+    int32_t *C_out;            // kind 1: [batch][n_out][3] control indices
+    int32_t *warn_out;         // [batch] ode45 calls that stopped on the minimum step size / the step bound
+};
+cudaError_t launch_rollout_plant(const PlantParams &pl, cudaStream_t st);
+
 }  // namespace bellman

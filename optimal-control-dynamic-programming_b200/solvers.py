@@ -320,6 +320,20 @@ class Solver_attitude(_AxisSolverBase):
         self.U_vector = np.array([-0.11, 0.0, 0.11])
         self.U1_Opt = self.U2_Opt = self.U3_Opt = None
 
+    # Solver_attitude.m:306-309: w0 = 0, q0 = angle2quat(5, 10, -9 deg) reversed (scalar last)
+    defaultX0_ode45 = np.array([0.0, 0.0, 0.0, 0.0501511024391496, 0.0833950587800888, -0.0818761044636256, 0.991880252153991])
+
+    def get_optimal_path_simplified_testode45(self, X0=None, n_steps=None, stride_out=1):
+        """:1669-1705 on the GPU for a batch X0 [batch, 7] = (w1 w2 w3 q1 q2 q3 q4): per stage
+        U(k) = U{k}_Opt(X(k), 2*asin(X(3+k))), then ode45 over one stage on the full rigid-body plant
+        (:1803-1849).  Returns X_ode45 [batch, n_out + 1, 7] and the applied torques [batch, n_out, 3]."""
+        sw = self._sweep
+        X0 = self.defaultX0_ode45[None] if X0 is None else np.asarray(X0, dtype=np.float64).reshape(-1, 7)
+        n_steps = int(np.ceil(self.T_final / self.h)) - 1 if n_steps is None else int(n_steps)
+        X, Cc, W = sw.rollout_attitude(self.U_vector, X0, n_steps, self.h, self.InertiaM, stride_out=stride_out)
+        self.ode45_warnings = W
+        return X, np.asarray(self.U_vector)[Cc]
+
     def _axis_descs(self):
         self.N_stage = int(np.ceil(self.T_final / self.h))
         ang = ((self.yaw_min, self.yaw_max), (self.pitch_min, self.pitch_max), (self.roll_min, self.roll_max))
@@ -463,6 +477,9 @@ class Solver_pos_att:
         for name, thr in zip(("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb"), self._channel_thrusters[channel]):
             setattr(self, "Opt_F_Thr%d" % thr, NearestPolicy(ctl["GridVectors"], np.asarray(ctl[name]).ravel()[uid]))
         self._channel_ctl[channel] = ctl
+        old = self._lookup_sweeps.pop(channel, None)
+        if old is not None:
+            old.close()
         return self
 
     def get_thruster_on_off_optimal(self, x, v, t, w, R0=None, V0=None, q=None):
@@ -486,16 +503,7 @@ class Solver_pos_att:
         """The same 'nearest' lookup for a BATCH of channel states [batch, 4] = (x, v, theta, w) on the
         GPU (bellman_policy_lookup): returns [batch, 4] levels of the channel's four thrusters."""
         ctl = self._channel_ctl[channel]
-        ch = "xyz".index(channel)
-        sw = self._lookup_sweeps.get(channel)
-        if sw is None:
-            d = self.channel_desc(ch)
-            for k in range(4):
-                if not np.array_equal(d.grid[k][0], ctl["GridVectors"][k]):
-                    raise ValueError("controller grid differs from this object's mesh settings")
-            sw = self._lookup_sweeps[channel] = Sweep(d, device=self.device)
-            stage = max(1, min(int(ctl.get("stop_stage", 1)) or 1, d.N - 1))
-            sw.set_stage(stage, None, np.asarray(ctl["U_Optimal_id"]).astype(np.int32).ravel(order="F") - 1)
+        sw = self._channel_sweep(channel)
         c = sw.policy_lookup(states)
         return np.stack([np.asarray(ctl[k]).ravel()[c] for k in ("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb")], 1)
 
@@ -516,6 +524,62 @@ class Solver_pos_att:
         W = h / np.linalg.norm(h)
         S = np.cross(W, R)
         return np.column_stack([R, S, W])
+
+    mu = 398600.0                                                        # :454
+
+    def get_target_R0V0(self):
+        """:759-777 — the same target orbit as Solver_position (perigee altitude 300 km, e = 0.1)."""
+        RE, e = 6378.0, 0.1
+        rp = RE + 300
+        ra = rp * (1 + e) / (1 - e)
+        h_ = np.sqrt(2 * self.mu * rp * ra / (ra + rp))
+        return Solver_position.sv_from_coe([h_, e, 0.0, 0.0, 0.0, 0.0], self.mu)
+
+    @staticmethod
+    def default_X0():
+        """:458-468 — dr0 = [-0.1 0 0], dv0 = 0, q0 = angle2quat(0, 3 deg, 0) reversed (scalar last), w0 = 0."""
+        a = tables.deg2rad(3.0) / 2
+        return np.array([-0.1, 0, 0, 0, 0, 0, 0.0, np.sin(a), 0.0, np.cos(a), 0, 0, 0])
+
+    def _channel_sweep(self, channel):
+        """Handle holding the channel's installed controller (set_controller) as its policy."""
+        ctl = self._channel_ctl[channel]
+        sw = self._lookup_sweeps.get(channel)
+        if sw is None:
+            d = self.channel_desc("xyz".index(channel))
+            if len(np.ravel(ctl["f0_allcomb"])) != d.C:                  # a failure-mode controller (:236-240)
+                d = self.channel_desc("xyz".index(channel), failure=True)
+            if len(np.ravel(ctl["f0_allcomb"])) != d.C:
+                raise ValueError("controller combinations differ from this object's thruster settings")
+            for k in range(4):
+                if not np.array_equal(d.grid[k][0], ctl["GridVectors"][k]):
+                    raise ValueError("controller grid differs from this object's mesh settings")
+            sw = self._lookup_sweeps[channel] = Sweep(d, device=self.device)
+            stage = max(1, min(int(ctl.get("stop_stage", 1)) or 1, d.N - 1))
+            sw.set_stage(stage, None, np.asarray(ctl["U_Optimal_id"]).astype(np.int32).ravel(order="F") - 1)
+        return sw
+
+    def get_optimal_path(self, X0=None, n_steps=None, stride_out=1, controllers=None):
+        """:452-500 on the GPU for a batch of initial states X0 [batch, 13] = (dr dv q w) (default the
+        reference's single state): thruster levels from the three installed channel controllers, moments
+        and forces, one ode45 call per stage on the 13-state plant.  ``controllers`` = three files / dicts
+        to install first (the reference loads channel_{x,y,z}_controller_1.mat, :469-471).
+        Returns X_ode45 [batch, n_out + 1, 13], F_Th_Opt [batch, n_out, 12], Force_Moment_log [batch, n_out, 6]."""
+        from ._lib import rollout_pos_att
+        if controllers is not None:
+            for ch, c in zip("xyz", controllers):
+                self.set_controller(c, ch)
+        X0 = self.default_X0()[None] if X0 is None else np.asarray(X0, dtype=np.float64).reshape(-1, 13)
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        n_steps = self.N_stage - 1 if n_steps is None else int(n_steps)
+        sws = [self._channel_sweep(ch) for ch in "xyz"]
+        fv = [np.stack([np.asarray(self._channel_ctl[ch][k], dtype=np.float64).ravel()
+                        for k in ("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb")]) for ch in "xyz"]
+        R0, V0 = self.get_target_R0V0()
+        X, F, FM, W = rollout_pos_att(sws, fv, X0, n_steps, self.h, R0, V0, self.InertiaM, self.Mass, self.T_dist,
+                                      mu=self.mu, stride_out=stride_out)
+        self.ode45_warnings = W
+        return X, F, FM
 
     def simplified_run(self, save=False, failure_mode=True, n_stages=None):
         """Solver_pos_att.m:197-242: x, y, z channels, then the x-channel failure mode."""
