@@ -43,6 +43,8 @@ classdef Solver_attitude < handle
         F_Values
         U_idx
         device = -1
+        last_desc_      % descriptor of the last simplified_run (for the forward simulation)
+        defaultX0
         n_gpus = 1      % > 1: the grid is cut into slabs over this many GPUs, driven from this one process
     end
 
@@ -63,6 +65,8 @@ classdef Solver_attitude < handle
             this.N_stage = ceil(this.T_final/this.h);
             this.J1 = this.InertiaM(1); this.J2 = this.InertiaM(5); this.J3 = this.InertiaM(9);
             this.U_vector = [-0.11 0 0.11];
+            q0 = [0.0501511024391496;0.0833950587800888;-0.0818761044636256;0.991880252153991];   % :306-309
+            this.defaultX0 = [0;0;0;q0];
         end
 
         function simplified_run(obj, n_stages)
@@ -89,6 +93,7 @@ classdef Solver_attitude < handle
             d.q  = {(s_w.^2)*Qw, qt};
             d.r  = (U.^2)*R;
             d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
+            obj.last_desc_ = d;
             sz = [obj.n_mesh_w, obj.n_mesh_t, 3];
             tic
             if obj.n_gpus > 1
@@ -106,6 +111,26 @@ classdef Solver_attitude < handle
             obj.U2_Opt = griddedInterpolant({s_w.', s_t(:,2).'}, obj.U_vector(obj.U_idx(:,:,2)), 'nearest');
             obj.U3_Opt = griddedInterpolant({s_w.', s_t(:,3).'}, obj.U_vector(obj.U_idx(:,:,3)), 'nearest');
             fprintf('...Done!\n')
+        end
+
+        function [X_ode45, U_ode45] = get_optimal_path_simplified_testode45(obj, X0)
+            % Solver_attitude.m:1669-1705 of the reference for every column of X0 (7 x batch: w1 w2 w3 q1 q2
+            % q3 q4; default obj.defaultX0): U(k) = U{k}_Opt(X(k), 2*asin(X(3+k))), then ode45 over one
+            % stage on the full rigid-body plant (:1803-1849), one GPU thread per initial state.
+            if nargin < 2, X0 = obj.defaultX0; end
+            d = obj.last_desc_;
+            hnd = bellman_mex('create', d);
+            bellman_mex('set_stage', hnd, 1, reshape(obj.F_Values, [], 3), reshape(obj.U_idx, [], 3));
+            N = obj.N_stage;
+            o = struct('n_steps', N - 1, 'stride_out', 1, 'h', obj.h, 'rtol', 1e-3, 'atol', 1e-6, 'InertiaM', obj.InertiaM);
+            [X, id] = bellman_mex('rollout_attitude', hnd, 1, o, obj.U_vector(:), X0);
+            bellman_mex('destroy', hnd);
+            batch = size(X0, 2);
+            X_ode45 = permute(reshape(X, 7, N, batch), [2 1 3]);                 % N x 7 (x batch), as :1683
+            U_ode45 = permute(reshape(obj.U_vector(id), 3, N - 1, batch), [2 1 3]);
+            T_ode45 = (0:N-1)*obj.h;
+            figure; hold on; grid on; plot(T_ode45, X_ode45(:,1:3,1)*180/pi); legend('w1','w2','w3')
+            figure; hold on; grid on; plot(T_ode45(1:end-1), U_ode45(:,:,1), '--'); legend('u1','u2','u3')
         end
     end
 end

@@ -4,7 +4,8 @@ classdef Solver_pos_att < handle
     %   simplified_run (:197-242), calculate_one_channel_U_Opt (:244-297), set_controller
     %   (:849-884), vectors_allcomb (:886-904), sym_linspace (:906-918).  fp64 throughout (the
     %   reference casts J to single); idsum50_prev starts at 0 (the reference reads it undefined).
-    %   The 13-state ode45 forward simulation is outside this build's scope.
+    %   get_optimal_path (:452-500): the 13-state plant under the three channel controllers, one ode45
+    %   call per stage (Dormand-Prince with MATLAB's default step control, restated), one GPU thread per X0.
 
     properties
         v_min
@@ -164,6 +165,49 @@ classdef Solver_pos_att < handle
                 case 'z', obj.Opt_F_Thr4 = g0; obj.Opt_F_Thr5 = g1; obj.Opt_F_Thr10 = g6; obj.Opt_F_Thr11 = g7;
                 otherwise, error('wrong channel, must be one of x-y-z values')
             end
+        end
+
+        function [X_ode45, F_Th_Opt, Force_Moment_log] = get_optimal_path(obj, X0)
+            % Solver_pos_att.m:452-500 of the reference for every column of X0 (13 x batch; default the
+            % reference's dr0 = [-0.1 0 0], q0 = angle2quat(0, 3 deg, 0) reversed): thruster levels from the
+            % three channel controllers, moments and forces, ode45 over one stage on the 13-state plant.
+            if nargin < 2
+                X0 = [-0.1 0 0, 0 0 0, 0 sin(deg2rad(3)/2) 0 cos(deg2rad(3)/2), 0 0 0].';
+            end
+            mu = 398600;  RE = 6378;  rp = RE + 300;  e = 0.1;            % get_target_R0V0, :759-777
+            ra = rp*(1 + e)/(1 - e);
+            h_ = sqrt(2*mu*rp*ra/(ra + rp));
+            R0 = (h_^2/mu)*(1/(1 + e))*[1 0 0];  V0 = (mu/h_)*[0 (e + 1) 0];
+            files = {'channel_x_controller_1.mat', 'channel_y_controller_1.mat', 'channel_z_controller_1.mat'};   % :469-471
+            hs = zeros(1, 3, 'uint64');  fv = cell(1, 3);
+            for c = 1:3
+                C = load(files{c});
+                gv = C.F_gI.GridVectors;
+                nC = numel(C.f0_allcomb);
+                % a handle that only has to hold the grid and the policy: identity dynamics, zero costs
+                d = struct('n', cellfun(@numel, gv), 'C', nC, 'P', 1, 'N', 2);
+                d.grid = cellfun(@(g) g(:), gv, 'UniformOutput', false);
+                d.src_a = [1 2 3 4];  d.src_b = [0 0 0 0];
+                d.Ta = d.grid;  d.Tb = {[], [], [], []};  d.Tc = {[], zeros(nC,1), [], zeros(nC,1)};
+                d.q_order = [1 2 3 4];  d.q = cellfun(@(g) zeros(numel(g),1), gv, 'UniformOutput', false);
+                d.r = zeros(nC, 1);  d.store_J_all = 0;  d.store_idx_all = 0;  d.device = obj.device;
+                hs(c) = bellman_mex('create', d);
+                bellman_mex('set_stage', hs(c), 1, [], double(C.U_Optimal_id(:)));
+                fv{c} = [C.f0_allcomb(:) C.f1_allcomb(:) C.f6_allcomb(:) C.f7_allcomb(:)].';
+            end
+            N = obj.N_stage;
+            o = struct('n_steps', N - 1, 'stride_out', 1, 'mu', mu, 'R0', R0, 'V0', V0, 'h', obj.h, ...
+                'rtol', 1e-3, 'atol', 1e-6, 'InertiaM', obj.InertiaM, 'Mass', obj.Mass, 'T_dist', obj.T_dist);
+            [X, F, FM] = bellman_mex('rollout_pos_att', hs, [1 1 1], o, fv{1}, fv{2}, fv{3}, X0);
+            for c = 1:3, bellman_mex('destroy', hs(c)); end
+            batch = size(X0, 2);
+            X_ode45 = permute(reshape(X, 13, N, batch), [2 1 3]);               % N x 13 (x batch), as :477
+            F_Th_Opt = permute(reshape(F, 12, N - 1, batch), [2 1 3]);
+            Force_Moment_log = permute(reshape(FM, 6, N - 1, batch), [2 1 3]);
+            T_ode45 = (0:N-2)*obj.h;
+            figure('Name','Thruster Firings'); plot(T_ode45, F_Th_Opt(:,:,1)); grid on
+            figure('Name','states - position'); plot((0:N-1)*obj.h, X_ode45(:,1:3,1)); grid on; legend('x1','x2','x3')
+            figure('Name','states - quaternions'); plot((0:N-1)*obj.h, X_ode45(:,7:10,1)); grid on; legend('q1','q2','q3','q4')
         end
 
         function [a1, a2, a3, a4] = vectors_allcomb(~, f1, f2, f3, f4)

@@ -18,6 +18,12 @@
 //   [X,id,w] = bellman_mex('rollout_orbit', h, stage, o, u_values, Y0)   Solver_position.get_optimal_path:
 //                                                     o: struct n_steps, stride_out, mu, R0, V0, h, tol; Y0: 6 x batch;
 //                                                     X: 6 x ((n_steps/stride_out+1)*batch), id (1-based): 3 x (n_out*batch)
+//   [X,F,FM,w] = bellman_mex('rollout_pos_att', [hx hy hz], stages, o, fx, fy, fz, Y0)   Solver_pos_att.get_optimal_path:
+//                                                     o: struct n_steps, stride_out, mu, R0, V0, h, rtol, atol, InertiaM (3x3),
+//                                                     Mass, T_dist; f*: 4 x C_ch thruster levels; Y0: 13 x batch;
+//                                                     X: 13 x ((n_out+1)*batch), F: 12 x (n_out*batch), FM: 6 x (n_out*batch)
+//   [X,id,w] = bellman_mex('rollout_attitude', h, stage, o, u_values, Y0)   Solver_attitude.get_optimal_path_simplified_testode45:
+//                                                     o: struct n_steps, stride_out, h, rtol, atol, InertiaM; Y0: 7 x batch
 //            bellman_mex('destroy', h)
 //   v      = bellman_mex('version')
 //
@@ -152,6 +158,26 @@ static const double *need_doubles(const mxArray *a, size_t want, const char *wha
         mexErrMsgIdAndTxt("bellman:BAD_ARG", "%s must be a real double array with %d elements", what, (int)want);
     return mxGetPr(a);
 }
+static void plant_opts_from(const mxArray *s, bellman_plant_opts &o) {
+    std::memset(&o, 0, sizeof(o));
+    o.struct_size = (int32_t)sizeof(o);
+    o.n_steps = (int32_t)field_scalar(s, "n_steps", 0);
+    o.stride_out = (int32_t)field_scalar(s, "stride_out", 1);
+    o.mu = field_scalar(s, "mu", 398600.0);
+    o.h = field_scalar(s, "h", 0.0);
+    o.rtol = field_scalar(s, "rtol", 1e-3);
+    o.atol = field_scalar(s, "atol", 1e-6);
+    o.mass = field_scalar(s, "Mass", 0.0);
+    o.t_dist = field_scalar(s, "T_dist", 0.0);
+    const double *Im = need_doubles(mxGetField(s, 0, "InertiaM"), 9, "o.InertiaM");
+    for (int k = 0; k < 9; ++k) o.inertia[k] = Im[k];
+    const mxArray *r0 = mxGetField(s, 0, "R0"), *v0 = mxGetField(s, 0, "V0");
+    if (r0 && v0) {
+        const double *R0 = need_doubles(r0, 3, "o.R0"), *V0 = need_doubles(v0, 3, "o.V0");
+        for (int k = 0; k < 3; ++k) { o.R0[k] = R0[k]; o.V0[k] = V0[k]; }
+    }
+    if (o.n_steps < 1 || o.stride_out < 1 || o.n_steps % o.stride_out) mexErrMsgIdAndTxt("bellman:BAD_ARG", "n_steps must be a positive multiple of stride_out");
+}
 static std::vector<std::pair<bellman_handle *, Shape>> g_shapes;
 
 static Shape shape_of(bellman_handle *h) {
@@ -213,6 +239,35 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
             for (bellman_handle *h : hs)
                 if (bellman_last_error(h)[0]) check(rc, h);
         check(rc, hs[0]);
+        return;
+    }
+    if (cmd == "rollout_pos_att") {
+        if (nrhs < 8 || !mxIsClass(prhs[1], "uint64") || mxGetNumberOfElements(prhs[1]) != 3 || !mxIsStruct(prhs[3]))
+            mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,F,FM,w] = bellman_mex('rollout_pos_att', [hx hy hz], stages, o, fx, fy, fz, Y0)");
+        bellman_handle *hs[3];
+        int32_t stage[3];
+        const double *fv[3];
+        const double *st = need_doubles(prhs[2], 3, "stages");
+        for (int k = 0; k < 3; ++k) {
+            hs[k] = reinterpret_cast<bellman_handle *>(static_cast<uint64_t *>(mxGetData(prhs[1]))[k]);
+            if (!g_live.count(hs[k])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "stale or foreign handle");
+            stage[k] = (int32_t)st[k];
+            fv[k] = need_doubles(prhs[4 + k], 4 * (size_t)shape_of(hs[k]).C, "f_x / f_y / f_z (4-by-C of the channel)");
+        }
+        bellman_plant_opts o;
+        plant_opts_from(prhs[3], o);
+        const size_t batch = mxGetN(prhs[7]);
+        need_doubles(prhs[7], 13 * batch, "Y0 (13-by-batch)");
+        const size_t n_out = (size_t)(o.n_steps / o.stride_out);
+        plhs[0] = mxCreateDoubleMatrix(13, (n_out + 1) * batch, mxREAL);
+        mxArray *F = mxCreateDoubleMatrix(12, n_out * batch, mxREAL);
+        mxArray *FM = mxCreateDoubleMatrix(6, n_out * batch, mxREAL);
+        mxArray *w = mxCreateNumericMatrix(1, batch, mxINT32_CLASS, mxREAL);
+        check(bellman_rollout_pos_att(hs[0], hs[1], hs[2], stage, &o, fv[0], fv[1], fv[2], mxGetPr(prhs[7]), (int32_t)batch,
+                                      mxGetPr(plhs[0]), mxGetPr(F), mxGetPr(FM), static_cast<int32_t *>(mxGetData(w))), hs[0]);
+        if (nlhs > 1) plhs[1] = F; else mxDestroyArray(F);
+        if (nlhs > 2) plhs[2] = FM; else mxDestroyArray(FM);
+        if (nlhs > 3) plhs[3] = w; else mxDestroyArray(w);
         return;
     }
     if (cmd == "create") {
@@ -381,6 +436,23 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         int32_t *pi = static_cast<int32_t *>(mxGetData(id));
         check(bellman_rollout_orbit(h, (int32_t)mxGetScalar(prhs[2]), &o, mxGetPr(prhs[4]), mxGetPr(prhs[5]), (int32_t)batch,
                                     mxGetPr(plhs[0]), pi, static_cast<int32_t *>(mxGetData(w))), h);
+        for (size_t k = 0; k < 3 * n_out * batch; ++k) pi[k] += 1;
+        if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
+        if (nlhs > 2) plhs[2] = w; else mxDestroyArray(w);
+    } else if (cmd == "rollout_attitude") {
+        if (nrhs < 6 || !mxIsStruct(prhs[3])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,id,w] = bellman_mex('rollout_attitude', h, stage, o, u_values, Y0)");
+        bellman_plant_opts o;
+        plant_opts_from(prhs[3], o);
+        const size_t batch = mxGetN(prhs[5]);
+        need_doubles(prhs[4], (size_t)sh.C, "u_values");
+        need_doubles(prhs[5], 7 * batch, "Y0 (7-by-batch)");
+        const size_t n_out = (size_t)(o.n_steps / o.stride_out);
+        plhs[0] = mxCreateDoubleMatrix(7, (n_out + 1) * batch, mxREAL);
+        mxArray *id = mxCreateNumericMatrix(3, n_out * batch, mxINT32_CLASS, mxREAL);
+        mxArray *w = mxCreateNumericMatrix(1, batch, mxINT32_CLASS, mxREAL);
+        int32_t *pi = static_cast<int32_t *>(mxGetData(id));
+        check(bellman_rollout_attitude(h, (int32_t)mxGetScalar(prhs[2]), &o, mxGetPr(prhs[4]), mxGetPr(prhs[5]), (int32_t)batch,
+                                       mxGetPr(plhs[0]), pi, static_cast<int32_t *>(mxGetData(w))), h);
         for (size_t k = 0; k < 3 * n_out * batch; ++k) pi[k] += 1;
         if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
         if (nlhs > 2) plhs[2] = w; else mxDestroyArray(w);
