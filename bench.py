@@ -331,6 +331,51 @@ def rollout_rate(bb, local):
             "state_steps_per_s": len(x0) * (d.N - 1) / dt, "call": "bellman_rollout (host x0 in, X and U out into pinned host arrays; median of %d calls)" % reps}
 
 
+def plant_rollout_rate(bb, local):
+    """Solver_pos_att.get_optimal_path (13-state plant, one ode45 call per stage) for a
+    batch of initial states through bellman_rollout_pos_att (host buffers), against the C restatement on
+    the host cores for a bounded sub-batch (the checker, timed as the CPU arm of this row)."""
+    from oracle import cbind
+    sp = bb.Solver_pos_att()
+    sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 12, 10, 8, 7
+    sp.check_period = 0
+    sp.device = local
+    descs, idxs, fvals = [], [], []
+    for ci, ch in enumerate("xyz"):
+        ctl = sp.calculate_one_channel_U_Opt(ci, n_stages=150)
+        sp.set_controller(ctl, ch)
+        d = sp.channel_desc(ci)
+        descs.append(d)
+        idxs.append((np.asarray(ctl["U_Optimal_id"]) - 1).astype(np.int32).ravel(order="F"))
+        fvals.append(np.stack([d.meta[k] for k in ("f0_allcomb", "f1_allcomb", "f6_allcomb", "f7_allcomb")]))
+    rng = np.random.default_rng(1)
+    batch, n_steps = 4096, 200
+    y0 = np.zeros((batch, 13))
+    y0[:, 0:3] = rng.uniform(-0.18, 0.18, size=(batch, 3))
+    y0[:, 3:6] = rng.uniform(-0.08, 0.08, size=(batch, 3))
+    y0[:, 6:9] = rng.uniform(-0.04, 0.04, size=(batch, 3))
+    y0[:, 9] = np.sqrt(1 - np.sum(y0[:, 6:9] ** 2, axis=1))
+    y0[:, 10:13] = rng.uniform(-0.03, 0.03, size=(batch, 3))
+    sp.get_optimal_path(y0[:64], n_steps=8)                       # warm-up (creates the channel handles)
+    dts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        Xg, Fg, _ = sp.get_optimal_path(y0, n_steps=n_steps)
+        dts.append(time.perf_counter() - t0)
+    dt = float(np.median(dts))
+    R0, V0 = sp.get_target_R0V0()
+    nb = 256
+    t0 = time.perf_counter()
+    Xo, Fo, _, _ = cbind.rollout_pos_att(descs, idxs, fvals, y0[:nb], n_steps, sp.h, R0, V0, sp.InertiaM, sp.Mass, sp.T_dist)
+    dt_cpu = time.perf_counter() - t0
+    same = np.all(Fg[:nb] == Fo, axis=(1, 2))
+    ok = bool(same.mean() >= 0.95 and np.allclose(Xg[:nb][same], Xo[same], rtol=0, atol=1e-9))
+    return {"x0": batch, "stages": n_steps, "ms": dt * 1e3, "trajectories_per_s": batch / dt,
+            "ode45_steps_per_s": batch * n_steps * 10 / dt, "cpu_port_trajectories_per_s": nb / dt_cpu,
+            "cpu_cores": cbind.num_threads(), "parity_vs_oracle": "pass" if ok else "FAIL",
+            "call": "bellman_rollout_pos_att (host x0 in; X, thruster levels, forces/moments out; median of 3 calls)"}
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -649,6 +694,7 @@ def main():
                 "bytes_per_launch": 3 * 16000 * 4800 * 20, "traffic": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][0],
                 "traffic_source": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][1]}
         others["rollout_64x64_x0"] = rollout_rate(bb, local)
+        others["pos_att_plant_rollout_4096_x0"] = plant_rollout_rate(bb, local)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -75,6 +75,8 @@ class Dynamic_Solver:
         # build options (not in the reference)
         self.store_J_star = True         # keep every stage's J / u_star on the host as the reference does
         self.device = -1
+        self.n_gpus = 1                  # > 1: slabs over this many GPUs driven from this one process
+        self.devices = None              # GPU of every slab (default 0 .. n_gpus-1)
         self.kernel = KERNEL_AUTO
         self.verbose = False
         self._sweep = None
@@ -96,8 +98,20 @@ class Dynamic_Solver:
         if self._sweep is not None:
             self._sweep.close()
         # u_star of every stage stays on the device: one or two bytes per state are enough for du controls
-        sw = self._sweep = Sweep(d, device=self.device, idx_bytes=1 if d.C <= 256 else 2 if d.C <= 65536 else 4)
-        sw.run(d.N - 1, kernel=self.kernel, sync_each_stage=self.verbose)
+        ib = 1 if d.C <= 256 else 2 if d.C <= 65536 else 4
+        if self.n_gpus > 1:
+            # one host thread, n slabs (bellman_group_run); every kept stage is then gathered into an
+            # unsharded handle so that get_optimal_path and the per-stage reads below work as after a one-GPU run
+            grp = SweepGroup(d, self.devices or list(range(self.n_gpus)), idx_bytes=ib)
+            grp.run(d.N - 1, kernel=self.kernel)
+            sw = self._sweep = Sweep(d, device=self.device, idx_bytes=ib)
+            for k in range(d.N - 1, 0, -1):          # u_star of every stage is always kept (store_idx_all)
+                sw.set_stage(k, grp.get_J(k) if (d.store_J_all or k == 1) else None, grp.get_idx(k))
+            self.sweep_stats = grp.stats()
+            grp.close()
+        else:
+            sw = self._sweep = Sweep(d, device=self.device, idx_bytes=ib)
+            sw.run(d.N - 1, kernel=self.kernel, sync_each_stage=self.verbose)
         if self.verbose:
             st = sw.stats()
             print("sweep: %d stages in %.3f ms (%s kernel)" % (d.N - 1, st["ms"], sw.last_kernel))
@@ -381,6 +395,8 @@ class Solver_pos_att:
         self.F_Thr2 = on.copy(); self.F_Thr3 = on.copy(); self.F_Thr8 = off.copy(); self.F_Thr9 = off.copy()
         self.F_Thr4 = on.copy(); self.F_Thr5 = on.copy(); self.F_Thr10 = off.copy(); self.F_Thr11 = off.copy()
         self.device = -1
+        self.n_gpus = 1                 # > 1: every channel sweep is cut into slabs over this many GPUs, one process
+        self.devices = None             # GPU of every slab (default 0 .. n_gpus-1)
         self.kernel = KERNEL_AUTO
         self.check_period = 50          # Solver_pos_att.m:273
         self.check_tol = 1e-2           # :269
@@ -416,7 +432,10 @@ class Solver_pos_att:
         """Solver_pos_att.m:244-297 for one channel; returns the controller dict that the reference
         saves (F_gI values + grid vectors, U_Optimal_id (1-based), f*_allcomb)."""
         d = self.channel_desc(ch, failure)
-        sw = Sweep(d, device=self.device)
+        if self.n_gpus > 1:     # one host thread, n slabs along the dimension with the smallest halo (bellman_group_run)
+            sw = SweepGroup(d, self.devices or list(range(self.n_gpus)))
+        else:
+            sw = Sweep(d, device=self.device)
         todo = d.N - 1 if n_stages is None else int(n_stages)
         sw.run(todo, kernel=self.kernel, check_period=self.check_period, check_tol=self.check_tol)
         shape = tuple(d.n)

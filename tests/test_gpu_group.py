@@ -136,3 +136,37 @@ def test_handles_with_different_window_sizes_coexist(bellman, oracle_lib):
     assert np.array_equal(a.get_J(), oa["J_last"]) and np.array_equal(b.get_J(), ob["J_last"])
     a.close()
     b.close()
+
+
+def test_facade_n_gpus_dynamic_solver_and_pos_att(bellman, oracle_lib):
+    """n_gpus on the two other facades: Dynamic_Solver (every stage's J_star / u_star gathered, rollouts on
+    the gathered policy) and Solver_pos_att (channel sweeps with the reference's Sigma-check and early stop)."""
+    def mk(n_gpus):
+        o = bellman.Dynamic_Solver()
+        o.dx, o.du, o.N = 96, 40, 30
+        o.n_gpus, o.devices = n_gpus, (_devices(n_gpus) if n_gpus > 1 else None)
+        return o.run()
+    a, b = mk(1), mk(2)
+    assert np.array_equal(a.J_star, b.J_star) and np.array_equal(a.u_star, b.u_star)
+    assert np.array_equal(a.u_star_idx, b.u_star_idx)
+    x0 = np.random.default_rng(4).uniform(-2.0, 2.5, size=(50, 2))
+    for mode, ssu in (("Nssu", 1), ("ssu", 7)):
+        Xa, Ua = a.get_optimal_path(x0, mode, ssu)
+        Xb, Ub = b.get_optimal_path(x0, mode, ssu)
+        np.testing.assert_array_equal(Xa, Xb)
+        np.testing.assert_array_equal(Ua, Ub)
+    b.store_J_star = False                                   # only stage 1 of J kept; the policies of all stages still are
+    b.run()
+    assert np.array_equal(b.F_Values, a.F_Values)
+    np.testing.assert_array_equal(b.get_optimal_path(x0)[0], a.get_optimal_path(x0)[0])
+
+    def ch(n_gpus):
+        sp = bellman.Solver_pos_att()
+        sp.n_mesh_x, sp.n_mesh_v, sp.n_mesh_t, sp.n_mesh_w = 24, 10, 12, 15
+        sp.check_tol = 0.0
+        sp.n_gpus, sp.devices = n_gpus, (_devices(n_gpus) if n_gpus > 1 else None)
+        return sp.calculate_one_channel_U_Opt(1, n_stages=120)
+    c1, c2 = ch(1), ch(2)
+    assert np.array_equal(c1["U_Optimal_id"], c2["U_Optimal_id"]) and np.array_equal(c1["F_gI_Values"], c2["F_gI_Values"])
+    assert c1["stop_stage"] == c2["stop_stage"]
+    assert np.array_equal(c1["check_log"][:, [0, 2]], c2["check_log"][:, [0, 2]])
