@@ -882,7 +882,7 @@ __device__ int ode45_last(const Rhs &rhs, double t0, double tf, double (&y)[Rhs:
     return 0;
 }
 
-__global__ void __launch_bounds__(64) k_rollout_pos_att(const __grid_constant__ PlantParams pl) {
+__global__ void __launch_bounds__(32) k_rollout_pos_att(const __grid_constant__ PlantParams pl) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= pl.batch) return;
     PosAttRhs rhs;
@@ -956,7 +956,7 @@ __global__ void __launch_bounds__(64) k_rollout_pos_att(const __grid_constant__ 
     if (pl.warn_out) pl.warn_out[b] = warns;
 }
 
-__global__ void __launch_bounds__(64) k_rollout_attitude(const __grid_constant__ PlantParams pl) {
+__global__ void __launch_bounds__(32) k_rollout_attitude(const __grid_constant__ PlantParams pl) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= pl.batch) return;
     AttRhs rhs;
@@ -1111,8 +1111,10 @@ cudaError_t launch_rollout_axis(const PolicyParams &pp, cudaStream_t st) {
 }
 
 cudaError_t launch_rollout_plant(const PlantParams &pl, cudaStream_t st) {
-    if (pl.kind == 0) k_rollout_pos_att<<<(pl.batch + 63) / 64, 64, 0, st>>>(pl);
-    else k_rollout_attitude<<<(pl.batch + 63) / 64, 64, 0, st>>>(pl);
+    // one warp per CTA: the trajectories are long serial chains (latency-bound), so a batch of a few
+    // thousand initial states must spread over all 148 SMs rather than fill a few of them
+    if (pl.kind == 0) k_rollout_pos_att<<<(pl.batch + 31) / 32, 32, 0, st>>>(pl);
+    else k_rollout_attitude<<<(pl.batch + 31) / 32, 32, 0, st>>>(pl);
     return cudaGetLastError();
 }
 cudaError_t launch_rollout_orbit(const OrbitParams &op, cudaStream_t st) {

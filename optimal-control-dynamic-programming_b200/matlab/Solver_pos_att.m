@@ -74,6 +74,7 @@ classdef Solver_pos_att < handle
         Opt_F_Thr10
         Opt_F_Thr11
         device = -1
+        n_gpus = 1      % > 1: every channel sweep is cut into slabs over this many GPUs, driven from this one process
     end
 
     methods
@@ -135,22 +136,29 @@ classdef Solver_pos_att < handle
             d.q  = {Qx*s_x.^2, Qv*s_v.^2, Qt*s_t.^2, Qw*s_w.^2};
             d.r  = R*f0_allcomb.^2 + R*f1_allcomb.^2 + R*f6_allcomb.^2 + R*f7_allcomb.^2;
             d.store_J_all = 0; d.store_idx_all = 0; d.device = obj.device;
-            hnd = bellman_mex('create', d);
             tic
-            bellman_mex('run', hnd, obj.N_stage - 1, struct('check_period', 50, 'check_tol', 1e-2));
-            lg = bellman_mex('check_log', hnd);
+            ropts = struct('check_period', 50, 'check_tol', 1e-2);
+            if obj.n_gpus > 1
+                [Jv, iv, ~, lg, stage_now] = bellman_sweep_multi(d, obj.N_stage - 1, obj.n_gpus, ropts);
+            else
+                hnd = bellman_mex('create', d);
+                bellman_mex('run', hnd, obj.N_stage - 1, ropts);
+                lg = bellman_mex('check_log', hnd);
+                stage_now = bellman_mex('current_stage', hnd);
+                Jv = bellman_mex('get_J', hnd);  iv = bellman_mex('get_idx', hnd);
+                bellman_mex('destroy', hnd);
+            end
             prev = [0; 0];
             for k = 1:size(lg, 2)
                 fprintf('stage %d - errorF %f - errorU %f\n', lg(1,k), lg(2,k) - prev(1), lg(3,k) - prev(2));
                 prev = lg(2:3,k);
             end
-            if bellman_mex('current_stage', hnd) > 1
+            if stage_now > 1
                 fprintf('sum of errors in the last 50 stages is under tolerance, breaking loop...\n')
             end
             fprintf('%f seconds\n', toc)
-            F_gI = griddedInterpolant({s_x.', s_v.', s_t.', s_w.'}, reshape(bellman_mex('get_J', hnd), d.n), 'linear');
-            U_Optimal_id = double(reshape(bellman_mex('get_idx', hnd), d.n));
-            bellman_mex('destroy', hnd);
+            F_gI = griddedInterpolant({s_x.', s_v.', s_t.', s_w.'}, reshape(Jv, d.n), 'linear');
+            U_Optimal_id = double(reshape(iv, d.n));
             save(file_name, 'F_gI', 'U_Optimal_id', 'f0_allcomb', 'f1_allcomb', 'f6_allcomb', 'f7_allcomb')
             fprintf('\nstage calculations complete.\n')
         end

@@ -1,11 +1,12 @@
-function [J, idx, st] = bellman_sweep_multi(d, n_stages, n_gpus, opts)
+function [J, idx, st, lg, stage] = bellman_sweep_multi(d, n_stages, n_gpus, opts)
 %BELLMAN_SWEEP_MULTI  Backward sweep of descriptor d on n_gpus GPUs, driven by this one MATLAB process.
-%   [J, idx, st] = bellman_sweep_multi(d, n_stages, n_gpus, opts) cuts the state grid into n_gpus slabs
+%   [J, idx, st, lg, stage] = bellman_sweep_multi(d, n_stages, n_gpus, opts) cuts the state grid into n_gpus slabs
 %   along the dimension with the smallest halo (bellman_mex('plan', ...)), creates one handle per GPU,
 %   links them (bellman_mex('group_init', ...): the stage kernels store halo values straight into the
 %   neighbouring slabs' buffers over NVLink, no NCCL, no second process) and runs n_stages stages on all
 %   slabs together.  Returns the value function J (S x P) and the 1-based argmin idx (S x P) of the last
-%   stage computed, stitched back into the global column-major order, and the run statistics.
+%   stage computed, stitched back into the global column-major order, the run statistics, the Sigma-check
+%   log (3 x checks: stage, sum(J), sum(idx); opts.check_period > 0) and the stage the run stopped at.
 %   d is the struct a facade's build_desc returns; store_J_all / store_idx_all are forced off (only the
 %   last stage is kept, as Solver_position / Solver_attitude / Solver_pos_att do).
     if nargin < 4, opts = struct(); end
@@ -20,6 +21,8 @@ function [J, idx, st] = bellman_sweep_multi(d, n_stages, n_gpus, opts)
         bellman_mex('group_init', hs);
         bellman_mex('group_run', hs, n_stages, opts);
         st = bellman_mex('stats', hs(1));
+        lg = bellman_mex('check_log', hs(1));
+        stage = bellman_mex('current_stage', hs(1));
         n = d.n(:).';
         parts_J = cell(1, n_gpus);  parts_I = cell(1, n_gpus);
         for r = 1:n_gpus
