@@ -564,7 +564,7 @@ __device__ __forceinline__ double eps_of(double t) {   // MATLAB eps(t)
     return ldexp(1.0, e - 53);
 }
 
-__global__ void __launch_bounds__(64) k_rollout_orbit(const __grid_constant__ OrbitParams op) {
+__global__ void __launch_bounds__(32) k_rollout_orbit(const __grid_constant__ OrbitParams op) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= op.batch) return;
     const double ra[6] = {0, 1. / 4, 3. / 8, 12. / 13, 1, 1. / 2};
@@ -1118,7 +1118,7 @@ cudaError_t launch_rollout_plant(const PlantParams &pl, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t launch_rollout_orbit(const OrbitParams &op, cudaStream_t st) {
-    k_rollout_orbit<<<(op.batch + 63) / 64, 64, 0, st>>>(op);
+    k_rollout_orbit<<<(op.batch + 31) / 32, 32, 0, st>>>(op);      // one warp per CTA (see launch_rollout_plant)
     return cudaGetLastError();
 }
 
