@@ -363,6 +363,9 @@ def plant_rollout_rate(bb, local):
         Xg, Fg, _ = sp.get_optimal_path(y0, n_steps=n_steps)
         dts.append(time.perf_counter() - t0)
     dt = float(np.median(dts))
+    t0 = time.perf_counter()
+    sp.get_optimal_path(y0, n_steps=n_steps, stride_out=n_steps)   # only the final states come back: the kernel alone
+    dt_last = time.perf_counter() - t0
     # a batch that fills the GPU (8 warps of 255 registers per SM): the same states, eight times over
     big = np.tile(y0, (8, 1))
     t0 = time.perf_counter()
@@ -376,7 +379,8 @@ def plant_rollout_rate(bb, local):
     same = np.all(Fg[:nb] == Fo, axis=(1, 2))
     ok = bool(same.mean() >= 0.95 and np.allclose(Xg[:nb][same], Xo[same], rtol=0, atol=1e-9))
     return {"x0": batch, "stages": n_steps, "ms": dt * 1e3, "trajectories_per_s": batch / dt,
-            "ode45_steps_per_s": batch * n_steps * 10 / dt, "trajectories_per_s_batch_32768": len(big) / dt_big,
+            "ode45_steps_per_s": batch * n_steps * 10 / dt, "ms_final_state_only": dt_last * 1e3,
+            "trajectories_per_s_batch_32768": len(big) / dt_big,
             "cpu_port_trajectories_per_s": nb / dt_cpu,
             "cpu_cores": cbind.num_threads(), "parity_vs_oracle": "pass" if ok else "FAIL",
             "call": "bellman_rollout_pos_att (host x0 in; X, thruster levels, forces/moments out; median of 3 calls)"}

@@ -529,7 +529,10 @@ __device__ double kepler_U(const OrbitTarget &tg, double dt) {
     return x;
 }
 
-__device__ void orbit_rates(const OrbitTarget &tg, const double (&acc)[3], double t, const double (&y)[6], double (&dydt)[6]) {
+// The part of the relative-motion equations that depends on t only (Solver_position.m:288-303 /
+// Solver_pos_att.m:713-733): the target propagated to t (update_RV_target) and the five coefficient
+// prefixes of the expressions below, in the reference's operation order.
+__device__ void target_coef(const OrbitTarget &tg, double t, double (&c)[5]) {
     // update_RV_target (:333-361)
     const double x = kepler_U(tg, t);
     const double z = tg.alpha * (x * x);
@@ -550,10 +553,22 @@ __device__ void orbit_rates(const OrbitTarget &tg, const double (&acc)[3], doubl
     const double H = pow((c0 * c0 + c1 * c1) + c2 * c2, .5);
     const double mu = tg.mu;
     const double nR2 = norm_R * norm_R, nR3 = pow(norm_R, 3.0), nR4 = pow(norm_R, 4.0), H2 = H * H;
+    c[0] = 2 * mu / nR3 + H2 / nR4;
+    c[1] = 2 * RdotV / nR4 * H;
+    c[2] = 2 * H / nR2;
+    c[3] = mu / nR3 - H2 / nR4;
+    c[4] = -mu / nR3;
+}
+__device__ __forceinline__ void relative_motion(const double (&c)[5], const double (&acc)[3], const double (&y)[6], double (&dydt)[6]) {
     dydt[0] = y[3]; dydt[1] = y[4]; dydt[2] = y[5];
-    dydt[3] = (2 * mu / nR3 + H2 / nR4) * y[0] - 2 * RdotV / nR4 * H * y[1] + 2 * H / nR2 * y[4] + acc[0];
-    dydt[4] = -(mu / nR3 - H2 / nR4) * y[1] + 2 * RdotV / nR4 * H * y[0] - 2 * H / nR2 * y[3] + acc[1];
-    dydt[5] = -mu / nR3 * y[2] + acc[2];
+    dydt[3] = c[0] * y[0] - c[1] * y[1] + c[2] * y[4] + acc[0];
+    dydt[4] = -c[3] * y[1] + c[1] * y[0] - c[2] * y[3] + acc[1];
+    dydt[5] = c[4] * y[2] + acc[2];
+}
+__device__ void orbit_rates(const OrbitTarget &tg, const double (&acc)[3], double t, const double (&y)[6], double (&dydt)[6]) {
+    double c[5];
+    target_coef(tg, t, c);
+    relative_motion(c, acc, y, dydt);
 }
 
 __device__ __forceinline__ double eps_of(double t) {   // MATLAB eps(t)
@@ -756,16 +771,42 @@ __device__ __forceinline__ void euler_wdot(const double *Im, const Chol3 &ch, co
     chol3_solve(ch, b, wd);
 }
 
+// Warp-cooperative target ephemeris.  The Kepler propagation of the target is by far the most expensive
+// part of a rate evaluation and depends on t only, and the lanes of a warp march in lock step as long
+// as ode45's step limit binds (MaxStep = (tf - t0)/10: always, for this plant).  So before each ode45 call
+// the warp predicts the 61 evaluation times of the call (f0, then six per step of ten steps) and its
+// lanes compute the coefficient sets of two times each, in parallel, into a shared table keyed by the
+// exact bits of t.  A rate evaluation looks its t up (cursor first, then a scan); a lane whose steps
+// leave the predicted sequence (a rejected step, another first step) simply misses and computes its own
+// coefficients.  Same function of the same t by the same instructions: results are bit-identical to
+// evaluating target_coef at every call.
+constexpr int EPH_SLOTS = 61;
 struct PosAttRhs {                         // Solver_pos_att.m:696-754
     static constexpr int NEQ = 13;
     OrbitTarget tg;
     double acc[3], UM[3], Im[9];
     Chol3 ch;
+    const double (*eph)[6];                // [EPH_SLOTS][t, c0..c4] in shared memory, or nullptr
+    mutable int cur;
     __device__ void operator()(double t, const double (&X)[13], double (&Xd)[13]) const {
-        double y6[6], d6[6];
+        double c[5], y6[6], d6[6];
+        int hit = -1;
+        if (eph) {
+            if (cur < EPH_SLOTS && eph[cur][0] == t) hit = cur;
+            else
+                for (int e = 0; e < EPH_SLOTS; ++e)
+                    if (eph[e][0] == t) { hit = e; break; }
+        }
+        if (hit >= 0) {
+#pragma unroll
+            for (int k = 0; k < 5; ++k) c[k] = eph[hit][1 + k];
+            cur = hit + 1;
+        } else {
+            target_coef(tg, t, c);
+        }
 #pragma unroll
         for (int k = 0; k < 6; ++k) y6[k] = X[k];
-        orbit_rates(tg, acc, t, y6, d6);
+        relative_motion(c, acc, y6, d6);
 #pragma unroll
         for (int k = 0; k < 6; ++k) Xd[k] = d6[k];
         const double q1 = X[6], q2 = X[7], q3 = X[8], q4 = X[9], w1 = X[10], w2 = X[11], w3 = X[12];
@@ -776,6 +817,27 @@ struct PosAttRhs {                         // Solver_pos_att.m:696-754
         euler_wdot(Im, ch, UM, &X[10], &Xd[10]);
     }
 };
+// evaluation time number e (0 = f0 at t0; 1 + 6 s + k = stage k of step s) of ode45 over [t0, tf] when
+// every step is accepted at the step limit; NaN beyond the last step
+__device__ double eph_time(double t0, double tf, int e) {
+    if (e == 0) return t0;
+    const double A[6] = {1. / 5, 3. / 10, 4. / 5, 8. / 9, 1, 1};
+    const double hmax = fabs(0.1 * (tf - t0));
+    const int s_want = (e - 1) / 6, k = (e - 1) % 6;
+    double t = t0;
+    for (int s = 0;; ++s) {
+        const double hmin = 16 * eps_of(t);
+        const double absh = fmin(hmax, fmax(hmin, hmax));
+        double h = absh;
+        bool done = false;
+        if (1.1 * absh >= fabs(tf - t)) { h = tf - t; done = true; }
+        double tnew = t + h * A[5];
+        if (done) tnew = tf;
+        if (s == s_want) return k < 5 ? t + h * A[k] : tnew;
+        if (done) return __longlong_as_double(0x7ff8000000000000LL);
+        t = tnew;
+    }
+}
 struct AttRhs {                            // Solver_attitude.m:1803-1849
     static constexpr int NEQ = 7;
     double U[3], Im[9];
@@ -909,7 +971,27 @@ __global__ void __launch_bounds__(32) k_rollout_pos_att(const __grid_constant__ 
 #pragma unroll
     for (int k = 0; k < 13; ++k) X[k] = y[k];
     int warns = 0;
+    __shared__ double eph[EPH_SLOTS][6];
+    const unsigned live = __activemask();                  // lanes of this (one-warp) CTA that own a trajectory
+    const int n_live = __popc(live), my_rank = __popc(live & ((1u << (threadIdx.x & 31)) - 1));
+    rhs.eph = eph;
     for (int ks = 1; ks <= pl.n_steps; ++ks) {
+        {   // the warp's ephemeris table for this stage's ode45 call
+            const double t0s = (double)(ks - 1) * pl.h, tfs = (double)ks * pl.h;
+            __syncwarp(live);
+            for (int e = my_rank; e < EPH_SLOTS; e += n_live) {
+                const double te = eph_time(t0s, tfs, e);
+                eph[e][0] = te;
+                if (te == te) {
+                    double c[5];
+                    target_coef(rhs.tg, te, c);
+#pragma unroll
+                    for (int k = 0; k < 5; ++k) eph[e][1 + k] = c[k];
+                }
+            }
+            __syncwarp(live);
+            rhs.cur = 0;
+        }
         double tq[3], M2[3][3], tmp[3], xb[3], vb[3], f[12];
 #pragma unroll
         for (int k = 0; k < 3; ++k) tq[k] = 2 * asin(y[6 + k]);            // :472-474
