@@ -352,6 +352,44 @@ int  bellman_rollout_attitude(bellman_handle *h, int32_t stage, const bellman_pl
                               const double *u_values, const double *y0, int32_t batch, double *X_out,
                               int32_t *C_out, int32_t *warn_out);
 
+/* The coupled 6-D attitude sweep — Solver_attitude.run (attitude-control/Solver_attitude.m:521-601): six
+ * state dimensions (w1 w2 w3 yaw pitch roll) and three controls with nu levels each.  The next state is
+ * not a sum of 1-D tables (Euler's equations couple the rates, the angle update goes through a
+ * quaternion: spacecraft_dynamics_taylor_estimate :825-925), so this path has its own descriptor and its
+ * own fused stage kernel instead of bellman_desc.  It replaces the nine-dimensional arrays the reference
+ * builds with repmat (:905-921) and calculate_J_U_opt_state_M (:767-823): J_current_state_fix +
+ * F(X1_next .. X6_next), then min over dim_U3, dim_U2, dim_U1.  The reference never ran this path (a
+ * one-argument method is called with two, :282 vs :384; the default mesh needs 2.7e13-element arrays):
+ * the semantics are the code as written with that call fixed, in fp64 — parity unpinned.
+ *
+ * Dense stage operator (normative arithmetic, restated by oracle_dense6_run).  S = prod n, dimension 0
+ * fastest, S3 = n0*n1*n2, s3 = the (w1, w2, w3) part of state s.  For every state s:
+ *   xq_d(u) = w_next[d][u*S3 + s3]  (d = 0..2, u = level of control d),   xq_{3+d} = a_next[d][s]
+ *   (cell, t) per dimension by the exact bin rule: cell = clamp(#{ i : grid[i] <= x } - 1, 0, n-2),
+ *              t = (x - grid[cell]) * rinv[cell],  rinv[i] = 1/(grid[i+1] - grid[i])
+ *   v   = 6-linear interpolation of J_{k+1}, dimension 0 reduced first, lerp(a,b,t) = fma(t, b - a, a),
+ *         linear extrapolation outside the grid
+ *   tot = (((gs[s] + r[0][u1]) + r[1][u2]) + r[2][u3]) + v
+ *   strict '<' over c = (u1*nu + u2)*nu + u3 in increasing order: the first minimiser, which is what the
+ *   three nested min calls of the reference select (U3 innermost).  J_k[s] = best, idx_k[s] = c. */
+typedef struct bellman_dense6_desc {
+    int32_t struct_size;          /* = sizeof(bellman_dense6_desc)                                   */
+    int32_t n[6];                 /* grid points of w1 w2 w3 yaw pitch roll (>= 2 each)              */
+    int32_t nu;                   /* levels of each of the three controls (1..8)                     */
+    int32_t device;               /* CUDA ordinal, -1 = current device                               */
+    const double *grid[6];        /* strictly increasing grid vectors                                */
+    const double *w_next[3];      /* [nu][S3] X{1,2,3}_next (:829-833)                               */
+    const double *a_next[3];      /* [S] X{4,5,6}_next: yaw, pitch, roll (:835-897)                  */
+    const double *gs;             /* [S] state part of J_current_state_fix (:629-640)                */
+    const double *r[3];           /* [nu] R_d * U_d^2                                                */
+} bellman_dense6_desc;
+/* Runs n_stages backward stages from J_N ([S], NULL = zeros: the reference's terminal cost) entirely on
+ * the device and returns the last stage computed: J_out [S], idx_out [S] (c as above, 0-based).  ms_out
+ * (may be NULL) receives the device time of the stage loop.  Stateless: every buffer is released before
+ * the call returns; errors are reported through bellman_last_error(NULL). */
+int  bellman_dense6_run(const bellman_dense6_desc *d, int32_t n_stages, const double *J_N, double *J_out,
+                        int32_t *idx_out, float *ms_out);
+
 #ifdef __cplusplus
 }
 #endif

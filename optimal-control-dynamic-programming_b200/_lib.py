@@ -57,6 +57,11 @@ class CPlantOpts(C.Structure):
                 ("mass", C.c_double), ("t_dist", C.c_double)]
 
 
+class CDense6(C.Structure):
+    _fields_ = [("struct_size", C.c_int32), ("n", C.c_int32 * 6), ("nu", C.c_int32), ("device", C.c_int32),
+                ("grid", _dp * 6), ("w_next", _dp * 3), ("a_next", _dp * 3), ("gs", _dp), ("r", _dp * 3)]
+
+
 class CSlab(C.Structure):
     _fields_ = [("own_lo", C.c_int32), ("own_hi", C.c_int32), ("ext_lo", C.c_int32), ("ext_hi", C.c_int32)]
 
@@ -69,7 +74,7 @@ EXPORTS = [
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
     "bellman_rollout_orbit", "bellman_get_points", "bellman_group_init", "bellman_group_run",
-    "bellman_rollout_pos_att", "bellman_rollout_attitude",
+    "bellman_rollout_pos_att", "bellman_rollout_attitude", "bellman_dense6_run",
 ]
 
 _lib = None
@@ -114,6 +119,7 @@ def load():
     lib.bellman_group_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
     lib.bellman_group_run.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.POINTER(CRunOpts)]
     lib.bellman_get_points.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, _dp, _ip]
+    lib.bellman_dense6_run.argtypes = [C.POINTER(CDense6), C.c_int32, _dp, _dp, _ip, C.POINTER(C.c_float)]
     lib.bellman_rollout_pos_att.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _ip, C.POINTER(CPlantOpts), _dp, _dp, _dp,
                                             _dp, C.c_int32, _dp, _dp, _dp, _ip]
     lib.bellman_rollout_attitude.argtypes = [C.c_void_p, C.c_int32, C.POINTER(CPlantOpts), _dp, _dp, C.c_int32, _dp, _ip, _ip]
@@ -427,6 +433,34 @@ class Sweep:
                                                       y0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp),
                                                       Cc.ctypes.data_as(_ip), W.ctypes.data_as(_ip)))
         return X, Cc, W
+
+
+def dense6_run(T, n_stages, J_N=None, device=-1):
+    """The coupled 6-D attitude sweep (Solver_attitude.run, Solver_attitude.m:521-601) on the tables of
+    tables.attitude6_tables, entirely on the GPU (bellman_dense6_run).  Returns (J [S], idx [S] 0-based
+    with idx = (u1*nu + u2)*nu + u3, device milliseconds of the stage loop)."""
+    lib = load()
+    keep = [_f64(g) for g in T.grid] + [_f64(w) for w in T.w_next] + [_f64(a) for a in T.a_next] + [_f64(x) for x in T.r]
+    cd = CDense6()
+    cd.struct_size, cd.nu, cd.device = C.sizeof(CDense6), int(T.nu), int(device)
+    for k in range(6):
+        cd.n[k] = int(T.n[k])
+        cd.grid[k] = keep[k].ctypes.data_as(_dp)
+    for k in range(3):
+        cd.w_next[k] = keep[6 + k].ctypes.data_as(_dp)
+        cd.a_next[k] = keep[9 + k].ctypes.data_as(_dp)
+        cd.r[k] = keep[12 + k].ctypes.data_as(_dp)
+    gs = _f64(T.gs)
+    cd.gs = gs.ctypes.data_as(_dp)
+    J = np.empty(T.S)
+    idx = np.empty(T.S, dtype=np.int32)
+    ms = C.c_float(0)
+    JN = None if J_N is None else _f64(J_N).ravel()
+    rc = lib.bellman_dense6_run(C.byref(cd), int(n_stages), _dp() if JN is None else JN.ctypes.data_as(_dp),
+                                J.ctypes.data_as(_dp), idx.ctypes.data_as(_ip), C.byref(ms))
+    if rc != 0:
+        raise BellmanError(rc, lib.bellman_last_error(None).decode())
+    return J, idx, float(ms.value)
 
 
 def _plant_opts(n_steps, stride_out, h_step, InertiaM, mu=0.0, R0=(0, 0, 0), V0=(0, 0, 0), rtol=1e-3, atol=1e-6,

@@ -20,6 +20,7 @@
 using namespace bellman;
 
 static thread_local std::string g_create_error;
+namespace bellman { void set_global_error(const std::string &msg) { g_create_error = msg; } }   // bellman_dense6.cu
 
 namespace bellman {
 bool raise_smem_limit(const void *fn, size_t bytes) {

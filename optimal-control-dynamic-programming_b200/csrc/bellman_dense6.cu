@@ -1,0 +1,249 @@
+// bellman_dense6.cu — the coupled 6-D attitude sweep, Solver_attitude.run
+// (attitude-control/Solver_attitude.m:521-601, calculate_J_U_opt_state_M :767-823): one fused stage kernel
+// that replaces the nine-dimensional arrays the reference builds with repmat (next states of every
+// (state, U1, U2, U3), J_current_state_fix + F(...), three nested min calls).
+//
+// Compiled with -fmad=false: one rounding per written operation; the only fused operations are the
+// explicit fma() calls of the lerps (include/bellman.h, "dense stage operator").
+//
+// Data layout in HBM (dimension 0 = w1 fastest, S = n0*n1*n2*n3*n4*n5, S3 = n0*n1*n2):
+//   J_next, J_out [S] fp64 (ping-pong), idx [S] int32
+//   a_next[3] [S]          next yaw / pitch / roll of every state (no control dependence)
+//   w_next[3] [nu][S3]     next w_d for level u of control d (no angle dependence: read through L1/L2)
+//   gs [S]                 state cost
+// Algorithmic HBM bytes per state and stage: 8 (J_next) + 24 (a_next) + 8 (gs) + 8 (J) + 4 (idx) = 52; the
+// 64-corner gathers and the w_next reads hit L1 / L2.  With nu^3 = 27 controls the stage is bound by the
+// fp64 pipe (about 60 lerps of 2 fp64 instructions per control after the sharing below), not by HBM.
+//
+// One thread per state.  The interpolation reduces dimension 0 first (w1, weight of U1), then 1 (w2, U2),
+// then 2 (w3, U3), then the angles.  The loops run U1, U2 outside and U3 inside, so for a fixed (U1, U2)
+// the reduction over dimensions 0 and 1 of one w3-node "plane" (8 values, one per angle corner) is shared
+// by every U3 whose cell touches that node: the two planes of the current w3 cell are kept in registers
+// and recomputed only when U3 moves to another cell.  Same operations in the same order as the
+// 64-corner evaluation — bit-identical to oracle_dense6_run.
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "bellman.h"
+#include "bellman_internal.h"
+
+namespace bellman {
+void set_global_error(const std::string &msg);   // bellman_api.cu: text behind bellman_last_error(NULL)
+
+namespace {
+
+constexpr int D6_BLOCK = 128;
+constexpr int D6_MAXU = 8;
+
+struct Dense6Params {
+    const double *grid[6], *rinv[6];
+    double inv_h[6];
+    int n[6];
+    long long stride[6];
+    long long S, S3;
+    int nu;
+    const double *w_next[3], *a_next[3], *gs, *r[3];
+    const double *J_next;
+    double *J_out;
+    int32_t *idx_out;
+};
+
+// exact bin rule cell = clamp(#{ s[i] <= x } - 1, 0, n-2): uniform guess, then a short scan either way
+__device__ __forceinline__ int locate6(const double *__restrict__ s, const double *__restrict__ rinv, int n, double inv_h,
+                                       double x, double &t) {
+    int cell = min(max(__double2int_rd((x - __ldg(s)) * inv_h), 0), n - 2);
+    while (cell < n - 2 && __ldg(s + cell + 1) <= x) ++cell;
+    while (cell > 0 && __ldg(s + cell) > x) --cell;
+    t = (x - __ldg(s + cell)) * __ldg(rinv + cell);
+    return cell;
+}
+
+__device__ __forceinline__ double lerp(double a, double b, double t) { return fma(t, b - a, a); }
+
+// dimensions 0 and 1 reduced at w3 node `node2`: one value per angle corner (bit m: +1 in dims 3, 4, 5)
+__device__ __forceinline__ void plane(const Dense6Params &p, const double *__restrict__ J, long long o01, long long oa,
+                                      int node2, double t0, double t1, double (&out)[8]) {
+    const long long base = o01 + (long long)node2 * p.stride[2] + oa;
+#pragma unroll
+    for (int m = 0; m < 8; ++m) {
+        const long long o = base + ((m & 1) ? p.stride[3] : 0) + ((m & 2) ? p.stride[4] : 0) + ((m & 4) ? p.stride[5] : 0);
+        const double v00 = __ldg(J + o), v10 = __ldg(J + o + 1);
+        const double v01 = __ldg(J + o + p.stride[1]), v11 = __ldg(J + o + p.stride[1] + 1);
+        out[m] = lerp(lerp(v00, v10, t0), lerp(v01, v11, t0), t1);
+    }
+}
+
+template <int NU>      // NU > 0: compile-time control count (unrolled); NU = 0: run-time p.nu <= D6_MAXU
+__global__ void __launch_bounds__(D6_BLOCK) k_stage_dense6(const __grid_constant__ Dense6Params p) {
+    const long long s = (long long)blockIdx.x * D6_BLOCK + threadIdx.x;
+    if (s >= p.S) return;
+    const int nu = NU > 0 ? NU : p.nu;
+    constexpr int MU = NU > 0 ? NU : D6_MAXU;
+    const long long s3 = s % p.S3;
+    int cw[3][MU], ca[3];
+    double tw[3][MU], ta[3];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+#pragma unroll
+        for (int u = 0; u < MU; ++u)
+            if (u < nu) cw[d][u] = locate6(p.grid[d], p.rinv[d], p.n[d], p.inv_h[d], __ldg(p.w_next[d] + (size_t)u * p.S3 + s3), tw[d][u]);
+        ca[d] = locate6(p.grid[3 + d], p.rinv[3 + d], p.n[3 + d], p.inv_h[3 + d], __ldg(p.a_next[d] + s), ta[d]);
+    }
+    const long long oa = ca[0] * p.stride[3] + ca[1] * p.stride[4] + ca[2] * p.stride[5];
+    const double gs = __ldg(p.gs + s);
+    const double *__restrict__ J = p.J_next;
+    double best = __longlong_as_double(0x7ff0000000000000LL);
+    int arg = 0;
+#pragma unroll
+    for (int u1 = 0; u1 < MU; ++u1) {
+        if (u1 >= nu) break;
+        const double g1 = gs + __ldg(p.r[0] + u1);
+#pragma unroll
+        for (int u2 = 0; u2 < MU; ++u2) {
+            if (u2 >= nu) break;
+            const double g2 = g1 + __ldg(p.r[1] + u2);
+            const long long o01 = cw[0][u1] + cw[1][u2] * p.stride[1];
+            const double t0 = tw[0][u1], t1 = tw[1][u2];
+            double lo[8], hi[8];
+            int have = -2;                                   // w3 cell whose two planes are in lo / hi
+#pragma unroll
+            for (int u3 = 0; u3 < MU; ++u3) {
+                if (u3 >= nu) break;
+                const int c2 = cw[2][u3];
+                if (c2 != have) {
+                    if (c2 == have + 1) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) lo[m] = hi[m];
+                    } else if (c2 == have - 1) {
+#pragma unroll
+                        for (int m = 0; m < 8; ++m) hi[m] = lo[m];
+                    }
+                    if (c2 != have + 1) plane(p, J, o01, oa, c2, t0, t1, lo);
+                    if (c2 != have - 1 || have < 0) plane(p, J, o01, oa, c2 + 1, t0, t1, hi);
+                    have = c2;
+                }
+                const double t2 = tw[2][u3];
+                double v[8];
+#pragma unroll
+                for (int m = 0; m < 8; ++m) v[m] = lerp(lo[m], hi[m], t2);          // dimension 2
+#pragma unroll
+                for (int m = 0; m < 4; ++m) v[m] = lerp(v[2 * m], v[2 * m + 1], ta[0]);   // yaw
+#pragma unroll
+                for (int m = 0; m < 2; ++m) v[m] = lerp(v[2 * m], v[2 * m + 1], ta[1]);   // pitch
+                const double val = lerp(v[0], v[1], ta[2]);                               // roll
+                const double tot = (g2 + __ldg(p.r[2] + u3)) + val;
+                if (tot < best) { best = tot; arg = (u1 * nu + u2) * nu + u3; }
+            }
+        }
+    }
+    p.J_out[s] = best;
+    p.idx_out[s] = arg;
+}
+
+struct DevBuf {
+    std::vector<void *> ptrs;
+    ~DevBuf() { for (void *q : ptrs) cudaFree(q); }
+    template <class T> cudaError_t alloc(T **out, size_t count) {
+        void *q = nullptr;
+        const cudaError_t e = cudaMalloc(&q, sizeof(T) * count);
+        if (e == cudaSuccess) ptrs.push_back(q);
+        *out = static_cast<T *>(q);
+        return e;
+    }
+};
+
+}  // namespace
+}  // namespace bellman
+
+using namespace bellman;
+
+extern "C" int bellman_dense6_run(const bellman_dense6_desc *d, int32_t n_stages, const double *J_N, double *J_out,
+                                  int32_t *idx_out, float *ms_out) {
+    auto fail = [](int code, const std::string &m) { set_global_error(m); return code; };
+    if (!d || !J_out || !idx_out) return fail(BELLMAN_ERR_BAD_ARG, "bellman_dense6_run: null argument");
+    if (d->struct_size != (int32_t)sizeof(bellman_dense6_desc)) return fail(BELLMAN_ERR_BAD_ARG, "bellman_dense6_desc.struct_size mismatch");
+    if (n_stages < 1) return fail(BELLMAN_ERR_BAD_ARG, "n_stages must be >= 1");
+    if (d->nu < 1 || d->nu > D6_MAXU) return fail(BELLMAN_ERR_BAD_ARG, "nu must be in 1..8");
+    Dense6Params p;
+    std::memset(&p, 0, sizeof(p));
+    long long S = 1;
+    for (int k = 0; k < 6; ++k) {
+        if (d->n[k] < 2 || !d->grid[k]) return fail(BELLMAN_ERR_BAD_ARG, "every dimension needs a grid of >= 2 points");
+        for (int i = 1; i < d->n[k]; ++i)
+            if (!(d->grid[k][i] > d->grid[k][i - 1])) return fail(BELLMAN_ERR_BAD_ARG, "grid must be strictly increasing");
+        p.n[k] = d->n[k];
+        p.stride[k] = S;
+        S *= d->n[k];
+    }
+    for (int k = 0; k < 3; ++k)
+        if (!d->w_next[k] || !d->a_next[k] || !d->r[k]) return fail(BELLMAN_ERR_BAD_ARG, "missing table");
+    if (!d->gs) return fail(BELLMAN_ERR_BAD_ARG, "missing table");
+    p.S = S;
+    p.S3 = (long long)d->n[0] * d->n[1] * d->n[2];
+    p.nu = d->nu;
+    int dev = d->device;
+    cudaError_t e = dev >= 0 ? cudaSetDevice(dev) : cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(BELLMAN_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    DevBuf buf;
+    cudaStream_t st = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    auto cleanup = [&]() { if (ev0) cudaEventDestroy(ev0); if (ev1) cudaEventDestroy(ev1); if (st) cudaStreamDestroy(st); };
+#define D6(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); \
+        return fail(_e == cudaErrorMemoryAllocation ? BELLMAN_ERR_OOM : BELLMAN_ERR_CUDA, cudaGetErrorString(_e)); } } while (0)
+    D6(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    D6(cudaEventCreate(&ev0));
+    D6(cudaEventCreate(&ev1));
+    for (int k = 0; k < 6; ++k) {
+        double *g = nullptr, *ri = nullptr;
+        std::vector<double> rinv((size_t)d->n[k] - 1);
+        for (int i = 0; i + 1 < d->n[k]; ++i) rinv[i] = 1.0 / (d->grid[k][i + 1] - d->grid[k][i]);
+        D6(buf.alloc(&g, (size_t)d->n[k]));
+        D6(buf.alloc(&ri, rinv.size()));
+        D6(cudaMemcpyAsync(g, d->grid[k], sizeof(double) * d->n[k], cudaMemcpyHostToDevice, st));
+        D6(cudaMemcpyAsync(ri, rinv.data(), sizeof(double) * rinv.size(), cudaMemcpyHostToDevice, st));
+        D6(cudaStreamSynchronize(st));               // rinv is a local
+        p.grid[k] = g; p.rinv[k] = ri;
+        p.inv_h[k] = (double)(d->n[k] - 1) / (d->grid[k][d->n[k] - 1] - d->grid[k][0]);
+    }
+    for (int k = 0; k < 3; ++k) {
+        double *w = nullptr, *a = nullptr, *r = nullptr;
+        D6(buf.alloc(&w, (size_t)d->nu * p.S3));
+        D6(buf.alloc(&a, (size_t)S));
+        D6(buf.alloc(&r, (size_t)d->nu));
+        D6(cudaMemcpyAsync(w, d->w_next[k], sizeof(double) * d->nu * p.S3, cudaMemcpyHostToDevice, st));
+        D6(cudaMemcpyAsync(a, d->a_next[k], sizeof(double) * S, cudaMemcpyHostToDevice, st));
+        D6(cudaMemcpyAsync(r, d->r[k], sizeof(double) * d->nu, cudaMemcpyHostToDevice, st));
+        p.w_next[k] = w; p.a_next[k] = a; p.r[k] = r;
+    }
+    double *gs = nullptr, *A = nullptr, *B = nullptr;
+    int32_t *idx = nullptr;
+    D6(buf.alloc(&gs, (size_t)S));
+    D6(buf.alloc(&A, (size_t)S));
+    D6(buf.alloc(&B, (size_t)S));
+    D6(buf.alloc(&idx, (size_t)S));
+    D6(cudaMemcpyAsync(gs, d->gs, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+    if (J_N) D6(cudaMemcpyAsync(A, J_N, sizeof(double) * S, cudaMemcpyHostToDevice, st));
+    else D6(cudaMemsetAsync(A, 0, sizeof(double) * S, st));
+    p.gs = gs; p.idx_out = idx;
+    const unsigned grid = (unsigned)((S + D6_BLOCK - 1) / D6_BLOCK);
+    D6(cudaEventRecord(ev0, st));
+    for (int k = 0; k < n_stages; ++k) {
+        p.J_next = A; p.J_out = B;
+        if (d->nu == 3) k_stage_dense6<3><<<grid, D6_BLOCK, 0, st>>>(p);
+        else k_stage_dense6<0><<<grid, D6_BLOCK, 0, st>>>(p);
+        D6(cudaGetLastError());
+        double *t = A; A = B; B = t;
+    }
+    D6(cudaEventRecord(ev1, st));
+    D6(cudaMemcpyAsync(J_out, A, sizeof(double) * S, cudaMemcpyDeviceToHost, st));
+    D6(cudaMemcpyAsync(idx_out, idx, sizeof(int32_t) * S, cudaMemcpyDeviceToHost, st));
+    D6(cudaStreamSynchronize(st));
+    if (ms_out) { float ms = 0; D6(cudaEventElapsedTime(&ms, ev0, ev1)); *ms_out = ms; }
+#undef D6
+    cleanup();
+    return BELLMAN_OK;
+}

@@ -34,10 +34,11 @@ compile bellman_window.cu -fmad=false
 compile bellman_kernels.cu -fmad=false
 compile bellman_tile.cu -fmad=false
 compile bellman_stream.cu -fmad=false
+compile bellman_dense6.cu -fmad=false
 compile bellman_api.cu
 compile bellman_plan.cpp -x cu
 for p in "${pids[@]:-}"; do [[ -n "$p" ]] && wait "$p"; done
 "$NVCC" $ARCH -shared -cudart static -o "$OUT" "$HERE"/build/bellman_kernels.o "$HERE"/build/bellman_window.o \
-    "$HERE"/build/bellman_tile.o "$HERE"/build/bellman_stream.o \
+    "$HERE"/build/bellman_tile.o "$HERE"/build/bellman_stream.o "$HERE"/build/bellman_dense6.o \
     "$HERE"/build/bellman_api.o "$HERE"/build/bellman_plan.o -ldl -lpthread -lrt
 echo "built $OUT"

@@ -348,6 +348,43 @@ class Solver_attitude(_AxisSolverBase):
         self.ode45_warnings = W
         return X, np.asarray(self.U_vector)[Cc]
 
+    # --- the coupled 6-D problem (Solver_attitude.m:521-601) --------------------------------------
+    def dense6_tables(self):
+        """reshape_states + calculate_J_current_state_fix_shaped + spacecraft_dynamics_taylor_estimate
+        (:1433-1485, :629-685, :825-925) on the mesh n_mesh_w^3 x n_mesh_q^3."""
+        self.N_stage = int(np.ceil(self.T_final / self.h))
+        sr = tables.linspace(self.w_min, self.w_max, self.n_mesh_w)
+        lim = ((self.yaw_min, self.yaw_max), (self.pitch_min, self.pitch_max), (self.roll_min, self.roll_max))
+        ang = [tables.linspace(tables.deg2rad(a), tables.deg2rad(b), self.n_mesh_q) for a, b in lim]
+        return tables.attitude6_tables((sr, sr, sr), ang[0], ang[1], ang[2], self.U_vector, self.J1, self.J2, self.J3,
+                                       (self.Q1, self.Q2, self.Q3, self.Q4, self.Q5, self.Q6), (self.R1, self.R2, self.R3),
+                                       self.h, self.N_stage)
+
+    def run(self, n_stages=None, max_bytes=64e9):
+        """Solver_attitude.run (:521-601): the coupled sweep over (w1 w2 w3 yaw pitch roll) with 27 control
+        combinations, on the GPU (bellman_dense6_run).  The reference never ran it (:282 calls a
+        one-argument method with two; its default n_mesh_w = 1000 needs 2.7e13-element arrays), so choose
+        n_mesh_w / n_mesh_q that fit: the tables take 9 doubles per state on the host.
+        Sets F_Values (J of the last stage computed, grid shaped), U1_Opt / U2_Opt / U3_Opt (the torque
+        VALUES chosen at every state, as :561-563 leave them) and U_idx6 (the three 1-based level indices)."""
+        from ._lib import dense6_run
+        S = float(self.n_mesh_w) ** 3 * float(self.n_mesh_q) ** 3
+        if S * 9 * 8 > max_bytes:
+            raise ValueError("the 6-D mesh %d^3 x %d^3 needs %.3g bytes of tables; lower n_mesh_w / n_mesh_q "
+                             "(the reference's default n_mesh_w = 1000 is infeasible, SURVEY 2.3)" % (self.n_mesh_w, self.n_mesh_q, S * 72))
+        T = self.dense6_tables()
+        todo = T.N - 1 if n_stages is None else int(n_stages)
+        J, idx, ms = dense6_run(T, todo, device=self.device)
+        shape = tuple(T.n)
+        nu = T.nu
+        u1, u2, u3 = idx // (nu * nu), (idx // nu) % nu, idx % nu
+        self.F_Values = _unflatten(J, shape)
+        self.U_idx6 = [_unflatten(u, shape) + 1 for u in (u1, u2, u3)]
+        U = np.asarray(self.U_vector)
+        self.U1_Opt, self.U2_Opt, self.U3_Opt = (U[k - 1] for k in self.U_idx6)
+        self.sweep_stats = {"ms": ms, "stages": todo, "kernel": "dense6"}
+        return self
+
     def _axis_descs(self):
         self.N_stage = int(np.ceil(self.T_final / self.h))
         ang = ((self.yaw_min, self.yaw_max), (self.pitch_min, self.pitch_max), (self.roll_min, self.roll_max))

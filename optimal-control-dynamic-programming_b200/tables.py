@@ -287,3 +287,78 @@ def pos_att_channel_desc(s_x, s_v, s_t, s_w, f0, f1, f6, f7, Qx, Qv, Qt, Qw, R, 
         meta={"class": "Solver_pos_att", "f0_allcomb": c0, "f1_allcomb": c1,
               "f6_allcomb": c6, "f7_allcomb": c7},
     ).validate()
+
+
+# ----------------------------------------------------------------------------------------------
+# Solver_attitude.run — the coupled 6-D problem (w1 w2 w3 yaw pitch roll) x 3 controls
+# ----------------------------------------------------------------------------------------------
+@dataclass
+class Dense6:
+    """Tables of the 6-D attitude sweep (attitude-control/Solver_attitude.m:521-601): the next state is
+    NOT a sum of 1-D tables (Euler's equations couple the three rates, the angle update goes through a
+    quaternion), so the next-state arrays the reference precomputes are kept — but only once each,
+    without the repmat over the dimensions they do not depend on:
+      w_next[d]  [nu, n0*n1*n2]   X{d}_next: depends on (w1, w2, w3) and on control d only   (:829-833)
+      a_next[d]  [S]              X{4,5,6}_next: depends on the state only                    (:835-897)
+      gs         [S]              state part of J_current_state_fix                           (:629-685)
+      r[d]       [nu]             R_d * U_d^2
+    S = prod(n), dimension 0 (w1) fastest."""
+    n: List[int]
+    nu: int
+    N: int
+    grid: List[np.ndarray]
+    w_next: List[np.ndarray]
+    a_next: List[np.ndarray]
+    gs: np.ndarray
+    r: List[np.ndarray]
+    U_vector: np.ndarray
+
+    @property
+    def S(self):
+        return int(np.prod(self.n))
+
+
+def attitude6_tables(sr, s_yaw, s_pitch, s_roll, U_vector, J1, J2, J3, Q, R, h, N):
+    """reshape_states (:1433-1485), calculate_J_current_state_fix_shaped (:629-685) and
+    spacecraft_dynamics_taylor_estimate (:825-925) with the reference's operation order, array at a time
+    (numpy broadcasting = MATLAB implicit expansion); sr = (sr_1, sr_2, sr_3), Q = (Q1..Q6), R = (R1, R2, R3)."""
+    f = lambda a: np.asarray(a, dtype=np.float64)
+    sr = [f(a) for a in sr]
+    s_yaw, s_pitch, s_roll, U = f(s_yaw), f(s_pitch), f(s_roll), f(U_vector)
+    X1V = sr[0].reshape(-1, 1, 1, 1, 1, 1)
+    X2V = sr[1].reshape(1, -1, 1, 1, 1, 1)
+    X3V = sr[2].reshape(1, 1, -1, 1, 1, 1)
+    c4, s4 = np.cos(s_yaw / 2).reshape(1, 1, 1, -1, 1, 1), np.sin(s_yaw / 2).reshape(1, 1, 1, -1, 1, 1)
+    c5, s5 = np.cos(s_pitch / 2).reshape(1, 1, 1, 1, -1, 1), np.sin(s_pitch / 2).reshape(1, 1, 1, 1, -1, 1)
+    c6, s6 = np.cos(s_roll / 2).reshape(1, 1, 1, 1, 1, -1), np.sin(s_roll / 2).reshape(1, 1, 1, 1, 1, -1)
+    qa = s4 * c5 * c6 - c4 * s5 * s6
+    qb = c4 * s5 * c6 + s4 * c5 * s6
+    qc = c4 * c5 * s6 - s4 * s5 * c6
+    Q1, Q2, Q3, Q4, Q5, Q6 = Q
+    n = [len(sr[0]), len(sr[1]), len(sr[2]), len(s_yaw), len(s_pitch), len(s_roll)]
+    gs = Q1 * X1V ** 2 + Q2 * X2V ** 2 + Q3 * X3V ** 2 + Q4 * qa ** 2 + Q5 * qb ** 2 + Q6 * qc ** 2       # :629-640
+    gs = np.broadcast_to(gs, n)
+    # :826-828
+    x7 = (1 - (qa ** 2 + qb ** 2 + qc ** 2)) ** 0.5
+    U1 = U.reshape(1, 1, 1, -1)
+    w3d = (X1V[..., 0, 0, 0], X2V[..., 0, 0, 0], X3V[..., 0, 0, 0])           # [n0,1,1], [1,n1,1], [1,1,n2]
+    Xa, Xb, Xc = (a[..., None] for a in w3d)
+    w_next = [np.broadcast_to(Xa + h * ((J2 - J3) / J1 * Xb * Xc + U1 / J1), n[:3] + [len(U)]),              # :829-833
+              np.broadcast_to(Xb + h * ((J3 - J1) / J2 * Xc * Xa + U1 / J2), n[:3] + [len(U)]),
+              np.broadcast_to(Xc + h * ((J1 - J2) / J3 * Xa * Xb + U1 / J3), n[:3] + [len(U)])]
+    X4n = qa + h * (0.5 * (X3V * qb - X2V * qc + X1V * x7))                                                   # :835-849
+    X5n = qb + h * (0.5 * (-X3V * qa + X1V * qc + X2V * x7))
+    X6n = qc + h * (0.5 * (X2V * qa - X1V * qb + X3V * x7))
+    x7n = x7 + h * (0.5 * (-X1V * qa - X2V * qb - X3V * qc))
+    Qs = np.sqrt(X4n ** 2 + X5n ** 2 + X6n ** 2 + x7n ** 2)                                                  # :865-873
+    X4n, X5n, X6n, x7n = X4n / Qs, X5n / Qs, X6n / Qs, x7n / Qs
+    yaw = np.arctan2(2. * (X6n * X5n + x7n * X4n), x7n ** 2 + X6n ** 2 - X5n ** 2 - X4n ** 2)                # :877-885
+    pitch = np.arcsin(-2. * (X6n * X4n - x7n * X5n))
+    roll = np.arctan2(2. * (X5n * X4n + x7n * X6n), x7n ** 2 - X6n ** 2 - X5n ** 2 + X4n ** 2)
+    flatF = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float64).ravel(order="F"))
+    R1, R2, R3 = R
+    return Dense6(
+        n=n, nu=len(U), N=int(N), grid=[sr[0], sr[1], sr[2], s_yaw, s_pitch, s_roll],
+        w_next=[np.ascontiguousarray(np.moveaxis(w, 3, 0).reshape(len(U), -1, order="F")) for w in w_next],
+        a_next=[flatF(yaw), flatF(pitch), flatF(roll)], gs=flatF(gs),
+        r=[f(R1 * U ** 2), f(R2 * U ** 2), f(R3 * U ** 2)], U_vector=U)

@@ -1025,3 +1025,66 @@ int oracle_rollout_attitude(const bellman_desc *d, const int32_t *modes, const i
         for (int k = 0; k < 2; ++k) free(g[p][k].rinv);
     return 0;
 }
+
+/* ==== the coupled 6-D attitude sweep ==========================================
+ * Solver_attitude.run (attitude-control/Solver_attitude.m:521-601) with calculate_J_U_opt_state_M
+ * (:767-823): F = griddedInterpolant({sr_1, sr_2, sr_3, s_yaw, s_pitch, s_roll}, ., 'linear') evaluated at
+ * the precomputed next states of every (state, U1, U2, U3), added to J_current_state_fix, then
+ * min over dim_U3, dim_U2, dim_U1 (nested minima = the first minimiser in the order U1 slowest, U3
+ * fastest).  The reference never ran this path (one-argument method called with two, :282 vs :384;
+ * 2.7e13-element arrays at the default mesh), so what is restated is the code as written, in fp64.
+ * Normative arithmetic of the dense stage operator (include/bellman.h, bellman_dense6_run):
+ *   per dimension the exact bin rule  cell = clamp(#{ s[i] <= x } - 1, 0, n-2),  t = (x - s[cell]) * rinv[cell]
+ *   v   = 6-linear interpolation, dimension 0 reduced first, lerp(a,b,t) = fma(t, b - a, a)
+ *   tot = (((gs + r1[u1]) + r2[u2]) + r3[u3]) + v        strict '<' in the order c = (u1*nu + u2)*nu + u3
+ * w_next[d] is [nu][n0*n1*n2], a_next[d] and gs are [S] (dimension 0 fastest), idx_out = c. */
+int oracle_dense6_run(const int32_t *n, int nu, const double *const *grid, const double *const *w_next,
+                      const double *const *a_next, const double *gs, const double *const *r, int n_stages,
+                      const double *J_N, double *J_out, int32_t *idx_out)
+{
+    int64_t S = 1, S3 = (int64_t)n[0] * n[1] * n[2], stride[6];
+    for (int k = 0; k < 6; ++k) { stride[k] = S; S *= n[k]; }
+    if (nu < 1 || nu > 8) return -1;
+    dimtab g[6];
+    for (int k = 0; k < 6; ++k) dimtab_init(&g[k], grid[k], n[k], BELLMAN_LOCATE_SEARCH);
+    double *A = (double *)malloc(sizeof(double) * (size_t)S), *B = (double *)malloc(sizeof(double) * (size_t)S);
+    if (J_N) memcpy(A, J_N, sizeof(double) * (size_t)S); else memset(A, 0, sizeof(double) * (size_t)S);
+    for (int st = 0; st < n_stages; ++st) {
+#pragma omp parallel for schedule(static)
+        for (int64_t s = 0; s < S; ++s) {
+            const int64_t s3 = s % S3;
+            int cw[3][8], ca[3];
+            double tw[3][8], ta[3];
+            for (int d = 0; d < 3; ++d) {
+                for (int u = 0; u < nu; ++u) cw[d][u] = locate(&g[d], w_next[d][(size_t)u * S3 + s3], &tw[d][u]);
+                ca[d] = locate(&g[3 + d], a_next[d][s], &ta[d]);
+            }
+            const int64_t oa = ca[0] * stride[3] + ca[1] * stride[4] + ca[2] * stride[5];
+            double best = INFINITY;
+            int arg = 0;
+            for (int u1 = 0; u1 < nu; ++u1)
+                for (int u2 = 0; u2 < nu; ++u2)
+                    for (int u3 = 0; u3 < nu; ++u3) {
+                        const int64_t o = oa + cw[0][u1] + cw[1][u2] * stride[1] + cw[2][u3] * stride[2];
+                        const double t[6] = {tw[0][u1], tw[1][u2], tw[2][u3], ta[0], ta[1], ta[2]};
+                        double v[64];
+                        for (int m = 0; m < 64; ++m) {
+                            int64_t oo = o;
+                            for (int d = 0; d < 6; ++d) if ((m >> d) & 1) oo += stride[d];
+                            v[m] = A[oo];
+                        }
+                        for (int d = 0, len = 32; d < 6; ++d, len >>= 1)
+                            for (int m = 0; m < len; ++m) v[m] = fma(t[d], v[2 * m + 1] - v[2 * m], v[2 * m]);
+                        const double tot = (((gs[s] + r[0][u1]) + r[1][u2]) + r[2][u3]) + v[0];
+                        if (tot < best) { best = tot; arg = (u1 * nu + u2) * nu + u3; }
+                    }
+            B[s] = best;
+            idx_out[s] = arg;
+        }
+        double *tmp = A; A = B; B = tmp;
+    }
+    memcpy(J_out, A, sizeof(double) * (size_t)S);
+    free(A); free(B);
+    for (int k = 0; k < 6; ++k) free(g[k].rinv);
+    return 0;
+}

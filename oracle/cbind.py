@@ -324,3 +324,24 @@ def rollout_attitude(d, idx, u_values, y0, n_steps, h, InertiaM, rtol=1e-3, atol
                                        X.ctypes.data_as(_dp), Cc.ctypes.data_as(ip), W.ctypes.data_as(ip))
     assert rc == 0
     return X, Cc, W
+
+
+def dense6_run(T, n_stages, J_N=None):
+    """The coupled 6-D attitude sweep (Solver_attitude.run) on the tables of tables.attitude6_tables.
+    Returns (J [S], idx [S]) of the last stage computed; idx = (u1*nu + u2)*nu + u3, 0-based."""
+    P6, P3 = _dp * 6, _dp * 3
+    keep = [_arr(g) for g in T.grid] + [_arr(w) for w in T.w_next] + [_arr(a) for a in T.a_next] + [_arr(x) for x in T.r]
+    grid = P6(*[a.ctypes.data_as(_dp) for a in keep[0:6]])
+    wn = P3(*[a.ctypes.data_as(_dp) for a in keep[6:9]])
+    an = P3(*[a.ctypes.data_as(_dp) for a in keep[9:12]])
+    rr = P3(*[a.ctypes.data_as(_dp) for a in keep[12:15]])
+    gs = _arr(T.gs)
+    n = np.asarray(T.n, dtype=np.int32)
+    J = np.zeros(T.S)
+    idx = np.zeros(T.S, dtype=np.int32)
+    JN = None if J_N is None else _arr(J_N).ravel()
+    rc = lib().oracle_dense6_run(n.ctypes.data_as(C.POINTER(C.c_int32)), C.c_int(T.nu), grid, wn, an, gs.ctypes.data_as(_dp), rr,
+                                 C.c_int(int(n_stages)), JN.ctypes.data_as(_dp) if JN is not None else _dp(),
+                                 J.ctypes.data_as(_dp), idx.ctypes.data_as(C.POINTER(C.c_int32)))
+    assert rc == 0
+    return J, idx

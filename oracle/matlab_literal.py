@@ -372,3 +372,84 @@ def simplified_axis_rollout_literal(s_a, s_b, U_opt_values, rate_dim, k_of_u, h,
         X[k + 1, r] = w_new
         X[k + 1, o] = t_new
     return X, U
+
+
+# --- Solver_attitude.run: the coupled 6-D sweep -------------------------------------------------
+class SolverAttitude6Literal:
+    """attitude-control/Solver_attitude.m:521-601 (run), :1433-1485 (reshape_states), :629-685
+    (calculate_J_current_state_fix_shaped), :825-925 (spacecraft_dynamics_taylor_estimate), :767-823
+    (calculate_J_U_opt_state_M), line by line with the full 9-D arrays (w1 w2 w3 yaw pitch roll U1 U2 U3)
+    the reference builds with repmat — usable at tiny meshes only.  The reference never ran this path
+    (run passes k_s to a one-argument method, :282 vs :384; the default mesh needs 2.7e13-element
+    arrays): what is restated is the code as written with that call fixed, fp64 instead of the single
+    interpolant values.  Parity unpinned."""
+
+    def __init__(self, n_mesh_w=4, n_mesh_q=3, h=0.005, N_stage=6, **kw):
+        self.w_min, self.w_max = -ml_deg2rad(50), -ml_deg2rad(-50)
+        self.n_mesh_w, self.n_mesh_q = n_mesh_w, n_mesh_q
+        self.yaw_min, self.yaw_max, self.pitch_min, self.pitch_max, self.roll_min, self.roll_max = -30, 30, -20, 20, -35, 35
+        self.J1, self.J2, self.J3 = 0.02836 + 0.00016, 0.026817 + 0.00150, 0.023 + 0.00150
+        self.Q1 = self.Q2 = self.Q3 = self.Q4 = self.Q5 = self.Q6 = 6
+        self.R1 = self.R2 = self.R3 = 4
+        self.h, self.N_stage = h, N_stage
+        self.U_vector = np.array([-0.11, 0, 0.11])
+        for k, v in kw.items():
+            setattr(self, k, v)
+        nw, nq = self.n_mesh_w, self.n_mesh_q
+        self.sr_1 = ml_linspace(self.w_min, self.w_max, nw)
+        self.sr_2 = ml_linspace(self.w_min, self.w_max, nw)
+        self.sr_3 = ml_linspace(self.w_min, self.w_max, nw)
+        self.s_yaw = ml_linspace(ml_deg2rad(self.yaw_min), ml_deg2rad(self.yaw_max), nq)
+        self.s_pitch = ml_linspace(ml_deg2rad(self.pitch_min), ml_deg2rad(self.pitch_max), nq)
+        self.s_roll = ml_linspace(ml_deg2rad(self.roll_min), ml_deg2rad(self.roll_max), nq)
+
+    def run(self, n_stages=None, J_N=None):
+        nw, nq, nu = self.n_mesh_w, self.n_mesh_q, len(self.U_vector)
+        sh = lambda v, ax: np.asarray(v, dtype=np.float64).reshape([-1 if k == ax else 1 for k in range(9)])
+        X1V, X2V, X3V = sh(self.sr_1, 0), sh(self.sr_2, 1), sh(self.sr_3, 2)                    # reshape_states
+        c4, s4 = sh(np.cos(self.s_yaw / 2), 3), sh(np.sin(self.s_yaw / 2), 3)
+        c5, s5 = sh(np.cos(self.s_pitch / 2), 4), sh(np.sin(self.s_pitch / 2), 4)
+        c6, s6 = sh(np.cos(self.s_roll / 2), 5), sh(np.sin(self.s_roll / 2), 5)
+        U1V, U2V, U3V = sh(self.U_vector, 6), sh(self.U_vector, 7), sh(self.U_vector, 8)
+        h, J1, J2, J3 = self.h, self.J1, self.J2, self.J3
+        J_fix = (self.Q1 * X1V ** 2 + self.Q2 * X2V ** 2 + self.Q3 * X3V ** 2 +                 # :629-685
+                 self.Q4 * (s4 * c5 * c6 - c4 * s5 * s6) ** 2 +
+                 self.Q5 * (c4 * s5 * c6 + s4 * c5 * s6) ** 2 +
+                 self.Q6 * (c4 * c5 * s6 - s4 * s5 * c6) ** 2 +
+                 self.R1 * U1V ** 2 + self.R2 * U2V ** 2 + self.R3 * U3V ** 2)
+        # spacecraft_dynamics_taylor_estimate :825-925
+        x7 = (1 - ((s4 * c5 * c6 - c4 * s5 * s6) ** 2 + (c4 * s5 * c6 + s4 * c5 * s6) ** 2 +
+                   (c4 * c5 * s6 - s4 * s5 * c6) ** 2)) ** 0.5
+        X1n = X1V + h * ((J2 - J3) / J1 * X2V * X3V + U1V / J1)
+        X2n = X2V + h * ((J3 - J1) / J2 * X3V * X1V + U2V / J2)
+        X3n = X3V + h * ((J1 - J2) / J3 * X1V * X2V + U3V / J3)
+        X4n = (s4 * c5 * c6 - c4 * s5 * s6) + h * (0.5 * (X3V * (c4 * s5 * c6 + s4 * c5 * s6)
+                                                          - X2V * (c4 * c5 * s6 - s4 * s5 * c6) + X1V * x7))
+        X5n = (c4 * s5 * c6 + s4 * c5 * s6) + h * (0.5 * (-X3V * (s4 * c5 * c6 - c4 * s5 * s6)
+                                                          + X1V * (c4 * c5 * s6 - s4 * s5 * c6) + X2V * x7))
+        X6n = (c4 * c5 * s6 - s4 * s5 * c6) + h * (0.5 * (X2V * (s4 * c5 * c6 - c4 * s5 * s6)
+                                                          - X1V * (c4 * s5 * c6 + s4 * c5 * s6) + X3V * x7))
+        x7 = x7 + h * (0.5 * (-X1V * (s4 * c5 * c6 - c4 * s5 * s6) - X2V * (c4 * s5 * c6 + s4 * c5 * s6)
+                              - X3V * (c4 * c5 * s6 - s4 * s5 * c6)))
+        Qs = np.sqrt(X4n ** 2 + X5n ** 2 + X6n ** 2 + x7 ** 2)
+        X4n, X5n, X6n, x7 = X4n / Qs, X5n / Qs, X6n / Qs, x7 / Qs
+        r1 = np.arctan2(2. * (X6n * X5n + x7 * X4n), x7 ** 2 + X6n ** 2 - X5n ** 2 - X4n ** 2)
+        r2 = np.arcsin(-2. * (X6n * X4n - x7 * X5n))
+        r3 = np.arctan2(2. * (X5n * X4n + x7 * X6n), x7 ** 2 - X6n ** 2 - X5n ** 2 + X4n ** 2)
+        full = (nw, nw, nw, nq, nq, nq, nu, nu, nu)
+        rep = lambda a: np.broadcast_to(a, full)                                               # the repmat calls :905-921
+        Xq = [rep(X1n), rep(X2n), rep(X3n), rep(r1), rep(r2), rep(r3)]
+        grids = [self.sr_1, self.sr_2, self.sr_3, self.s_yaw, self.s_pitch, self.s_roll]
+        F_values = np.zeros(full[:6]) if J_N is None else np.asarray(J_N, dtype=np.float64).reshape(full[:6], order="F")
+        todo = self.N_stage - 1 if n_stages is None else n_stages
+        for _ in range(todo):                                                                   # :549-555
+            F = GriddedInterpolantLinear(grids, F_values)
+            tot = J_fix + F(*Xq)
+            val, U3 = ml_min_last(tot)                                                          # min(.., [], dim_U3)
+            val, U2 = ml_min_last(val)                                                          # dim_U2
+            F_values, U1 = ml_min_last(val)                                                     # dim_U1
+        # intended composition of :557-559 (the reference indexes without the state subscripts)
+        U2s = np.take_along_axis(U2, (U1 - 1)[..., None], axis=-1)[..., 0]
+        U3s = np.take_along_axis(np.take_along_axis(U3, (U1 - 1)[..., None, None], axis=-2)[..., 0, :],
+                                 (U2s - 1)[..., None], axis=-1)[..., 0]
+        return F_values, U1, U2s, U3s
