@@ -386,6 +386,36 @@ def plant_rollout_rate(bb, local):
             "call": "bellman_rollout_pos_att (host x0 in; X, thruster levels, forces/moments out; median of 3 calls)"}
 
 
+def dense6_rate(bb, local):
+    """the coupled 6-D attitude sweep (Solver_attitude.run) on a 24^3 x 10^3 mesh with
+    27 control combinations, device time of the stage loop (bellman_dense6_run; tables built on the host
+    once, as the reference precomputes its next-state arrays), two stages on a smaller mesh from a rough
+    terminal cost checked bit for bit against the C restatement."""
+    from oracle import cbind
+    sa = bb.Solver_attitude()
+    sa.n_mesh_w, sa.n_mesh_q = 24, 10
+    sa.device = local
+    T = sa.dense6_tables()
+    stages = 10
+    bb.dense6_run(T, 2, device=local)                     # warm-up (module load, first-touch)
+    _, _, ms = bb.dense6_run(T, stages, device=local)
+    # parity and the CPU arm of this row on a 12^3 x 6^3 mesh (the C restatement needs ~1.2 us per update and core)
+    sa.n_mesh_w, sa.n_mesh_q = 12, 6
+    Ts = sa.dense6_tables()
+    JN = np.random.default_rng(0).normal(size=Ts.S)
+    Jg, Ig, _ = bb.dense6_run(Ts, 2, J_N=JN, device=local)
+    t0 = time.perf_counter()
+    Jo, Io = cbind.dense6_run(Ts, 2, J_N=JN)
+    dt_cpu = time.perf_counter() - t0
+    ok = bool(np.array_equal(Jg, Jo) and np.array_equal(Ig, Io))
+    upd = T.S * T.nu ** 3
+    return {"grid": list(T.n), "controls": T.nu ** 3, "states": T.S, "stages": stages, "ms_per_step": ms / stages,
+            "value": upd / (ms / stages * 1e-3), "unit": UNIT, "kernel": "dense6",
+            "hbm_frac": T.S * 52 / (ms / stages * 1e-3) / 1e9 / measured_peak_gbs()[0],
+            "cpu_port_updates_per_s": 2 * Ts.S * Ts.nu ** 3 / dt_cpu, "cpu_cores": cbind.num_threads(),
+            "parity_vs_oracle": "pass" if ok else "FAIL", "parity_sample": "2 stages on 12^3 x 6^3 from a rough terminal cost, bit-equal"}
+
+
 # ----------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -705,6 +735,7 @@ def main():
                 "traffic_source": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][1]}
         others["rollout_64x64_x0"] = rollout_rate(bb, local)
         others["pos_att_plant_rollout_4096_x0"] = plant_rollout_rate(bb, local)
+        others["attitude6_24x24x24x10x10x10x27"] = dense6_rate(bb, local)
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:

@@ -113,6 +113,61 @@ classdef Solver_attitude < handle
             fprintf('...Done!\n')
         end
 
+        function run(obj, n_stages)
+            % Solver_attitude.run of the reference (:521-601): the coupled sweep over (w1 w2 w3 yaw pitch
+            % roll) with 27 control combinations.  The next-state arrays are built here exactly as
+            % reshape_states / spacecraft_dynamics_taylor_estimate do (implicit expansion), but each only
+            % over the dimensions it depends on; the repmat to nine dimensions, J_current_state_fix + F(...)
+            % and the three nested min calls are one fused GPU stage (bellman_mex('dense6_run', ...)).
+            % The reference's default n_mesh_w = 1000 cannot be run anywhere (2.7e13-element arrays):
+            % set n_mesh_w / n_mesh_q to a mesh that fits (9 doubles per state on the host).
+            obj.N_stage = ceil(obj.T_final/obj.h);
+            if nargin < 2, n_stages = obj.N_stage - 1; end
+            nw = obj.n_mesh_w;  nq = obj.n_mesh_q;  U = obj.U_vector(:);  nu = numel(U);  hh = obj.h;
+            sr = linspace(obj.w_min, obj.w_max, nw);
+            s_yaw = linspace(deg2rad(obj.yaw_min), deg2rad(obj.yaw_max), nq);
+            s_pitch = linspace(deg2rad(obj.pitch_min), deg2rad(obj.pitch_max), nq);
+            s_roll = linspace(deg2rad(obj.roll_min), deg2rad(obj.roll_max), nq);
+            X1V = reshape(sr, [nw 1]);  X2V = reshape(sr, [1 nw]);  X3V = reshape(sr, [1 1 nw]);
+            c4 = reshape(cos(s_yaw/2), [1 1 1 nq]);      s4 = reshape(sin(s_yaw/2), [1 1 1 nq]);
+            c5 = reshape(cos(s_pitch/2), [1 1 1 1 nq]);  s5 = reshape(sin(s_pitch/2), [1 1 1 1 nq]);
+            c6 = reshape(cos(s_roll/2), [1 1 1 1 1 nq]); s6 = reshape(sin(s_roll/2), [1 1 1 1 1 nq]);
+            qa = s4.*c5.*c6 - c4.*s5.*s6;  qb = c4.*s5.*c6 + s4.*c5.*s6;  qc = c4.*c5.*s6 - s4.*s5.*c6;
+            full = [nw nw nw nq nq nq];
+            gs = obj.Q1*X1V.^2 + obj.Q2*X2V.^2 + obj.Q3*X3V.^2 + obj.Q4*qa.^2 + obj.Q5*qb.^2 + obj.Q6*qc.^2;
+            x7 = (1 - (qa.^2 + qb.^2 + qc.^2)).^0.5;
+            U1V = reshape(U, [1 1 1 nu]);
+            w1n = X1V + hh*((obj.J2-obj.J3)/obj.J1*X2V.*X3V + U1V/obj.J1);
+            w2n = X2V + hh*((obj.J3-obj.J1)/obj.J2*X3V.*X1V + U1V/obj.J2);
+            w3n = X3V + hh*((obj.J1-obj.J2)/obj.J3*X1V.*X2V + U1V/obj.J3);
+            X4n = qa + hh*(0.5*(X3V.*qb - X2V.*qc + X1V.*x7));
+            X5n = qb + hh*(0.5*(-X3V.*qa + X1V.*qc + X2V.*x7));
+            X6n = qc + hh*(0.5*(X2V.*qa - X1V.*qb + X3V.*x7));
+            x7 = x7 + hh*(0.5*(-X1V.*qa - X2V.*qb - X3V.*qc));
+            Qs = sqrt(X4n.^2 + X5n.^2 + X6n.^2 + x7.^2);
+            X4n = X4n./Qs;  X5n = X5n./Qs;  X6n = X6n./Qs;  x7 = x7./Qs;
+            yaw_n = atan2(2.*(X6n.*X5n + x7.*X4n), x7.^2 + X6n.^2 - X5n.^2 - X4n.^2);
+            pitch_n = asin(-2.*(X6n.*X4n - x7.*X5n));
+            roll_n = atan2(2.*(X5n.*X4n + x7.*X6n), x7.^2 - X6n.^2 - X5n.^2 + X4n.^2);
+            ex = @(a) reshape(a + zeros(full), [], 1);
+            d6 = struct('n', full, 'nu', nu, 'device', obj.device);
+            d6.grid = {sr(:), sr(:), sr(:), s_yaw(:), s_pitch(:), s_roll(:)};
+            d6.w_next = {reshape(w1n + zeros([nw nw nw nu]), [], nu), reshape(w2n + zeros([nw nw nw nu]), [], nu), ...
+                         reshape(w3n + zeros([nw nw nw nu]), [], nu)};
+            d6.a_next = {ex(yaw_n), ex(pitch_n), ex(roll_n)};
+            d6.gs = ex(gs);
+            d6.r = {obj.R1*U.^2, obj.R2*U.^2, obj.R3*U.^2};
+            tic
+            [J, id, ms] = bellman_mex('dense6_run', d6, n_stages, []);
+            fprintf('%d stages - %f seconds (device %.3f ms)\n', n_stages, toc, ms)
+            id = double(id) - 1;
+            obj.F_Values = reshape(J, full);
+            obj.U1_Opt = single(reshape(obj.U_vector(floor(id/(nu*nu)) + 1), full));     % :561-563
+            obj.U2_Opt = single(reshape(obj.U_vector(mod(floor(id/nu), nu) + 1), full));
+            obj.U3_Opt = single(reshape(obj.U_vector(mod(id, nu) + 1), full));
+            fprintf('...Done!\n')
+        end
+
         function [X_ode45, U_ode45] = get_optimal_path_simplified_testode45(obj, X0)
             % Solver_attitude.m:1669-1705 of the reference for every column of X0 (7 x batch: w1 w2 w3 q1 q2
             % q3 q4; default obj.defaultX0): U(k) = U{k}_Opt(X(k), 2*asin(X(3+k))), then ode45 over one

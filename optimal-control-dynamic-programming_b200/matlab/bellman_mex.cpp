@@ -24,6 +24,10 @@
 //                                                     X: 13 x ((n_out+1)*batch), F: 12 x (n_out*batch), FM: 6 x (n_out*batch)
 //   [X,id,w] = bellman_mex('rollout_attitude', h, stage, o, u_values, Y0)   Solver_attitude.get_optimal_path_simplified_testode45:
 //                                                     o: struct n_steps, stride_out, h, rtol, atol, InertiaM; Y0: 7 x batch
+//   [J,id,ms] = bellman_mex('dense6_run', d6, n_stages, J_N)   Solver_attitude.run (the coupled 6-D sweep):
+//                                                     d6: struct n (1x6), nu, device, grid {6}, w_next {3} (S3 x nu each),
+//                                                     a_next {3} (S x 1), gs (S x 1), r {3} (nu x 1); J_N [] = zeros;
+//                                                     J: S x 1, id (1-based, (u1-1)*nu^2 + (u2-1)*nu + u3): S x 1
 //            bellman_mex('destroy', h)
 //   v      = bellman_mex('version')
 //
@@ -239,6 +243,38 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
             for (bellman_handle *h : hs)
                 if (bellman_last_error(h)[0]) check(rc, h);
         check(rc, hs[0]);
+        return;
+    }
+    if (cmd == "dense6_run") {
+        if (nrhs < 3 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [J,id,ms] = bellman_mex('dense6_run', d6, n_stages, J_N)");
+        const mxArray *s = prhs[1];
+        bellman_dense6_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.struct_size = (int32_t)sizeof(d);
+        const double *nn = need_doubles(mxGetField(s, 0, "n"), 6, "d6.n");
+        size_t S = 1;
+        for (int k = 0; k < 6; ++k) { d.n[k] = (int32_t)nn[k]; S *= (size_t)d.n[k]; }
+        const size_t S3 = (size_t)d.n[0] * d.n[1] * d.n[2];
+        d.nu = (int32_t)field_scalar(s, "nu", 0);
+        d.device = (int32_t)field_scalar(s, "device", -1);
+        if (d.nu < 1 || d.nu > 8) mexErrMsgIdAndTxt("bellman:BAD_ARG", "d6.nu must be in 1..8");
+        for (int k = 0; k < 6; ++k) d.grid[k] = cell_table(s, "grid", k, (size_t)d.n[k], false);
+        for (int k = 0; k < 3; ++k) {
+            d.w_next[k] = cell_table(s, "w_next", k, S3 * (size_t)d.nu, false);
+            d.a_next[k] = cell_table(s, "a_next", k, S, false);
+            d.r[k] = cell_table(s, "r", k, (size_t)d.nu, false);
+        }
+        d.gs = need_doubles(mxGetField(s, 0, "gs"), S, "d6.gs");
+        const double *JN = (nrhs > 3 && !mxIsEmpty(prhs[3])) ? need_doubles(prhs[3], S, "J_N") : nullptr;
+        plhs[0] = mxCreateDoubleMatrix(S, 1, mxREAL);
+        mxArray *id = mxCreateNumericMatrix(S, 1, mxINT32_CLASS, mxREAL);
+        int32_t *pi = static_cast<int32_t *>(mxGetData(id));
+        float ms = 0;
+        const int rc = bellman_dense6_run(&d, (int32_t)mxGetScalar(prhs[2]), JN, mxGetPr(plhs[0]), pi, &ms);
+        if (rc != BELLMAN_OK) mexErrMsgIdAndTxt(code_name(rc), "%s", bellman_last_error(nullptr));
+        for (size_t k = 0; k < S; ++k) pi[k] += 1;
+        if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
+        if (nlhs > 2) plhs[2] = mxCreateDoubleScalar((double)ms);
         return;
     }
     if (cmd == "rollout_pos_att") {
