@@ -45,7 +45,7 @@ struct Dense6Params {
     int n[6];
     long long stride[6];
     long long S, S3;
-    int nu;
+    int nu, tiles0, tiles1;
     const double *w_next[3], *a_next[3], *gs, *r[3];
     const double *J_next;
     double *J_out;
@@ -77,13 +77,33 @@ __device__ __forceinline__ void plane(const Dense6Params &p, const double *__res
     }
 }
 
-template <int NU>      // NU > 0: compile-time control count (unrolled); NU = 0: run-time p.nu <= D6_MAXU
+// a[u] without dynamic register indexing for small arrays
+template <int MU, class T> __device__ __forceinline__ T pick(const T (&a)[MU], int u) {
+    if (MU <= 4) {
+        T v = a[0];
+#pragma unroll
+        for (int k = 1; k < MU; ++k) v = (u == k) ? a[k] : v;
+        return v;
+    }
+    return a[u];
+}
+
+// NU > 0: compile-time control count (unrolled U3 loop); NU = 0: run-time p.nu <= D6_MAXU.
+// (32-bit element offsets with the eight angle-corner offsets precomputed per state were measured: 5.4 ms
+// against 5.1 ms on the 24^3 x 10^3 mesh — no gain, the kernel waits on L1 / L2 latency, not on address arithmetic.)
+template <int NU>
 __global__ void __launch_bounds__(D6_BLOCK) k_stage_dense6(const __grid_constant__ Dense6Params p) {
-    const long long s = (long long)blockIdx.x * D6_BLOCK + threadIdx.x;
-    if (s >= p.S) return;
+    // a CTA is an 8 x 4 x 4 tile of (w1, w2, w3) at one angle triple (blockIdx.y = yaw + n3*pitch, blockIdx.z =
+    // roll): the threads of a tile gather from the same few w-neighbourhoods of 8 angle corners, so most of
+    // the 64-corner traffic is served by L1, and consecutive tiles (blockIdx.x) stay on one angle triple
+    const int i0 = (blockIdx.x % p.tiles0) * 8 + (threadIdx.x & 7);
+    const int i1 = ((blockIdx.x / p.tiles0) % p.tiles1) * 4 + ((threadIdx.x >> 3) & 3);
+    const int i2 = (blockIdx.x / (p.tiles0 * p.tiles1)) * 4 + (threadIdx.x >> 5);
+    if (i0 >= p.n[0] || i1 >= p.n[1] || i2 >= p.n[2]) return;
+    const long long s3 = i0 + (long long)p.n[0] * (i1 + (long long)p.n[1] * i2);
+    const long long s = s3 + p.S3 * (blockIdx.y + (long long)p.n[3] * p.n[4] * blockIdx.z);
     const int nu = NU > 0 ? NU : p.nu;
     constexpr int MU = NU > 0 ? NU : D6_MAXU;
-    const long long s3 = s % p.S3;
     int cw[3][MU], ca[3];
     double tw[3][MU], ta[3];
 #pragma unroll
@@ -98,16 +118,16 @@ __global__ void __launch_bounds__(D6_BLOCK) k_stage_dense6(const __grid_constant
     const double *__restrict__ J = p.J_next;
     double best = __longlong_as_double(0x7ff0000000000000LL);
     int arg = 0;
-#pragma unroll
-    for (int u1 = 0; u1 < MU; ++u1) {
-        if (u1 >= nu) break;
+    // U1 and U2 loops stay rolled: fully unrolled, the 27 combinations with their plane evaluations are
+    // 350 KB of code per kernel, far beyond the instruction caches
+#pragma unroll 1
+    for (int u1 = 0; u1 < nu; ++u1) {
         const double g1 = gs + __ldg(p.r[0] + u1);
-#pragma unroll
-        for (int u2 = 0; u2 < MU; ++u2) {
-            if (u2 >= nu) break;
+#pragma unroll 1
+        for (int u2 = 0; u2 < nu; ++u2) {
             const double g2 = g1 + __ldg(p.r[1] + u2);
-            const long long o01 = cw[0][u1] + cw[1][u2] * p.stride[1];
-            const double t0 = tw[0][u1], t1 = tw[1][u2];
+            const long long o01 = pick<MU>(cw[0], u1) + pick<MU>(cw[1], u2) * p.stride[1];
+            const double t0 = pick<MU>(tw[0], u1), t1 = pick<MU>(tw[1], u2);
             double lo[8], hi[8];
             int have = -2;                                   // w3 cell whose two planes are in lo / hi
 #pragma unroll
@@ -229,7 +249,10 @@ extern "C" int bellman_dense6_run(const bellman_dense6_desc *d, int32_t n_stages
     if (J_N) D6(cudaMemcpyAsync(A, J_N, sizeof(double) * S, cudaMemcpyHostToDevice, st));
     else D6(cudaMemsetAsync(A, 0, sizeof(double) * S, st));
     p.gs = gs; p.idx_out = idx;
-    const unsigned grid = (unsigned)((S + D6_BLOCK - 1) / D6_BLOCK);
+    p.tiles0 = (d->n[0] + 7) / 8;
+    p.tiles1 = (d->n[1] + 3) / 4;
+    if ((long long)d->n[3] * d->n[4] > 65535 || d->n[5] > 65535) { cleanup(); return fail(BELLMAN_ERR_BAD_ARG, "angle mesh too fine for the launch grid (n3*n4 and n5 must be <= 65535)"); }
+    const dim3 grid((unsigned)(p.tiles0 * p.tiles1 * ((d->n[2] + 3) / 4)), (unsigned)(d->n[3] * d->n[4]), (unsigned)d->n[5]);
     D6(cudaEventRecord(ev0, st));
     for (int k = 0; k < n_stages; ++k) {
         p.J_next = A; p.J_out = B;
