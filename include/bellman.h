@@ -390,6 +390,19 @@ typedef struct bellman_dense6_desc {
 int  bellman_dense6_run(const bellman_dense6_desc *d, int32_t n_stages, const double *J_N, double *J_out,
                         int32_t *idx_out, float *ms_out);
 
+/* Solver_attitude.get_optimal_path (attitude-control/Solver_attitude.m:1487-1530), the consumer of the 6-D
+ * policy, for a batch of initial states (one GPU thread each): per step
+ *   [yaw, pitch, roll] = quat2angle([X7 X6 X5 X4])      (Aerospace Toolbox, 'ZYX', input normalised)
+ *   U_k = FU_k(w1, w2, w3, yaw, pitch, roll)             'nearest' interpolants over U{1,2,3}_Opt (:1505-1519)
+ *   X   = next_stage_states(X, U, h, 'taylor')           X + h*f(X, U), quaternion renormalised (:1339-1371)
+ * d supplies n, nu, grid and device (its table pointers are not read); idx [S] is the policy of
+ * bellman_dense6_run (c = (u1*nu + u2)*nu + u3), u_values [nu], J123 = {J1, J2, J3} (the diagonal inertia
+ * spacecraft_dynamics_list uses, :1199-1245).  x0 [7][batch] = (w1 w2 w3 q1 q2 q3 q4), X_out
+ * [7][n_steps+1][batch], U_out [3][n_steps][batch].  An exact midpoint goes to the upper node. */
+int  bellman_rollout_attitude6(const bellman_dense6_desc *d, const int32_t *idx, const double *u_values,
+                               const double *J123, double h, int32_t n_steps, const double *x0, int32_t batch,
+                               double *X_out, double *U_out);
+
 #ifdef __cplusplus
 }
 #endif

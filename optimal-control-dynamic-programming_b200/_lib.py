@@ -74,7 +74,7 @@ EXPORTS = [
     "bellman_get_idx", "bellman_get_check_log", "bellman_owned_range", "bellman_last_run_stats",
     "bellman_last_kernel", "bellman_rollout", "bellman_policy_lookup", "bellman_rollout_axis",
     "bellman_rollout_orbit", "bellman_get_points", "bellman_group_init", "bellman_group_run",
-    "bellman_rollout_pos_att", "bellman_rollout_attitude", "bellman_dense6_run",
+    "bellman_rollout_pos_att", "bellman_rollout_attitude", "bellman_dense6_run", "bellman_rollout_attitude6",
 ]
 
 _lib = None
@@ -119,6 +119,7 @@ def load():
     lib.bellman_group_init.argtypes = [C.POINTER(C.c_void_p), C.c_int32]
     lib.bellman_group_run.argtypes = [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.POINTER(CRunOpts)]
     lib.bellman_get_points.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.POINTER(C.c_int64), C.c_int64, _dp, _ip]
+    lib.bellman_rollout_attitude6.argtypes = [C.POINTER(CDense6), _ip, _dp, _dp, C.c_double, C.c_int32, _dp, C.c_int32, _dp, _dp]
     lib.bellman_dense6_run.argtypes = [C.POINTER(CDense6), C.c_int32, _dp, _dp, _ip, C.POINTER(C.c_float)]
     lib.bellman_rollout_pos_att.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _ip, C.POINTER(CPlantOpts), _dp, _dp, _dp,
                                             _dp, C.c_int32, _dp, _dp, _dp, _ip]
@@ -461,6 +462,30 @@ def dense6_run(T, n_stages, J_N=None, device=-1):
     if rc != 0:
         raise BellmanError(rc, lib.bellman_last_error(None).decode())
     return J, idx, float(ms.value)
+
+
+def rollout_attitude6(T, idx, J123, h, n_steps, x0, device=-1):
+    """Solver_attitude.get_optimal_path (Solver_attitude.m:1487-1530) under the 6-D policy idx [S] for a batch
+    x0 [batch, 7] on the GPU (bellman_rollout_attitude6).  Returns X [batch, n_steps+1, 7], U [batch, n_steps, 3]."""
+    lib = load()
+    keep = [_f64(g) for g in T.grid]
+    cd = CDense6()
+    cd.struct_size, cd.nu, cd.device = C.sizeof(CDense6), int(T.nu), int(device)
+    for k in range(6):
+        cd.n[k] = int(T.n[k])
+        cd.grid[k] = keep[k].ctypes.data_as(_dp)
+    ia = np.ascontiguousarray(idx, dtype=np.int32).ravel()
+    uv, jd = _f64(T.U_vector), _f64(J123)
+    x0 = _f64(x0).reshape(-1, 7)
+    batch = len(x0)
+    X = np.empty((batch, int(n_steps) + 1, 7))
+    U = np.empty((batch, int(n_steps), 3))
+    rc = lib.bellman_rollout_attitude6(C.byref(cd), ia.ctypes.data_as(_ip), uv.ctypes.data_as(_dp), jd.ctypes.data_as(_dp),
+                                       float(h), int(n_steps), x0.ctypes.data_as(_dp), batch, X.ctypes.data_as(_dp),
+                                       U.ctypes.data_as(_dp))
+    if rc != 0:
+        raise BellmanError(rc, lib.bellman_last_error(None).decode())
+    return X, U
 
 
 def _plant_opts(n_steps, stride_out, h_step, InertiaM, mu=0.0, R0=(0, 0, 0), V0=(0, 0, 0), rtol=1e-3, atol=1e-6,

@@ -164,6 +164,73 @@ __global__ void __launch_bounds__(D6_BLOCK) k_stage_dense6(const __grid_constant
     p.idx_out[s] = arg;
 }
 
+// Solver_attitude.get_optimal_path (attitude-control/Solver_attitude.m:1487-1530), the consumer of the 6-D
+// policy: one thread per initial state.  Per step quat2angle([X7 X6 X5 X4]) (input normalised), the
+// 'nearest' node of (w1 w2 w3 yaw pitch roll), the three torque levels stored there, then
+// next_stage_states(.., 'taylor') (:1339-1371).  atan2 / asin are CUDA's: parity with the oracle is a tolerance.
+struct Roll6Params {
+    const double *grid[6];
+    int n[6];
+    long long stride[6];
+    int nu, n_steps, batch;
+    const int32_t *idx;
+    const double *u_values, *x0;
+    double J1, J2, J3, h;
+    double *X_out, *U_out;
+};
+__device__ __forceinline__ int nearest6(const double *__restrict__ s, int n, double x) {
+    int lo = 0, hi = n;                                   // count of s[i] <= x
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (__ldg(s + mid) <= x) lo = mid + 1; else hi = mid;
+    }
+    const int cell = min(max(lo - 1, 0), n - 2);
+    return cell + ((x - __ldg(s + cell)) >= (__ldg(s + cell + 1) - x) ? 1 : 0);    // exact midpoint -> upper node
+}
+__global__ void __launch_bounds__(64) k_rollout_attitude6(const __grid_constant__ Roll6Params p) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= p.batch) return;
+    double X[7];
+#pragma unroll
+    for (int k = 0; k < 7; ++k) X[k] = p.x0[(size_t)b * 7 + k];
+    double *Xo = p.X_out + (size_t)b * 7 * (p.n_steps + 1), *Uo = p.U_out + (size_t)b * 3 * p.n_steps;
+#pragma unroll
+    for (int k = 0; k < 7; ++k) Xo[k] = X[k];
+    const double J1 = p.J1, J2 = p.J2, J3 = p.J3, h = p.h;
+    const int nu = p.nu;
+    for (int ks = 0; ks < p.n_steps; ++ks) {
+        const double qm = sqrt(((X[6] * X[6] + X[5] * X[5]) + X[4] * X[4]) + X[3] * X[3]);
+        const double q0 = X[6] / qm, q1 = X[5] / qm, q2 = X[4] / qm, q3 = X[3] / qm;
+        const double xq[6] = {X[0], X[1], X[2],
+                              atan2(2 * (q1 * q2 + q0 * q3), ((q0 * q0 + q1 * q1) - q2 * q2) - q3 * q3),
+                              asin(-2 * (q1 * q3 - q0 * q2)),
+                              atan2(2 * (q2 * q3 + q0 * q1), ((q0 * q0 - q1 * q1) - q2 * q2) + q3 * q3)};
+        long long o = 0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) o += nearest6(p.grid[k], p.n[k], xq[k]) * p.stride[k];
+        const int c = __ldg(p.idx + o);
+        const double U[3] = {__ldg(p.u_values + c / (nu * nu)), __ldg(p.u_values + (c / nu) % nu), __ldg(p.u_values + c % nu)};
+#pragma unroll
+        for (int k = 0; k < 3; ++k) Uo[(size_t)ks * 3 + k] = U[k];
+        const double x1 = X[0], x2 = X[1], x3 = X[2], x4 = X[3], x5 = X[4], x6 = X[5], x7 = X[6];
+        double d[7];
+        d[0] = (J2 - J3) / J1 * x2 * x3 + U[0] / J1;
+        d[1] = (J3 - J1) / J2 * x3 * x1 + U[1] / J2;
+        d[2] = (J1 - J2) / J3 * x1 * x2 + U[2] / J3;
+        d[3] = 0.5 * ((x3 * x5 - x2 * x6) + x1 * x7);
+        d[4] = 0.5 * ((-x3 * x4 + x1 * x6) + x2 * x7);
+        d[5] = 0.5 * ((x2 * x4 - x1 * x5) + x3 * x7);
+        d[6] = 0.5 * ((-x1 * x4 - x2 * x5) - x3 * x6);
+#pragma unroll
+        for (int k = 0; k < 7; ++k) X[k] = X[k] + h * d[k];
+        const double qs = sqrt(((X[3] * X[3] + X[4] * X[4]) + X[5] * X[5]) + X[6] * X[6]);
+#pragma unroll
+        for (int k = 3; k < 7; ++k) X[k] = X[k] / qs;
+#pragma unroll
+        for (int k = 0; k < 7; ++k) Xo[(size_t)(ks + 1) * 7 + k] = X[k];
+    }
+}
+
 struct DevBuf {
     std::vector<void *> ptrs;
     ~DevBuf() { for (void *q : ptrs) cudaFree(q); }
@@ -267,6 +334,65 @@ extern "C" int bellman_dense6_run(const bellman_dense6_desc *d, int32_t n_stages
     D6(cudaStreamSynchronize(st));
     if (ms_out) { float ms = 0; D6(cudaEventElapsedTime(&ms, ev0, ev1)); *ms_out = ms; }
 #undef D6
+    cleanup();
+    return BELLMAN_OK;
+}
+
+extern "C" int bellman_rollout_attitude6(const bellman_dense6_desc *d, const int32_t *idx, const double *u_values,
+                                         const double *J123, double h, int32_t n_steps, const double *x0, int32_t batch,
+                                         double *X_out, double *U_out) {
+    auto fail = [](int code, const std::string &m) { set_global_error(m); return code; };
+    if (!d || !idx || !u_values || !J123 || !x0 || !X_out || !U_out || batch < 1 || n_steps < 1)
+        return fail(BELLMAN_ERR_BAD_ARG, "bellman_rollout_attitude6: null or non-positive argument");
+    if (d->struct_size != (int32_t)sizeof(bellman_dense6_desc)) return fail(BELLMAN_ERR_BAD_ARG, "bellman_dense6_desc.struct_size mismatch");
+    if (d->nu < 1 || d->nu > D6_MAXU) return fail(BELLMAN_ERR_BAD_ARG, "nu must be in 1..8");
+    if (!(J123[0] > 0 && J123[1] > 0 && J123[2] > 0) || !(h > 0)) return fail(BELLMAN_ERR_BAD_ARG, "J1, J2, J3 and h must be positive");
+    Roll6Params p;
+    std::memset(&p, 0, sizeof(p));
+    long long S = 1;
+    for (int k = 0; k < 6; ++k) {
+        if (d->n[k] < 2 || !d->grid[k]) return fail(BELLMAN_ERR_BAD_ARG, "every dimension needs a grid of >= 2 points");
+        p.n[k] = d->n[k];
+        p.stride[k] = S;
+        S *= d->n[k];
+    }
+    const int C = d->nu * d->nu * d->nu;
+    for (long long i = 0; i < S; ++i)
+        if (idx[i] < 0 || idx[i] >= C) return fail(BELLMAN_ERR_BAD_ARG, "policy index out of range");
+    int dev = d->device;
+    cudaError_t e = dev >= 0 ? cudaSetDevice(dev) : cudaGetDevice(&dev);
+    if (e != cudaSuccess) return fail(BELLMAN_ERR_CUDA, std::string("no usable CUDA device (there is no CPU fallback): ") + cudaGetErrorString(e));
+    DevBuf buf;
+    cudaStream_t st = nullptr;
+    auto cleanup = [&]() { if (st) cudaStreamDestroy(st); };
+#define R6(expr) do { cudaError_t _e = (expr); if (_e != cudaSuccess) { cleanup(); \
+        return fail(_e == cudaErrorMemoryAllocation ? BELLMAN_ERR_OOM : BELLMAN_ERR_CUDA, cudaGetErrorString(_e)); } } while (0)
+    R6(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    for (int k = 0; k < 6; ++k) {
+        double *g = nullptr;
+        R6(buf.alloc(&g, (size_t)d->n[k]));
+        R6(cudaMemcpyAsync(g, d->grid[k], sizeof(double) * d->n[k], cudaMemcpyHostToDevice, st));
+        p.grid[k] = g;
+    }
+    int32_t *d_idx = nullptr;
+    double *d_u = nullptr, *d_x0 = nullptr, *d_X = nullptr, *d_U = nullptr;
+    R6(buf.alloc(&d_idx, (size_t)S));
+    R6(buf.alloc(&d_u, (size_t)d->nu));
+    R6(buf.alloc(&d_x0, 7 * (size_t)batch));
+    R6(buf.alloc(&d_X, 7 * (size_t)(n_steps + 1) * batch));
+    R6(buf.alloc(&d_U, 3 * (size_t)n_steps * batch));
+    R6(cudaMemcpyAsync(d_idx, idx, sizeof(int32_t) * S, cudaMemcpyHostToDevice, st));
+    R6(cudaMemcpyAsync(d_u, u_values, sizeof(double) * d->nu, cudaMemcpyHostToDevice, st));
+    R6(cudaMemcpyAsync(d_x0, x0, sizeof(double) * 7 * batch, cudaMemcpyHostToDevice, st));
+    p.nu = d->nu; p.n_steps = n_steps; p.batch = batch;
+    p.idx = d_idx; p.u_values = d_u; p.x0 = d_x0; p.X_out = d_X; p.U_out = d_U;
+    p.J1 = J123[0]; p.J2 = J123[1]; p.J3 = J123[2]; p.h = h;
+    k_rollout_attitude6<<<(batch + 63) / 64, 64, 0, st>>>(p);
+    R6(cudaGetLastError());
+    R6(cudaMemcpyAsync(X_out, d_X, sizeof(double) * 7 * (size_t)(n_steps + 1) * batch, cudaMemcpyDeviceToHost, st));
+    R6(cudaMemcpyAsync(U_out, d_U, sizeof(double) * 3 * (size_t)n_steps * batch, cudaMemcpyDeviceToHost, st));
+    R6(cudaStreamSynchronize(st));
+#undef R6
     cleanup();
     return BELLMAN_OK;
 }

@@ -44,6 +44,7 @@ classdef Solver_attitude < handle
         U_idx
         device = -1
         last_desc_      % descriptor of the last simplified_run (for the forward simulation)
+        policy6_        % grids and policy of the last run() (for get_optimal_path)
         defaultX0
         n_gpus = 1      % > 1: the grid is cut into slabs over this many GPUs, driven from this one process
     end
@@ -160,12 +161,29 @@ classdef Solver_attitude < handle
             tic
             [J, id, ms] = bellman_mex('dense6_run', d6, n_stages, []);
             fprintf('%d stages - %f seconds (device %.3f ms)\n', n_stages, toc, ms)
+            obj.policy6_ = struct('d6', rmfield(d6, {'w_next', 'a_next', 'gs', 'r'}), 'id', id);   % for get_optimal_path
             id = double(id) - 1;
             obj.F_Values = reshape(J, full);
             obj.U1_Opt = single(reshape(obj.U_vector(floor(id/(nu*nu)) + 1), full));     % :561-563
             obj.U2_Opt = single(reshape(obj.U_vector(mod(floor(id/nu), nu) + 1), full));
             obj.U3_Opt = single(reshape(obj.U_vector(mod(id, nu) + 1), full));
             fprintf('...Done!\n')
+        end
+
+        function [X, U] = get_optimal_path(obj, X0)
+            % Solver_attitude.get_optimal_path of the reference (:1487-1530) with method 'nearest': the 6-D
+            % policy of run(), quat2angle per step, first-order ('taylor') plant step; every column of X0
+            % (7 x batch, default obj.defaultX0) is one GPU thread.  X: 7 x N x batch, U: 3 x (N-1) x batch.
+            if nargin < 2, X0 = obj.defaultX0; end
+            if isempty(obj.policy6_), error('run(obj) must complete before get_optimal_path'); end
+            N = obj.N_stage;
+            [Xf, Uf] = bellman_mex('rollout_attitude6', obj.policy6_.d6, obj.policy6_.id, obj.U_vector(:), ...
+                [obj.J1 obj.J2 obj.J3], obj.h, N - 1, X0);
+            batch = size(X0, 2);
+            X = reshape(Xf, 7, N, batch);  U = reshape(Uf, 3, N - 1, batch);
+            v_plot = 0:obj.h:obj.T_final-obj.h;
+            figure; hold on; grid on; plot(v_plot(1:N-1), U(:,:,1).', '--'); legend('u1','u2','u3'); xlabel('time (s)')
+            figure; hold on; grid on; plot(v_plot(1:N), X(1:3,:,1).'); legend('w1','w2','w3')
         end
 
         function [X_ode45, U_ode45] = get_optimal_path_simplified_testode45(obj, X0)

@@ -28,6 +28,10 @@
 //                                                     d6: struct n (1x6), nu, device, grid {6}, w_next {3} (S3 x nu each),
 //                                                     a_next {3} (S x 1), gs (S x 1), r {3} (nu x 1); J_N [] = zeros;
 //                                                     J: S x 1, id (1-based, (u1-1)*nu^2 + (u2-1)*nu + u3): S x 1
+//   [X,U]  = bellman_mex('rollout_attitude6', d6, id, u_values, J123, h, n_steps, X0)   Solver_attitude.get_optimal_path
+//                                                     under the 6-D policy id (S x 1, 1-based as 'dense6_run' returns it);
+//                                                     d6 needs n, nu, grid, device; X0: 7 x batch; X: 7 x ((n_steps+1)*batch),
+//                                                     U: 3 x (n_steps*batch)
 //            bellman_mex('destroy', h)
 //   v      = bellman_mex('version')
 //
@@ -275,6 +279,36 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
         for (size_t k = 0; k < S; ++k) pi[k] += 1;
         if (nlhs > 1) plhs[1] = id; else mxDestroyArray(id);
         if (nlhs > 2) plhs[2] = mxCreateDoubleScalar((double)ms);
+        return;
+    }
+    if (cmd == "rollout_attitude6") {
+        if (nrhs < 8 || !mxIsStruct(prhs[1])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "usage: [X,U] = bellman_mex('rollout_attitude6', d6, id, u_values, J123, h, n_steps, X0)");
+        const mxArray *s = prhs[1];
+        bellman_dense6_desc d;
+        std::memset(&d, 0, sizeof(d));
+        d.struct_size = (int32_t)sizeof(d);
+        const double *nn = need_doubles(mxGetField(s, 0, "n"), 6, "d6.n");
+        size_t S = 1;
+        for (int k = 0; k < 6; ++k) { d.n[k] = (int32_t)nn[k]; S *= (size_t)d.n[k]; }
+        d.nu = (int32_t)field_scalar(s, "nu", 0);
+        d.device = (int32_t)field_scalar(s, "device", -1);
+        if (d.nu < 1 || d.nu > 8) mexErrMsgIdAndTxt("bellman:BAD_ARG", "d6.nu must be in 1..8");
+        for (int k = 0; k < 6; ++k) d.grid[k] = cell_table(s, "grid", k, (size_t)d.n[k], false);
+        if (!mxIsClass(prhs[2], "int32") || mxGetNumberOfElements(prhs[2]) != S) mexErrMsgIdAndTxt("bellman:BAD_ARG", "id must be the int32 S-by-1 policy 'dense6_run' returns");
+        std::vector<int32_t> idx(S);
+        const int32_t *id1 = static_cast<const int32_t *>(mxGetData(prhs[2]));
+        for (size_t k = 0; k < S; ++k) idx[k] = id1[k] - 1;
+        const double *uv = need_doubles(prhs[3], (size_t)d.nu, "u_values"), *J123 = need_doubles(prhs[4], 3, "J123");
+        const int32_t n_steps = (int32_t)mxGetScalar(prhs[6]);
+        if (n_steps < 1) mexErrMsgIdAndTxt("bellman:BAD_ARG", "n_steps must be >= 1");
+        const size_t batch = mxGetN(prhs[7]);
+        need_doubles(prhs[7], 7 * batch, "X0 (7-by-batch)");
+        plhs[0] = mxCreateDoubleMatrix(7, (size_t)(n_steps + 1) * batch, mxREAL);
+        mxArray *U = mxCreateDoubleMatrix(3, (size_t)n_steps * batch, mxREAL);
+        const int rc = bellman_rollout_attitude6(&d, idx.data(), uv, J123, mxGetScalar(prhs[5]), n_steps, mxGetPr(prhs[7]),
+                                                 (int32_t)batch, mxGetPr(plhs[0]), mxGetPr(U));
+        if (rc != BELLMAN_OK) mexErrMsgIdAndTxt(code_name(rc), "%s", bellman_last_error(nullptr));
+        if (nlhs > 1) plhs[1] = U; else mxDestroyArray(U);
         return;
     }
     if (cmd == "rollout_pos_att") {

@@ -383,7 +383,20 @@ class Solver_attitude(_AxisSolverBase):
         U = np.asarray(self.U_vector)
         self.U1_Opt, self.U2_Opt, self.U3_Opt = (U[k - 1] for k in self.U_idx6)
         self.sweep_stats = {"ms": ms, "stages": todo, "kernel": "dense6"}
+        self._dense6 = (T, idx)
         return self
+
+    def get_optimal_path(self, X0=None, n_steps=None):
+        """:1487-1530 on the GPU for a batch X0 [batch, 7] = (w1 w2 w3 q1 q2 q3 q4) (default obj.defaultX0):
+        the 6-D 'nearest' policy of run(), first-order ('taylor') plant step.  Returns X [batch, n_steps+1, 7]
+        and the applied torques U [batch, n_steps, 3]."""
+        from ._lib import rollout_attitude6
+        if getattr(self, "_dense6", None) is None:
+            raise RuntimeError("run(obj) must complete before get_optimal_path")
+        T, idx = self._dense6
+        X0 = self.defaultX0_ode45[None] if X0 is None else np.asarray(X0, dtype=np.float64).reshape(-1, 7)
+        n_steps = T.N - 1 if n_steps is None else int(n_steps)
+        return rollout_attitude6(T, idx, (self.J1, self.J2, self.J3), self.h, n_steps, X0, device=self.device)
 
     def _axis_descs(self):
         self.N_stage = int(np.ceil(self.T_final / self.h))

@@ -1088,3 +1088,56 @@ int oracle_dense6_run(const int32_t *n, int nu, const double *const *grid, const
     for (int k = 0; k < 6; ++k) free(g[k].rinv);
     return 0;
 }
+
+/* Solver_attitude.get_optimal_path (attitude-control/Solver_attitude.m:1487-1530), the consumer of the
+ * 6-D policy: per step  [yaw, pitch, roll] = quat2angle([X7 X6 X5 X4])  (Aerospace Toolbox, 'ZYX', the
+ * quaternion normalised first),  U_k = FU_k(w1, w2, w3, yaw, pitch, roll)  with 'nearest' interpolants over
+ * U{1,2,3}_Opt,  X_next = next_stage_states(X, U, h, 'taylor')  (:1339-1371: X + h*f(X, U) with
+ * spacecraft_dynamics_list :1199-1245, then the quaternion renormalised).
+ * idx [S] holds c = (u1*nu + u2)*nu + u3 per grid node; x0 [7][batch]; X_out [7][n_steps+1][batch];
+ * U_out [3][n_steps][batch]; Jd = {J1, J2, J3}. */
+int oracle_rollout_attitude6(const int32_t *n, int nu, const double *const *grid, const int32_t *idx,
+                             const double *u_values, const double *Jd, double h, int n_steps, const double *x0,
+                             int batch, double *X_out, double *U_out)
+{
+    dimtab g[6];
+    int64_t stride[6], S = 1;
+    for (int k = 0; k < 6; ++k) { dimtab_init(&g[k], grid[k], n[k], BELLMAN_LOCATE_SEARCH); stride[k] = S; S *= n[k]; }
+    const double J1 = Jd[0], J2 = Jd[1], J3 = Jd[2];
+#pragma omp parallel for schedule(dynamic)
+    for (int b = 0; b < batch; ++b) {
+        double X[7];
+        for (int k = 0; k < 7; ++k) X[k] = x0[(size_t)b * 7 + k];
+        double *Xo = X_out + (size_t)b * 7 * (n_steps + 1), *Uo = U_out + (size_t)b * 3 * n_steps;
+        memcpy(Xo, X, sizeof(X));
+        for (int ks = 0; ks < n_steps; ++ks) {
+            /* quat2angle([X7 X6 X5 X4]): q0 = X7 (scalar), q1 = X6, q2 = X5, q3 = X4 */
+            const double qm = sqrt(((X[6] * X[6] + X[5] * X[5]) + X[4] * X[4]) + X[3] * X[3]);
+            const double q0 = X[6] / qm, q1 = X[5] / qm, q2 = X[4] / qm, q3 = X[3] / qm;
+            const double yaw = atan2(2 * (q1 * q2 + q0 * q3), ((q0 * q0 + q1 * q1) - q2 * q2) - q3 * q3);
+            const double pitch = asin(-2 * (q1 * q3 - q0 * q2));
+            const double roll = atan2(2 * (q2 * q3 + q0 * q1), ((q0 * q0 - q1 * q1) - q2 * q2) + q3 * q3);
+            const double xq[6] = {X[0], X[1], X[2], yaw, pitch, roll};
+            int64_t o = 0;
+            for (int k = 0; k < 6; ++k) o += nearest_node(&g[k], xq[k]) * stride[k];
+            const int c = idx[o];
+            const double U[3] = {u_values[c / (nu * nu)], u_values[(c / nu) % nu], u_values[c % nu]};
+            for (int k = 0; k < 3; ++k) Uo[(size_t)ks * 3 + k] = U[k];
+            const double x1 = X[0], x2 = X[1], x3 = X[2], x4 = X[3], x5 = X[4], x6 = X[5], x7 = X[6];
+            double d[7];
+            d[0] = (J2 - J3) / J1 * x2 * x3 + U[0] / J1;
+            d[1] = (J3 - J1) / J2 * x3 * x1 + U[1] / J2;
+            d[2] = (J1 - J2) / J3 * x1 * x2 + U[2] / J3;
+            d[3] = 0.5 * ((x3 * x5 - x2 * x6) + x1 * x7);
+            d[4] = 0.5 * ((-x3 * x4 + x1 * x6) + x2 * x7);
+            d[5] = 0.5 * ((x2 * x4 - x1 * x5) + x3 * x7);
+            d[6] = 0.5 * ((-x1 * x4 - x2 * x5) - x3 * x6);
+            for (int k = 0; k < 7; ++k) X[k] = X[k] + h * d[k];
+            const double qs = sqrt(((X[3] * X[3] + X[4] * X[4]) + X[5] * X[5]) + X[6] * X[6]);
+            for (int k = 3; k < 7; ++k) X[k] = X[k] / qs;
+            memcpy(Xo + (size_t)(ks + 1) * 7, X, sizeof(X));
+        }
+    }
+    for (int k = 0; k < 6; ++k) free(g[k].rinv);
+    return 0;
+}

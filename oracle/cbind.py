@@ -345,3 +345,24 @@ def dense6_run(T, n_stages, J_N=None):
                                  J.ctypes.data_as(_dp), idx.ctypes.data_as(C.POINTER(C.c_int32)))
     assert rc == 0
     return J, idx
+
+
+def rollout_attitude6(T, idx, Jd, h, n_steps, x0):
+    """Solver_attitude.get_optimal_path (:1487-1530) under the 6-D policy idx [S] (c = (u1*nu + u2)*nu + u3).
+    x0 [batch, 7].  Returns X [batch, n_steps+1, 7], U [batch, n_steps, 3]."""
+    P6 = _dp * 6
+    keep = [_arr(g) for g in T.grid]
+    grid = P6(*[a.ctypes.data_as(_dp) for a in keep])
+    n = np.asarray(T.n, dtype=np.int32)
+    ia = np.ascontiguousarray(idx, dtype=np.int32).ravel()
+    uv, jd = _arr(T.U_vector), _arr(Jd)
+    x0 = _arr(x0).reshape(-1, 7)
+    batch = len(x0)
+    X = np.zeros((batch, n_steps + 1, 7))
+    U = np.zeros((batch, n_steps, 3))
+    ip = C.POINTER(C.c_int32)
+    rc = lib().oracle_rollout_attitude6(n.ctypes.data_as(ip), C.c_int(T.nu), grid, ia.ctypes.data_as(ip), uv.ctypes.data_as(_dp),
+                                        jd.ctypes.data_as(_dp), C.c_double(h), C.c_int(n_steps), x0.ctypes.data_as(_dp),
+                                        C.c_int(batch), X.ctypes.data_as(_dp), U.ctypes.data_as(_dp))
+    assert rc == 0
+    return X, U

@@ -453,3 +453,31 @@ class SolverAttitude6Literal:
         U3s = np.take_along_axis(np.take_along_axis(U3, (U1 - 1)[..., None, None], axis=-2)[..., 0, :],
                                  (U2s - 1)[..., None], axis=-1)[..., 0]
         return F_values, U1, U2s, U3s
+
+
+def attitude6_get_optimal_path_literal(grids, U_opt_values, J123, h, X0, n_steps):
+    """Solver_attitude.get_optimal_path (:1487-1530) with method 'nearest': U_opt_values = the three
+    U{1,2,3}_Opt value arrays (grid shaped).  quat2angle = Aerospace Toolbox, 'ZYX', input normalised."""
+    J1, J2, J3 = J123
+    FU = [GriddedInterpolantNearest(grids, np.asarray(v)) for v in U_opt_values]
+    X = np.zeros((7, n_steps + 1))
+    U = np.zeros((3, n_steps))
+    X[:, 0] = X0
+    for k in range(n_steps):
+        q = np.array([X[6, k], X[5, k], X[4, k], X[3, k]])
+        q = q / np.sqrt(np.sum(q ** 2))                                     # quatnormalize
+        yaw = np.arctan2(2 * (q[1] * q[2] + q[0] * q[3]), q[0] ** 2 + q[1] ** 2 - q[2] ** 2 - q[3] ** 2)
+        pitch = np.arcsin(-2 * (q[1] * q[3] - q[0] * q[2]))
+        roll = np.arctan2(2 * (q[2] * q[3] + q[0] * q[1]), q[0] ** 2 - q[1] ** 2 - q[2] ** 2 + q[3] ** 2)
+        for a in range(3):
+            U[a, k] = FU[a](X[0, k], X[1, k], X[2, k], yaw, pitch, roll)
+        x1, x2, x3, x4, x5, x6, x7 = X[:, k]
+        u1, u2, u3 = U[:, k]
+        Xd = np.array([(J2 - J3) / J1 * x2 * x3 + u1 / J1, (J3 - J1) / J2 * x3 * x1 + u2 / J2,     # :1199-1245
+                       (J1 - J2) / J3 * x1 * x2 + u3 / J3,
+                       0.5 * (x3 * x5 - x2 * x6 + x1 * x7), 0.5 * (-x3 * x4 + x1 * x6 + x2 * x7),
+                       0.5 * (x2 * x4 - x1 * x5 + x3 * x7), 0.5 * (-x1 * x4 - x2 * x5 - x3 * x6)])
+        X2 = X[:, k] + h * Xd                                                # 'taylor' :1366-1367
+        X2[3:7] = X2[3:7] / np.sqrt(X2[3] ** 2 + X2[4] ** 2 + X2[5] ** 2 + X2[6] ** 2)
+        X[:, k + 1] = X2
+    return X, U

@@ -55,3 +55,28 @@ def test_dense6_oracle_rough_terminal_cost(bellman, oracle_lib):
     np.testing.assert_allclose(J, Fl, rtol=0, atol=1e-12)
     bad = idx != c
     assert bad.mean() < 0.01                            # (1-t)*a + t*b vs fma(t, b-a, a): only near-ties may flip
+
+
+def test_attitude6_rollout_oracle_vs_literal(bellman, oracle_lib):
+    """Solver_attitude.get_optimal_path (:1487-1530): the C restatement against the line-by-line numpy
+    restatement (quat2angle, three 6-D 'nearest' interpolants, 'taylor' step) under a swept 6-D policy."""
+    from oracle.matlab_literal import attitude6_get_optimal_path_literal
+    L, sa, T = _literal_and_tables(bellman, 8, 5, 40)
+    J, idx = oracle_lib.dense6_run(T, 30)
+    rng = np.random.default_rng(0)
+    x0 = np.zeros((4, 7))
+    x0[:, 0:3] = rng.uniform(-0.6, 0.6, (4, 3))
+    x0[:, 3:6] = rng.uniform(-0.15, 0.15, (4, 3))
+    x0[:, 6] = np.sqrt(1 - np.sum(x0[:, 3:6] ** 2, axis=1))
+    x0[0] = sa.defaultX0_ode45
+    X, U = oracle_lib.rollout_attitude6(T, idx, (sa.J1, sa.J2, sa.J3), sa.h, 120, x0)
+    shape = tuple(T.n)
+    vals = [T.U_vector[k].reshape(shape, order="F") for k in (idx // 9, (idx // 3) % 3, idx % 3)]
+    seen = set()
+    for b in range(4):
+        Xl, Ul = attitude6_get_optimal_path_literal(T.grid, vals, (sa.J1, sa.J2, sa.J3), sa.h, x0[b], 120)
+        assert np.array_equal(U[b], Ul.T)
+        np.testing.assert_allclose(X[b], Xl.T, rtol=0, atol=1e-13)
+        seen |= set(np.unique(U[b]))
+    assert seen == {-0.11, 0.0, 0.11}
+    np.testing.assert_allclose(np.linalg.norm(X[:, -1, 3:7], axis=1), 1.0, atol=1e-14)    # renormalised every step

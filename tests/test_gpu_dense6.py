@@ -54,3 +54,27 @@ def test_dense6_facade_run_and_errors(bellman, oracle_lib):
     T.nu = 9
     with pytest.raises(bellman.BellmanError):
         bellman.dense6_run(T, 1)
+
+
+def test_attitude6_rollout_matches_oracle(bellman, oracle_lib):
+    """run() then get_optimal_path() (Solver_attitude.m:1487-1530) for 200 initial states: identical torque
+    sequences, states within 1e-10 of the C restatement (atan2 / asin are CUDA's on the GPU)."""
+    sa = _solver(bellman, 12, 6, 60)
+    sa.run(n_stages=40)
+    T, idx = sa._dense6
+    rng = np.random.default_rng(3)
+    x0 = np.zeros((200, 7))
+    x0[:, 0:3] = rng.uniform(-0.7, 0.7, (200, 3))
+    x0[:, 3:6] = rng.uniform(-0.15, 0.15, (200, 3))
+    x0[:, 6] = np.sqrt(1 - np.sum(x0[:, 3:6] ** 2, axis=1))
+    x0[0] = sa.defaultX0_ode45
+    Xg, Ug = sa.get_optimal_path(x0, n_steps=300)
+    Xo, Uo = oracle_lib.rollout_attitude6(T, idx, (sa.J1, sa.J2, sa.J3), sa.h, 300, x0)
+    same = np.all(Ug == Uo, axis=(1, 2))
+    assert same.mean() >= 0.95, "torque sequences differ on %d of %d trajectories" % ((~same).sum(), len(same))
+    np.testing.assert_allclose(Xg[same], Xo[same], rtol=0, atol=1e-10)
+    assert len(np.unique(Uo)) == 3
+    X1, U1 = sa.get_optimal_path(n_steps=10)                           # default X0
+    assert X1.shape == (1, 11, 7) and U1.shape == (1, 10, 3) and np.array_equal(X1[0], Xg[0, :11])
+    with pytest.raises(RuntimeError):
+        _solver(bellman, 6, 4, 10).get_optimal_path()
