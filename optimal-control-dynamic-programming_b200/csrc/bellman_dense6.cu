@@ -90,7 +90,8 @@ template <int MU, class T> __device__ __forceinline__ T pick(const T (&a)[MU], i
 
 // NU > 0: compile-time control count (unrolled U3 loop); NU = 0: run-time p.nu <= D6_MAXU.
 // (32-bit element offsets with the eight angle-corner offsets precomputed per state were measured: 5.4 ms
-// against 5.1 ms on the 24^3 x 10^3 mesh — no gain, the kernel waits on L1 / L2 latency, not on address arithmetic.)
+// against 5.1 ms on the 24^3 x 10^3 mesh — no gain, the kernel waits on L1 / L2 latency, not on address arithmetic;
+// 5 CTAs per SM at 96 registers (__launch_bounds__(128, 5), 20 instead of 16 warps): 5.6 ms — the few spills cost more.)
 template <int NU>
 __global__ void __launch_bounds__(D6_BLOCK) k_stage_dense6(const __grid_constant__ Dense6Params p) {
     // a CTA is an 8 x 4 x 4 tile of (w1, w2, w3) at one angle triple (blockIdx.y = yaw + n3*pitch, blockIdx.z =
