@@ -381,6 +381,11 @@ extern "C" int bellman_set_stage(bellman_handle *h, int32_t stage, const double 
         h->err = "bellman_set_stage: stage must be in 1..N (and the terminal stage N has no policy)";
         return BELLMAN_ERR_BAD_ARG;
     }
+    if (idx_host && hp.idx_bytes == 4) {      // (narrower storage checks the range while narrowing, below)
+        const size_t ne = h->slot_elems_idx();
+        for (size_t k = 0; k < ne; ++k)       // the consumers index u_values / thruster tables with these
+            if (idx_host[k] < 0 || idx_host[k] >= hp.C) { h->err = "bellman_set_stage: control index out of range"; return BELLMAN_ERR_BAD_ARG; }
+    }
     h->cur_stage = stage;
     h->check_log.clear();
     int rc = upload_J(h, stage, J_host);

@@ -499,6 +499,11 @@ def test_set_stage_resume_and_errors(bellman, oracle_lib):
         assert np.array_equal(b.get_J(), Jend) and np.array_equal(b.get_idx(), iend)
         with pytest.raises(bellman.BellmanError):
             b.set_stage(d.N, None, np.zeros(d.S, dtype=np.int32))
+        bad = np.zeros(d.S, dtype=np.int32)
+        bad[7] = d.C                                                    # one index past the control grid
+        with pytest.raises(bellman.BellmanError):
+            b.set_stage(3, None, bad)
+        assert b.current_stage == 6                                     # a refused call leaves the handle as it was
 
 
 @pytest.mark.gpu
