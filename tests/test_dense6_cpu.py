@@ -80,3 +80,22 @@ def test_attitude6_rollout_oracle_vs_literal(bellman, oracle_lib):
         seen |= set(np.unique(U[b]))
     assert seen == {-0.11, 0.0, 0.11}
     np.testing.assert_allclose(np.linalg.norm(X[:, -1, 3:7], axis=1), 1.0, atol=1e-14)    # renormalised every step
+
+
+@pytest.mark.parametrize("U", [[0.0, 0.3], [-0.2, -0.05, 0.05, 0.2]])
+def test_dense6_oracle_vs_literal_other_control_counts(bellman, oracle_lib, U):
+    """nu = 2 and 4 torque levels (the reference fixes nu = 3): the flat argmin c = (u1*nu + u2)*nu + u3 of
+    the C restatement against the three nested min calls of the literal."""
+    from oracle.matlab_literal import SolverAttitude6Literal
+    L = SolverAttitude6Literal(n_mesh_w=4, n_mesh_q=3, N_stage=6, U_vector=np.array(U))
+    sa = bellman.Solver_attitude()
+    sa.n_mesh_w, sa.n_mesh_q, sa.U_vector = 4, 3, np.array(U)
+    sa.T_final = 6 * sa.h
+    T = sa.dense6_tables()
+    JN = np.random.default_rng(2).normal(size=T.S)
+    F, U1, U2, U3 = L.run(n_stages=3, J_N=JN)
+    J, idx = oracle_lib.dense6_run(T, 3, J_N=JN)
+    nu = len(U)
+    c = (((U1 - 1) * nu + (U2 - 1)) * nu + (U3 - 1)).ravel(order="F")
+    np.testing.assert_allclose(J, F.ravel(order="F"), rtol=0, atol=1e-12)
+    assert (idx != c).mean() < 0.01 and idx.max() < nu ** 3
