@@ -734,8 +734,13 @@ def main():
                 "bytes_per_launch": 3 * 16000 * 4800 * 20, "traffic": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][0],
                 "traffic_source": NCU_TRAFFIC["attitude_x16_3x16000x4800x3"][1]}
         others["rollout_64x64_x0"] = rollout_rate(bb, local)
-        others["pos_att_plant_rollout_4096_x0"] = plant_rollout_rate(bb, local)
-        others["attitude6_24x24x24x10x10x10x27"] = dense6_rate(bb, local)
+        # the two "next" rows of SURVEY 8f are reported beside the headline, never instead of it: a failure
+        # here is recorded in the line and must not take the main measurement down with it
+        for name, fn in (("pos_att_plant_rollout_4096_x0", plant_rollout_rate), ("attitude6_24x24x24x10x10x10x27", dense6_rate)):
+            try:
+                others[name] = fn(bb, local)
+            except Exception as e:      # noqa: BLE001
+                others[name] = {"error": "%s: %s" % (type(e).__name__, e)}
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
