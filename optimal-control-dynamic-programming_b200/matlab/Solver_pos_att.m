@@ -201,7 +201,7 @@ classdef Solver_pos_att < handle
                 d.r = zeros(nC, 1);  d.store_J_all = 0;  d.store_idx_all = 0;  d.device = obj.device;
                 hs(c) = bellman_mex('create', d);
                 bellman_mex('set_stage', hs(c), 1, [], double(C.U_Optimal_id(:)));
-                fv{c} = [C.f0_allcomb(:) C.f1_allcomb(:) C.f6_allcomb(:) C.f7_allcomb(:)].';
+                fv{c} = [C.f0_allcomb(:) C.f1_allcomb(:) C.f6_allcomb(:) C.f7_allcomb(:)];   % C_ch x 4: column m = thruster m of the channel
             end
             N = obj.N_stage;
             o = struct('n_steps', N - 1, 'stride_out', 1, 'mu', mu, 'R0', R0, 'V0', V0, 'h', obj.h, ...

@@ -20,7 +20,7 @@
 //                                                     X: 6 x ((n_steps/stride_out+1)*batch), id (1-based): 3 x (n_out*batch)
 //   [X,F,FM,w] = bellman_mex('rollout_pos_att', [hx hy hz], stages, o, fx, fy, fz, Y0)   Solver_pos_att.get_optimal_path:
 //                                                     o: struct n_steps, stride_out, mu, R0, V0, h, rtol, atol, InertiaM (3x3),
-//                                                     Mass, T_dist; f*: 4 x C_ch thruster levels; Y0: 13 x batch;
+//                                                     Mass, T_dist; f*: C_ch x 4 thruster levels (columns f0 f1 f6 f7 of the channel); Y0: 13 x batch;
 //                                                     X: 13 x ((n_out+1)*batch), F: 12 x (n_out*batch), FM: 6 x (n_out*batch)
 //   [X,id,w] = bellman_mex('rollout_attitude', h, stage, o, u_values, Y0)   Solver_attitude.get_optimal_path_simplified_testode45:
 //                                                     o: struct n_steps, stride_out, h, rtol, atol, InertiaM; Y0: 7 x batch
@@ -322,7 +322,7 @@ void mexFunction(int nlhs, mxArray *plhs[], int nrhs, const mxArray *prhs[]) {
             hs[k] = reinterpret_cast<bellman_handle *>(static_cast<uint64_t *>(mxGetData(prhs[1]))[k]);
             if (!g_live.count(hs[k])) mexErrMsgIdAndTxt("bellman:BAD_ARG", "stale or foreign handle");
             stage[k] = (int32_t)st[k];
-            fv[k] = need_doubles(prhs[4 + k], 4 * (size_t)shape_of(hs[k]).C, "f_x / f_y / f_z (4-by-C of the channel)");
+            fv[k] = need_doubles(prhs[4 + k], 4 * (size_t)shape_of(hs[k]).C, "f_x / f_y / f_z (C-by-4 of the channel)");
         }
         bellman_plant_opts o;
         plant_opts_from(prhs[3], o);
