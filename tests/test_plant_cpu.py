@@ -110,3 +110,18 @@ def test_attitude_plant_oracle_vs_literal(bellman, oracle_lib):
         Xl, Ul = lit.run(y0[b], n_steps)
         assert np.array_equal(sa.U_vector[Cc[b]], Ul)
         np.testing.assert_allclose(X[b], Xl, rtol=0, atol=1e-12)
+
+
+def test_pos_att_facade_constants_match_the_restatements(bellman, oracle_lib):
+    """Host-side pieces of Solver_pos_att.get_optimal_path that need no GPU: the target orbit
+    (get_target_R0V0, :759-777) and the default initial state (:458-468)."""
+    from oracle import plant_literal as pl
+    sp = bellman.Solver_pos_att()
+    R0, V0 = sp.get_target_R0V0()
+    Ro, Vo = oracle_lib.target_R0V0()
+    np.testing.assert_allclose(R0, Ro, rtol=1e-15)
+    np.testing.assert_allclose(V0, Vo, rtol=1e-15)
+    np.testing.assert_allclose(sp.default_X0(), pl.default_X0_pos_att(), rtol=0, atol=1e-17)
+    assert abs(np.linalg.norm(sp.default_X0()[6:10]) - 1) < 1e-15
+    with pytest.raises(KeyError):
+        sp.get_optimal_path(n_steps=4)                     # no controller installed yet (set_controller)
