@@ -442,6 +442,18 @@ def dense6_run(T, n_stages, J_N=None, device=-1):
     with idx = (u1*nu + u2)*nu + u3, device milliseconds of the stage loop)."""
     lib = load()
     keep = [_f64(g) for g in T.grid] + [_f64(w) for w in T.w_next] + [_f64(a) for a in T.a_next] + [_f64(x) for x in T.r]
+    S, S3 = int(np.prod(T.n)), int(np.prod(T.n[:3]))
+    # the C ABI takes bare pointers: check every extent here so a malformed table cannot be read past its end
+    if not 1 <= int(T.nu) <= 8:
+        raise BellmanError(-1, "nu must be in 1..8")
+    for k in range(6):
+        if keep[k].size != T.n[k]:
+            raise BellmanError(-1, "grid[%d] has %d points, n says %d" % (k, keep[k].size, T.n[k]))
+    for k in range(3):
+        if keep[6 + k].size != T.nu * S3 or keep[9 + k].size != S or keep[12 + k].size != T.nu:
+            raise BellmanError(-1, "w_next / a_next / r of control %d do not match n and nu" % k)
+    if np.size(T.gs) != S or (J_N is not None and np.size(J_N) != S):
+        raise BellmanError(-1, "gs / J_N must have one entry per state")
     cd = CDense6()
     cd.struct_size, cd.nu, cd.device = C.sizeof(CDense6), int(T.nu), int(device)
     for k in range(6):
@@ -476,6 +488,8 @@ def rollout_attitude6(T, idx, J123, h, n_steps, x0, device=-1):
         cd.grid[k] = keep[k].ctypes.data_as(_dp)
     ia = np.ascontiguousarray(idx, dtype=np.int32).ravel()
     uv, jd = _f64(T.U_vector), _f64(J123)
+    if ia.size != int(np.prod(T.n)) or uv.size != T.nu or jd.size != 3 or any(keep[k].size != T.n[k] for k in range(6)):
+        raise BellmanError(-1, "idx / u_values / J123 / grid do not match n and nu")
     x0 = _f64(x0).reshape(-1, 7)
     batch = len(x0)
     X = np.empty((batch, int(n_steps) + 1, 7))
