@@ -528,6 +528,9 @@ def rollout_pos_att(sweeps, f_values, y0, n_steps, h_step, R0, V0, InertiaM, Mas
     W = np.empty(batch, dtype=np.int32)
     o = _plant_opts(n_steps, stride_out, h_step, InertiaM, mu, R0, V0, rtol, atol, Mass, T_dist)
     fv = [_f64(f).reshape(4, -1) for f in f_values]
+    for sw, f in zip(sweeps, fv):
+        if f.shape[1] != int(sw.desc.C):
+            raise BellmanError(-1, "f_values must be [4, C] with C = %d combinations of the channel, got %s" % (sw.desc.C, f.shape))
     st = (C.c_int32 * 3)(*[int(s) for s in stages])
     sweeps[0]._check(lib.bellman_rollout_pos_att(sweeps[0].h, sweeps[1].h, sweeps[2].h, st, C.byref(o),
                                                  fv[0].ctypes.data_as(_dp), fv[1].ctypes.data_as(_dp), fv[2].ctypes.data_as(_dp),
